@@ -50,7 +50,7 @@ _OUTPUT_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
 
 
 def lib(backend: str = "det") -> C.CDLL:
-    if backend not in ("det", "libm"):
+    if backend not in ("det", "libm", "det_shebagold", "libm_shebagold"):
         raise ValueError(backend)
     if backend in _LIBS:
         return _LIBS[backend]

@@ -640,7 +640,11 @@ static void snow_precip(real* m_snow, real* H_abs_snow, real* thick_snow, real d
   *m_snow = *m_snow + dt * rho_l * (liquid_precip + solid_precip);
   *thick_snow = *thick_snow + d_thick;
   *H_abs_snow = *H_abs_snow + dt * T2m * liquid_precip * rho_l * c_l;
+#ifdef SAM_VARIANT_SNOW_T2M /* hypothesis test only: "replaced with T2m" without the min(.,-1) */
+  *H_abs_snow = *H_abs_snow + dt * T2m * solid_precip * rho_l * c_s;
+#else
   *H_abs_snow = *H_abs_snow + dt * r_min(T2m, -1.0) * solid_precip * rho_l * c_s;
+#endif
   *H_abs_snow = *H_abs_snow - dt * solid_precip * rho_l * latent_heat;
 }
 

@@ -1,0 +1,1159 @@
+// physics.cuh -- per-column device physics of the SAMSIM timestep for sm_100a.
+//
+// One thread owns one column.  Per-layer arrays live in an SoA, layer-major device buffer
+// (element k of column c of array a is arr[(a*LS + k)*ncol_pad + c]) so that the 32 columns of
+// a warp touch 32 consecutive doubles for every per-layer access.  Per-column scalars are
+// loaded into the Col struct (registers / local memory) for the duration of a launch.
+//
+// Arithmetic contract: this file is compiled with -fmad=false; every expression keeps the
+// reference's left-to-right operation order, the transcendental calls go through detmath.h,
+// and x**2._wp / x**3._wp / x**4._wp are products.  Under that contract the results are
+// bit-identical with the CPU oracle's "det" build (tests/test_parity_*.py).
+//
+// Each function cites the reference routine it replaces (paths relative to /root/reference).
+#pragma once
+
+#include <stdint.h>
+
+#include "detmath.h"
+#include "params.cuh"
+
+namespace samsim {
+
+// ---- run-wide configuration in constant memory -------------------------------------------
+struct DevCfg {
+  int testcase;
+  int Nlayer, N_top, N_middle, N_bottom;
+  int atmoflux_flag, grav_flag, prescribe_flag, grav_heat_flag, flush_heat_flag, turb_flag, salt_flag,
+      boundflux_flag, flush_flag, flood_flag, bottom_flag, precip_flag, harmonic_flag, tank_flag, albedo_flag,
+      lab_snow_flag, freeboard_snow_flag, snow_flush_flag, snow_precip_flag;
+  int i_time_out;
+  double dt, thick_0, thick_min, time_out;
+  double alpha_flux_instable, alpha_flux_stable, m_total;
+  double max_flux_plate, k_snow_flush, k_styropor;
+  // liquidus coefficients for salt_flag
+  double c2, c3, c4, d2, d3x2, d4x3;
+};
+
+// scalar slots: MUST stay in the order of samsim_scalar_id (include/samsim_b200.h)
+enum {
+  SC_T_BOTTOM = 0, SC_T_TOP, SC_S_BU_BOTTOM, SC_T2M, SC_FL_Q_BOTTOM,
+  SC_PSI_S_SNOW, SC_PSI_L_SNOW, SC_PSI_G_SNOW, SC_PHI_S, SC_S_ABS_SNOW, SC_H_ABS_SNOW, SC_M_SNOW, SC_T_SNOW,
+  SC_THICK_SNOW, SC_LIQUID_PRECIP, SC_SOLID_PRECIP, SC_FL_Q_SNOW,
+  SC_ENERGY_STORED, SC_TOTAL_RESIST, SC_FRESHWATER, SC_THICKNESS, SC_BULK_SALIN,
+  SC_ALBEDO, SC_FL_SW, SC_FL_LW, SC_FL_REST,
+  SC_GRAV_DRAIN, SC_GRAV_SALT, SC_GRAV_TEMP,
+  SC_MELT_THICK, SC_MELT_THICK_SNOW, SC_MELT_THICK_SNOW_OLD,
+  SC_MTO1, SC_MTO2, SC_MTO3,
+  SC_FREEBOARD, SC_T_FREEZE, SC_MELT_ERR, SC_S_TOTAL,
+  SC_TTOP_WARM, SC_TTOP_COLD, SC_OFLUX_AMP,
+  SC_COUNT
+};
+// array slots: first ARR_STATE_COUNT in the order of samsim_array_id, then launch-local scratch
+enum {
+  AR_M = 0, AR_S_ABS, AR_H_ABS, AR_THICK, AR_T, AR_PHI, AR_S_BU, AR_PSI_S, AR_PSI_L, AR_PSI_G, AR_RAY, AR_PERM,
+  AR_FLUSH_V, AR_FLUSH_H, AR_FL_Q,
+  AR_STATE_COUNT,
+  AR_S_BR = AR_STATE_COUNT, AR_V_EX, AR_FL_M, AR_W0, AR_W1, AR_W2, AR_W3,
+  AR_COUNT
+};
+enum { IN_N_ACTIVE = 0, IN_STATUS, IN_STYROPOR, IN_COUNT };
+
+// strided per-layer view of one column (1-based layer index like the reference)
+struct Lay {
+  double* p;
+  size_t ls;
+  __device__ __forceinline__ double& operator[](int k) const { return p[(size_t)k * ls]; }
+};
+
+// everything one thread needs
+struct Col {
+  Lay m, S_abs, H_abs, thick, T, phi, S_bu, psi_s, psi_l, psi_g, ray, perm, flush_v, flush_h, fl_Q;
+  Lay S_br, V_ex, fl_m, w0, w1, w2, w3;
+  int N_active, status, styropor_flag;
+  double sc[SC_COUNT];
+  // clock (shared by the batch, advanced in lock step)
+  double time;
+  long long i;
+  int n_time_out, time_counter;
+  // forcing of this column for the current step (filled by the kernel's S1)
+  double fsw0, fsw1, flw0, flw1;  // records time_counter-1 and time_counter, scaled
+  double ftime0, ftime1;
+};
+
+#define SCV(c, id) ((c).sc[id])
+
+__device__ __forceinline__ double f_max(double a, double b) { return (a > b) ? a : b; }  // Fortran MAX
+__device__ __forceinline__ double f_min(double a, double b) { return (a < b) ? a : b; }  // Fortran MIN
+__device__ __forceinline__ double f_sign(double a, double b) {                           // Fortran SIGN(a,b)
+  return (dm_bits(b) < 0) ? -fabs(a) : fabs(a);
+}
+__device__ __forceinline__ double P2(double x) { return x * x; }
+__device__ __forceinline__ double P3(double x) { return (x * x) * x; }
+__device__ __forceinline__ double P4(double x) { double x2 = x * x; return x2 * x2; }
+
+// ==========================================================================================
+// mo_thermo_functions.f90
+// ==========================================================================================
+
+// func_S_br(T), mo_thermo_functions.f90:308-351 (c1 = 0 is added first, as in the source)
+__device__ __forceinline__ double S_br_of(const DevCfg& g, double T) {
+  return 0.0 + g.c2 * T + g.c3 * P2(T) + g.c4 * P3(T);
+}
+// func_S_br(T,S_bu): clamp to >= S_bu, :353-357
+__device__ __forceinline__ double S_br_of(const DevCfg& g, double T, double S_bu) {
+  double s = S_br_of(g, T);
+  return (s < S_bu) ? S_bu : s;
+}
+// func_ddT_S_br, :380-414
+__device__ __forceinline__ double ddT_S_br_of(const DevCfg& g, double T) {
+  const double T_crit = -20.0;
+  double d = g.d2 + g.d3x2 * T + g.d4x3 * P2(T);
+  if (T < T_crit) d = g.d2 + g.d3x2 * T_crit + g.d4x3 * P2(T_crit);
+  return d;
+}
+
+// getT, mo_thermo_functions.f90:62-143: Newton for the freezing point, then Newton for T.
+// `phi` keeps its incoming value when no branch assigns it (cannot happen for finite input).
+__device__ __noinline__ void getT(const DevCfg& g, double H, double S_bu, double T_in, double& T_out, double& phi,
+                                  int& status) {
+  double T = H / c_l;
+  if (S_br_of(g, T, S_bu) > S_bu && S_bu > 0.001) {
+    double T_fr = -1.0, T_0, f, ddT_f;
+    while (fabs(S_br_of(g, T_fr) / S_bu - 1.0) > SAMSIM_F32(0.0001)) {  // :87
+      T_0 = T_fr;
+      f = S_br_of(g, T_0) - S_bu;
+      ddT_f = ddT_S_br_of(g, T_0);
+      T_fr = T_0 - f / ddT_f;
+    }
+    T_0 = T_in;
+    {
+      double sb = S_br_of(g, T_0);
+      f = -latent_heat - H + latent_heat * S_bu / f_max(sb, 0.000000001) + c_s * T_0 + c_s_beta * T_0 * T_0 / 2.0;  // :95
+      ddT_f = c_s + c_s_beta * T_0 - latent_heat * S_bu * ddT_S_br_of(g, T_0) / f_max(P2(sb), 0.0000000001);      // :96
+    }
+    T = T_0 - f / ddT_f;
+    int it = 0;
+    while (fabs(f) > 1.0) {  // :99
+      T_0 = T;
+      if (T_0 > 0.0 || T_0 < -200.0) T_0 = T_fr;
+      double sb = S_br_of(g, T_0);
+      f = -latent_heat - H + latent_heat * S_bu / f_max(sb, 0.0000000001) + c_s * T_0 + c_s_beta * T_0 * T_0 / 2.0;  // :104
+      ddT_f = c_s + c_s_beta * T_0 - latent_heat * S_bu * ddT_S_br_of(g, T_0) / f_max(sb * sb, 0.0000000001);       // :105
+      T = T_0 - f / ddT_f;
+      it++;
+      if (it == 260) {  // :114-123 STOP 99
+        status = 99;
+        break;
+      }
+    }
+    phi = 1.0 - S_bu / S_br_of(g, T, S_bu);  // :125
+  } else if (S_bu < 0.001) {  // :127-137 salt-free
+    if (H > 0.0) {
+      phi = 0.0;
+      T = H / c_l;
+    } else if (H <= -latent_heat) {
+      phi = 1.0;
+      T = (H + latent_heat) / c_s;
+    } else if (H <= 0.0 && -latent_heat < H) {
+      T = 0.0;
+      phi = -H / latent_heat;
+    }
+  } else {
+    phi = 0.0;
+  }
+  T_out = T;
+}
+
+// Expulsion, mo_thermo_functions.f90:157-187
+__device__ __forceinline__ void expulsion(double phi, double thick, double m, double& psi_s, double& psi_l,
+                                          double& psi_g, double& V_ex) {
+  double V_s = m * phi / rho_s;
+  double V_l = m * (1.0 - phi) / rho_l;
+  if (V_s + V_l > thick) V_ex = V_l + V_s - thick; else V_ex = 0.0;
+  psi_s = V_s / thick;
+  psi_l = (V_l - V_ex) / thick;
+  psi_g = (thick - V_l - V_s + V_ex) / thick;
+  if (psi_l < 0.0) psi_l = 0.0;
+  if (psi_g < 0.0) psi_g = 0.0;
+}
+
+// sub_fl_Q, :201-224
+__device__ __forceinline__ double fl_Q_between(double ps1, double pl1, double pg1, double th1, double T1, double ps2,
+                                               double pl2, double pg2, double th2, double T2) {
+  double k1 = ps1 * k_s + pl1 * k_l + pg1 * 0.0;
+  double k2 = ps2 * k_s + pl2 * k_l + pg2 * 0.0;
+  double R = th1 / (2.0 * k1) + th2 / (2.0 * k2);
+  return (T2 - T1) / R;
+}
+// sub_fl_Q_0 with direct_flag = -1 (the only value any call site passes), :238-265
+__device__ __forceinline__ double fl_Q_0_top(double ps, double pl, double pg, double th, double T, double T_bound) {
+  double k = ps * k_s + pl * k_l + pg * 0.0;
+  double R = th / (2.0 * k);
+  return (T - T_bound) / R;
+}
+
+// ==========================================================================================
+// mo_functions.f90
+// ==========================================================================================
+
+// func_density, mo_functions.f90:51-62
+__device__ __forceinline__ double density_of(double T, double S) {
+  double density_0 = 999.842594 + 6.8 / 100.0 * T;
+  return density_0 + 0.825 * S + (-5.7 / 1000.0) * det_pow(f_max(S, 0.0), 1.5);
+}
+
+// func_T_freeze, :239-250
+__device__ __forceinline__ double T_freeze_of(double S_bu, int salt_flag) {
+  double Tf = 0.0;
+  if (salt_flag == 2) {
+    const double c2 = (double)9.37f;
+    const double c3 = (double)(5.33f * 1e-7f);
+    Tf = -0.0592 * S_bu - c2 * P2(S_bu) - c3 * P3(S_bu);
+  } else if (salt_flag == 1) {
+    const double a = (double)(1.710523f * 1e-3f);
+    const double b = (double)(2.154996f * 1e-4f);
+    Tf = -0.0575 * S_bu + a * det_pow(S_bu, 1.5) - b * P2(S_bu);
+  }
+  return Tf;
+}
+
+// func_albedo, :157-208
+__device__ __forceinline__ double albedo_of(double thick_snow, double T_snow, double psi_l, double thick_min,
+                                            int albedo_flag) {
+  const double ice_dry = SAMSIM_F32(0.75), ice_wet = SAMSIM_F32(0.6), snow_dry = SAMSIM_F32(0.85),
+               snow_wet = SAMSIM_F32(0.75), water = SAMSIM_F32(0.2);
+  double albedo;
+  if (thick_snow > thick_min) {
+    albedo = (T_snow < SAMSIM_F32(-0.01)) ? snow_dry : snow_wet;
+    albedo = ice_dry + (albedo - ice_dry) * f_min(1.0, thick_snow / 0.3);
+  } else {
+    if (psi_l > 0.9) albedo = water;
+    else if (psi_l > 0.6) albedo = ice_wet + (water - ice_wet) * ((psi_l - 0.6) / 0.3);
+    else if (psi_l > 0.2) albedo = ice_wet;
+    else albedo = ice_dry;
+  }
+  if (albedo_flag == 1) {
+    if (thick_snow > thick_min) albedo = (T_snow < SAMSIM_F32(-0.01)) ? snow_dry : snow_wet;
+    else albedo = (psi_l < SAMSIM_F32(0.8)) ? ice_dry : water;
+  }
+  return albedo;
+}
+
+// func_k_snow, mo_snow.f90:560-573
+__device__ __forceinline__ double k_snow_of(double m_snow, double thick_snow) {
+  const double c0 = 0.138, c1 = -1.01 / 1000.0, c2 = 3.233 / 1000000.0;
+  double r = m_snow / thick_snow;
+  double k = c0 + c1 * m_snow / thick_snow + c2 * P2(r);
+  return k + SAMSIM_F32(0.15);
+}
+
+// sub_notzflux, mo_functions.f90:270-289
+__device__ __forceinline__ void notzflux(double time, double& fl_sw, double& fl_rest) {
+  double day = time / 86400.0;
+  while (day > 360) day = day - 360;
+  fl_sw = 314.0 * det_exp(-0.5 * P2((day - 164.0) / SAMSIM_F32(47.9)));
+  fl_rest = 118.0 * det_exp(-0.5 * P2((day - 206.0) / SAMSIM_F32(53.1))) + 179.0;
+  if (day < 60. || day > 300.) fl_sw = 0.0;
+}
+
+// forward sums in the reference's order: SUM(a(i:j)) and SUM(a(i:j)*b(i:j))
+__device__ __forceinline__ double sum_fwd(const Lay& a, int i, int j) {
+  double s = 0.0;
+  for (int q = i; q <= j; q++) s = s + a[q];
+  return s;
+}
+__device__ __forceinline__ double sum_prod_fwd(const Lay& a, const Lay& b, int i, int j) {
+  double s = 0.0;
+  for (int q = i; q <= j; q++) s = s + a[q] * b[q];
+  return s;
+}
+
+// func_freeboard, mo_functions.f90:79-130
+__device__ __noinline__ double freeboard_of(const DevCfg& g, const Col& c) {
+  const int Na = c.N_active;
+  const double snowmass = (g.freeboard_snow_flag == 0) ? SCV(c, SC_M_SNOW) : 0.0;
+  double buoy = sum_prod_fwd(c.psi_s, c.thick, 1, Na) * (rho_l - rho_s) + sum_prod_fwd(c.psi_g, c.thick, 1, Na) * rho_l;
+  double freeboard;
+  if (snowmass > buoy) {  // :99-102 snow pushes the ice under water
+    freeboard = buoy - snowmass;
+    freeboard = freeboard / rho_l;
+  } else {
+    double test1 = 0.0, test2 = 1.0, msum = 0.0, msum_prev = 0.0;
+    int k = 0;
+    while (test1 < test2) {  // :114-118
+      k = k + 1;
+      test2 = sum_prod_fwd(c.psi_s, c.thick, k + 1, Na) * (rho_l - rho_s) + sum_prod_fwd(c.psi_g, c.thick, k + 1, Na) * rho_l;
+      msum_prev = msum;
+      msum = msum + c.m[k];  // SUM(m(1:k)) is a fixed-start prefix: incremental is the same order
+      test1 = msum + snowmass;
+    }
+    test1 = msum_prev + snowmass;  // :121 SUM(m(1:k-1))
+    const double mk = c.m[k], tk = c.thick[k];
+    freeboard = test2 - test1 + (rho_l - mk / tk) * tk;  // :124
+    freeboard = freeboard / rho_l;
+    freeboard = freeboard + sum_fwd(c.thick, 1, k - 1);
+  }
+  return freeboard;
+}
+
+// sub_melt_thick, mo_functions.f90:386-428
+__device__ __forceinline__ void melt_thick_of(double psi_l, double psi_s, double psi_g, double T, double T_freeze,
+                                              double T_top, double fl_Q, double thick_snow, double dt,
+                                              double& melt_thick, double& thick, double thick_min) {
+  melt_thick = 0.0;
+  if (thick_snow < thick_min && T_top >= T_freeze) {
+    melt_thick = -fl_Q - 2.0 * (psi_l * k_l + psi_s * k_s) / thick * (T_freeze - T);
+    melt_thick = melt_thick * dt / f_max((latent_heat * rho_s * psi_s), 0.000000000000001);
+    melt_thick = f_min(psi_l * thick, melt_thick);
+  }
+  if (psi_s < psi_s_top_min) melt_thick = thick * (1.0 - psi_s / psi_s_top_min);
+  if (melt_thick > 0.0 && psi_g > gas_snow_ice2) {
+    if (melt_thick > (psi_g - gas_snow_ice2) * thick) {
+      melt_thick = melt_thick - (psi_g - gas_snow_ice2) * thick;
+      thick = thick * (1.0 - (psi_g - gas_snow_ice2));
+    } else {
+      thick = thick - melt_thick;
+      melt_thick = 0.0;
+    }
+  }
+}
+
+// sub_melt_snow, mo_functions.f90:443-474
+__device__ __forceinline__ void melt_snow(double& melt_thick, double& thick, double& thick_snow, double& H_abs,
+                                          double& H_abs_snow, double& m, double& m_snow, double& psi_g_snow) {
+  double shift = 1.0 / f_max(psi_g_snow, 0.01) * melt_thick;
+  if (shift >= thick_snow) {
+    melt_thick = melt_thick - thick_snow * psi_g_snow;
+    H_abs = H_abs + H_abs_snow;
+    m = m + m_snow;
+    thick = thick + (1.0 - psi_g_snow) * thick_snow;
+    thick_snow = 0.0;
+    m_snow = 0.0;
+    H_abs_snow = 0.0;
+  } else {
+    H_abs = H_abs + shift / thick_snow * H_abs_snow;
+    H_abs_snow = H_abs_snow - shift / thick_snow * H_abs_snow;
+    m = m + shift / thick_snow * m_snow;
+    m_snow = m_snow - shift / thick_snow * m_snow;
+    thick = thick + shift - melt_thick;
+    thick_snow = thick_snow - shift;
+    melt_thick = 0.0;
+  }
+}
+
+// ==========================================================================================
+// mo_mass.f90
+// ==========================================================================================
+
+// mass_transfer, mo_mass.f90:53-96, as ONE in-place forward pass.  The reference copies T, S_bu and
+// S_abs into TT/SS_bu/SS_abs first; T and S_bu are not modified by the routine and SS_abs(k+1)
+// is read before layer k+1 is updated, so reading the live arrays is equivalent.  S_abs(k-1)
+// in the last branch IS the updated value in the reference too (:91).
+__device__ __noinline__ void mass_transfer(const DevCfg& g, Col& c, const Lay& fl_m) {
+  const int Na = c.N_active;
+  const double T_bottom = SCV(c, SC_T_BOTTOM), S_bu_bottom = SCV(c, SC_S_BU_BOTTOM);
+  double T_km1 = 0.0, Sbu_km1 = 0.0, Sabs_km1 = 0.0;  // k = 1: fl_m(1) == 0 at every call site, never read
+  double T_k = c.T[1], Sbu_k = c.S_bu[1];
+  double f0 = fl_m[1];
+  for (int k = 1; k <= Na; k++) {
+    double T_kp1, Sbu_kp1, Sabs_kp1;
+    if (k < Na) {
+      T_kp1 = c.T[k + 1];
+      Sbu_kp1 = c.S_bu[k + 1];
+      Sabs_kp1 = c.S_abs[k + 1];
+    } else {
+      T_kp1 = T_bottom;
+      Sbu_kp1 = S_bu_bottom;
+      Sabs_kp1 = S_bu_bottom * 2000.0;
+    }
+    const double f1 = fl_m[k + 1];
+    double H = c.H_abs[k], S = c.S_abs[k];
+    if (f1 > 0.) {
+      H = H + f1 * T_kp1 * c_l;
+      S = S + f_min(f1 * S_br_of(g, T_kp1, Sbu_kp1), Sabs_kp1);
+    } else if (f1 < 0.) {
+      H = H + f1 * T_k * c_l;
+      S = S + f_max(f1 * S_br_of(g, T_k, Sbu_k), -S);
+    }
+    if (f0 > 0.) {
+      H = H - f0 * T_k * c_l;
+      S = S - f_min(f0 * S_br_of(g, T_k, Sbu_k), S);
+    } else if (f0 < 0) {
+      H = H - f0 * T_km1 * c_l;
+      S = S - f_max(f0 * S_br_of(g, T_km1, Sbu_km1), -Sabs_km1);
+    }
+    c.H_abs[k] = H;
+    c.S_abs[k] = S;
+    T_km1 = T_k; Sbu_km1 = Sbu_k; Sabs_km1 = S;
+    T_k = T_kp1; Sbu_k = Sbu_kp1;
+    f0 = f1;
+  }
+}
+
+// ==========================================================================================
+// mo_snow.f90
+// ==========================================================================================
+
+// snow_coupling, mo_snow.f90:61-104.  The reference's getT calls alias T_in with T, which makes
+// the first guess H/c_l; passed explicitly here.
+__device__ __noinline__ void snow_coupling(const DevCfg& g, Col& c, double& H_abs1, double& phi1, double& T1, double m1,
+                                           double S_bu1) {
+  double& H_abs_snow = SCV(c, SC_H_ABS_SNOW);
+  double& phi_s = SCV(c, SC_PHI_S);
+  double& T_snow = SCV(c, SC_T_SNOW);
+  const double m_snow = SCV(c, SC_M_SNOW), S_abs_snow = SCV(c, SC_S_ABS_SNOW);
+  H_abs1 = H_abs1 + m_snow * latent_heat + H_abs_snow;
+  H_abs_snow = -m_snow * latent_heat;
+  double H = H_abs1 / m1;
+  double hs = H_abs_snow / m_snow;
+  getT(g, hs, S_abs_snow / m_snow, hs / c_l, T_snow, phi_s, c.status);
+  getT(g, H, S_bu1, H / c_l, T1, phi1, c.status);
+  if (T1 > 0 && H_abs1 <= -H_abs_snow) {
+    H_abs_snow = H_abs_snow + H_abs1;
+    H_abs1 = 0.0;
+    hs = H_abs_snow / m_snow;
+    getT(g, hs, S_abs_snow / m_snow, hs / c_l, T_snow, phi_s, c.status);
+    getT(g, H, S_bu1, H / c_l, T1, phi1, c.status);  // H is NOT refreshed here in the reference (:79-80)
+  } else if (T1 > 0. && H_abs1 > -H_abs_snow) {
+    H_abs1 = (H_abs1 + H_abs_snow) * m1 / m_snow / (1.0 + m1 / m_snow);
+    H_abs_snow = H_abs1 * m_snow / m1;
+    hs = H_abs_snow / m_snow;
+    getT(g, hs, S_abs_snow / m_snow, hs / c_l, T_snow, phi_s, c.status);
+    getT(g, H, S_bu1, H / c_l, T1, phi1, c.status);
+  } else {
+    int jj = 0;
+    while (fabs(T1 - T_snow) > SAMSIM_F32(0.1) && jj < 201) {
+      double d = T_snow - (T_snow + T1) / 2.0;
+      double step = f_sign(f_max(fabs(d), 0.1), d) * c_s * m_snow;
+      H_abs_snow = H_abs_snow - step;
+      H_abs1 = H_abs1 + step;
+      jj = jj + 1;
+      H = H_abs1 / m1;
+      hs = H_abs_snow / m_snow;
+      getT(g, hs, S_abs_snow / m_snow, hs / c_l, T_snow, phi_s, c.status);
+      getT(g, H, S_bu1, H / c_l, T1, phi1, c.status);
+      if (c.status) return;
+    }
+    if (jj > 200 && fabs(T1 - T_snow) > 1.0) c.status = 16;
+  }
+}
+
+// snow_precip, mo_snow.f90:123-150 (have_solid: precip_flag 0 passes solid_precip)
+__device__ __forceinline__ void snow_precip(Col& c, double dt, double liquid_in, double T2m, bool have_solid,
+                                            double solid_in) {
+  double solid, liquid;
+  if (have_solid) { solid = solid_in; liquid = liquid_in; }
+  else if (T2m > 0.0) { solid = 0.0; liquid = liquid_in; }
+  else { solid = liquid_in; liquid = 0.0; }
+  double d_thick = dt * solid * rho_l / rho_snow;
+  SCV(c, SC_M_SNOW) = SCV(c, SC_M_SNOW) + dt * rho_l * (liquid + solid);
+  SCV(c, SC_THICK_SNOW) = SCV(c, SC_THICK_SNOW) + d_thick;
+  double H = SCV(c, SC_H_ABS_SNOW);
+  H = H + dt * T2m * liquid * rho_l * c_l;
+  H = H + dt * f_min(T2m, -1.0) * solid * rho_l * c_s;
+  H = H - dt * solid * rho_l * latent_heat;
+  SCV(c, SC_H_ABS_SNOW) = H;
+}
+
+// snow_precip_0, mo_snow.f90:167-192
+__device__ __forceinline__ void snow_precip_0(double& H_abs, double& S_abs, double m, double T, double dt,
+                                              double liquid_in, double T2m, bool have_solid, double solid_in) {
+  double solid, liquid;
+  if (have_solid) { solid = solid_in; liquid = liquid_in; }
+  else if (T2m > 0.0) { solid = 0.0; liquid = liquid_in; }
+  else { solid = liquid_in; liquid = 0.0; }
+  H_abs = H_abs + (liquid + solid) * (T2m - T) * dt;
+  H_abs = H_abs - solid * latent_heat * dt;
+  S_abs = S_abs - (liquid + solid) * S_abs / m * dt;
+}
+
+// snow_thermo (mo_snow.f90:212-319) and snow_thermo_meltwater (:331-458) share everything up to
+// the saturated-layer block; `meltwater` selects the variant.
+__device__ __noinline__ void snow_thermo(const DevCfg& g, Col& c, bool meltwater, double& m1, double& thick1,
+                                         double& H_abs1, double& melt_thick_snow) {
+  double& psi_l_snow = SCV(c, SC_PSI_L_SNOW);
+  double& psi_s_snow = SCV(c, SC_PSI_S_SNOW);
+  double& psi_g_snow = SCV(c, SC_PSI_G_SNOW);
+  double& thick_snow = SCV(c, SC_THICK_SNOW);
+  double& S_abs_snow = SCV(c, SC_S_ABS_SNOW);
+  double& H_abs_snow = SCV(c, SC_H_ABS_SNOW);
+  double& m_snow = SCV(c, SC_M_SNOW);
+  double& T_snow = SCV(c, SC_T_SNOW);
+  double phi_snow = 0.0, max_lwc, max_lwc_v, sat_snow;
+
+  const double H_snow = H_abs_snow / m_snow;
+  const double S_bu_snow = S_abs_snow / m_snow;
+  const double psi_s_old = psi_s_snow;
+  {
+    double T_in = T_snow;
+    getT(g, H_snow, S_bu_snow, T_in, T_snow, phi_snow, c.status);
+  }
+  psi_s_snow = m_snow * phi_snow / rho_s / thick_snow;
+  psi_l_snow = m_snow * (1.0 - phi_snow) / rho_l / thick_snow;
+  if (psi_s_snow + psi_l_snow > 1.0) {
+    thick_snow = m_snow * (phi_snow / rho_s + (1.0 - phi_snow) / rho_l);
+    psi_s_snow = m_snow * phi_snow / rho_s / thick_snow;
+    psi_l_snow = m_snow * (1.0 - phi_snow) / rho_l / thick_snow;
+    if (fabs(psi_s_snow + psi_l_snow - 1.0) > 0.0000001) { c.status = 345; return; }
+  }
+  psi_g_snow = 1.0 - psi_s_snow - psi_l_snow;
+  if (psi_s_snow > 0.0) max_lwc = 0.057 * (1.0 - psi_s_snow) / (psi_s_snow) + 0.017;
+  else max_lwc = 0.0;
+
+  if (psi_s_old > psi_s_snow && psi_s_snow > 0.0) {
+    if ((1.0 - phi_snow) > max_lwc) thick_snow = thick_snow * (1.0 - (psi_s_old - psi_s_snow) / psi_s_old);
+    if (thick_snow < (phi_snow * m_snow / rho_s + (1.0 - phi_snow) * m_snow / rho_l))
+      thick_snow = (phi_snow * m_snow / rho_s + (1.0 - phi_snow) * m_snow / rho_l);
+    psi_s_snow = m_snow * phi_snow / rho_s / thick_snow;
+    psi_l_snow = m_snow * (1.0 - phi_snow) / rho_l / thick_snow;
+    psi_g_snow = 1.0 - psi_s_snow - psi_l_snow;
+    psi_g_snow = fabs(psi_g_snow);
+  } else if (psi_s_snow < 0.000001) {
+    thick_snow = m_snow / rho_l;
+    psi_s_snow = 0.0;
+    psi_g_snow = 0.0;
+    psi_l_snow = 1.0;
+  }
+
+  const bool wet = meltwater ? ((1.0 - phi_snow) > max_lwc && psi_l_snow > 0.0 && psi_g_snow > 0.0)
+                             : ((1.0 - phi_snow) > max_lwc && psi_g_snow > 0.0);
+  if (wet) {
+    max_lwc_v = max_lwc * m_snow / (rho_l * thick_snow);
+    if (!meltwater) {  // mo_snow.f90:272-294
+      sat_snow = thick_snow * (psi_l_snow - max_lwc_v);
+      sat_snow = sat_snow / (1.0 - psi_s_snow - max_lwc_v - f_min(gas_snow_ice2, psi_g_snow));
+      thick_snow = thick_snow - sat_snow;
+      thick1 = thick1 + sat_snow;
+      m_snow = m_snow - sat_snow * (psi_s_snow * rho_s + (1.0 - psi_s_snow - gas_snow_ice2) * rho_l);
+      m1 = m1 + sat_snow * (psi_s_snow * rho_s + (1.0 - psi_s_snow - gas_snow_ice2) * rho_l);
+      H_abs_snow = H_abs_snow - sat_snow * psi_s_snow * rho_s * c_s * T_snow;
+      H_abs1 = H_abs1 + sat_snow * psi_s_snow * rho_s * c_s * T_snow;
+      H_abs_snow = H_abs_snow + sat_snow * psi_s_snow * rho_s * latent_heat;
+      H_abs1 = H_abs1 - sat_snow * psi_s_snow * rho_s * latent_heat;
+      H_abs_snow = H_abs_snow - sat_snow * (1.0 - psi_s_snow) * rho_l * c_l * T_snow;
+      H_abs1 = H_abs1 + sat_snow * (1.0 - psi_s_snow) * rho_l * c_l * T_snow;
+    } else {  // :399-430
+      const double slush = (psi_l_snow - max_lwc_v) * (1.0 - g.k_snow_flush);
+      const double flush = (psi_l_snow - max_lwc_v) * g.k_snow_flush;
+      melt_thick_snow = thick_snow * flush;
+      sat_snow = thick_snow * (slush);
+      sat_snow = sat_snow / (1.0 - psi_s_snow - max_lwc_v - f_min(gas_snow_ice2, psi_g_snow));
+      const double gg = f_min(gas_snow_ice2, psi_g_snow);
+      thick_snow = thick_snow - sat_snow - melt_thick_snow;
+      thick1 = thick1 + sat_snow;
+      m_snow = m_snow - sat_snow * (psi_s_snow * rho_s + (1.0 - psi_s_snow - gg) * rho_l) - melt_thick_snow * rho_l;
+      m1 = m1 + sat_snow * (psi_s_snow * rho_s + (1.0 - psi_s_snow - gg) * rho_l);
+      H_abs_snow = H_abs_snow - sat_snow * psi_s_snow * rho_s * c_s * T_snow;
+      H_abs1 = H_abs1 + sat_snow * psi_s_snow * rho_s * c_s * T_snow;
+      H_abs_snow = H_abs_snow + sat_snow * psi_s_snow * rho_s * latent_heat;
+      H_abs1 = H_abs1 - sat_snow * psi_s_snow * rho_s * latent_heat;
+      H_abs_snow = H_abs_snow - sat_snow * (1.0 - psi_s_snow - gg) * rho_l * c_l * T_snow -
+                   melt_thick_snow * rho_l * c_l * T_snow;
+      H_abs1 = H_abs1 + sat_snow * (1.0 - psi_s_snow - gg) * rho_l * c_l * T_snow;
+    }
+  } else if (psi_g_snow <= 0.0) {
+    H_abs1 = H_abs1 + H_abs_snow;
+    m1 = m1 + m_snow;
+    thick1 = thick1 + thick_snow;
+    H_abs_snow = 0.0; m_snow = 0.0; thick_snow = 0.0;
+    psi_g_snow = 0.0; psi_s_snow = 0.0; psi_l_snow = 0.0;
+  }
+  if (psi_g_snow < 0.0) c.status = 9876;
+}
+
+// the driver's snow block, mo_grotz.f90:273-292 and :601-621
+__device__ __forceinline__ void snow_block(const DevCfg& g, Col& c) {
+  if (SCV(c, SC_THICK_SNOW) > 0.0) {
+    double m1 = c.m[1], th1 = c.thick[1], H1 = c.H_abs[1];
+    if (g.snow_flush_flag == 0) {
+      double dummy = 0.0;
+      snow_thermo(g, c, false, m1, th1, H1, dummy);
+      SCV(c, SC_MELT_THICK_SNOW) = 0.0;
+    } else if (g.snow_flush_flag == 1) {
+      SCV(c, SC_MELT_THICK_SNOW) = 0.0;
+      snow_thermo(g, c, true, m1, th1, H1, SCV(c, SC_MELT_THICK_SNOW));
+    }
+    c.m[1] = m1; c.thick[1] = th1; c.H_abs[1] = H1;
+  } else {
+    SCV(c, SC_THICK_SNOW) = 0.0; SCV(c, SC_M_SNOW) = 0.0; SCV(c, SC_PSI_S_SNOW) = 0.0; SCV(c, SC_PSI_L_SNOW) = 0.0;
+    SCV(c, SC_PSI_G_SNOW) = 0.0; SCV(c, SC_H_ABS_SNOW) = 0.0; SCV(c, SC_S_ABS_SNOW) = 0.0;
+    SCV(c, SC_MELT_THICK_SNOW) = 0.0;
+  }
+}
+
+// sub_fl_Q_0_snow_thin :466-487, sub_fl_Q_snow :498-518, sub_fl_Q_0_snow :528-545
+__device__ __forceinline__ double fl_Q_0_snow_thin(double m_snow, double thick_snow, double T_snow, double ps,
+                                                   double pl, double pg, double thick, double T_bound) {
+  double ks = k_snow_of(m_snow, thick_snow);
+  double k = ps * k_s + pl * k_l + pg * 0.0;
+  k = thick_snow / (thick_snow + thick) * ks + thick / (thick_snow + thick) * k;
+  double R = (thick_snow + thick) / (2.0 * k);
+  return (T_snow - T_bound) / R;
+}
+__device__ __forceinline__ double fl_Q_snow_ice(double m_snow, double thick_snow, double T_snow, double ps2,
+                                                double pl2, double th2, double T2) {
+  double ks = k_snow_of(m_snow, thick_snow);
+  double k2 = ps2 * k_s + pl2 * k_l;
+  double R = thick_snow / (2.0 * ks) + th2 / (2.0 * k2);
+  return (T2 - T_snow) / R;
+}
+__device__ __forceinline__ double fl_Q_0_snow(double m_snow, double thick_snow, double T_snow, double T_bound) {
+  double k = k_snow_of(m_snow, thick_snow);
+  double R = thick_snow / (2.0 * k);
+  return (T_snow - T_bound) / R;
+}
+
+// ==========================================================================================
+// mo_grav_drain.f90
+// ==========================================================================================
+
+// fl_grav_drain, mo_grav_drain.f90:74-201.  Scratch: w0 perm, w1 thick/perm, w2 harmonic_perm, fl_m.
+// The FORALL fl_up(k:N_active) += flux (:162-164) is a running sum in layer order; only element k
+// is clamped (:166), which the carry does not see -- same additions, O(N) instead of O(N^2).
+__device__ __noinline__ void grav_drain(const DevCfg& g, Col& c) {
+  const int Na = c.N_active, N = g.Nlayer;
+  const double dt = g.dt;
+  Lay perm = c.w0, q = c.w1, hperm = c.w2, fl_m = c.fl_m;
+  double heat_loss = 0.0;
+
+  for (int k = 1; k <= N - 1; k++) c.ray[k] = 0.0;                                                  // :98
+  for (int k = 1; k <= Na; k++) perm[k] = 1e-17 * det_pow(1000.0 * fabs(c.psi_l[k]), 3.10);       // :104-106
+  const double bottom_h = c.thick[Na] * c.psi_s[Na] / psi_s_min;  // thick(N_active)*psi_s(N_active)/psi_s_min
+
+  if (g.harmonic_flag == 2) {  // :109-123
+    for (int k = 1; k <= Na - 1; k++) q[k] = c.thick[k] / perm[k];
+    const double qb = bottom_h / perm[Na];
+    // suffix minimum of perm(k:Na-1) is order independent; walk k downwards to build it
+    double mn = 0.0;
+    for (int k = Na - 1; k >= 1; k--) {
+      double pk = perm[k];
+      mn = (k == Na - 1) ? pk : f_min(mn, pk);
+      hperm[k] = mn;  // temporarily the suffix minimum
+    }
+    for (int k = 1; k <= Na - 1; k++) {
+      if (hperm[k] < 1e-14) {
+        hperm[k] = 0.0;
+      } else {
+        double h = 0.0, th = 0.0;
+        for (int kk = k; kk <= Na - 1; kk++) h = h + q[kk];
+        h = h + qb;
+        for (int kk = k; kk <= Na - 1; kk++) th = th + c.thick[kk];
+        hperm[k] = (th + bottom_h) / h;
+      }
+    }
+  }
+
+  const double S_br_Na = c.S_br[Na];
+  for (int k = 1; k <= Na - 1; k++) {  // :126-136
+    double d_S_br = c.S_br[k] - S_br_Na;
+    double height = sum_fwd(c.thick, k + 1, Na - 1) + bottom_h;
+    double r;
+    if (g.harmonic_flag == 1) {
+      double mn = perm[k];
+      for (int kk = k; kk <= Na; kk++) mn = f_min(mn, perm[kk]);
+      r = grav * rho_l * bbeta * d_S_br * height * mn;
+    } else {
+      r = grav * rho_l * bbeta * d_S_br * height * hperm[k];
+    }
+    r = r / (kappa_l * mu);
+    c.ray[k] = f_max(r, 0.0);
+  }
+
+  SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) + sum_fwd(c.S_abs, 1, Na);  // :141 (inactive layers hold 0)
+
+  double run = 0.0;  // running sum = fl_up(kk) for every kk not yet clamped
+  fl_m[1] = 0.0;
+  for (int k = 1; k <= Na - 1; k++) {  // :144-171
+    const double rk = c.ray[k], psk = c.psi_s[k], Sk = c.S_abs[k], mk = c.m[k], sbk = c.S_br[k];
+    double up = run;
+    if (rk > ray_crit && psk > 0.001 && Sk / mk > 0.1 && sbk > c.S_br[k + 1]) {
+      const double plk = c.psi_l[k], thk = c.thick[k], Tk = c.T[k];
+      double flux = x_grav * (rk - ray_crit) * dt * thk;
+      flux = f_min(flux, plk * rho_l * thk);
+      double Snew = Sk - flux * sbk;
+      c.S_abs[k] = Snew;
+      if (Snew < 0.0) { c.status = 21234; return; }
+      SCV(c, SC_GRAV_TEMP) = SCV(c, SC_GRAV_TEMP) + flux * Tk;
+      c.H_abs[k] = c.H_abs[k] - flux * c_l * Tk;
+      heat_loss = heat_loss + flux * c_l * Tk;
+      run = run + flux;
+      up = f_min(run, plk * rho_l * thk);
+    }
+    fl_m[k + 1] = up;  // fl_m(2:N_active+1) = fl_up(1:N_active), :177
+  }
+  fl_m[Na + 1] = run;
+  const double fl_up_Na = run;
+
+  SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) - sum_fwd(c.S_abs, 1, Na);  // :173
+
+  mass_transfer(g, c, fl_m);  // :188
+
+  SCV(c, SC_GRAV_DRAIN) = SCV(c, SC_GRAV_DRAIN) + fl_m[Na + 1];  // :190
+  if (g.grav_heat_flag == 2) c.H_abs[Na] = c.H_abs[Na] + heat_loss - fl_up_Na * c_l * SCV(c, SC_T_BOTTOM);  // :193-195
+  double mn = c.S_abs[1];
+  for (int k = 2; k <= Na; k++) mn = f_min(mn, c.S_abs[k]);
+  if (f_min(mn, 0.0) < 0.0) c.status = 1337;  // :198 MINVAL over all layers (inactive are 0)
+}
+
+// fl_grav_drain_simple, mo_grav_drain.f90:218-279 (grav_flag 3)
+__device__ __noinline__ void grav_drain_simple(const DevCfg& g, Col& c) {
+  const int Na = c.N_active, N = g.Nlayer;
+  Lay perm = c.w0, hperm = c.w2;
+  for (int k = 1; k <= N - 1; k++) c.ray[k] = 0.0;
+  for (int k = 1; k <= Na; k++) perm[k] = 1e-17 * det_pow(1000.0 * fabs(c.psi_l[k]), 3.10);
+  const double bottom_h = c.thick[Na] * c.psi_s[Na] / psi_s_min;
+  if (g.harmonic_flag == 2) {
+    for (int k = 1; k <= Na - 1; k++) {
+      double mn = perm[k];
+      for (int kk = k; kk <= Na - 1; kk++) mn = f_min(mn, perm[kk]);
+      if (mn < 1e-14) {
+        hperm[k] = 0.0;
+      } else {
+        double h = 0.0;
+        for (int kk = k; kk <= Na - 1; kk++) h = h + c.thick[kk] / perm[kk];
+        h = h + bottom_h / perm[Na];
+        hperm[k] = (sum_fwd(c.thick, k, Na - 1) + bottom_h) / h;
+      }
+    }
+  }
+  const double S_br_Na = c.S_br[Na];
+  for (int k = 1; k <= Na - 1; k++) {
+    double d_S_br = c.S_br[k] - S_br_Na;
+    double height = sum_fwd(c.thick, k + 1, Na - 1) + bottom_h;
+    double r;
+    if (g.harmonic_flag == 1) {
+      double mn = perm[k];
+      for (int kk = k; kk <= Na; kk++) mn = f_min(mn, perm[kk]);
+      r = grav * rho_l * bbeta * d_S_br * height * mn;
+    } else {
+      r = grav * rho_l * bbeta * d_S_br * height * hperm[k];
+    }
+    r = r / (kappa_l * mu);
+    c.ray[k] = f_max(r, 0.0);
+  }
+  for (int k = Na - 1; k >= 1; k--)
+    if (c.ray[k] > ray_crit) c.S_abs[k] = c.S_abs[k] * SAMSIM_F32(0.99);
+  SCV(c, SC_GRAV_DRAIN) = 0.0;
+}
+
+// ==========================================================================================
+// mo_flood.f90
+// ==========================================================================================
+
+// flood, mo_flood.f90:55-153
+__device__ __noinline__ void flood(const DevCfg& g, Col& c) {
+  const int Na = c.N_active;
+  const double dt = g.dt, freeboard = SCV(c, SC_FREEBOARD), psi_g_snow = SCV(c, SC_PSI_G_SNOW);
+  double& thick_snow = SCV(c, SC_THICK_SNOW);
+  double& H_abs_snow = SCV(c, SC_H_ABS_SNOW);
+  double& m_snow = SCV(c, SC_M_SNOW);
+  double hp = 0.0;
+  for (int k = 1; k <= Na - 1; k++) hp = hp + c.thick[k] / (1e-17 * det_pow(1000.0 * c.psi_l[k], 3.10));  // :73-79
+  const double bottom_h = c.thick[Na] * c.psi_s[Na] / psi_s_min;
+  hp = hp + bottom_h / (1e-17 * det_pow(1000.0 * c.psi_l[Na], 3.10));
+  hp = (sum_fwd(c.thick, 1, Na - 1) + bottom_h) / hp;
+
+  double flood_brine = -dt * grav * rho_l * rho_l * hp * (freeboard) / (mu * sum_fwd(c.thick, 1, Na));  // :85
+  const double shift_ice = flood_brine / (rho_l * psi_g_snow / ratio_flood);
+  const double shift_snow = shift_ice * (1 + psi_g_snow / (1.0 - psi_g_snow) * (1.0 - 1.0 / ratio_flood));
+
+  const double S_bu_Na = c.S_abs[Na] / c.m[Na];  // S_bu(k) = S_abs(k)/m(k) before any change, :93-95
+  double S1 = c.S_abs[1], H1 = c.H_abs[1], m1 = c.m[1], th1 = c.thick[1];
+  S1 = S1 + flood_brine * S_bu_Na;                  // :102-104
+  H1 = H1 + flood_brine * c.H_abs[Na] / c.m[Na];
+  m1 = m1 + flood_brine;
+  th1 = th1 + shift_ice;                            // :107-112
+  H1 = H1 + shift_snow / thick_snow * H_abs_snow;
+  H_abs_snow = H_abs_snow - shift_snow / thick_snow * H_abs_snow;
+  m1 = m1 + shift_snow / thick_snow * m_snow;
+  m_snow = m_snow - shift_snow / thick_snow * m_snow;
+  thick_snow = thick_snow - shift_snow;
+  c.S_abs[1] = S1; c.H_abs[1] = H1; c.m[1] = m1; c.thick[1] = th1;  // Na > 1 here, layer 1 != layer Na
+
+  if (freeboard + shift_ice < neg_free) {  // :117-138
+    const double shift = neg_free - (freeboard + shift_ice);
+    flood_brine = shift * (psi_g_snow)*rho_l;
+    const double T_Na = c.T[Na];
+    c.S_abs[Na] = c.S_abs[Na] + (SCV(c, SC_S_BU_BOTTOM) - S_bu_Na) * flood_brine;
+    c.H_abs[Na] = c.H_abs[Na] + (SCV(c, SC_T_BOTTOM) - T_Na) * c_l * flood_brine;
+    S1 = S1 + S_bu_Na * flood_brine;
+    H1 = H1 + T_Na * c_l * flood_brine;
+    m1 = m1 + flood_brine;
+    th1 = th1 + shift;
+    H1 = H1 + shift / thick_snow * H_abs_snow;
+    H_abs_snow = H_abs_snow - shift / thick_snow * H_abs_snow;
+    m1 = m1 + shift / thick_snow * m_snow;
+    m_snow = m_snow - shift / thick_snow * m_snow;
+    thick_snow = thick_snow - shift;
+    c.S_abs[1] = S1; c.H_abs[1] = H1; c.m[1] = m1; c.thick[1] = th1;
+  }
+}
+
+// flood_simple, mo_flood.f90:167-210
+__device__ __forceinline__ void flood_simple(Col& c) {
+  double& thick_snow = SCV(c, SC_THICK_SNOW);
+  double& H_abs_snow = SCV(c, SC_H_ABS_SNOW);
+  double& m_snow = SCV(c, SC_M_SNOW);
+  const double shift = SCV(c, SC_FREEBOARD) - neg_free;
+  const double flood_brine = -shift * SCV(c, SC_PSI_G_SNOW) * rho_l;
+  double S1 = c.S_abs[1], H1 = c.H_abs[1], m1 = c.m[1];
+  c.thick[1] = c.thick[1] - shift;
+  S1 = S1 + SCV(c, SC_S_BU_BOTTOM) * flood_brine;
+  H1 = H1 - shift / thick_snow * H_abs_snow;
+  H1 = H1 + SCV(c, SC_T_BOTTOM) * c_l * flood_brine;
+  m1 = m1 - shift / thick_snow * m_snow;
+  m1 = m1 + flood_brine;
+  H_abs_snow = H_abs_snow + shift / thick_snow * H_abs_snow;
+  m_snow = m_snow + shift / thick_snow * m_snow;
+  thick_snow = thick_snow + shift;
+  c.S_abs[1] = S1; c.H_abs[1] = H1; c.m[1] = m1;
+}
+
+// ==========================================================================================
+// mo_flush.f90
+// ==========================================================================================
+
+// flush3, mo_flush.f90:70-237.  Scratch: w0 R_v, w1 R_h, w2 R, w3 S_bu(local), fl_m.
+__device__ __noinline__ void flush3(const DevCfg& g, Col& c) {
+  const int Na = c.N_active, N = g.Nlayer;
+  const double dt = g.dt, freeboard = SCV(c, SC_FREEBOARD);
+  Lay R_v = c.w0, R_h = c.w1, R = c.w2, S_bu = c.w3, fl_m = c.fl_m;
+  double& melt_thick = SCV(c, SC_MELT_THICK);
+
+  for (int k = 1; k <= Na; k++) { c.flush_v[k] = 0.0; c.flush_h[k] = 0.0; }   // :101-102 (dummies are DIMENSION(N_active))
+  for (int k = 1; k <= Na; k++) S_bu[k] = c.S_abs[k] / c.m[k];              // :103
+  const double konst = sum_fwd(c.thick, 1, Na) * para_flush_horiz;          // :106
+  melt_thick = f_min(melt_thick, c.psi_l[1] * c.thick[1]);                  // :110
+  melt_thick = f_min(melt_thick, g.thick_0 / 3.0);                          // :112
+
+  if (g.snow_flush_flag == 1) {  // :114-125
+    for (int k = Na + 1; k <= N; k++) c.perm[k] = 0.0;
+    for (int k = 1; k <= Na; k++) {
+      double p = 1e-17 * det_pow(1000.0 * fabs(c.psi_l[k] + 2. * c.psi_g[k]), 3.10);
+      if (p == 0.0) p = 1.0;
+      c.perm[k] = p;
+    }
+  } else if (g.snow_flush_flag == 0) {  // :126-130
+    for (int k = Na + 1; k <= N; k++) c.perm[k] = 1.0;
+    for (int k = 1; k <= Na; k++) c.perm[k] = 1e-17 * det_pow(1000.0 * fabs(c.psi_l[k]), 3.10);
+  }
+  for (int k = 1; k <= Na; k++) {  // :133-137
+    const double pk = f_max(c.perm[k], 0.00000000000000000000001), thk = c.thick[k];
+    R_v[k] = mu * thk / pk;
+    R_h[k] = mu * konst / (thk * pk);
+  }
+  R[Na] = 0.0;
+  R[Na - 1] = R_v[Na - 1];
+  for (int k = Na - 2; k >= 1; k--) {  // :141-146
+    double r = R[k + 1] + R_v[k];
+    R[k] = ((r)*R_h[k]) / (r + R_h[k]);
+  }
+  const double T1 = c.T[1];
+  double flush_total = (freeboard + melt_thick) / R[1] * grav * dt * density_of(T1, S_br_of(g, T1)) * rho_l;  // :152
+  flush_total = f_min(flush_total, melt_thick * rho_l);
+  SCV(c, SC_MELT_ERR) = SCV(c, SC_MELT_ERR) + melt_thick - f_min(flush_total / rho_l, melt_thick);  // :156
+
+  {
+    const double den = R[2] + R_v[1] + R_h[1];
+    c.flush_h[1] = flush_total * (R[2] + R_v[1]) / den;  // :159-160
+    c.flush_v[1] = flush_total * R_h[1] / den;
+  }
+  for (int k = 2; k <= Na - 1; k++) {  // :161-164
+    const double fv = c.flush_v[k - 1], a = R[k + 1] + R_v[k], den = a + R_h[k];
+    c.flush_h[k] = fv * a / den;
+    c.flush_v[k] = fv * R_h[k] / den;
+  }
+  c.flush_v[Na] = c.flush_v[Na - 1];
+  c.flush_h[Na] = 0.0;
+
+  fl_m[1] = 0.0;  // :179-180
+  for (int k = 1; k <= Na; k++) fl_m[k + 1] = -c.flush_v[k];
+
+  {  // mass_transfer with the LOCAL S_bu (:182): swap the view for the call
+    Lay keep = c.S_bu;
+    c.S_bu = S_bu;
+    mass_transfer(g, c, fl_m);
+    c.S_bu = keep;
+  }
+  const double T_Na = c.T[Na];
+  if (g.flush_heat_flag == 2) c.H_abs[Na] = c.H_abs[Na] - fl_m[Na + 1] * T_Na * c_l;  // :185-187
+
+  c.m[1] = c.m[1] - flush_total;  // :190-191
+  c.thick[1] = c.thick[1] - flush_total / rho_l;
+
+  double sfh = 0.0;
+  double H_Na = c.H_abs[Na], S_Na = c.S_abs[Na];
+  for (int k = 1; k <= Na - 1; k++) {  // :196-206
+    const double fh = c.flush_h[k], Tk = c.T[k];
+    const double loss_S = fh * S_br_of(g, Tk, c.S_abs[k] / c.m[k]);
+    const double loss_H = fh * Tk * c_l;
+    c.S_abs[k] = c.S_abs[k] - loss_S;
+    c.H_abs[k] = c.H_abs[k] - loss_H;
+    H_Na = H_Na + loss_H;
+    S_Na = S_Na + loss_S;
+    sfh = sfh + fh;
+  }
+  sfh = sfh + c.flush_h[Na];  // SUM(flush_h) over the N_active-long dummy
+  const double loss_S = sfh * S_bu[Na];  // :207-208
+  const double loss_H = sfh * T_Na * c_l;
+  if (g.flush_heat_flag == 2) H_Na = H_Na - loss_H;
+  S_Na = S_Na - loss_S;
+  c.H_abs[Na] = H_Na;
+  c.S_abs[Na] = S_Na;
+
+  double mn = c.S_abs[1];
+  for (int k = 2; k <= Na; k++) mn = f_min(mn, c.S_abs[k]);
+  mn = f_min(mn, 0.0);  // MINVAL over all Nlayer: inactive layers hold 0 (only matters when Na < N)
+  if (mn < -0.00000000000000000000000001)
+    for (int k = 1; k <= Na; k++) c.S_abs[k] = f_max(c.S_abs[k], 0.0);
+  if (fabs(c.m[1]) < 0.000001) c.status = 9876;  // :230-233
+}
+
+// flush4, mo_flush.f90:253-296 (flush_flag 6)
+__device__ __noinline__ void flush4(const DevCfg& g, Col& c) {
+  const int N = g.Nlayer, Na = c.N_active;
+  double& melt_thick = SCV(c, SC_MELT_THICK);
+  const double S_bu1 = c.S_abs[1] / c.m[1], T1 = c.T[1];
+  c.H_abs[1] = c.H_abs[1] - melt_thick * rho_l * c_l * T1;
+  c.S_abs[1] = c.S_abs[1] - melt_thick * rho_l * S_br_of(g, T1, S_bu1);
+  c.thick[1] = c.thick[1] - melt_thick;
+  c.m[1] = c.m[1] - melt_thick * rho_l;
+  melt_thick = 0.0;
+  int k = 2;
+  while (k <= N && c.psi_l[k] > c.psi_l[k - 1]) {
+    c.S_abs[k] = para_flush_gamma * c.S_abs[k];
+    k = k + 1;
+  }
+  c.S_abs[1] = f_max(c.S_abs[1], 0.00);
+  double mn = c.S_abs[1];
+  for (int q = 2; q <= Na; q++) mn = f_min(mn, c.S_abs[q]);
+  if (mn < 0.0) c.status = 9876;
+}
+
+// ==========================================================================================
+// mo_layer_dynamics.f90.  Snapshots rho/S_bu/H of the reference become w0/w1/w2.
+// ==========================================================================================
+__device__ __forceinline__ void snapshot_layers(Col& c, int k0, int k1) {
+  for (int k = k0; k <= k1; k++) {
+    const double mk = c.m[k];
+    c.w0[k] = mk / c.thick[k];   // rho
+    c.w1[k] = c.S_abs[k] / mk;   // S_bu
+    c.w2[k] = c.H_abs[k] / mk;   // H
+  }
+}
+
+// top_melt, mo_layer_dynamics.f90:191-326
+__device__ __noinline__ void top_melt(const DevCfg& g, Col& c) {
+  const int N = g.Nlayer, N_middle = g.N_middle, N_top = g.N_top;
+  const double thick_0 = g.thick_0;
+  Lay rho = c.w0, S_bu = c.w1, H = c.w2;
+  snapshot_layers(c, 1, c.N_active);  // :218-223
+  c.m[1] = c.m[1] + c.m[2];           // :231-235
+  c.S_abs[1] = c.S_abs[1] + c.S_abs[2];
+  c.H_abs[1] = c.H_abs[1] + c.H_abs[2];
+  c.thick[1] = c.thick[1] + c.thick[2];
+  const int kmax = (N_top - 1 < c.N_active - 1) ? N_top - 1 : c.N_active - 1;
+  for (int k = 2; k <= kmax; k++) {  // :238-243
+    c.m[k] = rho[k + 1] * thick_0;
+    c.S_abs[k] = S_bu[k + 1] * rho[k + 1] * thick_0;
+    c.H_abs[k] = H[k + 1] * rho[k + 1] * thick_0;
+  }
+  if (c.N_active <= N_top) {  // :247-254
+    const int Na = c.N_active;
+    c.m[Na] = 0.0; c.S_abs[Na] = 0.0; c.H_abs[Na] = 0.0; c.thick[Na] = 0.0;
+    c.N_active = Na - 1;
+  } else if (c.N_active > N_top && c.N_active <= N && c.thick[N_top + 1] / thick_0 < 1.00001) {  // :256-273
+    const int Na = c.N_active;
+    for (int k = N_top; k <= Na - 1; k++) {
+      c.m[k] = rho[k + 1] * thick_0;
+      c.S_abs[k] = S_bu[k + 1] * rho[k + 1] * thick_0;
+      c.H_abs[k] = H[k + 1] * rho[k + 1] * thick_0;
+    }
+    c.m[Na] = 0.0; c.S_abs[Na] = 0.0; c.H_abs[Na] = 0.0; c.thick[Na] = 0.0;
+    c.N_active = Na - 1;
+  }
+  if (c.N_active == N && c.thick[N_top + 1] - thick_0 >= 0.000001) {  // :275-314
+    double loss_m = thick_0 * rho[N_top + 1];
+    double loss_S = loss_m * S_bu[N_top + 1];
+    double loss_H = loss_m * H[N_top + 1];
+    c.m[N_top] = loss_m;
+    c.S_abs[N_top] = loss_S;
+    c.H_abs[N_top] = loss_H;
+    for (int k = N_top + 1; k <= N_middle + N_top; k++) {
+      double mk = c.m[k] - loss_m, Hk = c.H_abs[k] - loss_H, Sk = c.S_abs[k] - loss_S;
+      const double shift = thick_0 * (double)(float)(N_middle - k + N_top) / (double)(float)(N_middle);  // :293
+      loss_m = shift * rho[k + 1];
+      loss_S = loss_m * S_bu[k + 1];
+      loss_H = loss_m * H[k + 1];
+      c.m[k] = mk + loss_m;
+      c.H_abs[k] = Hk + loss_H;
+      c.S_abs[k] = Sk + loss_S;
+    }
+    for (int k = N_top + 1; k <= N_top + N_middle; k++) c.thick[k] = c.thick[k] - thick_0 / (double)(float)(N_middle);
+  }
+  // :318-321 grid consistency, STOP 7889 (SUM(thick) over all layers; inactive are 0)
+  if (c.N_active < N) {
+    if (thick_0 * (c.N_active + 0.501) <= sum_fwd(c.thick, 1, N)) c.status = 7889;
+  }
+}
+
+// bottom_melt, mo_layer_dynamics.f90:341-420
+__device__ __noinline__ void bottom_melt(const DevCfg& g, Col& c) {
+  const int N = g.Nlayer, N_middle = g.N_middle, N_top = g.N_top;
+  Lay rho = c.w0, S_bu = c.w1, H = c.w2;
+  snapshot_layers(c, N_top + 1, N);  // :364-370
+  const double thN = c.thick[N];
+  double loss_m = 0.0, loss_S = 0.0, loss_H = 0.0;
+  for (int k = N_top + 1; k <= N_top + N_middle; k++) {  // :378-400
+    double mk = c.m[k] + loss_m, Hk = c.H_abs[k] + loss_H, Sk = c.S_abs[k] + loss_S;
+    const double shift = thN * (k - N_top) / (double)(float)(N_middle);
+    loss_m = shift * rho[k];
+    loss_H = loss_m * H[k];
+    loss_S = loss_m * S_bu[k];
+    c.m[k] = mk - loss_m;
+    c.H_abs[k] = Hk - loss_H;
+    c.S_abs[k] = Sk - loss_S;
+  }
+  for (int k = N_top + 1; k <= N_top + N_middle; k++) c.thick[k] = c.thick[k] - thN / (double)(float)(N_middle);
+  for (int k = N_top + N_middle + 1; k <= N; k++) {  // :410-415
+    const double thk = c.thick[k];
+    c.H_abs[k] = rho[k - 1] * thk * H[k - 1];
+    c.S_abs[k] = rho[k - 1] * thk * S_bu[k - 1];
+    c.m[k] = rho[k - 1] * thk;
+  }
+}
+
+// bottom_growth, mo_layer_dynamics.f90:438-520
+__device__ __noinline__ void bottom_growth(const DevCfg& g, Col& c) {
+  const int N = g.Nlayer, N_middle = g.N_middle, N_top = g.N_top, N_bottom = g.N_bottom;
+  Lay rho = c.w0, S_bu = c.w1, H = c.w2;
+  snapshot_layers(c, N_top + 1, N_top + N_middle + 1);  // :463-468
+  const double thN = c.thick[N];
+  double gain_m = 0.0, gain_S = 0.0, gain_H = 0.0;
+  for (int k = N_top + 1; k <= N_top + N_middle; k++) {  // :476-495
+    double mk = c.m[k] - gain_m, Hk = c.H_abs[k] - gain_H, Sk = c.S_abs[k] - gain_S;
+    const double shift = thN * (k - N_top) / (double)(float)(N_middle);
+    gain_m = shift * rho[k + 1];
+    gain_H = gain_m * H[k + 1];
+    gain_S = gain_m * S_bu[k + 1];
+    c.m[k] = mk + gain_m;
+    c.H_abs[k] = Hk + gain_H;
+    c.S_abs[k] = Sk + gain_S;
+  }
+  for (int k = N_top + 1; k <= N_top + N_middle; k++) c.thick[k] = c.thick[k] + thN / (double)(float)(N_middle);
+  for (int k = N - N_bottom + 1; k <= N - 1; k++) {  // :503-508
+    c.H_abs[k] = c.H_abs[k + 1];
+    c.S_abs[k] = c.S_abs[k + 1];
+    c.m[k] = c.m[k + 1];
+  }
+  const double mN = c.thick[N] * rho_l;  // :511-513
+  c.m[N] = mN;
+  c.H_abs[N] = mN * SCV(c, SC_T_BOTTOM) * c_l;
+  c.S_abs[N] = mN * SCV(c, SC_S_BU_BOTTOM);
+}
+
+// bottom_growth_simple :537-561, bottom_melt_simple :573-590
+__device__ __forceinline__ void bottom_growth_simple(const DevCfg& g, Col& c) {
+  const int Na = c.N_active + 1;
+  c.N_active = Na;
+  c.thick[Na] = g.thick_0;
+  const double mN = g.thick_0 * rho_l;
+  c.m[Na] = mN;
+  c.H_abs[Na] = mN * SCV(c, SC_T_BOTTOM) * c_l;
+  c.S_abs[Na] = mN * SCV(c, SC_S_BU_BOTTOM);
+}
+__device__ __forceinline__ void bottom_melt_simple(Col& c) {
+  const int Na = c.N_active;
+  c.thick[Na] = 0.0; c.m[Na] = 0.0; c.S_abs[Na] = 0.0; c.H_abs[Na] = 0.0;
+  c.N_active = Na - 1;
+}
+
+// top_grow, mo_layer_dynamics.f90:607-716
+__device__ __noinline__ void top_grow(const DevCfg& g, Col& c) {
+  const int N = g.Nlayer, N_middle = g.N_middle, N_top = g.N_top;
+  const double thick_0 = g.thick_0;
+  Lay rho = c.w0, S_bu = c.w1, H = c.w2;
+  snapshot_layers(c, 1, c.N_active);  // :631-636
+  {
+    const double loss_m = thick_0 * rho[1];  // :639-648
+    const double loss_S = loss_m * S_bu[1];
+    const double loss_H = loss_m * H[1];
+    c.m[1] = c.m[1] - loss_m;
+    c.S_abs[1] = c.S_abs[1] - loss_S;
+    c.H_abs[1] = c.H_abs[1] - loss_H;
+    c.thick[1] = c.thick[1] - thick_0;
+  }
+  const int kmax = (N_top < c.N_active) ? N_top : c.N_active;
+  for (int k = 2; k <= kmax; k++) {  // :651-656
+    c.m[k] = rho[k - 1] * thick_0;
+    c.S_abs[k] = S_bu[k - 1] * rho[k - 1] * thick_0;
+    c.H_abs[k] = H[k - 1] * rho[k - 1] * thick_0;
+  }
+  if (c.N_active <= N_top) {  // :659-665
+    const int Na = c.N_active + 1;
+    c.N_active = Na;
+    c.m[Na] = rho[Na - 1] * thick_0;
+    c.S_abs[Na] = S_bu[Na - 1] * thick_0 * rho[Na - 1];
+    c.H_abs[Na] = H[Na - 1] * thick_0 * rho[Na - 1];
+    c.thick[Na] = thick_0;
+  } else if (c.N_active > N_top && c.N_active < N) {  // :668-680
+    for (int k = N_top + 1; k <= c.N_active; k++) {
+      c.m[k] = rho[k - 1] * thick_0;
+      c.S_abs[k] = S_bu[k - 1] * rho[k - 1] * thick_0;
+      c.H_abs[k] = H[k - 1] * rho[k - 1] * thick_0;
+    }
+    const int Na = c.N_active + 1;
+    c.N_active = Na;
+    c.m[Na] = rho[Na - 1] * thick_0;
+    c.S_abs[Na] = S_bu[Na - 1] * thick_0 * rho[Na - 1];
+    c.H_abs[Na] = H[Na - 1] * thick_0 * rho[Na - 1];
+    c.thick[Na] = thick_0;
+  } else if (c.N_active == N) {  // :682-711
+    double loss_m = thick_0 * rho[N_top];
+    double loss_S = loss_m * S_bu[N_top];
+    double loss_H = loss_m * H[N_top];
+    for (int k = N_top + 1; k <= N_middle + N_top; k++) {
+      double mk = c.m[k] + loss_m, Hk = c.H_abs[k] + loss_H, Sk = c.S_abs[k] + loss_S;
+      const double shift = thick_0 * (double)(float)(N_middle - k + N_top) / (double)(float)(N_middle);
+      loss_m = shift * rho[k];
+      loss_S = loss_m * S_bu[k];
+      loss_H = loss_m * H[k];
+      c.m[k] = mk - loss_m;
+      c.H_abs[k] = Hk - loss_H;
+      c.S_abs[k] = Sk - loss_S;
+    }
+    for (int k = N_top + 1; k <= N_top + N_middle; k++) c.thick[k] = c.thick[k] + thick_0 / (double)(float)(N_middle);
+  }
+}
+
+// layer_dynamics dispatcher, mo_layer_dynamics.f90:64-175
+__device__ __noinline__ void layer_dynamics(const DevCfg& g, Col& c) {
+  const int N = g.Nlayer, N_top = g.N_top, Na = c.N_active;
+  const double thick_0 = g.thick_0;
+  const bool bf = (g.bottom_flag == 1);
+  const int nm1 = (Na - 1 > 1) ? Na - 1 : 1;
+  const double phi_Na = c.phi[Na], phi_nm1 = c.phi[nm1], th1 = c.thick[1];
+  const double mid_ratio = c.thick[N_top + 1] / thick_0;
+  if (c.phi[N - 1] <= psi_s_min / 2.0 && phi_Na < 0.00001 && Na == N && mid_ratio > 1.000001 && bf) {
+    bottom_melt(g, c);
+  } else if (Na > 1 && Na < N && phi_Na < 0.00001 && phi_nm1 <= psi_s_min / 2.0 && bf) {
+    bottom_melt_simple(c);
+  } else if (Na > 1 && phi_Na < 0.00001 && phi_nm1 <= psi_s_min / 2.0 && mid_ratio < 1.01 && bf) {
+    bottom_melt_simple(c);
+  } else if (phi_Na > psi_s_min && Na < N && bf) {
+    bottom_growth_simple(g, c);
+  } else if (c.phi[N] > psi_s_min && bf) {
+    bottom_growth(g, c);
+  } else if (th1 > 1.5 * thick_0) {
+    SCV(c, SC_MTO3) = SCV(c, SC_MTO3) - th1;
+    top_grow(g, c);
+    SCV(c, SC_MTO3) = SCV(c, SC_MTO3) + c.thick[1];
+  } else if (th1 < 0.5 * thick_0) {
+    SCV(c, SC_MTO3) = SCV(c, SC_MTO3) - th1;
+    top_melt(g, c);
+    SCV(c, SC_MTO3) = SCV(c, SC_MTO3) + c.thick[1];
+  }
+}
+
+}  // namespace samsim

@@ -1,0 +1,830 @@
+// samsim_b200.cu -- step kernel and the C ABI of include/samsim_b200.h.
+//
+// Build (see __graft_entry__.build): nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo
+// There is no CPU fallback: without a CUDA device samsim_b200_create returns SAMSIM_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/samsim_b200.h"
+#include "step.cuh"
+
+using namespace samsim;
+
+static_assert((int)SAMSIM_SC_COUNT == (int)SC_COUNT, "scalar ids out of sync with include/samsim_b200.h");
+static_assert((int)SAMSIM_ARR_COUNT == (int)AR_STATE_COUNT, "array ids out of sync with include/samsim_b200.h");
+static_assert((int)SAMSIM_INT_COUNT == (int)IN_COUNT, "int ids out of sync with include/samsim_b200.h");
+static_assert((int)SAMSIM_SNAPSC_COUNT == 20 && (int)SAMSIM_SNAPARR_COUNT == 10, "snapshot layout");
+
+#ifndef SAMSIM_BLOCK
+#define SAMSIM_BLOCK 128
+#endif
+#define SAMSIM_MAXWIN 24   // forcing records staged per launch (3-hourly): 22 * 10800 s of model time per launch
+#define SAMSIM_MAXSITE 16
+
+// ------------------------------------------------------------------------------------------
+// kernel parameters
+// ------------------------------------------------------------------------------------------
+struct KParams {
+  DevCfg cfg;
+  double* arr;   // [AR_COUNT][LS][ncol_pad]
+  double* sc;    // [SC_COUNT][ncol_pad]
+  int* in;       // [IN_COUNT][ncol_pad]
+  long long ncol, ncol_pad;
+  int LS;
+  // clock at launch
+  double time;
+  long long i;
+  int n_time_out, time_counter;
+  int nsteps;
+  // forcing
+  const double* series;   // [nsite][4][nrec] global
+  int nsite, nrec, win_first, win_len;
+  const int* site_of_col; // [ncol_pad] or nullptr
+  const double* fscale;   // [4][ncol_pad] or nullptr
+  const double* foffset;  // [4][ncol_pad] or nullptr
+  const double* lab;      // [nset][4][lab_nrec]
+  long long lab_nrec;
+  const int* set_of_col;
+  // snapshot
+  double* snap_sc;
+  double* snap_arr;
+};
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem_src));
+}
+
+__global__ void __launch_bounds__(SAMSIM_BLOCK) samsim_step_kernel(const __grid_constant__ KParams p) {
+  __shared__ double s_win[SAMSIM_MAXSITE * 4 * SAMSIM_MAXWIN];
+  // stage the forcing window: records win_first .. win_first+win_len-1 of every site/kind (cp.async)
+  if (p.series != nullptr) {
+    const int n = p.nsite * 4 * p.win_len;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      const int sk = e / p.win_len, r = e - sk * p.win_len;
+      cp_async8(&s_win[e], p.series + (size_t)sk * p.nrec + (p.win_first - 1 + r));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
+  }
+  __syncthreads();
+
+  const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= p.ncol) return;
+  const size_t ls = (size_t)p.ncol_pad;
+  const size_t astr = (size_t)p.LS * ls;
+
+  Col c;
+  double* base = p.arr + col;
+#define BIND(field, id) c.field.p = base + (size_t)(id)*astr; c.field.ls = ls;
+  BIND(m, AR_M) BIND(S_abs, AR_S_ABS) BIND(H_abs, AR_H_ABS) BIND(thick, AR_THICK) BIND(T, AR_T) BIND(phi, AR_PHI)
+  BIND(S_bu, AR_S_BU) BIND(psi_s, AR_PSI_S) BIND(psi_l, AR_PSI_L) BIND(psi_g, AR_PSI_G) BIND(ray, AR_RAY)
+  BIND(perm, AR_PERM) BIND(flush_v, AR_FLUSH_V) BIND(flush_h, AR_FLUSH_H) BIND(fl_Q, AR_FL_Q)
+  BIND(S_br, AR_S_BR) BIND(V_ex, AR_V_EX) BIND(fl_m, AR_FL_M) BIND(w0, AR_W0) BIND(w1, AR_W1) BIND(w2, AR_W2)
+  BIND(w3, AR_W3)
+#undef BIND
+  for (int q = 0; q < SC_COUNT; q++) c.sc[q] = p.sc[(size_t)q * ls + col];
+  c.N_active = p.in[(size_t)IN_N_ACTIVE * ls + col];
+  c.status = p.in[(size_t)IN_STATUS * ls + col];
+  c.styropor_flag = p.in[(size_t)IN_STYROPOR * ls + col];
+  c.time = p.time; c.i = p.i; c.n_time_out = p.n_time_out; c.time_counter = p.time_counter;
+  c.fsw0 = c.fsw1 = c.flw0 = c.flw1 = c.ftime0 = c.ftime1 = 0.0;
+
+  Forcing f;
+  f.win = s_win; f.win_len = p.win_len; f.win_first = p.win_first;
+  f.site = p.site_of_col ? p.site_of_col[col] : 0;
+  for (int k = 0; k < 4; k++) {
+    f.scale[k] = p.fscale ? p.fscale[(size_t)k * ls + col] : 1.0;
+    f.offset[k] = p.foffset ? p.foffset[(size_t)k * ls + col] : 0.0;
+  }
+  f.lab = p.lab; f.lab_nrec = p.lab_nrec;
+  f.lab_set = p.set_of_col ? p.set_of_col[col] : 0;
+
+  SnapOut snap;
+  snap.scalars = p.snap_sc; snap.arrays = p.snap_arr; snap.ncol_pad = ls; snap.col = (int)col;
+
+  if (c.status == 0) {
+    for (int s = 0; s < p.nsteps; s++) {
+      column_step(p.cfg, c, f, s == p.nsteps - 1, snap);
+      if (c.status) break;
+    }
+  }
+
+  for (int q = 0; q < SC_COUNT; q++) p.sc[(size_t)q * ls + col] = c.sc[q];
+  p.in[(size_t)IN_N_ACTIVE * ls + col] = c.N_active;
+  p.in[(size_t)IN_STATUS * ls + col] = c.status;
+  p.in[(size_t)IN_STYROPOR * ls + col] = c.styropor_flag;
+}
+
+// replicate one column (ensemble initialisation)
+__global__ void samsim_broadcast_kernel(double* arr, double* sc, int* in, long long ncol_pad, int LS, int src, int col0,
+                                        int n) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const long long col = col0 + t;
+  if (col == src) return;
+  const size_t ls = (size_t)ncol_pad;
+  for (int a = 0; a < AR_COUNT; a++)
+    for (int k = 0; k < LS; k++) {
+      const size_t o = ((size_t)a * LS + k) * ls;
+      arr[o + col] = arr[o + src];
+    }
+  for (int q = 0; q < SC_COUNT; q++) sc[(size_t)q * ls + col] = sc[(size_t)q * ls + src];
+  for (int q = 0; q < IN_COUNT; q++) in[(size_t)q * ls + col] = in[(size_t)q * ls + src];
+}
+
+// gather a snapshot block into host order: dst[(c*count + id)*ext + (k-1)]
+__global__ void samsim_gather_kernel(const double* src, double* dst, long long ncol_pad, int LS, int count, int ext,
+                                     int col0, int n, int k0) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n * count * ext;
+  if (t >= total) return;
+  // t enumerates (id, k, c) with c fastest so reads are coalesced
+  const int cc = (int)(t % n);
+  const long long r = t / n;
+  const int k = (int)(r % ext);
+  const int id = (int)(r / ext);
+  dst[((size_t)cc * count + id) * ext + k] = src[((size_t)id * LS + (k + k0)) * (size_t)ncol_pad + col0 + cc];
+}
+__global__ void samsim_scatter_kernel(double* dstdev, const double* srchost, long long ncol_pad, int LS, int id, int ext,
+                                      int col0, int n) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n * ext;
+  if (t >= total) return;
+  const int cc = (int)(t % n);
+  const int k = (int)(t / n);
+  dstdev[((size_t)id * LS + (k + 1)) * (size_t)ncol_pad + col0 + cc] = srchost[(size_t)cc * ext + k];
+}
+
+// block partial reductions for reduce_diag: out[block][6][3]
+__global__ void samsim_reduce_kernel(const double* sc, const int* in, long long ncol, long long ncol_pad, double* out) {
+  __shared__ double sh[6][3][128];
+  const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ids[5] = {SC_THICKNESS, SC_BULK_SALIN, SC_FREEBOARD, SC_THICK_SNOW, SC_T_TOP};
+  for (int j = 0; j < 6; j++) {
+    double v = 0.0, mn = 1e300, mx = -1e300;
+    if (col < ncol) {
+      v = (j < 5) ? sc[(size_t)ids[j] * ncol_pad + col] : (double)in[(size_t)IN_N_ACTIVE * ncol_pad + col];
+      mn = v; mx = v;
+    }
+    sh[j][0][threadIdx.x] = v; sh[j][1][threadIdx.x] = mn; sh[j][2][threadIdx.x] = mx;
+  }
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s)
+      for (int j = 0; j < 6; j++) {
+        sh[j][0][threadIdx.x] += sh[j][0][threadIdx.x + s];
+        sh[j][1][threadIdx.x] = fmin(sh[j][1][threadIdx.x], sh[j][1][threadIdx.x + s]);
+        sh[j][2][threadIdx.x] = fmax(sh[j][2][threadIdx.x], sh[j][2][threadIdx.x + s]);
+      }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    for (int j = 0; j < 6; j++)
+      for (int q = 0; q < 3; q++) out[((size_t)blockIdx.x * 6 + j) * 3 + q] = sh[j][q][0];
+}
+
+__global__ void samsim_count_failed_kernel(const int* in, long long ncol, long long ncol_pad, int* out) {
+  const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col < ncol && in[(size_t)IN_STATUS * ncol_pad + col] != 0) atomicAdd(out, 1);
+}
+
+// ---- KAT kernels -----------------------------------------------------------------------------
+__device__ void fill_liquidus(DevCfg& g, int salt_flag) {
+  g.salt_flag = salt_flag;
+  if (salt_flag == 1) { g.c2 = -18.7; g.c3 = -0.519; g.c4 = -0.00535; g.d2 = -21.4; g.d3x2 = 2.0 * -0.886; g.d4x3 = 3.0 * -0.0170; }
+  else { g.c2 = -17.6; g.c3 = -0.389; g.c4 = -0.00362; g.d2 = -17.6; g.d3x2 = 2.0 * -0.389; g.d4x3 = 3.0 * -0.00362; }
+}
+__global__ void samsim_kat_getT_kernel(int salt_flag, int n, const double* H, const double* S_bu, const double* T_in,
+                                       double* T_out, double* phi_out, int* st) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  DevCfg g;
+  fill_liquidus(g, salt_flag);
+  double T = 0.0, phi = 0.0;
+  int status = 0;
+  getT(g, H[q], S_bu[q], T_in[q], T, phi, status);
+  T_out[q] = T; phi_out[q] = phi; st[q] = status;
+}
+__global__ void samsim_kat_scalar_kernel(int fn, int salt_flag, int n, const double* a, const double* b, double* out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  DevCfg g;
+  fill_liquidus(g, salt_flag);
+  double r;
+  switch (fn) {
+    case 0: r = S_br_of(g, a[q]); break;
+    case 1: r = S_br_of(g, a[q], b[q]); break;
+    case 2: r = ddT_S_br_of(g, a[q]); break;
+    case 3: r = density_of(a[q], b[q]); break;
+    case 4: r = T_freeze_of(a[q], salt_flag); break;
+    case 5: r = k_snow_of(a[q], b[q]); break;
+    case 6: r = albedo_of(a[q], b[q], 0.1, 0.005, 2); break;
+    case 7: r = det_pow(a[q], b[q]); break;
+    case 8: r = det_exp(a[q]); break;
+    case 9: r = det_sin(a[q]); break;
+    default: r = nan("");
+  }
+  out[q] = r;
+}
+
+// FP64 peak: 8 independent fma chains per thread (explicit fma() is not affected by -fmad=false)
+__global__ void samsim_fp64_peak_kernel(double* out, int iters, double seed) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+  const double x = 1.0000001, y = 1e-9;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      a0 = fma(a0, x, y); a1 = fma(a1, x, y); a2 = fma(a2, x, y); a3 = fma(a3, x, y);
+      a4 = fma(a4, x, y); a5 = fma(a5, x, y); a6 = fma(a6, x, y); a7 = fma(a7, x, y);
+    }
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                             \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) return fail(SAMSIM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct samsim_b200_handle_s {
+  samsim_config_t cfg;
+  DevCfg dcfg;
+  int device;
+  long long ncol, ncol_pad;
+  int LS;
+  double* arr = nullptr;
+  double* sc = nullptr;
+  int* in = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  // clock
+  double time = 0.0;
+  long long i = 0;
+  int n_time_out = 0, time_counter = 1;
+  // forcing
+  double* series = nullptr;
+  int nsite = 0, nrec = 0;
+  int* site_of_col = nullptr;
+  double *fscale = nullptr, *foffset = nullptr;
+  double* lab = nullptr;
+  long long lab_nrec = 0;
+  int* set_of_col = nullptr;
+  // snapshot
+  int snap_mode = SAMSIM_SNAP_NONE;
+  double *snap_sc = nullptr, *snap_arr = nullptr;
+  // staging
+  double* stage = nullptr;
+  size_t stage_bytes = 0;
+  long long launches = 0;
+};
+
+static int ensure_stage(samsim_handle_t h, size_t bytes) {
+  if (h->stage_bytes >= bytes) return 0;
+  if (h->stage) cudaFree(h->stage);
+  h->stage = nullptr;
+  h->stage_bytes = 0;
+  CU(cudaMalloc(&h->stage, bytes));
+  h->stage_bytes = bytes;
+  return 0;
+}
+
+static double host_time_input(int k) { return ((double)(float)k - 1.0) * 3600.0 * 3.0; }
+
+extern "C" {
+
+const char* samsim_b200_last_error(void) { return g_err.c_str(); }
+const char* samsim_b200_version(void) { return "samsim_b200 0.1 (sm_100a, fp64, fmad=false)"; }
+
+int samsim_b200_create(const samsim_config_t* cfg, int32_t ncol, int32_t device, samsim_handle_t* out) {
+  if (!cfg || !out || ncol < 1) return fail(SAMSIM_ERR_ARG, "create: bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+    return fail(SAMSIM_ERR_NO_DEVICE, "no CUDA device: samsim_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(SAMSIM_ERR_ARG, "create: bad device index");
+  if (cfg->Nlayer < 3 || cfg->Nlayer != cfg->N_top + cfg->N_middle + cfg->N_bottom || cfg->N_top < 3)
+    return fail(SAMSIM_ERR_CONFIG, "Nlayer must equal N_top+N_middle+N_bottom with N_top >= 3 (mo_init.f90:2014-2017)");
+  if (cfg->prescribe_flag == 2) return fail(SAMSIM_ERR_CONFIG, "prescribe_flag 2 is not implemented (SURVEY 8f-4)");
+  if (!(cfg->salt_flag == 1 || cfg->salt_flag == 2)) return fail(SAMSIM_ERR_CONFIG, "salt_flag must be 1 or 2");
+  if (!(cfg->dt > 0.0) || !(cfg->thick_0 > 0.0)) return fail(SAMSIM_ERR_CONFIG, "dt and thick_0 must be positive");
+  CU(cudaSetDevice(device));
+  samsim_handle_t h = new samsim_b200_handle_s();
+  h->cfg = *cfg;
+  h->device = device;
+  h->ncol = ncol;
+  h->ncol_pad = ((long long)ncol + 127) / 128 * 128;
+  h->LS = cfg->Nlayer + 2;
+  DevCfg& d = h->dcfg;
+  memset(&d, 0, sizeof d);
+  d.testcase = cfg->testcase; d.Nlayer = cfg->Nlayer; d.N_top = cfg->N_top; d.N_middle = cfg->N_middle; d.N_bottom = cfg->N_bottom;
+  d.atmoflux_flag = cfg->atmoflux_flag; d.grav_flag = cfg->grav_flag; d.prescribe_flag = cfg->prescribe_flag;
+  d.grav_heat_flag = cfg->grav_heat_flag; d.flush_heat_flag = cfg->flush_heat_flag; d.turb_flag = cfg->turb_flag;
+  d.salt_flag = cfg->salt_flag; d.boundflux_flag = cfg->boundflux_flag; d.flush_flag = cfg->flush_flag;
+  d.flood_flag = cfg->flood_flag; d.bottom_flag = cfg->bottom_flag; d.precip_flag = cfg->precip_flag;
+  d.harmonic_flag = cfg->harmonic_flag; d.tank_flag = cfg->tank_flag; d.albedo_flag = cfg->albedo_flag;
+  d.lab_snow_flag = cfg->lab_snow_flag; d.freeboard_snow_flag = cfg->freeboard_snow_flag;
+  d.snow_flush_flag = cfg->snow_flush_flag; d.snow_precip_flag = cfg->snow_precip_flag;
+  d.i_time_out = cfg->i_time_out;
+  d.dt = cfg->dt; d.thick_0 = cfg->thick_0; d.thick_min = cfg->thick_min; d.time_out = cfg->time_out;
+  d.alpha_flux_instable = cfg->alpha_flux_instable; d.alpha_flux_stable = cfg->alpha_flux_stable; d.m_total = cfg->m_total;
+  d.max_flux_plate = cfg->max_flux_plate; d.k_snow_flush = cfg->k_snow_flush; d.k_styropor = cfg->k_styropor;
+  if (cfg->salt_flag == 1) {  // mo_thermo_functions.f90:321-326 / :393-397
+    d.c2 = -18.7; d.c3 = -0.519; d.c4 = -0.00535; d.d2 = -21.4; d.d3x2 = 2.0 * -0.886; d.d4x3 = 3.0 * -0.0170;
+  } else {                    // :331-336 / :398-402
+    d.c2 = -17.6; d.c3 = -0.389; d.c4 = -0.00362; d.d2 = -17.6; d.d3x2 = 2.0 * -0.389; d.d4x3 = 3.0 * -0.00362;
+  }
+  const size_t narr = (size_t)AR_COUNT * h->LS * h->ncol_pad;
+  cudaError_t e;
+  if ((e = cudaMalloc(&h->arr, narr * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(&h->sc, (size_t)SC_COUNT * h->ncol_pad * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(&h->in, (size_t)IN_COUNT * h->ncol_pad * sizeof(int))) != cudaSuccess) {
+    samsim_b200_destroy(h);
+    return fail(SAMSIM_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  cudaMemset(h->arr, 0, narr * sizeof(double));
+  cudaMemset(h->sc, 0, (size_t)SC_COUNT * h->ncol_pad * sizeof(double));
+  cudaMemset(h->in, 0, (size_t)IN_COUNT * h->ncol_pad * sizeof(int));
+  cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  cudaEventCreate(&h->ev0);
+  cudaEventCreate(&h->ev1);
+  *out = h;
+  return SAMSIM_OK;
+}
+
+void samsim_b200_destroy(samsim_handle_t h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->arr); cudaFree(h->sc); cudaFree(h->in); cudaFree(h->series); cudaFree(h->site_of_col);
+  cudaFree(h->fscale); cudaFree(h->foffset); cudaFree(h->lab); cudaFree(h->set_of_col); cudaFree(h->snap_sc);
+  cudaFree(h->snap_arr); cudaFree(h->stage);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int32_t samsim_b200_array_extent(samsim_handle_t h, int32_t id) {
+  if (!h || id < 0 || id >= SAMSIM_ARR_COUNT) return -1;
+  if (id == SAMSIM_ARR_RAY) return h->cfg.Nlayer - 1;
+  if (id == SAMSIM_ARR_FL_Q) return h->cfg.Nlayer + 1;
+  return h->cfg.Nlayer;
+}
+
+static int check_cols(samsim_handle_t h, int32_t col0, int32_t n) {
+  if (!h) return fail(SAMSIM_ERR_ARG, "null handle");
+  if (col0 < 0 || n < 0 || (long long)col0 + n > h->ncol) return fail(SAMSIM_ERR_ARG, "column range out of bounds");
+  return 0;
+}
+
+int samsim_b200_set_array(samsim_handle_t h, int32_t id, const double* host, int32_t col0, int32_t n) {
+  int rc = check_cols(h, col0, n);
+  if (rc) return rc;
+  const int ext = samsim_b200_array_extent(h, id);
+  if (ext < 0 || !host) return fail(SAMSIM_ERR_ARG, "set_array: bad id or null pointer");
+  if (n == 0) return 0;
+  CU(cudaSetDevice(h->device));
+  const size_t bytes = (size_t)n * ext * sizeof(double);
+  if ((rc = ensure_stage(h, bytes))) return rc;
+  CU(cudaMemcpyAsync(h->stage, host, bytes, cudaMemcpyHostToDevice, h->stream));
+  const long long total = (long long)n * ext;
+  samsim_scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->arr, h->stage, h->ncol_pad, h->LS, id, ext, col0, n);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int samsim_b200_get_array(samsim_handle_t h, int32_t id, double* host, int32_t col0, int32_t n) {
+  int rc = check_cols(h, col0, n);
+  if (rc) return rc;
+  const int ext = samsim_b200_array_extent(h, id);
+  if (ext < 0 || !host) return fail(SAMSIM_ERR_ARG, "get_array: bad id or null pointer");
+  if (n == 0) return 0;
+  CU(cudaSetDevice(h->device));
+  const size_t bytes = (size_t)n * ext * sizeof(double);
+  if ((rc = ensure_stage(h, bytes))) return rc;
+  const long long total = (long long)n * ext;
+  samsim_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->arr + (size_t)id * h->LS * h->ncol_pad, h->stage, h->ncol_pad, h->LS, 1, ext, col0, n, 1);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(host, h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int samsim_b200_set_scalar(samsim_handle_t h, int32_t id, const double* host, int32_t col0, int32_t n) {
+  int rc = check_cols(h, col0, n);
+  if (rc) return rc;
+  if (id < 0 || id >= SAMSIM_SC_COUNT || !host) return fail(SAMSIM_ERR_ARG, "set_scalar: bad id or null pointer");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->sc + (size_t)id * h->ncol_pad + col0, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int samsim_b200_get_scalar(samsim_handle_t h, int32_t id, double* host, int32_t col0, int32_t n) {
+  int rc = check_cols(h, col0, n);
+  if (rc) return rc;
+  if (id < 0 || id >= SAMSIM_SC_COUNT || !host) return fail(SAMSIM_ERR_ARG, "get_scalar: bad id or null pointer");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(host, h->sc + (size_t)id * h->ncol_pad + col0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int samsim_b200_set_int(samsim_handle_t h, int32_t id, const int32_t* host, int32_t col0, int32_t n) {
+  int rc = check_cols(h, col0, n);
+  if (rc) return rc;
+  if (id < 0 || id >= SAMSIM_INT_COUNT || !host) return fail(SAMSIM_ERR_ARG, "set_int: bad id or null pointer");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->in + (size_t)id * h->ncol_pad + col0, host, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int samsim_b200_get_int(samsim_handle_t h, int32_t id, int32_t* host, int32_t col0, int32_t n) {
+  int rc = check_cols(h, col0, n);
+  if (rc) return rc;
+  if (id < 0 || id >= SAMSIM_INT_COUNT || !host) return fail(SAMSIM_ERR_ARG, "get_int: bad id or null pointer");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(host, h->in + (size_t)id * h->ncol_pad + col0, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int samsim_b200_broadcast_column(samsim_handle_t h, int32_t src, int32_t col0, int32_t n) {
+  int rc = check_cols(h, col0, n);
+  if (rc) return rc;
+  if (src < 0 || src >= h->ncol) return fail(SAMSIM_ERR_ARG, "broadcast: bad source column");
+  if (n == 0) return 0;
+  CU(cudaSetDevice(h->device));
+  samsim_broadcast_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->arr, h->sc, h->in, h->ncol_pad, h->LS, src, col0, n);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int samsim_b200_set_clock(samsim_handle_t h, double time, int64_t i, int32_t n_time_out, int32_t time_counter) {
+  if (!h) return fail(SAMSIM_ERR_ARG, "null handle");
+  if (time_counter < 1) return fail(SAMSIM_ERR_ARG, "time_counter is 1-based");
+  h->time = time; h->i = i; h->n_time_out = n_time_out; h->time_counter = time_counter;
+  return 0;
+}
+int samsim_b200_get_clock(samsim_handle_t h, double* time, int64_t* i, int32_t* n_time_out, int32_t* time_counter) {
+  if (!h) return fail(SAMSIM_ERR_ARG, "null handle");
+  if (time) *time = h->time;
+  if (i) *i = h->i;
+  if (n_time_out) *n_time_out = h->n_time_out;
+  if (time_counter) *time_counter = h->time_counter;
+  return 0;
+}
+
+int samsim_b200_set_forcing(samsim_handle_t h, int32_t nsite, int32_t nrec, const double* series, const int32_t* site_of_col,
+                            const double* scale, const double* offset) {
+  if (!h || !series || nsite < 1 || nsite > SAMSIM_MAXSITE || nrec < 2) return fail(SAMSIM_ERR_ARG, "set_forcing: bad argument (nsite <= 16)");
+  CU(cudaSetDevice(h->device));
+  cudaFree(h->series); cudaFree(h->site_of_col); cudaFree(h->fscale); cudaFree(h->foffset);
+  h->series = nullptr; h->site_of_col = nullptr; h->fscale = nullptr; h->foffset = nullptr;
+  const size_t nb = (size_t)nsite * 4 * nrec * sizeof(double);
+  CU(cudaMalloc(&h->series, nb));
+  CU(cudaMemcpy(h->series, series, nb, cudaMemcpyHostToDevice));
+  h->nsite = nsite; h->nrec = nrec;
+  if (site_of_col) {
+    for (long long c = 0; c < h->ncol; c++)
+      if (site_of_col[c] < 0 || site_of_col[c] >= nsite) return fail(SAMSIM_ERR_ARG, "set_forcing: site index out of range");
+    CU(cudaMalloc(&h->site_of_col, (size_t)h->ncol_pad * sizeof(int)));
+    CU(cudaMemset(h->site_of_col, 0, (size_t)h->ncol_pad * sizeof(int)));
+    CU(cudaMemcpy(h->site_of_col, site_of_col, (size_t)h->ncol * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  for (int w = 0; w < 2; w++) {
+    const double* src = w ? offset : scale;
+    if (!src) continue;
+    double** dst = w ? &h->foffset : &h->fscale;
+    CU(cudaMalloc(dst, (size_t)4 * h->ncol_pad * sizeof(double)));
+    CU(cudaMemset(*dst, 0, (size_t)4 * h->ncol_pad * sizeof(double)));
+    CU(cudaMemcpy2D(*dst, (size_t)h->ncol_pad * sizeof(double), src, (size_t)h->ncol * sizeof(double), (size_t)h->ncol * sizeof(double), 4, cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+int samsim_b200_set_lab_forcing(samsim_handle_t h, int32_t nset, int64_t nrec, const double* series, const int32_t* set_of_col) {
+  if (!h || !series || nset < 1 || nrec < 1) return fail(SAMSIM_ERR_ARG, "set_lab_forcing: bad argument");
+  CU(cudaSetDevice(h->device));
+  cudaFree(h->lab); cudaFree(h->set_of_col);
+  h->lab = nullptr; h->set_of_col = nullptr;
+  const size_t nb = (size_t)nset * 4 * nrec * sizeof(double);
+  CU(cudaMalloc(&h->lab, nb));
+  CU(cudaMemcpy(h->lab, series, nb, cudaMemcpyHostToDevice));
+  if (h->cfg.snow_precip_flag == 0) {  // mo_grotz.f90:147-149
+    for (int s = 0; s < nset; s++) CU(cudaMemset(h->lab + ((size_t)s * 4 + 1) * nrec, 0, (size_t)nrec * sizeof(double)));
+  }
+  h->lab_nrec = nrec;
+  if (set_of_col) {
+    for (long long c = 0; c < h->ncol; c++)
+      if (set_of_col[c] < 0 || set_of_col[c] >= nset) return fail(SAMSIM_ERR_ARG, "set_lab_forcing: set index out of range");
+    CU(cudaMalloc(&h->set_of_col, (size_t)h->ncol_pad * sizeof(int)));
+    CU(cudaMemset(h->set_of_col, 0, (size_t)h->ncol_pad * sizeof(int)));
+    CU(cudaMemcpy(h->set_of_col, set_of_col, (size_t)h->ncol * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+// advance the host copy of the clock by one step exactly like the device does
+static inline void clock_tick(samsim_handle_t h) {
+  h->i += 1;
+  const bool out = (h->n_time_out == h->cfg.i_time_out || h->i == 1);
+  if (h->cfg.atmoflux_flag == 2 && h->time > host_time_input(h->time_counter)) h->time_counter += 1;
+  h->n_time_out = out ? 0 : h->n_time_out + 1;
+  h->time = h->time + h->cfg.dt;
+}
+
+int64_t samsim_b200_steps_to_next_output(samsim_handle_t h) {
+  if (!h) return -1;
+  if (h->i == 0) return 1;
+  return (int64_t)(h->cfg.i_time_out - h->n_time_out) + 1;
+}
+
+int samsim_b200_step(samsim_handle_t h, int64_t nsteps) {
+  if (!h || nsteps < 0) return fail(SAMSIM_ERR_ARG, "step: bad argument");
+  if (nsteps == 0) return 0;
+  const bool need_forcing = (h->cfg.atmoflux_flag == 2);
+  const bool need_lab = (h->cfg.testcase >= 101 && h->cfg.testcase <= 105) || (h->cfg.boundflux_flag == 3 && h->cfg.lab_snow_flag == 1);
+  if (need_forcing && !h->series) return fail(SAMSIM_ERR_STATE, "step: atmoflux_flag 2 needs samsim_b200_set_forcing first");
+  if (need_lab && !h->lab) return fail(SAMSIM_ERR_STATE, "step: lab testcases need samsim_b200_set_lab_forcing first");
+  CU(cudaSetDevice(h->device));
+  CU(cudaEventRecord(h->ev0, h->stream));
+  int64_t left = nsteps;
+  while (left > 0) {
+    // how many steps fit the staged forcing window?
+    KParams p;
+    memset(&p, 0, sizeof p);
+    p.cfg = h->dcfg;
+    p.arr = h->arr; p.sc = h->sc; p.in = h->in;
+    p.ncol = h->ncol; p.ncol_pad = h->ncol_pad; p.LS = h->LS;
+    p.time = h->time; p.i = h->i; p.n_time_out = h->n_time_out; p.time_counter = h->time_counter;
+    int64_t chunk = left;
+    if (chunk > 1000000) chunk = 1000000;
+    if (need_forcing) {
+      // simulate the clock to find the records the launch touches
+      const int tc0 = h->time_counter;
+      double t = h->time;
+      int tc = tc0;
+      int64_t s = 0;
+      const int first = (tc0 > 1) ? tc0 - 1 : 1;
+      for (; s < chunk; s++) {
+        int tcn = tc;
+        if (t > host_time_input(tcn)) tcn++;
+        if (tcn - first + 1 > SAMSIM_MAXWIN) break;
+        if (tcn > h->nrec) {
+          if (s == 0) return fail(SAMSIM_ERR_STATE, "step: forcing series exhausted (time beyond the last record)");
+          break;
+        }
+        tc = tcn;
+        t = t + h->cfg.dt;
+      }
+      chunk = s;
+      p.series = h->series; p.nsite = h->nsite; p.nrec = h->nrec;
+      p.win_first = first;
+      p.win_len = tc - first + 1;
+      if (p.win_len < 1) p.win_len = 1;
+      if (p.win_first + p.win_len - 1 > h->nrec) p.win_len = h->nrec - p.win_first + 1;
+      p.site_of_col = h->site_of_col; p.fscale = h->fscale; p.foffset = h->foffset;
+    }
+    if (need_lab) {
+      // records FLOOR(1 + time/dt) for every step of the chunk must exist
+      const double tend = h->time + (double)(chunk - 1) * h->cfg.dt;
+      const long long last = (long long)floor(1 + tend / h->cfg.dt);
+      if (last > h->lab_nrec) {
+        const long long ok = h->lab_nrec - (long long)floor(1 + h->time / h->cfg.dt) + 1;
+        if (ok < 1) return fail(SAMSIM_ERR_STATE, "step: lab series exhausted");
+        if (ok < chunk) chunk = ok;
+      }
+      p.lab = h->lab; p.lab_nrec = h->lab_nrec; p.set_of_col = h->set_of_col;
+    }
+    p.nsteps = (int)chunk;
+    p.snap_sc = (h->snap_mode >= SAMSIM_SNAP_SCALARS) ? h->snap_sc : nullptr;
+    p.snap_arr = (h->snap_mode >= SAMSIM_SNAP_FULL) ? h->snap_arr : nullptr;
+    const unsigned grid = (unsigned)((h->ncol + SAMSIM_BLOCK - 1) / SAMSIM_BLOCK);
+    samsim_step_kernel<<<grid, SAMSIM_BLOCK, 0, h->stream>>>(p);
+    CU(cudaGetLastError());
+    h->launches++;
+    for (int64_t s = 0; s < chunk; s++) clock_tick(h);
+    left -= chunk;
+  }
+  CU(cudaEventRecord(h->ev1, h->stream));
+  h->timed = true;
+  return 0;
+}
+
+int samsim_b200_synchronize(samsim_handle_t h) {
+  if (!h) return fail(SAMSIM_ERR_ARG, "null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int samsim_b200_set_snapshot_mode(samsim_handle_t h, int32_t mode) {
+  if (!h || mode < 0 || mode > 2) return fail(SAMSIM_ERR_ARG, "set_snapshot_mode: bad argument");
+  CU(cudaSetDevice(h->device));
+  if (mode >= SAMSIM_SNAP_SCALARS && !h->snap_sc) {
+    CU(cudaMalloc(&h->snap_sc, (size_t)SAMSIM_SNAPSC_COUNT * h->ncol_pad * sizeof(double)));
+    CU(cudaMemset(h->snap_sc, 0, (size_t)SAMSIM_SNAPSC_COUNT * h->ncol_pad * sizeof(double)));
+  }
+  if (mode >= SAMSIM_SNAP_FULL && !h->snap_arr) {
+    const size_t nb = (size_t)SAMSIM_SNAPARR_COUNT * h->LS * h->ncol_pad * sizeof(double);
+    CU(cudaMalloc(&h->snap_arr, nb));
+    CU(cudaMemset(h->snap_arr, 0, nb));
+  }
+  h->snap_mode = mode;
+  return 0;
+}
+
+int samsim_b200_get_snapshot(samsim_handle_t h, double* scalars, double* arrays, int32_t col0, int32_t n) {
+  int rc = check_cols(h, col0, n);
+  if (rc) return rc;
+  if (h->snap_mode == SAMSIM_SNAP_NONE) return fail(SAMSIM_ERR_STATE, "get_snapshot: snapshot mode is NONE");
+  if (arrays && h->snap_mode < SAMSIM_SNAP_FULL) return fail(SAMSIM_ERR_STATE, "get_snapshot: arrays need SAMSIM_SNAP_FULL");
+  if (n == 0) return 0;
+  CU(cudaSetDevice(h->device));
+  if (scalars) {
+    const size_t bytes = (size_t)n * SAMSIM_SNAPSC_COUNT * sizeof(double);
+    if ((rc = ensure_stage(h, bytes))) return rc;
+    const long long total = (long long)n * SAMSIM_SNAPSC_COUNT;
+    // scalars are [id][ncol_pad]: treat as count=SNAPSC_COUNT arrays of extent 1 with LS=1
+    samsim_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->snap_sc, h->stage, h->ncol_pad, 1, SAMSIM_SNAPSC_COUNT, 1, col0, n, 0);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(scalars, h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  if (arrays) {
+    const int ext = h->cfg.Nlayer;
+    const size_t bytes = (size_t)n * SAMSIM_SNAPARR_COUNT * ext * sizeof(double);
+    if ((rc = ensure_stage(h, bytes))) return rc;
+    const long long total = (long long)n * SAMSIM_SNAPARR_COUNT * ext;
+    samsim_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->snap_arr, h->stage, h->ncol_pad, h->LS, SAMSIM_SNAPARR_COUNT, ext, col0, n, 1);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(arrays, h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  return 0;
+}
+
+int samsim_b200_get_status(samsim_handle_t h, int32_t* status, int32_t col0, int32_t n) {
+  return samsim_b200_get_int(h, SAMSIM_INT_STATUS, status, col0, n);
+}
+
+int samsim_b200_count_failed(samsim_handle_t h, int32_t* nfailed) {
+  if (!h || !nfailed) return fail(SAMSIM_ERR_ARG, "count_failed: bad argument");
+  CU(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = ensure_stage(h, sizeof(int)))) return rc;
+  CU(cudaMemsetAsync(h->stage, 0, sizeof(int), h->stream));
+  samsim_count_failed_kernel<<<(unsigned)((h->ncol + 255) / 256), 256, 0, h->stream>>>(h->in, h->ncol, h->ncol_pad, (int*)h->stage);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(nfailed, h->stage, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int samsim_b200_reduce_diag(samsim_handle_t h, double* out18) {
+  if (!h || !out18) return fail(SAMSIM_ERR_ARG, "reduce_diag: bad argument");
+  CU(cudaSetDevice(h->device));
+  const unsigned nb = (unsigned)((h->ncol + 127) / 128);
+  int rc;
+  if ((rc = ensure_stage(h, (size_t)nb * 18 * sizeof(double)))) return rc;
+  samsim_reduce_kernel<<<nb, 128, 0, h->stream>>>(h->sc, h->in, h->ncol, h->ncol_pad, h->stage);
+  CU(cudaGetLastError());
+  std::vector<double> part((size_t)nb * 18);
+  CU(cudaMemcpyAsync(part.data(), h->stage, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int j = 0; j < 6; j++) {
+    double s = 0.0, mn = 1e300, mx = -1e300;
+    for (unsigned b = 0; b < nb; b++) {
+      s += part[((size_t)b * 6 + j) * 3 + 0];
+      mn = fmin(mn, part[((size_t)b * 6 + j) * 3 + 1]);
+      mx = fmax(mx, part[((size_t)b * 6 + j) * 3 + 2]);
+    }
+    out18[3 * j + 0] = s; out18[3 * j + 1] = mn; out18[3 * j + 2] = mx;
+  }
+  return 0;
+}
+
+int64_t samsim_b200_launch_count(samsim_handle_t h) { return h ? h->launches : -1; }
+
+int samsim_b200_last_step_ms(samsim_handle_t h, float* ms) {
+  if (!h || !ms) return fail(SAMSIM_ERR_ARG, "last_step_ms: bad argument");
+  if (!h->timed) return fail(SAMSIM_ERR_STATE, "last_step_ms: no step yet");
+  CU(cudaSetDevice(h->device));
+  CU(cudaEventSynchronize(h->ev1));
+  CU(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return 0;
+}
+
+int samsim_b200_device_layout(samsim_handle_t h, void** arrays, void** scalars, void** ints, int64_t* ncol_pad, int64_t* lstride) {
+  if (!h) return fail(SAMSIM_ERR_ARG, "null handle");
+  if (arrays) *arrays = h->arr;
+  if (scalars) *scalars = h->sc;
+  if (ints) *ints = h->in;
+  if (ncol_pad) *ncol_pad = h->ncol_pad;
+  if (lstride) *lstride = h->LS;
+  return 0;
+}
+
+// ---- KATs -------------------------------------------------------------------------------------
+static int kat_common(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(SAMSIM_ERR_NO_DEVICE, "no CUDA device: samsim_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(SAMSIM_ERR_ARG, "bad device index");
+  CU(cudaSetDevice(device));
+  return 0;
+}
+
+int samsim_b200_kat_getT(int32_t salt_flag, int32_t n, const double* H, const double* S_bu, const double* T_in, double* T_out,
+                         double* phi_out, int32_t* status_out, int32_t device) {
+  int rc = kat_common(device);
+  if (rc) return rc;
+  if (n < 1 || !H || !S_bu || !T_in || !T_out || !phi_out) return fail(SAMSIM_ERR_ARG, "kat_getT: bad argument");
+  double* d = nullptr;
+  int* ds = nullptr;
+  const size_t nb = (size_t)n * sizeof(double);
+  CU(cudaMalloc(&d, 5 * nb));
+  CU(cudaMalloc(&ds, (size_t)n * sizeof(int)));
+  CU(cudaMemcpy(d, H, nb, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d + n, S_bu, nb, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d + 2 * (size_t)n, T_in, nb, cudaMemcpyHostToDevice));
+  samsim_kat_getT_kernel<<<(n + 127) / 128, 128>>>(salt_flag, n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, d + 4 * (size_t)n, ds);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(T_out, d + 3 * (size_t)n, nb, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(phi_out, d + 4 * (size_t)n, nb, cudaMemcpyDeviceToHost));
+  if (status_out) CU(cudaMemcpy(status_out, ds, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  cudaFree(ds);
+  return 0;
+}
+
+int samsim_b200_kat_scalar(int32_t fn, int32_t salt_flag, int32_t n, const double* a, const double* b, double* out, int32_t device) {
+  int rc = kat_common(device);
+  if (rc) return rc;
+  if (n < 1 || !a || !out) return fail(SAMSIM_ERR_ARG, "kat_scalar: bad argument");
+  double* d = nullptr;
+  const size_t nb = (size_t)n * sizeof(double);
+  CU(cudaMalloc(&d, 3 * nb));
+  CU(cudaMemcpy(d, a, nb, cudaMemcpyHostToDevice));
+  if (b) CU(cudaMemcpy(d + n, b, nb, cudaMemcpyHostToDevice));
+  else CU(cudaMemset(d + n, 0, nb));
+  samsim_kat_scalar_kernel<<<(n + 127) / 128, 128>>>(fn, salt_flag, n, d, d + n, d + 2 * (size_t)n);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, d + 2 * (size_t)n, nb, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return 0;
+}
+
+int samsim_b200_fp64_peak(int32_t device, double seconds, double* tflops) {
+  int rc = kat_common(device);
+  if (rc) return rc;
+  if (!tflops) return fail(SAMSIM_ERR_ARG, "fp64_peak: bad argument");
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256;
+  double* d = nullptr;
+  CU(cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  int iters = 2000;
+  double best = 0.0, elapsed_total = 0.0;
+  samsim_fp64_peak_kernel<<<blocks, threads>>>(d, 100, 1.0);  // warm-up
+  CU(cudaDeviceSynchronize());
+  while (elapsed_total < seconds * 1000.0) {
+    cudaEventRecord(e0);
+    samsim_fp64_peak_kernel<<<blocks, threads>>>(d, iters, 1.0);
+    cudaEventRecord(e1);
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    elapsed_total += ms;
+    const double flop = 2.0 * 64.0 * (double)iters * blocks * threads;  // 8 chains x 8 unroll fma = 64 fma/iter
+    const double tf = flop / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+    if (ms < 50.f) iters *= 2;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,586 @@
+// step.cuh -- one iteration of the reference's time loop (mo_grotz.f90:182-835) for one column,
+// plus the surface energy balance (mo_heat_fluxes.f90:69-312).  See physics.cuh for the
+// arithmetic contract.
+#pragma once
+
+#include "physics.cuh"
+
+namespace samsim {
+
+// forcing tables visible to a thread
+struct Forcing {
+  // atmoflux_flag 2: window of records staged in shared memory, [(site*4 + kind)*win + r]
+  const double* win;      // shared memory
+  int win_len;            // records in the window
+  int win_first;          // 1-based record number of window element 0
+  int site;               // this column's site
+  double scale[4], offset[4];  // kind order: fl_sw, fl_lw, T2m, precip
+  // lab series in global memory, [(set*4 + kind)*nrec + r], kinds Tice, snowfall, heat, styropor
+  const double* lab;
+  long long lab_nrec;
+  int lab_set;
+};
+
+__device__ __forceinline__ double forcing_rec(const Forcing& f, int kind, int rec /*1-based*/) {
+  const double base = f.win[(f.site * 4 + kind) * f.win_len + (rec - f.win_first)];
+  return base * f.scale[kind] + f.offset[kind];
+}
+// time_input(k) = (REAL(k)-1._wp)*3600._wp*3._wp, mo_functions.f90:323-325
+__device__ __forceinline__ double time_input(int k) { return ((double)(float)k - 1.0) * 3600.0 * 3.0; }
+__device__ __forceinline__ double lab_rec(const Forcing& f, int kind, long long rec /*1-based*/) {
+  return f.lab[((long long)(f.lab_set * 4 + kind)) * f.lab_nrec + (rec - 1)];
+}
+
+// S0 vital signs, mo_grotz.f90:192-223 (diagnostics; psi_* are the previous step's)
+__device__ __noinline__ void vital_signs(const DevCfg& g, Col& c) {
+  const int Na = c.N_active;
+  double sumH = 0.0, summ = 0.0, sumS = 0.0;
+  for (int k = 1; k <= Na; k++) { sumH = sumH + c.H_abs[k]; summ = summ + c.m[k]; sumS = sumS + c.S_abs[k]; }
+  SCV(c, SC_ENERGY_STORED) = SCV(c, SC_H_ABS_SNOW) + sumH - SCV(c, SC_T_BOTTOM) * summ * c_l;
+  double fw = summ / rho_l;
+  fw = fw * (1.0 - sumS / summ / ref_salinity);
+  fw = fw + SCV(c, SC_M_SNOW) / rho_l;
+  SCV(c, SC_FRESHWATER) = fw;
+  double tr = 0.0;
+  for (int jj = 1; jj <= Na - 1; jj++) tr = tr + c.thick[jj] / (c.psi_l[jj] * k_l + c.psi_s[jj] * k_s);
+  const double thNa = c.thick[Na], psNa = c.psi_s[Na];
+  tr = tr + thNa * psNa / psi_s_min * (psi_s_min * k_s + 1.0 - psi_s_min * k_l);
+  if (SCV(c, SC_THICK_SNOW) > g.thick_min / 110.0) tr = tr + SCV(c, SC_THICK_SNOW) / k_snow_of(SCV(c, SC_M_SNOW), SCV(c, SC_THICK_SNOW));
+  SCV(c, SC_TOTAL_RESIST) = tr;
+  double th = (Na > 1) ? sum_fwd(c.thick, 1, Na - 1) : 0.0;
+  SCV(c, SC_THICKNESS) = th + thNa * psNa / psi_s_min;
+  if (Na > 1) {
+    double b = sum_fwd(c.S_abs, 1, Na - 1) + c.S_abs[Na] * psNa / psi_s_min;
+    b = b / (sum_fwd(c.m, 1, Na - 1) + c.m[Na] * psNa / psi_s_min);
+    SCV(c, SC_BULK_SALIN) = b;
+  } else {
+    SCV(c, SC_BULK_SALIN) = c.S_abs[1] / c.m[1];
+  }
+}
+
+// sub_heat_fluxes, mo_heat_fluxes.f90:69-312
+__device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
+  const int Na = c.N_active;
+  const double dt = g.dt, thick_min = g.thick_min;
+  const double ps1 = c.psi_s[1], pl1 = c.psi_l[1], pg1 = c.psi_g[1], th1 = c.thick[1];
+  double T1 = c.T[1];
+  double& thick_snow = SCV(c, SC_THICK_SNOW);
+  double& T_top = SCV(c, SC_T_TOP);
+  double& fl_q_snow = SCV(c, SC_FL_Q_SNOW);
+  double flQ1 = c.fl_Q[1];
+  double fl_rad_Na = 0.0;  // fl_rad(N_active): 0 unless boundflux 2 recomputes it (fl_rad = 0 from init, mo_init.f90:1988)
+
+  if (g.boundflux_flag == 1) {  // :77-86
+    flQ1 = fl_Q_0_top(ps1, pl1, pg1, th1, T1, T_top);
+    if (fabs(flQ1) > g.max_flux_plate) flQ1 = flQ1 / fabs(flQ1) * g.max_flux_plate;
+  }
+
+  if (g.boundflux_flag == 2) {  // :90-195
+    double& albedo = SCV(c, SC_ALBEDO);
+    double& fl_sw = SCV(c, SC_FL_SW);
+    double& fl_rest = SCV(c, SC_FL_REST);
+    albedo = albedo_of(thick_snow, SCV(c, SC_T_SNOW), pl1, thick_min, g.albedo_flag);
+    if (g.atmoflux_flag == 1) {
+      notzflux(c.time + 86400.0 * 180.0, fl_sw, fl_rest);
+    } else if (g.atmoflux_flag == 2) {  // :97-111
+      double fl_lw;
+      if (c.time == c.ftime1) {
+        fl_sw = c.fsw1;
+        fl_lw = c.flw1;
+      } else {
+        const double temp = (c.time - c.ftime0) / (c.ftime1 - c.ftime0);
+        fl_sw = (1.0 - temp) * c.fsw0 + temp * c.fsw1;
+        fl_lw = (1.0 - temp) * c.flw0 + temp * c.flw1;
+      }
+      SCV(c, SC_FL_LW) = fl_lw;
+      fl_rest = fl_lw + 0.0 + 0.0;  // fl_sen = fl_lat = 0
+    }
+    double T_old, emi, pen;
+    if (thick_snow < thick_min) { T_old = T1; emi = emissivity_ice; pen = penetr; }
+    else { T_old = SCV(c, SC_T_SNOW); emi = emissivity_snow; pen = 0.0; }
+    T_old = T_old + zeroK;
+    double temp1 = (1.0 - albedo) * (1.0 - pen) * fl_sw + fl_rest;  // :135-139
+    temp1 = temp1 + emi * 3.0 * sigma * P4(T_old);
+    temp1 = temp1 / (emi * 4.0 * sigma * P3(T_old));
+    temp1 = temp1 - zeroK;
+    T_old = temp1 + zeroK;  // :141-146
+    temp1 = (1.0 - albedo) * (1.0 - pen) * fl_sw + fl_rest;
+    temp1 = temp1 + emi * 3.0 * sigma * P4(T_old);
+    temp1 = temp1 / (emi * 4.0 * sigma * P3(T_old));
+    temp1 = temp1 - zeroK;
+    T_top = temp1;
+
+    // :151-155 Beer law.  Only fl_rad(N_active) is ever read (:283-284), but the running product
+    // must see every layer in order.  exp() of a repeated thickness is reused (same bits).
+    {
+      double temp2 = pen * (1.0 - albedo) * fl_sw;
+      double last_th = -1.0, last_e = 0.0;
+      for (int k = 1; k <= Na; k++) {
+        const double thk = c.thick[k];
+        if (thk != last_th) { last_e = det_exp(-extinc * thk); last_th = thk; }
+        if (k == Na) fl_rad_Na = temp2 - temp2 * last_e;
+        temp2 = temp2 * last_e;
+      }
+    }
+
+    double& T_freeze = SCV(c, SC_T_FREEZE);
+    if (thick_snow >= thick_min / 100.0) T_freeze = 0.0;  // :158-162
+    else T_freeze = T_freeze_of(c.S_abs[1] / c.m[1], g.salt_flag);
+
+    if (T_top > T_freeze && Na > 1) {  // :167-180
+      temp1 = emi * sigma * P4(T_freeze + zeroK) - (1.0 - albedo) * (1.0 - pen) * fl_sw - fl_rest;
+      if (thick_snow >= thick_min) {
+        fl_q_snow = temp1;
+        flQ1 = fl_Q_snow_ice(SCV(c, SC_M_SNOW), thick_snow, SCV(c, SC_T_SNOW), ps1, pl1, th1, T1);
+      } else if (thick_snow >= thick_min / 100.0) {
+        fl_q_snow = temp1;
+        flQ1 = 0.0;
+      } else {
+        flQ1 = temp1;
+      }
+      T_top = T_freeze;
+    } else {  // :185-193
+      if (thick_snow >= thick_min) {
+        flQ1 = fl_Q_snow_ice(SCV(c, SC_M_SNOW), thick_snow, SCV(c, SC_T_SNOW), ps1, pl1, th1, T1);
+        fl_q_snow = fl_Q_0_snow(SCV(c, SC_M_SNOW), thick_snow, SCV(c, SC_T_SNOW), T_top);
+      } else if (thick_snow > thick_min / 100.0 && thick_snow < thick_min) {
+        flQ1 = 0.0;
+        fl_q_snow = fl_Q_0_snow_thin(SCV(c, SC_M_SNOW), thick_snow, SCV(c, SC_T_SNOW), ps1, pl1, pg1, th1, T_top);
+      } else {
+        flQ1 = fl_Q_0_top(ps1, pl1, pg1, th1, T1, T_top);
+      }
+    }
+  }
+
+  if (g.boundflux_flag == 3) {  // :202-258
+    const double T2m = SCV(c, SC_T2M);
+    double& T_freeze = SCV(c, SC_T_FREEZE);
+    if (g.lab_snow_flag == 0 || thick_snow <= thick_min / 100.0) {
+      T_freeze = f_min(T_freeze_of(c.S_abs[Na] / c.m[Na], g.salt_flag), 0.0);
+      T_top = T1;
+      flQ1 = g.alpha_flux_instable * (T_top - T2m);
+      if (flQ1 < 0.0) {
+        T_top = f_max(T_freeze, T1);
+        flQ1 = g.alpha_flux_stable * (T_top - T2m);
+      }
+      if (thick_snow == 0.0 && g.lab_snow_flag == 1 && c.styropor_flag == 1) flQ1 = flQ1 * g.k_styropor;
+    } else if (g.lab_snow_flag == 1) {
+      T_freeze = T_freeze_of(SCV(c, SC_S_ABS_SNOW) / SCV(c, SC_M_SNOW), g.salt_flag);
+      T_top = SCV(c, SC_T_SNOW);
+      double temp1 = g.alpha_flux_instable * (T_top - T2m);
+      if (temp1 >= 0.0) {
+        if (thick_snow >= thick_min) {
+          fl_q_snow = temp1;
+          flQ1 = fl_Q_snow_ice(SCV(c, SC_M_SNOW), thick_snow, SCV(c, SC_T_SNOW), ps1, pl1, th1, T1);
+        } else if (thick_snow >= thick_min / 100.0) {
+          fl_q_snow = fl_Q_0_snow_thin(SCV(c, SC_M_SNOW), thick_snow, SCV(c, SC_T_SNOW), ps1, pl1, pg1, th1, (T2m + T_top) / 2.0);
+          flQ1 = 0.0;
+        }
+      } else {
+        temp1 = g.alpha_flux_stable * (T_top - T2m);
+        if (thick_snow >= thick_min) {
+          fl_q_snow = temp1;
+          flQ1 = fl_Q_snow_ice(SCV(c, SC_M_SNOW), thick_snow, SCV(c, SC_T_SNOW), ps1, pl1, th1, T1);
+        } else if (thick_snow >= thick_min / 100.0) {
+          fl_q_snow = temp1;
+          flQ1 = 0.0;
+        }
+      }
+    }
+  }
+
+  const double fl_q_bottom = SCV(c, SC_FL_Q_BOTTOM);
+  c.fl_Q[1] = flQ1;
+  c.fl_Q[Na + 1] = fl_q_bottom;  // :262
+
+  // :269-285 in one forward pass: energy sums (forward order), inter-layer fluxes, explicit update.
+  double temp1 = 0.0, temp2 = 0.0;
+  {
+    double fq_k = flQ1;
+    double ps_k = ps1, pl_k = pl1, pg_k = pg1, th_k = th1, T_k = T1;
+    const double rad = fl_rad_Na * dt;
+    for (int k = 1; k <= Na; k++) {
+      double fq_kp1;
+      double ps_n = 0.0, pl_n = 0.0, pg_n = 0.0, th_n = 0.0, T_n = 0.0;
+      if (k < Na) {
+        ps_n = c.psi_s[k + 1]; pl_n = c.psi_l[k + 1]; pg_n = c.psi_g[k + 1]; th_n = c.thick[k + 1]; T_n = c.T[k + 1];
+        fq_kp1 = fl_Q_between(ps_k, pl_k, pg_k, th_k, T_k, ps_n, pl_n, pg_n, th_n, T_n);  // :272-274
+        c.fl_Q[k + 1] = fq_kp1;
+      } else {
+        fq_kp1 = fl_q_bottom;
+      }
+      double H = c.H_abs[k];
+      temp1 = temp1 + H;                 // :269 sum(H_abs) before the update
+      H = H + (fq_kp1 - fq_k) * dt;      // :277-279
+      H = H + rad;                       // :282-285 (sic: fl_rad(N_active) for every layer)
+      c.H_abs[k] = H;
+      temp2 = temp2 + H;                 // :305 sum(H_abs) after the update (layer 1 re-added below if coupling changes it)
+      fq_k = fq_kp1;
+      ps_k = ps_n; pl_k = pl_n; pg_k = pg_n; th_k = th_n; T_k = T_n;
+    }
+    temp1 = temp1 + SCV(c, SC_H_ABS_SNOW);
+    for (int k = 1; k <= Na; k++) temp1 = temp1 + rad;  // :284 temp1 = temp1 + fl_rad(N_active)*dt, N_active times
+  }
+
+  bool layer1_changed = false;
+  if (thick_snow >= thick_min / 100.0 && thick_snow < thick_min) {  // :291-295
+    SCV(c, SC_H_ABS_SNOW) = SCV(c, SC_H_ABS_SNOW) - fl_q_snow * dt;
+    double H1 = c.H_abs[1], phi1 = c.phi[1];
+    snow_coupling(g, c, H1, phi1, T1, c.m[1], c.S_bu[1]);
+    c.H_abs[1] = H1; c.phi[1] = phi1; c.T[1] = T1;
+    layer1_changed = true;
+    temp1 = temp1 + fl_q_bottom * dt - fl_q_snow * dt;
+  } else if (thick_snow >= thick_min) {  // :296-299
+    SCV(c, SC_H_ABS_SNOW) = SCV(c, SC_H_ABS_SNOW) + (flQ1 - fl_q_snow) * dt;
+    temp1 = temp1 + fl_q_bottom * dt - fl_q_snow * dt;
+  } else {
+    temp1 = temp1 + fl_q_bottom * dt - flQ1 * dt;  // :302
+  }
+  if (layer1_changed) temp2 = sum_fwd(c.H_abs, 1, Na);  // forward order requires a fresh pass when H_abs(1) moved
+  temp2 = temp2 + SCV(c, SC_H_ABS_SNOW);
+  if (fabs((temp1 - temp2) / dt) > 0.00001) c.status = 431;  // :307-310
+}
+
+// One loop iteration.  `last_of_launch` makes the S0 diagnostics observable through get_scalar
+// (they are otherwise only consumed by S8); `snap` receives the S8 record.
+struct SnapOut {
+  double* scalars;  // [SNAPSC_COUNT][ncol_pad] or nullptr
+  double* arrays;   // [SNAPARR_COUNT][Nlayer+2][ncol_pad] or nullptr
+  size_t ncol_pad;
+  int col;
+};
+
+__device__ __noinline__ void write_snapshot(const DevCfg& g, const Col& c, const SnapOut& s) {
+  if (s.scalars) {
+    const int ids[19] = {SC_FREEBOARD, SC_THICK_SNOW, SC_T_SNOW, SC_PSI_L_SNOW, SC_PSI_S_SNOW, SC_ENERGY_STORED,
+                         SC_FRESHWATER, SC_TOTAL_RESIST, SC_THICKNESS, SC_BULK_SALIN, SC_GRAV_DRAIN, SC_GRAV_SALT,
+                         SC_GRAV_TEMP, SC_T2M, SC_T_TOP, SC_MTO1, SC_MTO2, SC_MTO3, -1};
+    for (int q = 0; q < 18; q++) s.scalars[(size_t)q * s.ncol_pad + s.col] = c.sc[ids[q]];
+    s.scalars[(size_t)18 * s.ncol_pad + s.col] = c.time;
+    s.scalars[(size_t)19 * s.ncol_pad + s.col] = (double)c.N_active;
+  }
+  if (s.arrays) {
+    const int N = g.Nlayer;
+    const size_t LS = (size_t)(N + 2);
+    const Lay* src[10] = {&c.T, &c.psi_s, &c.thick, &c.S_bu, &c.ray, &c.psi_l, &c.perm, &c.flush_v, &c.flush_h, &c.psi_g};
+    for (int a = 0; a < 10; a++) {
+      double* dst = s.arrays + ((size_t)a * LS) * s.ncol_pad + s.col;
+      const int n = (a == 4) ? N - 1 : N;
+      for (int k = 1; k <= n; k++) dst[(size_t)k * s.ncol_pad] = (*src[a])[k];
+    }
+  }
+}
+
+__device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing& f, bool want_diag, const SnapOut& snap) {
+  const double dt = g.dt;
+  const int N = g.Nlayer;
+  c.i = c.i + 1;
+  const bool output_step = (c.n_time_out == g.i_time_out || c.i == 1);
+
+  // ---- S0 :192-223 (only observable at S8 or through get_scalar after the launch) ----
+  if (output_step || want_diag) vital_signs(g, c);
+
+  // ---- S1 forcing :229-246 ----
+  if (g.atmoflux_flag == 2) {
+    if (c.time > time_input(c.time_counter)) c.time_counter = c.time_counter + 1;
+    const int tc = c.time_counter;
+    c.ftime1 = time_input(tc);
+    c.fsw1 = forcing_rec(f, 0, tc);
+    c.flw1 = forcing_rec(f, 1, tc);
+    if (c.time == c.ftime1) {
+      SCV(c, SC_T2M) = forcing_rec(f, 2, tc);
+      SCV(c, SC_LIQUID_PRECIP) = forcing_rec(f, 3, tc);
+      c.ftime0 = 0.0; c.fsw0 = 0.0; c.flw0 = 0.0;
+    } else {
+      c.ftime0 = time_input(tc - 1);
+      c.fsw0 = forcing_rec(f, 0, tc - 1);
+      c.flw0 = forcing_rec(f, 1, tc - 1);
+      const double temp = (c.time - c.ftime0) / (c.ftime1 - c.ftime0);
+      SCV(c, SC_T2M) = (1.0 - temp) * forcing_rec(f, 2, tc - 1) + temp * forcing_rec(f, 2, tc);
+      SCV(c, SC_LIQUID_PRECIP) = (1.0 - temp) * forcing_rec(f, 3, tc - 1) + temp * forcing_rec(f, 3, tc);
+    }
+  }
+  long long lab_idx = 0;
+  if (g.boundflux_flag == 3 && g.lab_snow_flag == 1) {  // :244-246
+    lab_idx = (long long)floor(1 + c.time / dt);
+    SCV(c, SC_SOLID_PRECIP) = lab_rec(f, 1, lab_idx);
+  }
+
+  // ---- S2 snow fall :251-265 ----
+  {
+    const double lp = SCV(c, SC_LIQUID_PRECIP), sp = SCV(c, SC_SOLID_PRECIP);
+    if (f_max(lp, sp) > 0.0 && (g.precip_flag == 1 || g.precip_flag == 0)) {
+      const bool have_solid = (g.precip_flag == 0);
+      if (c.N_active > 1) {
+        snow_precip(c, dt, lp, SCV(c, SC_T2M), have_solid, sp);
+      } else if (c.N_active == 1) {
+        double H1 = c.H_abs[1], S1 = c.S_abs[1];
+        snow_precip_0(H1, S1, c.m[1], c.T[1], dt, lp, SCV(c, SC_T2M), have_solid, sp);
+        c.H_abs[1] = H1; c.S_abs[1] = S1;
+      }
+    }
+  }
+
+  // ---- S3 snow thermodynamics :273-292 ----
+  snow_block(g, c);
+  if (c.status) return;
+
+  // ---- S4 backward sweep: S_bu, H -> T, phi -> S_br -> volume fractions :298-307 ----
+  {
+    double T_test = SCV(c, SC_T_BOTTOM);
+    for (int k = c.N_active; k >= 1; k--) {
+      const double mk = c.m[k];
+      const double sbu = c.S_abs[k] / mk;
+      const double H = c.H_abs[k] / mk;
+      double T, phi = c.phi[k];
+      getT(g, H, sbu, T_test, T, phi, c.status);
+      T_test = T;
+      c.S_bu[k] = sbu; c.T[k] = T; c.phi[k] = phi;
+      c.S_br[k] = S_br_of(g, T, sbu);
+      double ps, pl, pg, vex;
+      expulsion(phi, c.thick[k], mk, ps, pl, pg, vex);
+      c.psi_s[k] = ps; c.psi_l[k] = pl; c.psi_g[k] = pg; c.V_ex[k] = vex;
+    }
+    if (c.status) return;
+  }
+
+  // ---- S5 expulsion_flux (mo_mass.f90:112-136) then mass_transfer (skipped at i == 1) :312-321 ----
+  {
+    const int Na = c.N_active;
+    Lay fl_m = c.fl_m;
+    double f0 = 0.0;
+    fl_m[1] = 0.0;
+    for (int k = 1; k <= Na; k++) {
+      double f1;
+      const double vex = c.V_ex[k];
+      if (k == 1) {
+        f1 = -vex * rho_l;
+      } else {
+        const double pg = c.psi_g[k];
+        if (pg < SAMSIM_F32(0.001)) {
+          f1 = -vex * rho_l + f0;
+        } else {
+          const double thk = c.thick[k];
+          f1 = -f_max((vex - pg * thk) * rho_l, 0.0);
+          c.psi_g[k] = f_max((pg * thk - vex) / thk, 0.0);
+        }
+      }
+      fl_m[k + 1] = f1;
+      c.m[k] = c.m[k] + f1 - f0;
+      f0 = f1;
+    }
+    if (c.i != 1) mass_transfer(g, c, fl_m);
+    // ---- S7 :333-335 ----
+    for (int k = Na; k >= 1; k--) c.S_bu[k] = c.S_abs[k] / c.m[k];
+  }
+
+  // ---- S8 output :340-398 ----
+  if (output_step) {
+    SCV(c, SC_FREEBOARD) = (c.N_active > 1) ? freeboard_of(g, c) : 0.0;
+    if (g.grav_flag == 2) {
+      if (SCV(c, SC_GRAV_DRAIN) == 0.0) SCV(c, SC_GRAV_TEMP) = 0.0;
+      else SCV(c, SC_GRAV_TEMP) = SCV(c, SC_GRAV_TEMP) / SCV(c, SC_GRAV_DRAIN);
+      SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) / g.time_out;
+      SCV(c, SC_GRAV_DRAIN) = SCV(c, SC_GRAV_DRAIN) / g.time_out;
+    }
+    write_snapshot(g, c, snap);
+    SCV(c, SC_GRAV_DRAIN) = 0.0; SCV(c, SC_GRAV_SALT) = 0.0; SCV(c, SC_GRAV_TEMP) = 0.0;
+    SCV(c, SC_MTO1) = 0.0; SCV(c, SC_MTO2) = 0.0; SCV(c, SC_MTO3) = 0.0;
+    c.n_time_out = 0;
+  } else {
+    c.n_time_out = c.n_time_out + 1;
+  }
+
+  // ---- S9 gas in the lowest layer :405-410 ----
+  {
+    const int Na = c.N_active;
+    const double pg = c.psi_g[Na];
+    if (pg > 0.0) {
+      const double temp2 = pg * c.thick[Na] * rho_l;
+      c.m[Na] = c.m[Na] + temp2;
+      c.S_abs[Na] = c.S_abs[Na] + temp2 * SCV(c, SC_S_BU_BOTTOM);
+      c.H_abs[Na] = c.H_abs[Na] + temp2 * c_l * SCV(c, SC_T_BOTTOM);
+    }
+  }
+
+  // ---- S10 thin snow coupling :418-420 ----
+  if (SCV(c, SC_M_SNOW) > 0.0 && SCV(c, SC_THICK_SNOW) < g.thick_min) {
+    double H1 = c.H_abs[1], phi1 = c.phi[1], T1 = c.T[1];
+    snow_coupling(g, c, H1, phi1, T1, c.m[1], c.S_bu[1]);
+    c.H_abs[1] = H1; c.phi[1] = phi1; c.T[1] = T1;
+    if (c.status) return;
+  }
+
+  // ---- S11 flooding :428-445 ----
+  if (c.N_active > 1 && g.flood_flag > 1) {
+    SCV(c, SC_FREEBOARD) = freeboard_of(g, c);
+    if (SCV(c, SC_FREEBOARD) < 0.0) {
+      if (g.flood_flag == 2) flood(g, c);
+      else if (g.flood_flag == 3 && SCV(c, SC_FREEBOARD) < neg_free) flood_simple(c);
+    }
+  }
+
+  // ---- S12 turbulence (sub_turb_flux, mo_functions.f90:347-363) :450-457 ----
+  if (g.turb_flag == 2) {
+    const int Na = c.N_active;
+    const double S = c.S_abs[Na], mNa = c.m[Na];
+    const double turb = Turb_A * det_exp(Turb_B * (-density_of(SCV(c, SC_T_BOTTOM), SCV(c, SC_S_BU_BOTTOM)) + density_of(c.T[Na], S / mNa))) * dt;
+    c.S_abs[Na] = S - turb * (S / mNa - SCV(c, SC_S_BU_BOTTOM));
+  }
+
+  // ---- S13 gravity drainage :463-477 ----
+  if (g.grav_flag == 2 && c.N_active > 1) grav_drain(g, c);
+  else if (g.grav_flag == 3 && c.N_active > 1) grav_drain_simple(g, c);
+  if (c.status) return;
+
+  // ---- S15 testcase hooks :503-563 ----
+  if (g.testcase == 1) {  // sub_test1, mo_testcase_specifics.f90:42-89
+    const double j = rint(c.time / 43200.0);
+    if (j >= 1.0 && j <= 20.0 && fabs(c.time - 12.0 * j * 3600.0) < SAMSIM_F32(0.01))
+      SCV(c, SC_T_TOP) = (((int)j) & 1) ? SCV(c, SC_TTOP_COLD) : SCV(c, SC_TTOP_WARM);
+  } else if (g.testcase >= 101 && g.testcase <= 105) {  // :521-530
+    const long long idx = (long long)floor(1 + c.time / dt);
+    const double Sb = c.S_bu[c.N_active + 1];
+    SCV(c, SC_T2M) = lab_rec(f, 0, idx);
+    SCV(c, SC_SOLID_PRECIP) = lab_rec(f, 1, idx);
+    SCV(c, SC_FL_Q_BOTTOM) = lab_rec(f, 2, idx);
+    SCV(c, SC_T_BOTTOM) = -SAMSIM_F32(0.0575) * Sb + SAMSIM_F32(1.710523e-3) * det_pow(Sb, 3.0 / 2.0) -
+                          SAMSIM_F32(2.154996e-4) * P2(Sb) - SAMSIM_F32(7.53e-4) * sum_fwd(c.thick, 1, c.N_active - 1);
+    c.styropor_flag = (int)lab_rec(f, 3, idx);
+  } else if (g.testcase == 4 || g.testcase == 7) {  // sub_test4, mo_testcase_specifics.f90:197-202
+    const double amp = SCV(c, SC_OFLUX_AMP);
+    SCV(c, SC_FL_Q_BOTTOM) = -amp * det_sin(c.time * (2.0 * pi_sp) / (86400.0 * 365.0)) + amp;
+  }
+
+  // ---- S16 tank :573-578 ----
+  if (g.tank_flag == 2) {
+    SCV(c, SC_S_BU_BOTTOM) = (SCV(c, SC_S_TOTAL) - sum_fwd(c.S_abs, 1, c.N_active)) / (g.m_total - sum_fwd(c.m, 1, c.N_active));
+  }
+
+  // ---- S17 heat fluxes :584 ----
+  heat_fluxes(g, c);
+  if (c.status) return;
+
+  // ---- S18 second backward sweep :592-598 (psi_* are NOT refreshed) ----
+  {
+    double T_test = SCV(c, SC_T_BOTTOM);
+    for (int k = c.N_active; k >= 1; k--) {
+      const double mk = c.m[k];
+      const double sbu = c.S_abs[k] / mk;
+      const double H = c.H_abs[k] / mk;
+      double T, phi = c.phi[k];
+      getT(g, H, sbu, T_test, T, phi, c.status);
+      T_test = T;
+      c.S_bu[k] = sbu; c.T[k] = T; c.phi[k] = phi;
+    }
+    if (c.status) return;
+  }
+
+  // ---- S19 snow thermodynamics #2 :600-625 ----
+  SCV(c, SC_MELT_THICK_SNOW_OLD) = SCV(c, SC_MELT_THICK_SNOW);
+  snow_block(g, c);
+  if (c.status) return;
+  SCV(c, SC_MELT_THICK_SNOW) = SCV(c, SC_MELT_THICK_SNOW_OLD) + SCV(c, SC_MELT_THICK_SNOW);
+
+  // ---- S20 flushing preparations :632-664 ----
+  if (c.N_active > 1 && g.flush_flag > 2 && (g.boundflux_flag == 2 || g.boundflux_flag == 3)) {
+    SCV(c, SC_T_FREEZE) = T_freeze_of(c.S_abs[1] / c.m[1], g.salt_flag);
+    SCV(c, SC_MELT_THICK) = 0.0;
+    if (freeboard_of(g, c) > 0.0000000000001) {
+      const double ps1 = c.psi_s[1];
+      const double T_drive = (g.boundflux_flag == 2) ? SCV(c, SC_T_TOP) : SCV(c, SC_T2M);
+      if (ps1 < psi_s_top_min || T_drive >= SCV(c, SC_T_FREEZE)) {
+        double th1 = c.thick[1];
+        melt_thick_of(c.psi_l[1], ps1, c.psi_g[1], c.T[1], SCV(c, SC_T_FREEZE), T_drive, c.fl_Q[1], SCV(c, SC_THICK_SNOW), dt,
+                      SCV(c, SC_MELT_THICK), th1, g.thick_min);
+        if (g.boundflux_flag == 3) SCV(c, SC_MELT_THICK) = f_max(SCV(c, SC_MELT_THICK), 0.0);
+        if (SCV(c, SC_THICK_SNOW) >= g.thick_min / 100.0 && SCV(c, SC_MELT_THICK) > 0.00000000001 && SCV(c, SC_MELT_THICK_SNOW) == 0.0) {
+          double H1 = c.H_abs[1], m1 = c.m[1];
+          melt_snow(SCV(c, SC_MELT_THICK), th1, SCV(c, SC_THICK_SNOW), H1, SCV(c, SC_H_ABS_SNOW), m1, SCV(c, SC_M_SNOW), SCV(c, SC_PSI_G_SNOW));
+          c.H_abs[1] = H1; c.m[1] = m1;
+        }
+        c.thick[1] = th1;
+      }
+    }
+  }
+
+  // ---- S21 flushing :670-737 ----
+  SCV(c, SC_FREEBOARD) = freeboard_of(g, c);
+  SCV(c, SC_MTO1) = SCV(c, SC_MTO1) + SCV(c, SC_MELT_THICK);
+  SCV(c, SC_MTO2) = SCV(c, SC_MTO2) + SCV(c, SC_MELT_THICK_SNOW);
+  SCV(c, SC_MELT_THICK) = SCV(c, SC_MELT_THICK) + SCV(c, SC_MELT_THICK_SNOW);
+  if (SCV(c, SC_MELT_THICK_SNOW) > 0.0) {  // :677-685
+    const double mts = SCV(c, SC_MELT_THICK_SNOW), T_snow = SCV(c, SC_T_SNOW);
+    const double H1 = c.H_abs[1] + mts * rho_l * c_l * T_snow;
+    const double S1 = c.S_abs[1] + mts * rho_l * S_br_of(g, T_snow, SCV(c, SC_S_ABS_SNOW) / SCV(c, SC_M_SNOW));
+    const double m1 = c.m[1] + mts * rho_l;
+    c.H_abs[1] = H1; c.S_abs[1] = S1;
+    c.thick[1] = c.thick[1] + mts;
+    c.m[1] = m1;
+    c.S_bu[1] = S1 / m1;
+  }
+  // flush_v/h: old = cur; cur = 0; [flush3 fills 1..N_active]; cur = cur + old  (:697-701, :736-737).
+  // Without flush3 that is the identity; with it, new + old.  w-arrays hold the old values.
+  if (c.N_active > 1 && SCV(c, SC_FREEBOARD) > 0.001) {
+    if (g.flush_flag == 4) {  // :704-713
+      const double mt = SCV(c, SC_MELT_THICK);
+      if (mt > 0.000000000001 && c.N_active > 2) {
+        const double m1 = c.m[1];
+        c.H_abs[1] = c.H_abs[1] - mt * rho_l * c_l * c.T[1];
+        c.S_abs[1] = c.S_abs[1] * (1.0 - (mt * rho_l) / m1);
+        c.thick[1] = c.thick[1] - mt;
+        c.m[1] = m1 - mt * rho_l;
+      }
+    } else if (g.flush_flag == 5) {  // :715-728
+      if (SCV(c, SC_MELT_THICK) > 0.000000000001 && c.N_active > 2 && SCV(c, SC_FREEBOARD) > 0.0) {
+        SCV(c, SC_FREEBOARD) = freeboard_of(g, c);
+        const int Na = c.N_active;
+        Lay old_v = c.V_ex, old_h = c.S_br;  // both dead after S13
+        for (int k = 1; k <= Na; k++) { old_v[k] = c.flush_v[k]; old_h[k] = c.flush_h[k]; }
+        flush3(g, c);
+        for (int k = 1; k <= Na; k++) { c.flush_v[k] = c.flush_v[k] + old_v[k]; c.flush_h[k] = c.flush_h[k] + old_h[k]; }
+        if (c.status) return;
+      }
+    } else if (g.flush_flag == 6) {  // :729-733
+      if (SCV(c, SC_MELT_THICK) > 0.000000000001 && c.N_active > 2 && SCV(c, SC_THICK_SNOW) < g.thick_0) {
+        flush4(g, c);
+        if (c.status) return;
+      }
+    }
+  }
+
+  // ---- S23 layer dynamics :755-795 ----
+  if (c.N_active > 1) {
+    const int Na = c.N_active;
+    const double r1 = c.thick[1] / g.thick_0;
+    if (c.phi[Na] > psi_s_min || c.phi[Na - 1] <= psi_s_min / 2.0 || r1 > 1.5 || r1 < 0.5) {
+      layer_dynamics(g, c);
+      if (c.status) return;
+    }
+    const int Nb = c.N_active;
+    if (Nb < N && c.thick[(Nb + 1 < N) ? Nb + 1 : N] == 0) {  // :772-783 scrub
+      c.T[Nb + 1] = SCV(c, SC_T_BOTTOM);
+      c.S_bu[Nb + 1] = SCV(c, SC_S_BU_BOTTOM);
+      c.psi_l[Nb + 1] = 1.0;
+      c.psi_s[Nb + 1] = 0.0;
+    }
+  } else {
+    if (c.phi[1] > psi_s_min) layer_dynamics(g, c);
+    if (c.status) return;
+  }
+
+  // ---- S24 timestep + health check :802-819 ----
+  c.time = c.time + dt;
+  {
+    const int Na = c.N_active;
+    double mn = c.psi_s[1], ms = c.S_abs[1];
+    for (int k = 2; k <= Na; k++) { mn = f_min(mn, c.psi_s[k]); ms = f_min(ms, c.S_abs[k]); }
+    if (mn < 0.0) {
+      c.status = 1337;
+    } else if (ms < 0.0) {
+      for (int k = 1; k <= Na; k++) c.S_abs[k] = f_max(c.S_abs[k], 0.0);
+    }
+  }
+}
+
+}  // namespace samsim

@@ -1,0 +1,232 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle's deterministic-math build.
+
+Bar: integers (N_active, status) exact; FP64 state BIT-IDENTICAL (tolerance 0.0) -- possible because
+both sides use IEEE +,-,*,/ in the reference's operation order (gcc -ffp-contract=off / nvcc
+-fmad=false) and the same detmath.h for pow/exp/sin.
+"""
+import numpy as np
+import pytest
+
+from samsim_b200 import api
+from oracle import parity_util as pu
+
+pytestmark = pytest.mark.gpu
+
+
+def _fmt(bad, n=12):
+    return "\n".join(bad[:n]) + (f"\n... {len(bad)} mismatches" if len(bad) > n else "")
+
+
+def test_detmath_bitexact_on_gpu(oracle_mod):
+    L = oracle_mod.lib("det")
+    rng = np.random.default_rng(1)
+    x = np.concatenate([10 ** rng.uniform(-8, 3.5, 4000), [0.0, 1.0, 1000.0, 5e-324, 1e-310]])
+    for y in (3.1, 1.5, 0.37):
+        g = api.kat_scalar(7, 1, x, np.full_like(x, y))
+        o = np.array([L.sam_math_pow(float(a), y) for a in x])
+        assert pu.same_bits(g, o).all()
+    e = np.concatenate([rng.uniform(-40, 10, 4000), [-745.2, -744.0, -708.5, 0.0, 709.0]])
+    assert pu.same_bits(api.kat_scalar(8, 1, e), np.array([L.sam_math_exp(float(a)) for a in e])).all()
+    s = rng.uniform(-50, 50, 4000)
+    assert pu.same_bits(api.kat_scalar(9, 1, s), np.array([L.sam_math_sin(float(a)) for a in s])).all()
+
+
+@pytest.mark.parametrize("salt_flag", [1, 2])
+def test_getT_kat(oracle_mod, salt_flag):
+    """getT (mo_thermo_functions.f90:62-143): mushy, liquid, salt-free and pathological inputs."""
+    import ctypes as C
+    L = oracle_mod.lib("det")
+    rng = np.random.default_rng(2)
+    n = 20000
+    S = np.concatenate([rng.uniform(0.5, 40, n // 2), rng.uniform(0, 0.002, n // 4), rng.uniform(30, 250, n // 4)])
+    T_true = rng.uniform(-45, 2, n)
+    H = np.where(rng.random(n) < 0.8, -333500.0 * rng.random(n) ** 0.5 + 2020.0 * T_true, 3400.0 * T_true)
+    T_in = T_true + rng.normal(0, 0.3, n)
+    Tg, pg, st = api.kat_getT(salt_flag, H, S, T_in)
+    To, po = np.empty(n), np.empty(n)
+    dp = C.POINTER(C.c_double)
+    L.sam_kat_getT(salt_flag, n, H.ctypes.data_as(dp), S.ctypes.data_as(dp), T_in.ctypes.data_as(dp), To.ctypes.data_as(dp), po.ctypes.data_as(dp))
+    ok = st == 0
+    assert ok.sum() > 0.9 * n
+    assert pu.same_bits(Tg[ok], To[ok]).all()
+    assert pu.same_bits(pg[ok], po[ok]).all()
+    assert np.isnan(To[~ok]).all()  # the oracle STOPs (99) exactly where the GPU flags status 99
+
+
+@pytest.mark.parametrize("fn,two", [(0, False), (1, True), (2, False), (3, True), (4, False), (5, True), (6, True)])
+def test_scalar_kats(oracle_mod, fn, two):
+    import ctypes as C
+    L = oracle_mod.lib("det")
+    rng = np.random.default_rng(3 + fn)
+    n = 5000
+    a = rng.uniform(-40, 5, n) if fn in (0, 1, 2, 3) else rng.uniform(0.0, 60.0, n)
+    b = rng.uniform(0, 40, n)
+    if fn == 5:
+        a, b = rng.uniform(1, 200, n), rng.uniform(0.005, 0.6, n)
+    if fn == 6:
+        a, b = rng.uniform(0, 0.5, n), rng.uniform(-5, 0.5, n)
+    dp = C.POINTER(C.c_double)
+    for salt in (1, 2):
+        o = np.empty(n)
+        L.sam_kat_scalar(fn, salt, n, a.ctypes.data_as(dp), b.ctypes.data_as(dp), o.ctypes.data_as(dp))
+        g = api.kat_scalar(fn, salt, a, b if two else None) if two else api.kat_scalar(fn, salt, a)
+        assert pu.same_bits(g, o).all(), (fn, salt)
+
+
+def test_testcase1_from_init(oracle_mod):
+    """Config 1: testcase 1 from the reference's initial state; bitwise at growing step counts."""
+    col = oracle_mod.Column(1, "det")
+    eng = pu.engine_from_oracle(col, ncol=3)
+    done = 0
+    for target in (1, 2, 10, 100, 3000, 3601, 3603, 20000, 45000):
+        n = target - done
+        assert col.step(n) == 0
+        eng.step(n)
+        done = target
+        for c in (0, 2):
+            bad = pu.compare_column(col, eng, c, label=f"step {target} col {c}: ")
+            assert not bad, _fmt(bad)
+    assert col.int("N_active") > 20  # the run really grew ice and exercised bottom_growth_simple
+
+
+def _forcing(golden_dir, site="sheba"):
+    z = np.load(golden_dir / "forcing_era.npz")
+    return z[site]  # [4, nrec] fl_sw, fl_lw, T2m, precip
+
+
+def test_testcase4_from_init(oracle_mod, golden_dir):
+    """Config 2 (SHEBA): open water -> freeze-up with reanalysis forcing, first ~52 h."""
+    F = _forcing(golden_dir)
+    col = oracle_mod.Column(4, "det")
+    col.set_forcing(*F)
+    eng = pu.engine_from_oracle(col, ncol=2)
+    eng.set_forcing(F[None])
+    done = 0
+    for target in (1, 2, 1081, 1082, 8641, 8643, 19000):
+        n = target - done
+        assert col.step(n) == 0
+        eng.step(n)
+        done = target
+        bad = pu.compare_column(col, eng, 1, label=f"step {target}: ")
+        assert not bad, _fmt(bad)
+
+
+def _state(z, j):
+    p = f"state{j}_"
+    return {k[len(p):]: (z[k] if z[k].ndim else z[k].item()) for k in z.files if k.startswith(p)}
+
+
+# 1-based output record whose preceding state is restored -> regime exercised in the window
+SHEBA_WINDOWS = {
+    60: "autumn freeze-up, N_active growing (bottom_growth_simple), thin snow coupling",
+    100: "early winter, snow cover, gravity drainage",
+    200: "mid winter, N_active = 100, bottom_growth (grid full)",
+    330: "melt onset: wet snow, melt water flushing (flush3)",
+    345: "snow gone, surface melt, top_melt / layer merges",
+    400: "late summer melt, bottom_melt",
+    715: "second summer",
+    1000: "third winter",
+}
+
+
+@pytest.mark.parametrize("rec", sorted(SHEBA_WINDOWS))
+def test_sheba_windows(oracle_mod, golden_dir, rec):
+    """Restart both implementations from an oracle state of the SHEBA run and advance 2 days."""
+    z = np.load(golden_dir / "sheba_oracle_states.npz")
+    st = _state(z, rec)
+    F = _forcing(golden_dir)
+    col = oracle_mod.Column(4, "det")
+    col.set_forcing(*F)
+    col.load_state(st)
+    eng = pu.engine_from_oracle(col, ncol=2)
+    eng.set_forcing(F[None])
+    ev0 = {k: col.stat(k) for k in ("layer_events", "flush_calls", "coupling_iters")}
+    for n in (1, 999, 8641, 7641):
+        assert col.step(n) == 0
+        eng.step(n)
+        bad = pu.compare_column(col, eng, 1, label=f"rec {rec} (+{n}): ")
+        assert not bad, SHEBA_WINDOWS[rec] + "\n" + _fmt(bad)
+    print(rec, SHEBA_WINDOWS[rec], {k: col.stat(k) - ev0[k] for k in ev0})
+
+
+def test_snapshot_matches_oracle_output(oracle_mod, golden_dir):
+    """S8 capture (mo_grotz.f90:340-398): the device snapshot equals what the oracle hands to output()."""
+    z = np.load(golden_dir / "sheba_oracle_states.npz")
+    F = _forcing(golden_dir)
+    col = oracle_mod.Column(4, "det")
+    col.set_forcing(*F)
+    col.load_state(_state(z, 200))
+    col.record_outputs()
+    eng = pu.engine_from_oracle(col, ncol=2)
+    eng.set_forcing(F[None])
+    eng.set_snapshot_mode(api.SNAP_FULL)
+    for _ in range(2):
+        n = eng.steps_to_next_output()
+        assert col.step(n) == 0
+        eng.step(n)
+        rec = col.records[-1]
+        snap = eng.get_snapshot(1, 1)
+        for name in api.SNAP_SCALARS:
+            o = rec[name] if name != "N_active" else float(rec["N_active"])
+            assert pu.same_bits(snap[name][0], o), (name, snap[name][0], o)
+        for name in api.SNAP_ARRAYS:
+            o = np.asarray(rec[name])[: snap[name].shape[1]]
+            assert pu.same_bits(snap[name][0], o).all(), name
+
+
+def test_batch_invariance_and_perturbed_ensemble(oracle_mod, golden_dir):
+    """Column results do not depend on batch size or neighbours; per-column forcing perturbations
+    (value*scale + offset) match an oracle fed the perturbed series."""
+    z = np.load(golden_dir / "sheba_oracle_states.npz")
+    F = _forcing(golden_dir)
+    ncol = 70  # not a multiple of the block size
+    rng = np.random.default_rng(4)
+    scale = np.ones((4, ncol))
+    offset = np.zeros((4, ncol))
+    offset[2] = rng.uniform(-2, 2, ncol)       # T2m + U(-2,2)
+    scale[1] = rng.uniform(0.95, 1.05, ncol)   # fl_lw
+    scale[0] = rng.uniform(0.9, 1.1, ncol)     # fl_sw
+    scale[3] = rng.uniform(0.5, 1.5, ncol)     # precip
+    amp = 7.0 * rng.uniform(0.5, 1.5, ncol)
+    base = oracle_mod.Column(4, "det")
+    base.set_forcing(*F)
+    base.load_state(_state(z, 100))
+    eng = pu.engine_from_oracle(base, ncol=ncol)
+    eng.set_forcing(F[None], None, scale, offset)
+    eng.set_scalar("oflux_amp", amp)
+    eng.step(3000)
+    for c in (0, 1, 33, 69):
+        col = oracle_mod.Column(4, "det")
+        col.set_forcing(*[F[k] * scale[k, c] + offset[k, c] for k in range(4)])
+        col.load_state(_state(z, 100))
+        col.set_scalar("oflux_amp", amp[c])
+        assert col.step(3000) == 0
+        bad = pu.compare_column(col, eng, c, label=f"col {c}: ")
+        assert not bad, _fmt(bad)
+    assert eng.count_failed() == 0
+
+
+def test_status_codes_freeze_column(oracle_mod):
+    """A column that hits a reference STOP is frozen with that code; its neighbours continue."""
+    col = oracle_mod.Column(1, "det")
+    col.step(5000)
+    eng = pu.engine_from_oracle(col, ncol=4)
+    bad_state = col.state()
+    H = np.array(bad_state["H_abs"])
+    H[2] = -1e12  # absurd enthalpy: getT cannot converge -> STOP 99 (mo_thermo_functions.f90:114-123)
+    eng.set_array("H_abs", H[None, :], col0=2)
+    ref = oracle_mod.Column(1, "det")
+    ref.load_state(col.state())
+    ref.set_array("H_abs", H)
+    rc = ref.step(10)
+    eng.step(10)
+    st = eng.status()
+    assert rc != 0 and st[2] == rc and (st[[0, 1, 3]] == 0).all()
+    assert col.step(10) == 0
+    assert not pu.compare_column(col, eng, 0)
+    assert eng.count_failed() == 1
+
+
+def test_fp64_peak_runs():
+    tf = api.fp64_peak(0, 0.3)
+    assert 5.0 < tf < 80.0, tf
