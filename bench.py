@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- column-timesteps/sec of the SAMSIM column timestep on 1..8 B200.
+
+Workload (BASELINE.json config 5): 1,048,576 ERA-interim-style columns (testcase-4 flags, 100 layers, dt 10 s),
+sharded over the N ranks (strong scaling: the total is fixed).  Every column starts from the oracle's SHEBA state
+of mid January (output record 200: N_active = 100, 0.124 m of snow) and gets its own forcing: base site c mod 9 of
+input/ERA-interim, T2m + U(-2,2) K, fl_lw x U(.95,1.05), fl_sw x U(.9,1.1), precip x U(.5,1.5), oceanic flux
+amplitude 7 x U(.5,1.5) W/m2 (default_rng(4)).
+
+One bench "step" = MODEL_STEPS consecutive model timesteps of every column of the rank (one kernel launch).
+  value  : column-timesteps/s with the state resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e    : the same through the C ABI with HOST buffers inside the timed region: every step uploads the forcing
+           records the step needs (pinned host memory -> set_forcing), runs samsim_b200_step, and reads back the
+           per-column S8 diagnostics (20 doubles per column) plus the 18-number ensemble reduction.
+  roofline: FP64 vector pipe.  achieved = F_ALG x column-steps/s; peak = DFMA micro-benchmark run live on the same
+           GPU (MEASURED_PEAKS.json has no FP64 entry); HBM view alongside (peak from MEASURED_PEAKS.json).
+  cpu_baseline / --impl reference: the CPU oracle (C port of the Fortran; no Fortran compiler exists in this image),
+           one column per OS thread on all host cores, on a bounded sample of the same columns.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+TOTAL_COLUMNS = 1 << 20
+MODEL_STEPS = 16            # model timesteps per bench step (one launch)
+START_RECORD = 200          # oracle SHEBA state (tests/golden/sheba_oracle_states.npz)
+SITES = ["sheba", "70N00W", "75N00W", "75N180E", "80N00E", "80N90E", "85N180E", "NorthPole", "barrow"]
+# Algorithmic FP64 work of ONE column timestep of this workload, counted on the CPU oracle with the
+# operation-counting build (tools/count_flops.py; see DESIGN.md "Roofline"): +,-,*,/ = 1 flop each,
+# pow/exp/sin calls listed separately.
+F_ALG_FLOP_PER_COLUMN_STEP = 1.0e5
+B_ALG_BYTES_PER_COLUMN_STEP = 2 * 4 * 100 * 8  # read+write of m, S_abs, H_abs, thick once per model step
+
+
+def load_state(rec: int) -> dict:
+    z = np.load(ROOT / "tests" / "golden" / "sheba_oracle_states.npz")
+    p = f"state{rec}_"
+    return {k[len(p):]: (z[k] if z[k].ndim else z[k].item()) for k in z.files if k.startswith(p)}
+
+
+def load_sites(nrec_min: int) -> np.ndarray:
+    z = np.load(ROOT / "tests" / "golden" / "forcing_era.npz")
+    n = min(z[s].shape[1] for s in SITES)
+    assert n >= nrec_min
+    return np.stack([z[s][:, :n] for s in SITES])  # [9, 4, n]
+
+
+def perturbations(col0: int, n: int):
+    """Deterministic per-column perturbations for global columns [col0, col0+n)."""
+    rng = np.random.default_rng(4)
+    # draw for the whole ensemble so that a column's numbers do not depend on the sharding
+    T2m_off = rng.uniform(-2, 2, TOTAL_COLUMNS)
+    lw = rng.uniform(0.95, 1.05, TOTAL_COLUMNS)
+    sw = rng.uniform(0.9, 1.1, TOTAL_COLUMNS)
+    pr = rng.uniform(0.5, 1.5, TOTAL_COLUMNS)
+    amp = 7.0 * rng.uniform(0.5, 1.5, TOTAL_COLUMNS)
+    sl = slice(col0, col0 + n)
+    scale = np.ones((4, n))
+    offset = np.zeros((4, n))
+    scale[0], scale[1], scale[3] = sw[sl], lw[sl], pr[sl]
+    offset[2] = T2m_off[sl]
+    site = (np.arange(col0, col0 + n) % len(SITES)).astype(np.int32)
+    return site, scale, offset, amp[sl]
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self) -> dict:
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(r) > 3 + j and r[3 + j].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_oracle_columns(st: dict, sites: np.ndarray, cols: np.ndarray, backend: str = "det"):
+    from oracle import oracle
+    out = []
+    for c in cols:
+        s, sc, of, am = perturbations(int(c), 1)
+        col = oracle.Column(4, backend)
+        col.set_forcing(*[sites[s[0], k] * sc[k, 0] + of[k, 0] for k in range(4)])
+        col.load_state(st)
+        col.set_scalar("oflux_amp", float(am[0]))
+        out.append(col)
+    return out
+
+
+def cpu_oracle_rate(st: dict, sites: np.ndarray, ncols: int, nsteps: int, nthreads: int, reps: int = 1):
+    """column-steps/s of the CPU oracle, one column per OS thread."""
+    from oracle import oracle
+    oracle.build()
+    cols = make_oracle_columns(st, sites, np.linspace(0, TOTAL_COLUMNS - 1, ncols).astype(np.int64))
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        rc = oracle.run_batch(cols, nsteps, nthreads)
+        times.append(time.perf_counter() - t0)
+        if rc:
+            raise RuntimeError(f"oracle STOP {rc}")
+    return ncols * nsteps / min(times), times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncores = os.cpu_count() or 1
+    st = load_state(START_RECORD)
+    sites = load_sites(64)
+    sample_cols = 4 * ncores
+    from oracle import oracle
+    oracle.build()
+    cols = make_oracle_columns(st, sites, np.linspace(0, TOTAL_COLUMNS - 1, sample_cols).astype(np.int64))
+    steps_per = MODEL_STEPS * 64  # 1024 model steps per bench step so that a step is ~a second of CPU work
+    for _ in range(args.warmup):
+        oracle.run_batch(cols, steps_per, ncores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rc = oracle.run_batch(cols, steps_per, ncores)
+        if rc:
+            raise RuntimeError(f"oracle STOP {rc}")
+    dt = time.perf_counter() - t0
+    value = sample_cols * steps_per * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "column-timesteps/sec (FP64, 100 layers)", "value": value,
+        "unit": "column-timesteps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus, sample=f"{sample_cols} of the {TOTAL_COLUMNS} columns x {steps_per} model steps per step"),
+        "cpu_baseline": {"value": value, "unit": "column-timesteps/s", "cores": ncores, "kind": "port",
+                         "sample": f"{sample_cols} columns x {steps_per * args.steps} model steps, one column per thread; "
+                                   "C oracle (gcc -O2 -ffp-contract=off), the Fortran reference cannot be compiled in this image"},
+        "e2e": {"value": value, "unit": "column-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus: int, sample: str | None = None) -> dict:
+    cfg = {
+        "workload": "config 5: 1,048,576 ERA-interim-style columns (testcase 4 flags, Nlayer 100, dt 10 s), "
+                    "mid-January SHEBA state (N_active 100, snow 0.124 m), per-column perturbed forcing of 9 sites",
+        "columns_total": TOTAL_COLUMNS, "columns_per_gpu": TOTAL_COLUMNS // n_gpus,
+        "model_steps_per_step": MODEL_STEPS, "layers": 100, "dt_s": 10.0,
+        "parallelism": f"columns sharded over {n_gpus} GPU(s), no data-path collective",
+        "cache": "working set (>= 12 KB/column x columns) is far larger than the 126 MB L2; no flush needed",
+    }
+    if sample:
+        cfg["sample"] = sample
+    return cfg
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--columns", type=int, default=TOTAL_COLUMNS, help="total columns (default: the config-5 ensemble)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: samsim_b200 has no CPU path (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from samsim_b200 import api
+
+    total = args.columns
+    per = total // world
+    col0 = rank * per
+    st = load_state(START_RECORD)
+    sites = load_sites(64)
+    cfg = api.Config.from_state({**st, "thick_min": st["thick_min"]})
+    eng = api.Engine(cfg, per, local_rank)
+    eng.load_column_state(st, 0)
+    eng.broadcast_column(0, 0, per)
+    site, scale, offset, amp = perturbations(col0, per)
+    eng.set_forcing(sites, site, scale, offset)
+    eng.set_scalar("oflux_amp", amp)
+    eng.set_snapshot_mode(api.SNAP_SCALARS_ONLY)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- FP64 peak of this GPU (live) ----
+    fp64_peak = api.fp64_peak(local_rank, 0.5)
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        eng.step(MODEL_STEPS)
+
+    # ---- timed region A: device-resident ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    l0 = eng.launch_count()
+    kernel_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.step(MODEL_STEPS, sync=False)
+        eng.synchronize()
+        kernel_ms += eng.last_step_ms()     # CUDA events on the launching stream
+    barrier()
+    wall_a = time.perf_counter() - t0
+    launches = eng.launch_count() - l0
+
+    # ---- timed region B: end to end through the C ABI with host buffers ----
+    pinned = torch.from_numpy(np.ascontiguousarray(sites)).pin_memory()
+    diag_host = np.empty((per, len(api.SNAP_SCALARS)))
+    h2d = pinned.numel() * 8
+    d2h = diag_host.nbytes + 18 * 8
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        # upload this step's forcing tables (base series from pinned host memory + per-column affine vectors)
+        api._check(eng.L, eng.L.samsim_b200_set_forcing(eng.h, sites.shape[0], sites.shape[2], api._dp(pinned.numpy()),
+                                                        api._ip(site), api._dp(scale), api._dp(offset)))
+        eng.step(MODEL_STEPS, sync=False)
+        snap = eng.get_snapshot(0, per, arrays=False)
+        red = eng.reduce_diag()
+    barrier()
+    wall_b = time.perf_counter() - t0
+    h2d += scale.nbytes + offset.nbytes + site.nbytes
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    # ---- max over ranks ----
+    t = torch.tensor([kernel_ms * 1e-3, wall_a, wall_b], dtype=torch.float64, device="cuda")
+    nf = torch.tensor([eng.count_failed()], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nf, op=dist.ReduceOp.SUM)
+    kern_s, wall_a_s, wall_b_s = [float(x) for x in t.tolist()]
+    col_steps = total * MODEL_STEPS * args.steps
+    value = col_steps / wall_a_s
+    kernel_rate = col_steps / kern_s
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        per_gpu_rate = kernel_rate / world
+        achieved_tf = per_gpu_rate * F_ALG_FLOP_PER_COLUMN_STEP / 1e12
+        line = {
+            "metric": "column-timesteps/sec (FP64, 100 layers)", "value": value, "unit": "column-timesteps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": wall_a_s / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world) if total == TOTAL_COLUMNS else {**workload_config(world), "columns_total": total, "columns_per_gpu": per},
+            "e2e": {"value": col_steps / wall_b_s, "unit": "column-timesteps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved_tf / fp64_peak, "traffic": None,
+                         "peak_source": "DFMA micro-benchmark on this GPU in this run (samsim_b200_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                         "flop_per_column_step": F_ALG_FLOP_PER_COLUMN_STEP,
+                         "kernel": "samsim_step_kernel", "kernel_ms_per_launch": kern_s / max(launches, 1) * 1e3,
+                         "hbm": {"achieved": per_gpu_rate * B_ALG_BYTES_PER_COLUMN_STEP / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": per_gpu_rate * B_ALG_BYTES_PER_COLUMN_STEP / 1e9 / hbm_peak,
+                                 "bytes_per_column_step": B_ALG_BYTES_PER_COLUMN_STEP,
+                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}},
+            "clocks": sampler.summary(),
+            "failed_columns": int(nf.item()),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            ncores = os.cpu_count() or 1
+            ncols_cpu, nsteps_cpu = 4 * ncores, 4000
+            rate, times = cpu_oracle_rate(st, sites, ncols_cpu, nsteps_cpu, ncores)
+            line["cpu_baseline"] = {"value": rate, "unit": "column-timesteps/s", "cores": ncores, "kind": "port",
+                                    "sample": f"{ncols_cpu} of the {total} columns x {nsteps_cpu} model steps, one column per thread "
+                                              f"({times[0]:.1f} s); C oracle, Fortran reference not compilable here"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
