@@ -582,7 +582,11 @@ real sam_func_k_snow(real m_snow, real thick_snow) {
  * (`CALL getT(H, S_bu, T, T, phi, 5702)`); getT assigns T = H/c_l (:80) before it reads T_in
  * (:94), so with by-reference scalars the first guess is H/c_l.  Reproduced explicitly. */
 static void getT_aliased(sam_col* c, real H, real S_bu, real* T, real* phi, int k) {
+#ifdef SAM_VARIANT_COUPLING_NOALIAS /* hypothesis test only: T_in keeps the caller's old T (copy-in semantics) */
+  sam_getT(c, H, S_bu, *T, T, phi, k);
+#else
   sam_getT(c, H, S_bu, H / c_l, T, phi, k);
+#endif
 }
 
 static void snow_coupling(sam_col* c, real* H_abs_snow, real* phi_s, real* T_snow, real* H_abs, real* H, real* phi,

@@ -1,0 +1,84 @@
+"""N>1 host logic on CPU: world_size-2 gloo.  Columns shard with no data-path collective; per-column inputs do
+not depend on the sharding; the only collectives are the MAX of timings and the ensemble diagnostics reduction."""
+import os
+import subprocess
+import sys
+import textwrap
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_perturbations_are_shard_invariant():
+    sys.path.insert(0, str(ROOT))
+    import bench
+    site_a, sc_a, of_a, amp_a = bench.perturbations(0, 1024)
+    site_b, sc_b, of_b, amp_b = bench.perturbations(512, 512)
+    assert np.array_equal(site_a[512:], site_b) and np.array_equal(sc_a[:, 512:], sc_b)
+    assert np.array_equal(of_a[:, 512:], of_b) and np.array_equal(amp_a[512:], amp_b)
+    assert set(np.unique(site_a)) == set(range(9))
+    assert (sc_a[2] == 1).all() and (of_a[[0, 1, 3]] == 0).all()   # T2m is offset-only, the fluxes scale-only
+
+
+WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, %(root)r)
+    import numpy as np, torch, torch.distributed as dist
+    import bench
+    from oracle import oracle
+    dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    total = 8
+    per = total // world
+    col0 = rank * per
+    st = bench.load_state(bench.START_RECORD)
+    sites = bench.load_sites(64)
+    # each rank advances ITS columns (here with the CPU oracle standing in for the engine)
+    cols = []
+    for c in range(col0, col0 + per):
+        s, sc, of, am = bench.perturbations(c, 1)
+        col = oracle.Column(4, "det")
+        col.set_forcing(*[sites[s[0], k] * sc[k, 0] + of[k, 0] for k in range(4)])
+        col.load_state(st); col.set_scalar("oflux_amp", float(am[0])); col.step(50)
+        cols.append(col)
+    th = torch.tensor([c.scalar("thickness") for c in cols], dtype=torch.float64)
+    # the optional diagnostics gather / reduction is the only collective
+    gathered = [torch.zeros(per, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(gathered, th)
+    red = torch.tensor([th.sum().item(), -th.min().item(), th.max().item()], dtype=torch.float64)
+    s = red[:1].clone(); dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    mm = red[1:].clone(); dist.all_reduce(mm, op=dist.ReduceOp.MAX)
+    t = torch.tensor([0.5 + rank], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        np.save(%(out)r, np.concatenate([torch.cat(gathered).numpy(), [s.item(), -mm[0].item(), mm[1].item(), t.item()]]))
+    dist.destroy_process_group()
+""")
+
+
+def test_two_rank_gloo_sharding_matches_single_process(tmp_path, oracle_mod):
+    sys.path.insert(0, str(ROOT))
+    import bench
+    out = tmp_path / "res.npy"
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": str(ROOT), "out": str(out)})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29541", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r))) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    res = np.load(out)
+    # single-process reference: the same 8 columns
+    st = bench.load_state(bench.START_RECORD)
+    sites = bench.load_sites(64)
+    th = []
+    for c in range(8):
+        s, sc, of, am = bench.perturbations(c, 1)
+        col = oracle_mod.Column(4, "det")
+        col.set_forcing(*[sites[s[0], k] * sc[k, 0] + of[k, 0] for k in range(4)])
+        col.load_state(st); col.set_scalar("oflux_amp", float(am[0])); col.step(50)
+        th.append(col.scalar("thickness"))
+    th = np.array(th)
+    assert np.array_equal(res[:8], th)                 # shards give identical per-column results
+    assert res[8] == th[:4].sum() + th[4:].sum() and res[9] == th.min() and res[10] == th.max()
+    assert res[11] == 1.5                              # MAX over ranks of the timing
