@@ -11,8 +11,11 @@ from pathlib import Path
 
 import numpy as np
 
+import os
+
 _ROOT = Path(__file__).resolve().parent
-_LIB_PATH = _ROOT / "_lib" / "libsamsim_b200.so"
+# SAMSIM_B200_LIB selects another build of the SAME library (tuning variants under samsim_b200/_lib/)
+_LIB_PATH = Path(os.environ.get("SAMSIM_B200_LIB", _ROOT / "_lib" / "libsamsim_b200.so"))
 
 
 class SamsimError(RuntimeError):

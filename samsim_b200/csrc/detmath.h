@@ -27,8 +27,12 @@
 
 #if defined(__CUDACC__)
 #define DM_HD __host__ __device__ __forceinline__
+// the public entry points are single out-of-line copies on the device: the step kernel calls them from many
+// sites and its instruction footprint, not call overhead, is what stalls the warps (I-cache misses)
+#define DM_API __host__ __device__ __noinline__
 #else
 #define DM_HD static inline
+#define DM_API static inline
 #include <string.h>
 #endif
 
@@ -109,7 +113,7 @@ DM_HD double dm_exp2part(double xh, double xl) {
   return dm_scale2(p, k);
 }
 
-DM_HD double det_exp(double x) {
+DM_API double det_exp(double x) {
   if (x != x) return x;
   return dm_exp2part(x, 0.0);
 }
@@ -168,7 +172,7 @@ DM_HD void dm_log2part(double x, double* hi, double* lo) {
   *hi = h;
 }
 
-DM_HD double det_log(double x) {
+DM_API double det_log(double x) {
   if (x != x || x < 0.0) return dm_from_bits(0x7ff8000000000000LL);
   if (x == 0.0) return dm_from_bits((int64_t)0xfff0000000000000ULL);
   if (dm_bits(x) == 0x7ff0000000000000LL) return x;
@@ -178,7 +182,7 @@ DM_HD double det_log(double x) {
 }
 
 // x**y for x >= 0.  pow(0, y>0) = 0, pow(x, 0) = 1.
-DM_HD double det_pow(double x, double y) {
+DM_API double det_pow(double x, double y) {
   if (y == 0.0) return 1.0;
   if (x != x || y != y || x < 0.0) return dm_from_bits(0x7ff8000000000000LL);
   if (x == 0.0) return (y > 0.0) ? 0.0 : dm_from_bits(0x7ff0000000000000LL);
@@ -239,7 +243,7 @@ DM_HD int dm_rem_pio2(double x, double* rh, double* rl) {
   return k;
 }
 
-DM_HD double det_sin(double x) {
+DM_API double det_sin(double x) {
   if (x != x || fabs(x) > 1.0e5) return dm_from_bits(0x7ff8000000000000LL);
   double rh, rl;
   int k = dm_rem_pio2(x, &rh, &rl);
@@ -251,7 +255,7 @@ DM_HD double det_sin(double x) {
   }
 }
 
-DM_HD double det_cos(double x) {
+DM_API double det_cos(double x) {
   if (x != x || fabs(x) > 1.0e5) return dm_from_bits(0x7ff8000000000000LL);
   double rh, rl;
   int k = dm_rem_pio2(x, &rh, &rl);

@@ -62,15 +62,24 @@ enum { IN_N_ACTIVE = 0, IN_STATUS, IN_STYROPOR, IN_COUNT };
 // strided per-layer view of one column (1-based layer index like the reference)
 struct Lay {
   double* p;
-  size_t ls;
-  __device__ __forceinline__ double& operator[](int k) const { return p[(size_t)k * ls]; }
+  unsigned ls;  // ncol_pad; (Nlayer+2)*ncol_pad < 2^32 is checked at create time, so 32-bit index arithmetic
+  __device__ __forceinline__ double& operator[](int k) const { return p[(unsigned)k * ls]; }
+  // non-blocking L1 prefetch of layer k (sweeps are latency bound: one 256-byte warp request per layer and
+  // array, no spatial reuse between layers); k is clamped by the callers to [0, Nlayer+1]
+  __device__ __forceinline__ void prefetch(int k) const {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + (unsigned)k * ls));
+  }
 };
+#define SAMSIM_PF 4  // prefetch distance in layers
 
 // everything one thread needs
 struct Col {
   Lay m, S_abs, H_abs, thick, T, phi, S_bu, psi_s, psi_l, psi_g, ray, perm, flush_v, flush_h, fl_Q;
   Lay S_br, V_ex, fl_m, w0, w1, w2, w3;
   int N_active, status, styropor_flag;
+  // T, phi, S_bu of layers 2..N_active still equal what the S18 sweep of the previous step produced and
+  // m, S_abs, H_abs of those layers are untouched since: the S4 sweep may reuse them (bit-identical result)
+  bool thermo_valid;
   double sc[SC_COUNT];
   // clock (shared by the batch, advanced in lock step)
   double time;
@@ -269,30 +278,54 @@ __device__ __forceinline__ double sum_prod_fwd(const Lay& a, const Lay& b, int i
   return s;
 }
 
-// func_freeboard, mo_functions.f90:79-130
+// func_freeboard, mo_functions.f90:79-130.
+// The reference recomputes test2(k) = SUM(psi_s(k+1:Na)*thick(k+1:Na))*(rho_l-rho_s) + SUM(psi_g(..)*thick(..))*rho_l
+// with fresh forward sums for every k of its DO WHILE (O(N k)).  Only the value at the k where the loop stops is
+// used; for the earlier k only the outcome of `test1 < test2` matters.  Here the outcome is decided from
+// total - prefix (equal to the forward sum up to a rounding error bounded far below `margin`); the exact forward
+// sum is evaluated only where the decision is within the margin or the loop stops, so the returned value is the
+// reference's, bit for bit, at O(N) cost.
 __device__ __noinline__ double freeboard_of(const DevCfg& g, const Col& c) {
   const int Na = c.N_active;
   const double snowmass = (g.freeboard_snow_flag == 0) ? SCV(c, SC_M_SNOW) : 0.0;
-  double buoy = sum_prod_fwd(c.psi_s, c.thick, 1, Na) * (rho_l - rho_s) + sum_prod_fwd(c.psi_g, c.thick, 1, Na) * rho_l;
+  double A = 0.0, G = 0.0;  // forward totals, the reference's order
+  for (int q = 1; q <= Na; q++) {
+    if (q + SAMSIM_PF <= Na) { c.psi_s.prefetch(q + SAMSIM_PF); c.psi_g.prefetch(q + SAMSIM_PF); c.thick.prefetch(q + SAMSIM_PF); }
+    const double t = c.thick[q];
+    A = A + c.psi_s[q] * t;
+    G = G + c.psi_g[q] * t;
+  }
+  const double buoy = A * (rho_l - rho_s) + G * rho_l;
   double freeboard;
   if (snowmass > buoy) {  // :99-102 snow pushes the ice under water
     freeboard = buoy - snowmass;
     freeboard = freeboard / rho_l;
   } else {
-    double test1 = 0.0, test2 = 1.0, msum = 0.0, msum_prev = 0.0;
+    const double margin = 1e-9 * (fabs(buoy) + fabs(snowmass)) + 1e-300;
+    double pA = 0.0, pG = 0.0, msum = 0.0, msum_prev = 0.0, test1 = 0.0, test2 = 1.0, thsum = 0.0, thsum_prev = 0.0;
     int k = 0;
     while (test1 < test2) {  // :114-118
       k = k + 1;
-      test2 = sum_prod_fwd(c.psi_s, c.thick, k + 1, Na) * (rho_l - rho_s) + sum_prod_fwd(c.psi_g, c.thick, k + 1, Na) * rho_l;
+      const double t = c.thick[k];
+      pA = pA + c.psi_s[k] * t;   // same partial sums as the forward totals above
+      pG = pG + c.psi_g[k] * t;
       msum_prev = msum;
-      msum = msum + c.m[k];  // SUM(m(1:k)) is a fixed-start prefix: incremental is the same order
+      msum = msum + c.m[k];       // SUM(m(1:k)): fixed-start prefix, incremental is the same order
+      thsum_prev = thsum;
+      thsum = thsum + t;          // SUM(thick(1:k)) likewise
       test1 = msum + snowmass;
+      const double approx = (A - pA) * (rho_l - rho_s) + (G - pG) * rho_l;
+      if (test1 < approx - margin) {
+        test2 = approx + margin;  // certainly test1 < exact test2: keep looping (value unused)
+      } else {
+        test2 = sum_prod_fwd(c.psi_s, c.thick, k + 1, Na) * (rho_l - rho_s) + sum_prod_fwd(c.psi_g, c.thick, k + 1, Na) * rho_l;
+      }
     }
     test1 = msum_prev + snowmass;  // :121 SUM(m(1:k-1))
     const double mk = c.m[k], tk = c.thick[k];
     freeboard = test2 - test1 + (rho_l - mk / tk) * tk;  // :124
     freeboard = freeboard / rho_l;
-    freeboard = freeboard + sum_fwd(c.thick, 1, k - 1);
+    freeboard = freeboard + thsum_prev;                  // :126 SUM(thick(1:k-1))
   }
   return freeboard;
 }
@@ -608,66 +641,106 @@ __device__ __forceinline__ double fl_Q_0_snow(double m_snow, double thick_snow, 
 // mo_grav_drain.f90
 // ==========================================================================================
 
-// fl_grav_drain, mo_grav_drain.f90:74-201.  Scratch: w0 perm, w1 thick/perm, w2 harmonic_perm, fl_m.
-// The FORALL fl_up(k:N_active) += flux (:162-164) is a running sum in layer order; only element k
-// is clamped (:166), which the carry does not see -- same additions, O(N) instead of O(N^2).
+// fl_grav_drain, mo_grav_drain.f90:74-201.  Scratch: w0 perm, w1 thick/perm, w2 suffix-min(perm), fl_m.
+//
+// The reference evaluates, for every layer k, SUM_{kk=k}^{Na-1} thick(kk)/perm(kk) and SUM(thick(k:Na-1)) as fresh
+// forward sums (O(N^2), :115-120) and SUM(thick(k+1:Na-1)) for the height (:128).  Forward order is part of the
+// arithmetic contract, so the sums are kept as they are but evaluated for GB consecutive k at once with the GB
+// accumulators in registers: every thick/perm value is loaded once per block instead of once per k.
+// SUM(thick(k+1:Na-1)) of layer k is the same forward sum as SUM(thick(k':Na-1)) of layer k' = k+1.
+// The FORALL fl_up(k:N_active) += flux (:162-164) is a running sum in layer order; only element k is clamped
+// (:166), which the carry does not see -- same additions, O(N).
+#define SAMSIM_GB 8
 __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c) {
   const int Na = c.N_active, N = g.Nlayer;
   const double dt = g.dt;
-  Lay perm = c.w0, q = c.w1, hperm = c.w2, fl_m = c.fl_m;
+  Lay perm = c.w0, q = c.w1, smin = c.w2, fl_m = c.fl_m;
   double heat_loss = 0.0;
 
-  for (int k = 1; k <= N - 1; k++) c.ray[k] = 0.0;                                                  // :98
-  for (int k = 1; k <= Na; k++) perm[k] = 1e-17 * det_pow(1000.0 * fabs(c.psi_l[k]), 3.10);       // :104-106
+  for (int k = Na; k <= N - 1; k++) c.ray[k] = 0.0;  // :98 ray = 0 (entries below N_active are overwritten next)
   const double bottom_h = c.thick[Na] * c.psi_s[Na] / psi_s_min;  // thick(N_active)*psi_s(N_active)/psi_s_min
-
-  if (g.harmonic_flag == 2) {  // :109-123
-    for (int k = 1; k <= Na - 1; k++) q[k] = c.thick[k] / perm[k];
-    const double qb = bottom_h / perm[Na];
-    // suffix minimum of perm(k:Na-1) is order independent; walk k downwards to build it
+  // :104-106 permeability, thick/perm, and the order-independent suffix minimum of perm(k:Na-1), one backward pass
+  double perm_Na;
+  {
     double mn = 0.0;
-    for (int k = Na - 1; k >= 1; k--) {
-      double pk = perm[k];
+    for (int k = Na; k >= 1; k--) {
+      if (k - SAMSIM_PF >= 1) { c.psi_l.prefetch(k - SAMSIM_PF); c.thick.prefetch(k - SAMSIM_PF); }
+      const double pk = 1e-17 * det_pow(1000.0 * fabs(c.psi_l[k]), 3.10);
+      perm[k] = pk;
+      if (k == Na) { perm_Na = pk; continue; }
+      q[k] = c.thick[k] / pk;
       mn = (k == Na - 1) ? pk : f_min(mn, pk);
-      hperm[k] = mn;  // temporarily the suffix minimum
+      smin[k] = mn;
     }
-    for (int k = 1; k <= Na - 1; k++) {
-      if (hperm[k] < 1e-14) {
-        hperm[k] = 0.0;
-      } else {
-        double h = 0.0, th = 0.0;
-        for (int kk = k; kk <= Na - 1; kk++) h = h + q[kk];
-        h = h + qb;
-        for (int kk = k; kk <= Na - 1; kk++) th = th + c.thick[kk];
-        hperm[k] = (th + bottom_h) / h;
+    if (Na == 1) perm_Na = perm[1];
+  }
+  const double qb = bottom_h / perm_Na;
+  const double S_br_Na = c.S_br[Na];
+
+  // blocks of GB layers, from the bottom block upwards; `carry_t` = SUM(thick(k0+GB : Na-1)) of the block below
+  double carry_t = 0.0;
+  for (int k0 = ((Na - 2) / SAMSIM_GB) * SAMSIM_GB + 1; k0 >= 1 && Na >= 2; k0 -= SAMSIM_GB) {
+    double aq[SAMSIM_GB], at[SAMSIM_GB];
+#pragma unroll
+    for (int j = 0; j < SAMSIM_GB; j++) { aq[j] = 0.0; at[j] = 0.0; }
+#pragma unroll
+    for (int d = 0; d < SAMSIM_GB; d++) {  // triangular head: layer k0+d feeds accumulators 0..d
+      const int kk = k0 + d;
+      if (kk <= Na - 1) {
+        const double qv = q[kk], tv = c.thick[kk];
+#pragma unroll
+        for (int j = 0; j < SAMSIM_GB; j++)
+          if (j <= d) { aq[j] = aq[j] + qv; at[j] = at[j] + tv; }
       }
     }
-  }
-
-  const double S_br_Na = c.S_br[Na];
-  for (int k = 1; k <= Na - 1; k++) {  // :126-136
-    double d_S_br = c.S_br[k] - S_br_Na;
-    double height = sum_fwd(c.thick, k + 1, Na - 1) + bottom_h;
-    double r;
-    if (g.harmonic_flag == 1) {
-      double mn = perm[k];
-      for (int kk = k; kk <= Na; kk++) mn = f_min(mn, perm[kk]);
-      r = grav * rho_l * bbeta * d_S_br * height * mn;
-    } else {
-      r = grav * rho_l * bbeta * d_S_br * height * hperm[k];
+    for (int kk = k0 + SAMSIM_GB; kk <= Na - 1; kk++) {  // body: every accumulator takes every layer, in order
+      if (kk + SAMSIM_PF <= Na - 1) { q.prefetch(kk + SAMSIM_PF); c.thick.prefetch(kk + SAMSIM_PF); }
+      const double qv = q[kk], tv = c.thick[kk];
+#pragma unroll
+      for (int j = 0; j < SAMSIM_GB; j++) { aq[j] = aq[j] + qv; at[j] = at[j] + tv; }
     }
-    r = r / (kappa_l * mu);
-    c.ray[k] = f_max(r, 0.0);
+#pragma unroll
+    for (int j = SAMSIM_GB - 1; j >= 0; j--) {
+      const int k = k0 + j;
+      if (k <= Na - 1) {
+        // height = SUM(thick(k+1:Na-1)) + bottom_h, :128
+        const double below = (j == SAMSIM_GB - 1) ? carry_t : ((k + 1 <= Na - 1) ? at[(j + 1) % SAMSIM_GB] : 0.0);
+        const double height = below + bottom_h;
+        const double d_S_br = c.S_br[k] - S_br_Na;
+        double r;
+        if (g.harmonic_flag == 1) {
+          r = grav * rho_l * bbeta * d_S_br * height * f_min(smin[k], perm_Na);  // MINVAL(perm(k:N_active))
+        } else {
+          double hp;
+          if (smin[k] < 1e-14) {  // :112-113
+            hp = 0.0;
+          } else {                // :115-120
+            hp = aq[j] + qb;
+            hp = (at[j] + bottom_h) / hp;
+          }
+          r = grav * rho_l * bbeta * d_S_br * height * hp;
+        }
+        r = r / (kappa_l * mu);
+        c.ray[k] = f_max(r, 0.0);
+      }
+    }
+    carry_t = at[0];
   }
 
   SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) + sum_fwd(c.S_abs, 1, Na);  // :141 (inactive layers hold 0)
 
   double run = 0.0;  // running sum = fl_up(kk) for every kk not yet clamped
   fl_m[1] = 0.0;
+  double sbk = c.S_br[1];
   for (int k = 1; k <= Na - 1; k++) {  // :144-171
-    const double rk = c.ray[k], psk = c.psi_s[k], Sk = c.S_abs[k], mk = c.m[k], sbk = c.S_br[k];
+    if (k + SAMSIM_PF <= Na) {
+      c.ray.prefetch(k + SAMSIM_PF); c.psi_s.prefetch(k + SAMSIM_PF); c.S_abs.prefetch(k + SAMSIM_PF);
+      c.m.prefetch(k + SAMSIM_PF); c.S_br.prefetch(k + SAMSIM_PF);
+    }
+    const double rk = c.ray[k], psk = c.psi_s[k], Sk = c.S_abs[k], mk = c.m[k];
+    const double sbk1 = c.S_br[k + 1];
     double up = run;
-    if (rk > ray_crit && psk > 0.001 && Sk / mk > 0.1 && sbk > c.S_br[k + 1]) {
+    if (rk > ray_crit && psk > 0.001 && Sk / mk > 0.1 && sbk > sbk1) {
       const double plk = c.psi_l[k], thk = c.thick[k], Tk = c.T[k];
       double flux = x_grav * (rk - ray_crit) * dt * thk;
       flux = f_min(flux, plk * rho_l * thk);
@@ -681,6 +754,7 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c) {
       up = f_min(run, plk * rho_l * thk);
     }
     fl_m[k + 1] = up;  // fl_m(2:N_active+1) = fl_up(1:N_active), :177
+    sbk = sbk1;
   }
   fl_m[Na + 1] = run;
   const double fl_up_Na = run;

@@ -21,8 +21,13 @@ static_assert((int)SAMSIM_ARR_COUNT == (int)AR_STATE_COUNT, "array ids out of sy
 static_assert((int)SAMSIM_INT_COUNT == (int)IN_COUNT, "int ids out of sync with include/samsim_b200.h");
 static_assert((int)SAMSIM_SNAPSC_COUNT == 20 && (int)SAMSIM_SNAPARR_COUNT == 10, "snapshot layout");
 
+// Launch shape (measured on B200, profiles/README.md): 512-thread blocks, 2 blocks per SM (64 registers/thread,
+// 32 warps/SM) and a barrier between the phases of a step (SAMSIM_SYNC, step.cuh).
 #ifndef SAMSIM_BLOCK
-#define SAMSIM_BLOCK 128
+#define SAMSIM_BLOCK 512
+#endif
+#ifndef SAMSIM_MINBLOCKS
+#define SAMSIM_MINBLOCKS 2
 #endif
 #define SAMSIM_MAXWIN 24   // forcing records staged per launch (3-hourly): 22 * 10800 s of model time per launch
 #define SAMSIM_MAXSITE 16
@@ -61,7 +66,7 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem_src));
 }
 
-__global__ void __launch_bounds__(SAMSIM_BLOCK) samsim_step_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(SAMSIM_BLOCK, SAMSIM_MINBLOCKS) samsim_step_kernel(const __grid_constant__ KParams p) {
   __shared__ double s_win[SAMSIM_MAXSITE * 4 * SAMSIM_MAXWIN];
   // stage the forcing window: records win_first .. win_first+win_len-1 of every site/kind (cp.async)
   if (p.series != nullptr) {
@@ -75,14 +80,17 @@ __global__ void __launch_bounds__(SAMSIM_BLOCK) samsim_step_kernel(const __grid_
   }
   __syncthreads();
 
-  const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= p.ncol) return;
+  // Padding threads (col >= ncol, same block) stay in the loop for the phase barriers with status = -1; the
+  // buffers are allocated to ncol_pad so their loads are in bounds.
+  const long long col_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool padding = (col_raw >= p.ncol);
+  const long long col = padding ? (p.ncol - 1) : col_raw;
   const size_t ls = (size_t)p.ncol_pad;
   const size_t astr = (size_t)p.LS * ls;
 
   Col c;
   double* base = p.arr + col;
-#define BIND(field, id) c.field.p = base + (size_t)(id)*astr; c.field.ls = ls;
+#define BIND(field, id) c.field.p = base + (size_t)(id)*astr; c.field.ls = (unsigned)ls;
   BIND(m, AR_M) BIND(S_abs, AR_S_ABS) BIND(H_abs, AR_H_ABS) BIND(thick, AR_THICK) BIND(T, AR_T) BIND(phi, AR_PHI)
   BIND(S_bu, AR_S_BU) BIND(psi_s, AR_PSI_S) BIND(psi_l, AR_PSI_L) BIND(psi_g, AR_PSI_G) BIND(ray, AR_RAY)
   BIND(perm, AR_PERM) BIND(flush_v, AR_FLUSH_V) BIND(flush_h, AR_FLUSH_H) BIND(fl_Q, AR_FL_Q)
@@ -91,10 +99,11 @@ __global__ void __launch_bounds__(SAMSIM_BLOCK) samsim_step_kernel(const __grid_
 #undef BIND
   for (int q = 0; q < SC_COUNT; q++) c.sc[q] = p.sc[(size_t)q * ls + col];
   c.N_active = p.in[(size_t)IN_N_ACTIVE * ls + col];
-  c.status = p.in[(size_t)IN_STATUS * ls + col];
+  c.status = padding ? -1 : p.in[(size_t)IN_STATUS * ls + col];
   c.styropor_flag = p.in[(size_t)IN_STYROPOR * ls + col];
   c.time = p.time; c.i = p.i; c.n_time_out = p.n_time_out; c.time_counter = p.time_counter;
   c.fsw0 = c.fsw1 = c.flw0 = c.flw1 = c.ftime0 = c.ftime1 = 0.0;
+  c.thermo_valid = false;  // launch-local: the host may have changed the state between launches
 
   Forcing f;
   f.win = s_win; f.win_len = p.win_len; f.win_first = p.win_first;
@@ -109,13 +118,10 @@ __global__ void __launch_bounds__(SAMSIM_BLOCK) samsim_step_kernel(const __grid_
   SnapOut snap;
   snap.scalars = p.snap_sc; snap.arrays = p.snap_arr; snap.ncol_pad = ls; snap.col = (int)col;
 
-  if (c.status == 0) {
-    for (int s = 0; s < p.nsteps; s++) {
-      column_step(p.cfg, c, f, s == p.nsteps - 1, snap);
-      if (c.status) break;
-    }
-  }
+  // every thread runs every step: a failed column only skips the phase bodies (column_step checks c.status)
+  for (int s = 0; s < p.nsteps; s++) column_step(p.cfg, c, f, s == p.nsteps - 1, snap);
 
+  if (padding) return;
   for (int q = 0; q < SC_COUNT; q++) p.sc[(size_t)q * ls + col] = c.sc[q];
   p.in[(size_t)IN_N_ACTIVE * ls + col] = c.N_active;
   p.in[(size_t)IN_STATUS * ls + col] = c.status;
@@ -328,8 +334,12 @@ int samsim_b200_create(const samsim_config_t* cfg, int32_t ncol, int32_t device,
   h->cfg = *cfg;
   h->device = device;
   h->ncol = ncol;
-  h->ncol_pad = ((long long)ncol + 127) / 128 * 128;
+  h->ncol_pad = ((long long)ncol + SAMSIM_BLOCK - 1) / SAMSIM_BLOCK * SAMSIM_BLOCK;
   h->LS = cfg->Nlayer + 2;
+  if ((unsigned long long)h->LS * (unsigned long long)h->ncol_pad >= (1ull << 32)) {
+    delete h;
+    return fail(SAMSIM_ERR_ARG, "create: (Nlayer+2)*ncol must stay below 2^32 (32-bit layer-major index); use several handles");
+  }
   DevCfg& d = h->dcfg;
   memset(&d, 0, sizeof d);
   d.testcase = cfg->testcase; d.Nlayer = cfg->Nlayer; d.N_top = cfg->N_top; d.N_middle = cfg->N_middle; d.N_bottom = cfg->N_bottom;

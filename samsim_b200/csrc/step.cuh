@@ -243,6 +243,26 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
 
 // One loop iteration.  `last_of_launch` makes the S0 diagnostics observable through get_scalar
 // (they are otherwise only consumed by S8); `snap` receives the S8 record.
+// Phase synchronisation: with SAMSIM_SYNC=1 every warp of the block passes the same barrier between groups of
+// sub-steps, so all warps of the block execute the same few KB of code at the same time.  The step kernel is
+// ~600 KB of SASS and instruction fetch (stall_no_instruction), not the FP64 pipe, limits it otherwise.  The
+// barriers sit at block-uniform points: failed / padding columns skip the phase bodies but not the barriers.
+#ifndef SAMSIM_SYNC
+#define SAMSIM_SYNC 1
+#endif
+#if SAMSIM_SYNC
+#define SAMSIM_PHASE_SYNC() __syncthreads()
+#else
+#define SAMSIM_PHASE_SYNC() ((void)0)
+#endif
+// SAMSIM_SYNC=2 additionally re-aligns the warps after every layer of the two Newton sweeps (their trip counts
+// are data dependent); the sweeps then run a block-uniform Nlayer iterations with the body predicated on k <= N_active.
+#if SAMSIM_SYNC >= 2
+#define SAMSIM_LAYER_SYNC() __syncthreads()
+#else
+#define SAMSIM_LAYER_SYNC() ((void)0)
+#endif
+
 struct SnapOut {
   double* scalars;  // [SNAPSC_COUNT][ncol_pad] or nullptr
   double* arrays;   // [SNAPARR_COUNT][Nlayer+2][ncol_pad] or nullptr
@@ -277,6 +297,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   c.i = c.i + 1;
   const bool output_step = (c.n_time_out == g.i_time_out || c.i == 1);
 
+  if (c.status == 0) {  // ===== phase 0 =====
   // ---- S0 :192-223 (only observable at S8 or through get_scalar after the launch) ----
   if (output_step || want_diag) vital_signs(g, c);
 
@@ -323,27 +344,56 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
 
   // ---- S3 snow thermodynamics :273-292 ----
   snow_block(g, c);
-  if (c.status) return;
 
+  }
+  SAMSIM_PHASE_SYNC();
+#if SAMSIM_SYNC >= 2
+  {  // ===== phase 1: the sweep is block-uniform (barrier per layer), its body checks c.status =====
+#else
+  if (c.status == 0) {  // ===== phase 1 =====
+#endif
   // ---- S4 backward sweep: S_bu, H -> T, phi -> S_br -> volume fractions :298-307 ----
+  // When nothing touched m, S_abs, H_abs of layers 2..N_active since the S18 sweep of the previous step
+  // (c.thermo_valid), getT would be called with the same H, S_bu and the same chained first guess and return the
+  // same T, phi: those layers skip the Newton iterations.  Layer 1 (snow, precipitation, melt water) is always
+  // recomputed.  Expulsion depends on phi from S18, so it is evaluated every step.
   {
     double T_test = SCV(c, SC_T_BOTTOM);
+    const bool reuse = c.thermo_valid;
+#if SAMSIM_SYNC >= 2
+    for (int k = g.Nlayer; k >= 1; k--) {
+      SAMSIM_LAYER_SYNC();
+      if (k > c.N_active || c.status != 0) continue;
+#else
     for (int k = c.N_active; k >= 1; k--) {
+#endif
+      if (k - SAMSIM_PF >= 1) {
+        c.m.prefetch(k - SAMSIM_PF); c.thick.prefetch(k - SAMSIM_PF);
+        if (reuse) { c.T.prefetch(k - SAMSIM_PF); c.phi.prefetch(k - SAMSIM_PF); c.S_bu.prefetch(k - SAMSIM_PF); }
+        else { c.S_abs.prefetch(k - SAMSIM_PF); c.H_abs.prefetch(k - SAMSIM_PF); }
+      }
       const double mk = c.m[k];
-      const double sbu = c.S_abs[k] / mk;
-      const double H = c.H_abs[k] / mk;
-      double T, phi = c.phi[k];
-      getT(g, H, sbu, T_test, T, phi, c.status);
+      double sbu, T, phi;
+      if (reuse && k >= 2) {
+        sbu = c.S_bu[k]; T = c.T[k]; phi = c.phi[k];
+      } else {
+        sbu = c.S_abs[k] / mk;
+        const double H = c.H_abs[k] / mk;
+        phi = c.phi[k];
+        getT(g, H, sbu, T_test, T, phi, c.status);
+        c.S_bu[k] = sbu; c.T[k] = T; c.phi[k] = phi;
+      }
       T_test = T;
-      c.S_bu[k] = sbu; c.T[k] = T; c.phi[k] = phi;
       c.S_br[k] = S_br_of(g, T, sbu);
       double ps, pl, pg, vex;
       expulsion(phi, c.thick[k], mk, ps, pl, pg, vex);
       c.psi_s[k] = ps; c.psi_l[k] = pl; c.psi_g[k] = pg; c.V_ex[k] = vex;
     }
-    if (c.status) return;
-  }
+    }
 
+  }
+  SAMSIM_PHASE_SYNC();
+  if (c.status == 0) {  // ===== phase 2 =====
   // ---- S5 expulsion_flux (mo_mass.f90:112-136) then mass_transfer (skipped at i == 1) :312-321 ----
   {
     const int Na = c.N_active;
@@ -391,6 +441,9 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     c.n_time_out = c.n_time_out + 1;
   }
 
+  }
+  SAMSIM_PHASE_SYNC();
+  if (c.status == 0) {  // ===== phase 3 =====
   // ---- S9 gas in the lowest layer :405-410 ----
   {
     const int Na = c.N_active;
@@ -408,8 +461,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     double H1 = c.H_abs[1], phi1 = c.phi[1], T1 = c.T[1];
     snow_coupling(g, c, H1, phi1, T1, c.m[1], c.S_bu[1]);
     c.H_abs[1] = H1; c.phi[1] = phi1; c.T[1] = T1;
-    if (c.status) return;
-  }
+    }
 
   // ---- S11 flooding :428-445 ----
   if (c.N_active > 1 && g.flood_flag > 1) {
@@ -428,11 +480,16 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     c.S_abs[Na] = S - turb * (S / mNa - SCV(c, SC_S_BU_BOTTOM));
   }
 
+  }
+  SAMSIM_PHASE_SYNC();
+  if (c.status == 0) {  // ===== phase 4 =====
   // ---- S13 gravity drainage :463-477 ----
   if (g.grav_flag == 2 && c.N_active > 1) grav_drain(g, c);
   else if (g.grav_flag == 3 && c.N_active > 1) grav_drain_simple(g, c);
-  if (c.status) return;
 
+  }
+  SAMSIM_PHASE_SYNC();
+  if (c.status == 0) {  // ===== phase 5 =====
   // ---- S15 testcase hooks :503-563 ----
   if (g.testcase == 1) {  // sub_test1, mo_testcase_specifics.f90:42-89
     const double j = rint(c.time / 43200.0);
@@ -459,12 +516,25 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
 
   // ---- S17 heat fluxes :584 ----
   heat_fluxes(g, c);
-  if (c.status) return;
 
+  }
+  SAMSIM_PHASE_SYNC();
+#if SAMSIM_SYNC >= 2
+  {  // ===== phase 6: the sweep is block-uniform (barrier per layer), its body checks c.status =====
+#else
+  if (c.status == 0) {  // ===== phase 6 =====
+#endif
   // ---- S18 second backward sweep :592-598 (psi_* are NOT refreshed) ----
   {
     double T_test = SCV(c, SC_T_BOTTOM);
+#if SAMSIM_SYNC >= 2
+    for (int k = g.Nlayer; k >= 1; k--) {
+      SAMSIM_LAYER_SYNC();
+      if (k > c.N_active || c.status != 0) continue;
+#else
     for (int k = c.N_active; k >= 1; k--) {
+#endif
+      if (k - SAMSIM_PF >= 1) { c.m.prefetch(k - SAMSIM_PF); c.S_abs.prefetch(k - SAMSIM_PF); c.H_abs.prefetch(k - SAMSIM_PF); c.phi.prefetch(k - SAMSIM_PF); }
       const double mk = c.m[k];
       const double sbu = c.S_abs[k] / mk;
       const double H = c.H_abs[k] / mk;
@@ -473,13 +543,15 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
       T_test = T;
       c.S_bu[k] = sbu; c.T[k] = T; c.phi[k] = phi;
     }
-    if (c.status) return;
+      c.thermo_valid = true;  // invalidated below by anything that touches layers >= 2
   }
 
+  }
+  SAMSIM_PHASE_SYNC();
+  if (c.status == 0) {  // ===== phase 7 =====
   // ---- S19 snow thermodynamics #2 :600-625 ----
   SCV(c, SC_MELT_THICK_SNOW_OLD) = SCV(c, SC_MELT_THICK_SNOW);
   snow_block(g, c);
-  if (c.status) return;
   SCV(c, SC_MELT_THICK_SNOW) = SCV(c, SC_MELT_THICK_SNOW_OLD) + SCV(c, SC_MELT_THICK_SNOW);
 
   // ---- S20 flushing preparations :632-664 ----
@@ -538,25 +610,28 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
         Lay old_v = c.V_ex, old_h = c.S_br;  // both dead after S13
         for (int k = 1; k <= Na; k++) { old_v[k] = c.flush_v[k]; old_h[k] = c.flush_h[k]; }
         flush3(g, c);
+        c.thermo_valid = false;
         for (int k = 1; k <= Na; k++) { c.flush_v[k] = c.flush_v[k] + old_v[k]; c.flush_h[k] = c.flush_h[k] + old_h[k]; }
-        if (c.status) return;
-      }
+            }
     } else if (g.flush_flag == 6) {  // :729-733
       if (SCV(c, SC_MELT_THICK) > 0.000000000001 && c.N_active > 2 && SCV(c, SC_THICK_SNOW) < g.thick_0) {
         flush4(g, c);
-        if (c.status) return;
-      }
+        c.thermo_valid = false;
+            }
     }
   }
 
+  }
+  SAMSIM_PHASE_SYNC();
+  if (c.status == 0) {  // ===== phase 8 =====
   // ---- S23 layer dynamics :755-795 ----
   if (c.N_active > 1) {
     const int Na = c.N_active;
     const double r1 = c.thick[1] / g.thick_0;
     if (c.phi[Na] > psi_s_min || c.phi[Na - 1] <= psi_s_min / 2.0 || r1 > 1.5 || r1 < 0.5) {
       layer_dynamics(g, c);
-      if (c.status) return;
-    }
+      c.thermo_valid = false;
+        }
     const int Nb = c.N_active;
     if (Nb < N && c.thick[(Nb + 1 < N) ? Nb + 1 : N] == 0) {  // :772-783 scrub
       c.T[Nb + 1] = SCV(c, SC_T_BOTTOM);
@@ -565,9 +640,8 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
       c.psi_s[Nb + 1] = 0.0;
     }
   } else {
-    if (c.phi[1] > psi_s_min) layer_dynamics(g, c);
-    if (c.status) return;
-  }
+    if (c.phi[1] > psi_s_min) { layer_dynamics(g, c); c.thermo_valid = false; }
+    }
 
   // ---- S24 timestep + health check :802-819 ----
   c.time = c.time + dt;
@@ -579,8 +653,11 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
       c.status = 1337;
     } else if (ms < 0.0) {
       for (int k = 1; k <= Na; k++) c.S_abs[k] = f_max(c.S_abs[k], 0.0);
+      c.thermo_valid = false;
     }
   }
+  }
+  SAMSIM_PHASE_SYNC();
 }
 
 }  // namespace samsim
