@@ -72,14 +72,41 @@ struct Lay {
 };
 #define SAMSIM_PF 4  // prefetch distance in layers
 
-// everything one thread needs
+// everything one thread needs.  The per-layer views are built on the fly from three registers (base, ls, astr)
+// instead of being stored: 22 stored views were 350 B of local memory per thread and two local loads per access.
 struct Col {
-  Lay m, S_abs, H_abs, thick, T, phi, S_bu, psi_s, psi_l, psi_g, ray, perm, flush_v, flush_h, fl_Q;
-  Lay S_br, V_ex, fl_m, w0, w1, w2, w3;
+  double* base;    // &arr[col]
+  unsigned ls;     // ncol_pad
+  unsigned astr;   // (Nlayer+2)*ncol_pad: elements between consecutive arrays
+  __device__ __forceinline__ Lay A(int id) const { return Lay{base + (size_t)((unsigned)id * astr), ls}; }
+  __device__ __forceinline__ Lay m() const { return A(AR_M); }
+  __device__ __forceinline__ Lay S_abs() const { return A(AR_S_ABS); }
+  __device__ __forceinline__ Lay H_abs() const { return A(AR_H_ABS); }
+  __device__ __forceinline__ Lay thick() const { return A(AR_THICK); }
+  __device__ __forceinline__ Lay T() const { return A(AR_T); }
+  __device__ __forceinline__ Lay phi() const { return A(AR_PHI); }
+  __device__ __forceinline__ Lay S_bu() const { return A(AR_S_BU); }
+  __device__ __forceinline__ Lay psi_s() const { return A(AR_PSI_S); }
+  __device__ __forceinline__ Lay psi_l() const { return A(AR_PSI_L); }
+  __device__ __forceinline__ Lay psi_g() const { return A(AR_PSI_G); }
+  __device__ __forceinline__ Lay ray() const { return A(AR_RAY); }
+  __device__ __forceinline__ Lay perm() const { return A(AR_PERM); }
+  __device__ __forceinline__ Lay flush_v() const { return A(AR_FLUSH_V); }
+  __device__ __forceinline__ Lay flush_h() const { return A(AR_FLUSH_H); }
+  __device__ __forceinline__ Lay fl_Q() const { return A(AR_FL_Q); }
+  __device__ __forceinline__ Lay S_br() const { return A(AR_S_BR); }
+  __device__ __forceinline__ Lay V_ex() const { return A(AR_V_EX); }
+  __device__ __forceinline__ Lay fl_m() const { return A(AR_FL_M); }
+  __device__ __forceinline__ Lay w0() const { return A(AR_W0); }
+  __device__ __forceinline__ Lay w1() const { return A(AR_W1); }
+  __device__ __forceinline__ Lay w2() const { return A(AR_W2); }
+  __device__ __forceinline__ Lay w3() const { return A(AR_W3); }
   int N_active, status, styropor_flag;
   // T, phi, S_bu of layers 2..N_active still equal what the S18 sweep of the previous step produced and
   // m, S_abs, H_abs of those layers are untouched since: the S4 sweep may reuse them (bit-identical result)
   bool thermo_valid;
+  // last step of the launch: arrays that are only observable through get_array (fl_Q(2:)) are written
+  bool want_state;
   double sc[SC_COUNT];
   // clock (shared by the batch, advanced in lock step)
   double time;
@@ -290,10 +317,10 @@ __device__ __noinline__ double freeboard_of(const DevCfg& g, const Col& c) {
   const double snowmass = (g.freeboard_snow_flag == 0) ? SCV(c, SC_M_SNOW) : 0.0;
   double A = 0.0, G = 0.0;  // forward totals, the reference's order
   for (int q = 1; q <= Na; q++) {
-    if (q + SAMSIM_PF <= Na) { c.psi_s.prefetch(q + SAMSIM_PF); c.psi_g.prefetch(q + SAMSIM_PF); c.thick.prefetch(q + SAMSIM_PF); }
-    const double t = c.thick[q];
-    A = A + c.psi_s[q] * t;
-    G = G + c.psi_g[q] * t;
+    if (q + SAMSIM_PF <= Na) { c.psi_s().prefetch(q + SAMSIM_PF); c.psi_g().prefetch(q + SAMSIM_PF); c.thick().prefetch(q + SAMSIM_PF); }
+    const double t = c.thick()[q];
+    A = A + c.psi_s()[q] * t;
+    G = G + c.psi_g()[q] * t;
   }
   const double buoy = A * (rho_l - rho_s) + G * rho_l;
   double freeboard;
@@ -306,11 +333,11 @@ __device__ __noinline__ double freeboard_of(const DevCfg& g, const Col& c) {
     int k = 0;
     while (test1 < test2) {  // :114-118
       k = k + 1;
-      const double t = c.thick[k];
-      pA = pA + c.psi_s[k] * t;   // same partial sums as the forward totals above
-      pG = pG + c.psi_g[k] * t;
+      const double t = c.thick()[k];
+      pA = pA + c.psi_s()[k] * t;   // same partial sums as the forward totals above
+      pG = pG + c.psi_g()[k] * t;
       msum_prev = msum;
-      msum = msum + c.m[k];       // SUM(m(1:k)): fixed-start prefix, incremental is the same order
+      msum = msum + c.m()[k];       // SUM(m(1:k)): fixed-start prefix, incremental is the same order
       thsum_prev = thsum;
       thsum = thsum + t;          // SUM(thick(1:k)) likewise
       test1 = msum + snowmass;
@@ -318,11 +345,11 @@ __device__ __noinline__ double freeboard_of(const DevCfg& g, const Col& c) {
       if (test1 < approx - margin) {
         test2 = approx + margin;  // certainly test1 < exact test2: keep looping (value unused)
       } else {
-        test2 = sum_prod_fwd(c.psi_s, c.thick, k + 1, Na) * (rho_l - rho_s) + sum_prod_fwd(c.psi_g, c.thick, k + 1, Na) * rho_l;
+        test2 = sum_prod_fwd(c.psi_s(), c.thick(), k + 1, Na) * (rho_l - rho_s) + sum_prod_fwd(c.psi_g(), c.thick(), k + 1, Na) * rho_l;
       }
     }
     test1 = msum_prev + snowmass;  // :121 SUM(m(1:k-1))
-    const double mk = c.m[k], tk = c.thick[k];
+    const double mk = c.m()[k], tk = c.thick()[k];
     freeboard = test2 - test1 + (rho_l - mk / tk) * tk;  // :124
     freeboard = freeboard / rho_l;
     freeboard = freeboard + thsum_prev;                  // :126 SUM(thick(1:k-1))
@@ -379,45 +406,57 @@ __device__ __forceinline__ void melt_snow(double& melt_thick, double& thick, dou
 // mo_mass.f90
 // ==========================================================================================
 
+// One layer of mass_transfer, mo_mass.f90:76-95.  f1 = fl_m(k+1), f0 = fl_m(k); *_km1 / *_kp1 are the neighbours
+// (TT, SS_bu, SS_abs of the reference; Sabs_km1 is the ALREADY UPDATED S_abs(k-1), :91).  H, S = H_abs(k), S_abs(k).
+__device__ __forceinline__ void mass_transfer_layer(const DevCfg& g, double f1, double f0, double T_km1, double Sbu_km1,
+                                                    double Sabs_km1, double T_k, double Sbu_k, double T_kp1,
+                                                    double Sbu_kp1, double Sabs_kp1, double& H, double& S) {
+  if (f1 > 0.) {
+    H = H + f1 * T_kp1 * c_l;
+    S = S + f_min(f1 * S_br_of(g, T_kp1, Sbu_kp1), Sabs_kp1);
+  } else if (f1 < 0.) {
+    H = H + f1 * T_k * c_l;
+    S = S + f_max(f1 * S_br_of(g, T_k, Sbu_k), -S);
+  }
+  if (f0 > 0.) {
+    H = H - f0 * T_k * c_l;
+    S = S - f_min(f0 * S_br_of(g, T_k, Sbu_k), S);
+  } else if (f0 < 0) {
+    H = H - f0 * T_km1 * c_l;
+    S = S - f_max(f0 * S_br_of(g, T_km1, Sbu_km1), -Sabs_km1);
+  }
+}
+
 // mass_transfer, mo_mass.f90:53-96, as ONE in-place forward pass.  The reference copies T, S_bu and
 // S_abs into TT/SS_bu/SS_abs first; T and S_bu are not modified by the routine and SS_abs(k+1)
 // is read before layer k+1 is updated, so reading the live arrays is equivalent.  S_abs(k-1)
 // in the last branch IS the updated value in the reference too (:91).
-__device__ __noinline__ void mass_transfer(const DevCfg& g, Col& c, const Lay& fl_m) {
+__device__ __noinline__ void mass_transfer(const DevCfg& g, Col& c, const Lay& fl_m, const Lay& S_bu_view) {
   const int Na = c.N_active;
   const double T_bottom = SCV(c, SC_T_BOTTOM), S_bu_bottom = SCV(c, SC_S_BU_BOTTOM);
   double T_km1 = 0.0, Sbu_km1 = 0.0, Sabs_km1 = 0.0;  // k = 1: fl_m(1) == 0 at every call site, never read
-  double T_k = c.T[1], Sbu_k = c.S_bu[1];
+  double T_k = c.T()[1], Sbu_k = S_bu_view[1];
   double f0 = fl_m[1];
   for (int k = 1; k <= Na; k++) {
+    if (k + SAMSIM_PF <= Na) {
+      c.T().prefetch(k + SAMSIM_PF); S_bu_view.prefetch(k + SAMSIM_PF); c.S_abs().prefetch(k + SAMSIM_PF);
+      c.H_abs().prefetch(k + SAMSIM_PF); fl_m.prefetch(k + SAMSIM_PF);
+    }
     double T_kp1, Sbu_kp1, Sabs_kp1;
     if (k < Na) {
-      T_kp1 = c.T[k + 1];
-      Sbu_kp1 = c.S_bu[k + 1];
-      Sabs_kp1 = c.S_abs[k + 1];
+      T_kp1 = c.T()[k + 1];
+      Sbu_kp1 = S_bu_view[k + 1];
+      Sabs_kp1 = c.S_abs()[k + 1];
     } else {
       T_kp1 = T_bottom;
       Sbu_kp1 = S_bu_bottom;
       Sabs_kp1 = S_bu_bottom * 2000.0;
     }
     const double f1 = fl_m[k + 1];
-    double H = c.H_abs[k], S = c.S_abs[k];
-    if (f1 > 0.) {
-      H = H + f1 * T_kp1 * c_l;
-      S = S + f_min(f1 * S_br_of(g, T_kp1, Sbu_kp1), Sabs_kp1);
-    } else if (f1 < 0.) {
-      H = H + f1 * T_k * c_l;
-      S = S + f_max(f1 * S_br_of(g, T_k, Sbu_k), -S);
-    }
-    if (f0 > 0.) {
-      H = H - f0 * T_k * c_l;
-      S = S - f_min(f0 * S_br_of(g, T_k, Sbu_k), S);
-    } else if (f0 < 0) {
-      H = H - f0 * T_km1 * c_l;
-      S = S - f_max(f0 * S_br_of(g, T_km1, Sbu_km1), -Sabs_km1);
-    }
-    c.H_abs[k] = H;
-    c.S_abs[k] = S;
+    double H = c.H_abs()[k], S = c.S_abs()[k];
+    mass_transfer_layer(g, f1, f0, T_km1, Sbu_km1, Sabs_km1, T_k, Sbu_k, T_kp1, Sbu_kp1, Sabs_kp1, H, S);
+    c.H_abs()[k] = H;
+    c.S_abs()[k] = S;
     T_km1 = T_k; Sbu_km1 = Sbu_k; Sabs_km1 = S;
     T_k = T_kp1; Sbu_k = Sbu_kp1;
     f0 = f1;
@@ -598,7 +637,7 @@ __device__ __noinline__ void snow_thermo(const DevCfg& g, Col& c, bool meltwater
 // the driver's snow block, mo_grotz.f90:273-292 and :601-621
 __device__ __forceinline__ void snow_block(const DevCfg& g, Col& c) {
   if (SCV(c, SC_THICK_SNOW) > 0.0) {
-    double m1 = c.m[1], th1 = c.thick[1], H1 = c.H_abs[1];
+    double m1 = c.m()[1], th1 = c.thick()[1], H1 = c.H_abs()[1];
     if (g.snow_flush_flag == 0) {
       double dummy = 0.0;
       snow_thermo(g, c, false, m1, th1, H1, dummy);
@@ -607,7 +646,7 @@ __device__ __forceinline__ void snow_block(const DevCfg& g, Col& c) {
       SCV(c, SC_MELT_THICK_SNOW) = 0.0;
       snow_thermo(g, c, true, m1, th1, H1, SCV(c, SC_MELT_THICK_SNOW));
     }
-    c.m[1] = m1; c.thick[1] = th1; c.H_abs[1] = H1;
+    c.m()[1] = m1; c.thick()[1] = th1; c.H_abs()[1] = H1;
   } else {
     SCV(c, SC_THICK_SNOW) = 0.0; SCV(c, SC_M_SNOW) = 0.0; SCV(c, SC_PSI_S_SNOW) = 0.0; SCV(c, SC_PSI_L_SNOW) = 0.0;
     SCV(c, SC_PSI_G_SNOW) = 0.0; SCV(c, SC_H_ABS_SNOW) = 0.0; SCV(c, SC_S_ABS_SNOW) = 0.0;
@@ -654,28 +693,26 @@ __device__ __forceinline__ double fl_Q_0_snow(double m_snow, double thick_snow, 
 __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c) {
   const int Na = c.N_active, N = g.Nlayer;
   const double dt = g.dt;
-  Lay perm = c.w0, q = c.w1, smin = c.w2, fl_m = c.fl_m;
+  Lay q = c.w1(), smin = c.w2(), fl_m = c.fl_m();
   double heat_loss = 0.0;
 
-  for (int k = Na; k <= N - 1; k++) c.ray[k] = 0.0;  // :98 ray = 0 (entries below N_active are overwritten next)
-  const double bottom_h = c.thick[Na] * c.psi_s[Na] / psi_s_min;  // thick(N_active)*psi_s(N_active)/psi_s_min
+  for (int k = Na; k <= N - 1; k++) c.ray()[k] = 0.0;  // :98 ray = 0 (entries below N_active are overwritten next)
+  const double bottom_h = c.thick()[Na] * c.psi_s()[Na] / psi_s_min;  // thick(N_active)*psi_s(N_active)/psi_s_min
   // :104-106 permeability, thick/perm, and the order-independent suffix minimum of perm(k:Na-1), one backward pass
-  double perm_Na;
+  double perm_Na = 0.0;
   {
     double mn = 0.0;
     for (int k = Na; k >= 1; k--) {
-      if (k - SAMSIM_PF >= 1) { c.psi_l.prefetch(k - SAMSIM_PF); c.thick.prefetch(k - SAMSIM_PF); }
-      const double pk = 1e-17 * det_pow(1000.0 * fabs(c.psi_l[k]), 3.10);
-      perm[k] = pk;
-      if (k == Na) { perm_Na = pk; continue; }
-      q[k] = c.thick[k] / pk;
+      if (k - SAMSIM_PF >= 1) { c.psi_l().prefetch(k - SAMSIM_PF); c.thick().prefetch(k - SAMSIM_PF); }
+      const double pk = 1e-17 * det_pow(1000.0 * fabs(c.psi_l()[k]), 3.10);
+      if (k == Na) { perm_Na = pk; continue; }  // perm itself is not needed again: only thick/perm and the suffix minimum
+      q[k] = c.thick()[k] / pk;
       mn = (k == Na - 1) ? pk : f_min(mn, pk);
       smin[k] = mn;
     }
-    if (Na == 1) perm_Na = perm[1];
   }
   const double qb = bottom_h / perm_Na;
-  const double S_br_Na = c.S_br[Na];
+  const double S_br_Na = c.S_br()[Na];
 
   // blocks of GB layers, from the bottom block upwards; `carry_t` = SUM(thick(k0+GB : Na-1)) of the block below
   double carry_t = 0.0;
@@ -687,15 +724,15 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c) {
     for (int d = 0; d < SAMSIM_GB; d++) {  // triangular head: layer k0+d feeds accumulators 0..d
       const int kk = k0 + d;
       if (kk <= Na - 1) {
-        const double qv = q[kk], tv = c.thick[kk];
+        const double qv = q[kk], tv = c.thick()[kk];
 #pragma unroll
         for (int j = 0; j < SAMSIM_GB; j++)
           if (j <= d) { aq[j] = aq[j] + qv; at[j] = at[j] + tv; }
       }
     }
     for (int kk = k0 + SAMSIM_GB; kk <= Na - 1; kk++) {  // body: every accumulator takes every layer, in order
-      if (kk + SAMSIM_PF <= Na - 1) { q.prefetch(kk + SAMSIM_PF); c.thick.prefetch(kk + SAMSIM_PF); }
-      const double qv = q[kk], tv = c.thick[kk];
+      if (kk + SAMSIM_PF <= Na - 1) { q.prefetch(kk + SAMSIM_PF); c.thick().prefetch(kk + SAMSIM_PF); }
+      const double qv = q[kk], tv = c.thick()[kk];
 #pragma unroll
       for (int j = 0; j < SAMSIM_GB; j++) { aq[j] = aq[j] + qv; at[j] = at[j] + tv; }
     }
@@ -706,7 +743,7 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c) {
         // height = SUM(thick(k+1:Na-1)) + bottom_h, :128
         const double below = (j == SAMSIM_GB - 1) ? carry_t : ((k + 1 <= Na - 1) ? at[(j + 1) % SAMSIM_GB] : 0.0);
         const double height = below + bottom_h;
-        const double d_S_br = c.S_br[k] - S_br_Na;
+        const double d_S_br = c.S_br()[k] - S_br_Na;
         double r;
         if (g.harmonic_flag == 1) {
           r = grav * rho_l * bbeta * d_S_br * height * f_min(smin[k], perm_Na);  // MINVAL(perm(k:N_active))
@@ -721,34 +758,34 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c) {
           r = grav * rho_l * bbeta * d_S_br * height * hp;
         }
         r = r / (kappa_l * mu);
-        c.ray[k] = f_max(r, 0.0);
+        c.ray()[k] = f_max(r, 0.0);
       }
     }
     carry_t = at[0];
   }
 
-  SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) + sum_fwd(c.S_abs, 1, Na);  // :141 (inactive layers hold 0)
+  SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) + sum_fwd(c.S_abs(), 1, Na);  // :141 (inactive layers hold 0)
 
   double run = 0.0;  // running sum = fl_up(kk) for every kk not yet clamped
   fl_m[1] = 0.0;
-  double sbk = c.S_br[1];
+  double sbk = c.S_br()[1];
   for (int k = 1; k <= Na - 1; k++) {  // :144-171
     if (k + SAMSIM_PF <= Na) {
-      c.ray.prefetch(k + SAMSIM_PF); c.psi_s.prefetch(k + SAMSIM_PF); c.S_abs.prefetch(k + SAMSIM_PF);
-      c.m.prefetch(k + SAMSIM_PF); c.S_br.prefetch(k + SAMSIM_PF);
+      c.ray().prefetch(k + SAMSIM_PF); c.psi_s().prefetch(k + SAMSIM_PF); c.S_abs().prefetch(k + SAMSIM_PF);
+      c.m().prefetch(k + SAMSIM_PF); c.S_br().prefetch(k + SAMSIM_PF);
     }
-    const double rk = c.ray[k], psk = c.psi_s[k], Sk = c.S_abs[k], mk = c.m[k];
-    const double sbk1 = c.S_br[k + 1];
+    const double rk = c.ray()[k], psk = c.psi_s()[k], Sk = c.S_abs()[k], mk = c.m()[k];
+    const double sbk1 = c.S_br()[k + 1];
     double up = run;
     if (rk > ray_crit && psk > 0.001 && Sk / mk > 0.1 && sbk > sbk1) {
-      const double plk = c.psi_l[k], thk = c.thick[k], Tk = c.T[k];
+      const double plk = c.psi_l()[k], thk = c.thick()[k], Tk = c.T()[k];
       double flux = x_grav * (rk - ray_crit) * dt * thk;
       flux = f_min(flux, plk * rho_l * thk);
       double Snew = Sk - flux * sbk;
-      c.S_abs[k] = Snew;
+      c.S_abs()[k] = Snew;
       if (Snew < 0.0) { c.status = 21234; return; }
       SCV(c, SC_GRAV_TEMP) = SCV(c, SC_GRAV_TEMP) + flux * Tk;
-      c.H_abs[k] = c.H_abs[k] - flux * c_l * Tk;
+      c.H_abs()[k] = c.H_abs()[k] - flux * c_l * Tk;
       heat_loss = heat_loss + flux * c_l * Tk;
       run = run + flux;
       up = f_min(run, plk * rho_l * thk);
@@ -759,24 +796,24 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c) {
   fl_m[Na + 1] = run;
   const double fl_up_Na = run;
 
-  SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) - sum_fwd(c.S_abs, 1, Na);  // :173
+  SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) - sum_fwd(c.S_abs(), 1, Na);  // :173
 
-  mass_transfer(g, c, fl_m);  // :188
+  mass_transfer(g, c, fl_m, c.S_bu());  // :188
 
   SCV(c, SC_GRAV_DRAIN) = SCV(c, SC_GRAV_DRAIN) + fl_m[Na + 1];  // :190
-  if (g.grav_heat_flag == 2) c.H_abs[Na] = c.H_abs[Na] + heat_loss - fl_up_Na * c_l * SCV(c, SC_T_BOTTOM);  // :193-195
-  double mn = c.S_abs[1];
-  for (int k = 2; k <= Na; k++) mn = f_min(mn, c.S_abs[k]);
+  if (g.grav_heat_flag == 2) c.H_abs()[Na] = c.H_abs()[Na] + heat_loss - fl_up_Na * c_l * SCV(c, SC_T_BOTTOM);  // :193-195
+  double mn = c.S_abs()[1];
+  for (int k = 2; k <= Na; k++) mn = f_min(mn, c.S_abs()[k]);
   if (f_min(mn, 0.0) < 0.0) c.status = 1337;  // :198 MINVAL over all layers (inactive are 0)
 }
 
 // fl_grav_drain_simple, mo_grav_drain.f90:218-279 (grav_flag 3)
 __device__ __noinline__ void grav_drain_simple(const DevCfg& g, Col& c) {
   const int Na = c.N_active, N = g.Nlayer;
-  Lay perm = c.w0, hperm = c.w2;
-  for (int k = 1; k <= N - 1; k++) c.ray[k] = 0.0;
-  for (int k = 1; k <= Na; k++) perm[k] = 1e-17 * det_pow(1000.0 * fabs(c.psi_l[k]), 3.10);
-  const double bottom_h = c.thick[Na] * c.psi_s[Na] / psi_s_min;
+  Lay perm = c.w0(), hperm = c.w2();
+  for (int k = 1; k <= N - 1; k++) c.ray()[k] = 0.0;
+  for (int k = 1; k <= Na; k++) perm[k] = 1e-17 * det_pow(1000.0 * fabs(c.psi_l()[k]), 3.10);
+  const double bottom_h = c.thick()[Na] * c.psi_s()[Na] / psi_s_min;
   if (g.harmonic_flag == 2) {
     for (int k = 1; k <= Na - 1; k++) {
       double mn = perm[k];
@@ -785,16 +822,16 @@ __device__ __noinline__ void grav_drain_simple(const DevCfg& g, Col& c) {
         hperm[k] = 0.0;
       } else {
         double h = 0.0;
-        for (int kk = k; kk <= Na - 1; kk++) h = h + c.thick[kk] / perm[kk];
+        for (int kk = k; kk <= Na - 1; kk++) h = h + c.thick()[kk] / perm[kk];
         h = h + bottom_h / perm[Na];
-        hperm[k] = (sum_fwd(c.thick, k, Na - 1) + bottom_h) / h;
+        hperm[k] = (sum_fwd(c.thick(), k, Na - 1) + bottom_h) / h;
       }
     }
   }
-  const double S_br_Na = c.S_br[Na];
+  const double S_br_Na = c.S_br()[Na];
   for (int k = 1; k <= Na - 1; k++) {
-    double d_S_br = c.S_br[k] - S_br_Na;
-    double height = sum_fwd(c.thick, k + 1, Na - 1) + bottom_h;
+    double d_S_br = c.S_br()[k] - S_br_Na;
+    double height = sum_fwd(c.thick(), k + 1, Na - 1) + bottom_h;
     double r;
     if (g.harmonic_flag == 1) {
       double mn = perm[k];
@@ -804,10 +841,10 @@ __device__ __noinline__ void grav_drain_simple(const DevCfg& g, Col& c) {
       r = grav * rho_l * bbeta * d_S_br * height * hperm[k];
     }
     r = r / (kappa_l * mu);
-    c.ray[k] = f_max(r, 0.0);
+    c.ray()[k] = f_max(r, 0.0);
   }
   for (int k = Na - 1; k >= 1; k--)
-    if (c.ray[k] > ray_crit) c.S_abs[k] = c.S_abs[k] * SAMSIM_F32(0.99);
+    if (c.ray()[k] > ray_crit) c.S_abs()[k] = c.S_abs()[k] * SAMSIM_F32(0.99);
   SCV(c, SC_GRAV_DRAIN) = 0.0;
 }
 
@@ -823,19 +860,19 @@ __device__ __noinline__ void flood(const DevCfg& g, Col& c) {
   double& H_abs_snow = SCV(c, SC_H_ABS_SNOW);
   double& m_snow = SCV(c, SC_M_SNOW);
   double hp = 0.0;
-  for (int k = 1; k <= Na - 1; k++) hp = hp + c.thick[k] / (1e-17 * det_pow(1000.0 * c.psi_l[k], 3.10));  // :73-79
-  const double bottom_h = c.thick[Na] * c.psi_s[Na] / psi_s_min;
-  hp = hp + bottom_h / (1e-17 * det_pow(1000.0 * c.psi_l[Na], 3.10));
-  hp = (sum_fwd(c.thick, 1, Na - 1) + bottom_h) / hp;
+  for (int k = 1; k <= Na - 1; k++) hp = hp + c.thick()[k] / (1e-17 * det_pow(1000.0 * c.psi_l()[k], 3.10));  // :73-79
+  const double bottom_h = c.thick()[Na] * c.psi_s()[Na] / psi_s_min;
+  hp = hp + bottom_h / (1e-17 * det_pow(1000.0 * c.psi_l()[Na], 3.10));
+  hp = (sum_fwd(c.thick(), 1, Na - 1) + bottom_h) / hp;
 
-  double flood_brine = -dt * grav * rho_l * rho_l * hp * (freeboard) / (mu * sum_fwd(c.thick, 1, Na));  // :85
+  double flood_brine = -dt * grav * rho_l * rho_l * hp * (freeboard) / (mu * sum_fwd(c.thick(), 1, Na));  // :85
   const double shift_ice = flood_brine / (rho_l * psi_g_snow / ratio_flood);
   const double shift_snow = shift_ice * (1 + psi_g_snow / (1.0 - psi_g_snow) * (1.0 - 1.0 / ratio_flood));
 
-  const double S_bu_Na = c.S_abs[Na] / c.m[Na];  // S_bu(k) = S_abs(k)/m(k) before any change, :93-95
-  double S1 = c.S_abs[1], H1 = c.H_abs[1], m1 = c.m[1], th1 = c.thick[1];
+  const double S_bu_Na = c.S_abs()[Na] / c.m()[Na];  // S_bu(k) = S_abs(k)/m(k) before any change, :93-95
+  double S1 = c.S_abs()[1], H1 = c.H_abs()[1], m1 = c.m()[1], th1 = c.thick()[1];
   S1 = S1 + flood_brine * S_bu_Na;                  // :102-104
-  H1 = H1 + flood_brine * c.H_abs[Na] / c.m[Na];
+  H1 = H1 + flood_brine * c.H_abs()[Na] / c.m()[Na];
   m1 = m1 + flood_brine;
   th1 = th1 + shift_ice;                            // :107-112
   H1 = H1 + shift_snow / thick_snow * H_abs_snow;
@@ -843,14 +880,14 @@ __device__ __noinline__ void flood(const DevCfg& g, Col& c) {
   m1 = m1 + shift_snow / thick_snow * m_snow;
   m_snow = m_snow - shift_snow / thick_snow * m_snow;
   thick_snow = thick_snow - shift_snow;
-  c.S_abs[1] = S1; c.H_abs[1] = H1; c.m[1] = m1; c.thick[1] = th1;  // Na > 1 here, layer 1 != layer Na
+  c.S_abs()[1] = S1; c.H_abs()[1] = H1; c.m()[1] = m1; c.thick()[1] = th1;  // Na > 1 here, layer 1 != layer Na
 
   if (freeboard + shift_ice < neg_free) {  // :117-138
     const double shift = neg_free - (freeboard + shift_ice);
     flood_brine = shift * (psi_g_snow)*rho_l;
-    const double T_Na = c.T[Na];
-    c.S_abs[Na] = c.S_abs[Na] + (SCV(c, SC_S_BU_BOTTOM) - S_bu_Na) * flood_brine;
-    c.H_abs[Na] = c.H_abs[Na] + (SCV(c, SC_T_BOTTOM) - T_Na) * c_l * flood_brine;
+    const double T_Na = c.T()[Na];
+    c.S_abs()[Na] = c.S_abs()[Na] + (SCV(c, SC_S_BU_BOTTOM) - S_bu_Na) * flood_brine;
+    c.H_abs()[Na] = c.H_abs()[Na] + (SCV(c, SC_T_BOTTOM) - T_Na) * c_l * flood_brine;
     S1 = S1 + S_bu_Na * flood_brine;
     H1 = H1 + T_Na * c_l * flood_brine;
     m1 = m1 + flood_brine;
@@ -860,7 +897,7 @@ __device__ __noinline__ void flood(const DevCfg& g, Col& c) {
     m1 = m1 + shift / thick_snow * m_snow;
     m_snow = m_snow - shift / thick_snow * m_snow;
     thick_snow = thick_snow - shift;
-    c.S_abs[1] = S1; c.H_abs[1] = H1; c.m[1] = m1; c.thick[1] = th1;
+    c.S_abs()[1] = S1; c.H_abs()[1] = H1; c.m()[1] = m1; c.thick()[1] = th1;
   }
 }
 
@@ -871,8 +908,8 @@ __device__ __forceinline__ void flood_simple(Col& c) {
   double& m_snow = SCV(c, SC_M_SNOW);
   const double shift = SCV(c, SC_FREEBOARD) - neg_free;
   const double flood_brine = -shift * SCV(c, SC_PSI_G_SNOW) * rho_l;
-  double S1 = c.S_abs[1], H1 = c.H_abs[1], m1 = c.m[1];
-  c.thick[1] = c.thick[1] - shift;
+  double S1 = c.S_abs()[1], H1 = c.H_abs()[1], m1 = c.m()[1];
+  c.thick()[1] = c.thick()[1] - shift;
   S1 = S1 + SCV(c, SC_S_BU_BOTTOM) * flood_brine;
   H1 = H1 - shift / thick_snow * H_abs_snow;
   H1 = H1 + SCV(c, SC_T_BOTTOM) * c_l * flood_brine;
@@ -881,7 +918,7 @@ __device__ __forceinline__ void flood_simple(Col& c) {
   H_abs_snow = H_abs_snow + shift / thick_snow * H_abs_snow;
   m_snow = m_snow + shift / thick_snow * m_snow;
   thick_snow = thick_snow + shift;
-  c.S_abs[1] = S1; c.H_abs[1] = H1; c.m[1] = m1;
+  c.S_abs()[1] = S1; c.H_abs()[1] = H1; c.m()[1] = m1;
 }
 
 // ==========================================================================================
@@ -892,28 +929,28 @@ __device__ __forceinline__ void flood_simple(Col& c) {
 __device__ __noinline__ void flush3(const DevCfg& g, Col& c) {
   const int Na = c.N_active, N = g.Nlayer;
   const double dt = g.dt, freeboard = SCV(c, SC_FREEBOARD);
-  Lay R_v = c.w0, R_h = c.w1, R = c.w2, S_bu = c.w3, fl_m = c.fl_m;
+  Lay R_v = c.w0(), R_h = c.w1(), R = c.w2(), S_bu = c.w3(), fl_m = c.fl_m();
   double& melt_thick = SCV(c, SC_MELT_THICK);
 
-  for (int k = 1; k <= Na; k++) { c.flush_v[k] = 0.0; c.flush_h[k] = 0.0; }   // :101-102 (dummies are DIMENSION(N_active))
-  for (int k = 1; k <= Na; k++) S_bu[k] = c.S_abs[k] / c.m[k];              // :103
-  const double konst = sum_fwd(c.thick, 1, Na) * para_flush_horiz;          // :106
-  melt_thick = f_min(melt_thick, c.psi_l[1] * c.thick[1]);                  // :110
+  for (int k = 1; k <= Na; k++) { c.flush_v()[k] = 0.0; c.flush_h()[k] = 0.0; }   // :101-102 (dummies are DIMENSION(N_active))
+  for (int k = 1; k <= Na; k++) S_bu[k] = c.S_abs()[k] / c.m()[k];              // :103
+  const double konst = sum_fwd(c.thick(), 1, Na) * para_flush_horiz;          // :106
+  melt_thick = f_min(melt_thick, c.psi_l()[1] * c.thick()[1]);                  // :110
   melt_thick = f_min(melt_thick, g.thick_0 / 3.0);                          // :112
 
   if (g.snow_flush_flag == 1) {  // :114-125
-    for (int k = Na + 1; k <= N; k++) c.perm[k] = 0.0;
+    for (int k = Na + 1; k <= N; k++) c.perm()[k] = 0.0;
     for (int k = 1; k <= Na; k++) {
-      double p = 1e-17 * det_pow(1000.0 * fabs(c.psi_l[k] + 2. * c.psi_g[k]), 3.10);
+      double p = 1e-17 * det_pow(1000.0 * fabs(c.psi_l()[k] + 2. * c.psi_g()[k]), 3.10);
       if (p == 0.0) p = 1.0;
-      c.perm[k] = p;
+      c.perm()[k] = p;
     }
   } else if (g.snow_flush_flag == 0) {  // :126-130
-    for (int k = Na + 1; k <= N; k++) c.perm[k] = 1.0;
-    for (int k = 1; k <= Na; k++) c.perm[k] = 1e-17 * det_pow(1000.0 * fabs(c.psi_l[k]), 3.10);
+    for (int k = Na + 1; k <= N; k++) c.perm()[k] = 1.0;
+    for (int k = 1; k <= Na; k++) c.perm()[k] = 1e-17 * det_pow(1000.0 * fabs(c.psi_l()[k]), 3.10);
   }
   for (int k = 1; k <= Na; k++) {  // :133-137
-    const double pk = f_max(c.perm[k], 0.00000000000000000000001), thk = c.thick[k];
+    const double pk = f_max(c.perm()[k], 0.00000000000000000000001), thk = c.thick()[k];
     R_v[k] = mu * thk / pk;
     R_h[k] = mu * konst / (thk * pk);
   }
@@ -923,85 +960,80 @@ __device__ __noinline__ void flush3(const DevCfg& g, Col& c) {
     double r = R[k + 1] + R_v[k];
     R[k] = ((r)*R_h[k]) / (r + R_h[k]);
   }
-  const double T1 = c.T[1];
+  const double T1 = c.T()[1];
   double flush_total = (freeboard + melt_thick) / R[1] * grav * dt * density_of(T1, S_br_of(g, T1)) * rho_l;  // :152
   flush_total = f_min(flush_total, melt_thick * rho_l);
   SCV(c, SC_MELT_ERR) = SCV(c, SC_MELT_ERR) + melt_thick - f_min(flush_total / rho_l, melt_thick);  // :156
 
   {
     const double den = R[2] + R_v[1] + R_h[1];
-    c.flush_h[1] = flush_total * (R[2] + R_v[1]) / den;  // :159-160
-    c.flush_v[1] = flush_total * R_h[1] / den;
+    c.flush_h()[1] = flush_total * (R[2] + R_v[1]) / den;  // :159-160
+    c.flush_v()[1] = flush_total * R_h[1] / den;
   }
   for (int k = 2; k <= Na - 1; k++) {  // :161-164
-    const double fv = c.flush_v[k - 1], a = R[k + 1] + R_v[k], den = a + R_h[k];
-    c.flush_h[k] = fv * a / den;
-    c.flush_v[k] = fv * R_h[k] / den;
+    const double fv = c.flush_v()[k - 1], a = R[k + 1] + R_v[k], den = a + R_h[k];
+    c.flush_h()[k] = fv * a / den;
+    c.flush_v()[k] = fv * R_h[k] / den;
   }
-  c.flush_v[Na] = c.flush_v[Na - 1];
-  c.flush_h[Na] = 0.0;
+  c.flush_v()[Na] = c.flush_v()[Na - 1];
+  c.flush_h()[Na] = 0.0;
 
   fl_m[1] = 0.0;  // :179-180
-  for (int k = 1; k <= Na; k++) fl_m[k + 1] = -c.flush_v[k];
+  for (int k = 1; k <= Na; k++) fl_m[k + 1] = -c.flush_v()[k];
 
-  {  // mass_transfer with the LOCAL S_bu (:182): swap the view for the call
-    Lay keep = c.S_bu;
-    c.S_bu = S_bu;
-    mass_transfer(g, c, fl_m);
-    c.S_bu = keep;
-  }
-  const double T_Na = c.T[Na];
-  if (g.flush_heat_flag == 2) c.H_abs[Na] = c.H_abs[Na] - fl_m[Na + 1] * T_Na * c_l;  // :185-187
+  mass_transfer(g, c, fl_m, S_bu);  // with the LOCAL S_bu (:182)
+  const double T_Na = c.T()[Na];
+  if (g.flush_heat_flag == 2) c.H_abs()[Na] = c.H_abs()[Na] - fl_m[Na + 1] * T_Na * c_l;  // :185-187
 
-  c.m[1] = c.m[1] - flush_total;  // :190-191
-  c.thick[1] = c.thick[1] - flush_total / rho_l;
+  c.m()[1] = c.m()[1] - flush_total;  // :190-191
+  c.thick()[1] = c.thick()[1] - flush_total / rho_l;
 
   double sfh = 0.0;
-  double H_Na = c.H_abs[Na], S_Na = c.S_abs[Na];
+  double H_Na = c.H_abs()[Na], S_Na = c.S_abs()[Na];
   for (int k = 1; k <= Na - 1; k++) {  // :196-206
-    const double fh = c.flush_h[k], Tk = c.T[k];
-    const double loss_S = fh * S_br_of(g, Tk, c.S_abs[k] / c.m[k]);
+    const double fh = c.flush_h()[k], Tk = c.T()[k];
+    const double loss_S = fh * S_br_of(g, Tk, c.S_abs()[k] / c.m()[k]);
     const double loss_H = fh * Tk * c_l;
-    c.S_abs[k] = c.S_abs[k] - loss_S;
-    c.H_abs[k] = c.H_abs[k] - loss_H;
+    c.S_abs()[k] = c.S_abs()[k] - loss_S;
+    c.H_abs()[k] = c.H_abs()[k] - loss_H;
     H_Na = H_Na + loss_H;
     S_Na = S_Na + loss_S;
     sfh = sfh + fh;
   }
-  sfh = sfh + c.flush_h[Na];  // SUM(flush_h) over the N_active-long dummy
+  sfh = sfh + c.flush_h()[Na];  // SUM(flush_h) over the N_active-long dummy
   const double loss_S = sfh * S_bu[Na];  // :207-208
   const double loss_H = sfh * T_Na * c_l;
   if (g.flush_heat_flag == 2) H_Na = H_Na - loss_H;
   S_Na = S_Na - loss_S;
-  c.H_abs[Na] = H_Na;
-  c.S_abs[Na] = S_Na;
+  c.H_abs()[Na] = H_Na;
+  c.S_abs()[Na] = S_Na;
 
-  double mn = c.S_abs[1];
-  for (int k = 2; k <= Na; k++) mn = f_min(mn, c.S_abs[k]);
+  double mn = c.S_abs()[1];
+  for (int k = 2; k <= Na; k++) mn = f_min(mn, c.S_abs()[k]);
   mn = f_min(mn, 0.0);  // MINVAL over all Nlayer: inactive layers hold 0 (only matters when Na < N)
   if (mn < -0.00000000000000000000000001)
-    for (int k = 1; k <= Na; k++) c.S_abs[k] = f_max(c.S_abs[k], 0.0);
-  if (fabs(c.m[1]) < 0.000001) c.status = 9876;  // :230-233
+    for (int k = 1; k <= Na; k++) c.S_abs()[k] = f_max(c.S_abs()[k], 0.0);
+  if (fabs(c.m()[1]) < 0.000001) c.status = 9876;  // :230-233
 }
 
 // flush4, mo_flush.f90:253-296 (flush_flag 6)
 __device__ __noinline__ void flush4(const DevCfg& g, Col& c) {
   const int N = g.Nlayer, Na = c.N_active;
   double& melt_thick = SCV(c, SC_MELT_THICK);
-  const double S_bu1 = c.S_abs[1] / c.m[1], T1 = c.T[1];
-  c.H_abs[1] = c.H_abs[1] - melt_thick * rho_l * c_l * T1;
-  c.S_abs[1] = c.S_abs[1] - melt_thick * rho_l * S_br_of(g, T1, S_bu1);
-  c.thick[1] = c.thick[1] - melt_thick;
-  c.m[1] = c.m[1] - melt_thick * rho_l;
+  const double S_bu1 = c.S_abs()[1] / c.m()[1], T1 = c.T()[1];
+  c.H_abs()[1] = c.H_abs()[1] - melt_thick * rho_l * c_l * T1;
+  c.S_abs()[1] = c.S_abs()[1] - melt_thick * rho_l * S_br_of(g, T1, S_bu1);
+  c.thick()[1] = c.thick()[1] - melt_thick;
+  c.m()[1] = c.m()[1] - melt_thick * rho_l;
   melt_thick = 0.0;
   int k = 2;
-  while (k <= N && c.psi_l[k] > c.psi_l[k - 1]) {
-    c.S_abs[k] = para_flush_gamma * c.S_abs[k];
+  while (k <= N && c.psi_l()[k] > c.psi_l()[k - 1]) {
+    c.S_abs()[k] = para_flush_gamma * c.S_abs()[k];
     k = k + 1;
   }
-  c.S_abs[1] = f_max(c.S_abs[1], 0.00);
-  double mn = c.S_abs[1];
-  for (int q = 2; q <= Na; q++) mn = f_min(mn, c.S_abs[q]);
+  c.S_abs()[1] = f_max(c.S_abs()[1], 0.00);
+  double mn = c.S_abs()[1];
+  for (int q = 2; q <= Na; q++) mn = f_min(mn, c.S_abs()[q]);
   if (mn < 0.0) c.status = 9876;
 }
 
@@ -1010,10 +1042,10 @@ __device__ __noinline__ void flush4(const DevCfg& g, Col& c) {
 // ==========================================================================================
 __device__ __forceinline__ void snapshot_layers(Col& c, int k0, int k1) {
   for (int k = k0; k <= k1; k++) {
-    const double mk = c.m[k];
-    c.w0[k] = mk / c.thick[k];   // rho
-    c.w1[k] = c.S_abs[k] / mk;   // S_bu
-    c.w2[k] = c.H_abs[k] / mk;   // H
+    const double mk = c.m()[k];
+    c.w0()[k] = mk / c.thick()[k];   // rho
+    c.w1()[k] = c.S_abs()[k] / mk;   // S_bu
+    c.w2()[k] = c.H_abs()[k] / mk;   // H
   }
 }
 
@@ -1021,125 +1053,125 @@ __device__ __forceinline__ void snapshot_layers(Col& c, int k0, int k1) {
 __device__ __noinline__ void top_melt(const DevCfg& g, Col& c) {
   const int N = g.Nlayer, N_middle = g.N_middle, N_top = g.N_top;
   const double thick_0 = g.thick_0;
-  Lay rho = c.w0, S_bu = c.w1, H = c.w2;
+  Lay rho = c.w0(), S_bu = c.w1(), H = c.w2();
   snapshot_layers(c, 1, c.N_active);  // :218-223
-  c.m[1] = c.m[1] + c.m[2];           // :231-235
-  c.S_abs[1] = c.S_abs[1] + c.S_abs[2];
-  c.H_abs[1] = c.H_abs[1] + c.H_abs[2];
-  c.thick[1] = c.thick[1] + c.thick[2];
+  c.m()[1] = c.m()[1] + c.m()[2];           // :231-235
+  c.S_abs()[1] = c.S_abs()[1] + c.S_abs()[2];
+  c.H_abs()[1] = c.H_abs()[1] + c.H_abs()[2];
+  c.thick()[1] = c.thick()[1] + c.thick()[2];
   const int kmax = (N_top - 1 < c.N_active - 1) ? N_top - 1 : c.N_active - 1;
   for (int k = 2; k <= kmax; k++) {  // :238-243
-    c.m[k] = rho[k + 1] * thick_0;
-    c.S_abs[k] = S_bu[k + 1] * rho[k + 1] * thick_0;
-    c.H_abs[k] = H[k + 1] * rho[k + 1] * thick_0;
+    c.m()[k] = rho[k + 1] * thick_0;
+    c.S_abs()[k] = S_bu[k + 1] * rho[k + 1] * thick_0;
+    c.H_abs()[k] = H[k + 1] * rho[k + 1] * thick_0;
   }
   if (c.N_active <= N_top) {  // :247-254
     const int Na = c.N_active;
-    c.m[Na] = 0.0; c.S_abs[Na] = 0.0; c.H_abs[Na] = 0.0; c.thick[Na] = 0.0;
+    c.m()[Na] = 0.0; c.S_abs()[Na] = 0.0; c.H_abs()[Na] = 0.0; c.thick()[Na] = 0.0;
     c.N_active = Na - 1;
-  } else if (c.N_active > N_top && c.N_active <= N && c.thick[N_top + 1] / thick_0 < 1.00001) {  // :256-273
+  } else if (c.N_active > N_top && c.N_active <= N && c.thick()[N_top + 1] / thick_0 < 1.00001) {  // :256-273
     const int Na = c.N_active;
     for (int k = N_top; k <= Na - 1; k++) {
-      c.m[k] = rho[k + 1] * thick_0;
-      c.S_abs[k] = S_bu[k + 1] * rho[k + 1] * thick_0;
-      c.H_abs[k] = H[k + 1] * rho[k + 1] * thick_0;
+      c.m()[k] = rho[k + 1] * thick_0;
+      c.S_abs()[k] = S_bu[k + 1] * rho[k + 1] * thick_0;
+      c.H_abs()[k] = H[k + 1] * rho[k + 1] * thick_0;
     }
-    c.m[Na] = 0.0; c.S_abs[Na] = 0.0; c.H_abs[Na] = 0.0; c.thick[Na] = 0.0;
+    c.m()[Na] = 0.0; c.S_abs()[Na] = 0.0; c.H_abs()[Na] = 0.0; c.thick()[Na] = 0.0;
     c.N_active = Na - 1;
   }
-  if (c.N_active == N && c.thick[N_top + 1] - thick_0 >= 0.000001) {  // :275-314
+  if (c.N_active == N && c.thick()[N_top + 1] - thick_0 >= 0.000001) {  // :275-314
     double loss_m = thick_0 * rho[N_top + 1];
     double loss_S = loss_m * S_bu[N_top + 1];
     double loss_H = loss_m * H[N_top + 1];
-    c.m[N_top] = loss_m;
-    c.S_abs[N_top] = loss_S;
-    c.H_abs[N_top] = loss_H;
+    c.m()[N_top] = loss_m;
+    c.S_abs()[N_top] = loss_S;
+    c.H_abs()[N_top] = loss_H;
     for (int k = N_top + 1; k <= N_middle + N_top; k++) {
-      double mk = c.m[k] - loss_m, Hk = c.H_abs[k] - loss_H, Sk = c.S_abs[k] - loss_S;
+      double mk = c.m()[k] - loss_m, Hk = c.H_abs()[k] - loss_H, Sk = c.S_abs()[k] - loss_S;
       const double shift = thick_0 * (double)(float)(N_middle - k + N_top) / (double)(float)(N_middle);  // :293
       loss_m = shift * rho[k + 1];
       loss_S = loss_m * S_bu[k + 1];
       loss_H = loss_m * H[k + 1];
-      c.m[k] = mk + loss_m;
-      c.H_abs[k] = Hk + loss_H;
-      c.S_abs[k] = Sk + loss_S;
+      c.m()[k] = mk + loss_m;
+      c.H_abs()[k] = Hk + loss_H;
+      c.S_abs()[k] = Sk + loss_S;
     }
-    for (int k = N_top + 1; k <= N_top + N_middle; k++) c.thick[k] = c.thick[k] - thick_0 / (double)(float)(N_middle);
+    for (int k = N_top + 1; k <= N_top + N_middle; k++) c.thick()[k] = c.thick()[k] - thick_0 / (double)(float)(N_middle);
   }
   // :318-321 grid consistency, STOP 7889 (SUM(thick) over all layers; inactive are 0)
   if (c.N_active < N) {
-    if (thick_0 * (c.N_active + 0.501) <= sum_fwd(c.thick, 1, N)) c.status = 7889;
+    if (thick_0 * (c.N_active + 0.501) <= sum_fwd(c.thick(), 1, N)) c.status = 7889;
   }
 }
 
 // bottom_melt, mo_layer_dynamics.f90:341-420
 __device__ __noinline__ void bottom_melt(const DevCfg& g, Col& c) {
   const int N = g.Nlayer, N_middle = g.N_middle, N_top = g.N_top;
-  Lay rho = c.w0, S_bu = c.w1, H = c.w2;
+  Lay rho = c.w0(), S_bu = c.w1(), H = c.w2();
   snapshot_layers(c, N_top + 1, N);  // :364-370
-  const double thN = c.thick[N];
+  const double thN = c.thick()[N];
   double loss_m = 0.0, loss_S = 0.0, loss_H = 0.0;
   for (int k = N_top + 1; k <= N_top + N_middle; k++) {  // :378-400
-    double mk = c.m[k] + loss_m, Hk = c.H_abs[k] + loss_H, Sk = c.S_abs[k] + loss_S;
+    double mk = c.m()[k] + loss_m, Hk = c.H_abs()[k] + loss_H, Sk = c.S_abs()[k] + loss_S;
     const double shift = thN * (k - N_top) / (double)(float)(N_middle);
     loss_m = shift * rho[k];
     loss_H = loss_m * H[k];
     loss_S = loss_m * S_bu[k];
-    c.m[k] = mk - loss_m;
-    c.H_abs[k] = Hk - loss_H;
-    c.S_abs[k] = Sk - loss_S;
+    c.m()[k] = mk - loss_m;
+    c.H_abs()[k] = Hk - loss_H;
+    c.S_abs()[k] = Sk - loss_S;
   }
-  for (int k = N_top + 1; k <= N_top + N_middle; k++) c.thick[k] = c.thick[k] - thN / (double)(float)(N_middle);
+  for (int k = N_top + 1; k <= N_top + N_middle; k++) c.thick()[k] = c.thick()[k] - thN / (double)(float)(N_middle);
   for (int k = N_top + N_middle + 1; k <= N; k++) {  // :410-415
-    const double thk = c.thick[k];
-    c.H_abs[k] = rho[k - 1] * thk * H[k - 1];
-    c.S_abs[k] = rho[k - 1] * thk * S_bu[k - 1];
-    c.m[k] = rho[k - 1] * thk;
+    const double thk = c.thick()[k];
+    c.H_abs()[k] = rho[k - 1] * thk * H[k - 1];
+    c.S_abs()[k] = rho[k - 1] * thk * S_bu[k - 1];
+    c.m()[k] = rho[k - 1] * thk;
   }
 }
 
 // bottom_growth, mo_layer_dynamics.f90:438-520
 __device__ __noinline__ void bottom_growth(const DevCfg& g, Col& c) {
   const int N = g.Nlayer, N_middle = g.N_middle, N_top = g.N_top, N_bottom = g.N_bottom;
-  Lay rho = c.w0, S_bu = c.w1, H = c.w2;
+  Lay rho = c.w0(), S_bu = c.w1(), H = c.w2();
   snapshot_layers(c, N_top + 1, N_top + N_middle + 1);  // :463-468
-  const double thN = c.thick[N];
+  const double thN = c.thick()[N];
   double gain_m = 0.0, gain_S = 0.0, gain_H = 0.0;
   for (int k = N_top + 1; k <= N_top + N_middle; k++) {  // :476-495
-    double mk = c.m[k] - gain_m, Hk = c.H_abs[k] - gain_H, Sk = c.S_abs[k] - gain_S;
+    double mk = c.m()[k] - gain_m, Hk = c.H_abs()[k] - gain_H, Sk = c.S_abs()[k] - gain_S;
     const double shift = thN * (k - N_top) / (double)(float)(N_middle);
     gain_m = shift * rho[k + 1];
     gain_H = gain_m * H[k + 1];
     gain_S = gain_m * S_bu[k + 1];
-    c.m[k] = mk + gain_m;
-    c.H_abs[k] = Hk + gain_H;
-    c.S_abs[k] = Sk + gain_S;
+    c.m()[k] = mk + gain_m;
+    c.H_abs()[k] = Hk + gain_H;
+    c.S_abs()[k] = Sk + gain_S;
   }
-  for (int k = N_top + 1; k <= N_top + N_middle; k++) c.thick[k] = c.thick[k] + thN / (double)(float)(N_middle);
+  for (int k = N_top + 1; k <= N_top + N_middle; k++) c.thick()[k] = c.thick()[k] + thN / (double)(float)(N_middle);
   for (int k = N - N_bottom + 1; k <= N - 1; k++) {  // :503-508
-    c.H_abs[k] = c.H_abs[k + 1];
-    c.S_abs[k] = c.S_abs[k + 1];
-    c.m[k] = c.m[k + 1];
+    c.H_abs()[k] = c.H_abs()[k + 1];
+    c.S_abs()[k] = c.S_abs()[k + 1];
+    c.m()[k] = c.m()[k + 1];
   }
-  const double mN = c.thick[N] * rho_l;  // :511-513
-  c.m[N] = mN;
-  c.H_abs[N] = mN * SCV(c, SC_T_BOTTOM) * c_l;
-  c.S_abs[N] = mN * SCV(c, SC_S_BU_BOTTOM);
+  const double mN = c.thick()[N] * rho_l;  // :511-513
+  c.m()[N] = mN;
+  c.H_abs()[N] = mN * SCV(c, SC_T_BOTTOM) * c_l;
+  c.S_abs()[N] = mN * SCV(c, SC_S_BU_BOTTOM);
 }
 
 // bottom_growth_simple :537-561, bottom_melt_simple :573-590
 __device__ __forceinline__ void bottom_growth_simple(const DevCfg& g, Col& c) {
   const int Na = c.N_active + 1;
   c.N_active = Na;
-  c.thick[Na] = g.thick_0;
+  c.thick()[Na] = g.thick_0;
   const double mN = g.thick_0 * rho_l;
-  c.m[Na] = mN;
-  c.H_abs[Na] = mN * SCV(c, SC_T_BOTTOM) * c_l;
-  c.S_abs[Na] = mN * SCV(c, SC_S_BU_BOTTOM);
+  c.m()[Na] = mN;
+  c.H_abs()[Na] = mN * SCV(c, SC_T_BOTTOM) * c_l;
+  c.S_abs()[Na] = mN * SCV(c, SC_S_BU_BOTTOM);
 }
 __device__ __forceinline__ void bottom_melt_simple(Col& c) {
   const int Na = c.N_active;
-  c.thick[Na] = 0.0; c.m[Na] = 0.0; c.S_abs[Na] = 0.0; c.H_abs[Na] = 0.0;
+  c.thick()[Na] = 0.0; c.m()[Na] = 0.0; c.S_abs()[Na] = 0.0; c.H_abs()[Na] = 0.0;
   c.N_active = Na - 1;
 }
 
@@ -1147,57 +1179,57 @@ __device__ __forceinline__ void bottom_melt_simple(Col& c) {
 __device__ __noinline__ void top_grow(const DevCfg& g, Col& c) {
   const int N = g.Nlayer, N_middle = g.N_middle, N_top = g.N_top;
   const double thick_0 = g.thick_0;
-  Lay rho = c.w0, S_bu = c.w1, H = c.w2;
+  Lay rho = c.w0(), S_bu = c.w1(), H = c.w2();
   snapshot_layers(c, 1, c.N_active);  // :631-636
   {
     const double loss_m = thick_0 * rho[1];  // :639-648
     const double loss_S = loss_m * S_bu[1];
     const double loss_H = loss_m * H[1];
-    c.m[1] = c.m[1] - loss_m;
-    c.S_abs[1] = c.S_abs[1] - loss_S;
-    c.H_abs[1] = c.H_abs[1] - loss_H;
-    c.thick[1] = c.thick[1] - thick_0;
+    c.m()[1] = c.m()[1] - loss_m;
+    c.S_abs()[1] = c.S_abs()[1] - loss_S;
+    c.H_abs()[1] = c.H_abs()[1] - loss_H;
+    c.thick()[1] = c.thick()[1] - thick_0;
   }
   const int kmax = (N_top < c.N_active) ? N_top : c.N_active;
   for (int k = 2; k <= kmax; k++) {  // :651-656
-    c.m[k] = rho[k - 1] * thick_0;
-    c.S_abs[k] = S_bu[k - 1] * rho[k - 1] * thick_0;
-    c.H_abs[k] = H[k - 1] * rho[k - 1] * thick_0;
+    c.m()[k] = rho[k - 1] * thick_0;
+    c.S_abs()[k] = S_bu[k - 1] * rho[k - 1] * thick_0;
+    c.H_abs()[k] = H[k - 1] * rho[k - 1] * thick_0;
   }
   if (c.N_active <= N_top) {  // :659-665
     const int Na = c.N_active + 1;
     c.N_active = Na;
-    c.m[Na] = rho[Na - 1] * thick_0;
-    c.S_abs[Na] = S_bu[Na - 1] * thick_0 * rho[Na - 1];
-    c.H_abs[Na] = H[Na - 1] * thick_0 * rho[Na - 1];
-    c.thick[Na] = thick_0;
+    c.m()[Na] = rho[Na - 1] * thick_0;
+    c.S_abs()[Na] = S_bu[Na - 1] * thick_0 * rho[Na - 1];
+    c.H_abs()[Na] = H[Na - 1] * thick_0 * rho[Na - 1];
+    c.thick()[Na] = thick_0;
   } else if (c.N_active > N_top && c.N_active < N) {  // :668-680
     for (int k = N_top + 1; k <= c.N_active; k++) {
-      c.m[k] = rho[k - 1] * thick_0;
-      c.S_abs[k] = S_bu[k - 1] * rho[k - 1] * thick_0;
-      c.H_abs[k] = H[k - 1] * rho[k - 1] * thick_0;
+      c.m()[k] = rho[k - 1] * thick_0;
+      c.S_abs()[k] = S_bu[k - 1] * rho[k - 1] * thick_0;
+      c.H_abs()[k] = H[k - 1] * rho[k - 1] * thick_0;
     }
     const int Na = c.N_active + 1;
     c.N_active = Na;
-    c.m[Na] = rho[Na - 1] * thick_0;
-    c.S_abs[Na] = S_bu[Na - 1] * thick_0 * rho[Na - 1];
-    c.H_abs[Na] = H[Na - 1] * thick_0 * rho[Na - 1];
-    c.thick[Na] = thick_0;
+    c.m()[Na] = rho[Na - 1] * thick_0;
+    c.S_abs()[Na] = S_bu[Na - 1] * thick_0 * rho[Na - 1];
+    c.H_abs()[Na] = H[Na - 1] * thick_0 * rho[Na - 1];
+    c.thick()[Na] = thick_0;
   } else if (c.N_active == N) {  // :682-711
     double loss_m = thick_0 * rho[N_top];
     double loss_S = loss_m * S_bu[N_top];
     double loss_H = loss_m * H[N_top];
     for (int k = N_top + 1; k <= N_middle + N_top; k++) {
-      double mk = c.m[k] + loss_m, Hk = c.H_abs[k] + loss_H, Sk = c.S_abs[k] + loss_S;
+      double mk = c.m()[k] + loss_m, Hk = c.H_abs()[k] + loss_H, Sk = c.S_abs()[k] + loss_S;
       const double shift = thick_0 * (double)(float)(N_middle - k + N_top) / (double)(float)(N_middle);
       loss_m = shift * rho[k];
       loss_S = loss_m * S_bu[k];
       loss_H = loss_m * H[k];
-      c.m[k] = mk - loss_m;
-      c.H_abs[k] = Hk - loss_H;
-      c.S_abs[k] = Sk - loss_S;
+      c.m()[k] = mk - loss_m;
+      c.H_abs()[k] = Hk - loss_H;
+      c.S_abs()[k] = Sk - loss_S;
     }
-    for (int k = N_top + 1; k <= N_top + N_middle; k++) c.thick[k] = c.thick[k] + thick_0 / (double)(float)(N_middle);
+    for (int k = N_top + 1; k <= N_top + N_middle; k++) c.thick()[k] = c.thick()[k] + thick_0 / (double)(float)(N_middle);
   }
 }
 
@@ -1207,9 +1239,9 @@ __device__ __noinline__ void layer_dynamics(const DevCfg& g, Col& c) {
   const double thick_0 = g.thick_0;
   const bool bf = (g.bottom_flag == 1);
   const int nm1 = (Na - 1 > 1) ? Na - 1 : 1;
-  const double phi_Na = c.phi[Na], phi_nm1 = c.phi[nm1], th1 = c.thick[1];
-  const double mid_ratio = c.thick[N_top + 1] / thick_0;
-  if (c.phi[N - 1] <= psi_s_min / 2.0 && phi_Na < 0.00001 && Na == N && mid_ratio > 1.000001 && bf) {
+  const double phi_Na = c.phi()[Na], phi_nm1 = c.phi()[nm1], th1 = c.thick()[1];
+  const double mid_ratio = c.thick()[N_top + 1] / thick_0;
+  if (c.phi()[N - 1] <= psi_s_min / 2.0 && phi_Na < 0.00001 && Na == N && mid_ratio > 1.000001 && bf) {
     bottom_melt(g, c);
   } else if (Na > 1 && Na < N && phi_Na < 0.00001 && phi_nm1 <= psi_s_min / 2.0 && bf) {
     bottom_melt_simple(c);
@@ -1217,16 +1249,16 @@ __device__ __noinline__ void layer_dynamics(const DevCfg& g, Col& c) {
     bottom_melt_simple(c);
   } else if (phi_Na > psi_s_min && Na < N && bf) {
     bottom_growth_simple(g, c);
-  } else if (c.phi[N] > psi_s_min && bf) {
+  } else if (c.phi()[N] > psi_s_min && bf) {
     bottom_growth(g, c);
   } else if (th1 > 1.5 * thick_0) {
     SCV(c, SC_MTO3) = SCV(c, SC_MTO3) - th1;
     top_grow(g, c);
-    SCV(c, SC_MTO3) = SCV(c, SC_MTO3) + c.thick[1];
+    SCV(c, SC_MTO3) = SCV(c, SC_MTO3) + c.thick()[1];
   } else if (th1 < 0.5 * thick_0) {
     SCV(c, SC_MTO3) = SCV(c, SC_MTO3) - th1;
     top_melt(g, c);
-    SCV(c, SC_MTO3) = SCV(c, SC_MTO3) + c.thick[1];
+    SCV(c, SC_MTO3) = SCV(c, SC_MTO3) + c.thick()[1];
   }
 }
 

@@ -89,14 +89,9 @@ __global__ void __launch_bounds__(SAMSIM_BLOCK, SAMSIM_MINBLOCKS) samsim_step_ke
   const size_t astr = (size_t)p.LS * ls;
 
   Col c;
-  double* base = p.arr + col;
-#define BIND(field, id) c.field.p = base + (size_t)(id)*astr; c.field.ls = (unsigned)ls;
-  BIND(m, AR_M) BIND(S_abs, AR_S_ABS) BIND(H_abs, AR_H_ABS) BIND(thick, AR_THICK) BIND(T, AR_T) BIND(phi, AR_PHI)
-  BIND(S_bu, AR_S_BU) BIND(psi_s, AR_PSI_S) BIND(psi_l, AR_PSI_L) BIND(psi_g, AR_PSI_G) BIND(ray, AR_RAY)
-  BIND(perm, AR_PERM) BIND(flush_v, AR_FLUSH_V) BIND(flush_h, AR_FLUSH_H) BIND(fl_Q, AR_FL_Q)
-  BIND(S_br, AR_S_BR) BIND(V_ex, AR_V_EX) BIND(fl_m, AR_FL_M) BIND(w0, AR_W0) BIND(w1, AR_W1) BIND(w2, AR_W2)
-  BIND(w3, AR_W3)
-#undef BIND
+  c.base = p.arr + col;
+  c.ls = (unsigned)ls;
+  c.astr = (unsigned)astr;
   for (int q = 0; q < SC_COUNT; q++) c.sc[q] = p.sc[(size_t)q * ls + col];
   c.N_active = p.in[(size_t)IN_N_ACTIVE * ls + col];
   c.status = padding ? -1 : p.in[(size_t)IN_STATUS * ls + col];
@@ -336,9 +331,9 @@ int samsim_b200_create(const samsim_config_t* cfg, int32_t ncol, int32_t device,
   h->ncol = ncol;
   h->ncol_pad = ((long long)ncol + SAMSIM_BLOCK - 1) / SAMSIM_BLOCK * SAMSIM_BLOCK;
   h->LS = cfg->Nlayer + 2;
-  if ((unsigned long long)h->LS * (unsigned long long)h->ncol_pad >= (1ull << 32)) {
+  if ((unsigned long long)AR_COUNT * h->LS * (unsigned long long)h->ncol_pad >= (1ull << 32)) {
     delete h;
-    return fail(SAMSIM_ERR_ARG, "create: (Nlayer+2)*ncol must stay below 2^32 (32-bit layer-major index); use several handles");
+    return fail(SAMSIM_ERR_ARG, "create: 22*(Nlayer+2)*ncol must stay below 2^32 (32-bit element index); use several handles");
   }
   DevCfg& d = h->dcfg;
   memset(&d, 0, sizeof d);

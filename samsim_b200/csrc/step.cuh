@@ -35,26 +35,26 @@ __device__ __forceinline__ double lab_rec(const Forcing& f, int kind, long long 
 __device__ __noinline__ void vital_signs(const DevCfg& g, Col& c) {
   const int Na = c.N_active;
   double sumH = 0.0, summ = 0.0, sumS = 0.0;
-  for (int k = 1; k <= Na; k++) { sumH = sumH + c.H_abs[k]; summ = summ + c.m[k]; sumS = sumS + c.S_abs[k]; }
+  for (int k = 1; k <= Na; k++) { sumH = sumH + c.H_abs()[k]; summ = summ + c.m()[k]; sumS = sumS + c.S_abs()[k]; }
   SCV(c, SC_ENERGY_STORED) = SCV(c, SC_H_ABS_SNOW) + sumH - SCV(c, SC_T_BOTTOM) * summ * c_l;
   double fw = summ / rho_l;
   fw = fw * (1.0 - sumS / summ / ref_salinity);
   fw = fw + SCV(c, SC_M_SNOW) / rho_l;
   SCV(c, SC_FRESHWATER) = fw;
   double tr = 0.0;
-  for (int jj = 1; jj <= Na - 1; jj++) tr = tr + c.thick[jj] / (c.psi_l[jj] * k_l + c.psi_s[jj] * k_s);
-  const double thNa = c.thick[Na], psNa = c.psi_s[Na];
+  for (int jj = 1; jj <= Na - 1; jj++) tr = tr + c.thick()[jj] / (c.psi_l()[jj] * k_l + c.psi_s()[jj] * k_s);
+  const double thNa = c.thick()[Na], psNa = c.psi_s()[Na];
   tr = tr + thNa * psNa / psi_s_min * (psi_s_min * k_s + 1.0 - psi_s_min * k_l);
   if (SCV(c, SC_THICK_SNOW) > g.thick_min / 110.0) tr = tr + SCV(c, SC_THICK_SNOW) / k_snow_of(SCV(c, SC_M_SNOW), SCV(c, SC_THICK_SNOW));
   SCV(c, SC_TOTAL_RESIST) = tr;
-  double th = (Na > 1) ? sum_fwd(c.thick, 1, Na - 1) : 0.0;
+  double th = (Na > 1) ? sum_fwd(c.thick(), 1, Na - 1) : 0.0;
   SCV(c, SC_THICKNESS) = th + thNa * psNa / psi_s_min;
   if (Na > 1) {
-    double b = sum_fwd(c.S_abs, 1, Na - 1) + c.S_abs[Na] * psNa / psi_s_min;
-    b = b / (sum_fwd(c.m, 1, Na - 1) + c.m[Na] * psNa / psi_s_min);
+    double b = sum_fwd(c.S_abs(), 1, Na - 1) + c.S_abs()[Na] * psNa / psi_s_min;
+    b = b / (sum_fwd(c.m(), 1, Na - 1) + c.m()[Na] * psNa / psi_s_min);
     SCV(c, SC_BULK_SALIN) = b;
   } else {
-    SCV(c, SC_BULK_SALIN) = c.S_abs[1] / c.m[1];
+    SCV(c, SC_BULK_SALIN) = c.S_abs()[1] / c.m()[1];
   }
 }
 
@@ -62,12 +62,12 @@ __device__ __noinline__ void vital_signs(const DevCfg& g, Col& c) {
 __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
   const int Na = c.N_active;
   const double dt = g.dt, thick_min = g.thick_min;
-  const double ps1 = c.psi_s[1], pl1 = c.psi_l[1], pg1 = c.psi_g[1], th1 = c.thick[1];
-  double T1 = c.T[1];
+  const double ps1 = c.psi_s()[1], pl1 = c.psi_l()[1], pg1 = c.psi_g()[1], th1 = c.thick()[1];
+  double T1 = c.T()[1];
   double& thick_snow = SCV(c, SC_THICK_SNOW);
   double& T_top = SCV(c, SC_T_TOP);
   double& fl_q_snow = SCV(c, SC_FL_Q_SNOW);
-  double flQ1 = c.fl_Q[1];
+  double flQ1 = c.fl_Q()[1];
   double fl_rad_Na = 0.0;  // fl_rad(N_active): 0 unless boundflux 2 recomputes it (fl_rad = 0 from init, mo_init.f90:1988)
 
   if (g.boundflux_flag == 1) {  // :77-86
@@ -115,8 +115,11 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
     {
       double temp2 = pen * (1.0 - albedo) * fl_sw;
       double last_th = -1.0, last_e = 0.0;
-      for (int k = 1; k <= Na; k++) {
-        const double thk = c.thick[k];
+      // no penetrating short wave (polar night, or snow: pen = 0): 0 - 0*exp(..) = 0 and the product stays 0
+      const int kend = (temp2 == 0.0) ? 0 : Na;
+      for (int k = 1; k <= kend; k++) {
+        if (k + SAMSIM_PF <= Na) c.thick().prefetch(k + SAMSIM_PF);
+        const double thk = c.thick()[k];
         if (thk != last_th) { last_e = det_exp(-extinc * thk); last_th = thk; }
         if (k == Na) fl_rad_Na = temp2 - temp2 * last_e;
         temp2 = temp2 * last_e;
@@ -125,7 +128,7 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
 
     double& T_freeze = SCV(c, SC_T_FREEZE);
     if (thick_snow >= thick_min / 100.0) T_freeze = 0.0;  // :158-162
-    else T_freeze = T_freeze_of(c.S_abs[1] / c.m[1], g.salt_flag);
+    else T_freeze = T_freeze_of(c.S_abs()[1] / c.m()[1], g.salt_flag);
 
     if (T_top > T_freeze && Na > 1) {  // :167-180
       temp1 = emi * sigma * P4(T_freeze + zeroK) - (1.0 - albedo) * (1.0 - pen) * fl_sw - fl_rest;
@@ -156,7 +159,7 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
     const double T2m = SCV(c, SC_T2M);
     double& T_freeze = SCV(c, SC_T_FREEZE);
     if (g.lab_snow_flag == 0 || thick_snow <= thick_min / 100.0) {
-      T_freeze = f_min(T_freeze_of(c.S_abs[Na] / c.m[Na], g.salt_flag), 0.0);
+      T_freeze = f_min(T_freeze_of(c.S_abs()[Na] / c.m()[Na], g.salt_flag), 0.0);
       T_top = T1;
       flQ1 = g.alpha_flux_instable * (T_top - T2m);
       if (flQ1 < 0.0) {
@@ -190,8 +193,8 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
   }
 
   const double fl_q_bottom = SCV(c, SC_FL_Q_BOTTOM);
-  c.fl_Q[1] = flQ1;
-  c.fl_Q[Na + 1] = fl_q_bottom;  // :262
+  c.fl_Q()[1] = flQ1;
+  c.fl_Q()[Na + 1] = fl_q_bottom;  // :262 (every step: it is the entry that stays behind when N_active shrinks)
 
   // :269-285 in one forward pass: energy sums (forward order), inter-layer fluxes, explicit update.
   double temp1 = 0.0, temp2 = 0.0;
@@ -200,20 +203,26 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
     double ps_k = ps1, pl_k = pl1, pg_k = pg1, th_k = th1, T_k = T1;
     const double rad = fl_rad_Na * dt;
     for (int k = 1; k <= Na; k++) {
+      if (k + 1 + SAMSIM_PF <= Na) {
+        const int kp = k + 1 + SAMSIM_PF;
+        c.psi_s().prefetch(kp); c.psi_l().prefetch(kp); c.psi_g().prefetch(kp); c.thick().prefetch(kp); c.T().prefetch(kp);
+        c.H_abs().prefetch(kp);
+      }
       double fq_kp1;
       double ps_n = 0.0, pl_n = 0.0, pg_n = 0.0, th_n = 0.0, T_n = 0.0;
       if (k < Na) {
-        ps_n = c.psi_s[k + 1]; pl_n = c.psi_l[k + 1]; pg_n = c.psi_g[k + 1]; th_n = c.thick[k + 1]; T_n = c.T[k + 1];
+        ps_n = c.psi_s()[k + 1]; pl_n = c.psi_l()[k + 1]; pg_n = c.psi_g()[k + 1]; th_n = c.thick()[k + 1]; T_n = c.T()[k + 1];
         fq_kp1 = fl_Q_between(ps_k, pl_k, pg_k, th_k, T_k, ps_n, pl_n, pg_n, th_n, T_n);  // :272-274
-        c.fl_Q[k + 1] = fq_kp1;
+        if (c.want_state) c.fl_Q()[k + 1] = fq_kp1;  // fl_Q(2:N_active) is never read back by the loop body; N_active moves by
+                                                     // at most 1 per step, so a stale interior entry is always overwritten by a later :262
       } else {
         fq_kp1 = fl_q_bottom;
       }
-      double H = c.H_abs[k];
+      double H = c.H_abs()[k];
       temp1 = temp1 + H;                 // :269 sum(H_abs) before the update
       H = H + (fq_kp1 - fq_k) * dt;      // :277-279
       H = H + rad;                       // :282-285 (sic: fl_rad(N_active) for every layer)
-      c.H_abs[k] = H;
+      c.H_abs()[k] = H;
       temp2 = temp2 + H;                 // :305 sum(H_abs) after the update (layer 1 re-added below if coupling changes it)
       fq_k = fq_kp1;
       ps_k = ps_n; pl_k = pl_n; pg_k = pg_n; th_k = th_n; T_k = T_n;
@@ -225,9 +234,9 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
   bool layer1_changed = false;
   if (thick_snow >= thick_min / 100.0 && thick_snow < thick_min) {  // :291-295
     SCV(c, SC_H_ABS_SNOW) = SCV(c, SC_H_ABS_SNOW) - fl_q_snow * dt;
-    double H1 = c.H_abs[1], phi1 = c.phi[1];
-    snow_coupling(g, c, H1, phi1, T1, c.m[1], c.S_bu[1]);
-    c.H_abs[1] = H1; c.phi[1] = phi1; c.T[1] = T1;
+    double H1 = c.H_abs()[1], phi1 = c.phi()[1];
+    snow_coupling(g, c, H1, phi1, T1, c.m()[1], c.S_bu()[1]);
+    c.H_abs()[1] = H1; c.phi()[1] = phi1; c.T()[1] = T1;
     layer1_changed = true;
     temp1 = temp1 + fl_q_bottom * dt - fl_q_snow * dt;
   } else if (thick_snow >= thick_min) {  // :296-299
@@ -236,7 +245,7 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
   } else {
     temp1 = temp1 + fl_q_bottom * dt - flQ1 * dt;  // :302
   }
-  if (layer1_changed) temp2 = sum_fwd(c.H_abs, 1, Na);  // forward order requires a fresh pass when H_abs(1) moved
+  if (layer1_changed) temp2 = sum_fwd(c.H_abs(), 1, Na);  // forward order requires a fresh pass when H_abs(1) moved
   temp2 = temp2 + SCV(c, SC_H_ABS_SNOW);
   if (fabs((temp1 - temp2) / dt) > 0.00001) c.status = 431;  // :307-310
 }
@@ -282,12 +291,85 @@ __device__ __noinline__ void write_snapshot(const DevCfg& g, const Col& c, const
   if (s.arrays) {
     const int N = g.Nlayer;
     const size_t LS = (size_t)(N + 2);
-    const Lay* src[10] = {&c.T, &c.psi_s, &c.thick, &c.S_bu, &c.ray, &c.psi_l, &c.perm, &c.flush_v, &c.flush_h, &c.psi_g};
+    const int src[10] = {AR_T, AR_PSI_S, AR_THICK, AR_S_BU, AR_RAY, AR_PSI_L, AR_PERM, AR_FLUSH_V, AR_FLUSH_H, AR_PSI_G};
     for (int a = 0; a < 10; a++) {
       double* dst = s.arrays + ((size_t)a * LS) * s.ncol_pad + s.col;
+      const Lay from = c.A(src[a]);
       const int n = (a == 4) ? N - 1 : N;
-      for (int k = 1; k <= n; k++) dst[(size_t)k * s.ncol_pad] = (*src[a])[k];
+      for (int k = 1; k <= n; k++) dst[(size_t)k * s.ncol_pad] = from[k];
     }
+  }
+}
+
+// S4 + S5 + S7 in ONE forward pass, valid when c.thermo_valid (layers 2..N_active carry T, phi, S_bu from the S18
+// sweep, so S4 has no backward dependency left): volume fractions and S_br (S4, :298-307), expulsion_flux
+// (mo_mass.f90:112-136), mass_transfer (mo_mass.f90:53-96, skipped at i == 1) and S_bu = S_abs/m (S7, :333-335)
+// per layer, with fl_m and V_ex carried in registers instead of being written and re-read.  Same operations in
+// the same order as the three separate sweeps:
+//   * expulsion_flux finishes before mass_transfer starts in the reference, but mass_transfer reads neither m
+//     nor psi_g, and expulsion_flux reads neither H_abs nor S_abs;
+//   * mass_transfer(k) needs S_bu(k-1), S_bu(k+1) from S4 -> the old value is carried / not yet overwritten;
+//   * S7 overwrites S_bu(k) only after mass_transfer(k) and (through the carry) mass_transfer(k+1) used the old one.
+__device__ __noinline__ void fused_thermo_expulsion(const DevCfg& g, Col& c) {
+  const int Na = c.N_active;
+  const bool transfer = (c.i != 1);
+  const double T_bottom = SCV(c, SC_T_BOTTOM), S_bu_bottom = SCV(c, SC_S_BU_BOTTOM);
+  // layer 1 is always recomputed; its first guess is T(2) of the (valid) sweep, T_bottom when it is the only layer
+  double T_k, sbu_k, phi_k;
+  double m_k = c.m()[1];
+  {
+    sbu_k = c.S_abs()[1] / m_k;
+    const double H = c.H_abs()[1] / m_k;
+    phi_k = c.phi()[1];
+    const double T_test = (Na >= 2) ? c.T()[2] : T_bottom;
+    getT(g, H, sbu_k, T_test, T_k, phi_k, c.status);
+    c.T()[1] = T_k; c.phi()[1] = phi_k;
+  }
+  double T_km1 = 0.0, Sbu_km1 = 0.0, Sabs_km1 = 0.0, f0 = 0.0;
+  for (int k = 1; k <= Na; k++) {
+    if (k + SAMSIM_PF <= Na) {
+      c.T().prefetch(k + SAMSIM_PF); c.S_bu().prefetch(k + SAMSIM_PF); c.phi().prefetch(k + SAMSIM_PF);
+      c.m().prefetch(k + SAMSIM_PF); c.thick().prefetch(k + SAMSIM_PF); c.S_abs().prefetch(k + SAMSIM_PF);
+      c.H_abs().prefetch(k + SAMSIM_PF);
+    }
+    const double thk = c.thick()[k];
+    // neighbour below: old T, S_bu (S4 values) and the not yet updated S_abs
+    double T_kp1, Sbu_kp1, Sabs_kp1, phi_kp1 = 0.0, m_kp1 = 0.0;
+    if (k < Na) {
+      T_kp1 = c.T()[k + 1]; Sbu_kp1 = c.S_bu()[k + 1]; Sabs_kp1 = c.S_abs()[k + 1];
+      phi_kp1 = c.phi()[k + 1]; m_kp1 = c.m()[k + 1];
+    } else {
+      T_kp1 = T_bottom; Sbu_kp1 = S_bu_bottom; Sabs_kp1 = S_bu_bottom * 2000.0;
+    }
+    // S4: brine salinity and volume fractions
+    c.S_br()[k] = S_br_of(g, T_k, sbu_k);
+    double ps, pl, pg, vex;
+    expulsion(phi_k, thk, m_k, ps, pl, pg, vex);
+    // expulsion_flux, mo_mass.f90:121-134
+    double f1;
+    if (k == 1) {
+      f1 = -vex * rho_l;
+    } else if (pg < SAMSIM_F32(0.001)) {
+      f1 = -vex * rho_l + f0;
+    } else {
+      f1 = -f_max((vex - pg * thk) * rho_l, 0.0);
+      pg = f_max((pg * thk - vex) / thk, 0.0);
+    }
+    c.psi_s()[k] = ps; c.psi_l()[k] = pl; c.psi_g()[k] = pg;
+    const double m_new = m_k + f1 - f0;
+    c.m()[k] = m_new;
+    // mass_transfer layer k, then S7
+    double S = c.S_abs()[k];
+    if (transfer) {
+      double H = c.H_abs()[k];
+      mass_transfer_layer(g, f1, f0, T_km1, Sbu_km1, Sabs_km1, T_k, sbu_k, T_kp1, Sbu_kp1, Sabs_kp1, H, S);
+      c.H_abs()[k] = H;
+      c.S_abs()[k] = S;
+    }
+    c.S_bu()[k] = S / m_new;
+    T_km1 = T_k; Sbu_km1 = sbu_k; Sabs_km1 = S;
+    T_k = T_kp1; sbu_k = Sbu_kp1; phi_k = phi_kp1; m_k = m_kp1;
+    f0 = f1;
   }
 }
 
@@ -295,7 +377,9 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   const double dt = g.dt;
   const int N = g.Nlayer;
   c.i = c.i + 1;
+  c.want_state = want_diag;
   const bool output_step = (c.n_time_out == g.i_time_out || c.i == 1);
+  const bool fused = c.thermo_valid;  // S4+S5+S7 as one forward pass (bit-identical, see fused_thermo_expulsion)
 
   if (c.status == 0) {  // ===== phase 0 =====
   // ---- S0 :192-223 (only observable at S8 or through get_scalar after the launch) ----
@@ -335,9 +419,9 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
       if (c.N_active > 1) {
         snow_precip(c, dt, lp, SCV(c, SC_T2M), have_solid, sp);
       } else if (c.N_active == 1) {
-        double H1 = c.H_abs[1], S1 = c.S_abs[1];
-        snow_precip_0(H1, S1, c.m[1], c.T[1], dt, lp, SCV(c, SC_T2M), have_solid, sp);
-        c.H_abs[1] = H1; c.S_abs[1] = S1;
+        double H1 = c.H_abs()[1], S1 = c.S_abs()[1];
+        snow_precip_0(H1, S1, c.m()[1], c.T()[1], dt, lp, SCV(c, SC_T2M), have_solid, sp);
+        c.H_abs()[1] = H1; c.S_abs()[1] = S1;
       }
     }
   }
@@ -357,9 +441,11 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   // (c.thermo_valid), getT would be called with the same H, S_bu and the same chained first guess and return the
   // same T, phi: those layers skip the Newton iterations.  Layer 1 (snow, precipitation, melt water) is always
   // recomputed.  Expulsion depends on phi from S18, so it is evaluated every step.
-  {
+  if (fused) {
+    fused_thermo_expulsion(g, c);
+  } else {
     double T_test = SCV(c, SC_T_BOTTOM);
-    const bool reuse = c.thermo_valid;
+    const bool reuse = false;
 #if SAMSIM_SYNC >= 2
     for (int k = g.Nlayer; k >= 1; k--) {
       SAMSIM_LAYER_SYNC();
@@ -368,26 +454,26 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     for (int k = c.N_active; k >= 1; k--) {
 #endif
       if (k - SAMSIM_PF >= 1) {
-        c.m.prefetch(k - SAMSIM_PF); c.thick.prefetch(k - SAMSIM_PF);
-        if (reuse) { c.T.prefetch(k - SAMSIM_PF); c.phi.prefetch(k - SAMSIM_PF); c.S_bu.prefetch(k - SAMSIM_PF); }
-        else { c.S_abs.prefetch(k - SAMSIM_PF); c.H_abs.prefetch(k - SAMSIM_PF); }
+        c.m().prefetch(k - SAMSIM_PF); c.thick().prefetch(k - SAMSIM_PF);
+        if (reuse) { c.T().prefetch(k - SAMSIM_PF); c.phi().prefetch(k - SAMSIM_PF); c.S_bu().prefetch(k - SAMSIM_PF); }
+        else { c.S_abs().prefetch(k - SAMSIM_PF); c.H_abs().prefetch(k - SAMSIM_PF); }
       }
-      const double mk = c.m[k];
+      const double mk = c.m()[k];
       double sbu, T, phi;
       if (reuse && k >= 2) {
-        sbu = c.S_bu[k]; T = c.T[k]; phi = c.phi[k];
+        sbu = c.S_bu()[k]; T = c.T()[k]; phi = c.phi()[k];
       } else {
-        sbu = c.S_abs[k] / mk;
-        const double H = c.H_abs[k] / mk;
-        phi = c.phi[k];
+        sbu = c.S_abs()[k] / mk;
+        const double H = c.H_abs()[k] / mk;
+        phi = c.phi()[k];
         getT(g, H, sbu, T_test, T, phi, c.status);
-        c.S_bu[k] = sbu; c.T[k] = T; c.phi[k] = phi;
+        c.S_bu()[k] = sbu; c.T()[k] = T; c.phi()[k] = phi;
       }
       T_test = T;
-      c.S_br[k] = S_br_of(g, T, sbu);
+      c.S_br()[k] = S_br_of(g, T, sbu);
       double ps, pl, pg, vex;
-      expulsion(phi, c.thick[k], mk, ps, pl, pg, vex);
-      c.psi_s[k] = ps; c.psi_l[k] = pl; c.psi_g[k] = pg; c.V_ex[k] = vex;
+      expulsion(phi, c.thick()[k], mk, ps, pl, pg, vex);
+      c.psi_s()[k] = ps; c.psi_l()[k] = pl; c.psi_g()[k] = pg; c.V_ex()[k] = vex;
     }
     }
 
@@ -395,33 +481,33 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   SAMSIM_PHASE_SYNC();
   if (c.status == 0) {  // ===== phase 2 =====
   // ---- S5 expulsion_flux (mo_mass.f90:112-136) then mass_transfer (skipped at i == 1) :312-321 ----
-  {
+  if (!fused) {
     const int Na = c.N_active;
-    Lay fl_m = c.fl_m;
+    Lay fl_m = c.fl_m();
     double f0 = 0.0;
     fl_m[1] = 0.0;
     for (int k = 1; k <= Na; k++) {
       double f1;
-      const double vex = c.V_ex[k];
+      const double vex = c.V_ex()[k];
       if (k == 1) {
         f1 = -vex * rho_l;
       } else {
-        const double pg = c.psi_g[k];
+        const double pg = c.psi_g()[k];
         if (pg < SAMSIM_F32(0.001)) {
           f1 = -vex * rho_l + f0;
         } else {
-          const double thk = c.thick[k];
+          const double thk = c.thick()[k];
           f1 = -f_max((vex - pg * thk) * rho_l, 0.0);
-          c.psi_g[k] = f_max((pg * thk - vex) / thk, 0.0);
+          c.psi_g()[k] = f_max((pg * thk - vex) / thk, 0.0);
         }
       }
       fl_m[k + 1] = f1;
-      c.m[k] = c.m[k] + f1 - f0;
+      c.m()[k] = c.m()[k] + f1 - f0;
       f0 = f1;
     }
-    if (c.i != 1) mass_transfer(g, c, fl_m);
+    if (c.i != 1) mass_transfer(g, c, fl_m, c.S_bu());
     // ---- S7 :333-335 ----
-    for (int k = Na; k >= 1; k--) c.S_bu[k] = c.S_abs[k] / c.m[k];
+    for (int k = Na; k >= 1; k--) c.S_bu()[k] = c.S_abs()[k] / c.m()[k];
   }
 
   // ---- S8 output :340-398 ----
@@ -447,20 +533,20 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   // ---- S9 gas in the lowest layer :405-410 ----
   {
     const int Na = c.N_active;
-    const double pg = c.psi_g[Na];
+    const double pg = c.psi_g()[Na];
     if (pg > 0.0) {
-      const double temp2 = pg * c.thick[Na] * rho_l;
-      c.m[Na] = c.m[Na] + temp2;
-      c.S_abs[Na] = c.S_abs[Na] + temp2 * SCV(c, SC_S_BU_BOTTOM);
-      c.H_abs[Na] = c.H_abs[Na] + temp2 * c_l * SCV(c, SC_T_BOTTOM);
+      const double temp2 = pg * c.thick()[Na] * rho_l;
+      c.m()[Na] = c.m()[Na] + temp2;
+      c.S_abs()[Na] = c.S_abs()[Na] + temp2 * SCV(c, SC_S_BU_BOTTOM);
+      c.H_abs()[Na] = c.H_abs()[Na] + temp2 * c_l * SCV(c, SC_T_BOTTOM);
     }
   }
 
   // ---- S10 thin snow coupling :418-420 ----
   if (SCV(c, SC_M_SNOW) > 0.0 && SCV(c, SC_THICK_SNOW) < g.thick_min) {
-    double H1 = c.H_abs[1], phi1 = c.phi[1], T1 = c.T[1];
-    snow_coupling(g, c, H1, phi1, T1, c.m[1], c.S_bu[1]);
-    c.H_abs[1] = H1; c.phi[1] = phi1; c.T[1] = T1;
+    double H1 = c.H_abs()[1], phi1 = c.phi()[1], T1 = c.T()[1];
+    snow_coupling(g, c, H1, phi1, T1, c.m()[1], c.S_bu()[1]);
+    c.H_abs()[1] = H1; c.phi()[1] = phi1; c.T()[1] = T1;
     }
 
   // ---- S11 flooding :428-445 ----
@@ -475,9 +561,9 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   // ---- S12 turbulence (sub_turb_flux, mo_functions.f90:347-363) :450-457 ----
   if (g.turb_flag == 2) {
     const int Na = c.N_active;
-    const double S = c.S_abs[Na], mNa = c.m[Na];
-    const double turb = Turb_A * det_exp(Turb_B * (-density_of(SCV(c, SC_T_BOTTOM), SCV(c, SC_S_BU_BOTTOM)) + density_of(c.T[Na], S / mNa))) * dt;
-    c.S_abs[Na] = S - turb * (S / mNa - SCV(c, SC_S_BU_BOTTOM));
+    const double S = c.S_abs()[Na], mNa = c.m()[Na];
+    const double turb = Turb_A * det_exp(Turb_B * (-density_of(SCV(c, SC_T_BOTTOM), SCV(c, SC_S_BU_BOTTOM)) + density_of(c.T()[Na], S / mNa))) * dt;
+    c.S_abs()[Na] = S - turb * (S / mNa - SCV(c, SC_S_BU_BOTTOM));
   }
 
   }
@@ -497,12 +583,12 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
       SCV(c, SC_T_TOP) = (((int)j) & 1) ? SCV(c, SC_TTOP_COLD) : SCV(c, SC_TTOP_WARM);
   } else if (g.testcase >= 101 && g.testcase <= 105) {  // :521-530
     const long long idx = (long long)floor(1 + c.time / dt);
-    const double Sb = c.S_bu[c.N_active + 1];
+    const double Sb = c.S_bu()[c.N_active + 1];
     SCV(c, SC_T2M) = lab_rec(f, 0, idx);
     SCV(c, SC_SOLID_PRECIP) = lab_rec(f, 1, idx);
     SCV(c, SC_FL_Q_BOTTOM) = lab_rec(f, 2, idx);
     SCV(c, SC_T_BOTTOM) = -SAMSIM_F32(0.0575) * Sb + SAMSIM_F32(1.710523e-3) * det_pow(Sb, 3.0 / 2.0) -
-                          SAMSIM_F32(2.154996e-4) * P2(Sb) - SAMSIM_F32(7.53e-4) * sum_fwd(c.thick, 1, c.N_active - 1);
+                          SAMSIM_F32(2.154996e-4) * P2(Sb) - SAMSIM_F32(7.53e-4) * sum_fwd(c.thick(), 1, c.N_active - 1);
     c.styropor_flag = (int)lab_rec(f, 3, idx);
   } else if (g.testcase == 4 || g.testcase == 7) {  // sub_test4, mo_testcase_specifics.f90:197-202
     const double amp = SCV(c, SC_OFLUX_AMP);
@@ -511,7 +597,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
 
   // ---- S16 tank :573-578 ----
   if (g.tank_flag == 2) {
-    SCV(c, SC_S_BU_BOTTOM) = (SCV(c, SC_S_TOTAL) - sum_fwd(c.S_abs, 1, c.N_active)) / (g.m_total - sum_fwd(c.m, 1, c.N_active));
+    SCV(c, SC_S_BU_BOTTOM) = (SCV(c, SC_S_TOTAL) - sum_fwd(c.S_abs(), 1, c.N_active)) / (g.m_total - sum_fwd(c.m(), 1, c.N_active));
   }
 
   // ---- S17 heat fluxes :584 ----
@@ -534,14 +620,14 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
 #else
     for (int k = c.N_active; k >= 1; k--) {
 #endif
-      if (k - SAMSIM_PF >= 1) { c.m.prefetch(k - SAMSIM_PF); c.S_abs.prefetch(k - SAMSIM_PF); c.H_abs.prefetch(k - SAMSIM_PF); c.phi.prefetch(k - SAMSIM_PF); }
-      const double mk = c.m[k];
-      const double sbu = c.S_abs[k] / mk;
-      const double H = c.H_abs[k] / mk;
-      double T, phi = c.phi[k];
+      if (k - SAMSIM_PF >= 1) { c.m().prefetch(k - SAMSIM_PF); c.S_abs().prefetch(k - SAMSIM_PF); c.H_abs().prefetch(k - SAMSIM_PF); c.phi().prefetch(k - SAMSIM_PF); }
+      const double mk = c.m()[k];
+      const double sbu = c.S_abs()[k] / mk;
+      const double H = c.H_abs()[k] / mk;
+      double T, phi = c.phi()[k];
       getT(g, H, sbu, T_test, T, phi, c.status);
       T_test = T;
-      c.S_bu[k] = sbu; c.T[k] = T; c.phi[k] = phi;
+      c.S_bu()[k] = sbu; c.T()[k] = T; c.phi()[k] = phi;
     }
       c.thermo_valid = true;  // invalidated below by anything that touches layers >= 2
   }
@@ -556,22 +642,22 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
 
   // ---- S20 flushing preparations :632-664 ----
   if (c.N_active > 1 && g.flush_flag > 2 && (g.boundflux_flag == 2 || g.boundflux_flag == 3)) {
-    SCV(c, SC_T_FREEZE) = T_freeze_of(c.S_abs[1] / c.m[1], g.salt_flag);
+    SCV(c, SC_T_FREEZE) = T_freeze_of(c.S_abs()[1] / c.m()[1], g.salt_flag);
     SCV(c, SC_MELT_THICK) = 0.0;
     if (freeboard_of(g, c) > 0.0000000000001) {
-      const double ps1 = c.psi_s[1];
+      const double ps1 = c.psi_s()[1];
       const double T_drive = (g.boundflux_flag == 2) ? SCV(c, SC_T_TOP) : SCV(c, SC_T2M);
       if (ps1 < psi_s_top_min || T_drive >= SCV(c, SC_T_FREEZE)) {
-        double th1 = c.thick[1];
-        melt_thick_of(c.psi_l[1], ps1, c.psi_g[1], c.T[1], SCV(c, SC_T_FREEZE), T_drive, c.fl_Q[1], SCV(c, SC_THICK_SNOW), dt,
+        double th1 = c.thick()[1];
+        melt_thick_of(c.psi_l()[1], ps1, c.psi_g()[1], c.T()[1], SCV(c, SC_T_FREEZE), T_drive, c.fl_Q()[1], SCV(c, SC_THICK_SNOW), dt,
                       SCV(c, SC_MELT_THICK), th1, g.thick_min);
         if (g.boundflux_flag == 3) SCV(c, SC_MELT_THICK) = f_max(SCV(c, SC_MELT_THICK), 0.0);
         if (SCV(c, SC_THICK_SNOW) >= g.thick_min / 100.0 && SCV(c, SC_MELT_THICK) > 0.00000000001 && SCV(c, SC_MELT_THICK_SNOW) == 0.0) {
-          double H1 = c.H_abs[1], m1 = c.m[1];
+          double H1 = c.H_abs()[1], m1 = c.m()[1];
           melt_snow(SCV(c, SC_MELT_THICK), th1, SCV(c, SC_THICK_SNOW), H1, SCV(c, SC_H_ABS_SNOW), m1, SCV(c, SC_M_SNOW), SCV(c, SC_PSI_G_SNOW));
-          c.H_abs[1] = H1; c.m[1] = m1;
+          c.H_abs()[1] = H1; c.m()[1] = m1;
         }
-        c.thick[1] = th1;
+        c.thick()[1] = th1;
       }
     }
   }
@@ -583,13 +669,13 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   SCV(c, SC_MELT_THICK) = SCV(c, SC_MELT_THICK) + SCV(c, SC_MELT_THICK_SNOW);
   if (SCV(c, SC_MELT_THICK_SNOW) > 0.0) {  // :677-685
     const double mts = SCV(c, SC_MELT_THICK_SNOW), T_snow = SCV(c, SC_T_SNOW);
-    const double H1 = c.H_abs[1] + mts * rho_l * c_l * T_snow;
-    const double S1 = c.S_abs[1] + mts * rho_l * S_br_of(g, T_snow, SCV(c, SC_S_ABS_SNOW) / SCV(c, SC_M_SNOW));
-    const double m1 = c.m[1] + mts * rho_l;
-    c.H_abs[1] = H1; c.S_abs[1] = S1;
-    c.thick[1] = c.thick[1] + mts;
-    c.m[1] = m1;
-    c.S_bu[1] = S1 / m1;
+    const double H1 = c.H_abs()[1] + mts * rho_l * c_l * T_snow;
+    const double S1 = c.S_abs()[1] + mts * rho_l * S_br_of(g, T_snow, SCV(c, SC_S_ABS_SNOW) / SCV(c, SC_M_SNOW));
+    const double m1 = c.m()[1] + mts * rho_l;
+    c.H_abs()[1] = H1; c.S_abs()[1] = S1;
+    c.thick()[1] = c.thick()[1] + mts;
+    c.m()[1] = m1;
+    c.S_bu()[1] = S1 / m1;
   }
   // flush_v/h: old = cur; cur = 0; [flush3 fills 1..N_active]; cur = cur + old  (:697-701, :736-737).
   // Without flush3 that is the identity; with it, new + old.  w-arrays hold the old values.
@@ -597,21 +683,21 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     if (g.flush_flag == 4) {  // :704-713
       const double mt = SCV(c, SC_MELT_THICK);
       if (mt > 0.000000000001 && c.N_active > 2) {
-        const double m1 = c.m[1];
-        c.H_abs[1] = c.H_abs[1] - mt * rho_l * c_l * c.T[1];
-        c.S_abs[1] = c.S_abs[1] * (1.0 - (mt * rho_l) / m1);
-        c.thick[1] = c.thick[1] - mt;
-        c.m[1] = m1 - mt * rho_l;
+        const double m1 = c.m()[1];
+        c.H_abs()[1] = c.H_abs()[1] - mt * rho_l * c_l * c.T()[1];
+        c.S_abs()[1] = c.S_abs()[1] * (1.0 - (mt * rho_l) / m1);
+        c.thick()[1] = c.thick()[1] - mt;
+        c.m()[1] = m1 - mt * rho_l;
       }
     } else if (g.flush_flag == 5) {  // :715-728
       if (SCV(c, SC_MELT_THICK) > 0.000000000001 && c.N_active > 2 && SCV(c, SC_FREEBOARD) > 0.0) {
         SCV(c, SC_FREEBOARD) = freeboard_of(g, c);
         const int Na = c.N_active;
-        Lay old_v = c.V_ex, old_h = c.S_br;  // both dead after S13
-        for (int k = 1; k <= Na; k++) { old_v[k] = c.flush_v[k]; old_h[k] = c.flush_h[k]; }
+        Lay old_v = c.V_ex(), old_h = c.S_br();  // both dead after S13
+        for (int k = 1; k <= Na; k++) { old_v[k] = c.flush_v()[k]; old_h[k] = c.flush_h()[k]; }
         flush3(g, c);
         c.thermo_valid = false;
-        for (int k = 1; k <= Na; k++) { c.flush_v[k] = c.flush_v[k] + old_v[k]; c.flush_h[k] = c.flush_h[k] + old_h[k]; }
+        for (int k = 1; k <= Na; k++) { c.flush_v()[k] = c.flush_v()[k] + old_v[k]; c.flush_h()[k] = c.flush_h()[k] + old_h[k]; }
             }
     } else if (g.flush_flag == 6) {  // :729-733
       if (SCV(c, SC_MELT_THICK) > 0.000000000001 && c.N_active > 2 && SCV(c, SC_THICK_SNOW) < g.thick_0) {
@@ -627,32 +713,32 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   // ---- S23 layer dynamics :755-795 ----
   if (c.N_active > 1) {
     const int Na = c.N_active;
-    const double r1 = c.thick[1] / g.thick_0;
-    if (c.phi[Na] > psi_s_min || c.phi[Na - 1] <= psi_s_min / 2.0 || r1 > 1.5 || r1 < 0.5) {
+    const double r1 = c.thick()[1] / g.thick_0;
+    if (c.phi()[Na] > psi_s_min || c.phi()[Na - 1] <= psi_s_min / 2.0 || r1 > 1.5 || r1 < 0.5) {
       layer_dynamics(g, c);
       c.thermo_valid = false;
         }
     const int Nb = c.N_active;
-    if (Nb < N && c.thick[(Nb + 1 < N) ? Nb + 1 : N] == 0) {  // :772-783 scrub
-      c.T[Nb + 1] = SCV(c, SC_T_BOTTOM);
-      c.S_bu[Nb + 1] = SCV(c, SC_S_BU_BOTTOM);
-      c.psi_l[Nb + 1] = 1.0;
-      c.psi_s[Nb + 1] = 0.0;
+    if (Nb < N && c.thick()[(Nb + 1 < N) ? Nb + 1 : N] == 0) {  // :772-783 scrub
+      c.T()[Nb + 1] = SCV(c, SC_T_BOTTOM);
+      c.S_bu()[Nb + 1] = SCV(c, SC_S_BU_BOTTOM);
+      c.psi_l()[Nb + 1] = 1.0;
+      c.psi_s()[Nb + 1] = 0.0;
     }
   } else {
-    if (c.phi[1] > psi_s_min) { layer_dynamics(g, c); c.thermo_valid = false; }
+    if (c.phi()[1] > psi_s_min) { layer_dynamics(g, c); c.thermo_valid = false; }
     }
 
   // ---- S24 timestep + health check :802-819 ----
   c.time = c.time + dt;
   {
     const int Na = c.N_active;
-    double mn = c.psi_s[1], ms = c.S_abs[1];
-    for (int k = 2; k <= Na; k++) { mn = f_min(mn, c.psi_s[k]); ms = f_min(ms, c.S_abs[k]); }
+    double mn = c.psi_s()[1], ms = c.S_abs()[1];
+    for (int k = 2; k <= Na; k++) { mn = f_min(mn, c.psi_s()[k]); ms = f_min(ms, c.S_abs()[k]); }
     if (mn < 0.0) {
       c.status = 1337;
     } else if (ms < 0.0) {
-      for (int k = 1; k <= Na; k++) c.S_abs[k] = f_max(c.S_abs[k], 0.0);
+      for (int k = 1; k <= Na; k++) c.S_abs()[k] = f_max(c.S_abs()[k], 0.0);
       c.thermo_valid = false;
     }
   }
