@@ -107,6 +107,15 @@ struct Col {
   bool thermo_valid;
   // last step of the launch: arrays that are only observable through get_array (fl_Q(2:)) are written
   bool want_state;
+  // func_freeboard memo (see freeboard_of): everything here is a value the reference would recompute identically
+  struct FbMemo {
+    bool tot_valid;  double t1, A, G;          // forward totals SUM(psi_s*thick), SUM(psi_g*thick) for thick(1) == t1
+    bool suf_valid;  int ks; double As, Gs;    // exact forward sums over layers ks+1..N_active
+    bool res_valid;  double m1, th1, msnow, result;  // last result and the layer-1 / snow inputs it was computed from
+    int k_last;                                // waterline layer of the last evaluation (start guess for the next step)
+  } fb;
+  // order-independent minima gathered by sweeps that read the data anyway (S24 health check, mo_grotz.f90:808-819)
+  double min_psi_s, min_S_abs_2;
   double sc[SC_COUNT];
   // clock (shared by the batch, advanced in lock step)
   double time;
@@ -312,15 +321,28 @@ __device__ __forceinline__ double sum_prod_fwd(const Lay& a, const Lay& b, int i
 // total - prefix (equal to the forward sum up to a rounding error bounded far below `margin`); the exact forward
 // sum is evaluated only where the decision is within the margin or the loop stops, so the returned value is the
 // reference's, bit for bit, at O(N) cost.
-__device__ __noinline__ double freeboard_of(const DevCfg& g, const Col& c) {
+// Memo: (1) the result is reused while its inputs are unchanged -- psi_s, psi_g, thick(2:), m(2:) only change at
+// S4/S5 and at flood/flush/layer events (which reset the memo), so between the calls of one step only m(1),
+// thick(1), m_snow can differ and they are compared; (2) the forward totals are reused while thick(1) is unchanged;
+// (3) the exact suffix sums for waterline layer ks are reused.  (2) and (3) are pre-filled by the fused S4 pass.
+__device__ __noinline__ double freeboard_of(const DevCfg& g, Col& c) {
   const int Na = c.N_active;
   const double snowmass = (g.freeboard_snow_flag == 0) ? SCV(c, SC_M_SNOW) : 0.0;
-  double A = 0.0, G = 0.0;  // forward totals, the reference's order
-  for (int q = 1; q <= Na; q++) {
-    if (q + SAMSIM_PF <= Na) { c.psi_s().prefetch(q + SAMSIM_PF); c.psi_g().prefetch(q + SAMSIM_PF); c.thick().prefetch(q + SAMSIM_PF); }
-    const double t = c.thick()[q];
-    A = A + c.psi_s()[q] * t;
-    G = G + c.psi_g()[q] * t;
+  const double m1 = c.m()[1], th1 = c.thick()[1];
+  Col::FbMemo& fb = c.fb;
+  if (fb.res_valid && fb.m1 == m1 && fb.th1 == th1 && fb.msnow == snowmass) return fb.result;
+  double A, G;
+  if (fb.tot_valid && fb.t1 == th1) {
+    A = fb.A; G = fb.G;
+  } else {
+    A = 0.0; G = 0.0;  // forward totals, the reference's order
+    for (int q = 1; q <= Na; q++) {
+      if (q + SAMSIM_PF <= Na) { c.psi_s().prefetch(q + SAMSIM_PF); c.psi_g().prefetch(q + SAMSIM_PF); c.thick().prefetch(q + SAMSIM_PF); }
+      const double t = c.thick()[q];
+      A = A + c.psi_s()[q] * t;
+      G = G + c.psi_g()[q] * t;
+    }
+    fb.tot_valid = true; fb.t1 = th1; fb.A = A; fb.G = G;
   }
   const double buoy = A * (rho_l - rho_s) + G * rho_l;
   double freeboard;
@@ -339,23 +361,32 @@ __device__ __noinline__ double freeboard_of(const DevCfg& g, const Col& c) {
       msum_prev = msum;
       msum = msum + c.m()[k];       // SUM(m(1:k)): fixed-start prefix, incremental is the same order
       thsum_prev = thsum;
-      thsum = thsum + t;          // SUM(thick(1:k)) likewise
+      thsum = thsum + t;            // SUM(thick(1:k)) likewise
       test1 = msum + snowmass;
       const double approx = (A - pA) * (rho_l - rho_s) + (G - pG) * rho_l;
       if (test1 < approx - margin) {
-        test2 = approx + margin;  // certainly test1 < exact test2: keep looping (value unused)
+        test2 = approx + margin;    // certainly test1 < exact test2: keep looping (value unused)
       } else {
-        test2 = sum_prod_fwd(c.psi_s(), c.thick(), k + 1, Na) * (rho_l - rho_s) + sum_prod_fwd(c.psi_g(), c.thick(), k + 1, Na) * rho_l;
+        if (!(fb.suf_valid && fb.ks == k)) {
+          fb.As = sum_prod_fwd(c.psi_s(), c.thick(), k + 1, Na);
+          fb.Gs = sum_prod_fwd(c.psi_g(), c.thick(), k + 1, Na);
+          fb.ks = k; fb.suf_valid = true;
+        }
+        test2 = fb.As * (rho_l - rho_s) + fb.Gs * rho_l;
       }
     }
+    fb.k_last = k;
     test1 = msum_prev + snowmass;  // :121 SUM(m(1:k-1))
     const double mk = c.m()[k], tk = c.thick()[k];
     freeboard = test2 - test1 + (rho_l - mk / tk) * tk;  // :124
     freeboard = freeboard / rho_l;
     freeboard = freeboard + thsum_prev;                  // :126 SUM(thick(1:k-1))
   }
+  fb.res_valid = true; fb.m1 = m1; fb.th1 = th1; fb.msnow = snowmass; fb.result = freeboard;
   return freeboard;
 }
+// every change of psi_s / psi_g / thick(2:) / m(2:) / N_active goes through one of these
+__device__ __forceinline__ void fb_reset(Col& c) { c.fb.tot_valid = false; c.fb.suf_valid = false; c.fb.res_valid = false; }
 
 // sub_melt_thick, mo_functions.f90:386-428
 __device__ __forceinline__ void melt_thick_of(double psi_l, double psi_s, double psi_g, double T, double T_freeze,
@@ -764,7 +795,9 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c) {
     carry_t = at[0];
   }
 
-  SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) + sum_fwd(c.S_abs(), 1, Na);  // :141 (inactive layers hold 0)
+  // :141 / :173 grav_salt = grav_salt + SUM(S_abs) before the drain loop and - SUM(S_abs) after it: both are
+  // forward sums over the layers the loop visits in the same order, so they are accumulated inside it.
+  double sum_before = 0.0, sum_after = 0.0;
 
   double run = 0.0;  // running sum = fl_up(kk) for every kk not yet clamped
   fl_m[1] = 0.0;
@@ -777,12 +810,15 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c) {
     const double rk = c.ray()[k], psk = c.psi_s()[k], Sk = c.S_abs()[k], mk = c.m()[k];
     const double sbk1 = c.S_br()[k + 1];
     double up = run;
+    double S_after = Sk;
+    sum_before = sum_before + Sk;
     if (rk > ray_crit && psk > 0.001 && Sk / mk > 0.1 && sbk > sbk1) {
       const double plk = c.psi_l()[k], thk = c.thick()[k], Tk = c.T()[k];
       double flux = x_grav * (rk - ray_crit) * dt * thk;
       flux = f_min(flux, plk * rho_l * thk);
       double Snew = Sk - flux * sbk;
       c.S_abs()[k] = Snew;
+      S_after = Snew;
       if (Snew < 0.0) { c.status = 21234; return; }
       SCV(c, SC_GRAV_TEMP) = SCV(c, SC_GRAV_TEMP) + flux * Tk;
       c.H_abs()[k] = c.H_abs()[k] - flux * c_l * Tk;
@@ -791,12 +827,18 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c) {
       up = f_min(run, plk * rho_l * thk);
     }
     fl_m[k + 1] = up;  // fl_m(2:N_active+1) = fl_up(1:N_active), :177
+    sum_after = sum_after + S_after;
     sbk = sbk1;
   }
   fl_m[Na + 1] = run;
   const double fl_up_Na = run;
-
-  SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) - sum_fwd(c.S_abs(), 1, Na);  // :173
+  {
+    const double S_Na = c.S_abs()[Na];  // layer N_active never drains; inactive layers hold 0
+    sum_before = sum_before + S_Na;
+    sum_after = sum_after + S_Na;
+  }
+  SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) + sum_before;  // :141
+  SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) - sum_after;   // :173
 
   mass_transfer(g, c, fl_m, c.S_bu());  // :188
 

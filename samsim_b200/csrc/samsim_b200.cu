@@ -99,6 +99,9 @@ __global__ void __launch_bounds__(SAMSIM_BLOCK, SAMSIM_MINBLOCKS) samsim_step_ke
   c.time = p.time; c.i = p.i; c.n_time_out = p.n_time_out; c.time_counter = p.time_counter;
   c.fsw0 = c.fsw1 = c.flw0 = c.flw1 = c.ftime0 = c.ftime1 = 0.0;
   c.thermo_valid = false;  // launch-local: the host may have changed the state between launches
+  c.want_state = false;
+  c.fb.tot_valid = c.fb.suf_valid = c.fb.res_valid = false; c.fb.k_last = 0; c.fb.ks = 0;
+  c.min_psi_s = 0.0; c.min_S_abs_2 = 0.0;
 
   Forcing f;
   f.win = s_win; f.win_len = p.win_len; f.win_first = p.win_first;

@@ -326,6 +326,10 @@ __device__ __noinline__ void fused_thermo_expulsion(const DevCfg& g, Col& c) {
     c.T()[1] = T_k; c.phi()[1] = phi_k;
   }
   double T_km1 = 0.0, Sbu_km1 = 0.0, Sabs_km1 = 0.0, f0 = 0.0;
+  // func_freeboard memo: forward totals and the exact suffix sums for the waterline layer of the previous step
+  double fbA = 0.0, fbG = 0.0, fbAs = 0.0, fbGs = 0.0;
+  const int ks = (c.fb.k_last >= 1 && c.fb.k_last < Na) ? c.fb.k_last : 0;
+  double min_ps = 1e300;
   for (int k = 1; k <= Na; k++) {
     if (k + SAMSIM_PF <= Na) {
       c.T().prefetch(k + SAMSIM_PF); c.S_bu().prefetch(k + SAMSIM_PF); c.phi().prefetch(k + SAMSIM_PF);
@@ -356,6 +360,10 @@ __device__ __noinline__ void fused_thermo_expulsion(const DevCfg& g, Col& c) {
       pg = f_max((pg * thk - vex) / thk, 0.0);
     }
     c.psi_s()[k] = ps; c.psi_l()[k] = pl; c.psi_g()[k] = pg;
+    fbA = fbA + ps * thk;
+    fbG = fbG + pg * thk;
+    if (ks && k > ks) { fbAs = fbAs + ps * thk; fbGs = fbGs + pg * thk; }
+    min_ps = f_min(min_ps, ps);
     const double m_new = m_k + f1 - f0;
     c.m()[k] = m_new;
     // mass_transfer layer k, then S7
@@ -371,6 +379,10 @@ __device__ __noinline__ void fused_thermo_expulsion(const DevCfg& g, Col& c) {
     T_k = T_kp1; sbu_k = Sbu_kp1; phi_k = phi_kp1; m_k = m_kp1;
     f0 = f1;
   }
+  c.fb.tot_valid = true; c.fb.t1 = c.thick()[1]; c.fb.A = fbA; c.fb.G = fbG;
+  c.fb.suf_valid = (ks != 0); c.fb.ks = ks; c.fb.As = fbAs; c.fb.Gs = fbGs;
+  c.fb.res_valid = false;
+  c.min_psi_s = min_ps;
 }
 
 __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing& f, bool want_diag, const SnapOut& snap) {
@@ -444,6 +456,8 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   if (fused) {
     fused_thermo_expulsion(g, c);
   } else {
+    fb_reset(c);
+    c.min_psi_s = 1e300;
     double T_test = SCV(c, SC_T_BOTTOM);
     const bool reuse = false;
 #if SAMSIM_SYNC >= 2
@@ -474,6 +488,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
       double ps, pl, pg, vex;
       expulsion(phi, c.thick()[k], mk, ps, pl, pg, vex);
       c.psi_s()[k] = ps; c.psi_l()[k] = pl; c.psi_g()[k] = pg; c.V_ex()[k] = vex;
+      c.min_psi_s = f_min(c.min_psi_s, ps);
     }
     }
 
@@ -536,6 +551,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     const double pg = c.psi_g()[Na];
     if (pg > 0.0) {
       const double temp2 = pg * c.thick()[Na] * rho_l;
+      c.fb.res_valid = false;
       c.m()[Na] = c.m()[Na] + temp2;
       c.S_abs()[Na] = c.S_abs()[Na] + temp2 * SCV(c, SC_S_BU_BOTTOM);
       c.H_abs()[Na] = c.H_abs()[Na] + temp2 * c_l * SCV(c, SC_T_BOTTOM);
@@ -553,8 +569,8 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   if (c.N_active > 1 && g.flood_flag > 1) {
     SCV(c, SC_FREEBOARD) = freeboard_of(g, c);
     if (SCV(c, SC_FREEBOARD) < 0.0) {
-      if (g.flood_flag == 2) flood(g, c);
-      else if (g.flood_flag == 3 && SCV(c, SC_FREEBOARD) < neg_free) flood_simple(c);
+      if (g.flood_flag == 2) { flood(g, c); fb_reset(c); }
+      else if (g.flood_flag == 3 && SCV(c, SC_FREEBOARD) < neg_free) { flood_simple(c); fb_reset(c); }
     }
   }
 
@@ -613,6 +629,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   // ---- S18 second backward sweep :592-598 (psi_* are NOT refreshed) ----
   {
     double T_test = SCV(c, SC_T_BOTTOM);
+    double min_S2 = 1e300;
 #if SAMSIM_SYNC >= 2
     for (int k = g.Nlayer; k >= 1; k--) {
       SAMSIM_LAYER_SYNC();
@@ -622,14 +639,17 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
 #endif
       if (k - SAMSIM_PF >= 1) { c.m().prefetch(k - SAMSIM_PF); c.S_abs().prefetch(k - SAMSIM_PF); c.H_abs().prefetch(k - SAMSIM_PF); c.phi().prefetch(k - SAMSIM_PF); }
       const double mk = c.m()[k];
-      const double sbu = c.S_abs()[k] / mk;
+      const double Sk = c.S_abs()[k];
+      if (k >= 2) min_S2 = f_min(min_S2, Sk);
+      const double sbu = Sk / mk;
       const double H = c.H_abs()[k] / mk;
       double T, phi = c.phi()[k];
       getT(g, H, sbu, T_test, T, phi, c.status);
       T_test = T;
       c.S_bu()[k] = sbu; c.T()[k] = T; c.phi()[k] = phi;
     }
-      c.thermo_valid = true;  // invalidated below by anything that touches layers >= 2
+    c.min_S_abs_2 = min_S2;
+    c.thermo_valid = true;  // invalidated below by anything that touches layers >= 2
   }
 
   }
@@ -717,6 +737,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     if (c.phi()[Na] > psi_s_min || c.phi()[Na - 1] <= psi_s_min / 2.0 || r1 > 1.5 || r1 < 0.5) {
       layer_dynamics(g, c);
       c.thermo_valid = false;
+      fb_reset(c);
         }
     const int Nb = c.N_active;
     if (Nb < N && c.thick()[(Nb + 1 < N) ? Nb + 1 : N] == 0) {  // :772-783 scrub
@@ -726,15 +747,23 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
       c.psi_s()[Nb + 1] = 0.0;
     }
   } else {
-    if (c.phi()[1] > psi_s_min) { layer_dynamics(g, c); c.thermo_valid = false; }
+    if (c.phi()[1] > psi_s_min) { layer_dynamics(g, c); c.thermo_valid = false; fb_reset(c); }
     }
 
   // ---- S24 timestep + health check :802-819 ----
   c.time = c.time + dt;
   {
     const int Na = c.N_active;
-    double mn = c.psi_s()[1], ms = c.S_abs()[1];
-    for (int k = 2; k <= Na; k++) { mn = f_min(mn, c.psi_s()[k]); ms = f_min(ms, c.S_abs()[k]); }
+    double mn, ms;
+    if (c.thermo_valid) {
+      // nothing touched psi_s(1:N_active) since S4, nor S_abs(2:N_active) since S18, and N_active is unchanged:
+      // the minima gathered by those sweeps are the MINVALs of :808 and :812
+      mn = c.min_psi_s;
+      ms = f_min(c.S_abs()[1], c.min_S_abs_2);
+    } else {
+      mn = c.psi_s()[1]; ms = c.S_abs()[1];
+      for (int k = 2; k <= Na; k++) { mn = f_min(mn, c.psi_s()[k]); ms = f_min(ms, c.S_abs()[k]); }
+    }
     if (mn < 0.0) {
       c.status = 1337;
     } else if (ms < 0.0) {

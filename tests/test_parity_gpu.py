@@ -230,3 +230,82 @@ def test_status_codes_freeze_column(oracle_mod):
 def test_fp64_peak_runs():
     tf = api.fp64_peak(0, 0.3)
     assert 5.0 < tf < 80.0, tf
+
+
+def _lab_series(n):
+    """Config 3 stand-ins for the absent 2017_input/ files: per-second series."""
+    t = np.arange(n, dtype=np.float64)
+    Tice = -5.0 - 10.0 * (1.0 - np.cos(2.0 * np.pi * t / 86400.0))
+    snowfall = np.where((t >= 2.0 * 3600) & (t < 3.0 * 3600), 1e-7, 0.0)   # an early snow event so the window sees it
+    heat = np.full(n, 5.0)
+    styropor = np.where((t >= 4.0 * 3600) & (t < 5.0 * 3600), 1.0, 0.0)
+    return np.stack([Tice, snowfall, heat, styropor])
+
+
+def test_lab_tank_batch_of_five(oracle_mod):
+    """Config 3: testcases 101-105 (Nlayer 200, boundflux 3, tank salinity feedback, lab snow) as ONE batch of five
+    columns with per-column S_bu_bottom / S_total and per-column forcing sets; GPU vs oracle, bitwise."""
+    n = 30000
+    base = _lab_series(n)
+    sets = np.stack([base * np.array([1.0 + 0.03 * q, 1.0 + 0.5 * q, 1.0, 1.0])[:, None] for q in range(5)])
+    cols = []
+    for q in range(5):
+        col = oracle_mod.Column(101 + q, "det")
+        col.set_lab_forcing(*sets[q])
+        cols.append(col)
+    cfg = pu.config_from_oracle(cols[0])
+    eng = api.Engine(cfg, 5)
+    for q, col in enumerate(cols):
+        eng.load_column_state(col.state(), q, set_clock=(q == 0))
+        eng.set_scalar("S_total", [col.scalar("S_total")], col0=q)
+    eng.set_lab_forcing(sets, np.arange(5, dtype=np.int32))
+    done = 0
+    for target in (1, 2, 3601, 3602, 9000, 20000):
+        nstep = target - done
+        eng.step(nstep)
+        for q, col in enumerate(cols):
+            assert col.step(nstep) == 0
+        done = target
+        for q, col in enumerate(cols):
+            bad = pu.compare_column(col, eng, q, label=f"testcase {101 + q} step {target}: ")
+            assert not bad, _fmt(bad)
+    assert max(c.int("N_active") for c in cols) >= 3 and max(c.stat("coupling_iters") for c in cols) > 1000  # thin lab snow: iterative snow_coupling
+
+
+def test_testcase1_perturbed_ensemble(oracle_mod):
+    """Config 4 in small: members differ in the T_top levels, T_bottom, S_bu_bottom and fl_q_bottom."""
+    ncol = 40
+    rng = np.random.default_rng(20170301)
+    d1, d2 = rng.normal(0, 0.5, ncol), rng.normal(0, 0.5, ncol)
+    Sb = 34.0 + rng.normal(0, 0.5, ncol)
+    Tb = np.maximum(-1.0 + rng.normal(0, 0.05, ncol), -1.7)
+    fq = np.abs(rng.normal(0, 2.0, ncol))
+    base = oracle_mod.Column(1, "det")
+    eng = pu.engine_from_oracle(base, ncol=ncol)
+    rho_l, c_l = 1028.0, 3400.0
+    m1 = base.array("m")[0]
+
+    def personalise(col, j):
+        col.set_scalar("ttop_warm", -5.0 + d1[j]); col.set_scalar("ttop_cold", -10.0 + d2[j])
+        col.set_scalar("T_top", -5.0 + d1[j]); col.set_scalar("T_bottom", Tb[j]); col.set_scalar("S_bu_bottom", Sb[j])
+        col.set_scalar("fl_q_bottom", fq[j])
+        S = col.array("S_abs"); S[0] = Sb[j] * m1; col.set_array("S_abs", S)
+        H = col.array("H_abs"); H[0] = m1 * Tb[j] * c_l; col.set_array("H_abs", H)
+        T = col.array("T"); T[:] = Tb[j]; col.set_array("T", T)
+        Sbu = col.array("S_bu"); Sbu[:] = Sb[j]; col.set_array("S_bu", Sbu)
+
+    eng.set_scalar("ttop_warm", -5.0 + d1); eng.set_scalar("ttop_cold", -10.0 + d2); eng.set_scalar("T_top", -5.0 + d1)
+    eng.set_scalar("T_bottom", Tb); eng.set_scalar("S_bu_bottom", Sb); eng.set_scalar("fl_q_bottom", fq)
+    S = np.tile(base.array("S_abs"), (ncol, 1)); S[:, 0] = Sb * m1; eng.set_array("S_abs", S)
+    H = np.tile(base.array("H_abs"), (ncol, 1)); H[:, 0] = m1 * Tb * c_l; eng.set_array("H_abs", H)
+    eng.set_array("T", np.repeat(Tb[:, None], 90, 1)); eng.set_array("S_bu", np.repeat(Sb[:, None], 90, 1))
+    nsteps = 46000   # passes the first T_top switch at t = 12 h
+    eng.step(nsteps)
+    for j in (0, 7, 39):
+        col = oracle_mod.Column(1, "det")
+        personalise(col, j)
+        assert col.step(nsteps) == 0
+        bad = pu.compare_column(col, eng, j, label=f"member {j}: ")
+        assert not bad, _fmt(bad)
+    na = eng.get_int("N_active")
+    assert na.min() >= 2 and len(np.unique(na)) > 1   # members really diverged
