@@ -38,9 +38,10 @@ MODEL_STEPS = 16            # model timesteps per bench step (one launch)
 START_RECORD = 200          # oracle SHEBA state (tests/golden/sheba_oracle_states.npz)
 SITES = ["sheba", "70N00W", "75N00W", "75N180E", "80N00E", "80N90E", "85N180E", "NorthPole", "barrow"]
 # Algorithmic FP64 work of ONE column timestep of this workload, counted on the CPU oracle with the
-# operation-counting build (tools/count_flops.py; see DESIGN.md "Roofline"): +,-,*,/ = 1 flop each,
-# pow/exp/sin calls listed separately.
-F_ALG_FLOP_PER_COLUMN_STEP = 1.0e5
+# operation-counting build (python tools/count_flops.py): the reference algorithm as written
+# executes 50775 add/sub + 49926 mul + 12229 div = 112930 flop (+ 103 pow, 201 exp, 1 sin calls, not counted)
+# per column-timestep from the mid-January SHEBA state (N_active = 100).
+F_ALG_FLOP_PER_COLUMN_STEP = 112930.0
 B_ALG_BYTES_PER_COLUMN_STEP = 2 * 4 * 100 * 8  # read+write of m, S_abs, H_abs, thick once per model step
 
 

@@ -50,13 +50,16 @@ _OUTPUT_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
 
 
 def lib(backend: str = "det") -> C.CDLL:
-    if backend not in ("det", "libm", "det_shebagold", "libm_shebagold"):
+    if backend not in ("det", "libm", "det_shebagold", "libm_shebagold", "count"):
         raise ValueError(backend)
     if backend in _LIBS:
         return _LIBS[backend]
     path = _BUILD / f"liboracle_{backend}.so"
     if not path.exists():
-        build()
+        if backend == "count":  # C++ operation-counting build (oracle/count_real.h), see tools/count_flops.py
+            subprocess.run(["make", "-C", str(_HERE), "count"], check=True, capture_output=True)
+        else:
+            build()
     L = C.CDLL(str(path))
     L.sam_create.restype = C.c_void_p
     L.sam_create.argtypes = [C.c_int]
@@ -86,6 +89,8 @@ def lib(backend: str = "det") -> C.CDLL:
     L.sam_run_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_long, C.c_int]
     L.sam_kat_getT.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp]
     L.sam_kat_scalar.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp]
+    if backend == "count":
+        L.sam_get_op_counts.argtypes = [C.POINTER(C.c_longlong)]
     _LIBS[backend] = L
     return L
 

@@ -30,6 +30,20 @@
 static inline real P3(real x) { return (x * x) * x; }
 static inline real P4(real x) { real x2 = x * x; return x2 * x2; }
 static const char* k_backend = "det";
+#elif defined(SAMSIM_COUNT_OPS)
+#define M_POW(x, y) pow((x), (y))
+#define M_EXP(x) exp(x)
+#define M_SIN(x) sin(x)
+#define P2(x) ((x) * (x))
+static inline real P3(real x) { return (x * x) * x; }
+static inline real P4(real x) { real x2 = x * x; return x2 * x2; }
+static const char* k_backend = "libm-count";
+sam_op_counts g_sam_ops = {0, 0, 0, 0, 0, 0, 0};
+extern "C" void sam_get_op_counts(long long* out) {
+  out[0] = g_sam_ops.add; out[1] = g_sam_ops.mul; out[2] = g_sam_ops.div; out[3] = g_sam_ops.cmp;
+  out[4] = g_sam_ops.pw; out[5] = g_sam_ops.ex; out[6] = g_sam_ops.sn;
+}
+extern "C" void sam_reset_op_counts(void) { g_sam_ops = sam_op_counts{0, 0, 0, 0, 0, 0, 0}; }
 #else
 #define M_POW(x, y) pow((x), (y))
 #define M_EXP(x) exp(x)
@@ -2092,8 +2106,8 @@ void sam_kat_getT(int salt_flag, int n, const double* H, const double* S_bu, con
       continue;
     }
     sam_getT(&c, H[q], S_bu[q], T_in[q], &T, &phi, 0);
-    T_out[q] = T;
-    phi_out[q] = phi;
+    T_out[q] = (double)T;
+    phi_out[q] = (double)phi;
   }
 }
 
@@ -2106,13 +2120,13 @@ void sam_kat_scalar(int fn, int salt_flag, int n, const double* a, const double*
   c.salt_flag = salt_flag;
   for (q = 0; q < n; q++) {
     switch (fn) {
-      case 0: out[q] = sam_func_S_br(&c, a[q]); break;
-      case 1: out[q] = sam_func_S_br2(&c, a[q], b[q]); break;
-      case 2: out[q] = sam_func_ddT_S_br(&c, a[q]); break;
-      case 3: out[q] = sam_func_density(a[q], b[q]); break;
-      case 4: out[q] = sam_func_T_freeze(a[q], salt_flag); break;
-      case 5: out[q] = sam_func_k_snow(a[q], b[q]); break;
-      case 6: out[q] = sam_func_albedo(a[q], b[q], 0.1, 0.005, 2); break;
+      case 0: out[q] = (double)sam_func_S_br(&c, a[q]); break;
+      case 1: out[q] = (double)sam_func_S_br2(&c, a[q], b[q]); break;
+      case 2: out[q] = (double)sam_func_ddT_S_br(&c, a[q]); break;
+      case 3: out[q] = (double)sam_func_density(a[q], b[q]); break;
+      case 4: out[q] = (double)sam_func_T_freeze(a[q], salt_flag); break;
+      case 5: out[q] = (double)sam_func_k_snow(a[q], b[q]); break;
+      case 6: out[q] = (double)sam_func_albedo(a[q], b[q], 0.1, 0.005, 2); break;
       default: out[q] = NAN;
     }
   }
