@@ -1,0 +1,276 @@
+// grotz_host.cpp -- C++ host side above the C ABI (include/samsim_b200_host.h).
+//
+// Mirrors the parts of the reference that stay on the host: init(testcase) (mo_init.f90), sub_input
+// (mo_functions.f90:304-327), output_begin / output_settings / output (mo_output.f90) and the driver skeleton of
+// grotz (mo_grotz.f90:119-176, :840-876).  The time loop itself is samsim_b200_step.  No physics here.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../../include/samsim_b200_host.h"
+
+namespace {
+
+const double rho_l = 1028.0, c_l = 3400.0;  // mo_parameters.f90:51,53
+
+void alloc_case(samsim_host_case_t* c) {
+  const int N = c->cfg.Nlayer;
+  for (int a = 0; a < SAMSIM_ARR_COUNT; a++) {
+    int ext = N;
+    if (a == SAMSIM_ARR_RAY) ext = N - 1;
+    if (a == SAMSIM_ARR_FL_Q) ext = N + 1;
+    c->arrays[a] = (double*)calloc((size_t)ext, sizeof(double));  // sub_allocate zero-fills, mo_init.f90:2082-2088
+  }
+}
+
+void defaults(samsim_config_t* g) {  // mo_init.f90:83-109 and mo_parameters.f90:107-112
+  memset(g, 0, sizeof *g);
+  g->boundflux_flag = 1; g->atmoflux_flag = 1; g->albedo_flag = 2;
+  g->grav_heat_flag = 1; g->flush_heat_flag = 1; g->flood_flag = 2; g->flush_flag = 5; g->grav_flag = 2; g->harmonic_flag = 2;
+  g->prescribe_flag = 1; g->salt_flag = 1;
+  g->turb_flag = 2; g->bottom_flag = 1; g->tank_flag = 1;
+  g->precip_flag = 0; g->freeboard_snow_flag = 0; g->snow_flush_flag = 1; g->snow_precip_flag = 1;
+  g->lab_snow_flag = 0;
+  g->max_flux_plate = 10000.0; g->k_snow_flush = 0.75; g->k_styropor = 0.8;
+}
+
+// Fortran edit descriptors as the reference uses them (mo_output.f90:300-319): F9.3 / F9.5 / ES14.7 then 2x.
+void put_F(FILE* f, double v, int w, int d) {
+  char buf[64];
+  int n = snprintf(buf, sizeof buf, "%*.*f", w, d, v);
+  if (n > w) {  // Fortran prints w asterisks when the value does not fit
+    for (int q = 0; q < w; q++) fputc('*', f);
+  } else {
+    fputs(buf, f);
+  }
+}
+void put_ES(FILE* f, double v) {  // ES14.7
+  char buf[64];
+  snprintf(buf, sizeof buf, "%14.7E", v);
+  fputs(buf, f);
+}
+void row_F(FILE* f, const double* a, int n, int w, int d) {
+  for (int k = 0; k < n; k++) { put_F(f, a[k], w, d); fputs("  ", f); }
+  fputc('\n', f);
+}
+void row_ES(FILE* f, const double* a, int n) {
+  for (int k = 0; k < n; k++) { put_ES(f, a[k]); fputs("  ", f); }
+  fputc('\n', f);
+}
+
+struct OutFiles {
+  FILE *T, *psi_s, *thick, *S_bu, *ray, *psi_l, *freeboard, *snow, *vital, *grav, *T2m, *perm, *flush_v, *flush_h, *psi_g, *melt;
+};
+
+FILE* open_out(const std::string& dir, const char* name) { return fopen((dir + "/" + name).c_str(), "w"); }
+
+}  // namespace
+
+extern "C" {
+
+int samsim_host_init_testcase(int32_t testcase, samsim_host_case_t* c) {
+  if (!c) return SAMSIM_ERR_ARG;
+  memset(c, 0, sizeof *c);
+  samsim_config_t* g = &c->cfg;
+  defaults(g);
+  g->testcase = testcase;
+  double* sc = c->scalars;
+  double T_top = 0.0, T_bottom = 0.0, S_bu_bottom = 0.0, fl_q_bottom = 0.0, time_out = 0.0, T2m = 0.0;
+  const bool lab = (testcase >= 101 && testcase <= 105);
+  if (testcase == 1) {  // mo_init.f90:865-945
+    g->Nlayer = 90; g->N_top = 5; g->N_bottom = 5; g->N_middle = g->Nlayer - g->N_top - g->N_bottom;
+    g->turb_flag = 1; g->boundflux_flag = 1; g->grav_heat_flag = 1; g->flush_flag = 1; g->salt_flag = 2;
+    T_top = -5.0; T_bottom = -1.; S_bu_bottom = 34.; fl_q_bottom = 0.0;
+    g->thick_0 = 0.002; g->dt = 1.0; time_out = 3600.0; c->time_total = time_out * 72.0;
+    alloc_case(c);
+    c->arrays[SAMSIM_ARR_THICK][0] = g->thick_0;
+    c->arrays[SAMSIM_ARR_M][0] = c->arrays[SAMSIM_ARR_THICK][0] * rho_l;
+    c->arrays[SAMSIM_ARR_S_ABS][0] = S_bu_bottom * c->arrays[SAMSIM_ARR_M][0];
+    c->arrays[SAMSIM_ARR_H_ABS][0] = c->arrays[SAMSIM_ARR_M][0] * (T_bottom)*c_l;
+  } else if (testcase == 4) {  // mo_init.f90:1127-1207
+    g->Nlayer = 100; g->N_bottom = 20; g->N_top = 20; g->N_middle = g->Nlayer - g->N_top - g->N_bottom;
+    g->atmoflux_flag = 2; g->precip_flag = 1; g->boundflux_flag = 2; g->snow_flush_flag = 1; g->flush_heat_flag = 2;
+    g->snow_precip_flag = 1;
+    T_bottom = -1.0; S_bu_bottom = 34.0;
+    g->thick_0 = 0.01; time_out = 86400.0; c->time_total = time_out * 365.0 * 4.5; g->dt = 10.0;
+    alloc_case(c);
+    c->arrays[SAMSIM_ARR_THICK][0] = g->thick_0;
+    for (int k = 0; k < g->Nlayer; k++) {
+      c->arrays[SAMSIM_ARR_M][k] = c->arrays[SAMSIM_ARR_THICK][k] * rho_l;
+      c->arrays[SAMSIM_ARR_S_ABS][k] = S_bu_bottom * c->arrays[SAMSIM_ARR_M][k];
+      c->arrays[SAMSIM_ARR_H_ABS][k] = 0.0;
+    }
+  } else if (lab) {  // mo_init.f90:222-767
+    static const double Sb[5] = {25.6664555556, 26.1336777778, 26.0335888889, 27.0363, 31.5625333333};
+    static const double tt[5] = {1625000.0, 1124000.0, 1283000.0, 2439000.0, 1549000.0};
+    static const int64_t len[5] = {1628263, 1124187, 1283092, 2439729, 1549323};
+    const int q = testcase - 101;
+    const double tank_depth = 0.94;
+    g->alpha_flux_instable = 22.0; g->alpha_flux_stable = 21.0;
+    g->Nlayer = 200; g->N_bottom = 10; g->N_top = 5; g->N_middle = g->Nlayer - g->N_top - g->N_bottom;
+    c->length_input_lab = len[q];
+    g->tank_flag = 2; g->boundflux_flag = 3; g->precip_flag = 0; g->grav_heat_flag = 1; g->flush_flag = 5; g->flood_flag = 2;
+    g->grav_flag = 2; g->lab_snow_flag = 1; g->freeboard_snow_flag = 1; g->snow_flush_flag = 1; g->flush_heat_flag = 2;
+    g->snow_precip_flag = 1;
+    T2m = 0.0; T_top = 0.0; T_bottom = -1.3; S_bu_bottom = Sb[q];
+    g->thick_0 = 0.01; time_out = 60.0 * 60.0; c->time_total = tt[q]; g->dt = 1.0;
+    g->m_total = rho_l * tank_depth;
+    sc[SAMSIM_SC_S_TOTAL] = rho_l * S_bu_bottom * tank_depth;
+    alloc_case(c);
+    c->arrays[SAMSIM_ARR_THICK][0] = g->thick_0;
+    for (int k = 0; k < g->Nlayer; k++) {
+      c->arrays[SAMSIM_ARR_M][k] = c->arrays[SAMSIM_ARR_THICK][k] * rho_l;
+      c->arrays[SAMSIM_ARR_S_ABS][k] = S_bu_bottom * c->arrays[SAMSIM_ARR_M][k];
+      c->arrays[SAMSIM_ARR_H_ABS][k] = c->arrays[SAMSIM_ARR_M][k] * T_bottom;  // sic: no c_l (mo_init.f90:299)
+    }
+  } else {
+    return SAMSIM_ERR_CONFIG;
+  }
+  // common tail, mo_init.f90:1982-2009
+  for (int k = 0; k < g->Nlayer; k++) {
+    c->arrays[SAMSIM_ARR_T][k] = T_bottom;
+    c->arrays[SAMSIM_ARR_S_BU][k] = S_bu_bottom;
+    c->arrays[SAMSIM_ARR_PSI_L][k] = 1.0;
+  }
+  g->thick_min = g->thick_0 / 2.0;
+  g->time_out = time_out;
+  c->i_time = (int32_t)(c->time_total / g->dt);
+  g->i_time_out = (int32_t)(time_out / g->dt);
+  c->N_active = 1;
+  sc[SAMSIM_SC_T_BOTTOM] = T_bottom; sc[SAMSIM_SC_T_TOP] = T_top; sc[SAMSIM_SC_S_BU_BOTTOM] = S_bu_bottom;
+  sc[SAMSIM_SC_T2M] = T2m; sc[SAMSIM_SC_FL_Q_BOTTOM] = fl_q_bottom;
+  sc[SAMSIM_SC_BULK_SALIN] = c->arrays[SAMSIM_ARR_S_ABS][0] / c->arrays[SAMSIM_ARR_M][0];
+  sc[SAMSIM_SC_TTOP_WARM] = -5.0; sc[SAMSIM_SC_TTOP_COLD] = -10.0; sc[SAMSIM_SC_OFLUX_AMP] = 7.0;
+  return SAMSIM_OK;
+}
+
+void samsim_host_case_free(samsim_host_case_t* c) {
+  if (!c) return;
+  for (int a = 0; a < SAMSIM_ARR_COUNT; a++) { free(c->arrays[a]); c->arrays[a] = nullptr; }
+}
+
+int samsim_host_read_forcing(const char* dir, int32_t nrec, double* series) {
+  static const char* names[4] = {"flux_sw.txt.input", "flux_lw.txt.input", "T2m.txt.input", "precip.txt.input"};
+  if (!series || nrec < 1) return SAMSIM_ERR_ARG;
+  const std::string d = dir ? dir : ".";
+  for (int kind = 0; kind < 4; kind++) {
+    FILE* f = fopen((d + "/" + names[kind]).c_str(), "r");
+    if (!f) return SAMSIM_ERR_STATE;
+    for (int r = 0; r < nrec; r++) {
+      if (fscanf(f, "%lf", &series[(size_t)kind * nrec + r]) != 1) { fclose(f); return SAMSIM_ERR_STATE; }
+    }
+    fclose(f);
+  }
+  return SAMSIM_OK;
+}
+
+int samsim_grotz(int32_t testcase, const char* description, const samsim_grotz_options_t* opt) {
+  if (!opt || opt->ncol < 1 || !opt->output_dir) return SAMSIM_ERR_ARG;
+  samsim_host_case_t cs;
+  int rc = samsim_host_init_testcase(testcase, &cs);
+  if (rc) return rc;
+  const samsim_config_t& g = cs.cfg;
+  const int N = g.Nlayer;
+  const std::string out = opt->output_dir;
+
+  // ---- output_begin / output_settings (mo_output.f90:276-339, :41-106) ----
+  OutFiles F;
+  F.T = open_out(out, "dat_T.dat"); F.psi_s = open_out(out, "dat_psi_s.dat"); F.thick = open_out(out, "dat_thick.dat");
+  F.S_bu = open_out(out, "dat_S_bu.dat"); F.ray = open_out(out, "dat_ray.dat"); F.psi_l = open_out(out, "dat_psi_l.dat");
+  F.freeboard = open_out(out, "dat_freeboard.dat"); F.snow = open_out(out, "dat_snow.dat");
+  F.vital = open_out(out, "dat_vital_signs.dat"); F.grav = open_out(out, "dat_grav_drain.dat");
+  F.T2m = open_out(out, "dat_T2m_T_top.dat"); F.perm = open_out(out, "dat_perm.dat"); F.flush_v = open_out(out, "dat_flush_v.dat");
+  F.flush_h = open_out(out, "dat_flush_h.dat"); F.psi_g = open_out(out, "dat_psi_g.dat"); F.melt = open_out(out, "dat_melt.dat");
+  if (!F.T || !F.melt) { samsim_host_case_free(&cs); return SAMSIM_ERR_STATE; }
+  {
+    FILE* s = open_out(out, "dat_settings.dat");
+    if (s) {
+      fprintf(s, " ################  Description  ###############\n %s\n #################  Testcase  #################\ntestcase         %8d\n", description ? description : "", testcase);
+      fprintf(s, " ##############  Basic settings  ##############\ndt               %14.3f\nthick_0          %14.3f\ntime_out         %14.3f\ntime_total       %14.3f\n", g.dt, g.thick_0, g.time_out, cs.time_total);
+      fprintf(s, "fl_q_bottom      %14.3f\nT_bottom         %14.3f\nS_bu_bottom      %14.3f\nN_top            %8d\nN_middle         %8d\nN_bottom         %8d\nNlayer           %8d\n",
+              cs.scalars[SAMSIM_SC_FL_Q_BOTTOM], cs.scalars[SAMSIM_SC_T_BOTTOM], cs.scalars[SAMSIM_SC_S_BU_BOTTOM], g.N_top, g.N_middle, g.N_bottom, g.Nlayer);
+      fprintf(s, " ##################  Flags  ###################\nboundflux_flag   %8d\natmoflux_flag    %8d\nalbedo_flag      %8d\ngrav_flag        %8d\nflush_flag       %8d\nflood_flag       %8d\ngrav_heat_flag   %8d\nflush_heat_flag  %8d\nharmonic_flag    %8d\nk_snow_flush     %14.3f\nprescribe_flag   %8d\nsalt_flag        %8d\nturb_flag        %8d\nbottom_flag      %8d\ntank_flag        %8d\nprecip_flag      %8d\n",
+              g.boundflux_flag, g.atmoflux_flag, g.albedo_flag, g.grav_flag, g.flush_flag, g.flood_flag, g.grav_heat_flag, g.flush_heat_flag, g.harmonic_flag, g.k_snow_flush, g.prescribe_flag, g.salt_flag, g.turb_flag, g.bottom_flag, g.tank_flag, g.precip_flag);
+      fprintf(s, " engine           %s\n ncol             %d\n", samsim_b200_version(), opt->ncol);
+      fclose(s);
+    }
+  }
+
+  // ---- device ----
+  samsim_handle_t h = nullptr;
+  rc = samsim_b200_create(&g, opt->ncol, opt->device, &h);
+  if (rc) { samsim_host_case_free(&cs); return rc; }
+  for (int a = 0; a < SAMSIM_ARR_COUNT && !rc; a++) rc = samsim_b200_set_array(h, a, cs.arrays[a], 0, 1);
+  for (int q = 0; q < SAMSIM_SC_COUNT && !rc; q++) rc = samsim_b200_set_scalar(h, q, &cs.scalars[q], 0, 1);
+  if (!rc) rc = samsim_b200_set_int(h, SAMSIM_INT_N_ACTIVE, &cs.N_active, 0, 1);
+  if (!rc) rc = samsim_b200_set_clock(h, 0.0, 0, 0, 1);
+  if (!rc && opt->ncol > 1) rc = samsim_b200_broadcast_column(h, 0, 0, opt->ncol);
+  if (!rc && opt->ttop_warm) rc = samsim_b200_set_scalar(h, SAMSIM_SC_TTOP_WARM, opt->ttop_warm, 0, opt->ncol);
+  if (!rc && opt->ttop_warm) rc = samsim_b200_set_scalar(h, SAMSIM_SC_T_TOP, opt->ttop_warm, 0, opt->ncol);  // T_top starts at the warm level (mo_init.f90:894)
+  if (!rc && opt->ttop_cold) rc = samsim_b200_set_scalar(h, SAMSIM_SC_TTOP_COLD, opt->ttop_cold, 0, opt->ncol);
+  if (!rc && opt->oflux_amp) rc = samsim_b200_set_scalar(h, SAMSIM_SC_OFLUX_AMP, opt->oflux_amp, 0, opt->ncol);
+  if (!rc && g.atmoflux_flag == 2) {  // mo_grotz.f90:131-135
+    const int nrec = 13148;
+    std::vector<double> series((size_t)4 * nrec);
+    rc = samsim_host_read_forcing(opt->forcing_dir, nrec, series.data());
+    if (!rc) rc = samsim_b200_set_forcing(h, 1, nrec, series.data(), nullptr, opt->forcing_scale, opt->forcing_offset);
+  }
+  if (!rc) rc = samsim_b200_set_snapshot_mode(h, SAMSIM_SNAP_FULL);
+
+  // ---- the time loop in chunks that end on output steps (mo_grotz.f90:182, :340) ----
+  const int64_t total = (opt->max_steps > 0 && opt->max_steps < cs.i_time) ? opt->max_steps : cs.i_time;
+  int64_t done = 0;
+  std::vector<double> ssc(SAMSIM_SNAPSC_COUNT), sar((size_t)SAMSIM_SNAPARR_COUNT * N);
+  int32_t status = 0;
+  while (!rc && done < total) {
+    int64_t n = samsim_b200_steps_to_next_output(h);
+    const bool wrote = (done + n <= total);
+    if (n > total - done) n = total - done;
+    rc = samsim_b200_step(h, n);
+    if (rc) break;
+    done += n;
+    rc = samsim_b200_get_status(h, &status, 0, 1);
+    if (rc || status) break;
+    if (wrote) {  // S8: CALL output(...) (mo_output.f90:116-146) with the values the device captured there
+      rc = samsim_b200_get_snapshot(h, ssc.data(), sar.data(), 0, 1);
+      if (rc) break;
+      const double* A = sar.data();
+      row_F(F.T, A + (size_t)SAMSIM_SNAPARR_T * N, N, 9, 3);
+      row_F(F.psi_s, A + (size_t)SAMSIM_SNAPARR_PSI_S * N, N, 9, 3);
+      row_F(F.thick, A + (size_t)SAMSIM_SNAPARR_THICK * N, N, 9, 5);
+      row_F(F.S_bu, A + (size_t)SAMSIM_SNAPARR_S_BU * N, N, 9, 3);
+      row_F(F.ray, A + (size_t)SAMSIM_SNAPARR_RAY * N, N - 1, 9, 3);
+      row_F(F.psi_l, A + (size_t)SAMSIM_SNAPARR_PSI_L * N, N, 9, 3);
+      put_F(F.freeboard, ssc[SAMSIM_SNAPSC_FREEBOARD], 9, 3); fputc('\n', F.freeboard);
+      put_F(F.snow, ssc[SAMSIM_SNAPSC_THICK_SNOW], 9, 3); fputs("  ", F.snow); put_F(F.snow, ssc[SAMSIM_SNAPSC_T_SNOW], 9, 3); fputs("  ", F.snow);
+      put_F(F.snow, ssc[SAMSIM_SNAPSC_PSI_L_SNOW], 9, 3); fputs("  ", F.snow); put_F(F.snow, ssc[SAMSIM_SNAPSC_PSI_S_SNOW], 9, 3); fputc('\n', F.snow);
+      put_F(F.vital, ssc[SAMSIM_SNAPSC_ENERGY_STORED], 15, 1);
+      for (int q : {SAMSIM_SNAPSC_FRESHWATER, SAMSIM_SNAPSC_TOTAL_RESIST, SAMSIM_SNAPSC_THICKNESS, SAMSIM_SNAPSC_BULK_SALIN}) { fputs("  ", F.vital); put_F(F.vital, ssc[q], 10, 5); }
+      fputc('\n', F.vital);
+      put_F(F.grav, ssc[SAMSIM_SNAPSC_GRAV_DRAIN], 9, 6); fputs("  ", F.grav); put_F(F.grav, ssc[SAMSIM_SNAPSC_GRAV_SALT], 9, 5); fputs("  ", F.grav);
+      put_F(F.grav, ssc[SAMSIM_SNAPSC_GRAV_TEMP], 7, 3); fputc('\n', F.grav);
+      fprintf(F.T2m, "  %24.16E  %24.16E\n", ssc[SAMSIM_SNAPSC_T2M], ssc[SAMSIM_SNAPSC_T_TOP]);  // WRITE(45,*): list-directed, 17 digits
+      row_ES(F.perm, A + (size_t)SAMSIM_SNAPARR_PERM * N, N);
+      row_ES(F.flush_v, A + (size_t)SAMSIM_SNAPARR_FLUSH_V * N, N);
+      row_ES(F.flush_h, A + (size_t)SAMSIM_SNAPARR_FLUSH_H * N, N);
+      row_F(F.psi_g, A + (size_t)SAMSIM_SNAPARR_PSI_G * N, N, 9, 3);
+      put_ES(F.melt, ssc[SAMSIM_SNAPSC_MELT_THICK_OUTPUT1]); fputs("  ", F.melt); put_ES(F.melt, ssc[SAMSIM_SNAPSC_MELT_THICK_OUTPUT2]); fputs("  ", F.melt);
+      put_ES(F.melt, ssc[SAMSIM_SNAPSC_MELT_THICK_OUTPUT3]); fputc('\n', F.melt);
+      if (!opt->quiet)
+        printf("progress: %3d%%,  thickness: %6.3f m,  surface T: %7.3f C,  T2m: %7.3f\n", (int)(100.0 * ssc[SAMSIM_SNAPSC_TIME] / cs.time_total),
+               ssc[SAMSIM_SNAPSC_THICKNESS], ssc[SAMSIM_SNAPSC_T_TOP], ssc[SAMSIM_SNAPSC_T2M]);
+    }
+  }
+  for (FILE* f : {F.T, F.psi_s, F.thick, F.S_bu, F.ray, F.psi_l, F.freeboard, F.snow, F.vital, F.grav, F.T2m, F.perm, F.flush_v, F.flush_h, F.psi_g, F.melt})
+    if (f) fclose(f);
+  if (h) samsim_b200_destroy(h);
+  samsim_host_case_free(&cs);
+  if (rc) return rc;
+  return status;  // 0 or the reference STOP code of column 0
+}
+
+}  // extern "C"

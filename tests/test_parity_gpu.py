@@ -309,3 +309,54 @@ def test_testcase1_perturbed_ensemble(oracle_mod):
         assert not bad, _fmt(bad)
     na = eng.get_int("N_active")
     assert na.min() >= 2 and len(np.unique(na)) > 1   # members really diverged
+
+
+def _read_dat(path):
+    return np.loadtxt(path, ndmin=2)
+
+
+def test_grotz_testcase1_output_files_match_reference_output(tmp_path, golden_dir):
+    """Drop-in check end to end: the C++ host `grotz(1, ...)` runs the whole testcase on the GPU and writes
+    dat_*.dat; those FILES are compared with reference_output/Reference_testcase1_with_Version_2 at the print
+    precision of the Fortran formats (F9.3 / F9.5), N_active exact in all 72 records."""
+    from samsim_b200 import grotz
+    rc = grotz.grotz(1, "parity run", output_dir=tmp_path)
+    assert rc == 0
+    gold = np.load(golden_dir / "tc1_reference.npz")
+    thick = _read_dat(tmp_path / "dat_thick.dat")
+    assert thick.shape == (72, 90)
+    assert np.array_equal((thick != 0).sum(1), gold["N_active"])
+    for name, tol in (("T", 1.0e-3), ("psi_s", 1.0e-3), ("psi_l", 1.0e-3), ("psi_g", 1.0e-3), ("S_bu", 1.0e-3), ("ray", 1.0e-3), ("thick", 1.0e-5)):
+        mine = _read_dat(tmp_path / f"dat_{name}.dat")
+        g = gold[name]
+        assert mine.shape == g.shape, name
+        d = np.abs(mine - g)
+        # both sides are rounded to the last printed digit: they may differ by one unit of it on a rounding boundary
+        assert d.max() <= tol + 1e-12, (name, d.max())
+        assert (d > 1e-12).mean() < 0.02, (name, (d > 1e-12).mean())
+    vs = _read_dat(tmp_path / "dat_vital_signs.dat")
+    assert np.abs(vs[:, 3] - gold["vital_signs"][:, 3]).max() <= 1.0e-5 + 1e-12       # thickness
+    assert np.abs(_read_dat(tmp_path / "dat_freeboard.dat")[:, 0] - gold["freeboard"]).max() <= 1.0e-3 + 1e-12
+
+
+def test_grotz_sheba_first_records(tmp_path, golden_dir):
+    """grotz(4, ...) with the forcing read from *.txt.input files like sub_input: records 1-13 against the golden
+    SHEBA files (T2m in all digits, T_top to 1e-9, N_active exact)."""
+    from samsim_b200 import grotz
+    F = np.load(golden_dir / "forcing_era.npz")["sheba"]
+    fdir = tmp_path / "forcing"
+    fdir.mkdir()
+    for name, row in zip(["flux_sw", "flux_lw", "T2m", "precip"], F):
+        with open(fdir / f"{name}.txt.input", "w") as f:
+            for v in row:
+                f.write(f"  {v: .7e}\n")
+    out = tmp_path / "output"
+    rc = grotz.grotz(4, "sheba", output_dir=out, forcing_dir=fdir, max_steps=12 * 8641 + 1)
+    assert rc == 0
+    gold = np.load(golden_dir / "sheba_reference.npz")
+    tt = _read_dat(out / "dat_T2m_T_top.dat")
+    assert tt.shape == (13, 2)
+    assert np.array_equal(tt[:, 0], gold["T2m_T_top"][:13, 0])
+    assert np.abs(tt[:, 1] - gold["T2m_T_top"][:13, 1]).max() <= 1e-9
+    thick = _read_dat(out / "dat_thick.dat")
+    assert np.array_equal((thick != 0).sum(1), gold["N_active"][:13])
