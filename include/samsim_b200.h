@@ -161,6 +161,10 @@ int samsim_b200_get_clock(samsim_handle_t h, double* time, int64_t* i, int32_t* 
  * matches bit for bit. */
 int samsim_b200_set_forcing(samsim_handle_t h, int32_t nsite, int32_t nrec, const double* series,
                             const int32_t* site_of_col, const double* scale, const double* offset);
+/* Refresh the base series of an existing forcing table in place (same nsite/nrec; per-column vectors are kept):
+ * the streaming path when new reanalysis records arrive while the run is in progress.  Asynchronous on the handle's
+ * stream when `series` is pinned host memory. */
+int samsim_b200_update_forcing(samsim_handle_t h, const double* series);
 /* lab series (mo_grotz.f90:138-169): nset record sets of nrec per-dt values, kinds
  * 0 Tice->T2m, 1 snowfall->solid_precip, 2 heat->fl_q_bottom, 3 styropor; series[(set*4+kind)*nrec + r];
  * set_of_col NULL = set 0.  snow_precip_flag 0 zeroes the snowfall like the reference. */

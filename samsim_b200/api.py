@@ -145,6 +145,7 @@ def load_library() -> C.CDLL:
         "samsim_b200_set_clock": (C.c_int, [H, C.c_double, C.c_int64, C.c_int32, C.c_int32]),
         "samsim_b200_get_clock": (C.c_int, [H, dp, C.POINTER(C.c_int64), ip, ip]),
         "samsim_b200_set_forcing": (C.c_int, [H, C.c_int32, C.c_int32, dp, ip, dp, dp]),
+        "samsim_b200_update_forcing": (C.c_int, [H, dp]),
         "samsim_b200_set_lab_forcing": (C.c_int, [H, C.c_int32, C.c_int64, dp, ip]),
         "samsim_b200_step": (C.c_int, [H, C.c_int64]),
         "samsim_b200_synchronize": (C.c_int, [H]),
@@ -174,7 +175,8 @@ EXPORTED_SYMBOLS = [
     "samsim_b200_create", "samsim_b200_destroy", "samsim_b200_last_error", "samsim_b200_version",
     "samsim_b200_array_extent", "samsim_b200_set_array", "samsim_b200_get_array", "samsim_b200_set_scalar",
     "samsim_b200_get_scalar", "samsim_b200_set_int", "samsim_b200_get_int", "samsim_b200_broadcast_column",
-    "samsim_b200_set_clock", "samsim_b200_get_clock", "samsim_b200_set_forcing", "samsim_b200_set_lab_forcing",
+    "samsim_b200_set_clock", "samsim_b200_get_clock", "samsim_b200_set_forcing", "samsim_b200_update_forcing",
+    "samsim_b200_set_lab_forcing",
     "samsim_b200_step", "samsim_b200_synchronize", "samsim_b200_steps_to_next_output",
     "samsim_b200_set_snapshot_mode", "samsim_b200_get_snapshot", "samsim_b200_get_status",
     "samsim_b200_count_failed", "samsim_b200_reduce_diag", "samsim_b200_launch_count", "samsim_b200_last_step_ms",
@@ -244,9 +246,10 @@ class Engine:
         v = np.ascontiguousarray(np.atleast_1d(values), dtype=np.float64)
         _check(self.L, self.L.samsim_b200_set_scalar(self.h, SCALAR_IDS[name], _dp(v), col0, v.shape[0]))
 
-    def get_scalar(self, name: str, col0: int = 0, n: int | None = None) -> np.ndarray:
+    def get_scalar(self, name: str, col0: int = 0, n: int | None = None, out: np.ndarray | None = None) -> np.ndarray:
         n = self.ncol - col0 if n is None else n
-        out = np.empty(n, dtype=np.float64)
+        out = np.empty(n, dtype=np.float64) if out is None else out
+        assert out.shape == (n,) and out.dtype == np.float64 and out.flags.c_contiguous
         _check(self.L, self.L.samsim_b200_get_scalar(self.h, SCALAR_IDS[name], _dp(out), col0, n))
         return out
 
@@ -306,6 +309,12 @@ class Engine:
         of = None if offset is None else np.ascontiguousarray(offset, dtype=np.float64).reshape(4, self.ncol)
         _check(self.L, self.L.samsim_b200_set_forcing(self.h, nsite, nrec, _dp(s), _ip(soc), _dp(sc), _dp(of)))
 
+    def update_forcing(self, series):
+        """Refresh the base series in place (same shape as the last set_forcing); `series` may be a pinned buffer."""
+        s = series if isinstance(series, np.ndarray) and series.flags.c_contiguous and series.dtype == np.float64 \
+            else np.ascontiguousarray(series, dtype=np.float64)
+        _check(self.L, self.L.samsim_b200_update_forcing(self.h, _dp(s)))
+
     def set_lab_forcing(self, series, set_of_col=None):
         """series[nset, 4, nrec] in kind order Tice, snowfall, heat, styropor."""
         s = np.ascontiguousarray(series, dtype=np.float64)
@@ -331,9 +340,12 @@ class Engine:
     def set_snapshot_mode(self, mode: int):
         _check(self.L, self.L.samsim_b200_set_snapshot_mode(self.h, mode))
 
-    def get_snapshot(self, col0: int = 0, n: int | None = None, arrays: bool = True):
+    def get_snapshot(self, col0: int = 0, n: int | None = None, arrays: bool = True, out_scalars: np.ndarray | None = None):
+        """S8 record of columns [col0, col0+n).  `out_scalars` (n x 20, C-contiguous float64, e.g. a pinned buffer)
+        receives the scalars without an allocation."""
         n = self.ncol - col0 if n is None else n
-        sc = np.empty((n, len(SNAP_SCALARS)), dtype=np.float64)
+        sc = out_scalars if out_scalars is not None else np.empty((n, len(SNAP_SCALARS)), dtype=np.float64)
+        assert sc.shape == (n, len(SNAP_SCALARS)) and sc.flags.c_contiguous and sc.dtype == np.float64
         ar = np.empty((n, len(SNAP_ARRAYS), self.cfg.Nlayer), dtype=np.float64) if arrays else None
         _check(self.L, self.L.samsim_b200_get_snapshot(self.h, _dp(sc), _dp(ar), col0, n))
         out = {name: sc[:, j] for j, name in enumerate(SNAP_SCALARS)}

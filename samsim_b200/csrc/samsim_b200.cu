@@ -527,6 +527,14 @@ int samsim_b200_set_forcing(samsim_handle_t h, int32_t nsite, int32_t nrec, cons
   return 0;
 }
 
+int samsim_b200_update_forcing(samsim_handle_t h, const double* series) {
+  if (!h || !series) return fail(SAMSIM_ERR_ARG, "update_forcing: bad argument");
+  if (!h->series) return fail(SAMSIM_ERR_STATE, "update_forcing: call samsim_b200_set_forcing first");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->series, series, (size_t)h->nsite * 4 * h->nrec * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
 int samsim_b200_set_lab_forcing(samsim_handle_t h, int32_t nset, int64_t nrec, const double* series, const int32_t* set_of_col) {
   if (!h || !series || nset < 1 || nrec < 1) return fail(SAMSIM_ERR_ARG, "set_lab_forcing: bad argument");
   CU(cudaSetDevice(h->device));
