@@ -462,13 +462,18 @@ __device__ __forceinline__ void mass_transfer_layer(const DevCfg& g, double f1, 
 // S_abs into TT/SS_bu/SS_abs first; T and S_bu are not modified by the routine and SS_abs(k+1)
 // is read before layer k+1 is updated, so reading the live arrays is equivalent.  S_abs(k-1)
 // in the last branch IS the updated value in the reference too (:91).
-__device__ __noinline__ void mass_transfer(const DevCfg& g, Col& c, const Lay& fl_m, const Lay& S_bu_view) {
+// `kstart`: the caller guarantees fl_m(1:kstart) == 0, so layers 1..kstart-1 are left untouched (both of their
+// faces carry no flux) and the pass starts at kstart; with kstart > 1 the carried neighbour values are loaded.
+__device__ __noinline__ void mass_transfer(const DevCfg& g, Col& c, const Lay& fl_m, const Lay& S_bu_view, int kstart = 1) {
   const int Na = c.N_active;
   const double T_bottom = SCV(c, SC_T_BOTTOM), S_bu_bottom = SCV(c, SC_S_BU_BOTTOM);
+  if (kstart < 1) kstart = 1;
+  if (kstart > Na) return;
   double T_km1 = 0.0, Sbu_km1 = 0.0, Sabs_km1 = 0.0;  // k = 1: fl_m(1) == 0 at every call site, never read
-  double T_k = c.T()[1], Sbu_k = S_bu_view[1];
-  double f0 = fl_m[1];
-  for (int k = 1; k <= Na; k++) {
+  if (kstart > 1) { T_km1 = c.T()[kstart - 1]; Sbu_km1 = S_bu_view[kstart - 1]; Sabs_km1 = c.S_abs()[kstart - 1]; }
+  double T_k = c.T()[kstart], Sbu_k = S_bu_view[kstart];
+  double f0 = fl_m[kstart];
+  for (int k = kstart; k <= Na; k++) {
     if (k + SAMSIM_PF <= Na) {
       c.T().prefetch(k + SAMSIM_PF); S_bu_view.prefetch(k + SAMSIM_PF); c.S_abs().prefetch(k + SAMSIM_PF);
       c.H_abs().prefetch(k + SAMSIM_PF); fl_m.prefetch(k + SAMSIM_PF);
@@ -798,21 +803,24 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c) {
   // :141 / :173 grav_salt = grav_salt + SUM(S_abs) before the drain loop and - SUM(S_abs) after it: both are
   // forward sums over the layers the loop visits in the same order, so they are accumulated inside it.
   double sum_before = 0.0, sum_after = 0.0;
+  double min_S = 1e300;  // minimum over the S_abs values this routine leaves behind (:198)
+  int kfirst = 0;        // first draining layer: fl_m(1:kfirst) == 0
 
   double run = 0.0;  // running sum = fl_up(kk) for every kk not yet clamped
-  fl_m[1] = 0.0;
   double sbk = c.S_br()[1];
   for (int k = 1; k <= Na - 1; k++) {  // :144-171
     if (k + SAMSIM_PF <= Na) {
       c.ray().prefetch(k + SAMSIM_PF); c.psi_s().prefetch(k + SAMSIM_PF); c.S_abs().prefetch(k + SAMSIM_PF);
       c.m().prefetch(k + SAMSIM_PF); c.S_br().prefetch(k + SAMSIM_PF);
     }
-    const double rk = c.ray()[k], psk = c.psi_s()[k], Sk = c.S_abs()[k], mk = c.m()[k];
+    const double rk = c.ray()[k], Sk = c.S_abs()[k];
     const double sbk1 = c.S_br()[k + 1];
     double up = run;
     double S_after = Sk;
     sum_before = sum_before + Sk;
-    if (rk > ray_crit && psk > 0.001 && Sk / mk > 0.1 && sbk > sbk1) {
+    // same && chain as :145, evaluated left to right: psi_s and m are only touched where ray exceeds ray_crit
+    if (rk > ray_crit && c.psi_s()[k] > 0.001 && Sk / c.m()[k] > 0.1 && sbk > sbk1) {
+      if (kfirst == 0) { kfirst = k; fl_m[k] = 0.0; }  // fl_m(kfirst) = fl_up(kfirst-1) = 0: first face read by mass_transfer
       const double plk = c.psi_l()[k], thk = c.thick()[k], Tk = c.T()[k];
       double flux = x_grav * (rk - ray_crit) * dt * thk;
       flux = f_min(flux, plk * rho_l * thk);
@@ -826,11 +834,12 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c) {
       run = run + flux;
       up = f_min(run, plk * rho_l * thk);
     }
-    fl_m[k + 1] = up;  // fl_m(2:N_active+1) = fl_up(1:N_active), :177
+    if (kfirst) fl_m[k + 1] = up;            // fl_m(2:N_active+1) = fl_up(1:N_active), :177 (zeros above kfirst are not stored)
+    else min_S = f_min(min_S, Sk);           // layers above the first draining layer keep this value
     sum_after = sum_after + S_after;
     sbk = sbk1;
   }
-  fl_m[Na + 1] = run;
+  if (kfirst) fl_m[Na + 1] = run;
   const double fl_up_Na = run;
   {
     const double S_Na = c.S_abs()[Na];  // layer N_active never drains; inactive layers hold 0
@@ -840,13 +849,17 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c) {
   SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) + sum_before;  // :141
   SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) - sum_after;   // :173
 
-  mass_transfer(g, c, fl_m, c.S_bu());  // :188
+  // :188 -- nothing moves above the first draining layer (fl_m(1:kfirst) == 0); without any drainage nothing moves
+  if (kfirst) mass_transfer(g, c, fl_m, c.S_bu(), kfirst);
 
-  SCV(c, SC_GRAV_DRAIN) = SCV(c, SC_GRAV_DRAIN) + fl_m[Na + 1];  // :190
+  SCV(c, SC_GRAV_DRAIN) = SCV(c, SC_GRAV_DRAIN) + run;  // :190 fl_m(N_active+1)
   if (g.grav_heat_flag == 2) c.H_abs()[Na] = c.H_abs()[Na] + heat_loss - fl_up_Na * c_l * SCV(c, SC_T_BOTTOM);  // :193-195
-  double mn = c.S_abs()[1];
-  for (int k = 2; k <= Na; k++) mn = f_min(mn, c.S_abs()[k]);
-  if (f_min(mn, 0.0) < 0.0) c.status = 1337;  // :198 MINVAL over all layers (inactive are 0)
+  // :198 MINVAL(S_abs) < 0: layers above kfirst kept the values scanned by the drain loop (min_S); the others
+  // were rewritten by mass_transfer and are scanned here
+  double mn = min_S;
+  if (kfirst) for (int k = kfirst; k <= Na; k++) mn = f_min(mn, c.S_abs()[k]);
+  else mn = f_min(mn, c.S_abs()[Na]);
+  if (f_min(mn, 0.0) < 0.0) c.status = 1337;  // (inactive layers are 0)
 }
 
 // fl_grav_drain_simple, mo_grav_drain.f90:218-279 (grav_flag 3)

@@ -205,13 +205,14 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
     for (int k = 1; k <= Na; k++) {
       if (k + 1 + SAMSIM_PF <= Na) {
         const int kp = k + 1 + SAMSIM_PF;
-        c.psi_s().prefetch(kp); c.psi_l().prefetch(kp); c.psi_g().prefetch(kp); c.thick().prefetch(kp); c.T().prefetch(kp);
+        c.psi_s().prefetch(kp); c.psi_l().prefetch(kp); c.thick().prefetch(kp); c.T().prefetch(kp);
         c.H_abs().prefetch(kp);
       }
       double fq_kp1;
       double ps_n = 0.0, pl_n = 0.0, pg_n = 0.0, th_n = 0.0, T_n = 0.0;
       if (k < Na) {
-        ps_n = c.psi_s()[k + 1]; pl_n = c.psi_l()[k + 1]; pg_n = c.psi_g()[k + 1]; th_n = c.thick()[k + 1]; T_n = c.T()[k + 1];
+        // psi_g enters k = psi_s*k_s + psi_l*k_l + psi_g*0._wp only as +-0 (psi_g is a finite volume fraction, k > 0)
+        ps_n = c.psi_s()[k + 1]; pl_n = c.psi_l()[k + 1]; pg_n = 0.0; th_n = c.thick()[k + 1]; T_n = c.T()[k + 1];
         fq_kp1 = fl_Q_between(ps_k, pl_k, pg_k, th_k, T_k, ps_n, pl_n, pg_n, th_n, T_n);  // :272-274
         if (c.want_state) c.fl_Q()[k + 1] = fq_kp1;  // fl_Q(2:N_active) is never read back by the loop body; N_active moves by
                                                      // at most 1 per step, so a stale interior entry is always overwritten by a later :262
