@@ -146,3 +146,25 @@ def test_sheba_head_source_differs_only_after_spring(oracle_mod, golden_dir):
     assert max(d[:25]) < 1e-8
     rel = abs(col.records[31]["melt_thick_output2"] - melt[330, 1]) / melt[330, 1]
     assert 1e-4 < rel < 2e-3   # 7.3e-4 with the HEAD source, 2.5e-7 with the shebagold build
+
+
+def test_bare_ice_melt_onset_amplifies_one_ulp(oracle_mod, golden_dir):
+    """Why the SHEBA golden run cannot be followed bit-level past record 347: from the SAME restart state the
+    libm and det back-ends (pow/exp/sin equal to < 1 ulp) stay together to 1e-13 K for days, but the hours in
+    which the last snow vanishes and bare-ice melt starts amplify that last-bit difference by ~1e9
+    (melt_thick = MIN(psi_l*thick, ...) with psi_l(1) ~ 7e-4 obtained by cancellation, mo_functions.f90:398).
+    The golden file differs from either back-end by the same 5e-5 ... 9e-5 there."""
+    z = np.load(golden_dir / "sheba_oracle_states.npz")
+    recs = {}
+    for be in ("libm", "det"):
+        col = _sheba(oracle_mod, golden_dir, be)
+        col.load_state(_state(z, 345))
+        col.record_outputs()
+        assert col.step(4 * 8641 + 1) == 0
+        recs[be] = col.records
+    dT = [np.abs(np.asarray(a["T"]) - np.asarray(b["T"])).max() for a, b in zip(recs["libm"], recs["det"])]
+    assert max(dT[:3]) < 1e-12                       # three days of identical trajectories
+    a, b = recs["libm"][3]["melt_thick_output1"], recs["det"][3]["melt_thick_output1"]
+    assert a > 0.005 and b > 0.005                    # bare-ice melt has started
+    assert 1e-6 < abs(a - b) / a < 1e-3               # 8.9e-5: last-bit differences are now visible at 1e-4
+    assert dT[3] > 1e-8
