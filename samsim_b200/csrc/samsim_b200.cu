@@ -297,6 +297,7 @@ struct samsim_b200_handle_s {
   double* stage = nullptr;
   size_t stage_bytes = 0;
   long long launches = 0;
+  int num_sms = 148;
 };
 
 static int ensure_stage(samsim_handle_t h, size_t bytes) {
@@ -329,6 +330,10 @@ int samsim_b200_create(const samsim_config_t* cfg, int32_t ncol, int32_t device,
   if (!(cfg->dt > 0.0) || !(cfg->thick_0 > 0.0)) return fail(SAMSIM_ERR_CONFIG, "dt and thick_0 must be positive");
   CU(cudaSetDevice(device));
   samsim_handle_t h = new samsim_b200_handle_s();
+  {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->num_sms = sms;
+  }
   h->cfg = *cfg;
   h->device = device;
   h->ncol = ncol;
@@ -632,8 +637,11 @@ int samsim_b200_step(samsim_handle_t h, int64_t nsteps) {
     p.nsteps = (int)chunk;
     p.snap_sc = (h->snap_mode >= SAMSIM_SNAP_SCALARS) ? h->snap_sc : nullptr;
     p.snap_arr = (h->snap_mode >= SAMSIM_SNAP_FULL) ? h->snap_arr : nullptr;
-    const unsigned grid = (unsigned)((h->ncol + SAMSIM_BLOCK - 1) / SAMSIM_BLOCK);
-    samsim_step_kernel<<<grid, SAMSIM_BLOCK, 0, h->stream>>>(p);
+    // small batches: shrink the block (the kernel is compiled for <= SAMSIM_BLOCK threads) until every SM has work
+    int block = SAMSIM_BLOCK;
+    while (block > 64 && (h->ncol + block - 1) / block < 2 * h->num_sms) block >>= 1;
+    const unsigned grid = (unsigned)((h->ncol + block - 1) / block);
+    samsim_step_kernel<<<grid, block, 0, h->stream>>>(p);
     CU(cudaGetLastError());
     h->launches++;
     for (int64_t s = 0; s < chunk; s++) clock_tick(h);
