@@ -212,11 +212,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from samsim_b200 import api
+    from samsim_b200 import api, distributed as D
 
     total = args.columns
-    per = total // world
-    col0 = rank * per
+    col0, per = D.shard(total, rank, world)
     st = load_state(START_RECORD)
     sites = load_sites(64)
     cfg = api.Config.from_state({**st, "thick_min": st["thick_min"]})
@@ -279,6 +278,9 @@ def main():
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
+    # ---- ensemble diagnostics: the only cross-GPU exchange of the model (NCCL all-reduce of 18 numbers) ----
+    ensemble = D.reduce_ensemble(eng.reduce_diag(), per, device=torch.device("cuda", local_rank))
+
     # ---- max over ranks ----
     t = torch.tensor([kernel_ms * 1e-3, wall_a, wall_b], dtype=torch.float64, device="cuda")
     nf = torch.tensor([eng.count_failed()], dtype=torch.int64, device="cuda")
@@ -318,6 +320,7 @@ def main():
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}},
             "clocks": sampler.summary(),
             "failed_columns": int(nf.item()),
+            "ensemble": {k: ensemble[k] for k in ("thickness", "thick_snow", "N_active", "columns")},
         }
         if world == 1 and not args.no_cpu_baseline:
             ncores = os.cpu_count() or 1

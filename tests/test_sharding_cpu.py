@@ -82,3 +82,43 @@ def test_two_rank_gloo_sharding_matches_single_process(tmp_path, oracle_mod):
     assert np.array_equal(res[:8], th)                 # shards give identical per-column results
     assert res[8] == th[:4].sum() + th[4:].sum() and res[9] == th.min() and res[10] == th.max()
     assert res[11] == 1.5                              # MAX over ranks of the timing
+
+
+def test_shard_partition_covers_all_columns():
+    from samsim_b200 import distributed as D
+    for total, world in ((1 << 20, 8), (10, 4), (7, 8), (100, 3)):
+        spans = [D.shard(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and sum(n for _, n in spans) == total
+        for (a, n), (b, _) in zip(spans, spans[1:]):
+            assert a + n == b
+
+
+WORKER2 = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, %(root)r)
+    import numpy as np, torch, torch.distributed as dist
+    from samsim_b200 import distributed as D
+    dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    col0, n = D.shard(11, rank, world)
+    vals = np.arange(col0, col0 + n, dtype=np.float64) + 1.0
+    local = {k: {"sum": float(vals.sum()), "min": float(vals.min()), "max": float(vals.max())} for k in D.NAMES}
+    red = D.reduce_ensemble(local, n)
+    g = D.gather_columns(torch.from_numpy(vals))
+    if rank == 0:
+        np.save(%(out)r, np.array([red["thickness"]["mean"], red["thickness"]["min"], red["thickness"]["max"], red["columns"]] + g.tolist()))
+    dist.destroy_process_group()
+""")
+
+
+def test_ensemble_reduction_and_gather_two_ranks(tmp_path):
+    out = tmp_path / "r.npy"
+    script = tmp_path / "w.py"
+    script.write_text(WORKER2 % {"root": str(ROOT), "out": str(out)})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29542", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r))) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=120) == 0
+    r = np.load(out)
+    assert r[0] == 6.0 and r[1] == 1.0 and r[2] == 11.0 and r[3] == 11
+    assert np.array_equal(r[4:], np.arange(1, 12, dtype=np.float64))   # uneven shards (6 + 5) gathered in order
