@@ -727,8 +727,15 @@ __device__ __forceinline__ double fl_Q_0_snow(double m_snow, double thick_snow, 
 // SUM(thick(k+1:Na-1)) of layer k is the same forward sum as SUM(thick(k':Na-1)) of layer k' = k+1.
 // The FORALL fl_up(k:N_active) += flux (:162-164) is a running sum in layer order; only element k is clamped
 // (:166), which the carry does not see -- same additions, O(N).
+//
+// Lazy Rayleigh numbers (exact_all == false).  ray(k) is observable only through the S8 record of the NEXT step
+// and through get_array after the launch; on every other step it matters only where it can exceed ray_crit (:145).
+// The backward pass therefore also accumulates the two sums as plain suffix sums (same terms, other order:
+// relative deviation <= ~1e-14) and classifies every layer with them; the reference's forward sums are evaluated
+// only for layers whose estimate is above ray_crit*(1 - 1e-10) -- a margin four orders wider than the deviation --
+// so decisions and fluxes are the reference's, bit for bit, and layers that cannot drain cost O(1).
 #define SAMSIM_GB 8
-__device__ __noinline__ void grav_drain(const DevCfg& g, Col& c) {
+__device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all) {
   const int Na = c.N_active, N = g.Nlayer;
   const double dt = g.dt;
   Lay q = c.w1(), smin = c.w2(), fl_m = c.fl_m();
@@ -736,25 +743,45 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c) {
 
   for (int k = Na; k <= N - 1; k++) c.ray()[k] = 0.0;  // :98 ray = 0 (entries below N_active are overwritten next)
   const double bottom_h = c.thick()[Na] * c.psi_s()[Na] / psi_s_min;  // thick(N_active)*psi_s(N_active)/psi_s_min
+  const double S_br_Na = c.S_br()[Na];
   // :104-106 permeability, thick/perm, and the order-independent suffix minimum of perm(k:Na-1), one backward pass
   double perm_Na = 0.0;
   {
-    double mn = 0.0;
+    double mn = 0.0, sq = 0.0, st = 0.0, st_below = 0.0, qb_est = 0.0;  // suffix sums for the estimate
     for (int k = Na; k >= 1; k--) {
-      if (k - SAMSIM_PF >= 1) { c.psi_l().prefetch(k - SAMSIM_PF); c.thick().prefetch(k - SAMSIM_PF); }
+      if (k - SAMSIM_PF >= 1) { c.psi_l().prefetch(k - SAMSIM_PF); c.thick().prefetch(k - SAMSIM_PF); c.S_br().prefetch(k - SAMSIM_PF); }
       const double pk = 1e-17 * det_pow(1000.0 * fabs(c.psi_l()[k]), 3.10);
-      if (k == Na) { perm_Na = pk; continue; }  // perm itself is not needed again: only thick/perm and the suffix minimum
-      q[k] = c.thick()[k] / pk;
+      if (k == Na) { perm_Na = pk; qb_est = bottom_h / pk; continue; }  // perm itself is not needed again
+      const double thk = c.thick()[k];
+      const double qk = thk / pk;
+      q[k] = qk;
       mn = (k == Na - 1) ? pk : f_min(mn, pk);
-      smin[k] = mn;
+      if (exact_all) {
+        smin[k] = mn;
+      } else {
+        st_below = st;          // ~SUM(thick(k+1:Na-1))
+        sq = sq + qk;           // ~SUM(thick/perm (k:Na-1))
+        st = st + thk;          // ~SUM(thick(k:Na-1))
+        double est;
+        if (g.harmonic_flag == 1) {
+          est = grav * rho_l * bbeta * (c.S_br()[k] - S_br_Na) * (st_below + bottom_h) * f_min(mn, perm_Na);
+          smin[k] = mn;  // needed again by the exact evaluation of candidates
+        } else {
+          const double hp = (mn < 1e-14) ? 0.0 : (st + bottom_h) / (sq + qb_est);
+          est = grav * rho_l * bbeta * (c.S_br()[k] - S_br_Na) * (st_below + bottom_h) * hp;
+        }
+        est = est / (kappa_l * mu);
+        // exactly 0 where the reference's value is exactly 0 (hp == 0); negative estimates clip like :135
+        // (harmonic_flag 2: a candidate has est > 0, hence mn >= 1e-14: its exact evaluation needs no smin)
+        c.ray()[k] = (g.harmonic_flag == 2 && mn < 1e-14) ? 0.0 : f_max(est, 0.0);
+      }
     }
   }
   const double qb = bottom_h / perm_Na;
-  const double S_br_Na = c.S_br()[Na];
 
   // blocks of GB layers, from the bottom block upwards; `carry_t` = SUM(thick(k0+GB : Na-1)) of the block below
   double carry_t = 0.0;
-  for (int k0 = ((Na - 2) / SAMSIM_GB) * SAMSIM_GB + 1; k0 >= 1 && Na >= 2; k0 -= SAMSIM_GB) {
+  for (int k0 = ((Na - 2) / SAMSIM_GB) * SAMSIM_GB + 1; exact_all && k0 >= 1 && Na >= 2; k0 -= SAMSIM_GB) {
     double aq[SAMSIM_GB], at[SAMSIM_GB];
 #pragma unroll
     for (int j = 0; j < SAMSIM_GB; j++) { aq[j] = 0.0; at[j] = 0.0; }
@@ -815,8 +842,32 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c) {
       c.ray().prefetch(k + SAMSIM_PF); c.psi_s().prefetch(k + SAMSIM_PF); c.S_abs().prefetch(k + SAMSIM_PF);
       c.m().prefetch(k + SAMSIM_PF); c.S_br().prefetch(k + SAMSIM_PF);
     }
-    const double rk = c.ray()[k], Sk = c.S_abs()[k];
+    double rk = c.ray()[k];
+    const double Sk = c.S_abs()[k];
     const double sbk1 = c.S_br()[k + 1];
+    if (!exact_all && rk > ray_crit * (1.0 - 1e-10)) {
+      // candidate: the reference's forward sums (:115-120, :128) for this layer only, then ray(k) as at :126-136
+      double hq = 0.0, ht = 0.0, hb = 0.0;
+      for (int kk = k; kk <= Na - 1; kk++) {
+        const double tv = c.thick()[kk];
+        hq = hq + q[kk];
+        ht = ht + tv;
+        if (kk > k) hb = hb + tv;
+      }
+      const double height = hb + bottom_h;
+      const double d_S_br = sbk - S_br_Na;
+      double r;
+      if (g.harmonic_flag == 1) {
+        r = grav * rho_l * bbeta * d_S_br * height * f_min(smin[k], perm_Na);
+      } else {
+        double hp = hq + qb;  // the estimate was > 0, so minval(perm(k:Na-1)) >= 1e-14 (:112) holds
+        hp = (ht + bottom_h) / hp;
+        r = grav * rho_l * bbeta * d_S_br * height * hp;
+      }
+      r = r / (kappa_l * mu);
+      rk = f_max(r, 0.0);
+      c.ray()[k] = rk;
+    }
     double up = run;
     double S_after = Sk;
     sum_before = sum_before + Sk;

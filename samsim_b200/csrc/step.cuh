@@ -587,7 +587,12 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   SAMSIM_PHASE_SYNC();
   if (c.status == 0) {  // ===== phase 4 =====
   // ---- S13 gravity drainage :463-477 ----
-  if (g.grav_flag == 2 && c.N_active > 1) grav_drain(g, c);
+  if (g.grav_flag == 2 && c.N_active > 1) {
+    // ray(1:N-1) is observable through the S8 record of the next step (n_time_out was already advanced by S8 above)
+    // and through get_array after the launch; otherwise only layers that can drain need their exact value
+    const bool next_step_outputs = (c.n_time_out == g.i_time_out);
+    grav_drain(g, c, c.want_state || next_step_outputs);
+  }
   else if (g.grav_flag == 3 && c.N_active > 1) grav_drain_simple(g, c);
 
   }
