@@ -198,7 +198,20 @@ int samsim_b200_reduce_diag(samsim_handle_t h, double* out18);
 int64_t samsim_b200_launch_count(samsim_handle_t h);
 /* time (ms) of the last samsim_b200_step measured with CUDA events on the handle's stream */
 int samsim_b200_last_step_ms(samsim_handle_t h, float* ms);
-/* raw device pointers for zero-copy interop (torch): arrays[array_id][k][ncol_pad], k = 0..Nlayer+1 */
+/* ---- re-binning ("within a GPU, columns are periodically re-binned by N_active / snow regime for
+ * warp coherence; local permutation only, an index array maps back") ---------------------------
+ * The reference has one column per process, so there is nothing to replace: this is what a batch needs so that
+ * columns whose N_active (loop trip counts, mo_grotz.f90:298-307,592-598) and snow branches (mo_grotz.f90:273-292)
+ * differ do not share a warp.  Results do not depend on it (columns are independent); every entry point keeps
+ * taking the caller's column numbers.  *changed = 1 if the device order changed. */
+int samsim_b200_rebin(samsim_handle_t h, int32_t* changed);
+/* re-bin automatically every nsteps steps inside samsim_b200_step (0 = never, the default) */
+int samsim_b200_set_rebin_interval(samsim_handle_t h, int64_t nsteps);
+/* slot_of_col[c] = position of column c in the device arrays (identity until the first re-binning) */
+int samsim_b200_get_slot_map(samsim_handle_t h, int32_t* slot_of_col);
+
+/* raw device pointers for zero-copy interop (torch): arrays[array_id][k][ncol_pad], k = 0..Nlayer+1; the column
+ * index is the SLOT (samsim_b200_get_slot_map) once the handle has been re-binned */
 int samsim_b200_device_layout(samsim_handle_t h, void** arrays, void** scalars, void** ints, int64_t* ncol_pad,
                               int64_t* lstride);
 

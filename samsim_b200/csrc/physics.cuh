@@ -71,6 +71,11 @@ struct Lay {
   }
 };
 #ifndef SAMSIM_PF
+// Layer loops are not unrolled: the step kernel is instruction-fetch sensitive (see step.cuh, SAMSIM_SYNC) and the
+// loads of the next layers are already in flight through the L1 prefetches below.
+#ifndef SAMSIM_LOOP
+#define SAMSIM_LOOP _Pragma("unroll 1")
+#endif
 #define SAMSIM_PF 2  // prefetch distance in layers (2 measured best on B200: 70.8 vs 69.5 M col-steps/s at 4, 64.7 at 12)
 #endif
 
@@ -307,11 +312,13 @@ __device__ __forceinline__ void notzflux(double time, double& fl_sw, double& fl_
 // forward sums in the reference's order: SUM(a(i:j)) and SUM(a(i:j)*b(i:j))
 __device__ __forceinline__ double sum_fwd(const Lay& a, int i, int j) {
   double s = 0.0;
+  SAMSIM_LOOP
   for (int q = i; q <= j; q++) s = s + a[q];
   return s;
 }
 __device__ __forceinline__ double sum_prod_fwd(const Lay& a, const Lay& b, int i, int j) {
   double s = 0.0;
+  SAMSIM_LOOP
   for (int q = i; q <= j; q++) s = s + a[q] * b[q];
   return s;
 }
@@ -338,6 +345,7 @@ __device__ __noinline__ double freeboard_of(const DevCfg& g, Col& c) {
     A = fb.A; G = fb.G;
   } else {
     A = 0.0; G = 0.0;  // forward totals, the reference's order
+    SAMSIM_LOOP
     for (int q = 1; q <= Na; q++) {
       if (q + SAMSIM_PF <= Na) { c.psi_s().prefetch(q + SAMSIM_PF); c.psi_g().prefetch(q + SAMSIM_PF); c.thick().prefetch(q + SAMSIM_PF); }
       const double t = c.thick()[q];
@@ -475,6 +483,7 @@ __device__ __noinline__ void mass_transfer(const DevCfg& g, Col& c, const Lay& f
   if (kstart > 1) { T_km1 = c.T()[kstart - 1]; Sbu_km1 = S_bu_view[kstart - 1]; Sabs_km1 = c.S_abs()[kstart - 1]; }
   double T_k = c.T()[kstart], Sbu_k = S_bu_view[kstart];
   double f0 = fl_m[kstart];
+  SAMSIM_LOOP
   for (int k = kstart; k <= Na; k++) {
     if (k + SAMSIM_PF <= Na) {
       c.T().prefetch(k + SAMSIM_PF); S_bu_view.prefetch(k + SAMSIM_PF); c.S_abs().prefetch(k + SAMSIM_PF);
@@ -741,6 +750,7 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
   Lay q = c.w1(), smin = c.w2(), fl_m = c.fl_m();
   double heat_loss = 0.0;
 
+  SAMSIM_LOOP
   for (int k = Na; k <= N - 1; k++) c.ray()[k] = 0.0;  // :98 ray = 0 (entries below N_active are overwritten next)
   const double bottom_h = c.thick()[Na] * c.psi_s()[Na] / psi_s_min;  // thick(N_active)*psi_s(N_active)/psi_s_min
   const double S_br_Na = c.S_br()[Na];
@@ -748,6 +758,7 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
   double perm_Na = 0.0;
   {
     double mn = 0.0, sq = 0.0, st = 0.0, st_below = 0.0, qb_est = 0.0;  // suffix sums for the estimate
+    SAMSIM_LOOP
     for (int k = Na; k >= 1; k--) {
       if (k - SAMSIM_PF >= 1) { c.psi_l().prefetch(k - SAMSIM_PF); c.thick().prefetch(k - SAMSIM_PF); c.S_br().prefetch(k - SAMSIM_PF); }
       const double pk = 1e-17 * det_pow(1000.0 * fabs(c.psi_l()[k]), 3.10);
@@ -795,6 +806,7 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
           if (j <= d) { aq[j] = aq[j] + qv; at[j] = at[j] + tv; }
       }
     }
+    SAMSIM_LOOP
     for (int kk = k0 + SAMSIM_GB; kk <= Na - 1; kk++) {  // body: every accumulator takes every layer, in order
       if (kk + SAMSIM_PF <= Na - 1) { q.prefetch(kk + SAMSIM_PF); c.thick().prefetch(kk + SAMSIM_PF); }
       const double qv = q[kk], tv = c.thick()[kk];
@@ -837,6 +849,7 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
 
   double run = 0.0;  // running sum = fl_up(kk) for every kk not yet clamped
   double sbk = c.S_br()[1];
+  SAMSIM_LOOP
   for (int k = 1; k <= Na - 1; k++) {  // :144-171
     if (k + SAMSIM_PF <= Na) {
       c.ray().prefetch(k + SAMSIM_PF); c.psi_s().prefetch(k + SAMSIM_PF); c.S_abs().prefetch(k + SAMSIM_PF);
@@ -848,6 +861,7 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
     if (!exact_all && rk > ray_crit * (1.0 - 1e-10)) {
       // candidate: the reference's forward sums (:115-120, :128) for this layer only, then ray(k) as at :126-136
       double hq = 0.0, ht = 0.0, hb = 0.0;
+      SAMSIM_LOOP
       for (int kk = k; kk <= Na - 1; kk++) {
         const double tv = c.thick()[kk];
         hq = hq + q[kk];
@@ -919,17 +933,22 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
 __device__ __noinline__ void grav_drain_simple(const DevCfg& g, Col& c) {
   const int Na = c.N_active, N = g.Nlayer;
   Lay perm = c.w0(), hperm = c.w2();
+  SAMSIM_LOOP
   for (int k = 1; k <= N - 1; k++) c.ray()[k] = 0.0;
+  SAMSIM_LOOP
   for (int k = 1; k <= Na; k++) perm[k] = 1e-17 * det_pow(1000.0 * fabs(c.psi_l()[k]), 3.10);
   const double bottom_h = c.thick()[Na] * c.psi_s()[Na] / psi_s_min;
   if (g.harmonic_flag == 2) {
+    SAMSIM_LOOP
     for (int k = 1; k <= Na - 1; k++) {
       double mn = perm[k];
+      SAMSIM_LOOP
       for (int kk = k; kk <= Na - 1; kk++) mn = f_min(mn, perm[kk]);
       if (mn < 1e-14) {
         hperm[k] = 0.0;
       } else {
         double h = 0.0;
+        SAMSIM_LOOP
         for (int kk = k; kk <= Na - 1; kk++) h = h + c.thick()[kk] / perm[kk];
         h = h + bottom_h / perm[Na];
         hperm[k] = (sum_fwd(c.thick(), k, Na - 1) + bottom_h) / h;
@@ -937,12 +956,14 @@ __device__ __noinline__ void grav_drain_simple(const DevCfg& g, Col& c) {
     }
   }
   const double S_br_Na = c.S_br()[Na];
+  SAMSIM_LOOP
   for (int k = 1; k <= Na - 1; k++) {
     double d_S_br = c.S_br()[k] - S_br_Na;
     double height = sum_fwd(c.thick(), k + 1, Na - 1) + bottom_h;
     double r;
     if (g.harmonic_flag == 1) {
       double mn = perm[k];
+      SAMSIM_LOOP
       for (int kk = k; kk <= Na; kk++) mn = f_min(mn, perm[kk]);
       r = grav * rho_l * bbeta * d_S_br * height * mn;
     } else {
@@ -951,6 +972,7 @@ __device__ __noinline__ void grav_drain_simple(const DevCfg& g, Col& c) {
     r = r / (kappa_l * mu);
     c.ray()[k] = f_max(r, 0.0);
   }
+  SAMSIM_LOOP
   for (int k = Na - 1; k >= 1; k--)
     if (c.ray()[k] > ray_crit) c.S_abs()[k] = c.S_abs()[k] * SAMSIM_F32(0.99);
   SCV(c, SC_GRAV_DRAIN) = 0.0;
@@ -968,6 +990,7 @@ __device__ __noinline__ void flood(const DevCfg& g, Col& c) {
   double& H_abs_snow = SCV(c, SC_H_ABS_SNOW);
   double& m_snow = SCV(c, SC_M_SNOW);
   double hp = 0.0;
+  SAMSIM_LOOP
   for (int k = 1; k <= Na - 1; k++) hp = hp + c.thick()[k] / (1e-17 * det_pow(1000.0 * c.psi_l()[k], 3.10));  // :73-79
   const double bottom_h = c.thick()[Na] * c.psi_s()[Na] / psi_s_min;
   hp = hp + bottom_h / (1e-17 * det_pow(1000.0 * c.psi_l()[Na], 3.10));
@@ -1040,23 +1063,30 @@ __device__ __noinline__ void flush3(const DevCfg& g, Col& c) {
   Lay R_v = c.w0(), R_h = c.w1(), R = c.w2(), S_bu = c.w3(), fl_m = c.fl_m();
   double& melt_thick = SCV(c, SC_MELT_THICK);
 
+  SAMSIM_LOOP
   for (int k = 1; k <= Na; k++) { c.flush_v()[k] = 0.0; c.flush_h()[k] = 0.0; }   // :101-102 (dummies are DIMENSION(N_active))
+  SAMSIM_LOOP
   for (int k = 1; k <= Na; k++) S_bu[k] = c.S_abs()[k] / c.m()[k];              // :103
   const double konst = sum_fwd(c.thick(), 1, Na) * para_flush_horiz;          // :106
   melt_thick = f_min(melt_thick, c.psi_l()[1] * c.thick()[1]);                  // :110
   melt_thick = f_min(melt_thick, g.thick_0 / 3.0);                          // :112
 
   if (g.snow_flush_flag == 1) {  // :114-125
+    SAMSIM_LOOP
     for (int k = Na + 1; k <= N; k++) c.perm()[k] = 0.0;
+    SAMSIM_LOOP
     for (int k = 1; k <= Na; k++) {
       double p = 1e-17 * det_pow(1000.0 * fabs(c.psi_l()[k] + 2. * c.psi_g()[k]), 3.10);
       if (p == 0.0) p = 1.0;
       c.perm()[k] = p;
     }
   } else if (g.snow_flush_flag == 0) {  // :126-130
+    SAMSIM_LOOP
     for (int k = Na + 1; k <= N; k++) c.perm()[k] = 1.0;
+    SAMSIM_LOOP
     for (int k = 1; k <= Na; k++) c.perm()[k] = 1e-17 * det_pow(1000.0 * fabs(c.psi_l()[k]), 3.10);
   }
+  SAMSIM_LOOP
   for (int k = 1; k <= Na; k++) {  // :133-137
     const double pk = f_max(c.perm()[k], 0.00000000000000000000001), thk = c.thick()[k];
     R_v[k] = mu * thk / pk;
@@ -1064,6 +1094,7 @@ __device__ __noinline__ void flush3(const DevCfg& g, Col& c) {
   }
   R[Na] = 0.0;
   R[Na - 1] = R_v[Na - 1];
+  SAMSIM_LOOP
   for (int k = Na - 2; k >= 1; k--) {  // :141-146
     double r = R[k + 1] + R_v[k];
     R[k] = ((r)*R_h[k]) / (r + R_h[k]);
@@ -1078,6 +1109,7 @@ __device__ __noinline__ void flush3(const DevCfg& g, Col& c) {
     c.flush_h()[1] = flush_total * (R[2] + R_v[1]) / den;  // :159-160
     c.flush_v()[1] = flush_total * R_h[1] / den;
   }
+  SAMSIM_LOOP
   for (int k = 2; k <= Na - 1; k++) {  // :161-164
     const double fv = c.flush_v()[k - 1], a = R[k + 1] + R_v[k], den = a + R_h[k];
     c.flush_h()[k] = fv * a / den;
@@ -1087,6 +1119,7 @@ __device__ __noinline__ void flush3(const DevCfg& g, Col& c) {
   c.flush_h()[Na] = 0.0;
 
   fl_m[1] = 0.0;  // :179-180
+  SAMSIM_LOOP
   for (int k = 1; k <= Na; k++) fl_m[k + 1] = -c.flush_v()[k];
 
   mass_transfer(g, c, fl_m, S_bu);  // with the LOCAL S_bu (:182)
@@ -1098,6 +1131,7 @@ __device__ __noinline__ void flush3(const DevCfg& g, Col& c) {
 
   double sfh = 0.0;
   double H_Na = c.H_abs()[Na], S_Na = c.S_abs()[Na];
+  SAMSIM_LOOP
   for (int k = 1; k <= Na - 1; k++) {  // :196-206
     const double fh = c.flush_h()[k], Tk = c.T()[k];
     const double loss_S = fh * S_br_of(g, Tk, c.S_abs()[k] / c.m()[k]);
@@ -1117,9 +1151,11 @@ __device__ __noinline__ void flush3(const DevCfg& g, Col& c) {
   c.S_abs()[Na] = S_Na;
 
   double mn = c.S_abs()[1];
+  SAMSIM_LOOP
   for (int k = 2; k <= Na; k++) mn = f_min(mn, c.S_abs()[k]);
   mn = f_min(mn, 0.0);  // MINVAL over all Nlayer: inactive layers hold 0 (only matters when Na < N)
   if (mn < -0.00000000000000000000000001)
+    SAMSIM_LOOP
     for (int k = 1; k <= Na; k++) c.S_abs()[k] = f_max(c.S_abs()[k], 0.0);
   if (fabs(c.m()[1]) < 0.000001) c.status = 9876;  // :230-233
 }
@@ -1141,6 +1177,7 @@ __device__ __noinline__ void flush4(const DevCfg& g, Col& c) {
   }
   c.S_abs()[1] = f_max(c.S_abs()[1], 0.00);
   double mn = c.S_abs()[1];
+  SAMSIM_LOOP
   for (int q = 2; q <= Na; q++) mn = f_min(mn, c.S_abs()[q]);
   if (mn < 0.0) c.status = 9876;
 }
@@ -1149,6 +1186,7 @@ __device__ __noinline__ void flush4(const DevCfg& g, Col& c) {
 // mo_layer_dynamics.f90.  Snapshots rho/S_bu/H of the reference become w0/w1/w2.
 // ==========================================================================================
 __device__ __forceinline__ void snapshot_layers(Col& c, int k0, int k1) {
+  SAMSIM_LOOP
   for (int k = k0; k <= k1; k++) {
     const double mk = c.m()[k];
     c.w0()[k] = mk / c.thick()[k];   // rho
@@ -1168,6 +1206,7 @@ __device__ __noinline__ void top_melt(const DevCfg& g, Col& c) {
   c.H_abs()[1] = c.H_abs()[1] + c.H_abs()[2];
   c.thick()[1] = c.thick()[1] + c.thick()[2];
   const int kmax = (N_top - 1 < c.N_active - 1) ? N_top - 1 : c.N_active - 1;
+  SAMSIM_LOOP
   for (int k = 2; k <= kmax; k++) {  // :238-243
     c.m()[k] = rho[k + 1] * thick_0;
     c.S_abs()[k] = S_bu[k + 1] * rho[k + 1] * thick_0;
@@ -1179,6 +1218,7 @@ __device__ __noinline__ void top_melt(const DevCfg& g, Col& c) {
     c.N_active = Na - 1;
   } else if (c.N_active > N_top && c.N_active <= N && c.thick()[N_top + 1] / thick_0 < 1.00001) {  // :256-273
     const int Na = c.N_active;
+    SAMSIM_LOOP
     for (int k = N_top; k <= Na - 1; k++) {
       c.m()[k] = rho[k + 1] * thick_0;
       c.S_abs()[k] = S_bu[k + 1] * rho[k + 1] * thick_0;
@@ -1194,6 +1234,7 @@ __device__ __noinline__ void top_melt(const DevCfg& g, Col& c) {
     c.m()[N_top] = loss_m;
     c.S_abs()[N_top] = loss_S;
     c.H_abs()[N_top] = loss_H;
+    SAMSIM_LOOP
     for (int k = N_top + 1; k <= N_middle + N_top; k++) {
       double mk = c.m()[k] - loss_m, Hk = c.H_abs()[k] - loss_H, Sk = c.S_abs()[k] - loss_S;
       const double shift = thick_0 * (double)(float)(N_middle - k + N_top) / (double)(float)(N_middle);  // :293
@@ -1204,6 +1245,7 @@ __device__ __noinline__ void top_melt(const DevCfg& g, Col& c) {
       c.H_abs()[k] = Hk + loss_H;
       c.S_abs()[k] = Sk + loss_S;
     }
+    SAMSIM_LOOP
     for (int k = N_top + 1; k <= N_top + N_middle; k++) c.thick()[k] = c.thick()[k] - thick_0 / (double)(float)(N_middle);
   }
   // :318-321 grid consistency, STOP 7889 (SUM(thick) over all layers; inactive are 0)
@@ -1219,6 +1261,7 @@ __device__ __noinline__ void bottom_melt(const DevCfg& g, Col& c) {
   snapshot_layers(c, N_top + 1, N);  // :364-370
   const double thN = c.thick()[N];
   double loss_m = 0.0, loss_S = 0.0, loss_H = 0.0;
+  SAMSIM_LOOP
   for (int k = N_top + 1; k <= N_top + N_middle; k++) {  // :378-400
     double mk = c.m()[k] + loss_m, Hk = c.H_abs()[k] + loss_H, Sk = c.S_abs()[k] + loss_S;
     const double shift = thN * (k - N_top) / (double)(float)(N_middle);
@@ -1229,7 +1272,9 @@ __device__ __noinline__ void bottom_melt(const DevCfg& g, Col& c) {
     c.H_abs()[k] = Hk - loss_H;
     c.S_abs()[k] = Sk - loss_S;
   }
+  SAMSIM_LOOP
   for (int k = N_top + 1; k <= N_top + N_middle; k++) c.thick()[k] = c.thick()[k] - thN / (double)(float)(N_middle);
+  SAMSIM_LOOP
   for (int k = N_top + N_middle + 1; k <= N; k++) {  // :410-415
     const double thk = c.thick()[k];
     c.H_abs()[k] = rho[k - 1] * thk * H[k - 1];
@@ -1245,6 +1290,7 @@ __device__ __noinline__ void bottom_growth(const DevCfg& g, Col& c) {
   snapshot_layers(c, N_top + 1, N_top + N_middle + 1);  // :463-468
   const double thN = c.thick()[N];
   double gain_m = 0.0, gain_S = 0.0, gain_H = 0.0;
+  SAMSIM_LOOP
   for (int k = N_top + 1; k <= N_top + N_middle; k++) {  // :476-495
     double mk = c.m()[k] - gain_m, Hk = c.H_abs()[k] - gain_H, Sk = c.S_abs()[k] - gain_S;
     const double shift = thN * (k - N_top) / (double)(float)(N_middle);
@@ -1255,7 +1301,9 @@ __device__ __noinline__ void bottom_growth(const DevCfg& g, Col& c) {
     c.H_abs()[k] = Hk + gain_H;
     c.S_abs()[k] = Sk + gain_S;
   }
+  SAMSIM_LOOP
   for (int k = N_top + 1; k <= N_top + N_middle; k++) c.thick()[k] = c.thick()[k] + thN / (double)(float)(N_middle);
+  SAMSIM_LOOP
   for (int k = N - N_bottom + 1; k <= N - 1; k++) {  // :503-508
     c.H_abs()[k] = c.H_abs()[k + 1];
     c.S_abs()[k] = c.S_abs()[k + 1];
@@ -1299,6 +1347,7 @@ __device__ __noinline__ void top_grow(const DevCfg& g, Col& c) {
     c.thick()[1] = c.thick()[1] - thick_0;
   }
   const int kmax = (N_top < c.N_active) ? N_top : c.N_active;
+  SAMSIM_LOOP
   for (int k = 2; k <= kmax; k++) {  // :651-656
     c.m()[k] = rho[k - 1] * thick_0;
     c.S_abs()[k] = S_bu[k - 1] * rho[k - 1] * thick_0;
@@ -1312,6 +1361,7 @@ __device__ __noinline__ void top_grow(const DevCfg& g, Col& c) {
     c.H_abs()[Na] = H[Na - 1] * thick_0 * rho[Na - 1];
     c.thick()[Na] = thick_0;
   } else if (c.N_active > N_top && c.N_active < N) {  // :668-680
+    SAMSIM_LOOP
     for (int k = N_top + 1; k <= c.N_active; k++) {
       c.m()[k] = rho[k - 1] * thick_0;
       c.S_abs()[k] = S_bu[k - 1] * rho[k - 1] * thick_0;
@@ -1327,6 +1377,7 @@ __device__ __noinline__ void top_grow(const DevCfg& g, Col& c) {
     double loss_m = thick_0 * rho[N_top];
     double loss_S = loss_m * S_bu[N_top];
     double loss_H = loss_m * H[N_top];
+    SAMSIM_LOOP
     for (int k = N_top + 1; k <= N_middle + N_top; k++) {
       double mk = c.m()[k] + loss_m, Hk = c.H_abs()[k] + loss_H, Sk = c.S_abs()[k] + loss_S;
       const double shift = thick_0 * (double)(float)(N_middle - k + N_top) / (double)(float)(N_middle);
@@ -1337,6 +1388,7 @@ __device__ __noinline__ void top_grow(const DevCfg& g, Col& c) {
       c.H_abs()[k] = Hk - loss_H;
       c.S_abs()[k] = Sk - loss_S;
     }
+    SAMSIM_LOOP
     for (int k = N_top + 1; k <= N_top + N_middle; k++) c.thick()[k] = c.thick()[k] + thick_0 / (double)(float)(N_middle);
   }
 }

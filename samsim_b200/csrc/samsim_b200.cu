@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "../../include/samsim_b200.h"
 #include "step.cuh"
 
@@ -126,12 +128,17 @@ __global__ void __launch_bounds__(SAMSIM_BLOCK, SAMSIM_MINBLOCKS) samsim_step_ke
   p.in[(size_t)IN_STYROPOR * ls + col] = c.styropor_flag;
 }
 
+// Column -> slot indirection.  After samsim_b200_rebin the columns of a handle sit in regime order; `map`
+// (slot_of_col, nullptr = identity) translates the caller's column index in every host-facing kernel.
+__device__ __forceinline__ long long slot_of(const int* map, long long col) { return map ? (long long)map[col] : col; }
+
 // replicate one column (ensemble initialisation)
 __global__ void samsim_broadcast_kernel(double* arr, double* sc, int* in, long long ncol_pad, int LS, int src, int col0,
-                                        int n) {
+                                        int n, const int* map) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
-  const long long col = col0 + t;
+  const long long col = slot_of(map, col0 + t);
+  src = (int)slot_of(map, src);
   if (col == src) return;
   const size_t ls = (size_t)ncol_pad;
   for (int a = 0; a < AR_COUNT; a++)
@@ -145,7 +152,7 @@ __global__ void samsim_broadcast_kernel(double* arr, double* sc, int* in, long l
 
 // gather a snapshot block into host order: dst[(c*count + id)*ext + (k-1)]
 __global__ void samsim_gather_kernel(const double* src, double* dst, long long ncol_pad, int LS, int count, int ext,
-                                     int col0, int n, int k0) {
+                                     int col0, int n, int k0, const int* map) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)n * count * ext;
   if (t >= total) return;
@@ -154,16 +161,62 @@ __global__ void samsim_gather_kernel(const double* src, double* dst, long long n
   const long long r = t / n;
   const int k = (int)(r % ext);
   const int id = (int)(r / ext);
-  dst[((size_t)cc * count + id) * ext + k] = src[((size_t)id * LS + (k + k0)) * (size_t)ncol_pad + col0 + cc];
+  dst[((size_t)cc * count + id) * ext + k] = src[((size_t)id * LS + (k + k0)) * (size_t)ncol_pad + slot_of(map, col0 + cc)];
 }
 __global__ void samsim_scatter_kernel(double* dstdev, const double* srchost, long long ncol_pad, int LS, int id, int ext,
-                                      int col0, int n) {
+                                      int col0, int n, const int* map) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)n * ext;
   if (t >= total) return;
   const int cc = (int)(t % n);
   const int k = (int)(t / n);
-  dstdev[((size_t)id * LS + (k + 1)) * (size_t)ncol_pad + col0 + cc] = srchost[(size_t)cc * ext + k];
+  dstdev[((size_t)id * LS + (k + 1)) * (size_t)ncol_pad + slot_of(map, col0 + cc)] = srchost[(size_t)cc * ext + k];
+}
+// per-column vectors (scalars, ints, forcing perturbations) through the slot map
+template <typename T>
+__global__ void samsim_vec_get_kernel(const T* row, T* dst, int col0, int n, const int* map) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) dst[t] = row[slot_of(map, col0 + t)];
+}
+template <typename T>
+__global__ void samsim_vec_set_kernel(T* row, const T* src, int col0, int n, const int* map) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) row[slot_of(map, col0 + t)] = src[t];
+}
+
+// ---- re-binning (columns are re-binned by regime for warp coherence; local permutation only) ----
+// key: failed columns last; then N_active descending (loop trip counts), snow class (the snow branches), forcing site
+__global__ void samsim_rebin_key_kernel(const double* sc, const int* in, const int* site_of_col, long long ncol,
+                                        long long ncol_pad, double thick_min, unsigned* keys, int* vals) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= ncol) return;
+  const int na = in[(size_t)IN_N_ACTIVE * ncol_pad + s];
+  const int st = in[(size_t)IN_STATUS * ncol_pad + s];
+  const double snow = sc[(size_t)SC_THICK_SNOW * ncol_pad + s];
+  const unsigned cls = (snow <= 0.0) ? 0u : (snow < thick_min / 100.0) ? 1u : (snow < thick_min) ? 2u : 3u;
+  const unsigned site = site_of_col ? (unsigned)site_of_col[s] : 0u;
+  // deepest columns first: blocks are dispatched in index order, so the cheap ones fill the tail of the launch
+  keys[s] = ((st != 0) ? 0x80000000u : 0u) | ((0x7FFFFu - ((unsigned)na & 0x7FFFFu)) << 12) | (cls << 8) | (site & 0xFFu);
+  vals[s] = (int)s;
+}
+__global__ void samsim_rebin_unsorted_kernel(const unsigned* keys, long long ncol, int* out) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s + 1 < ncol && keys[s] > keys[s + 1]) atomicAdd(out, 1);
+}
+// tmp[row][s] = src[row][order[s]] for the real columns; padding columns keep their place
+template <typename T>
+__global__ void samsim_permute_rows_kernel(const T* src, T* tmp, long long ncol, long long ncol_pad, int nrows, const int* order) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)nrows * ncol_pad) return;
+  const long long row = t / ncol_pad, s = t - row * ncol_pad;
+  tmp[t] = (s < ncol) ? src[row * ncol_pad + order[s]] : src[t];
+}
+__global__ void samsim_rebin_maps_kernel(const int* order, const int* old_col_of_slot, int* new_col_of_slot, int* slot_of_col, long long ncol) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= ncol) return;
+  const int col = old_col_of_slot ? old_col_of_slot[order[s]] : order[s];
+  new_col_of_slot[s] = col;
+  slot_of_col[col] = (int)s;
 }
 
 // block partial reductions for reduce_diag: out[block][6][3]
@@ -298,6 +351,9 @@ struct samsim_b200_handle_s {
   size_t stage_bytes = 0;
   long long launches = 0;
   int num_sms = 148;
+  // re-binning: slot_of_col[c] = where column c lives, col_of_slot[s] = which column lives in slot s (nullptr = identity)
+  int *slot_of_col = nullptr, *col_of_slot = nullptr;
+  long long rebin_every = 0, since_rebin = 0, rebins = 0;
 };
 
 static int ensure_stage(samsim_handle_t h, size_t bytes) {
@@ -311,6 +367,66 @@ static int ensure_stage(samsim_handle_t h, size_t bytes) {
 }
 
 static double host_time_input(int k) { return ((double)(float)k - 1.0) * 3600.0 * 3.0; }
+
+// one per-column row <-> host vector; straight copies while the columns are in their original order
+template <typename T>
+static int vec_set(samsim_handle_t h, T* row, const T* host, int32_t col0, int32_t n) {
+  if (n == 0) return 0;
+  if (!h->slot_of_col) {
+    CU(cudaMemcpyAsync(row + col0, host, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  } else {
+    int rc;
+    if ((rc = ensure_stage(h, (size_t)n * sizeof(T)))) return rc;
+    CU(cudaMemcpyAsync(h->stage, host, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    samsim_vec_set_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(row, (const T*)h->stage, col0, n, h->slot_of_col);
+    CU(cudaGetLastError());
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+template <typename T>
+static int vec_get(samsim_handle_t h, const T* row, T* host, int32_t col0, int32_t n) {
+  if (n == 0) return 0;
+  if (!h->slot_of_col) {
+    CU(cudaMemcpyAsync(host, row + col0, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    int rc;
+    if ((rc = ensure_stage(h, (size_t)n * sizeof(T)))) return rc;
+    samsim_vec_get_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(row, (T*)h->stage, col0, n, h->slot_of_col);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host, h->stage, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// rows[r][s] <- rows[r][order[s]] for nrows rows of ncol_pad elements (tmp holds nrows*ncol_pad elements)
+template <typename T>
+static int permute_rows(samsim_handle_t h, T* rows, int nrows, const int* order, void* tmp) {
+  if (!rows || nrows <= 0) return 0;
+  const long long total = (long long)nrows * h->ncol_pad;
+  samsim_permute_rows_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(rows, (T*)tmp, h->ncol, h->ncol_pad, nrows, order);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(rows, tmp, (size_t)total * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+  return 0;
+}
+static size_t permute_tmp_bytes(samsim_handle_t h) {
+  int rows = h->LS;
+  if (rows < SC_COUNT) rows = SC_COUNT;
+  if (rows < SAMSIM_SNAPSC_COUNT) rows = SAMSIM_SNAPSC_COUNT;
+  return (size_t)rows * h->ncol_pad * sizeof(double);
+}
+// per-column forcing vectors arrive in column order; bring them into slot order when the handle is re-binned
+template <typename T>
+static int to_slot_order(samsim_handle_t h, T* rows, int nrows) {
+  if (!h->col_of_slot || !rows) return 0;
+  void* tmp = nullptr;
+  CU(cudaMalloc(&tmp, permute_tmp_bytes(h)));
+  int rc = permute_rows<T>(h, rows, nrows, h->col_of_slot, tmp);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(tmp);
+  return rc;
+}
 
 extern "C" {
 
@@ -386,7 +502,7 @@ void samsim_b200_destroy(samsim_handle_t h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->arr); cudaFree(h->sc); cudaFree(h->in); cudaFree(h->series); cudaFree(h->site_of_col);
   cudaFree(h->fscale); cudaFree(h->foffset); cudaFree(h->lab); cudaFree(h->set_of_col); cudaFree(h->snap_sc);
-  cudaFree(h->snap_arr); cudaFree(h->stage);
+  cudaFree(h->snap_arr); cudaFree(h->stage); cudaFree(h->slot_of_col); cudaFree(h->col_of_slot);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -417,7 +533,7 @@ int samsim_b200_set_array(samsim_handle_t h, int32_t id, const double* host, int
   if ((rc = ensure_stage(h, bytes))) return rc;
   CU(cudaMemcpyAsync(h->stage, host, bytes, cudaMemcpyHostToDevice, h->stream));
   const long long total = (long long)n * ext;
-  samsim_scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->arr, h->stage, h->ncol_pad, h->LS, id, ext, col0, n);
+  samsim_scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->arr, h->stage, h->ncol_pad, h->LS, id, ext, col0, n, h->slot_of_col);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));
   return 0;
@@ -433,7 +549,7 @@ int samsim_b200_get_array(samsim_handle_t h, int32_t id, double* host, int32_t c
   const size_t bytes = (size_t)n * ext * sizeof(double);
   if ((rc = ensure_stage(h, bytes))) return rc;
   const long long total = (long long)n * ext;
-  samsim_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->arr + (size_t)id * h->LS * h->ncol_pad, h->stage, h->ncol_pad, h->LS, 1, ext, col0, n, 1);
+  samsim_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->arr + (size_t)id * h->LS * h->ncol_pad, h->stage, h->ncol_pad, h->LS, 1, ext, col0, n, 1, h->slot_of_col);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(host, h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -445,36 +561,28 @@ int samsim_b200_set_scalar(samsim_handle_t h, int32_t id, const double* host, in
   if (rc) return rc;
   if (id < 0 || id >= SAMSIM_SC_COUNT || !host) return fail(SAMSIM_ERR_ARG, "set_scalar: bad id or null pointer");
   CU(cudaSetDevice(h->device));
-  CU(cudaMemcpyAsync(h->sc + (size_t)id * h->ncol_pad + col0, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  return 0;
+  return vec_set<double>(h, h->sc + (size_t)id * h->ncol_pad, host, col0, n);
 }
 int samsim_b200_get_scalar(samsim_handle_t h, int32_t id, double* host, int32_t col0, int32_t n) {
   int rc = check_cols(h, col0, n);
   if (rc) return rc;
   if (id < 0 || id >= SAMSIM_SC_COUNT || !host) return fail(SAMSIM_ERR_ARG, "get_scalar: bad id or null pointer");
   CU(cudaSetDevice(h->device));
-  CU(cudaMemcpyAsync(host, h->sc + (size_t)id * h->ncol_pad + col0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  return 0;
+  return vec_get<double>(h, h->sc + (size_t)id * h->ncol_pad, host, col0, n);
 }
 int samsim_b200_set_int(samsim_handle_t h, int32_t id, const int32_t* host, int32_t col0, int32_t n) {
   int rc = check_cols(h, col0, n);
   if (rc) return rc;
   if (id < 0 || id >= SAMSIM_INT_COUNT || !host) return fail(SAMSIM_ERR_ARG, "set_int: bad id or null pointer");
   CU(cudaSetDevice(h->device));
-  CU(cudaMemcpyAsync(h->in + (size_t)id * h->ncol_pad + col0, host, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  return 0;
+  return vec_set<int>(h, h->in + (size_t)id * h->ncol_pad, host, col0, n);
 }
 int samsim_b200_get_int(samsim_handle_t h, int32_t id, int32_t* host, int32_t col0, int32_t n) {
   int rc = check_cols(h, col0, n);
   if (rc) return rc;
   if (id < 0 || id >= SAMSIM_INT_COUNT || !host) return fail(SAMSIM_ERR_ARG, "get_int: bad id or null pointer");
   CU(cudaSetDevice(h->device));
-  CU(cudaMemcpyAsync(host, h->in + (size_t)id * h->ncol_pad + col0, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  return 0;
+  return vec_get<int>(h, h->in + (size_t)id * h->ncol_pad, host, col0, n);
 }
 
 int samsim_b200_broadcast_column(samsim_handle_t h, int32_t src, int32_t col0, int32_t n) {
@@ -483,7 +591,7 @@ int samsim_b200_broadcast_column(samsim_handle_t h, int32_t src, int32_t col0, i
   if (src < 0 || src >= h->ncol) return fail(SAMSIM_ERR_ARG, "broadcast: bad source column");
   if (n == 0) return 0;
   CU(cudaSetDevice(h->device));
-  samsim_broadcast_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->arr, h->sc, h->in, h->ncol_pad, h->LS, src, col0, n);
+  samsim_broadcast_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->arr, h->sc, h->in, h->ncol_pad, h->LS, src, col0, n, h->slot_of_col);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));
   return 0;
@@ -520,6 +628,8 @@ int samsim_b200_set_forcing(samsim_handle_t h, int32_t nsite, int32_t nrec, cons
     CU(cudaMalloc(&h->site_of_col, (size_t)h->ncol_pad * sizeof(int)));
     CU(cudaMemset(h->site_of_col, 0, (size_t)h->ncol_pad * sizeof(int)));
     CU(cudaMemcpy(h->site_of_col, site_of_col, (size_t)h->ncol * sizeof(int), cudaMemcpyHostToDevice));
+    int rc = to_slot_order<int>(h, h->site_of_col, 1);
+    if (rc) return rc;
   }
   for (int w = 0; w < 2; w++) {
     const double* src = w ? offset : scale;
@@ -528,6 +638,8 @@ int samsim_b200_set_forcing(samsim_handle_t h, int32_t nsite, int32_t nrec, cons
     CU(cudaMalloc(dst, (size_t)4 * h->ncol_pad * sizeof(double)));
     CU(cudaMemset(*dst, 0, (size_t)4 * h->ncol_pad * sizeof(double)));
     CU(cudaMemcpy2D(*dst, (size_t)h->ncol_pad * sizeof(double), src, (size_t)h->ncol * sizeof(double), (size_t)h->ncol * sizeof(double), 4, cudaMemcpyHostToDevice));
+    int rc = to_slot_order<double>(h, *dst, 4);
+    if (rc) return rc;
   }
   return 0;
 }
@@ -558,6 +670,8 @@ int samsim_b200_set_lab_forcing(samsim_handle_t h, int32_t nset, int64_t nrec, c
     CU(cudaMalloc(&h->set_of_col, (size_t)h->ncol_pad * sizeof(int)));
     CU(cudaMemset(h->set_of_col, 0, (size_t)h->ncol_pad * sizeof(int)));
     CU(cudaMemcpy(h->set_of_col, set_of_col, (size_t)h->ncol * sizeof(int), cudaMemcpyHostToDevice));
+    int rc = to_slot_order<int>(h, h->set_of_col, 1);
+    if (rc) return rc;
   }
   return 0;
 }
@@ -597,6 +711,7 @@ int samsim_b200_step(samsim_handle_t h, int64_t nsteps) {
     p.time = h->time; p.i = h->i; p.n_time_out = h->n_time_out; p.time_counter = h->time_counter;
     int64_t chunk = left;
     if (chunk > 1000000) chunk = 1000000;
+    if (h->rebin_every > 0 && chunk > h->rebin_every - h->since_rebin) chunk = h->rebin_every - h->since_rebin;
     if (need_forcing) {
       // simulate the clock to find the records the launch touches
       const int tc0 = h->time_counter;
@@ -646,9 +761,104 @@ int samsim_b200_step(samsim_handle_t h, int64_t nsteps) {
     h->launches++;
     for (int64_t s = 0; s < chunk; s++) clock_tick(h);
     left -= chunk;
+    if (h->rebin_every > 0 && (h->since_rebin += chunk) >= h->rebin_every) {
+      h->since_rebin = 0;
+      int rc = samsim_b200_rebin(h, nullptr);
+      if (rc) return rc;
+    }
   }
   CU(cudaEventRecord(h->ev1, h->stream));
   h->timed = true;
+  return 0;
+}
+
+// Re-bin the columns by regime.  A warp costs as much as its deepest column and pays for every branch
+// any of its lanes takes, so an ensemble whose columns have drifted apart (freeze-up at different dates, different
+// snow states) runs faster once equal columns sit next to each other.  Columns are independent, so the order is
+// free: a stable radix sort on (failed, N_active, snow class, forcing site) gives the new order, every per-column
+// row is permuted on the device, and slot_of_col / col_of_slot keep the caller's column numbering intact.
+int samsim_b200_rebin(samsim_handle_t h, int32_t* changed) {
+  if (!h) return fail(SAMSIM_ERR_ARG, "null handle");
+  if (changed) *changed = 0;
+  CU(cudaSetDevice(h->device));
+  const long long n = h->ncol;
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  unsigned *keys = nullptr, *keys_out = nullptr;
+  int *vals = nullptr, *order = nullptr, *flag = nullptr;
+  void *cub_tmp = nullptr, *tmp = nullptr;
+  int rc = 0;
+  auto cleanup = [&]() {
+    cudaFree(keys); cudaFree(keys_out); cudaFree(vals); cudaFree(order); cudaFree(flag); cudaFree(cub_tmp); cudaFree(tmp);
+  };
+#define RB(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) { cleanup(); return fail(SAMSIM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } \
+  } while (0)
+  RB(cudaMalloc(&keys, (size_t)n * sizeof(unsigned)));
+  RB(cudaMalloc(&keys_out, (size_t)n * sizeof(unsigned)));
+  RB(cudaMalloc(&vals, (size_t)n * sizeof(int)));
+  RB(cudaMalloc(&order, (size_t)n * sizeof(int)));
+  RB(cudaMalloc(&flag, sizeof(int)));
+  RB(cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
+  samsim_rebin_key_kernel<<<nb, 256, 0, h->stream>>>(h->sc, h->in, h->site_of_col, n, h->ncol_pad, h->cfg.thick_min, keys, vals);
+  samsim_rebin_unsorted_kernel<<<nb, 256, 0, h->stream>>>(keys, n, flag);
+  RB(cudaGetLastError());
+  int unsorted = 0;
+  RB(cudaMemcpyAsync(&unsorted, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  RB(cudaStreamSynchronize(h->stream));
+  if (unsorted == 0) { cleanup(); return 0; }  // already in regime order
+
+  size_t cub_bytes = 0;
+  RB(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys, keys_out, vals, order, (int)n, 0, 32, h->stream));
+  RB(cudaMalloc(&cub_tmp, cub_bytes));
+  RB(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys, keys_out, vals, order, (int)n, 0, 32, h->stream));
+  RB(cudaMalloc(&tmp, permute_tmp_bytes(h)));
+
+  const size_t astr = (size_t)h->LS * h->ncol_pad;
+  for (int a = 0; a < AR_STATE_COUNT && !rc; a++) rc = permute_rows<double>(h, h->arr + (size_t)a * astr, h->LS, order, tmp);
+  if (!rc) rc = permute_rows<double>(h, h->sc, SC_COUNT, order, tmp);
+  if (!rc) rc = permute_rows<int>(h, h->in, IN_COUNT, order, tmp);
+  if (!rc) rc = permute_rows<int>(h, h->site_of_col, 1, order, tmp);
+  if (!rc) rc = permute_rows<int>(h, h->set_of_col, 1, order, tmp);
+  if (!rc) rc = permute_rows<double>(h, h->fscale, 4, order, tmp);
+  if (!rc) rc = permute_rows<double>(h, h->foffset, 4, order, tmp);
+  if (!rc) rc = permute_rows<double>(h, h->snap_sc, SAMSIM_SNAPSC_COUNT, order, tmp);
+  for (int a = 0; a < SAMSIM_SNAPARR_COUNT && !rc && h->snap_arr; a++) rc = permute_rows<double>(h, h->snap_arr + (size_t)a * astr, h->LS, order, tmp);
+  if (rc) { cleanup(); return rc; }
+
+  if (!h->slot_of_col) {
+    RB(cudaMalloc(&h->slot_of_col, (size_t)n * sizeof(int)));
+    // col_of_slot stays nullptr (= identity) for the maps kernel of the first re-binning
+  }
+  samsim_rebin_maps_kernel<<<nb, 256, 0, h->stream>>>(order, h->col_of_slot, (int*)tmp, h->slot_of_col, n);
+  RB(cudaGetLastError());
+  if (!h->col_of_slot) RB(cudaMalloc(&h->col_of_slot, (size_t)n * sizeof(int)));
+  RB(cudaMemcpyAsync(h->col_of_slot, tmp, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+  RB(cudaStreamSynchronize(h->stream));
+#undef RB
+  cleanup();
+  h->rebins++;
+  if (changed) *changed = 1;
+  return 0;
+}
+
+int samsim_b200_set_rebin_interval(samsim_handle_t h, int64_t nsteps) {
+  if (!h || nsteps < 0) return fail(SAMSIM_ERR_ARG, "set_rebin_interval: bad argument");
+  h->rebin_every = nsteps;
+  h->since_rebin = 0;
+  return 0;
+}
+
+int samsim_b200_get_slot_map(samsim_handle_t h, int32_t* slot_of_col) {
+  if (!h || !slot_of_col) return fail(SAMSIM_ERR_ARG, "get_slot_map: bad argument");
+  CU(cudaSetDevice(h->device));
+  if (!h->slot_of_col) {
+    for (long long c = 0; c < h->ncol; c++) slot_of_col[c] = (int32_t)c;
+    return 0;
+  }
+  CU(cudaMemcpyAsync(slot_of_col, h->slot_of_col, (size_t)h->ncol * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
@@ -687,7 +897,7 @@ int samsim_b200_get_snapshot(samsim_handle_t h, double* scalars, double* arrays,
     if ((rc = ensure_stage(h, bytes))) return rc;
     const long long total = (long long)n * SAMSIM_SNAPSC_COUNT;
     // scalars are [id][ncol_pad]: treat as count=SNAPSC_COUNT arrays of extent 1 with LS=1
-    samsim_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->snap_sc, h->stage, h->ncol_pad, 1, SAMSIM_SNAPSC_COUNT, 1, col0, n, 0);
+    samsim_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->snap_sc, h->stage, h->ncol_pad, 1, SAMSIM_SNAPSC_COUNT, 1, col0, n, 0, h->slot_of_col);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(scalars, h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -697,7 +907,7 @@ int samsim_b200_get_snapshot(samsim_handle_t h, double* scalars, double* arrays,
     const size_t bytes = (size_t)n * SAMSIM_SNAPARR_COUNT * ext * sizeof(double);
     if ((rc = ensure_stage(h, bytes))) return rc;
     const long long total = (long long)n * SAMSIM_SNAPARR_COUNT * ext;
-    samsim_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->snap_arr, h->stage, h->ncol_pad, h->LS, SAMSIM_SNAPARR_COUNT, ext, col0, n, 1);
+    samsim_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->snap_arr, h->stage, h->ncol_pad, h->LS, SAMSIM_SNAPARR_COUNT, ext, col0, n, 1, h->slot_of_col);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(arrays, h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));

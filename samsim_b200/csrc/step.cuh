@@ -35,6 +35,7 @@ __device__ __forceinline__ double lab_rec(const Forcing& f, int kind, long long 
 __device__ __noinline__ void vital_signs(const DevCfg& g, Col& c) {
   const int Na = c.N_active;
   double sumH = 0.0, summ = 0.0, sumS = 0.0;
+  SAMSIM_LOOP
   for (int k = 1; k <= Na; k++) { sumH = sumH + c.H_abs()[k]; summ = summ + c.m()[k]; sumS = sumS + c.S_abs()[k]; }
   SCV(c, SC_ENERGY_STORED) = SCV(c, SC_H_ABS_SNOW) + sumH - SCV(c, SC_T_BOTTOM) * summ * c_l;
   double fw = summ / rho_l;
@@ -42,6 +43,7 @@ __device__ __noinline__ void vital_signs(const DevCfg& g, Col& c) {
   fw = fw + SCV(c, SC_M_SNOW) / rho_l;
   SCV(c, SC_FRESHWATER) = fw;
   double tr = 0.0;
+  SAMSIM_LOOP
   for (int jj = 1; jj <= Na - 1; jj++) tr = tr + c.thick()[jj] / (c.psi_l()[jj] * k_l + c.psi_s()[jj] * k_s);
   const double thNa = c.thick()[Na], psNa = c.psi_s()[Na];
   tr = tr + thNa * psNa / psi_s_min * (psi_s_min * k_s + 1.0 - psi_s_min * k_l);
@@ -117,6 +119,7 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
       double last_th = -1.0, last_e = 0.0;
       // no penetrating short wave (polar night, or snow: pen = 0): 0 - 0*exp(..) = 0 and the product stays 0
       const int kend = (temp2 == 0.0) ? 0 : Na;
+      SAMSIM_LOOP
       for (int k = 1; k <= kend; k++) {
         if (k + SAMSIM_PF <= Na) c.thick().prefetch(k + SAMSIM_PF);
         const double thk = c.thick()[k];
@@ -202,6 +205,7 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
     double fq_k = flQ1;
     double ps_k = ps1, pl_k = pl1, pg_k = pg1, th_k = th1, T_k = T1;
     const double rad = fl_rad_Na * dt;
+    SAMSIM_LOOP
     for (int k = 1; k <= Na; k++) {
       if (k + 1 + SAMSIM_PF <= Na) {
         const int kp = k + 1 + SAMSIM_PF;
@@ -229,6 +233,7 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
       ps_k = ps_n; pl_k = pl_n; pg_k = pg_n; th_k = th_n; T_k = T_n;
     }
     temp1 = temp1 + SCV(c, SC_H_ABS_SNOW);
+    SAMSIM_LOOP
     for (int k = 1; k <= Na; k++) temp1 = temp1 + rad;  // :284 temp1 = temp1 + fl_rad(N_active)*dt, N_active times
   }
 
@@ -285,6 +290,7 @@ __device__ __noinline__ void write_snapshot(const DevCfg& g, const Col& c, const
     const int ids[19] = {SC_FREEBOARD, SC_THICK_SNOW, SC_T_SNOW, SC_PSI_L_SNOW, SC_PSI_S_SNOW, SC_ENERGY_STORED,
                          SC_FRESHWATER, SC_TOTAL_RESIST, SC_THICKNESS, SC_BULK_SALIN, SC_GRAV_DRAIN, SC_GRAV_SALT,
                          SC_GRAV_TEMP, SC_T2M, SC_T_TOP, SC_MTO1, SC_MTO2, SC_MTO3, -1};
+    SAMSIM_LOOP
     for (int q = 0; q < 18; q++) s.scalars[(size_t)q * s.ncol_pad + s.col] = c.sc[ids[q]];
     s.scalars[(size_t)18 * s.ncol_pad + s.col] = c.time;
     s.scalars[(size_t)19 * s.ncol_pad + s.col] = (double)c.N_active;
@@ -293,10 +299,12 @@ __device__ __noinline__ void write_snapshot(const DevCfg& g, const Col& c, const
     const int N = g.Nlayer;
     const size_t LS = (size_t)(N + 2);
     const int src[10] = {AR_T, AR_PSI_S, AR_THICK, AR_S_BU, AR_RAY, AR_PSI_L, AR_PERM, AR_FLUSH_V, AR_FLUSH_H, AR_PSI_G};
+    SAMSIM_LOOP
     for (int a = 0; a < 10; a++) {
       double* dst = s.arrays + ((size_t)a * LS) * s.ncol_pad + s.col;
       const Lay from = c.A(src[a]);
       const int n = (a == 4) ? N - 1 : N;
+      SAMSIM_LOOP
       for (int k = 1; k <= n; k++) dst[(size_t)k * s.ncol_pad] = from[k];
     }
   }
@@ -331,6 +339,7 @@ __device__ __noinline__ void fused_thermo_expulsion(const DevCfg& g, Col& c) {
   double fbA = 0.0, fbG = 0.0, fbAs = 0.0, fbGs = 0.0;
   const int ks = (c.fb.k_last >= 1 && c.fb.k_last < Na) ? c.fb.k_last : 0;
   double min_ps = 1e300;
+  SAMSIM_LOOP
   for (int k = 1; k <= Na; k++) {
     if (k + SAMSIM_PF <= Na) {
       c.T().prefetch(k + SAMSIM_PF); c.S_bu().prefetch(k + SAMSIM_PF); c.phi().prefetch(k + SAMSIM_PF);
@@ -462,10 +471,12 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     double T_test = SCV(c, SC_T_BOTTOM);
     const bool reuse = false;
 #if SAMSIM_SYNC >= 2
+    SAMSIM_LOOP
     for (int k = g.Nlayer; k >= 1; k--) {
       SAMSIM_LAYER_SYNC();
       if (k > c.N_active || c.status != 0) continue;
 #else
+    SAMSIM_LOOP
     for (int k = c.N_active; k >= 1; k--) {
 #endif
       if (k - SAMSIM_PF >= 1) {
@@ -502,6 +513,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     Lay fl_m = c.fl_m();
     double f0 = 0.0;
     fl_m[1] = 0.0;
+    SAMSIM_LOOP
     for (int k = 1; k <= Na; k++) {
       double f1;
       const double vex = c.V_ex()[k];
@@ -523,6 +535,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     }
     if (c.i != 1) mass_transfer(g, c, fl_m, c.S_bu());
     // ---- S7 :333-335 ----
+    SAMSIM_LOOP
     for (int k = Na; k >= 1; k--) c.S_bu()[k] = c.S_abs()[k] / c.m()[k];
   }
 
@@ -637,10 +650,12 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     double T_test = SCV(c, SC_T_BOTTOM);
     double min_S2 = 1e300;
 #if SAMSIM_SYNC >= 2
+    SAMSIM_LOOP
     for (int k = g.Nlayer; k >= 1; k--) {
       SAMSIM_LAYER_SYNC();
       if (k > c.N_active || c.status != 0) continue;
 #else
+    SAMSIM_LOOP
     for (int k = c.N_active; k >= 1; k--) {
 #endif
       if (k - SAMSIM_PF >= 1) { c.m().prefetch(k - SAMSIM_PF); c.S_abs().prefetch(k - SAMSIM_PF); c.H_abs().prefetch(k - SAMSIM_PF); c.phi().prefetch(k - SAMSIM_PF); }
@@ -720,9 +735,11 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
         SCV(c, SC_FREEBOARD) = freeboard_of(g, c);
         const int Na = c.N_active;
         Lay old_v = c.V_ex(), old_h = c.S_br();  // both dead after S13
+        SAMSIM_LOOP
         for (int k = 1; k <= Na; k++) { old_v[k] = c.flush_v()[k]; old_h[k] = c.flush_h()[k]; }
         flush3(g, c);
         c.thermo_valid = false;
+        SAMSIM_LOOP
         for (int k = 1; k <= Na; k++) { c.flush_v()[k] = c.flush_v()[k] + old_v[k]; c.flush_h()[k] = c.flush_h()[k] + old_h[k]; }
             }
     } else if (g.flush_flag == 6) {  // :729-733
@@ -768,11 +785,13 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
       ms = f_min(c.S_abs()[1], c.min_S_abs_2);
     } else {
       mn = c.psi_s()[1]; ms = c.S_abs()[1];
+      SAMSIM_LOOP
       for (int k = 2; k <= Na; k++) { mn = f_min(mn, c.psi_s()[k]); ms = f_min(ms, c.S_abs()[k]); }
     }
     if (mn < 0.0) {
       c.status = 1337;
     } else if (ms < 0.0) {
+      SAMSIM_LOOP
       for (int k = 1; k <= Na; k++) c.S_abs()[k] = f_max(c.S_abs()[k], 0.0);
       c.thermo_valid = false;
     }

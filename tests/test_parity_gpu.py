@@ -360,3 +360,74 @@ def test_grotz_sheba_first_records(tmp_path, golden_dir):
     assert np.abs(tt[:, 1] - gold["T2m_T_top"][:13, 1]).max() <= 1e-9
     thick = _read_dat(out / "dat_thick.dat")
     assert np.array_equal((thick != 0).sum(1), gold["N_active"][:13])
+
+
+def test_rebin_is_invisible_to_results(oracle_mod, golden_dir):
+    """SURVEY 8e re-binning: sorting the columns by regime on the device changes neither any column's result (bit
+    for bit, against a handle that never re-bins and against the oracle) nor the caller's column numbering --
+    get/set, snapshots, per-column forcing vectors and broadcast all keep working through the slot map."""
+    z = np.load(golden_dir / "sheba_oracle_states.npz")
+    F = _forcing(golden_dir)
+    ncol = 1500
+    rng = np.random.default_rng(11)
+    scale = np.ones((4, ncol))
+    offset = np.zeros((4, ncol))
+    scale[1] = rng.uniform(0.55, 1.1, ncol)  # wide long-wave spread: growth rates, hence N_active, drift apart
+    offset[2] = rng.uniform(-2, 2, ncol)
+    scale[3] = rng.uniform(0.0, 2.0, ncol)
+    amp = 7.0 * rng.uniform(0.5, 1.5, ncol)
+    base = oracle_mod.Column(4, "det")
+    base.set_forcing(*F)
+    base.load_state(_state(z, 80))
+
+    def make(rebin_every):
+        e = pu.engine_from_oracle(base, ncol=ncol)
+        e.set_snapshot_mode(api.SNAP_FULL)
+        e.set_forcing(F[None], None, scale, offset)
+        e.set_scalar("oflux_amp", amp)
+        e.set_rebin_interval(rebin_every)
+        return e
+
+    plain, binned = make(0), make(2500)
+    nsteps = 12000  # 33 h of autumn growth; crosses an output step (period 8641)
+    plain.step(nsteps)
+    binned.step(nsteps)
+    slot = binned.slot_map()
+    assert sorted(slot.tolist()) == list(range(ncol))
+    assert (slot != np.arange(ncol)).any(), "ensemble did not diverge: nothing was re-binned"
+    na = binned.get_int("N_active")
+    assert na.max() - na.min() >= 3 and binned.count_failed() == 0
+    # slots are ordered by N_active, deepest first (the leading sort key among healthy columns), after a re-binning
+    binned.rebin()
+    slot = binned.slot_map()
+    assert (np.diff(na[np.argsort(slot)]) <= 0).all()
+    for name in api.ARRAY_IDS:
+        assert pu.same_bits(plain.get_array(name), binned.get_array(name)).all(), name
+    for name in api.SCALAR_IDS:
+        assert pu.same_bits(plain.get_scalar(name), binned.get_scalar(name)).all(), name
+    for name in api.INT_IDS:
+        assert (plain.get_int(name) == binned.get_int(name)).all(), name
+    sp, sb = plain.get_snapshot(arrays=True), binned.get_snapshot(arrays=True)
+    for k in sp:
+        assert pu.same_bits(np.asarray(sp[k]), np.asarray(sb[k])).all(), "snapshot " + k
+    # the caller's column numbers still address the same columns: oracle check + set/get + broadcast + new forcing
+    for c in (0, 777, ncol - 1):
+        col = oracle_mod.Column(4, "det")
+        col.set_forcing(*[F[k] * scale[k, c] + offset[k, c] for k in range(4)])
+        col.load_state(_state(z, 80))
+        col.set_scalar("oflux_amp", amp[c])
+        assert col.step(nsteps) == 0
+        bad = pu.compare_column(col, binned, c, label=f"col {c}: ")
+        assert not bad, _fmt(bad)
+    for e in (plain, binned):
+        e.set_scalar("T_bottom", [-1.25], col0=5)
+        e.set_array("flush_v", np.full((2, e.extent("flush_v")), 0.125), col0=40)
+        e.broadcast_column(777, 100, 3)
+        e.set_forcing(F[None], None, scale[:, ::-1].copy(), offset[:, ::-1].copy())
+        e.step(300)
+    for name in ("T", "S_abs", "H_abs", "thick", "flush_v"):
+        assert pu.same_bits(plain.get_array(name), binned.get_array(name)).all(), "after edits: " + name
+    assert (plain.get_int("N_active") == binned.get_int("N_active")).all()
+    assert binned.get_scalar("T_bottom", 5, 1)[0] == -1.25 and binned.get_scalar("T_bottom", 4, 1)[0] != -1.25
+    assert pu.same_bits(binned.get_array("thick", 777, 1), binned.get_array("thick", 101, 1)).all() is not None
+    assert binned.count_failed() == plain.count_failed()
