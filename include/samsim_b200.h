@@ -210,6 +210,14 @@ int samsim_b200_set_rebin_interval(samsim_handle_t h, int64_t nsteps);
 /* slot_of_col[c] = position of column c in the device arrays (identity until the first re-binning) */
 int samsim_b200_get_slot_map(samsim_handle_t h, int32_t* slot_of_col);
 
+/* ---- checkpoint / restart ------------------------------------------------------
+ * The reference can only start from init(testcase) (mo_init.f90:62); a year of 1 M columns wants restarts.
+ * save: every state array, scalar and int of every column plus the clock, in the caller's column order.
+ * load: into a handle created with the same config and column count (else SAMSIM_ERR_CONFIG); forcing tables are
+ * inputs and must be set again.  A restarted run continues bit-identically. */
+int samsim_b200_save_checkpoint(samsim_handle_t h, const char* path);
+int samsim_b200_load_checkpoint(samsim_handle_t h, const char* path);
+
 /* raw device pointers for zero-copy interop (torch): arrays[array_id][k][ncol_pad], k = 0..Nlayer+1; the column
  * index is the SLOT (samsim_b200_get_slot_map) once the handle has been re-binned */
 int samsim_b200_device_layout(samsim_handle_t h, void** arrays, void** scalars, void** ints, int64_t* ncol_pad,

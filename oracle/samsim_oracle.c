@@ -1316,6 +1316,38 @@ static void sub_test4(sam_col* c) {
   c->fl_q_bottom = -c->oflux_amp * M_SIN(c->time * (2.0 * pi_sp) / (86400.0 * 365.0)) + c->oflux_amp;
 }
 
+/* sub_test2, mo_testcase_specifics.f90:92-101 */
+static void sub_test2(sam_col* c) {
+  if (c->time > 86400.0 * 25.0) c->T2m = 15.0;
+  else if (c->time > 86400.0 * 15.0) c->T2m = 1.0;
+}
+
+/* sub_test9, mo_testcase_specifics.f90:105-116 */
+static void sub_test9(sam_col* c) {
+  if (c->time < (19.75 * 3600.0)) c->T2m = 0.0;
+  else if (c->time < (86400.0 * 3.0 + 2.25 * 3600.0)) c->T2m = -15.0;
+  else c->T2m = 1.0;
+}
+
+/* sub_test3, mo_testcase_specifics.f90:170-185 (the day counter it computes is unused) */
+static void sub_test3(sam_col* c) {
+  c->liquid_precip = 0.0;
+  c->solid_precip = 0.15 / 86400.0 / 356.0;
+}
+
+/* sub_test6, mo_testcase_specifics.f90:218-243 */
+static void sub_test6(sam_col* c) {
+  const real t = c->time;
+  if (t > 1714.0 * 60.0) c->T2m = -19.0;
+  else if (t > 1676.0 * 60.0) c->T2m = -5.0;
+  else if (t > 1525.0 * 60.0) c->T2m = -18.0;
+  else if (t > 1483.0 * 60.0) c->T2m = -5.0;
+  else if (t > 1385.0 * 60.0) c->T2m = -18.0;
+  else if (t > 1349.0 * 60.0) c->T2m = -5.0;
+  else if (t > 1160.0 * 60.0) c->T2m = -18.0;
+  else if (t > 1100.0 * 60.0) c->T2m = -5.0;
+}
+
 /* ==========================================================================================
  * mo_heat_fluxes.f90
  * ======================================================================================== */
@@ -1651,8 +1683,18 @@ static void one_step(sam_col* c) {
     c->T_bottom = -F32(0.0575) * Sb + F32(1.710523e-3) * M_POW(Sb, 3.0 / 2.0) - F32(2.154996e-4) * P2(Sb) -
                   F32(7.53e-4) * sum_arr(thick, 1, c->N_active - 1);
     c->styropor_flag = (int)c->styropor_input[idx];
+  } else if (c->testcase == 2) {
+    sub_test2(c);
+  } else if (c->testcase == 9) {
+    sub_test9(c);
+  } else if (c->testcase == 3) {
+    sub_test3(c);
   } else if (c->testcase == 4 || c->testcase == 7) {
     sub_test4(c);
+  } else if (c->testcase == 6) {
+    sub_test6(c);
+  } else if (c->testcase == 5 && c->i == 2) { /* :541-542 */
+    for (k = 1; k <= Nlayer; k++) S_abs[k] = 5.0 * m[k];
   }
 
   /* ---- S16 tank :573-578 ---- */
@@ -1824,7 +1866,9 @@ sam_col* sam_create(int testcase) {
   sam_col* c;
   int k;
   int is_lab = (testcase >= 101 && testcase <= 105);
-  if (!(testcase == 1 || testcase == 4 || is_lab)) return NULL;
+  if (!(testcase == 1 || testcase == 2 || testcase == 3 || testcase == 4 || testcase == 5 || testcase == 6 || testcase == 7 ||
+        testcase == 9 || is_lab))
+    return NULL; /* 8 needs Tinput.txt (not shipped, "settings are likely outdated", mo_init.f90:1453) */
   c = (sam_col*)calloc(1, sizeof(sam_col));
   c->testcase = testcase;
   /* defaults, mo_init.f90:83-132 */
@@ -1858,6 +1902,78 @@ sam_col* sam_create(int testcase) {
     c->snow_precip_flag = 1;
     c->T_bottom = -1.0; c->S_bu_bottom = 34.0;
     c->thick_0 = 0.01; c->time = 0.0; c->time_out = 86400.0; c->time_total = c->time_out * 365.0 * 4.5; c->dt = 10.0;
+    c->thick[1] = c->thick_0;
+    for (k = 1; k <= c->Nlayer; k++) c->m[k] = c->thick[k] * rho_l;
+    for (k = 1; k <= c->Nlayer; k++) c->S_abs[k] = c->S_bu_bottom * c->m[k];
+    for (k = 1; k <= c->Nlayer; k++) c->H_abs[k] = 0.0;
+    c->bgc_flag = 1;
+  } else if (testcase == 2 || testcase == 6 || testcase == 9) { /* cooling-chamber tanks, mo_init.f90:948-1042, 1278-1357, 1684-1776 */
+    if (testcase == 2) {
+      c->fl_q_bottom = 10.0; c->alpha_flux_instable = 22.0; c->alpha_flux_stable = 15.0; c->tank_depth = 1.0;
+      c->Nlayer = 100; c->N_bottom = 10; c->N_top = 3;
+    } else if (testcase == 6) {
+      c->fl_q_bottom = 35.0; c->alpha_flux_instable = 22.0; c->alpha_flux_stable = 11.0; c->tank_depth = 0.159;
+      c->Nlayer = 40; c->N_bottom = 3; c->N_top = 3;
+    } else {
+      c->fl_q_bottom = 10.0; c->alpha_flux_instable = 22.0; c->alpha_flux_stable = 15.0; c->tank_depth = 0.8;
+      c->Nlayer = 100; c->N_bottom = 10; c->N_top = 3;
+    }
+    c->N_active = 1;
+    c->N_middle = c->Nlayer - c->N_top - c->N_bottom;
+    sub_allocate(c, c->Nlayer);
+    c->tank_flag = 2; c->boundflux_flag = 3; c->grav_heat_flag = 1;
+    if (testcase == 2) {
+      c->T2m = -20.0; c->T_top = -18.0; c->T_bottom = 0.0; c->S_bu_bottom = 31.2;
+      c->thick_0 = 0.01; c->time_out = 3600.0 * 6.0; c->time_total = c->time_out * 4.0 * 30.0; c->dt = 30.0;
+    } else if (testcase == 6) {
+      c->T2m = -18.0; c->T_top = -18.0; c->T_bottom = 0.0; c->S_bu_bottom = 31.2;
+      c->thick_0 = 0.0025; c->time_out = 1800.0 / 2.0; c->time_total = c->time_out * 39.0 * 2.0 * 2.0; c->dt = 0.5;
+    } else {
+      c->T2m = -15.0; c->T_top = -10.0; c->T_bottom = -0.07; c->S_bu_bottom = 34.6;
+      c->thick_0 = 0.005; c->time_out = 3600.0 * 2.0; c->time_total = c->time_out * 12.0 * 6.0; c->dt = 10.0;
+    }
+    c->m_total = rho_l * c->tank_depth;
+    c->S_total = rho_l * c->S_bu_bottom * c->tank_depth;
+    c->thick[1] = c->thick_0;
+    for (k = 1; k <= c->Nlayer; k++) c->m[k] = c->thick[k] * rho_l;
+    for (k = 1; k <= c->Nlayer; k++) c->S_abs[k] = c->S_bu_bottom * c->m[k];
+    for (k = 1; k <= c->Nlayer; k++) c->H_abs[k] = c->m[k] * c->T_bottom;
+    c->bgc_flag = (testcase == 9) ? 1 : 2;
+  } else if (testcase == 3) { /* mo_init.f90:1045-1124: climatological forcing (notzflux), constant oceanic heat flux */
+    c->Nlayer = 20; c->N_bottom = 5; c->N_top = 5; c->N_active = 1;
+    c->N_middle = c->Nlayer - c->N_top - c->N_bottom;
+    sub_allocate(c, c->Nlayer);
+    c->atmoflux_flag = 1; c->precip_flag = 0; c->boundflux_flag = 2;
+    c->fl_q_bottom = 8.0; c->T_bottom = -1.0; c->S_bu_bottom = 34.0;
+    c->thick_0 = 0.03; c->time = 0.0; c->time_out = 86400.0 * 3.5; c->time_total = c->time_out * 54.0 * 2.0 * 2.0; c->dt = 60.0;
+    c->thick[1] = c->thick_0;
+    for (k = 1; k <= c->Nlayer; k++) c->m[k] = c->thick[k] * rho_l;
+    for (k = 1; k <= c->Nlayer; k++) c->S_abs[k] = c->S_bu_bottom * c->m[k];
+    for (k = 1; k <= c->Nlayer; k++) c->H_abs[k] = 0.0;
+    c->bgc_flag = 1;
+  } else if (testcase == 5) { /* mo_init.f90:1210-1275: top melt of a 1 m block of cold fresh ice */
+    c->Nlayer = 100; c->N_active = c->Nlayer; c->N_bottom = 10; c->N_top = 20;
+    c->N_middle = c->Nlayer - c->N_top - c->N_bottom;
+    sub_allocate(c, c->Nlayer);
+    c->boundflux_flag = 2; c->atmoflux_flag = 3; c->flush_heat_flag = 2;
+    c->flush_flag = 5; c->grav_flag = 1; c->flood_flag = 1;
+    c->fl_sw = 0.0; c->fl_rest = 7072810000.0 * sigma; /* 290._wp**4*sigma, an integer power folded at compile time */ c->fl_q_bottom = 15.0;
+    c->S_bu_bottom = 5.0; c->T_bottom = 0.;
+    c->thick_0 = 0.01; c->time = 0.0; c->time_out = 3600.0 * 3.0; c->time_total = c->time_out * 24.0 * 10.0; c->dt = 10.0;
+    for (k = 1; k <= c->Nlayer; k++) c->thick[k] = c->thick_0;
+    for (k = 1; k <= c->Nlayer; k++) c->m[k] = c->thick[k] * rho_l;
+    for (k = 1; k <= c->Nlayer; k++) c->S_abs[k] = c->m[k] * c->S_bu_bottom;
+    for (k = 1; k <= c->Nlayer; k++) c->H_abs[k] = c->m[k] * (-90.0) * c_l;
+    c->bgc_flag = 1;
+  } else if (testcase == 7) { /* mo_init.f90:1360-1448: testcase 4 with the simple parametrisations */
+    c->Nlayer = 100; c->N_bottom = 20; c->N_top = 20; c->N_active = 1;
+    c->N_middle = c->Nlayer - c->N_top - c->N_bottom;
+    sub_allocate(c, c->Nlayer);
+    c->atmoflux_flag = 2; c->precip_flag = 1; c->boundflux_flag = 2;
+    c->albedo_flag = 1; c->grav_heat_flag = 2; c->flush_heat_flag = 2;
+    c->flush_flag = 4; c->grav_flag = 3; c->flood_flag = 3;
+    c->T_bottom = -1.0; c->S_bu_bottom = 34.0;
+    c->thick_0 = 0.01; c->time = 0.0; c->time_out = 86400.0 / 2.0; c->time_total = c->time_out * 365.0 * 9.0; c->dt = 10.0;
     c->thick[1] = c->thick_0;
     for (k = 1; k <= c->Nlayer; k++) c->m[k] = c->thick[k] * rho_l;
     for (k = 1; k <= c->Nlayer; k++) c->S_abs[k] = c->S_bu_bottom * c->m[k];

@@ -159,6 +159,8 @@ def load_library() -> C.CDLL:
         "samsim_b200_last_step_ms": (C.c_int, [H, C.POINTER(C.c_float)]),
         "samsim_b200_device_layout": (C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                                 C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+        "samsim_b200_save_checkpoint": (C.c_int, [H, C.c_char_p]),
+        "samsim_b200_load_checkpoint": (C.c_int, [H, C.c_char_p]),
         "samsim_b200_rebin": (C.c_int, [H, ip]),
         "samsim_b200_set_rebin_interval": (C.c_int, [H, C.c_int64]),
         "samsim_b200_get_slot_map": (C.c_int, [H, ip]),
@@ -183,7 +185,7 @@ EXPORTED_SYMBOLS = [
     "samsim_b200_step", "samsim_b200_synchronize", "samsim_b200_steps_to_next_output",
     "samsim_b200_set_snapshot_mode", "samsim_b200_get_snapshot", "samsim_b200_get_status",
     "samsim_b200_count_failed", "samsim_b200_reduce_diag", "samsim_b200_launch_count", "samsim_b200_last_step_ms",
-    "samsim_b200_device_layout", "samsim_b200_rebin", "samsim_b200_set_rebin_interval", "samsim_b200_get_slot_map",
+    "samsim_b200_device_layout", "samsim_b200_save_checkpoint", "samsim_b200_load_checkpoint", "samsim_b200_rebin", "samsim_b200_set_rebin_interval", "samsim_b200_get_slot_map",
     "samsim_b200_kat_getT", "samsim_b200_kat_scalar", "samsim_b200_fp64_peak",
 ]
 
@@ -366,6 +368,12 @@ class Engine:
         v = C.c_int32()
         _check(self.L, self.L.samsim_b200_count_failed(self.h, C.byref(v)))
         return v.value
+
+    def save_checkpoint(self, path) -> None:
+        _check(self.L, self.L.samsim_b200_save_checkpoint(self.h, str(path).encode()))
+
+    def load_checkpoint(self, path) -> None:
+        _check(self.L, self.L.samsim_b200_load_checkpoint(self.h, str(path).encode()))
 
     def rebin(self) -> bool:
         """Sort the columns by regime on the device; column numbering seen by the caller is unchanged."""

@@ -16,6 +16,7 @@
 namespace {
 
 const double rho_l = 1028.0, c_l = 3400.0;  // mo_parameters.f90:51,53
+const double sigma_sb = 5.6704 * (double)1e-8f;  // mo_parameters.f90:59 (5.6704_wp*1e-8: the second factor is single precision)
 
 void alloc_case(samsim_host_case_t* c) {
   const int N = c->cfg.Nlayer;
@@ -80,6 +81,7 @@ int samsim_host_init_testcase(int32_t testcase, samsim_host_case_t* c) {
   g->testcase = testcase;
   double* sc = c->scalars;
   double T_top = 0.0, T_bottom = 0.0, S_bu_bottom = 0.0, fl_q_bottom = 0.0, time_out = 0.0, T2m = 0.0;
+  int N_active = 1;
   const bool lab = (testcase >= 101 && testcase <= 105);
   if (testcase == 1) {  // mo_init.f90:865-945
     g->Nlayer = 90; g->N_top = 5; g->N_bottom = 5; g->N_middle = g->Nlayer - g->N_top - g->N_bottom;
@@ -97,6 +99,77 @@ int samsim_host_init_testcase(int32_t testcase, samsim_host_case_t* c) {
     g->snow_precip_flag = 1;
     T_bottom = -1.0; S_bu_bottom = 34.0;
     g->thick_0 = 0.01; time_out = 86400.0; c->time_total = time_out * 365.0 * 4.5; g->dt = 10.0;
+    alloc_case(c);
+    c->arrays[SAMSIM_ARR_THICK][0] = g->thick_0;
+    for (int k = 0; k < g->Nlayer; k++) {
+      c->arrays[SAMSIM_ARR_M][k] = c->arrays[SAMSIM_ARR_THICK][k] * rho_l;
+      c->arrays[SAMSIM_ARR_S_ABS][k] = S_bu_bottom * c->arrays[SAMSIM_ARR_M][k];
+      c->arrays[SAMSIM_ARR_H_ABS][k] = 0.0;
+    }
+  } else if (testcase == 2 || testcase == 6 || testcase == 9) {
+    // cooling-chamber tanks: mo_init.f90:948-1042 (2), :1278-1357 (6), :1684-1776 (9)
+    double tank_depth;
+    if (testcase == 2) {
+      fl_q_bottom = 10.0; g->alpha_flux_instable = 22.0; g->alpha_flux_stable = 15.0; tank_depth = 1.0;
+      g->Nlayer = 100; g->N_bottom = 10; g->N_top = 3;
+      T2m = -20.0; T_top = -18.0; T_bottom = 0.0; S_bu_bottom = 31.2;
+      g->thick_0 = 0.01; time_out = 3600.0 * 6.0; c->time_total = time_out * 4.0 * 30.0; g->dt = 30.0;
+    } else if (testcase == 6) {
+      fl_q_bottom = 35.0; g->alpha_flux_instable = 22.0; g->alpha_flux_stable = 11.0; tank_depth = 0.159;
+      g->Nlayer = 40; g->N_bottom = 3; g->N_top = 3;
+      T2m = -18.0; T_top = -18.0; T_bottom = 0.0; S_bu_bottom = 31.2;
+      g->thick_0 = 0.0025; time_out = 1800.0 / 2.0; c->time_total = time_out * 39.0 * 2.0 * 2.0; g->dt = 0.5;
+    } else {
+      fl_q_bottom = 10.0; g->alpha_flux_instable = 22.0; g->alpha_flux_stable = 15.0; tank_depth = 0.8;
+      g->Nlayer = 100; g->N_bottom = 10; g->N_top = 3;
+      T2m = -15.0; T_top = -10.0; T_bottom = -0.07; S_bu_bottom = 34.6;
+      g->thick_0 = 0.005; time_out = 3600.0 * 2.0; c->time_total = time_out * 12.0 * 6.0; g->dt = 10.0;
+    }
+    g->N_middle = g->Nlayer - g->N_top - g->N_bottom;
+    g->tank_flag = 2; g->boundflux_flag = 3; g->grav_heat_flag = 1;
+    g->m_total = rho_l * tank_depth;
+    sc[SAMSIM_SC_S_TOTAL] = rho_l * S_bu_bottom * tank_depth;
+    alloc_case(c);
+    c->arrays[SAMSIM_ARR_THICK][0] = g->thick_0;
+    for (int k = 0; k < g->Nlayer; k++) {
+      c->arrays[SAMSIM_ARR_M][k] = c->arrays[SAMSIM_ARR_THICK][k] * rho_l;
+      c->arrays[SAMSIM_ARR_S_ABS][k] = S_bu_bottom * c->arrays[SAMSIM_ARR_M][k];
+      c->arrays[SAMSIM_ARR_H_ABS][k] = c->arrays[SAMSIM_ARR_M][k] * T_bottom;
+    }
+  } else if (testcase == 3) {  // mo_init.f90:1045-1124
+    g->Nlayer = 20; g->N_bottom = 5; g->N_top = 5; g->N_middle = g->Nlayer - g->N_top - g->N_bottom;
+    g->atmoflux_flag = 1; g->precip_flag = 0; g->boundflux_flag = 2;
+    fl_q_bottom = 8.0; T_bottom = -1.0; S_bu_bottom = 34.0;
+    g->thick_0 = 0.03; time_out = 86400.0 * 3.5; c->time_total = time_out * 54.0 * 2.0 * 2.0; g->dt = 60.0;
+    alloc_case(c);
+    c->arrays[SAMSIM_ARR_THICK][0] = g->thick_0;
+    for (int k = 0; k < g->Nlayer; k++) {
+      c->arrays[SAMSIM_ARR_M][k] = c->arrays[SAMSIM_ARR_THICK][k] * rho_l;
+      c->arrays[SAMSIM_ARR_S_ABS][k] = S_bu_bottom * c->arrays[SAMSIM_ARR_M][k];
+      c->arrays[SAMSIM_ARR_H_ABS][k] = 0.0;
+    }
+  } else if (testcase == 5) {  // mo_init.f90:1210-1275
+    g->Nlayer = 100; N_active = g->Nlayer; g->N_bottom = 10; g->N_top = 20; g->N_middle = g->Nlayer - g->N_top - g->N_bottom;
+    g->boundflux_flag = 2; g->atmoflux_flag = 3; g->flush_heat_flag = 2;
+    g->flush_flag = 5; g->grav_flag = 1; g->flood_flag = 1;
+    sc[SAMSIM_SC_FL_SW] = 0.0;
+    sc[SAMSIM_SC_FL_REST] = 7072810000.0 * sigma_sb;  // 290._wp**4*sigma
+    fl_q_bottom = 15.0; S_bu_bottom = 5.0; T_bottom = 0.;
+    g->thick_0 = 0.01; time_out = 3600.0 * 3.0; c->time_total = time_out * 24.0 * 10.0; g->dt = 10.0;
+    alloc_case(c);
+    for (int k = 0; k < g->Nlayer; k++) {
+      c->arrays[SAMSIM_ARR_THICK][k] = g->thick_0;
+      c->arrays[SAMSIM_ARR_M][k] = c->arrays[SAMSIM_ARR_THICK][k] * rho_l;
+      c->arrays[SAMSIM_ARR_S_ABS][k] = c->arrays[SAMSIM_ARR_M][k] * S_bu_bottom;
+      c->arrays[SAMSIM_ARR_H_ABS][k] = c->arrays[SAMSIM_ARR_M][k] * (-90.0) * c_l;
+    }
+  } else if (testcase == 7) {  // mo_init.f90:1360-1448
+    g->Nlayer = 100; g->N_bottom = 20; g->N_top = 20; g->N_middle = g->Nlayer - g->N_top - g->N_bottom;
+    g->atmoflux_flag = 2; g->precip_flag = 1; g->boundflux_flag = 2;
+    g->albedo_flag = 1; g->grav_heat_flag = 2; g->flush_heat_flag = 2;
+    g->flush_flag = 4; g->grav_flag = 3; g->flood_flag = 3;
+    T_bottom = -1.0; S_bu_bottom = 34.0;
+    g->thick_0 = 0.01; time_out = 86400.0 / 2.0; c->time_total = time_out * 365.0 * 9.0; g->dt = 10.0;
     alloc_case(c);
     c->arrays[SAMSIM_ARR_THICK][0] = g->thick_0;
     for (int k = 0; k < g->Nlayer; k++) {
@@ -140,10 +213,14 @@ int samsim_host_init_testcase(int32_t testcase, samsim_host_case_t* c) {
   g->time_out = time_out;
   c->i_time = (int32_t)(c->time_total / g->dt);
   g->i_time_out = (int32_t)(time_out / g->dt);
-  c->N_active = 1;
+  c->N_active = N_active;
   sc[SAMSIM_SC_T_BOTTOM] = T_bottom; sc[SAMSIM_SC_T_TOP] = T_top; sc[SAMSIM_SC_S_BU_BOTTOM] = S_bu_bottom;
   sc[SAMSIM_SC_T2M] = T2m; sc[SAMSIM_SC_FL_Q_BOTTOM] = fl_q_bottom;
-  sc[SAMSIM_SC_BULK_SALIN] = c->arrays[SAMSIM_ARR_S_ABS][0] / c->arrays[SAMSIM_ARR_M][0];
+  {
+    double sS = 0.0, sm = 0.0;  // bulk_salin = SUM(S_abs(1:N_active))/SUM(m(1:N_active)), mo_init.f90:2007
+    for (int k = 0; k < N_active; k++) { sS = sS + c->arrays[SAMSIM_ARR_S_ABS][k]; sm = sm + c->arrays[SAMSIM_ARR_M][k]; }
+    sc[SAMSIM_SC_BULK_SALIN] = sS / sm;
+  }
   sc[SAMSIM_SC_TTOP_WARM] = -5.0; sc[SAMSIM_SC_TTOP_COLD] = -10.0; sc[SAMSIM_SC_OFLUX_AMP] = 7.0;
   return SAMSIM_OK;
 }

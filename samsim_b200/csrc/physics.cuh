@@ -70,12 +70,12 @@ struct Lay {
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p + (unsigned)k * ls));
   }
 };
-#ifndef SAMSIM_PF
 // Layer loops are not unrolled: the step kernel is instruction-fetch sensitive (see step.cuh, SAMSIM_SYNC) and the
 // loads of the next layers are already in flight through the L1 prefetches below.
 #ifndef SAMSIM_LOOP
 #define SAMSIM_LOOP _Pragma("unroll 1")
 #endif
+#ifndef SAMSIM_PF
 #define SAMSIM_PF 2  // prefetch distance in layers (2 measured best on B200: 70.8 vs 69.5 M col-steps/s at 4, 64.7 at 12)
 #endif
 

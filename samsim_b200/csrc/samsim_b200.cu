@@ -441,7 +441,6 @@ int samsim_b200_create(const samsim_config_t* cfg, int32_t ncol, int32_t device,
   if (device < 0 || device >= ndev) return fail(SAMSIM_ERR_ARG, "create: bad device index");
   if (cfg->Nlayer < 3 || cfg->Nlayer != cfg->N_top + cfg->N_middle + cfg->N_bottom || cfg->N_top < 3)
     return fail(SAMSIM_ERR_CONFIG, "Nlayer must equal N_top+N_middle+N_bottom with N_top >= 3 (mo_init.f90:2014-2017)");
-  if (cfg->prescribe_flag == 2) return fail(SAMSIM_ERR_CONFIG, "prescribe_flag 2 is not implemented (SURVEY 8f-4)");
   if (!(cfg->salt_flag == 1 || cfg->salt_flag == 2)) return fail(SAMSIM_ERR_CONFIG, "salt_flag must be 1 or 2");
   if (!(cfg->dt > 0.0) || !(cfg->thick_0 > 0.0)) return fail(SAMSIM_ERR_CONFIG, "dt and thick_0 must be positive");
   CU(cudaSetDevice(device));
@@ -859,6 +858,92 @@ int samsim_b200_get_slot_map(samsim_handle_t h, int32_t* slot_of_col) {
   }
   CU(cudaMemcpyAsync(slot_of_col, h->slot_of_col, (size_t)h->ncol * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// ---- binary checkpoint / restart (the reference can only start from init) ----------------------
+// File: "SAMB2CK1", sizeof(samsim_config_t), the config, ncol, the clock, then in the caller's column order
+// arrays[id][col][extent], scalars[id][col], ints[id][col].  Forcing tables are inputs, not state: set them again.
+static const char CK_MAGIC[8] = {'S', 'A', 'M', 'B', '2', 'C', 'K', '1'};
+
+int samsim_b200_save_checkpoint(samsim_handle_t h, const char* path) {
+  if (!h || !path) return fail(SAMSIM_ERR_ARG, "save_checkpoint: bad argument");
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(SAMSIM_ERR_STATE, std::string("save_checkpoint: cannot open ") + path);
+  const int64_t cfg_size = (int64_t)sizeof(samsim_config_t), ncol = h->ncol;
+  const int64_t clock_i[3] = {h->i, h->n_time_out, h->time_counter};
+  bool ok = fwrite(CK_MAGIC, 1, 8, f) == 8 && fwrite(&cfg_size, 8, 1, f) == 1 && fwrite(&h->cfg, sizeof h->cfg, 1, f) == 1 &&
+            fwrite(&ncol, 8, 1, f) == 1 && fwrite(&h->time, 8, 1, f) == 1 && fwrite(clock_i, 8, 3, f) == 3;
+  int rc = 0;
+  const int32_t chunk = 65536;
+  std::vector<double> buf;
+  for (int id = 0; ok && !rc && id < SAMSIM_ARR_COUNT; id++) {
+    const int ext = samsim_b200_array_extent(h, id);
+    buf.resize((size_t)chunk * ext);
+    for (int64_t c0 = 0; ok && !rc && c0 < ncol; c0 += chunk) {
+      const int32_t n = (int32_t)((ncol - c0 < chunk) ? ncol - c0 : chunk);
+      rc = samsim_b200_get_array(h, id, buf.data(), (int32_t)c0, n);
+      if (!rc) ok = fwrite(buf.data(), sizeof(double), (size_t)n * ext, f) == (size_t)n * ext;
+    }
+  }
+  buf.resize((size_t)ncol);
+  for (int id = 0; ok && !rc && id < SAMSIM_SC_COUNT; id++) {
+    rc = samsim_b200_get_scalar(h, id, buf.data(), 0, (int32_t)ncol);
+    if (!rc) ok = fwrite(buf.data(), sizeof(double), (size_t)ncol, f) == (size_t)ncol;
+  }
+  std::vector<int32_t> ibuf((size_t)ncol);
+  for (int id = 0; ok && !rc && id < SAMSIM_INT_COUNT; id++) {
+    rc = samsim_b200_get_int(h, id, ibuf.data(), 0, (int32_t)ncol);
+    if (!rc) ok = fwrite(ibuf.data(), sizeof(int32_t), (size_t)ncol, f) == (size_t)ncol;
+  }
+  ok = (fclose(f) == 0) && ok;
+  if (rc) return rc;
+  if (!ok) return fail(SAMSIM_ERR_STATE, std::string("save_checkpoint: short write to ") + path);
+  return 0;
+}
+
+int samsim_b200_load_checkpoint(samsim_handle_t h, const char* path) {
+  if (!h || !path) return fail(SAMSIM_ERR_ARG, "load_checkpoint: bad argument");
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(SAMSIM_ERR_STATE, std::string("load_checkpoint: cannot open ") + path);
+  char magic[8];
+  int64_t cfg_size = 0, ncol = 0, clock_i[3];
+  samsim_config_t cfg;
+  double time = 0.0;
+  bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, CK_MAGIC, 8) == 0 && fread(&cfg_size, 8, 1, f) == 1 &&
+            cfg_size == (int64_t)sizeof(samsim_config_t) && fread(&cfg, sizeof cfg, 1, f) == 1 && fread(&ncol, 8, 1, f) == 1 &&
+            fread(&time, 8, 1, f) == 1 && fread(clock_i, 8, 3, f) == 3;
+  if (!ok) { fclose(f); return fail(SAMSIM_ERR_STATE, "load_checkpoint: not a samsim_b200 checkpoint of this version"); }
+  if (ncol != h->ncol || memcmp(&cfg, &h->cfg, sizeof cfg) != 0) {
+    fclose(f);
+    return fail(SAMSIM_ERR_CONFIG, "load_checkpoint: the handle was created with another configuration or column count");
+  }
+  int rc = 0;
+  const int32_t chunk = 65536;
+  std::vector<double> buf;
+  for (int id = 0; ok && !rc && id < SAMSIM_ARR_COUNT; id++) {
+    const int ext = samsim_b200_array_extent(h, id);
+    buf.resize((size_t)chunk * ext);
+    for (int64_t c0 = 0; ok && !rc && c0 < ncol; c0 += chunk) {
+      const int32_t n = (int32_t)((ncol - c0 < chunk) ? ncol - c0 : chunk);
+      ok = fread(buf.data(), sizeof(double), (size_t)n * ext, f) == (size_t)n * ext;
+      if (ok) rc = samsim_b200_set_array(h, id, buf.data(), (int32_t)c0, n);
+    }
+  }
+  buf.resize((size_t)ncol);
+  for (int id = 0; ok && !rc && id < SAMSIM_SC_COUNT; id++) {
+    ok = fread(buf.data(), sizeof(double), (size_t)ncol, f) == (size_t)ncol;
+    if (ok) rc = samsim_b200_set_scalar(h, id, buf.data(), 0, (int32_t)ncol);
+  }
+  std::vector<int32_t> ibuf((size_t)ncol);
+  for (int id = 0; ok && !rc && id < SAMSIM_INT_COUNT; id++) {
+    ok = fread(ibuf.data(), sizeof(int32_t), (size_t)ncol, f) == (size_t)ncol;
+    if (ok) rc = samsim_b200_set_int(h, id, ibuf.data(), 0, (int32_t)ncol);
+  }
+  fclose(f);
+  if (rc) return rc;
+  if (!ok) return fail(SAMSIM_ERR_STATE, "load_checkpoint: truncated file");
+  h->time = time; h->i = clock_i[0]; h->n_time_out = (int)clock_i[1]; h->time_counter = (int)clock_i[2];
   return 0;
 }
 

@@ -608,6 +608,25 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   }
   else if (g.grav_flag == 3 && c.N_active > 1) grav_drain_simple(g, c);
 
+  // ---- S14 prescribed salinity profile :482-497 (prescribe_flag 2) ----
+  if (g.prescribe_flag == 2) {
+    const int Na = c.N_active;
+    const double Sb = SCV(c, SC_S_BU_BOTTOM);
+    int k = Na;
+    while (k > 1 && sum_fwd(c.thick(), k, Na) < 0.15) {
+      c.S_bu()[k] = Sb - sum_fwd(c.thick(), k, Na) / 0.15 * (Sb - 4.0);
+      k = k - 1;
+    }
+    while (k > 1 && sum_fwd(c.thick(), k, Na) >= 0.15) {
+      c.S_bu()[k] = 4.0 - 4.0 * (sum_fwd(c.thick(), k, Na) - 0.15) / (sum_fwd(c.thick(), 1, Na) - 0.15);
+      k = k - 1;
+      c.S_bu()[1] = 0.0;
+    }
+    c.S_bu()[Na] = Sb;
+    SAMSIM_LOOP
+    for (int kk = 1; kk <= N; kk++) c.S_abs()[kk] = c.S_bu()[kk] * c.m()[kk];  // S_abs = S_bu*m, whole arrays
+  }
+
   }
   SAMSIM_PHASE_SYNC();
   if (c.status == 0) {  // ===== phase 5 =====
@@ -628,6 +647,29 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   } else if (g.testcase == 4 || g.testcase == 7) {  // sub_test4, mo_testcase_specifics.f90:197-202
     const double amp = SCV(c, SC_OFLUX_AMP);
     SCV(c, SC_FL_Q_BOTTOM) = -amp * det_sin(c.time * (2.0 * pi_sp) / (86400.0 * 365.0)) + amp;
+  } else if (g.testcase == 2) {  // sub_test2, mo_testcase_specifics.f90:92-101
+    if (c.time > 86400.0 * 25.0) SCV(c, SC_T2M) = 15.0;
+    else if (c.time > 86400.0 * 15.0) SCV(c, SC_T2M) = 1.0;
+  } else if (g.testcase == 9) {  // sub_test9, :105-116
+    if (c.time < (19.75 * 3600.0)) SCV(c, SC_T2M) = 0.0;
+    else if (c.time < (86400.0 * 3.0 + 2.25 * 3600.0)) SCV(c, SC_T2M) = -15.0;
+    else SCV(c, SC_T2M) = 1.0;
+  } else if (g.testcase == 3) {  // sub_test3, :170-185
+    SCV(c, SC_LIQUID_PRECIP) = 0.0;
+    SCV(c, SC_SOLID_PRECIP) = 0.15 / 86400.0 / 356.0;
+  } else if (g.testcase == 6) {  // sub_test6, :218-243
+    const double t = c.time;
+    if (t > 1714.0 * 60.0) SCV(c, SC_T2M) = -19.0;
+    else if (t > 1676.0 * 60.0) SCV(c, SC_T2M) = -5.0;
+    else if (t > 1525.0 * 60.0) SCV(c, SC_T2M) = -18.0;
+    else if (t > 1483.0 * 60.0) SCV(c, SC_T2M) = -5.0;
+    else if (t > 1385.0 * 60.0) SCV(c, SC_T2M) = -18.0;
+    else if (t > 1349.0 * 60.0) SCV(c, SC_T2M) = -5.0;
+    else if (t > 1160.0 * 60.0) SCV(c, SC_T2M) = -18.0;
+    else if (t > 1100.0 * 60.0) SCV(c, SC_T2M) = -5.0;
+  } else if (g.testcase == 5 && c.i == 2) {  // mo_grotz.f90:541-542
+    SAMSIM_LOOP
+    for (int k = 1; k <= N; k++) c.S_abs()[k] = 5.0 * c.m()[k];
   }
 
   // ---- S16 tank :573-578 ----

@@ -431,3 +431,94 @@ def test_rebin_is_invisible_to_results(oracle_mod, golden_dir):
     assert binned.get_scalar("T_bottom", 5, 1)[0] == -1.25 and binned.get_scalar("T_bottom", 4, 1)[0] != -1.25
     assert pu.same_bits(binned.get_array("thick", 777, 1), binned.get_array("thick", 101, 1)).all() is not None
     assert binned.count_failed() == plain.count_failed()
+
+
+# the remaining testcases of mo_init.f90 (no golden output exists for them: GPU vs oracle only)
+OTHER_TESTCASES = {
+    2: (40000, "cooling chamber: tank, boundflux 3, T2m steps to +1 after 15 days (sub_test2)"),
+    3: (260000, "climatological forcing (notzflux) + solid precipitation, half a year into winter (sub_test3)"),
+    5: (30000, "top melt of a 1 m block of cold fresh ice, atmoflux 3, N_active = Nlayer from the start, S_abs reset at i = 2"),
+    6: (160000, "small tank, dt 0.5 s, T2m schedule of sub_test6"),
+    9: (30000, "cooling chamber with the T2m schedule of sub_test9 (growth, then melt)"),
+}
+
+
+@pytest.mark.parametrize("testcase", sorted(OTHER_TESTCASES))
+def test_other_testcases_from_init(oracle_mod, testcase):
+    nsteps, _what = OTHER_TESTCASES[testcase]
+    col = oracle_mod.Column(testcase, "det")
+    eng = pu.engine_from_oracle(col, ncol=2)
+    done = 0
+    for target in (1, 2, 3, nsteps // 3, nsteps):
+        n = target - done
+        assert col.step(n) == 0
+        eng.step(n)
+        done = target
+        bad = pu.compare_column(col, eng, 1, label=f"testcase {testcase} step {target}: ")
+        assert not bad, _fmt(bad)
+    if testcase != 5:
+        assert col.int("N_active") > 1, "the run never grew ice"
+
+
+def test_testcase7_simple_parametrisations(oracle_mod, golden_dir):
+    """Testcase 7 = SHEBA forcing with fl_grav_drain_simple, flush4, flood_simple and albedo_flag 1: from the
+    oracle's autumn state so that ice exists within the window."""
+    F = _forcing(golden_dir)
+    col = oracle_mod.Column(7, "det")
+    col.set_forcing(*F)
+    assert col.step(1100000) == 0  # ~127 days from 1 July: freeze-up done
+    assert col.int("N_active") > 5
+    eng = pu.engine_from_oracle(col, ncol=2)
+    eng.set_forcing(F[None])
+    for n in (1, 2000, 30000):
+        assert col.step(n) == 0
+        eng.step(n)
+        bad = pu.compare_column(col, eng, 1, label=f"testcase 7 +{n}: ")
+        assert not bad, _fmt(bad)
+
+
+def test_prescribe_flag_2(oracle_mod):
+    """mo_grotz.f90:482-497: the prescribed salinity profile (no config uses it; parity with the oracle)."""
+    col = oracle_mod.Column(1, "det")
+    col.set_int("prescribe_flag", 2)
+    eng = pu.engine_from_oracle(col, ncol=2)
+    for n in (1, 5000, 40000):
+        assert col.step(n) == 0
+        eng.step(n)
+        bad = pu.compare_column(col, eng, 0, label=f"prescribe +{n}: ")
+        assert not bad, _fmt(bad)
+    assert col.int("N_active") > 10
+
+
+def test_checkpoint_restart_is_bit_identical(oracle_mod, golden_dir, tmp_path):
+    """save -> new handle -> load continues exactly like the uninterrupted run (also across a
+    re-binning, which must not leak into the file)."""
+    z = np.load(golden_dir / "sheba_oracle_states.npz")
+    F = _forcing(golden_dir)
+    ncol = 600
+    rng = np.random.default_rng(3)
+    scale = np.ones((4, ncol)); offset = np.zeros((4, ncol))
+    scale[1] = rng.uniform(0.6, 1.1, ncol)
+    base = oracle_mod.Column(4, "det")
+    base.set_forcing(*F)
+    base.load_state(_state(z, 80))
+    a = pu.engine_from_oracle(base, ncol=ncol)
+    a.set_forcing(F[None], None, scale, offset)
+    a.step(6000)
+    a.rebin()
+    a.save_checkpoint(tmp_path / "ck.bin")
+    a.step(3000)
+    b = api.Engine(a.cfg, ncol, 0)
+    b.load_checkpoint(tmp_path / "ck.bin")
+    b.set_forcing(F[None], None, scale, offset)
+    b.step(3000)
+    assert a.get_clock() == b.get_clock()
+    for name in api.ARRAY_IDS:
+        assert pu.same_bits(a.get_array(name), b.get_array(name)).all(), name
+    for name in api.SCALAR_IDS:
+        assert pu.same_bits(a.get_scalar(name), b.get_scalar(name)).all(), name
+    for name in api.INT_IDS:
+        assert (a.get_int(name) == b.get_int(name)).all(), name
+    other = api.Engine(a.cfg, ncol + 1, 0)
+    with pytest.raises(api.SamsimError):
+        other.load_checkpoint(tmp_path / "ck.bin")
