@@ -17,7 +17,7 @@ _BUILD = _HERE / "_build"
 
 ARRAY_NAMES = [
     "H", "H_abs", "fl_Q", "T", "S_bu", "S_abs", "S_br", "thick", "m", "fl_m", "V_ex", "phi", "psi_s", "psi_l",
-    "psi_g", "ray", "perm", "flush_v", "flush_h", "flush_v_old", "flush_h_old", "fl_rad",
+    "psi_g", "ray", "perm", "flush_v", "flush_h", "flush_v_old", "flush_h_old", "fl_rad", "bgc_abs1", "bgc_abs2",
 ]
 SCALAR_NAMES = [
     "dt", "thick_0", "time", "freeboard", "T_freeze", "time_out", "time_total", "T_bottom", "T_top", "S_bu_bottom",
@@ -27,14 +27,14 @@ SCALAR_NAMES = [
     "grav_drain", "grav_salt", "grav_temp", "melt_thick", "melt_thick_snow", "melt_thick_snow_old",
     "melt_thick_output1", "melt_thick_output2", "melt_thick_output3", "alpha_flux_instable", "alpha_flux_stable",
     "m_total", "S_total", "tank_depth", "melt_err", "max_flux_plate", "k_snow_flush", "k_styropor", "ttop_warm",
-    "ttop_cold", "oflux_amp",
+    "ttop_cold", "oflux_amp", "bgc_bottom1", "bgc_bottom2", "bgc_total1", "bgc_total2",
 ]
 INT_NAMES = [
     "testcase", "Nlayer", "N_top", "N_middle", "N_bottom", "N_active", "i", "i_time", "i_time_out", "n_time_out",
     "time_counter", "length_input", "styropor_flag", "atmoflux_flag", "grav_flag", "prescribe_flag",
     "grav_heat_flag", "flush_heat_flag", "turb_flag", "salt_flag", "boundflux_flag", "flush_flag", "flood_flag",
     "bottom_flag", "debug_flag", "precip_flag", "harmonic_flag", "tank_flag", "albedo_flag", "lab_snow_flag",
-    "freeboard_snow_flag", "snow_flush_flag", "snow_precip_flag", "bgc_flag", "status",
+    "freeboard_snow_flag", "snow_flush_flag", "snow_precip_flag", "bgc_flag", "N_bgc", "status",
 ]
 
 
@@ -161,7 +161,27 @@ class Column:
         d = {n: self.array(n) for n in SNAP_ARRAYS}
         d.update({n: self.scalar(n) for n in SNAP_SCALARS})
         d["N_active"] = self.int("N_active")
+        if self.int("bgc_flag") == 2:
+            d.update(self.bgc_output())
         return d
+
+    def bgc_output(self) -> dict:
+        """bgc_bu / bgc_br rows as output_bgc writes them (mo_output.f90:156-188)."""
+        rho_l = 1028.0
+        Na, N = self.int("N_active"), self.int("Nlayer")
+        m, psi_l, thick = self.array("m"), self.array("psi_l"), self.array("thick")
+        out = {}
+        for t in range(1, self.int("N_bgc") + 1):
+            a, bottom = self.array(f"bgc_abs{t}"), self.scalar(f"bgc_bottom{t}")
+            bu, br = np.full(N, bottom), np.full(N, bottom)
+            for k in range(Na):
+                if m[k] != 0.0:
+                    bu[k] = a[k] / m[k]
+                    br[k] = a[k] / psi_l[k] / thick[k] / rho_l if (psi_l[k] != 0.0 and thick[k] != 0) else 0.0
+                else:
+                    bu[k] = br[k] = 0.0
+            out[f"bgc{t}_bu"], out[f"bgc{t}_br"] = bu, br
+        return out
 
     # --- access --------------------------------------------------------------------------
     def array(self, name: str) -> np.ndarray:

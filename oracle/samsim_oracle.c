@@ -447,6 +447,44 @@ static void expulsion_flux(sam_col* c) {
  * ======================================================================================== */
 
 /* fl_grav_drain, mo_grav_drain.f90:74-201 (bgc bookkeeping omitted: no feedback on H,S,m) */
+/* fl_brine_bgc(i,j): brine moved from layer i to layer j this step (i or j = N_active+1: the ocean) */
+#define FB(c, i, j) ((c)->fl_brine_bgc[(size_t)(i) * ((c)->Nlayer + 2) + (j)])
+
+/* bgc_advection, mo_mass.f90:150-209: upwind advection of the tracers with the recorded brine fluxes; each flux
+ * is limited to a third of the layer's content */
+static void bgc_advection(sam_col* c) {
+  const int N_active = c->N_active, Nlayer = c->Nlayer, N_bgc = c->N_bgc;
+  real *psi_l = c->psi_l, *thick = c->thick;
+  int i, j, k;
+  for (k = 1; k <= N_bgc; k++) {
+    real* bgc_abs = c->bgc_abs[k];
+    real* bgc_temp = c->scr[3];
+    real* bgc_br = c->scr[4];
+    real flux;
+    for (i = 1; i <= Nlayer; i++) bgc_temp[i] = bgc_abs[i];
+    for (i = 1; i <= N_active; i++) bgc_br[i] = bgc_abs[i] / (r_max(psi_l[i] * thick[i] * rho_l, 0.000000000000001)); /* :171 */
+    /* tracers are independent: the reference's (i,j,k) nest visits, for each tracer, the cells in the same (i,j) order */
+    for (i = 1; i <= N_active; i++) { /* :179-190 internal flows */
+      for (j = 1; j <= N_active; j++) {
+        /* an empty cell moves MIN(0*br, abs/3) = 0 unless the layer's content is negative: x -/+ 0 leaves x as it is */
+        if (FB(c, i, j) == 0.0 && bgc_abs[i] >= 0.0 && bgc_br[i] == bgc_br[i] && bgc_br[i] - bgc_br[i] == 0.0) continue;
+        flux = r_min(FB(c, i, j) * bgc_br[i], bgc_abs[i] / 3.0);
+        bgc_temp[i] = bgc_temp[i] - flux;
+        bgc_temp[j] = bgc_temp[j] + flux;
+      }
+    }
+    for (i = 1; i <= N_active; i++) { /* :193-199 flows which leave the domain */
+      flux = r_min(FB(c, i, N_active + 1) * bgc_br[i], bgc_abs[i] / 3.0);
+      bgc_temp[i] = bgc_temp[i] - flux;
+    }
+    for (j = 1; j <= N_active; j++) { /* :202-208 flows which enter the domain */
+      flux = FB(c, N_active + 1, j) * c->bgc_bottom[k];
+      bgc_temp[j] = bgc_temp[j] + flux;
+    }
+    for (i = 1; i <= Nlayer; i++) bgc_abs[i] = bgc_temp[i];
+  }
+}
+
 static void fl_grav_drain(sam_col* c) {
   const int N_active = c->N_active, Nlayer = c->Nlayer;
   real *S_br = c->S_br, *S_bu = c->S_bu, *psi_l = c->psi_l, *psi_s = c->psi_s, *thick = c->thick, *S_abs = c->S_abs,
@@ -521,6 +559,11 @@ static void fl_grav_drain(sam_col* c) {
 
   fl_m[1] = 0.0; /* :176-177 */
   for (k = 1; k <= N_active; k++) fl_m[k + 1] = fl_up[k];
+
+  if (c->bgc_flag == 2) { /* :178-185 (sic: column N_active+1 is assigned from column N_active) */
+    for (k = 1; k <= N_active - 1; k++) FB(c, k, N_active + 1) = FB(c, k, N_active) + fl_down[k];
+    for (k = 1; k <= N_active; k++) FB(c, k + 1, k) = FB(c, k + 1, k) + fl_up[k];
+  }
 
   mass_transfer(c, T, H_abs, S_abs, S_bu, fl_m); /* :188 */
 
@@ -895,6 +938,10 @@ static void flood(sam_col* c) {
     c->m_snow = c->m_snow - shift / c->thick_snow * c->m_snow;
     c->thick_snow = c->thick_snow - shift;
   }
+  if (c->bgc_flag == 2) { /* :140-144 */
+    FB(c, N_active, 1) = FB(c, N_active, 1) + flood_brine;
+    FB(c, N_active + 1, N_active) = FB(c, N_active + 1, N_active) + flood_brine;
+  }
   (void)Nlayer;
 }
 
@@ -982,6 +1029,12 @@ static void flush3(sam_col* c) {
   flush_v[N_active] = flush_v[N_active - 1];
   flush_h[N_active] = 0.0;
 
+  if (c->bgc_flag == 2) { /* :168-175; SUM(flush_h(:)) runs over the N_active-long dummy */
+    for (k = 1; k <= N_active - 1; k++) FB(c, k, N_active) = FB(c, k, N_active) + flush_h[k];
+    FB(c, N_active, N_active + 1) = FB(c, N_active, N_active + 1) + sum_arr(flush_h, 1, N_active);
+    for (k = 1; k <= N_active; k++) FB(c, k, k + 1) = FB(c, k, k + 1) + flush_v[k];
+  }
+
   fl_m[1] = 0.0; /* :179-180 */
   for (k = 1; k <= N_active; k++) fl_m[k + 1] = -flush_v[k];
 
@@ -1049,20 +1102,30 @@ static void flush4(sam_col* c) {
  * ======================================================================================== */
 
 /* top_melt, mo_layer_dynamics.f90:191-326 */
+/* tracers in the layer-dynamics routines: bgc_temp / bgc_bulk of the reference (the routines work on bgc_abs in place:
+ * bgc_temp is copied back unconditionally at their end) */
+#define BGC_DECL(c) real* bgc[3] = {NULL, (c)->bgc_abs[1], (c)->bgc_abs[2]}; real* bulk[3] = {NULL, (c)->scr[6], (c)->scr[7]}; \
+  const int n_bgc_ = ((c)->bgc_flag == 2) ? (c)->N_bgc : 0
+#define BGC_EACH(q) for ((q) = 1; (q) <= n_bgc_; (q)++)
+
 static void top_melt(sam_col* c, real* rho, real* H, real* S_bu) {
   const int Nlayer = c->Nlayer, N_middle = c->N_middle, N_top = c->N_top;
   const real thick_0 = c->thick_0;
   real *m = c->m, *S_abs = c->S_abs, *H_abs = c->H_abs, *thick = c->thick;
   real loss_m, loss_S_abs, loss_H_abs, shift;
-  int k, kmax;
+  real loss_bgc[3] = {0.0, 0.0, 0.0};
+  int k, kmax, q;
+  BGC_DECL(c);
   for (k = 1; k <= c->N_active; k++) { /* :218-223 */
     rho[k] = m[k] / thick[k];
     S_bu[k] = S_abs[k] / m[k];
     H[k] = H_abs[k] / m[k];
+    BGC_EACH(q) bulk[q][k] = bgc[q][k] / m[k];
   }
   m[1] = m[1] + m[2]; /* :231-235 */
   S_abs[1] = S_abs[1] + S_abs[2];
   H_abs[1] = H_abs[1] + H_abs[2];
+  BGC_EACH(q) bgc[q][1] = bgc[q][1] + bgc[q][2];
   thick[1] = thick[1] + thick[2];
 
   kmax = (N_top - 1 < c->N_active - 1) ? N_top - 1 : c->N_active - 1;
@@ -1070,18 +1133,22 @@ static void top_melt(sam_col* c, real* rho, real* H, real* S_bu) {
     m[k] = rho[k + 1] * thick_0;
     S_abs[k] = S_bu[k + 1] * rho[k + 1] * thick_0;
     H_abs[k] = H[k + 1] * rho[k + 1] * thick_0;
+    BGC_EACH(q) bgc[q][k] = bulk[q][k + 1] * rho[k + 1] * thick_0;
   }
 
   if (c->N_active <= N_top) { /* :247-254 */
     m[c->N_active] = 0.0; S_abs[c->N_active] = 0.0; H_abs[c->N_active] = 0.0; thick[c->N_active] = 0.0;
+    BGC_EACH(q) bgc[q][c->N_active] = 0.0;
     c->N_active = c->N_active - 1;
   } else if (c->N_active > N_top && c->N_active <= Nlayer && thick[N_top + 1] / thick_0 < 1.00001) { /* :256-273 */
     for (k = N_top; k <= c->N_active - 1; k++) {
       m[k] = rho[k + 1] * thick_0;
       S_abs[k] = S_bu[k + 1] * rho[k + 1] * thick_0;
       H_abs[k] = H[k + 1] * rho[k + 1] * thick_0;
+      BGC_EACH(q) bgc[q][k] = bulk[q][k + 1] * rho[k + 1] * thick_0;
     }
     m[c->N_active] = 0.0; S_abs[c->N_active] = 0.0; H_abs[c->N_active] = 0.0; thick[c->N_active] = 0.0;
+    BGC_EACH(q) bgc[q][c->N_active] = 0.0;
     c->N_active = c->N_active - 1;
   }
 
@@ -1089,20 +1156,25 @@ static void top_melt(sam_col* c, real* rho, real* H, real* S_bu) {
     loss_m = thick_0 * rho[N_top + 1];
     loss_S_abs = loss_m * S_bu[N_top + 1];
     loss_H_abs = loss_m * H[N_top + 1];
+    BGC_EACH(q) loss_bgc[q] = loss_m * bulk[q][N_top + 1];
     m[N_top] = loss_m;
     S_abs[N_top] = loss_S_abs;
     H_abs[N_top] = loss_H_abs;
+    BGC_EACH(q) bgc[q][N_top] = loss_bgc[q];
     for (k = N_top + 1; k <= N_middle + N_top; k++) {
       m[k] = m[k] - loss_m;
       H_abs[k] = H_abs[k] - loss_H_abs;
       S_abs[k] = S_abs[k] - loss_S_abs;
+      BGC_EACH(q) bgc[q][k] = bgc[q][k] - loss_bgc[q];
       shift = thick_0 * (double)(float)(N_middle - k + N_top) / (double)(float)(N_middle); /* :293 */
       loss_m = shift * rho[k + 1];
       loss_S_abs = loss_m * S_bu[k + 1];
       loss_H_abs = loss_m * H[k + 1];
+      BGC_EACH(q) loss_bgc[q] = loss_m * bulk[q][k + 1];
       m[k] = m[k] + loss_m;
       H_abs[k] = H_abs[k] + loss_H_abs;
       S_abs[k] = S_abs[k] + loss_S_abs;
+      BGC_EACH(q) bgc[q][k] = bgc[q][k] + loss_bgc[q];
     }
     for (k = N_top + 1; k <= N_top + N_middle; k++) thick[k] = thick[k] - thick_0 / (double)(float)(N_middle); /* :311-313 */
   }
@@ -1115,29 +1187,36 @@ static void bottom_melt(sam_col* c, real* rho, real* H, real* S_bu) {
   const int Nlayer = c->Nlayer, N_middle = c->N_middle, N_top = c->N_top;
   real *m = c->m, *S_abs = c->S_abs, *H_abs = c->H_abs, *thick = c->thick;
   real loss_m = 0.0, loss_S_abs = 0.0, loss_H_abs = 0.0, shift;
-  int k;
+  real loss_bgc[3] = {0.0, 0.0, 0.0};
+  int k, q;
+  BGC_DECL(c);
   for (k = N_top + 1; k <= Nlayer; k++) { /* :364-370 */
     rho[k] = m[k] / thick[k];
     S_bu[k] = S_abs[k] / m[k];
     H[k] = H_abs[k] / m[k];
+    BGC_EACH(q) bulk[q][k] = bgc[q][k] / m[k];
   }
   for (k = N_top + 1; k <= N_top + N_middle; k++) { /* :378-400 */
     m[k] = m[k] + loss_m;
     H_abs[k] = H_abs[k] + loss_H_abs;
     S_abs[k] = S_abs[k] + loss_S_abs;
+    BGC_EACH(q) bgc[q][k] = bgc[q][k] + loss_bgc[q];
     shift = thick[Nlayer] * (k - N_top) / (double)(float)(N_middle); /* :387 */
     loss_m = shift * rho[k];
     loss_H_abs = loss_m * H[k];
     loss_S_abs = loss_m * S_bu[k];
+    BGC_EACH(q) loss_bgc[q] = loss_m * bulk[q][k];
     m[k] = m[k] - loss_m;
     H_abs[k] = H_abs[k] - loss_H_abs;
     S_abs[k] = S_abs[k] - loss_S_abs;
+    BGC_EACH(q) bgc[q][k] = bgc[q][k] - loss_bgc[q];
   }
   for (k = N_top + 1; k <= N_top + N_middle; k++) thick[k] = thick[k] - thick[Nlayer] / (double)(float)(N_middle); /* :405-407 */
   for (k = N_top + N_middle + 1; k <= Nlayer; k++) { /* :410-415 */
     H_abs[k] = rho[k - 1] * thick[k] * H[k - 1];
     S_abs[k] = rho[k - 1] * thick[k] * S_bu[k - 1];
     m[k] = rho[k - 1] * thick[k];
+    BGC_EACH(q) bgc[q][k] = rho[k - 1] * thick[k] * bulk[q][k - 1];
   }
 }
 
@@ -1146,33 +1225,41 @@ static void bottom_growth(sam_col* c, real* rho, real* H, real* S_bu) {
   const int Nlayer = c->Nlayer, N_middle = c->N_middle, N_top = c->N_top, N_bottom = c->N_bottom;
   real *m = c->m, *S_abs = c->S_abs, *H_abs = c->H_abs, *thick = c->thick;
   real gain_m = 0.0, gain_S_abs = 0.0, gain_H_abs = 0.0, shift;
-  int k;
+  real gain_bgc[3] = {0.0, 0.0, 0.0};
+  int k, q;
+  BGC_DECL(c);
   for (k = N_top + 1; k <= N_top + N_middle + 1; k++) { /* :463-468 */
     rho[k] = m[k] / thick[k];
     S_bu[k] = S_abs[k] / m[k];
     H[k] = H_abs[k] / m[k];
+    BGC_EACH(q) bulk[q][k] = bgc[q][k] / m[k];
   }
   for (k = N_top + 1; k <= N_top + N_middle; k++) { /* :476-495 */
     m[k] = m[k] - gain_m;
     H_abs[k] = H_abs[k] - gain_H_abs;
     S_abs[k] = S_abs[k] - gain_S_abs;
+    BGC_EACH(q) bgc[q][k] = bgc[q][k] - gain_bgc[q];
     shift = thick[Nlayer] * (k - N_top) / (double)(float)(N_middle); /* :483 */
     gain_m = shift * rho[k + 1];
     gain_H_abs = gain_m * H[k + 1];
     gain_S_abs = gain_m * S_bu[k + 1];
+    BGC_EACH(q) gain_bgc[q] = gain_m * bulk[q][k + 1];
     m[k] = m[k] + gain_m;
     H_abs[k] = H_abs[k] + gain_H_abs;
     S_abs[k] = S_abs[k] + gain_S_abs;
+    BGC_EACH(q) bgc[q][k] = bgc[q][k] + gain_bgc[q];
   }
   for (k = N_top + 1; k <= N_top + N_middle; k++) thick[k] = thick[k] + thick[Nlayer] / (double)(float)(N_middle); /* :498-500 */
   for (k = Nlayer - N_bottom + 1; k <= Nlayer - 1; k++) { /* :503-508 */
     H_abs[k] = H_abs[k + 1];
     S_abs[k] = S_abs[k + 1];
     m[k] = m[k + 1];
+    BGC_EACH(q) bgc[q][k] = bgc[q][k + 1];
   }
   m[Nlayer] = thick[Nlayer] * rho_l; /* :511-513 */
   H_abs[Nlayer] = m[Nlayer] * c->T_bottom * c_l;
   S_abs[Nlayer] = m[Nlayer] * c->S_bu_bottom;
+  BGC_EACH(q) bgc[q][Nlayer] = m[Nlayer] * c->bgc_bottom[q]; /* :516 */
 }
 
 /* bottom_growth_simple, mo_layer_dynamics.f90:537-561 */
@@ -1183,6 +1270,10 @@ static void bottom_growth_simple(sam_col* c) {
   m[c->N_active] = thick[c->N_active] * rho_l;
   H_abs[c->N_active] = m[c->N_active] * c->T_bottom * c_l;
   S_abs[c->N_active] = m[c->N_active] * c->S_bu_bottom;
+  if (c->bgc_flag == 2) {
+    int q;
+    for (q = 1; q <= c->N_bgc; q++) c->bgc_abs[q][c->N_active] = c->bgc_bottom[q] * m[c->N_active]; /* :557 */
+  }
 }
 
 /* bottom_melt_simple, mo_layer_dynamics.f90:573-590 */
@@ -1191,6 +1282,10 @@ static void bottom_melt_simple(sam_col* c) {
   c->m[c->N_active] = 0.0;
   c->S_abs[c->N_active] = 0.0;
   c->H_abs[c->N_active] = 0.0;
+  if (c->bgc_flag == 2) {
+    int q;
+    for (q = 1; q <= c->N_bgc; q++) c->bgc_abs[q][c->N_active] = 0.0; /* :586 */
+  }
   c->N_active = c->N_active - 1;
 }
 
@@ -1200,18 +1295,23 @@ static void top_grow(sam_col* c, real* rho, real* H, real* S_bu) {
   const real thick_0 = c->thick_0;
   real *m = c->m, *S_abs = c->S_abs, *H_abs = c->H_abs, *thick = c->thick;
   real loss_m, loss_S_abs, loss_H_abs, shift;
-  int k, kmax;
+  real loss_bgc[3] = {0.0, 0.0, 0.0};
+  int k, kmax, q;
+  BGC_DECL(c);
   for (k = 1; k <= c->N_active; k++) { /* :631-636 */
     rho[k] = m[k] / thick[k];
     S_bu[k] = S_abs[k] / m[k];
     H[k] = H_abs[k] / m[k];
+    BGC_EACH(q) bulk[q][k] = bgc[q][k] / m[k];
   }
   loss_m = thick_0 * rho[1]; /* :639-642 */
   loss_S_abs = loss_m * S_bu[1];
   loss_H_abs = loss_m * H[1];
+  BGC_EACH(q) loss_bgc[q] = loss_m * bulk[q][1];
   m[1] = m[1] - loss_m; /* :644-648 */
   S_abs[1] = S_abs[1] - loss_S_abs;
   H_abs[1] = H_abs[1] - loss_H_abs;
+  BGC_EACH(q) bgc[q][1] = bgc[q][1] - loss_bgc[q];
   thick[1] = thick[1] - thick_0;
 
   kmax = (N_top < c->N_active) ? N_top : c->N_active;
@@ -1219,6 +1319,7 @@ static void top_grow(sam_col* c, real* rho, real* H, real* S_bu) {
     m[k] = rho[k - 1] * thick_0;
     S_abs[k] = S_bu[k - 1] * rho[k - 1] * thick_0;
     H_abs[k] = H[k - 1] * rho[k - 1] * thick_0;
+    BGC_EACH(q) bgc[q][k] = bulk[q][k - 1] * rho[k - 1] * thick_0;
   }
 
   if (c->N_active <= N_top) { /* :659-665 */
@@ -1226,33 +1327,40 @@ static void top_grow(sam_col* c, real* rho, real* H, real* S_bu) {
     m[c->N_active] = rho[c->N_active - 1] * thick_0;
     S_abs[c->N_active] = S_bu[c->N_active - 1] * thick_0 * rho[c->N_active - 1];
     H_abs[c->N_active] = H[c->N_active - 1] * thick_0 * rho[c->N_active - 1];
+    BGC_EACH(q) bgc[q][c->N_active] = bulk[q][c->N_active - 1] * thick_0 * rho[c->N_active - 1];
     thick[c->N_active] = thick_0;
   } else if (c->N_active > N_top && c->N_active < Nlayer) { /* :668-680 */
     for (k = N_top + 1; k <= c->N_active; k++) {
       m[k] = rho[k - 1] * thick_0;
       S_abs[k] = S_bu[k - 1] * rho[k - 1] * thick_0;
       H_abs[k] = H[k - 1] * rho[k - 1] * thick_0;
+      BGC_EACH(q) bgc[q][k] = bulk[q][k - 1] * rho[k - 1] * thick_0;
     }
     c->N_active = c->N_active + 1;
     m[c->N_active] = rho[c->N_active - 1] * thick_0;
     S_abs[c->N_active] = S_bu[c->N_active - 1] * thick_0 * rho[c->N_active - 1];
     H_abs[c->N_active] = H[c->N_active - 1] * thick_0 * rho[c->N_active - 1];
+    BGC_EACH(q) bgc[q][c->N_active] = bulk[q][c->N_active - 1] * thick_0 * rho[c->N_active - 1];
     thick[c->N_active] = thick_0;
   } else if (c->N_active == Nlayer) { /* :682-711 */
     loss_m = thick_0 * rho[N_top];
     loss_S_abs = loss_m * S_bu[N_top];
     loss_H_abs = loss_m * H[N_top];
+    BGC_EACH(q) loss_bgc[q] = loss_m * bulk[q][N_top];
     for (k = N_top + 1; k <= N_middle + N_top; k++) {
       m[k] = m[k] + loss_m;
       H_abs[k] = H_abs[k] + loss_H_abs;
       S_abs[k] = S_abs[k] + loss_S_abs;
+      BGC_EACH(q) bgc[q][k] = bgc[q][k] + loss_bgc[q];
       shift = thick_0 * (double)(float)(N_middle - k + N_top) / (double)(float)(N_middle); /* :692 */
       loss_m = shift * rho[k];
       loss_S_abs = loss_m * S_bu[k];
       loss_H_abs = loss_m * H[k];
+      BGC_EACH(q) loss_bgc[q] = loss_m * bulk[q][k];
       m[k] = m[k] - loss_m;
       H_abs[k] = H_abs[k] - loss_H_abs;
       S_abs[k] = S_abs[k] - loss_S_abs;
+      BGC_EACH(q) bgc[q][k] = bgc[q][k] - loss_bgc[q];
     }
     for (k = N_top + 1; k <= N_top + N_middle; k++) thick[k] = thick[k] + thick_0 / (double)(float)(N_middle); /* :707-709 */
   }
@@ -1593,7 +1701,12 @@ static void one_step(sam_col* c) {
 
   /* ---- S5 brine flux due to expulsion :312-321 ---- */
   expulsion_flux(c);
-  if (c->i != 1) mass_transfer(c, T, H_abs, S_abs, S_bu, c->fl_m);
+  if (c->i != 1) {
+    mass_transfer(c, T, H_abs, S_abs, S_bu, c->fl_m);
+    if (c->bgc_flag == 2) { /* :316-320 */
+      for (k = 1; k <= c->N_active; k++) FB(c, k, k + 1) = -c->fl_m[k + 1];
+    }
+  }
 
   /* ---- S7 :333-335 ---- */
   for (k = c->N_active; k >= 1; k--) S_bu[k] = S_abs[k] / m[k];
@@ -1645,6 +1758,13 @@ static void one_step(sam_col* c) {
 
   /* ---- S12 turbulence :450-457 ---- */
   if (c->turb_flag == 2) {
+    if (c->bgc_flag == 2) { /* :451-453, mo_functions.f90:355-360: turb from the S_abs before its update */
+      const int Na = c->N_active;
+      int q;
+      const real turb = Turb_A * M_EXP(Turb_B * (-sam_func_density(c->T_bottom, c->S_bu_bottom) + sam_func_density(T[Na], S_abs[Na] / m[Na]))) * dt;
+      S_abs[Na] = S_abs[Na] - turb * (S_abs[Na] / m[Na] - c->S_bu_bottom);
+      for (q = 1; q <= c->N_bgc; q++) c->bgc_abs[q][Na] = c->bgc_abs[q][Na] - turb * (c->bgc_abs[q][Na] / m[Na] - c->bgc_bottom[q]);
+    } else
     sub_turb_flux(c->T_bottom, c->S_bu_bottom, T[c->N_active], &S_abs[c->N_active], m[c->N_active], dt);
   }
 
@@ -1700,6 +1820,11 @@ static void one_step(sam_col* c) {
   /* ---- S16 tank :573-578 ---- */
   if (c->tank_flag == 2) {
     c->S_bu_bottom = (c->S_total - sum_arr(S_abs, 1, Nlayer)) / (c->m_total - sum_arr(m, 1, Nlayer));
+    if (c->bgc_flag == 2) { /* :575-577 (sic: every tracer gets the value computed from tracer 1) */
+      int q;
+      const real v = (c->bgc_total[1] - sum_arr(c->bgc_abs[1], 1, Nlayer)) / (c->m_total - sum_arr(m, 1, Nlayer));
+      for (q = 1; q <= c->N_bgc; q++) c->bgc_bottom[q] = v;
+    }
   }
 
   /* ---- S17 heat fluxes :584 ---- */
@@ -1796,6 +1921,12 @@ static void one_step(sam_col* c) {
     c->flush_h[k] = c->flush_h[k] + c->flush_h_old[k];
   }
 
+  /* ---- S22 tracer advection :742-747 ---- */
+  if (c->bgc_flag == 2) {
+    bgc_advection(c);
+    memset(c->fl_brine_bgc, 0, sizeof(real) * (size_t)(Nlayer + 2) * (size_t)(Nlayer + 2));
+  }
+
   /* ---- S23 layer dynamics :755-795 ---- */
   if (c->N_active > 1) {
     if (phi[c->N_active] > psi_s_min || phi[c->N_active - 1] <= psi_s_min / 2.0 || thick[1] / c->thick_0 > 1.5 ||
@@ -1810,6 +1941,10 @@ static void one_step(sam_col* c) {
         H[c->N_active + 1] = 0.0;
         psi_l[c->N_active + 1] = 1.0;
         psi_s[c->N_active + 1] = 0.0;
+        if (c->bgc_flag == 2) { /* :778-780 */
+          int q;
+          for (q = 1; q <= c->N_bgc; q++) c->bgc_abs[q][c->N_active + 1] = 0.0;
+        }
       }
     }
   } else {
@@ -1860,6 +1995,9 @@ static void sub_allocate(sam_col* c, int Nlayer) { /* mo_init.f90:2040-2088 */
     int q;
     for (q = 0; q < 8; q++) c->scr[q] = alloc_arr(Nlayer + 1); /* automatic arrays of the callees */
   }
+  /* sub_allocate_bgc (mo_init.f90:2093-2110); allocated for every column so that bgc_flag can be switched on by a test */
+  c->bgc_abs[0] = NULL; c->bgc_abs[1] = alloc_arr(Nlayer + 1); c->bgc_abs[2] = alloc_arr(Nlayer + 1);
+  c->fl_brine_bgc = (real*)calloc((size_t)(Nlayer + 2) * (size_t)(Nlayer + 2), sizeof(real));
 }
 
 sam_col* sam_create(int testcase) {
@@ -1893,7 +2031,10 @@ sam_col* sam_create(int testcase) {
     c->m[1] = c->thick[1] * rho_l;
     c->S_abs[1] = c->S_bu_bottom * c->m[1];
     c->H_abs[1] = c->m[1] * (c->T_bottom) * c_l;
-    c->bgc_flag = 2;
+    c->bgc_flag = 2; /* :921-944 */
+    c->N_bgc = 2;
+    c->bgc_bottom[1] = 400.0; c->bgc_bottom[2] = 500.0;
+    c->bgc_abs[1][1] = c->bgc_bottom[1] * c->m[1]; c->bgc_abs[2][1] = c->bgc_bottom[2] * c->m[1];
   } else if (testcase == 4) { /* mo_init.f90:1127-1207 */
     c->Nlayer = 100; c->N_bottom = 20; c->N_top = 20; c->N_active = 1;
     c->N_middle = c->Nlayer - c->N_top - c->N_bottom;
@@ -1939,6 +2080,15 @@ sam_col* sam_create(int testcase) {
     for (k = 1; k <= c->Nlayer; k++) c->S_abs[k] = c->S_bu_bottom * c->m[k];
     for (k = 1; k <= c->Nlayer; k++) c->H_abs[k] = c->m[k] * c->T_bottom;
     c->bgc_flag = (testcase == 9) ? 1 : 2;
+    if (c->bgc_flag == 2) { /* :1016-1040 (2: two tracers), :1331-1355 (6: one tracer) */
+      int q;
+      c->N_bgc = (testcase == 2) ? 2 : 1;
+      for (q = 1; q <= c->N_bgc; q++) {
+        c->bgc_bottom[q] = 385.0;
+        c->bgc_total[q] = c->bgc_bottom[q] * rho_l * c->tank_depth;
+        c->bgc_abs[q][1] = c->bgc_bottom[q] * c->m[1];
+      }
+    }
   } else if (testcase == 3) { /* mo_init.f90:1045-1124: climatological forcing (notzflux), constant oceanic heat flux */
     c->Nlayer = 20; c->N_bottom = 5; c->N_top = 5; c->N_active = 1;
     c->N_middle = c->Nlayer - c->N_top - c->N_bottom;
@@ -2032,6 +2182,7 @@ void sam_destroy(sam_col* c) {
   free(c->time_input); free(c->T2m_input); free(c->precip_input); free(c->fl_sw_input); free(c->fl_lw_input);
   free(c->Tinput); free(c->precipinput); free(c->ocean_flux_input); free(c->styropor_input);
   { int q; for (q = 0; q < 8; q++) free(c->scr[q]); }
+  free(c->bgc_abs[1]); free(c->bgc_abs[2]); free(c->fl_brine_bgc);
   free(c);
 }
 
@@ -2078,7 +2229,8 @@ static const arr_desc k_arrays[] = {
     {"fl_m", AOFF(fl_m), 1}, {"V_ex", AOFF(V_ex), 0}, {"phi", AOFF(phi), 0}, {"psi_s", AOFF(psi_s), 0},
     {"psi_l", AOFF(psi_l), 0}, {"psi_g", AOFF(psi_g), 0}, {"ray", AOFF(ray), -1}, {"perm", AOFF(perm), 0},
     {"flush_v", AOFF(flush_v), 0}, {"flush_h", AOFF(flush_h), 0}, {"flush_v_old", AOFF(flush_v_old), 0},
-    {"flush_h_old", AOFF(flush_h_old), 0}, {"fl_rad", AOFF(fl_rad), 0}, {NULL, 0, 0}};
+    {"flush_h_old", AOFF(flush_h_old), 0}, {"fl_rad", AOFF(fl_rad), 0}, {"bgc_abs1", AOFF(bgc_abs[1]), 0},
+    {"bgc_abs2", AOFF(bgc_abs[2]), 0}, {NULL, 0, 0}};
 
 static const arr_desc* find_arr(const char* name) {
   const arr_desc* d;
@@ -2134,7 +2286,9 @@ static const sc_desc k_scalars[] = {
     {"alpha_flux_instable", AOFF(alpha_flux_instable)}, {"alpha_flux_stable", AOFF(alpha_flux_stable)},
     {"m_total", AOFF(m_total)}, {"S_total", AOFF(S_total)}, {"tank_depth", AOFF(tank_depth)}, {"melt_err", AOFF(melt_err)},
     {"max_flux_plate", AOFF(max_flux_plate)}, {"k_snow_flush", AOFF(k_snow_flush)}, {"k_styropor", AOFF(k_styropor)},
-    {"ttop_warm", AOFF(ttop_warm)}, {"ttop_cold", AOFF(ttop_cold)}, {"oflux_amp", AOFF(oflux_amp)}, {NULL, 0}};
+    {"ttop_warm", AOFF(ttop_warm)}, {"ttop_cold", AOFF(ttop_cold)}, {"oflux_amp", AOFF(oflux_amp)},
+    {"bgc_bottom1", AOFF(bgc_bottom[1])}, {"bgc_bottom2", AOFF(bgc_bottom[2])}, {"bgc_total1", AOFF(bgc_total[1])},
+    {"bgc_total2", AOFF(bgc_total[2])}, {NULL, 0}};
 
 static const sc_desc k_ints[] = {
     {"testcase", AOFF(testcase)}, {"Nlayer", AOFF(Nlayer)}, {"N_top", AOFF(N_top)}, {"N_middle", AOFF(N_middle)},
@@ -2148,7 +2302,7 @@ static const sc_desc k_ints[] = {
     {"harmonic_flag", AOFF(harmonic_flag)}, {"tank_flag", AOFF(tank_flag)}, {"albedo_flag", AOFF(albedo_flag)},
     {"lab_snow_flag", AOFF(lab_snow_flag)}, {"freeboard_snow_flag", AOFF(freeboard_snow_flag)},
     {"snow_flush_flag", AOFF(snow_flush_flag)}, {"snow_precip_flag", AOFF(snow_precip_flag)}, {"bgc_flag", AOFF(bgc_flag)},
-    {"status", AOFF(status)}, {NULL, 0}};
+    {"N_bgc", AOFF(N_bgc)}, {"status", AOFF(status)}, {NULL, 0}};
 
 int sam_get_scalar(const sam_col* c, const char* name, double* out) {
   const sc_desc* d;

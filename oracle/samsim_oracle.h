@@ -70,6 +70,11 @@ struct sam_col {
   real *H, *H_abs, *fl_Q, *T, *S_bu, *S_abs, *S_br, *thick, *m, *fl_m, *V_ex, *phi, *psi_s, *psi_l, *psi_g, *ray,
       *perm, *flush_v, *flush_h, *flush_v_old, *flush_h_old, *fl_rad;
   real* scr[8]; /* scratch standing in for the callees' automatic arrays */
+  /* ---- passive tracers, bgc_flag == 2 (mo_data.f90 bgc_*; mo_init.f90 sub_allocate_bgc) ---- */
+  int N_bgc;                 /* 0..2 */
+  real* bgc_abs[3];          /* [tracer 1..2][layer 1..Nlayer] */
+  real bgc_bottom[3], bgc_total[3];
+  real* fl_brine_bgc;        /* (Nlayer+1) x (Nlayer+1), FB(i,j), 1-based */
   /* ---- forcing (atmoflux_flag==2), 1-based, length_input records ---- */
   double *time_input, *T2m_input, *precip_input, *fl_sw_input, *fl_lw_input;
   /* ---- lab forcing (testcases 101-105), 1-based ---- */

@@ -42,12 +42,17 @@ def _check_record(rec, gold, r, fields=HALF, label=""):
 def test_testcase1_full_run_matches_reference_output(oracle_mod, golden_dir):
     """Config 1: all 72 records x 90 layers of the reference's testcase-1 output."""
     gold = np.load(golden_dir / "tc1_reference.npz")
+    bgc = np.load(golden_dir / "tc1_bgc_reference.npz")
     col = oracle_mod.Column(1, "libm")
     col.record_outputs()
     assert col.step(col.int("i_time")) == 0
     assert len(col.records) == 72
     for r, rec in enumerate(col.records):
         assert rec["N_active"] == gold["N_active"][r], f"record {r}"
+        # passive tracers (bgc_flag 2, SURVEY 8f-3): dat_bgc0{1,2}.{bu,br}.dat are printed with F16.8, so these four
+        # files pin the brine fluxes of expulsion and gravity drainage and the layer shifts to 8 decimals
+        for k in ("bgc1_bu", "bgc1_br", "bgc2_bu", "bgc2_br"):
+            assert np.abs(rec[k] - bgc[k][r]).max() <= 0.5e-8 + 1e-9, (k, r)
         _check_record(rec, gold, r, label=f"record {r} ")
         vs = gold["vital_signs"][r]
         mine = [rec["energy_stored"], rec["freshwater"], rec["total_resist"], rec["thickness"], rec["bulk_salin"]]

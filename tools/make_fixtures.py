@@ -3,6 +3,7 @@
   tests/golden/forcing_era.npz      ERA-interim forcing of the 9 sites (sub_input format, mo_functions.f90:304-327):
                                     sheba: 13148 records (full testcase-4 run), other sites: first 2928 records (1 year)
   tests/golden/tc1_reference.npz    reference_output/Reference_testcase1_with_Version_2 (all 72 records)
+  tests/golden/tc1_bgc_reference.npz  its dat_bgc0{1,2}.{bu,br}.dat tracer files (72 x 90, F16.8)
   tests/golden/sheba_reference.npz  reference_output/Reference_SHEBA_with_Version_2: every record of the scalar files,
                                     every 6th record (+ the melt-onset window 320-360) of the per-layer files
 Usage: python tools/make_fixtures.py            (reference data -> fixtures)
@@ -53,8 +54,23 @@ def golden(dirname, outname, rec_sel):
     print(outname, (OUT / outname).stat().st_size)
 
 
+def bgc_golden():
+    """dat_bgc0{1,2}.{bu,br}.dat of the testcase-1 golden run: 72 records x 90 layers, F16.8 (tight pins on the
+    brine fluxes that move the passive tracers)."""
+    d = REF / 'reference_output' / 'Reference_testcase1_with_Version_2'
+    keep = {}
+    for t in (1, 2):
+        for kind in ('bu', 'br'):
+            a = np.loadtxt(d / f'dat_bgc0{t}.{kind}.dat')
+            assert a.shape == (72, 90), a.shape
+            keep[f'bgc{t}_{kind}'] = a
+    np.savez_compressed(OUT / 'tc1_bgc_reference.npz', **keep)
+    print('tc1_bgc_reference.npz', (OUT / 'tc1_bgc_reference.npz').stat().st_size)
+
+
 def main_reference():
     forcing()
+    bgc_golden()
     golden('Reference_testcase1_with_Version_2', 'tc1_reference.npz', np.arange(72))
     sel = sorted(set(range(0, 1643, 6)) | set(range(320, 361)) | {1642})
     golden('Reference_SHEBA_with_Version_2', 'sheba_reference.npz', np.array(sel))
