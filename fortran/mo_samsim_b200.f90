@@ -23,7 +23,7 @@ MODULE mo_samsim_b200
           &                salt_flag, boundflux_flag, flush_flag, flood_flag, bottom_flag, precip_flag, harmonic_flag, &
           &                tank_flag, albedo_flag, lab_snow_flag, freeboard_snow_flag, snow_flush_flag, snow_precip_flag
      INTEGER(C_INT32_T) :: i_time_out
-     INTEGER(C_INT32_T) :: reserved0
+     INTEGER(C_INT32_T) :: N_bgc
      REAL(C_DOUBLE)     :: dt, thick_0, thick_min, time_out
      REAL(C_DOUBLE)     :: alpha_flux_instable, alpha_flux_stable
      REAL(C_DOUBLE)     :: m_total
@@ -212,7 +212,7 @@ CONTAINS
     cfg%harmonic_flag = harmonic_flag;  cfg%tank_flag = tank_flag;  cfg%albedo_flag = albedo_flag
     cfg%lab_snow_flag = lab_snow_flag;  cfg%freeboard_snow_flag = freeboard_snow_flag
     cfg%snow_flush_flag = snow_flush_flag;  cfg%snow_precip_flag = snow_precip_flag
-    cfg%i_time_out = i_time_out;  cfg%reserved0 = 0
+    cfg%i_time_out = i_time_out;  cfg%N_bgc = MERGE(N_bgc, 0, bgc_flag == 2)
     cfg%dt = dt;  cfg%thick_0 = thick_0;  cfg%thick_min = thick_min;  cfg%time_out = time_out
     cfg%alpha_flux_instable = alpha_flux_instable;  cfg%alpha_flux_stable = alpha_flux_stable
     cfg%m_total = m_total

@@ -40,7 +40,7 @@ typedef enum {
   SAMSIM_ERR_ARG = -1,       /* bad argument (null pointer, range, unknown id) */
   SAMSIM_ERR_CUDA = -2,      /* CUDA runtime error; text via samsim_b200_last_error */
   SAMSIM_ERR_NO_DEVICE = -3, /* no CUDA device: there is NO CPU fallback */
-  SAMSIM_ERR_CONFIG = -4,    /* flag combination not implemented (e.g. prescribe_flag 2, bgc_flag 2 tracers) */
+  SAMSIM_ERR_CONFIG = -4,    /* configuration not accepted (inconsistent grid, unknown flag value, N_bgc > 2) */
   SAMSIM_ERR_STATE = -5      /* call order (forcing missing, snapshot disabled, ...) */
 } samsim_b200_err;
 
@@ -54,7 +54,7 @@ typedef struct {
       boundflux_flag, flush_flag, flood_flag, bottom_flag, precip_flag, harmonic_flag, tank_flag, albedo_flag,
       lab_snow_flag, freeboard_snow_flag, snow_flush_flag, snow_precip_flag;
   int32_t i_time_out;    /* INT(time_out/dt), mo_init.f90:1999: a record every i_time_out+1 steps */
-  int32_t reserved0;
+  int32_t N_bgc;         /* passive tracers: 0 = bgc_flag 1 (none); 1 or 2 = bgc_flag 2 with N_bgc tracers (mo_data.f90 bgc_*) */
   double dt, thick_0, thick_min, time_out;
   double alpha_flux_instable, alpha_flux_stable; /* mo_data.f90:132-133 */
   double m_total;        /* tank_flag 2 (mo_data.f90:195); S_total is per column (SAMSIM_SC_S_TOTAL) */
@@ -80,6 +80,8 @@ typedef enum {
   SAMSIM_ARR_FLUSH_V,   /* flush_v :55 */
   SAMSIM_ARR_FLUSH_H,   /* flush_h :55 */
   SAMSIM_ARR_FL_Q,      /* fl_Q   :37, extent Nlayer+1 */
+  SAMSIM_ARR_BGC_ABS1,  /* bgc_abs(:,1), only with N_bgc >= 1 (array_extent returns -1 otherwise) */
+  SAMSIM_ARR_BGC_ABS2,  /* bgc_abs(:,2), only with N_bgc == 2 */
   SAMSIM_ARR_COUNT
 } samsim_array_id;
 
@@ -99,6 +101,8 @@ typedef enum {
   SAMSIM_SC_TTOP_WARM,  /* -5  in sub_test1, mo_testcase_specifics.f90:46-87 */
   SAMSIM_SC_TTOP_COLD,  /* -10 in sub_test1 */
   SAMSIM_SC_OFLUX_AMP,  /* 7 W/m2 in sub_test4, mo_testcase_specifics.f90:200 */
+  SAMSIM_SC_BGC_BOTTOM1, SAMSIM_SC_BGC_BOTTOM2, /* bgc_bottom(1:2): tracer concentration of the water below */
+  SAMSIM_SC_BGC_TOTAL1, SAMSIM_SC_BGC_TOTAL2,   /* bgc_total(1:2): tank budget (tank_flag 2) */
   SAMSIM_SC_COUNT
 } samsim_scalar_id;
 
@@ -126,6 +130,8 @@ typedef enum {
 typedef enum {
   SAMSIM_SNAPARR_T = 0, SAMSIM_SNAPARR_PSI_S, SAMSIM_SNAPARR_THICK, SAMSIM_SNAPARR_S_BU, SAMSIM_SNAPARR_RAY,
   SAMSIM_SNAPARR_PSI_L, SAMSIM_SNAPARR_PERM, SAMSIM_SNAPARR_FLUSH_V, SAMSIM_SNAPARR_FLUSH_H, SAMSIM_SNAPARR_PSI_G,
+  /* rows of output_bgc (mo_output.f90:156-188): bulk and brine concentration per tracer; zero without tracers */
+  SAMSIM_SNAPARR_BGC1_BU, SAMSIM_SNAPARR_BGC1_BR, SAMSIM_SNAPARR_BGC2_BU, SAMSIM_SNAPARR_BGC2_BR,
   SAMSIM_SNAPARR_COUNT
 } samsim_snapshot_array_id;
 

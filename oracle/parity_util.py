@@ -17,7 +17,7 @@ def config_from_oracle(col) -> api.Config:
                                    "prescribe_flag", "grav_heat_flag", "flush_heat_flag", "turb_flag", "salt_flag",
                                    "boundflux_flag", "flush_flag", "flood_flag", "bottom_flag", "precip_flag",
                                    "harmonic_flag", "tank_flag", "albedo_flag", "lab_snow_flag", "freeboard_snow_flag",
-                                   "snow_flush_flag", "snow_precip_flag", "i_time_out"]}
+                                   "snow_flush_flag", "snow_precip_flag", "i_time_out", "bgc_flag", "N_bgc"]}
     st.update({n: col.scalar(n) for n in ["dt", "thick_0", "thick_min", "time_out", "alpha_flux_instable",
                                           "alpha_flux_stable", "m_total", "max_flux_plate", "k_snow_flush", "k_styropor"]})
     return api.Config.from_state(st)
@@ -38,7 +38,7 @@ def compare_column(oracle_col, eng, col: int = 0, rtol: float = 0.0, label: str 
         g = int(eng.get_int(n, col, 1)[0])
         if g != int(ost[n]):
             bad.append(f"{label}{n}: oracle {ost[n]} gpu {g}")
-    for n in CMP_ARRAYS:
+    for n in CMP_ARRAYS + [f"bgc_abs{t}" for t in range(1, eng.cfg.N_bgc + 1)]:
         g = eng.get_array(n, col, 1)[0]
         o = np.asarray(ost[n])[: len(g)]
         ok = same_bits(o, g) if rtol == 0.0 else np.isclose(o, g, rtol=rtol, atol=0.0) | same_bits(o, g)

@@ -31,26 +31,27 @@ def lib_path() -> Path:
 # ---- ids: must mirror include/samsim_b200.h ---------------------------------------------------
 ARRAY_IDS = {n: i for i, n in enumerate(
     ["m", "S_abs", "H_abs", "thick", "T", "phi", "S_bu", "psi_s", "psi_l", "psi_g", "ray", "perm", "flush_v",
-     "flush_h", "fl_Q"])}
+     "flush_h", "fl_Q", "bgc_abs1", "bgc_abs2"])}
 SCALAR_IDS = {n: i for i, n in enumerate(
     ["T_bottom", "T_top", "S_bu_bottom", "T2m", "fl_q_bottom", "psi_s_snow", "psi_l_snow", "psi_g_snow", "phi_s",
      "S_abs_snow", "H_abs_snow", "m_snow", "T_snow", "thick_snow", "liquid_precip", "solid_precip", "fl_q_snow",
      "energy_stored", "total_resist", "freshwater", "thickness", "bulk_salin", "albedo", "fl_sw", "fl_lw", "fl_rest",
      "grav_drain", "grav_salt", "grav_temp", "melt_thick", "melt_thick_snow", "melt_thick_snow_old",
      "melt_thick_output1", "melt_thick_output2", "melt_thick_output3", "freeboard", "T_freeze", "melt_err", "S_total",
-     "ttop_warm", "ttop_cold", "oflux_amp"])}
+     "ttop_warm", "ttop_cold", "oflux_amp", "bgc_bottom1", "bgc_bottom2", "bgc_total1", "bgc_total2"])}
 INT_IDS = {"N_active": 0, "status": 1, "styropor_flag": 2}
 SNAP_SCALARS = ["freeboard", "thick_snow", "T_snow", "psi_l_snow", "psi_s_snow", "energy_stored", "freshwater",
                 "total_resist", "thickness", "bulk_salin", "grav_drain", "grav_salt", "grav_temp", "T2m", "T_top",
                 "melt_thick_output1", "melt_thick_output2", "melt_thick_output3", "time", "N_active"]
-SNAP_ARRAYS = ["T", "psi_s", "thick", "S_bu", "ray", "psi_l", "perm", "flush_v", "flush_h", "psi_g"]
+SNAP_ARRAYS = ["T", "psi_s", "thick", "S_bu", "ray", "psi_l", "perm", "flush_v", "flush_h", "psi_g",
+               "bgc1_bu", "bgc1_br", "bgc2_bu", "bgc2_br"]
 SNAP_NONE, SNAP_SCALARS_ONLY, SNAP_FULL = 0, 1, 2
 
 _CFG_INT_FIELDS = ["testcase", "Nlayer", "N_top", "N_middle", "N_bottom", "atmoflux_flag", "grav_flag",
                    "prescribe_flag", "grav_heat_flag", "flush_heat_flag", "turb_flag", "salt_flag", "boundflux_flag",
                    "flush_flag", "flood_flag", "bottom_flag", "precip_flag", "harmonic_flag", "tank_flag",
                    "albedo_flag", "lab_snow_flag", "freeboard_snow_flag", "snow_flush_flag", "snow_precip_flag",
-                   "i_time_out", "reserved0"]
+                   "i_time_out", "N_bgc"]
 _CFG_DBL_FIELDS = ["dt", "thick_0", "thick_min", "time_out", "alpha_flux_instable", "alpha_flux_stable", "m_total",
                    "max_flux_plate", "k_snow_flush", "k_styropor"]
 
@@ -87,7 +88,7 @@ class Config:
     snow_flush_flag: int = 1
     snow_precip_flag: int = 1
     i_time_out: int = 0
-    reserved0: int = 0
+    N_bgc: int = 0  # passive tracers: 0 = bgc_flag 1; 1..2 = bgc_flag 2 with that many tracers
     dt: float = 0.0
     thick_0: float = 0.0
     thick_min: float = 0.0
@@ -112,6 +113,8 @@ class Config:
         for f in fields(cls):
             if f.name in st:
                 kw[f.name] = type(f.default)(st[f.name])
+        if "bgc_flag" in st:  # mo_data carries bgc_flag and N_bgc; the C config only N_bgc (0 = no tracers)
+            kw["N_bgc"] = int(st.get("N_bgc", 0)) if int(st["bgc_flag"]) == 2 else 0
         return cls(**kw)
 
 
@@ -284,8 +287,8 @@ class Engine:
     def load_column_state(self, st: dict, col: int = 0, set_clock: bool = True):
         """Load one column from a dict keyed by mo_data names (arrays 0-based, Fortran element 1 first)."""
         for name in ARRAY_IDS:
-            if name in st:
-                self.set_array(name, np.asarray(st[name], dtype=np.float64)[None, :], col0=col)
+            if name in st and self.extent(name) > 0:  # tracer arrays exist only with N_bgc > 0
+                self.set_array(name, np.asarray(st[name], dtype=np.float64)[None, :self.extent(name)], col0=col)
         for name in SCALAR_IDS:
             if name in st:
                 self.set_scalar(name, [st[name]], col0=col)
@@ -296,7 +299,7 @@ class Engine:
             self.set_clock(st["time"], st["i"], st["n_time_out"], max(int(st.get("time_counter", 1)), 1))
 
     def column_state(self, col: int = 0) -> dict:
-        d = {n: self.get_array(n, col, 1)[0] for n in ARRAY_IDS}
+        d = {n: self.get_array(n, col, 1)[0] for n in ARRAY_IDS if self.extent(n) > 0}
         d.update({n: float(self.get_scalar(n, col, 1)[0]) for n in SCALAR_IDS})
         d.update({n: int(self.get_int(n, col, 1)[0]) for n in INT_IDS})
         d.update(self.get_clock())

@@ -222,6 +222,17 @@ int samsim_host_init_testcase(int32_t testcase, samsim_host_case_t* c) {
     sc[SAMSIM_SC_BULK_SALIN] = sS / sm;
   }
   sc[SAMSIM_SC_TTOP_WARM] = -5.0; sc[SAMSIM_SC_TTOP_COLD] = -10.0; sc[SAMSIM_SC_OFLUX_AMP] = 7.0;
+  // passive tracers (bgc_flag 2): testcase 1 (mo_init.f90:921-944), 2 (:1016-1040), 6 (:1331-1355)
+  if (testcase == 1 || testcase == 2 || testcase == 6) {
+    g->N_bgc = (testcase == 6) ? 1 : 2;
+    const double tank_depth = (testcase == 2) ? 1.0 : 0.159;
+    for (int q = 0; q < g->N_bgc; q++) {
+      const double bottom = (testcase == 1) ? (q == 0 ? 400.0 : 500.0) : 385.0;
+      sc[SAMSIM_SC_BGC_BOTTOM1 + q] = bottom;
+      if (testcase != 1) sc[SAMSIM_SC_BGC_TOTAL1 + q] = bottom * rho_l * tank_depth;
+      c->arrays[SAMSIM_ARR_BGC_ABS1 + q][0] = bottom * c->arrays[SAMSIM_ARR_M][0];
+    }
+  }
   return SAMSIM_OK;
 }
 
@@ -277,11 +288,20 @@ int samsim_grotz(int32_t testcase, const char* description, const samsim_grotz_o
     }
   }
 
+  // output_begin_bgc (mo_output.f90:354-384): dat_bgc0<k>.bu.dat / .br.dat per tracer
+  FILE* Fbgc[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  for (int q = 0; q < g.N_bgc; q++) {
+    char name[32];
+    snprintf(name, sizeof name, "dat_bgc0%d.bu.dat", q + 1); Fbgc[q][0] = open_out(out, name);
+    snprintf(name, sizeof name, "dat_bgc0%d.br.dat", q + 1); Fbgc[q][1] = open_out(out, name);
+  }
+
   // ---- device ----
   samsim_handle_t h = nullptr;
   rc = samsim_b200_create(&g, opt->ncol, opt->device, &h);
   if (rc) { samsim_host_case_free(&cs); return rc; }
-  for (int a = 0; a < SAMSIM_ARR_COUNT && !rc; a++) rc = samsim_b200_set_array(h, a, cs.arrays[a], 0, 1);
+  for (int a = 0; a < SAMSIM_ARR_COUNT && !rc; a++)
+    if (samsim_b200_array_extent(h, a) > 0) rc = samsim_b200_set_array(h, a, cs.arrays[a], 0, 1);
   for (int q = 0; q < SAMSIM_SC_COUNT && !rc; q++) rc = samsim_b200_set_scalar(h, q, &cs.scalars[q], 0, 1);
   if (!rc) rc = samsim_b200_set_int(h, SAMSIM_INT_N_ACTIVE, &cs.N_active, 0, 1);
   if (!rc) rc = samsim_b200_set_clock(h, 0.0, 0, 0, 1);
@@ -335,6 +355,10 @@ int samsim_grotz(int32_t testcase, const char* description, const samsim_grotz_o
       row_ES(F.flush_v, A + (size_t)SAMSIM_SNAPARR_FLUSH_V * N, N);
       row_ES(F.flush_h, A + (size_t)SAMSIM_SNAPARR_FLUSH_H * N, N);
       row_F(F.psi_g, A + (size_t)SAMSIM_SNAPARR_PSI_G * N, N, 9, 3);
+      for (int q = 0; q < g.N_bgc; q++) {  // output_bgc, format_bgc = Nlayer x (F16.8,2x)
+        if (Fbgc[q][0]) row_F(Fbgc[q][0], A + (size_t)(SAMSIM_SNAPARR_BGC1_BU + 2 * q) * N, N, 16, 8);
+        if (Fbgc[q][1]) row_F(Fbgc[q][1], A + (size_t)(SAMSIM_SNAPARR_BGC1_BR + 2 * q) * N, N, 16, 8);
+      }
       put_ES(F.melt, ssc[SAMSIM_SNAPSC_MELT_THICK_OUTPUT1]); fputs("  ", F.melt); put_ES(F.melt, ssc[SAMSIM_SNAPSC_MELT_THICK_OUTPUT2]); fputs("  ", F.melt);
       put_ES(F.melt, ssc[SAMSIM_SNAPSC_MELT_THICK_OUTPUT3]); fputc('\n', F.melt);
       if (!opt->quiet)
@@ -344,6 +368,9 @@ int samsim_grotz(int32_t testcase, const char* description, const samsim_grotz_o
   }
   for (FILE* f : {F.T, F.psi_s, F.thick, F.S_bu, F.ray, F.psi_l, F.freeboard, F.snow, F.vital, F.grav, F.T2m, F.perm, F.flush_v, F.flush_h, F.psi_g, F.melt})
     if (f) fclose(f);
+  for (int q = 0; q < 2; q++)
+    for (int w = 0; w < 2; w++)
+      if (Fbgc[q][w]) fclose(Fbgc[q][w]);
   if (h) samsim_b200_destroy(h);
   samsim_host_case_free(&cs);
   if (rc) return rc;

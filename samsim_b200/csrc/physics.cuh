@@ -28,6 +28,7 @@ struct DevCfg {
       boundflux_flag, flush_flag, flood_flag, bottom_flag, precip_flag, harmonic_flag, tank_flag, albedo_flag,
       lab_snow_flag, freeboard_snow_flag, snow_flush_flag, snow_precip_flag;
   int i_time_out;
+  int n_bgc;  // 0: bgc_flag 1 (no tracers); 1..2: bgc_flag 2 with that many passive tracers
   double dt, thick_0, thick_min, time_out;
   double alpha_flux_instable, alpha_flux_stable, m_total;
   double max_flux_plate, k_snow_flush, k_styropor;
@@ -47,6 +48,7 @@ enum {
   SC_MTO1, SC_MTO2, SC_MTO3,
   SC_FREEBOARD, SC_T_FREEZE, SC_MELT_ERR, SC_S_TOTAL,
   SC_TTOP_WARM, SC_TTOP_COLD, SC_OFLUX_AMP,
+  SC_BGC_BOTTOM1, SC_BGC_BOTTOM2, SC_BGC_TOTAL1, SC_BGC_TOTAL2,
   SC_COUNT
 };
 // array slots: first ARR_STATE_COUNT in the order of samsim_array_id, then launch-local scratch
@@ -55,6 +57,10 @@ enum {
   AR_FLUSH_V, AR_FLUSH_H, AR_FL_Q,
   AR_STATE_COUNT,
   AR_S_BR = AR_STATE_COUNT, AR_V_EX, AR_FL_M, AR_W0, AR_W1, AR_W2, AR_W3,
+  AR_CORE_COUNT,
+  // passive tracers (allocated only when n_bgc > 0): state bgc_abs(:,1:2), then the step-local sparse form of the
+  // brine-flux matrix fl_brine_bgc (see fb_cell)
+  AR_BGC1 = AR_CORE_COUNT, AR_BGC2, AR_FB_D, AR_FB_U, AR_FB_A, AR_FB_O,
   AR_COUNT
 };
 enum { IN_N_ACTIVE = 0, IN_STATUS, IN_STYROPOR, IN_COUNT };
@@ -108,6 +114,8 @@ struct Col {
   __device__ __forceinline__ Lay w1() const { return A(AR_W1); }
   __device__ __forceinline__ Lay w2() const { return A(AR_W2); }
   __device__ __forceinline__ Lay w3() const { return A(AR_W3); }
+  __device__ __forceinline__ Lay bgc(int q) const { return A(AR_BGC1 + q); }  // q = 0, 1
+  double fb_x;  // fl_brine_bgc(N_active, 1): flooding (N_active >= 3; it is the up-cell of layer 1 when N_active == 2)
   int N_active, status, styropor_flag;
   // T, phi, S_bu of layers 2..N_active still equal what the S18 sweep of the previous step produced and
   // m, S_abs, H_abs of those layers are untouched since: the S4 sweep may reuse them (bit-identical result)
@@ -884,6 +892,7 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
     }
     double up = run;
     double S_after = Sk;
+    double fl_down_k = 0.0;
     sum_before = sum_before + Sk;
     // same && chain as :145, evaluated left to right: psi_s and m are only touched where ray exceeds ray_crit
     if (rk > ray_crit && c.psi_s()[k] > 0.001 && Sk / c.m()[k] > 0.1 && sbk > sbk1) {
@@ -891,6 +900,7 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
       const double plk = c.psi_l()[k], thk = c.thick()[k], Tk = c.T()[k];
       double flux = x_grav * (rk - ray_crit) * dt * thk;
       flux = f_min(flux, plk * rho_l * thk);
+      fl_down_k = flux;
       double Snew = Sk - flux * sbk;
       c.S_abs()[k] = Snew;
       S_after = Snew;
@@ -901,12 +911,18 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
       run = run + flux;
       up = f_min(run, plk * rho_l * thk);
     }
+    if (g.n_bgc) {  // :178-183 (sic: column N_active+1 is assigned from column N_active), fl_down(k) = this layer's flux
+      const double cellNa = (k == Na - 1) ? c.A(AR_FB_D)[k] : c.A(AR_FB_A)[k];
+      c.A(AR_FB_O)[k] = cellNa + fl_down_k;
+      c.A(AR_FB_U)[k] = c.A(AR_FB_U)[k] + up;
+    }
     if (kfirst) fl_m[k + 1] = up;            // fl_m(2:N_active+1) = fl_up(1:N_active), :177 (zeros above kfirst are not stored)
     else min_S = f_min(min_S, Sk);           // layers above the first draining layer keep this value
     sum_after = sum_after + S_after;
     sbk = sbk1;
   }
   if (kfirst) fl_m[Na + 1] = run;
+  if (g.n_bgc) c.A(AR_FB_U)[Na] = c.A(AR_FB_U)[Na] + run;  // fl_up(N_active)
   const double fl_up_Na = run;
   {
     const double S_Na = c.S_abs()[Na];  // layer N_active never drains; inactive layers hold 0
@@ -1030,6 +1046,11 @@ __device__ __noinline__ void flood(const DevCfg& g, Col& c) {
     thick_snow = thick_snow - shift;
     c.S_abs()[1] = S1; c.H_abs()[1] = H1; c.m()[1] = m1; c.thick()[1] = th1;
   }
+  if (g.n_bgc) {  // :140-144 fl_brine_bgc(N_active,1) and (N_active+1,N_active) += flood_brine
+    Lay U = c.A(AR_FB_U);
+    if (Na >= 3) c.fb_x = c.fb_x + flood_brine; else U[1] = U[1] + flood_brine;
+    U[Na] = U[Na] + flood_brine;
+  }
 }
 
 // flood_simple, mo_flood.f90:167-210
@@ -1117,6 +1138,21 @@ __device__ __noinline__ void flush3(const DevCfg& g, Col& c) {
   }
   c.flush_v()[Na] = c.flush_v()[Na - 1];
   c.flush_h()[Na] = 0.0;
+
+  if (g.n_bgc) {  // :168-175
+    Lay D = c.A(AR_FB_D), Ac = c.A(AR_FB_A);
+    double sum_h = 0.0;
+    SAMSIM_LOOP
+    for (int k = 1; k <= Na - 1; k++) {
+      const double fh = c.flush_h()[k];
+      if (k == Na - 1) D[k] = D[k] + fh; else Ac[k] = Ac[k] + fh;  // cell (N_active-1, N_active) is the down-cell
+      sum_h = sum_h + fh;
+    }
+    sum_h = sum_h + c.flush_h()[Na];
+    D[Na] = D[Na] + sum_h;
+    SAMSIM_LOOP
+    for (int k = 1; k <= Na; k++) D[k] = D[k] + c.flush_v()[k];
+  }
 
   fl_m[1] = 0.0;  // :179-180
   SAMSIM_LOOP
@@ -1393,6 +1429,183 @@ __device__ __noinline__ void top_grow(const DevCfg& g, Col& c) {
   }
 }
 
+
+// ==========================================================================================
+// Passive tracers (bgc_flag 2): mo_mass.f90:150-209 and the bgc lines of mo_layer_dynamics.f90
+// ==========================================================================================
+//
+// fl_brine_bgc is an (Nlayer+1)^2 matrix in the reference, but only these cells are ever written
+// (Na = N_active, Na+1 = the ocean):
+//   (k,k+1)  k = 1..Na    expulsion (mo_grotz.f90:316-320), flush_v (mo_flush.f90:171-173)        -> D[k]
+//   (k+1,k)  k = 1..Na    fl_up of gravity drainage (mo_grav_drain.f90:181-183), flooding (Na+1,Na) -> U[k]
+//   (k,Na)   k = 1..Na-2  flush_h (mo_flush.f90:169); for k = Na-1 this IS the cell (k,k+1) = D[k]    -> A[k]
+//   (k,Na+1) k = 1..Na-1  fl_down of gravity drainage (:179); for k = Na it is the cell D[Na]         -> O[k]
+//   (Na,1)                flooding (mo_flood.f90:141); for Na = 2 it is the cell U[1]                 -> fb_x
+// The arrays are step-local: the S5 sweep assigns D and clears U, A, O, fb_x (the reference zeroes the matrix
+// after bgc_advection, mo_grotz.f90:745).
+__device__ __forceinline__ double fb_get(const Col& c, int Na, int i, int j) {
+  if (j == i + 1 && i <= Na) return c.A(AR_FB_D)[i];
+  if (i == j + 1 && j <= Na) return c.A(AR_FB_U)[j];
+  if (j == Na && i <= Na - 2) return c.A(AR_FB_A)[i];
+  if (j == Na + 1 && i <= Na - 1) return c.A(AR_FB_O)[i];
+  if (i == Na && j == 1 && Na >= 3) return c.fb_x;
+  return 0.0;
+}
+
+// bgc_advection.  The reference visits every (i,j) pair; an empty cell moves MIN(0*br, abs/3) = 0 and x -/+ 0 is x,
+// so rows whose content is non-negative (and whose brine concentration is finite) only visit their written cells,
+// in the same ascending-j order; any other row runs the dense loop.  temp/br are the scratch arrays w0/w1.
+__device__ __noinline__ void bgc_advection(const DevCfg& g, Col& c) {
+  const int Na = c.N_active, N = g.Nlayer;
+  Lay temp = c.w0(), br = c.w1();
+  Lay D = c.A(AR_FB_D), U = c.A(AR_FB_U), Ac = c.A(AR_FB_A), O = c.A(AR_FB_O);
+  for (int q = 0; q < g.n_bgc; q++) {
+    Lay x = c.bgc(q);
+    const double bottom = SCV(c, SC_BGC_BOTTOM1 + q);
+    SAMSIM_LOOP
+    for (int k = 1; k <= N; k++) temp[k] = x[k];
+    SAMSIM_LOOP
+    for (int k = 1; k <= Na; k++) br[k] = x[k] / (f_max(c.psi_l()[k] * c.thick()[k] * rho_l, 0.000000000000001));  // :171
+    SAMSIM_LOOP
+    for (int i = 1; i <= Na; i++) {  // :179-190
+      const double xi = x[i], bi = br[i], lim = xi / 3.0;
+      if (xi >= 0.0 && bi - bi == 0.0) {
+        if (i == Na && Na >= 3) { const double f = f_min(c.fb_x * bi, lim); temp[i] = temp[i] - f; temp[1] = temp[1] + f; }
+        if (i >= 2) { const double f = f_min(U[i - 1] * bi, lim); temp[i] = temp[i] - f; temp[i - 1] = temp[i - 1] + f; }
+        if (i <= Na - 1) { const double f = f_min(D[i] * bi, lim); temp[i] = temp[i] - f; temp[i + 1] = temp[i + 1] + f; }
+        if (i <= Na - 2) { const double f = f_min(Ac[i] * bi, lim); temp[i] = temp[i] - f; temp[Na] = temp[Na] + f; }
+      } else {
+        for (int j = 1; j <= Na; j++) {
+          const double f = f_min(fb_get(c, Na, i, j) * bi, lim);
+          temp[i] = temp[i] - f;
+          temp[j] = temp[j] + f;
+        }
+      }
+    }
+    SAMSIM_LOOP
+    for (int i = 1; i <= Na; i++) {  // :193-199 flows which leave the domain
+      const double cell = (i == Na) ? D[i] : O[i];
+      const double f = f_min(cell * br[i], x[i] / 3.0);
+      temp[i] = temp[i] - f;
+    }
+    for (int j = 1; j <= Na; j++) {  // :202-208 flows which enter the domain: only (Na+1, Na) is ever written
+      const double f = ((j == Na) ? U[Na] : 0.0) * bottom;
+      temp[j] = temp[j] + f;
+    }
+    SAMSIM_LOOP
+    for (int k = 1; k <= N; k++) x[k] = temp[k];
+  }
+}
+
+// The six layer-dynamics routines treat a tracer exactly like S_abs (bgc_bulk = bgc/m next to S_bu = S_abs/m, the
+// same products in the same order, bgc_bottom in the place of S_bu_bottom).  tracer_layer_dynamics replays the
+// routine layer_dynamics() is about to run, for one tracer array, BEFORE m / thick / N_active change; rho and bulk
+// are recomputed from that untouched state, so they equal the reference's snapshots.  `op` = routine chosen by the
+// dispatcher below: 1 bottom_melt, 2 bottom_melt_simple, 3 bottom_growth_simple, 4 bottom_growth, 5 top_grow, 6 top_melt.
+__device__ __noinline__ void tracer_layer_dynamics(const DevCfg& g, Col& c, int op, Lay x, double bottom) {
+  const int N = g.Nlayer, N_top = g.N_top, N_middle = g.N_middle, N_bottom = g.N_bottom, Na = c.N_active;
+  const double thick_0 = g.thick_0;
+  Lay bulk = c.w3();
+  auto rho = [&](int k) { return c.m()[k] / c.thick()[k]; };
+  if (op == 2) { x[Na] = 0.0; return; }                                             // bottom_melt_simple :586
+  if (op == 3) { x[Na + 1] = bottom * (thick_0 * rho_l); return; }                  // bottom_growth_simple :557, m = thick_0*rho_l
+  if (op == 1) {  // bottom_melt :341-420
+    SAMSIM_LOOP
+    for (int k = N_top + 1; k <= N; k++) bulk[k] = x[k] / c.m()[k];
+    double loss = 0.0;
+    SAMSIM_LOOP
+    for (int k = N_top + 1; k <= N_top + N_middle; k++) {
+      double xk = x[k] + loss;
+      const double shift = c.thick()[N] * (k - N_top) / (double)(float)(N_middle);
+      const double loss_m = shift * rho(k);
+      loss = loss_m * bulk[k];
+      x[k] = xk - loss;
+    }
+    // thick(k) of the bottom layers is not touched by the routine
+    SAMSIM_LOOP
+    for (int k = N_top + N_middle + 1; k <= N; k++) x[k] = rho(k - 1) * c.thick()[k] * bulk[k - 1];
+    return;
+  }
+  if (op == 4) {  // bottom_growth :438-520
+    SAMSIM_LOOP
+    for (int k = N_top + 1; k <= N_top + N_middle + 1; k++) bulk[k] = x[k] / c.m()[k];
+    double gain = 0.0;
+    SAMSIM_LOOP
+    for (int k = N_top + 1; k <= N_top + N_middle; k++) {
+      double xk = x[k] - gain;
+      const double shift = c.thick()[N] * (k - N_top) / (double)(float)(N_middle);
+      const double gain_m = shift * rho(k + 1);
+      gain = gain_m * bulk[k + 1];
+      x[k] = xk + gain;
+    }
+    SAMSIM_LOOP
+    for (int k = N - N_bottom + 1; k <= N - 1; k++) x[k] = x[k + 1];
+    x[N] = (c.thick()[N] * rho_l) * bottom;  // m(Nlayer)*bgc_bottom with the new m(Nlayer) = thick(Nlayer)*rho_l
+    return;
+  }
+  // top_grow / top_melt work on layers 1..N_active
+  SAMSIM_LOOP
+  for (int k = 1; k <= Na; k++) bulk[k] = x[k] / c.m()[k];
+  if (op == 5) {  // top_grow :607-716
+    {
+      const double loss_m = thick_0 * rho(1);
+      x[1] = x[1] - loss_m * bulk[1];
+    }
+    const int kmax = (N_top < Na) ? N_top : Na;
+    SAMSIM_LOOP
+    for (int k = 2; k <= kmax; k++) x[k] = bulk[k - 1] * rho(k - 1) * thick_0;
+    if (Na <= N_top) {
+      x[Na + 1] = bulk[Na] * thick_0 * rho(Na);
+    } else if (Na > N_top && Na < N) {
+      SAMSIM_LOOP
+      for (int k = N_top + 1; k <= Na; k++) x[k] = bulk[k - 1] * rho(k - 1) * thick_0;
+      x[Na + 1] = bulk[Na] * thick_0 * rho(Na);
+    } else if (Na == N) {
+      double loss_m = thick_0 * rho(N_top);
+      double loss = loss_m * bulk[N_top];
+      SAMSIM_LOOP
+      for (int k = N_top + 1; k <= N_middle + N_top; k++) {
+        const double xk = x[k] + loss;
+        const double shift = thick_0 * (double)(float)(N_middle - k + N_top) / (double)(float)(N_middle);
+        loss_m = shift * rho(k);
+        loss = loss_m * bulk[k];
+        x[k] = xk - loss;
+      }
+    }
+    return;
+  }
+  // op == 6: top_melt :191-326
+  x[1] = x[1] + x[2];
+  {
+    const int kmax = (N_top - 1 < Na - 1) ? N_top - 1 : Na - 1;
+    SAMSIM_LOOP
+    for (int k = 2; k <= kmax; k++) x[k] = bulk[k + 1] * rho(k + 1) * thick_0;
+  }
+  int Nb = Na;
+  if (Na <= N_top) {
+    x[Na] = 0.0;
+    Nb = Na - 1;
+  } else if (Na > N_top && Na <= N && c.thick()[N_top + 1] / thick_0 < 1.00001) {
+    SAMSIM_LOOP
+    for (int k = N_top; k <= Na - 1; k++) x[k] = bulk[k + 1] * rho(k + 1) * thick_0;
+    x[Na] = 0.0;
+    Nb = Na - 1;
+  }
+  if (Nb == N && c.thick()[N_top + 1] - thick_0 >= 0.000001) {
+    double loss_m = thick_0 * rho(N_top + 1);
+    double loss = loss_m * bulk[N_top + 1];
+    x[N_top] = loss;
+    SAMSIM_LOOP
+    for (int k = N_top + 1; k <= N_middle + N_top; k++) {
+      const double xk = x[k] - loss;
+      const double shift = thick_0 * (double)(float)(N_middle - k + N_top) / (double)(float)(N_middle);
+      loss_m = shift * rho(k + 1);
+      loss = loss_m * bulk[k + 1];
+      x[k] = xk + loss;
+    }
+  }
+}
+
 // layer_dynamics dispatcher, mo_layer_dynamics.f90:64-175
 __device__ __noinline__ void layer_dynamics(const DevCfg& g, Col& c) {
   const int N = g.Nlayer, N_top = g.N_top, Na = c.N_active;
@@ -1401,22 +1614,33 @@ __device__ __noinline__ void layer_dynamics(const DevCfg& g, Col& c) {
   const int nm1 = (Na - 1 > 1) ? Na - 1 : 1;
   const double phi_Na = c.phi()[Na], phi_nm1 = c.phi()[nm1], th1 = c.thick()[1];
   const double mid_ratio = c.thick()[N_top + 1] / thick_0;
+  // tracers first (they read the untouched m, thick, N_active), then the routine itself
+  auto tracers = [&](int op) {
+    for (int q = 0; q < g.n_bgc; q++) tracer_layer_dynamics(g, c, op, c.bgc(q), SCV(c, SC_BGC_BOTTOM1 + q));
+  };
   if (c.phi()[N - 1] <= psi_s_min / 2.0 && phi_Na < 0.00001 && Na == N && mid_ratio > 1.000001 && bf) {
+    tracers(1);
     bottom_melt(g, c);
   } else if (Na > 1 && Na < N && phi_Na < 0.00001 && phi_nm1 <= psi_s_min / 2.0 && bf) {
+    tracers(2);
     bottom_melt_simple(c);
   } else if (Na > 1 && phi_Na < 0.00001 && phi_nm1 <= psi_s_min / 2.0 && mid_ratio < 1.01 && bf) {
+    tracers(2);
     bottom_melt_simple(c);
   } else if (phi_Na > psi_s_min && Na < N && bf) {
+    tracers(3);
     bottom_growth_simple(g, c);
   } else if (c.phi()[N] > psi_s_min && bf) {
+    tracers(4);
     bottom_growth(g, c);
   } else if (th1 > 1.5 * thick_0) {
     SCV(c, SC_MTO3) = SCV(c, SC_MTO3) - th1;
+    tracers(5);
     top_grow(g, c);
     SCV(c, SC_MTO3) = SCV(c, SC_MTO3) + c.thick()[1];
   } else if (th1 < 0.5 * thick_0) {
     SCV(c, SC_MTO3) = SCV(c, SC_MTO3) - th1;
+    tracers(6);
     top_melt(g, c);
     SCV(c, SC_MTO3) = SCV(c, SC_MTO3) + c.thick()[1];
   }

@@ -19,9 +19,10 @@
 using namespace samsim;
 
 static_assert((int)SAMSIM_SC_COUNT == (int)SC_COUNT, "scalar ids out of sync with include/samsim_b200.h");
-static_assert((int)SAMSIM_ARR_COUNT == (int)AR_STATE_COUNT, "array ids out of sync with include/samsim_b200.h");
+static_assert((int)SAMSIM_ARR_COUNT == (int)AR_STATE_COUNT + 2 && (int)SAMSIM_ARR_BGC_ABS1 == (int)AR_STATE_COUNT,
+              "array ids out of sync with include/samsim_b200.h");
 static_assert((int)SAMSIM_INT_COUNT == (int)IN_COUNT, "int ids out of sync with include/samsim_b200.h");
-static_assert((int)SAMSIM_SNAPSC_COUNT == 20 && (int)SAMSIM_SNAPARR_COUNT == 10, "snapshot layout");
+static_assert((int)SAMSIM_SNAPSC_COUNT == 20 && (int)SAMSIM_SNAPARR_COUNT == 14, "snapshot layout");
 
 // Launch shape (measured on B200, profiles/README.md): 512-thread blocks, 2 blocks per SM (64 registers/thread,
 // 32 warps/SM) and a barrier between the phases of a step (SAMSIM_SYNC, step.cuh).
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(SAMSIM_BLOCK, SAMSIM_MINBLOCKS) samsim_step_ke
   c.want_state = false;
   c.fb.tot_valid = c.fb.suf_valid = c.fb.res_valid = false; c.fb.k_last = 0; c.fb.ks = 0;
   c.min_psi_s = 0.0; c.min_S_abs_2 = 0.0;
+  c.fb_x = 0.0;
 
   Forcing f;
   f.win = s_win; f.win_len = p.win_len; f.win_first = p.win_first;
@@ -134,14 +136,14 @@ __device__ __forceinline__ long long slot_of(const int* map, long long col) { re
 
 // replicate one column (ensemble initialisation)
 __global__ void samsim_broadcast_kernel(double* arr, double* sc, int* in, long long ncol_pad, int LS, int src, int col0,
-                                        int n, const int* map) {
+                                        int n, const int* map, int n_arr) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const long long col = slot_of(map, col0 + t);
   src = (int)slot_of(map, src);
   if (col == src) return;
   const size_t ls = (size_t)ncol_pad;
-  for (int a = 0; a < AR_COUNT; a++)
+  for (int a = 0; a < n_arr; a++)
     for (int k = 0; k < LS; k++) {
       const size_t o = ((size_t)a * LS + k) * ls;
       arr[o + col] = arr[o + src];
@@ -351,6 +353,7 @@ struct samsim_b200_handle_s {
   size_t stage_bytes = 0;
   long long launches = 0;
   int num_sms = 148;
+  int n_arr = AR_CORE_COUNT;  // AR_COUNT when tracers are on (cfg.N_bgc > 0)
   // re-binning: slot_of_col[c] = where column c lives, col_of_slot[s] = which column lives in slot s (nullptr = identity)
   int *slot_of_col = nullptr, *col_of_slot = nullptr;
   long long rebin_every = 0, since_rebin = 0, rebins = 0;
@@ -442,6 +445,7 @@ int samsim_b200_create(const samsim_config_t* cfg, int32_t ncol, int32_t device,
   if (cfg->Nlayer < 3 || cfg->Nlayer != cfg->N_top + cfg->N_middle + cfg->N_bottom || cfg->N_top < 3)
     return fail(SAMSIM_ERR_CONFIG, "Nlayer must equal N_top+N_middle+N_bottom with N_top >= 3 (mo_init.f90:2014-2017)");
   if (!(cfg->salt_flag == 1 || cfg->salt_flag == 2)) return fail(SAMSIM_ERR_CONFIG, "salt_flag must be 1 or 2");
+  if (cfg->N_bgc < 0 || cfg->N_bgc > 2) return fail(SAMSIM_ERR_CONFIG, "N_bgc must be 0 (bgc_flag 1), 1 or 2");
   if (!(cfg->dt > 0.0) || !(cfg->thick_0 > 0.0)) return fail(SAMSIM_ERR_CONFIG, "dt and thick_0 must be positive");
   CU(cudaSetDevice(device));
   samsim_handle_t h = new samsim_b200_handle_s();
@@ -454,9 +458,10 @@ int samsim_b200_create(const samsim_config_t* cfg, int32_t ncol, int32_t device,
   h->ncol = ncol;
   h->ncol_pad = ((long long)ncol + SAMSIM_BLOCK - 1) / SAMSIM_BLOCK * SAMSIM_BLOCK;
   h->LS = cfg->Nlayer + 2;
-  if ((unsigned long long)AR_COUNT * h->LS * (unsigned long long)h->ncol_pad >= (1ull << 32)) {
+  h->n_arr = (cfg->N_bgc > 0) ? AR_COUNT : AR_CORE_COUNT;
+  if ((unsigned long long)h->n_arr * h->LS * (unsigned long long)h->ncol_pad >= (1ull << 32)) {
     delete h;
-    return fail(SAMSIM_ERR_ARG, "create: 22*(Nlayer+2)*ncol must stay below 2^32 (32-bit element index); use several handles");
+    return fail(SAMSIM_ERR_ARG, "create: 22*(Nlayer+2)*ncol (28 with tracers) must stay below 2^32 (32-bit element index); use several handles");
   }
   DevCfg& d = h->dcfg;
   memset(&d, 0, sizeof d);
@@ -469,6 +474,7 @@ int samsim_b200_create(const samsim_config_t* cfg, int32_t ncol, int32_t device,
   d.lab_snow_flag = cfg->lab_snow_flag; d.freeboard_snow_flag = cfg->freeboard_snow_flag;
   d.snow_flush_flag = cfg->snow_flush_flag; d.snow_precip_flag = cfg->snow_precip_flag;
   d.i_time_out = cfg->i_time_out;
+  d.n_bgc = cfg->N_bgc;
   d.dt = cfg->dt; d.thick_0 = cfg->thick_0; d.thick_min = cfg->thick_min; d.time_out = cfg->time_out;
   d.alpha_flux_instable = cfg->alpha_flux_instable; d.alpha_flux_stable = cfg->alpha_flux_stable; d.m_total = cfg->m_total;
   d.max_flux_plate = cfg->max_flux_plate; d.k_snow_flush = cfg->k_snow_flush; d.k_styropor = cfg->k_styropor;
@@ -477,7 +483,7 @@ int samsim_b200_create(const samsim_config_t* cfg, int32_t ncol, int32_t device,
   } else {                    // :331-336 / :398-402
     d.c2 = -17.6; d.c3 = -0.389; d.c4 = -0.00362; d.d2 = -17.6; d.d3x2 = 2.0 * -0.389; d.d4x3 = 3.0 * -0.00362;
   }
-  const size_t narr = (size_t)AR_COUNT * h->LS * h->ncol_pad;
+  const size_t narr = (size_t)h->n_arr * h->LS * h->ncol_pad;
   cudaError_t e;
   if ((e = cudaMalloc(&h->arr, narr * sizeof(double))) != cudaSuccess ||
       (e = cudaMalloc(&h->sc, (size_t)SC_COUNT * h->ncol_pad * sizeof(double))) != cudaSuccess ||
@@ -508,8 +514,12 @@ void samsim_b200_destroy(samsim_handle_t h) {
   delete h;
 }
 
+// public array id -> slot in the device buffer (the tracer arrays sit behind the scratch arrays)
+static inline int arr_slot(int32_t id) { return (id < AR_STATE_COUNT) ? id : AR_BGC1 + (id - AR_STATE_COUNT); }
+
 int32_t samsim_b200_array_extent(samsim_handle_t h, int32_t id) {
   if (!h || id < 0 || id >= SAMSIM_ARR_COUNT) return -1;
+  if (id >= SAMSIM_ARR_BGC_ABS1) return (id - SAMSIM_ARR_BGC_ABS1 < h->cfg.N_bgc) ? h->cfg.Nlayer : -1;
   if (id == SAMSIM_ARR_RAY) return h->cfg.Nlayer - 1;
   if (id == SAMSIM_ARR_FL_Q) return h->cfg.Nlayer + 1;
   return h->cfg.Nlayer;
@@ -532,7 +542,7 @@ int samsim_b200_set_array(samsim_handle_t h, int32_t id, const double* host, int
   if ((rc = ensure_stage(h, bytes))) return rc;
   CU(cudaMemcpyAsync(h->stage, host, bytes, cudaMemcpyHostToDevice, h->stream));
   const long long total = (long long)n * ext;
-  samsim_scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->arr, h->stage, h->ncol_pad, h->LS, id, ext, col0, n, h->slot_of_col);
+  samsim_scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->arr, h->stage, h->ncol_pad, h->LS, arr_slot(id), ext, col0, n, h->slot_of_col);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));
   return 0;
@@ -548,7 +558,7 @@ int samsim_b200_get_array(samsim_handle_t h, int32_t id, double* host, int32_t c
   const size_t bytes = (size_t)n * ext * sizeof(double);
   if ((rc = ensure_stage(h, bytes))) return rc;
   const long long total = (long long)n * ext;
-  samsim_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->arr + (size_t)id * h->LS * h->ncol_pad, h->stage, h->ncol_pad, h->LS, 1, ext, col0, n, 1, h->slot_of_col);
+  samsim_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->arr + (size_t)arr_slot(id) * h->LS * h->ncol_pad, h->stage, h->ncol_pad, h->LS, 1, ext, col0, n, 1, h->slot_of_col);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(host, h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -590,7 +600,7 @@ int samsim_b200_broadcast_column(samsim_handle_t h, int32_t src, int32_t col0, i
   if (src < 0 || src >= h->ncol) return fail(SAMSIM_ERR_ARG, "broadcast: bad source column");
   if (n == 0) return 0;
   CU(cudaSetDevice(h->device));
-  samsim_broadcast_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->arr, h->sc, h->in, h->ncol_pad, h->LS, src, col0, n, h->slot_of_col);
+  samsim_broadcast_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->arr, h->sc, h->in, h->ncol_pad, h->LS, src, col0, n, h->slot_of_col, h->n_arr);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));
   return 0;
@@ -816,6 +826,7 @@ int samsim_b200_rebin(samsim_handle_t h, int32_t* changed) {
 
   const size_t astr = (size_t)h->LS * h->ncol_pad;
   for (int a = 0; a < AR_STATE_COUNT && !rc; a++) rc = permute_rows<double>(h, h->arr + (size_t)a * astr, h->LS, order, tmp);
+  for (int q = 0; q < h->cfg.N_bgc && !rc; q++) rc = permute_rows<double>(h, h->arr + (size_t)(AR_BGC1 + q) * astr, h->LS, order, tmp);
   if (!rc) rc = permute_rows<double>(h, h->sc, SC_COUNT, order, tmp);
   if (!rc) rc = permute_rows<int>(h, h->in, IN_COUNT, order, tmp);
   if (!rc) rc = permute_rows<int>(h, h->site_of_col, 1, order, tmp);
@@ -879,6 +890,7 @@ int samsim_b200_save_checkpoint(samsim_handle_t h, const char* path) {
   std::vector<double> buf;
   for (int id = 0; ok && !rc && id < SAMSIM_ARR_COUNT; id++) {
     const int ext = samsim_b200_array_extent(h, id);
+    if (ext < 0) continue;  // tracer arrays of a run without tracers
     buf.resize((size_t)chunk * ext);
     for (int64_t c0 = 0; ok && !rc && c0 < ncol; c0 += chunk) {
       const int32_t n = (int32_t)((ncol - c0 < chunk) ? ncol - c0 : chunk);
@@ -923,6 +935,7 @@ int samsim_b200_load_checkpoint(samsim_handle_t h, const char* path) {
   std::vector<double> buf;
   for (int id = 0; ok && !rc && id < SAMSIM_ARR_COUNT; id++) {
     const int ext = samsim_b200_array_extent(h, id);
+    if (ext < 0) continue;
     buf.resize((size_t)chunk * ext);
     for (int64_t c0 = 0; ok && !rc && c0 < ncol; c0 += chunk) {
       const int32_t n = (int32_t)((ncol - c0 < chunk) ? ncol - c0 : chunk);

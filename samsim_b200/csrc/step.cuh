@@ -307,6 +307,28 @@ __device__ __noinline__ void write_snapshot(const DevCfg& g, const Col& c, const
       SAMSIM_LOOP
       for (int k = 1; k <= n; k++) dst[(size_t)k * s.ncol_pad] = from[k];
     }
+    for (int q = 0; q < g.n_bgc; q++) {  // output_bgc, mo_output.f90:165-186
+      double* bu = s.arrays + ((size_t)(10 + 2 * q) * LS) * s.ncol_pad + s.col;
+      double* br = s.arrays + ((size_t)(11 + 2 * q) * LS) * s.ncol_pad + s.col;
+      const Lay x = c.bgc(q);
+      const double bottom = c.sc[SC_BGC_BOTTOM1 + q];
+      SAMSIM_LOOP
+      for (int k = 1; k <= N; k++) {
+        double vbu = bottom, vbr = bottom;
+        if (k <= c.N_active) {
+          const double mk = c.m()[k];
+          if (mk != 0.0) {
+            vbu = x[k] / mk;
+            const double pl = c.psi_l()[k], th = c.thick()[k];
+            vbr = (pl != 0.0 && th != 0.0) ? x[k] / pl / th / rho_l : 0.0;
+          } else {
+            vbu = 0.0; vbr = 0.0;
+          }
+        }
+        bu[(size_t)k * s.ncol_pad] = vbu;
+        br[(size_t)k * s.ncol_pad] = vbr;
+      }
+    }
   }
 }
 
@@ -385,6 +407,10 @@ __device__ __noinline__ void fused_thermo_expulsion(const DevCfg& g, Col& c) {
       c.S_abs()[k] = S;
     }
     c.S_bu()[k] = S / m_new;
+    if (g.n_bgc) {  // mo_grotz.f90:316-320: fl_brine_bgc(k,k+1) = -fl_m(k+1); the other cells start the step empty
+      c.A(AR_FB_D)[k] = transfer ? -f1 : 0.0;
+      c.A(AR_FB_U)[k] = 0.0; c.A(AR_FB_A)[k] = 0.0; c.A(AR_FB_O)[k] = 0.0;
+    }
     T_km1 = T_k; Sbu_km1 = sbu_k; Sabs_km1 = S;
     T_k = T_kp1; sbu_k = Sbu_kp1; phi_k = phi_kp1; m_k = m_kp1;
     f0 = f1;
@@ -534,11 +560,19 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
       f0 = f1;
     }
     if (c.i != 1) mass_transfer(g, c, fl_m, c.S_bu());
+    if (g.n_bgc) {  // :316-320
+      SAMSIM_LOOP
+      for (int k = 1; k <= Na; k++) {
+        c.A(AR_FB_D)[k] = (c.i != 1) ? -fl_m[k + 1] : 0.0;
+        c.A(AR_FB_U)[k] = 0.0; c.A(AR_FB_A)[k] = 0.0; c.A(AR_FB_O)[k] = 0.0;
+      }
+    }
     // ---- S7 :333-335 ----
     SAMSIM_LOOP
     for (int k = Na; k >= 1; k--) c.S_bu()[k] = c.S_abs()[k] / c.m()[k];
   }
 
+  c.fb_x = 0.0;
   // ---- S8 output :340-398 ----
   if (output_step) {
     SCV(c, SC_FREEBOARD) = (c.N_active > 1) ? freeboard_of(g, c) : 0.0;
@@ -594,6 +628,10 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     const double S = c.S_abs()[Na], mNa = c.m()[Na];
     const double turb = Turb_A * det_exp(Turb_B * (-density_of(SCV(c, SC_T_BOTTOM), SCV(c, SC_S_BU_BOTTOM)) + density_of(c.T()[Na], S / mNa))) * dt;
     c.S_abs()[Na] = S - turb * (S / mNa - SCV(c, SC_S_BU_BOTTOM));
+    for (int q = 0; q < g.n_bgc; q++) {  // mo_functions.f90:357-359
+      const double b = c.bgc(q)[Na];
+      c.bgc(q)[Na] = b - turb * (b / mNa - SCV(c, SC_BGC_BOTTOM1 + q));
+    }
   }
 
   }
@@ -675,6 +713,10 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   // ---- S16 tank :573-578 ----
   if (g.tank_flag == 2) {
     SCV(c, SC_S_BU_BOTTOM) = (SCV(c, SC_S_TOTAL) - sum_fwd(c.S_abs(), 1, c.N_active)) / (g.m_total - sum_fwd(c.m(), 1, c.N_active));
+    if (g.n_bgc) {  // :575-577 (sic: every tracer gets the value computed from tracer 1)
+      const double v = (SCV(c, SC_BGC_TOTAL1) - sum_fwd(c.bgc(0), 1, c.N_active)) / (g.m_total - sum_fwd(c.m(), 1, c.N_active));
+      for (int q = 0; q < g.n_bgc; q++) SCV(c, SC_BGC_BOTTOM1 + q) = v;
+    }
   }
 
   // ---- S17 heat fluxes :584 ----
@@ -792,6 +834,9 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     }
   }
 
+  // ---- S22 tracer advection :742-747 ----
+  if (g.n_bgc) bgc_advection(g, c);
+
   }
   SAMSIM_PHASE_SYNC();
   if (c.status == 0) {  // ===== phase 8 =====
@@ -810,6 +855,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
       c.S_bu()[Nb + 1] = SCV(c, SC_S_BU_BOTTOM);
       c.psi_l()[Nb + 1] = 1.0;
       c.psi_s()[Nb + 1] = 0.0;
+      for (int q = 0; q < g.n_bgc; q++) c.bgc(q)[Nb + 1] = 0.0;  // :778-780
     }
   } else {
     if (c.phi()[1] > psi_s_min) { layer_dynamics(g, c); c.thermo_valid = false; fb_reset(c); }
