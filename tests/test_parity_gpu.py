@@ -170,6 +170,8 @@ def test_snapshot_matches_oracle_output(oracle_mod, golden_dir):
             o = rec[name] if name != "N_active" else float(rec["N_active"])
             assert pu.same_bits(snap[name][0], o), (name, snap[name][0], o)
         for name in api.SNAP_ARRAYS:
+            if name.startswith("bgc"):
+                continue  # tracer rows: test_tracers_tank_and_snapshot (testcase 4 runs without tracers)
             o = np.asarray(rec[name])[: snap[name].shape[1]]
             assert pu.same_bits(snap[name][0], o).all(), name
 
