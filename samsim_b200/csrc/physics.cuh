@@ -860,8 +860,9 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
   SAMSIM_LOOP
   for (int k = 1; k <= Na - 1; k++) {  // :144-171
     if (k + SAMSIM_PF <= Na) {
-      c.ray().prefetch(k + SAMSIM_PF); c.psi_s().prefetch(k + SAMSIM_PF); c.S_abs().prefetch(k + SAMSIM_PF);
-      c.m().prefetch(k + SAMSIM_PF); c.S_br().prefetch(k + SAMSIM_PF);
+      // psi_s and m are only read for layers above ray_crit: prefetching them for every layer was 16 B of DRAM
+      // traffic per layer and step for nothing
+      c.ray().prefetch(k + SAMSIM_PF); c.S_abs().prefetch(k + SAMSIM_PF); c.S_br().prefetch(k + SAMSIM_PF);
     }
     double rk = c.ray()[k];
     const double Sk = c.S_abs()[k];
@@ -1456,16 +1457,19 @@ __device__ __forceinline__ double fb_get(const Col& c, int Na, int i, int j) {
 // so rows whose content is non-negative (and whose brine concentration is finite) only visit their written cells,
 // in the same ascending-j order; any other row runs the dense loop.  temp/br are the scratch arrays w0/w1.
 __device__ __noinline__ void bgc_advection(const DevCfg& g, Col& c) {
-  const int Na = c.N_active, N = g.Nlayer;
+  const int Na = c.N_active;
   Lay temp = c.w0(), br = c.w1();
   Lay D = c.A(AR_FB_D), U = c.A(AR_FB_U), Ac = c.A(AR_FB_A), O = c.A(AR_FB_O);
   for (int q = 0; q < g.n_bgc; q++) {
     Lay x = c.bgc(q);
     const double bottom = SCV(c, SC_BGC_BOTTOM1 + q);
+    // bgc_temp = bgc_abs (layers below N_active are not touched: copied back unchanged) and bgc_br, :171
     SAMSIM_LOOP
-    for (int k = 1; k <= N; k++) temp[k] = x[k];
-    SAMSIM_LOOP
-    for (int k = 1; k <= Na; k++) br[k] = x[k] / (f_max(c.psi_l()[k] * c.thick()[k] * rho_l, 0.000000000000001));  // :171
+    for (int k = 1; k <= Na; k++) {
+      const double xk = x[k];
+      temp[k] = xk;
+      br[k] = xk / (f_max(c.psi_l()[k] * c.thick()[k] * rho_l, 0.000000000000001));
+    }
     SAMSIM_LOOP
     for (int i = 1; i <= Na; i++) {  // :179-190
       const double xi = x[i], bi = br[i], lim = xi / 3.0;
@@ -1482,18 +1486,16 @@ __device__ __noinline__ void bgc_advection(const DevCfg& g, Col& c) {
         }
       }
     }
+    // :193-199 flows which leave the domain, then :202-208 flows which enter it -- only cell (Na+1, Na) is ever
+    // written, the other layers receive 0*bgc_bottom = 0 -- and bgc_abs = bgc_temp
     SAMSIM_LOOP
-    for (int i = 1; i <= Na; i++) {  // :193-199 flows which leave the domain
+    for (int i = 1; i <= Na; i++) {
       const double cell = (i == Na) ? D[i] : O[i];
       const double f = f_min(cell * br[i], x[i] / 3.0);
-      temp[i] = temp[i] - f;
+      double t = temp[i] - f;
+      t = t + ((i == Na) ? U[Na] : 0.0) * bottom;
+      x[i] = t;
     }
-    for (int j = 1; j <= Na; j++) {  // :202-208 flows which enter the domain: only (Na+1, Na) is ever written
-      const double f = ((j == Na) ? U[Na] : 0.0) * bottom;
-      temp[j] = temp[j] + f;
-    }
-    SAMSIM_LOOP
-    for (int k = 1; k <= N; k++) x[k] = temp[k];
   }
 }
 
