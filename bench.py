@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """bench.py -- column-timesteps/sec of the SAMSIM column timestep on 1..8 B200.
 
-Workload (BASELINE.json config 5): 1,048,576 ERA-interim-style columns (testcase-4 flags, 100 layers, dt 10 s),
-sharded over the N ranks (strong scaling: the total is fixed).  Every column starts from the oracle's SHEBA state
+Workload (BASELINE.json config 5): 1,048,576 ERA-interim-style columns (testcase-4 flags, 100 layers, dt 10 s) PER
+GPU: the columns are independent, so the ensemble is sharded over the N ranks with no data-path collective and the
+bench reports weak scaling (N x 1,048,576 columns on N GPUs; `--scaling strong` shards a fixed total instead, which
+at 8 GPUs leaves 131,072 columns = 0.86 of a wave per GPU).  Every column starts from the oracle's SHEBA state
 of mid January (output record 200: N_active = 100, 0.124 m of snow) and gets its own forcing: base site c mod 9 of
 input/ERA-interim, T2m + U(-2,2) K, fl_lw x U(.95,1.05), fl_sw x U(.9,1.1), precip x U(.5,1.5), oceanic flux
 amplitude 7 x U(.5,1.5) W/m2 (default_rng(4)).
@@ -58,22 +60,37 @@ def load_sites(nrec_min: int) -> np.ndarray:
     return np.stack([z[s][:, :n] for s in SITES])  # [9, 4, n]
 
 
-def perturbations(col0: int, n: int):
-    """Deterministic per-column perturbations for global columns [col0, col0+n)."""
-    rng = np.random.default_rng(4)
-    # draw for the whole ensemble so that a column's numbers do not depend on the sharding
+def _perturbation_block(b: int):
+    """The five perturbation vectors of global columns [b*TOTAL_COLUMNS, (b+1)*TOTAL_COLUMNS)."""
+    # drawn per block of TOTAL_COLUMNS so that a column's numbers do not depend on the sharding; block 0 is the
+    # config-5 ensemble (default_rng(4), SURVEY 8d), further blocks extend it for the weak-scaling runs
+    rng = np.random.default_rng(4) if b == 0 else np.random.default_rng([4, b])
     T2m_off = rng.uniform(-2, 2, TOTAL_COLUMNS)
     lw = rng.uniform(0.95, 1.05, TOTAL_COLUMNS)
     sw = rng.uniform(0.9, 1.1, TOTAL_COLUMNS)
     pr = rng.uniform(0.5, 1.5, TOTAL_COLUMNS)
     amp = 7.0 * rng.uniform(0.5, 1.5, TOTAL_COLUMNS)
-    sl = slice(col0, col0 + n)
+    return T2m_off, lw, sw, pr, amp
+
+
+def perturbations(col0: int, n: int):
+    """Deterministic per-column perturbations for global columns [col0, col0+n)."""
     scale = np.ones((4, n))
     offset = np.zeros((4, n))
-    scale[0], scale[1], scale[3] = sw[sl], lw[sl], pr[sl]
-    offset[2] = T2m_off[sl]
+    amp = np.empty(n)
+    done = 0
+    while done < n:
+        g = col0 + done
+        b, lo = divmod(g, TOTAL_COLUMNS)
+        cnt = min(n - done, TOTAL_COLUMNS - lo)
+        T2m_off, lw, sw, pr, am = _perturbation_block(b)
+        sl, dst = slice(lo, lo + cnt), slice(done, done + cnt)
+        scale[0, dst], scale[1, dst], scale[3, dst] = sw[sl], lw[sl], pr[sl]
+        offset[2, dst] = T2m_off[sl]
+        amp[dst] = am[sl]
+        done += cnt
     site = (np.arange(col0, col0 + n) % len(SITES)).astype(np.int32)
-    return site, scale, offset, amp[sl]
+    return site, scale, offset, amp
 
 
 class ClockSampler(threading.Thread):
@@ -160,9 +177,9 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": "column-timesteps/sec (FP64, 100 layers)", "value": value,
         "unit": "column-timesteps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus, sample=f"{sample_cols} of the {TOTAL_COLUMNS} columns x {steps_per} model steps per step"),
+        "config": workload_config(args.gpus, scaling=args.scaling, per_gpu=(args.columns if args.scaling == "weak" else args.columns // max(args.gpus, 1)), sample=f"{sample_cols} of the {TOTAL_COLUMNS} columns x {steps_per} model steps per step"),
         "cpu_baseline": {"value": value, "unit": "column-timesteps/s", "cores": ncores, "kind": "port",
                          "sample": f"{sample_cols} columns x {steps_per * args.steps} model steps, one column per thread; "
                                    "C oracle (gcc -O2 -ffp-contract=off), the Fortran reference cannot be compiled in this image"},
@@ -171,11 +188,12 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-def workload_config(n_gpus: int, sample: str | None = None) -> dict:
+def workload_config(n_gpus: int, sample: str | None = None, scaling: str = "weak", per_gpu: int | None = None) -> dict:
+    per = per_gpu if per_gpu is not None else (TOTAL_COLUMNS if scaling == "weak" else TOTAL_COLUMNS // n_gpus)
     cfg = {
-        "workload": "config 5: 1,048,576 ERA-interim-style columns (testcase 4 flags, Nlayer 100, dt 10 s), "
+        "workload": "config 5: 1,048,576 ERA-interim-style columns per GPU (testcase 4 flags, Nlayer 100, dt 10 s), "
                     "mid-January SHEBA state (N_active 100, snow 0.124 m), per-column perturbed forcing of 9 sites",
-        "columns_total": TOTAL_COLUMNS, "columns_per_gpu": TOTAL_COLUMNS // n_gpus,
+        "columns_total": per * n_gpus, "columns_per_gpu": per,
         "model_steps_per_step": MODEL_STEPS, "layers": 100, "dt_s": 10.0,
         "parallelism": f"columns sharded over {n_gpus} GPU(s), no data-path collective",
         "cache": "working set (>= 12 KB/column x columns) is far larger than the 126 MB L2; no flush needed",
@@ -191,7 +209,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--columns", type=int, default=TOTAL_COLUMNS, help="total columns (default: the config-5 ensemble)")
+    ap.add_argument("--columns", type=int, default=TOTAL_COLUMNS,
+                    help="columns per GPU (weak scaling, default: the config-5 ensemble) or in total (--scaling strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -214,8 +234,12 @@ def main():
 
     from samsim_b200 import api, distributed as D
 
-    total = args.columns
-    col0, per = D.shard(total, rank, world)
+    if args.scaling == "weak":   # per-GPU work fixed: rank r owns global columns [r*per, (r+1)*per)
+        per = args.columns
+        col0, total = rank * per, per * world
+    else:                        # total fixed, contiguous shards
+        total = args.columns
+        col0, per = D.shard(total, rank, world)
     st = load_state(START_RECORD)
     sites = load_sites(64)
     cfg = api.Config.from_state({**st, "thick_min": st["thick_min"]})
@@ -304,9 +328,9 @@ def main():
         line = {
             "metric": "column-timesteps/sec (FP64, 100 layers)", "value": value, "unit": "column-timesteps/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": wall_a_s / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "ms_per_step": wall_a_s / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world) if total == TOTAL_COLUMNS else {**workload_config(world), "columns_total": total, "columns_per_gpu": per},
+            "config": workload_config(world, scaling=args.scaling, per_gpu=per),
             "e2e": {"value": col_steps / wall_b_s, "unit": "column-timesteps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",

@@ -20,6 +20,16 @@ def test_perturbations_are_shard_invariant():
     assert np.array_equal(of_a[:, 512:], of_b) and np.array_equal(amp_a[512:], amp_b)
     assert set(np.unique(site_a)) == set(range(9))
     assert (sc_a[2] == 1).all() and (of_a[[0, 1, 3]] == 0).all()   # T2m is offset-only, the fluxes scale-only
+    # weak scaling: rank r owns global columns [r*TOTAL, (r+1)*TOTAL); block 0 is the config-5 ensemble and a range
+    # that crosses a block boundary is the concatenation of the two blocks' numbers
+    T = bench.TOTAL_COLUMNS
+    s_x, sc_x, of_x, amp_x = bench.perturbations(T - 3, 8)
+    s_0, sc_0, of_0, amp_0 = bench.perturbations(T - 3, 3)
+    s_1, sc_1, of_1, amp_1 = bench.perturbations(T, 5)
+    assert np.array_equal(np.concatenate([amp_0, amp_1]), amp_x) and np.array_equal(np.concatenate([sc_0, sc_1], 1), sc_x)
+    assert np.array_equal(np.concatenate([of_0, of_1], 1), of_x) and np.array_equal(np.concatenate([s_0, s_1]), s_x)
+    assert not np.array_equal(bench.perturbations(0, 64)[3], amp_1[:5].repeat(13)[:64])  # block 1 is not block 0 again
+    assert not np.array_equal(bench.perturbations(0, 5)[3], amp_1)
 
 
 WORKER = textwrap.dedent("""
