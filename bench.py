@@ -229,6 +229,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: samsim_b200 has no CPU path (use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # keep stdout to the one JSON line: with NCCL_DEBUG set, NCCL writes its version banner / log to stdout
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
