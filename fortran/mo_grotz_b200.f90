@@ -41,6 +41,7 @@ CONTAINS
     TYPE(samsim_config_t)  :: cfg
     INTEGER(C_INT64_T)     :: n, done, total
     LOGICAL                :: wrote
+    INTEGER                :: k
     REAL(C_DOUBLE), ALLOCATABLE :: series(:), snap_sc(:), snap_ar(:,:)
     REAL(wp), ALLOCATABLE  :: o_T(:), o_psi_s(:), o_thick(:), o_S_bu(:), o_ray(:), o_psi_l(:), o_perm(:), o_fv(:), &
          &                    o_fh(:), o_psi_g(:)
@@ -55,7 +56,7 @@ CONTAINS
          & time_total,dt,boundflux_flag,atmoflux_flag,albedo_flag,grav_flag,flush_flag,flood_flag,grav_heat_flag,      &
          & flush_heat_flag,harmonic_flag,prescribe_flag,salt_flag,turb_flag,bottom_flag,tank_flag,precip_flag,bgc_flag, &
          & N_bgc,k_snow_flush)
-    IF (bgc_flag == 2) PRINT*, 'samsim_b200: bgc tracers are not advected on the device (passive, no feedback)'
+    IF (bgc_flag == 2) CALL output_begin_bgc(Nlayer,N_bgc,format_bgc)      ! mo_grotz.f90:121-123
     IF (atmoflux_flag == 2) THEN
        Length_Input = 13148
        time_counter = 1
@@ -95,7 +96,7 @@ CONTAINS
        DEALLOCATE(series)
     END IF
     CALL b200_check(samsim_b200_set_snapshot_mode(h, SAMSIM_SNAP_FULL), 'snapshot mode')
-    ALLOCATE(snap_sc(20), snap_ar(Nlayer,10))
+    ALLOCATE(snap_sc(20), snap_ar(Nlayer,14))   ! SAMSIM_SNAPSC_COUNT, SAMSIM_SNAPARR_COUNT of include/samsim_b200.h
     ALLOCATE(o_T(Nlayer), o_psi_s(Nlayer), o_thick(Nlayer), o_S_bu(Nlayer), o_ray(Nlayer-1), o_psi_l(Nlayer), &
          &   o_perm(Nlayer), o_fv(Nlayer), o_fh(Nlayer), o_psi_g(Nlayer))
 
@@ -119,6 +120,12 @@ CONTAINS
                & snap_sc(1),snap_sc(2),snap_sc(3),snap_sc(4),snap_sc(5),snap_sc(6),snap_sc(7),snap_sc(8),snap_sc(9),   &
                & snap_sc(10),snap_sc(11),snap_sc(12),snap_sc(13),snap_sc(14),snap_sc(15),o_perm,format_perm,o_fv,o_fh, &
                & o_psi_g,o_mto,format_melt)
+          IF (bgc_flag == 2) THEN   ! output_bgc (mo_output.f90:156-188): the device captured bgc_bu / bgc_br per tracer
+             DO k = 1, N_bgc
+                WRITE(2*k+400,format_bgc) snap_ar(:,9+2*k)
+                WRITE(2*k+401,format_bgc) snap_ar(:,10+2*k)
+             END DO
+          END IF
           WRITE(*,'(A10,I3,A15,F6.3)') 'progress: ', INT(100._wp*snap_sc(19)/time_total), '%,  thickness: ', snap_sc(9)
        END IF
     END DO
@@ -130,6 +137,11 @@ CONTAINS
     CLOSE(30); CLOSE(31); CLOSE(32); CLOSE(33); CLOSE(34); CLOSE(35)
     CLOSE(40); CLOSE(41); CLOSE(42); CLOSE(43); CLOSE(44); CLOSE(45); CLOSE(46); CLOSE(47); CLOSE(48); CLOSE(49)
     CLOSE(50); CLOSE(66)
+    IF (bgc_flag == 2) THEN                 ! mo_grotz.f90:850-855
+       DO k = 1, N_bgc
+          CLOSE(2*k+400); CLOSE(2*k+401)
+       END DO
+    END IF
     CALL sub_deallocate
   END SUBROUTINE grotz_batch
 

@@ -34,7 +34,7 @@ MODULE mo_samsim_b200
   INTEGER(C_INT32_T), PARAMETER :: SAMSIM_ARR_M = 0, SAMSIM_ARR_S_ABS = 1, SAMSIM_ARR_H_ABS = 2, SAMSIM_ARR_THICK = 3, &
        & SAMSIM_ARR_T = 4, SAMSIM_ARR_PHI = 5, SAMSIM_ARR_S_BU = 6, SAMSIM_ARR_PSI_S = 7, SAMSIM_ARR_PSI_L = 8, &
        & SAMSIM_ARR_PSI_G = 9, SAMSIM_ARR_RAY = 10, SAMSIM_ARR_PERM = 11, SAMSIM_ARR_FLUSH_V = 12, &
-       & SAMSIM_ARR_FLUSH_H = 13, SAMSIM_ARR_FL_Q = 14
+       & SAMSIM_ARR_FLUSH_H = 13, SAMSIM_ARR_FL_Q = 14, SAMSIM_ARR_BGC_ABS1 = 15, SAMSIM_ARR_BGC_ABS2 = 16
   ! samsim_scalar_id (order of include/samsim_b200.h)
   INTEGER(C_INT32_T), PARAMETER :: SC_T_BOTTOM = 0, SC_T_TOP = 1, SC_S_BU_BOTTOM = 2, SC_T2M = 3, SC_FL_Q_BOTTOM = 4, &
        & SC_PSI_S_SNOW = 5, SC_PSI_L_SNOW = 6, SC_PSI_G_SNOW = 7, SC_PHI_S = 8, SC_S_ABS_SNOW = 9, SC_H_ABS_SNOW = 10, &
@@ -43,7 +43,8 @@ MODULE mo_samsim_b200
        & SC_BULK_SALIN = 21, SC_ALBEDO = 22, SC_FL_SW = 23, SC_FL_LW = 24, SC_FL_REST = 25, SC_GRAV_DRAIN = 26, &
        & SC_GRAV_SALT = 27, SC_GRAV_TEMP = 28, SC_MELT_THICK = 29, SC_MELT_THICK_SNOW = 30, &
        & SC_MELT_THICK_SNOW_OLD = 31, SC_MTO1 = 32, SC_MTO2 = 33, SC_MTO3 = 34, SC_FREEBOARD = 35, SC_T_FREEZE = 36, &
-       & SC_MELT_ERR = 37, SC_S_TOTAL = 38, SC_TTOP_WARM = 39, SC_TTOP_COLD = 40, SC_OFLUX_AMP = 41
+       & SC_MELT_ERR = 37, SC_S_TOTAL = 38, SC_TTOP_WARM = 39, SC_TTOP_COLD = 40, SC_OFLUX_AMP = 41, &
+       & SC_BGC_BOTTOM1 = 42, SC_BGC_BOTTOM2 = 43, SC_BGC_TOTAL1 = 44, SC_BGC_TOTAL2 = 45
   INTEGER(C_INT32_T), PARAMETER :: SAMSIM_INT_N_ACTIVE = 0, SAMSIM_INT_STATUS = 1, SAMSIM_INT_STYROPOR_FLAG = 2
   INTEGER(C_INT32_T), PARAMETER :: SAMSIM_SNAP_NONE = 0, SAMSIM_SNAP_SCALARS = 1, SAMSIM_SNAP_FULL = 2
 
@@ -179,6 +180,31 @@ MODULE mo_samsim_b200
        INTEGER(C_INT32_T), VALUE :: col0, n
      END FUNCTION samsim_b200_get_status
 
+     ! batch-only helpers (nothing in the reference to replace): re-binning of drifted ensembles, restart files
+     INTEGER(C_INT) FUNCTION samsim_b200_rebin(handle, changed) BIND(C, NAME='samsim_b200_rebin')
+       IMPORT :: C_PTR, C_INT, C_INT32_T
+       TYPE(C_PTR), VALUE :: handle
+       INTEGER(C_INT32_T), INTENT(out) :: changed
+     END FUNCTION samsim_b200_rebin
+
+     INTEGER(C_INT) FUNCTION samsim_b200_set_rebin_interval(handle, nsteps) BIND(C, NAME='samsim_b200_set_rebin_interval')
+       IMPORT :: C_PTR, C_INT, C_INT64_T
+       TYPE(C_PTR), VALUE :: handle
+       INTEGER(C_INT64_T), VALUE :: nsteps
+     END FUNCTION samsim_b200_set_rebin_interval
+
+     INTEGER(C_INT) FUNCTION samsim_b200_save_checkpoint(handle, path) BIND(C, NAME='samsim_b200_save_checkpoint')
+       IMPORT :: C_PTR, C_INT, C_CHAR
+       TYPE(C_PTR), VALUE :: handle
+       CHARACTER(KIND=C_CHAR), DIMENSION(*), INTENT(in) :: path      ! NUL-terminated
+     END FUNCTION samsim_b200_save_checkpoint
+
+     INTEGER(C_INT) FUNCTION samsim_b200_load_checkpoint(handle, path) BIND(C, NAME='samsim_b200_load_checkpoint')
+       IMPORT :: C_PTR, C_INT, C_CHAR
+       TYPE(C_PTR), VALUE :: handle
+       CHARACTER(KIND=C_CHAR), DIMENSION(*), INTENT(in) :: path
+     END FUNCTION samsim_b200_load_checkpoint
+
      FUNCTION samsim_b200_last_error() BIND(C, NAME='samsim_b200_last_error') RESULT(msg)
        IMPORT :: C_PTR
        TYPE(C_PTR) :: msg
@@ -278,6 +304,14 @@ CONTAINS
     CALL put_sc(h, SC_TTOP_WARM, -5._C_DOUBLE)    ! literals of sub_test1 / sub_test4: identity values
     CALL put_sc(h, SC_TTOP_COLD, -10._C_DOUBLE)
     CALL put_sc(h, SC_OFLUX_AMP, 7._C_DOUBLE)
+    IF (bgc_flag == 2) THEN                       ! passive tracers: bgc_abs(:,k) is a contiguous column
+       CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_BGC_ABS1, bgc_abs(:,1), 0, 1), 'bgc_abs(:,1)')
+       CALL put_sc(h, SC_BGC_BOTTOM1, bgc_bottom(1));  CALL put_sc(h, SC_BGC_TOTAL1, bgc_total(1))
+       IF (N_bgc >= 2) THEN
+          CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_BGC_ABS2, bgc_abs(:,2), 0, 1), 'bgc_abs(:,2)')
+          CALL put_sc(h, SC_BGC_BOTTOM2, bgc_bottom(2));  CALL put_sc(h, SC_BGC_TOTAL2, bgc_total(2))
+       END IF
+    END IF
     ibuf(1) = N_active
     CALL b200_check(samsim_b200_set_int(h, SAMSIM_INT_N_ACTIVE, ibuf, 0, 1), 'N_active')
     ibuf(1) = styropor_flag
@@ -333,6 +367,14 @@ CONTAINS
     CALL get_sc(h, SC_MTO1, melt_thick_output(1)); CALL get_sc(h, SC_MTO2, melt_thick_output(2))
     CALL get_sc(h, SC_MTO3, melt_thick_output(3)); CALL get_sc(h, SC_FREEBOARD, freeboard)
     CALL get_sc(h, SC_T_FREEZE, T_freeze);        CALL get_sc(h, SC_MELT_ERR, melt_err)
+    IF (bgc_flag == 2) THEN
+       CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_BGC_ABS1, bgc_abs(:,1), 0, 1), 'bgc_abs(:,1)')
+       CALL get_sc(h, SC_BGC_BOTTOM1, bgc_bottom(1))
+       IF (N_bgc >= 2) THEN
+          CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_BGC_ABS2, bgc_abs(:,2), 0, 1), 'bgc_abs(:,2)')
+          CALL get_sc(h, SC_BGC_BOTTOM2, bgc_bottom(2))
+       END IF
+    END IF
     CALL b200_check(samsim_b200_get_int(h, SAMSIM_INT_N_ACTIVE, ibuf, 0, 1), 'N_active')
     N_active = ibuf(1)
     CALL b200_check(samsim_b200_get_int(h, SAMSIM_INT_STYROPOR_FLAG, ibuf, 0, 1), 'styropor_flag')
