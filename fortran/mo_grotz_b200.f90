@@ -40,8 +40,7 @@ CONTAINS
     TYPE(C_PTR)            :: h
     TYPE(samsim_config_t)  :: cfg
     INTEGER(C_INT64_T)     :: n, done, total
-    LOGICAL                :: wrote
-    INTEGER                :: k
+    LOGICAL                :: wrote                 ! (the layer index k is mo_data's)
     REAL(C_DOUBLE), ALLOCATABLE :: series(:), snap_sc(:), snap_ar(:,:)
     REAL(wp), ALLOCATABLE  :: o_T(:), o_psi_s(:), o_thick(:), o_S_bu(:), o_ray(:), o_psi_l(:), o_perm(:), o_fv(:), &
          &                    o_fh(:), o_psi_g(:)
