@@ -229,10 +229,22 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: samsim_b200 has no CPU path (use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # keep stdout to the one JSON line: with NCCL_DEBUG set, NCCL writes its version banner / log to stdout
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # stdout carries exactly one JSON line: NCCL prints its version banner (and, with NCCL_DEBUG set, its log) to
+        # stdout when the communicator is created, i.e. at the first collective -- do that with fd 1 pointing at stderr
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     from samsim_b200 import api, distributed as D
 
