@@ -203,7 +203,10 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
   double temp1 = 0.0, temp2 = 0.0;
   {
     double fq_k = flQ1;
-    double ps_k = ps1, pl_k = pl1, pg_k = pg1, th_k = th1, T_k = T1;
+    // sub_fl_Q (mo_thermo_functions.f90:201-224): R = thick_1/(2 k_1) + thick_2/(2 k_2).  The half resistance of a
+    // layer is the same expression whether the layer is the upper or the lower one of a pair, so it is evaluated
+    // once per layer and carried (one division per layer instead of two, same bits).
+    double hr_k = th1 / (2.0 * (ps1 * k_s + pl1 * k_l + pg1 * 0.0)), T_k = T1;
     const double rad = fl_rad_Na * dt;
     SAMSIM_LOOP
     for (int k = 1; k <= Na; k++) {
@@ -213,11 +216,14 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
         c.H_abs().prefetch(kp);
       }
       double fq_kp1;
-      double ps_n = 0.0, pl_n = 0.0, pg_n = 0.0, th_n = 0.0, T_n = 0.0;
+      double hr_n = 0.0, T_n = 0.0;
       if (k < Na) {
         // psi_g enters k = psi_s*k_s + psi_l*k_l + psi_g*0._wp only as +-0 (psi_g is a finite volume fraction, k > 0)
-        ps_n = c.psi_s()[k + 1]; pl_n = c.psi_l()[k + 1]; pg_n = 0.0; th_n = c.thick()[k + 1]; T_n = c.T()[k + 1];
-        fq_kp1 = fl_Q_between(ps_k, pl_k, pg_k, th_k, T_k, ps_n, pl_n, pg_n, th_n, T_n);  // :272-274
+        const double ps_n = c.psi_s()[k + 1], pl_n = c.psi_l()[k + 1], th_n = c.thick()[k + 1];
+        T_n = c.T()[k + 1];
+        hr_n = th_n / (2.0 * (ps_n * k_s + pl_n * k_l + 0.0 * 0.0));
+        const double R = hr_k + hr_n;
+        fq_kp1 = (T_n - T_k) / R;  // :272-274
         if (c.want_state) c.fl_Q()[k + 1] = fq_kp1;  // fl_Q(2:N_active) is never read back by the loop body; N_active moves by
                                                      // at most 1 per step, so a stale interior entry is always overwritten by a later :262
       } else {
@@ -230,7 +236,7 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
       c.H_abs()[k] = H;
       temp2 = temp2 + H;                 // :305 sum(H_abs) after the update (layer 1 re-added below if coupling changes it)
       fq_k = fq_kp1;
-      ps_k = ps_n; pl_k = pl_n; pg_k = pg_n; th_k = th_n; T_k = T_n;
+      hr_k = hr_n; T_k = T_n;
     }
     temp1 = temp1 + SCV(c, SC_H_ABS_SNOW);
     SAMSIM_LOOP
