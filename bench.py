@@ -362,7 +362,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             ncores = os.cpu_count() or 1
-            ncols_cpu, nsteps_cpu = 4 * ncores, 4000
+            ncols_cpu, nsteps_cpu = 4 * ncores, 50000   # ~10 s of CPU work on all host cores
             rate, times = cpu_oracle_rate(st, sites, ncols_cpu, nsteps_cpu, ncores)
             line["cpu_baseline"] = {"value": rate, "unit": "column-timesteps/s", "cores": ncores, "kind": "port",
                                     "sample": f"{ncols_cpu} of the {total} columns x {nsteps_cpu} model steps, one column per thread "
