@@ -45,6 +45,8 @@ SITES = ["sheba", "70N00W", "75N00W", "75N180E", "80N00E", "80N90E", "85N180E", 
 # per column-timestep from the mid-January SHEBA state (N_active = 100).
 F_ALG_FLOP_PER_COLUMN_STEP = 112930.0
 B_ALG_BYTES_PER_COLUMN_STEP = 2 * 4 * 100 * 8  # read+write of m, S_abs, H_abs, thick once per model step
+NCU_DIGEST = "r1h_ncu_step_kernel.json"          # committed ncu --set full digest of samsim_step_kernel
+NCU_DIGEST_COLUMN_STEPS = 262144 * 16            # columns x model steps of the launch captured there
 
 
 def load_state(rec: int) -> dict:
@@ -339,6 +341,20 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         per_gpu_rate = kernel_rate / world
         achieved_tf = per_gpu_rate * F_ALG_FLOP_PER_COLUMN_STEP / 1e12
+        # DRAM traffic of the step kernel from the committed ncu capture (profiles/): bytes per column-step there,
+        # scaled to the columns x steps of one launch here (None if the digest is missing)
+        traffic, traffic_src = None, None
+        try:
+            dig = json.loads((ROOT / "profiles" / NCU_DIGEST).read_text())
+            m = dig["metrics"]
+            unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Tbyte": 1e12, "Kbyte": 1e3, "byte": 1.0}
+            dram = sum(float(m[k][0]) * unit[m[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            per_colstep = dram / NCU_DIGEST_COLUMN_STEPS
+            traffic = per_colstep * per * MODEL_STEPS
+            traffic_src = (f"profiles/{NCU_DIGEST}: {per_colstep / 1e3:.1f} KB of DRAM traffic per column-step (ncu --set full, "
+                           f"{NCU_DIGEST_COLUMN_STEPS} column-steps in the captured launch) x the column-steps of one launch here")
+        except Exception:
+            pass
         line = {
             "metric": "column-timesteps/sec (FP64, 100 layers)", "value": value, "unit": "column-timesteps/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -348,7 +364,8 @@ def main():
             "e2e": {"value": col_steps / wall_b_s, "unit": "column-timesteps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / fp64_peak, "traffic": None,
+                         "frac": achieved_tf / fp64_peak, "traffic": traffic, "traffic_unit": "bytes of DRAM traffic per launch",
+                         "traffic_source": traffic_src,
                          "peak_source": "DFMA micro-benchmark on this GPU in this run (samsim_b200_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                          "flop_per_column_step": F_ALG_FLOP_PER_COLUMN_STEP,
                          "kernel": "samsim_step_kernel", "kernel_ms_per_launch": kern_s / max(launches, 1) * 1e3,
