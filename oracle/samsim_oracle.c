@@ -8,6 +8,14 @@
  * of libm: identical when both link glibc) and in x**2._wp, x**3._wp, x**4._wp, which
  * this file evaluates by pow() in the libm build and by multiplication in the det build.
  *
+ * PARITY PINNED: checked against the reference's own golden output (tests/test_oracle_golden.py, fixtures from
+ * reference_output/ via tools/make_fixtures.py): testcase 1 -- all 72 records x 90 layers of every per-layer file
+ * at print precision, N_active exact, and the four passive-tracer files to their 8 printed decimals; SHEBA --
+ * T2m in all digits, T_top (17 digits) to 1e-13..1e-10, melt / flushing / permeability files to 8 digits and
+ * N_active exact through record 347 (one full year) with the snow_precip revision the golden run was made with
+ * (-DSAM_VARIANT_SNOW_T2M), the later divergence being the model's own 1-ulp sensitivity.
+ * The Fortran reference itself cannot be compiled in this image (no Fortran compiler), so there is no oracle/_ref.
+ *
  * Two math back-ends, selected at compile time:
  *   default            : glibc libm (what the reference binary calls)
  *   -DSAM_DETMATH      : samsim_b200/csrc/detmath.h (bit-reproducible on the GPU); this
