@@ -266,7 +266,7 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
 // (they are otherwise only consumed by S8); `snap` receives the S8 record.
 // Phase synchronisation: with SAMSIM_SYNC=1 every warp of the block passes the same barrier between groups of
 // sub-steps, so all warps of the block execute the same few KB of code at the same time.  The step kernel is
-// ~600 KB of SASS and instruction fetch (stall_no_instruction), not the FP64 pipe, limits it otherwise.  The
+// ~300 KB of SASS and instruction fetch (stall_no_instruction), not the FP64 pipe, limits it otherwise.  The
 // barriers sit at block-uniform points: failed / padding columns skip the phase bodies but not the barriers.
 #ifndef SAMSIM_SYNC
 #define SAMSIM_SYNC 1
