@@ -73,7 +73,11 @@ struct Lay {
   // non-blocking L1 prefetch of layer k (sweeps are latency bound: one 256-byte warp request per layer and
   // array, no spatial reuse between layers); k is clamped by the callers to [0, Nlayer+1]
   __device__ __forceinline__ void prefetch(int k) const {
+#ifndef SAMSIM_HOST_BUILD   // (tests/hostbuild compiles these device functions for the host: no PTX there)
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p + (unsigned)k * ls));
+#else
+    (void)k;
+#endif
   }
 };
 // Layer loops are not unrolled: the step kernel is instruction-fetch sensitive (see step.cuh, SAMSIM_SYNC) and the

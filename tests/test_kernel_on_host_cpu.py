@@ -1,0 +1,93 @@
+"""The CUDA device functions (samsim_b200/csrc/step.cuh, physics.cuh) compiled for the HOST by
+tests/hostbuild/kernel_on_host.cpp and advanced next to the oracle: every state array, scalar and integer must be
+bit-identical, exactly like tests/test_parity_gpu.py demands of the GPU build.  This puts the kernel's own logic --
+fused sweeps, memoised forward sums, lazy Rayleigh numbers, tracer replay, launch-boundary handling -- under the
+no-GPU test stage.  It is a test harness: the product has no CPU path (see test_cabi_cpu.py)."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+from hostbuild import hostkernel as hk  # noqa: E402
+from oracle import parity_util as pu  # noqa: E402
+
+
+def _fmt(bad, n=10):
+    return "\n".join(bad[:n]) + (f"\n... {len(bad)} mismatches" if len(bad) > n else "")
+
+
+def _from_oracle(col):
+    k = hk.HostKernel(pu.config_from_oracle(col))
+    k.load_state(col.state())
+    return k
+
+
+def _state(z, j):
+    p = f"state{j}_"
+    return {k[len(p):]: (z[k] if z[k].ndim else z[k].item()) for k in z.files if k.startswith(p)}
+
+
+def _advance(col, k, chunks):
+    for n in chunks:  # every chunk is one "launch": S4 reuse restarts, ray is exact at its last step
+        assert col.step(n) == 0
+        assert k.step(n) == 0
+        bad = pu.compare_column(col, k, 0, label=f"+{n}: ")
+        assert not bad, _fmt(bad)
+
+
+@pytest.mark.parametrize("testcase,chunks", [
+    (1, (1, 1, 7, 100, 3493, 3601, 12000)),          # plate cooling, NaCl, two tracers, first output records
+    (2, (1, 2, 5000, 15000)),                         # tank + tracers, boundflux 3
+    (3, (1, 2, 100000, 60000)),                       # notzflux, snow, 20-layer grid filling up
+    (5, (1, 1, 3000, 4000)),                          # full grid from the start, top melt
+    (6, (1, 2, 70000)),                               # small tank, one tracer, dt 0.5 s
+    (9, (1, 2, 12000)),
+])
+def test_device_code_on_host_equals_oracle_from_init(oracle_mod, testcase, chunks):
+    col = oracle_mod.Column(testcase, "det")
+    _advance(col, _from_oracle(col), chunks)
+
+
+@pytest.mark.parametrize("rec,chunks", [
+    (60, (1, 500, 2500)), (100, (1, 700, 1500)), (200, (3, 400, 1200)), (330, (1, 900, 1500)),
+    (345, (2, 600, 1500)), (400, (1, 800, 1200)),
+])
+def test_device_code_on_host_equals_oracle_in_the_sheba_year(oracle_mod, golden_dir, rec, chunks):
+    """Restart states of the SHEBA run: freeze-up, winter growth, full grid, melt onset with flushing, bare-ice melt
+    with layer merges, late-summer bottom melt."""
+    z = np.load(golden_dir / "sheba_oracle_states.npz")
+    F = np.load(golden_dir / "forcing_era.npz")["sheba"]
+    col = oracle_mod.Column(4, "det")
+    col.set_forcing(*F)
+    col.load_state(_state(z, rec))
+    k = _from_oracle(col)
+    k.set_forcing(F)
+    _advance(col, k, chunks)
+
+
+def test_device_code_on_host_output_record_and_simple_parametrisations(oracle_mod, golden_dir):
+    """S8 record captured by the device code = what the oracle hands to output(); testcase 7 switches to
+    fl_grav_drain_simple / flush4 / flood_simple."""
+    z = np.load(golden_dir / "sheba_oracle_states.npz")
+    F = np.load(golden_dir / "forcing_era.npz")["sheba"]
+    col = oracle_mod.Column(4, "det")
+    col.set_forcing(*F)
+    col.load_state(_state(z, 200))
+    col.record_outputs()
+    k = _from_oracle(col)
+    k.set_forcing(F)
+    n = 8641 - col.int("n_time_out") + 5  # crosses the next output step
+    assert col.step(n) == 0 and k.step(n) == 0 and len(col.records) >= 1
+    rec, snap = col.records[-1], k.snapshot()
+    for name in ("T", "psi_s", "thick", "S_bu", "ray", "psi_l", "perm", "flush_v", "flush_h", "psi_g"):
+        assert pu.same_bits(np.asarray(rec[name])[: len(snap[name])], snap[name]).all(), name
+    for name in ("freeboard", "thick_snow", "energy_stored", "total_resist", "thickness", "bulk_salin", "grav_drain", "T_top"):
+        assert pu.same_bits(rec[name], snap[name]), name
+    col7 = oracle_mod.Column(7, "det")
+    col7.set_forcing(*F)
+    assert col7.step(880000) == 0 and col7.int("N_active") > 5
+    k7 = _from_oracle(col7)
+    k7.set_forcing(F)
+    _advance(col7, k7, (1, 3000, 6000))
