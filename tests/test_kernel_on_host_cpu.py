@@ -91,3 +91,26 @@ def test_device_code_on_host_output_record_and_simple_parametrisations(oracle_mo
     k7 = _from_oracle(col7)
     k7.set_forcing(F)
     _advance(col7, k7, (1, 3000, 6000))
+
+
+def test_device_code_on_host_with_impermeable_layers(oracle_mod, golden_dir):
+    """fl_grav_drain's `minval(perm(k:N_active-1)) < 1e-14 -> harmonic_perm = 0` branch (mo_grav_drain.f90:112-113):
+    a band of nearly fresh layers in the mid-winter column makes the layers above it non-draining while the layers
+    below keep their Rayleigh numbers."""
+    z = np.load(golden_dir / "sheba_oracle_states.npz")
+    F = np.load(golden_dir / "forcing_era.npz")["sheba"]
+    st = _state(z, 200)
+    st["S_abs"] = np.array(st["S_abs"], dtype=np.float64)
+    st["S_abs"][35:45] *= 0.02
+    col = oracle_mod.Column(4, "det")
+    col.set_forcing(*F)
+    col.load_state(st)
+    k = _from_oracle(col)
+    k.set_forcing(F)
+    _advance(col, k, (1, 2, 50, 400))
+    psi_l = col.array("psi_l")[: col.int("N_active") - 1]
+    perm = 1e-17 * (1000.0 * np.abs(psi_l)) ** 3.10
+    assert (perm < 1e-14).any() and (perm[-10:] >= 1e-14).all(), "the impermeable band is not there"
+    ray = col.array("ray")
+    j_last = int(np.nonzero(perm < 1e-14)[0].max())
+    assert (ray[: j_last + 1] == 0.0).all() and (ray[j_last + 1: col.int("N_active") - 1] > 0.0).any()
