@@ -114,3 +114,43 @@ def test_device_code_on_host_with_impermeable_layers(oracle_mod, golden_dir):
     ray = col.array("ray")
     j_last = int(np.nonzero(perm < 1e-14)[0].max())
     assert (ray[: j_last + 1] == 0.0).all() and (ray[j_last + 1: col.int("N_active") - 1] > 0.0).any()
+
+
+def _lab_series(n):
+    """Synthetic per-second lab inputs (the reference's 2017_input files are not shipped): Tice, snowfall, heat, styropor."""
+    t = np.arange(n, dtype=np.float64)
+    Tice = -5.0 - 10.0 * (1.0 - np.cos(2.0 * np.pi * t / 86400.0))
+    snow = np.where((t >= 2 * 3600) & (t < 3 * 3600), 1e-7, 0.0)
+    heat = np.full(n, 5.0)
+    sty = np.where((t >= 4 * 3600) & (t < 5 * 3600), 1.0, 0.0)
+    return np.stack([Tice, snow, heat, sty])
+
+
+@pytest.mark.parametrize("testcase", [101, 104])
+def test_device_code_on_host_lab_tank(oracle_mod, testcase):
+    """Config 3 (lab tank, Nlayer 200, boundflux 3, tank salinity feedback, lab snow, styropor)."""
+    n = 22000
+    series = _lab_series(n) * np.array([1.0 + 0.03 * (testcase - 101), 1.5, 1.0, 1.0])[:, None]
+    col = oracle_mod.Column(testcase, "det")
+    col.set_lab_forcing(*series)
+    k = _from_oracle(col)
+    k.set_lab_forcing(series)
+    _advance(col, k, (1, 2, 3598, 3, 9000, 9000))
+    assert col.int("N_active") >= 3
+
+
+def test_device_code_on_host_perturbed_forcing_and_prescribed_salinity(oracle_mod, golden_dir):
+    """value*scale + offset forcing of one column (the device interpolates the base series) against an oracle fed the
+    perturbed series; prescribe_flag 2 (mo_grotz.f90:482-497) on testcase 1."""
+    z = np.load(golden_dir / "sheba_oracle_states.npz")
+    F = np.load(golden_dir / "forcing_era.npz")["sheba"]
+    scale, offset = np.array([1.07, 0.96, 1.0, 1.4]), np.array([0.0, 0.0, -1.7, 0.0])
+    col = oracle_mod.Column(4, "det")
+    col.set_forcing(*[F[q] * scale[q] + offset[q] for q in range(4)])
+    col.load_state(_state(z, 100))
+    k = _from_oracle(col)
+    k.set_forcing(F, scale, offset)
+    _advance(col, k, (1, 1081, 1500))
+    col1 = oracle_mod.Column(1, "det")
+    col1.set_int("prescribe_flag", 2)
+    _advance(col1, _from_oracle(col1), (1, 4000, 16000))
