@@ -1,0 +1,58 @@
+"""Fuzz the device code (compiled for the host, tests/hostbuild) against the oracle: random restart states of the
+SHEBA year, random forcing perturbations, random edits of the column, random launch chunking.  Every state value must
+stay bit-identical.  Usage: python tools/fuzz_host_kernel.py [trials] [seed]"""
+import sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import numpy as np
+from hostbuild import hostkernel as hk
+from oracle import oracle, parity_util as pu
+
+trials = int(sys.argv[1]) if len(sys.argv) > 1 else 50
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+rng = np.random.default_rng(seed)
+z = np.load(ROOT / "tests/golden/sheba_oracle_states.npz")
+F = np.load(ROOT / "tests/golden/forcing_era.npz")["sheba"]
+recs = sorted({int(k.split("_")[0][5:]) for k in z.files if k.startswith("state") and k.split("_")[0][5:].isdigit()})
+nbad = 0
+for t in range(trials):
+    rec = int(rng.choice(recs))
+    p = f"state{rec}_"
+    st = {k[len(p):]: (z[k] if z[k].ndim else z[k].item()) for k in z.files if k.startswith(p)}
+    scale = np.array([rng.uniform(0.5, 1.5), rng.uniform(0.8, 1.15), 1.0, rng.uniform(0.0, 3.0)])
+    offset = np.array([0.0, 0.0, rng.uniform(-15, 8), 0.0])
+    Na = int(st["N_active"])
+    edits = []
+    if Na > 4 and rng.random() < 0.6:   # salinity / enthalpy edits in a random band
+        a = int(rng.integers(0, Na - 1)); b = int(rng.integers(a + 1, Na))
+        f = float(rng.choice([0.02, 0.3, 0.8, 1.3]))
+        st["S_abs"] = np.array(st["S_abs"], dtype=np.float64); st["S_abs"][a:b] *= f
+        edits.append(f"S_abs[{a}:{b}]*={f}")
+    if rng.random() < 0.3:
+        st["oflux_amp"] = float(rng.uniform(0, 40)); edits.append(f"oflux {st['oflux_amp']:.1f}")
+    col = oracle.Column(4, "det")
+    col.set_forcing(*[F[q] * scale[q] + offset[q] for q in range(4)])
+    col.load_state(st)
+    if "oflux_amp" in st: col.set_scalar("oflux_amp", st["oflux_amp"])
+    k = hk.HostKernel(pu.config_from_oracle(col))
+    k.load_state(col.state())
+    k.set_forcing(F, scale, offset)
+    total = int(rng.integers(200, 6000))
+    done = 0
+    ok = True
+    while done < total and ok:
+        n = int(min(total - done, rng.choice([1, 2, 3, 17, 250, 1081, 3000])))
+        rc_o, rc_k = col.step(n), k.step(n)
+        done += n
+        bad = pu.compare_column(col, k, 0)
+        if rc_o != rc_k or bad:
+            ok = False
+            nbad += 1
+            print(f"MISMATCH trial {t} rec {rec} scale {scale} offset {offset} edits {edits} after {done} steps rc {rc_o}/{rc_k}")
+            for b_ in bad[:6]: print("   ", b_)
+        if rc_o != 0:
+            break
+    if ok:
+        print(f"trial {t}: rec {rec} {total} steps N_active {col.int('N_active')} status {col.int('status')} {edits} ok", flush=True)
+print("mismatching trials:", nbad)
