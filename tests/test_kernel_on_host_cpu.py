@@ -154,3 +154,30 @@ def test_device_code_on_host_perturbed_forcing_and_prescribed_salinity(oracle_mo
     col1 = oracle_mod.Column(1, "det")
     col1.set_int("prescribe_flag", 2)
     _advance(col1, _from_oracle(col1), (1, 4000, 16000))
+
+
+@pytest.mark.parametrize("what", ["H_abs layer 3 = -1e12 (getT cannot converge, STOP 99)",
+                                  "S_abs layer 5 negative (STOP 1337 / 21234 family)",
+                                  "thick layer 1 = 10 thick_0 (layer bookkeeping, STOP 7889 family)"])
+def test_device_code_on_host_stop_codes(oracle_mod, what):
+    """Reference STOPs become per-column status codes: the device code must report the oracle's code (or run on
+    exactly like it when the reference does not stop)."""
+    col = oracle_mod.Column(1, "det")
+    assert col.step(5000) == 0
+    st = col.state()
+    if what.startswith("H_abs"):
+        a = np.array(st["H_abs"]); a[2] = -1e12; st["H_abs"] = a
+    elif what.startswith("S_abs"):
+        a = np.array(st["S_abs"]); a[4] = -abs(a[4]); st["S_abs"] = a
+    else:
+        a = np.array(st["thick"]); a[0] = 10.0 * col.scalar("thick_0"); st["thick"] = a
+    ref = oracle_mod.Column(1, "det")
+    ref.load_state(st)
+    k = hk.HostKernel(pu.config_from_oracle(ref))
+    k.load_state(ref.state())
+    rc_o, rc_k = ref.step(50), k.step(50)
+    assert rc_o == rc_k, (rc_o, rc_k)
+    assert int(k.get_int("status")[0]) == rc_o
+    if rc_o == 0:
+        bad = pu.compare_column(ref, k, 0)
+        assert not bad, _fmt(bad)
