@@ -157,11 +157,11 @@ def test_device_code_on_host_perturbed_forcing_and_prescribed_salinity(oracle_mo
 
 
 @pytest.mark.parametrize("what", ["H_abs layer 3 = -1e12 (getT cannot converge, STOP 99)",
-                                  "S_abs layer 5 negative (STOP 1337 / 21234 family)",
-                                  "thick layer 1 = 10 thick_0 (layer bookkeeping, STOP 7889 family)"])
+                                  "S_abs layer 5 negative (soft path: PRINT + clamp, mo_grotz.f90:812-818)",
+                                  "thick layer 1 = 10 thick_0 (top_grow on consecutive steps)"])
 def test_device_code_on_host_stop_codes(oracle_mod, what):
-    """Reference STOPs become per-column status codes: the device code must report the oracle's code (or run on
-    exactly like it when the reference does not stop)."""
+    """Reference STOPs become per-column status codes: the device code must report the oracle's code, and take the
+    reference's soft paths (clamp and continue) exactly like it where the reference does not stop."""
     col = oracle_mod.Column(1, "det")
     assert col.step(5000) == 0
     st = col.state()
