@@ -21,9 +21,21 @@ nbad = 0
 
 def other_testcase(t):
     """testcases 1, 2, 3, 5, 6, 9 from init with random boundary values (and testcase 1's tracers)"""
-    tc = int(rng.choice([1, 1, 2, 3, 5, 6, 9]))
+    tc = int(rng.choice([1, 1, 2, 3, 5, 6, 9, 101, 103, 105]))
     col = oracle.Column(tc, "det")
     edits = []
+    lab = None
+    if tc > 100:   # synthetic per-second lab inputs (the reference's 2017_input files are not shipped)
+        n = 40000
+        tt = np.arange(n, dtype=np.float64)
+        amp, mean = float(rng.uniform(2, 14)), float(rng.uniform(-12, -2))
+        snow0 = int(rng.integers(0, 20000))
+        lab = np.stack([mean - amp * (1.0 - np.cos(2.0 * np.pi * tt / 86400.0)),
+                        np.where((tt >= snow0) & (tt < snow0 + 3600), float(rng.choice([0.0, 1e-7, 4e-7])), 0.0),
+                        np.full(n, float(rng.uniform(0, 15))),
+                        np.where((tt >= 9000) & (tt < 15000), float(rng.integers(0, 2)), 0.0)])
+        col.set_lab_forcing(*lab)
+        edits = [f"lab mean {mean:.1f} amp {amp:.1f}"]
     if tc == 1:
         w, c_ = float(rng.uniform(-9, -1)), float(rng.uniform(-25, -6))
         col.set_scalar("ttop_warm", w); col.set_scalar("ttop_cold", c_); col.set_scalar("T_top", w)
@@ -35,7 +47,9 @@ def other_testcase(t):
         col.set_scalar("alpha_flux_instable", float(rng.uniform(10, 40)))
     k = hk.HostKernel(pu.config_from_oracle(col))
     k.load_state(col.state())
-    total = int(rng.integers(500, {1: 60000, 2: 30000, 3: 250000, 5: 20000, 6: 150000, 9: 30000}[tc]))
+    if lab is not None:
+        k.set_lab_forcing(lab)
+    total = int(rng.integers(500, {1: 60000, 2: 30000, 3: 250000, 5: 20000, 6: 150000, 9: 30000}.get(tc, 38000)))
     done, ok = 0, True
     while done < total and ok:
         n = int(min(total - done, rng.choice([1, 2, 5, 100, 3601, 20000])))
