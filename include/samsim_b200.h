@@ -110,8 +110,67 @@ typedef enum {
   SAMSIM_INT_N_ACTIVE = 0, /* mo_data.f90:66 */
   SAMSIM_INT_STATUS,       /* 0 or the reference's STOP code (99, 98, 16, 345, 9876, 21234, 1337, 431, 7889) */
   SAMSIM_INT_STYROPOR_FLAG,/* :69 */
+  SAMSIM_INT_EVENTS0,      /* branch events 0..31 (samsim_event_id): bit set once the column has executed the branch */
+  SAMSIM_INT_EVENTS1,      /* branch events 32..63 */
   SAMSIM_INT_COUNT
 } samsim_int_id;
+
+/* Branch events.  Not in the reference (it has one column and PRINTs under debug_flag 2, e.g.
+ * mo_layer_dynamics.f90:78-80): a per-column bit mask that records which rarely taken branches of the path a column
+ * has executed since the words were last cleared (samsim_b200_set_int with zeros).  Bit id of
+ * SAMSIM_INT_EVENTS0 (id < 32) / SAMSIM_INT_EVENTS1 (id - 32).  The parity tests assert these next to the CPU
+ * oracle's counters of the same branches, so a test that claims to cover a branch proves that it ran. */
+typedef enum {
+  SAMSIM_EV_FLOOD = 0,            /* flood                          mo_flood.f90:55 */
+  SAMSIM_EV_FLOOD_NEG_FREE,       /*   instant flooding beyond neg_free          :117-138 */
+  SAMSIM_EV_FLOOD_SIMPLE,         /* flood_simple                   mo_flood.f90:167 */
+  SAMSIM_EV_FLUSH3,               /* flush3                         mo_flush.f90:70 */
+  SAMSIM_EV_FLUSH4,               /* flush4                         mo_flush.f90:253 */
+  SAMSIM_EV_FLUSH_INLINE,         /* flush_flag 4                   mo_grotz.f90:704-713 */
+  SAMSIM_EV_STYROPOR,             /* sub_fl_Q_styropor              mo_thermo_functions.f90:276 (call: mo_heat_fluxes.f90:202-258) */
+  SAMSIM_EV_SNOW_THERMO,          /* snow_thermo (snow_flush_flag 0) mo_snow.f90:212 */
+  SAMSIM_EV_SNOW_THERMO_MELTWATER,/* snow_thermo_meltwater          mo_snow.f90:331 */
+  SAMSIM_EV_SNOW_WET,             /*   saturated-layer branch       :271 / :398 */
+  SAMSIM_EV_SNOW_MERGE,           /*   snow without gas joins layer 1 :296 / :431 */
+  SAMSIM_EV_SNOW_COMPACTION,      /*   psi_s_old > psi_s_snow       :253-263 */
+  SAMSIM_EV_SNOW_COUPLING_ITER,   /* snow_coupling, iterative branch mo_snow.f90:87-98 */
+  SAMSIM_EV_SNOW_COUPLING_WARM1,  /*   :76-80 */
+  SAMSIM_EV_SNOW_COUPLING_WARM2,  /*   :81-85 */
+  SAMSIM_EV_SNOW_PRECIP,          /* snow_precip                    mo_snow.f90:123 */
+  SAMSIM_EV_SNOW_PRECIP_0,        /* snow_precip_0                  mo_snow.f90:167 */
+  SAMSIM_EV_MELT_SNOW_ALL,        /* sub_melt_snow, all snow floods mo_functions.f90:453 */
+  SAMSIM_EV_MELT_SNOW_PART,       /*   partial                      :461 */
+  SAMSIM_EV_BOTTOM_MELT,          /* bottom_melt                    mo_layer_dynamics.f90:85 -> :341 */
+  SAMSIM_EV_BOTTOM_MELT_SIMPLE_A, /* bottom_melt_simple, N_active < Nlayer   :95 */
+  SAMSIM_EV_BOTTOM_MELT_SIMPLE_B, /* bottom_melt_simple, grid full, middle = thick_0   :106 */
+  SAMSIM_EV_BOTTOM_GROWTH_SIMPLE, /* bottom_growth_simple           :122 -> :537 */
+  SAMSIM_EV_BOTTOM_GROWTH,        /* bottom_growth                  :132 -> :438 */
+  SAMSIM_EV_TOP_GROW_A,           /* top_grow, N_active <= N_top    :656 */
+  SAMSIM_EV_TOP_GROW_B,           /* top_grow, N_top < N_active < Nlayer   :665 */
+  SAMSIM_EV_TOP_GROW_C,           /* top_grow, N_active == Nlayer   :679 */
+  SAMSIM_EV_TOP_MELT_A,           /* top_melt, N_active <= N_top    :244 */
+  SAMSIM_EV_TOP_MELT_B,           /* top_melt, middle layers at thick_0   :253 */
+  SAMSIM_EV_TOP_MELT_C,           /* top_melt, middle layers shrink :272 */
+  SAMSIM_EV_GRAV_DRAINED,         /* fl_grav_drain: a layer above ray_crit drained   mo_grav_drain.f90:145 */
+  SAMSIM_EV_SALT_CLAMP,           /* negative S_abs clamped         mo_grotz.f90:812-818 */
+  SAMSIM_EV_GAS_REFILL,           /* gas in the lowest layer replaced by ocean water   mo_grotz.f90:405-410 */
+  SAMSIM_EV_GETT_TFR_FALLBACK,    /* getT: iterate outside [-200, 0] restarts at T_fr   mo_thermo_functions.f90:101 */
+  SAMSIM_EV_GETT_SALTFREE,        /* getT: salt-free branch         :127-137 */
+  SAMSIM_EV_GETT_LIQUID,          /* getT: liquid layer             :138-140 */
+  SAMSIM_EV_HEAT_MELT,            /* sub_heat_fluxes: surface at the melting point   mo_heat_fluxes.f90:167-180 */
+  SAMSIM_EV_HEAT_THIN_SNOW,       /* sub_heat_fluxes: thin snow coupled to layer 1   :291-295 */
+  SAMSIM_EV_MELT_THICK_GAS,       /* sub_melt_thick: gas-fraction correction   mo_functions.f90:418-426 */
+  SAMSIM_EV_SNOW_MELTWATER_TO_ICE,/* snow melt water added to layer 1   mo_grotz.f90:677-685 */
+  SAMSIM_EV_PRESCRIBE,            /* prescribe_flag 2               mo_grotz.f90:482-497 */
+  SAMSIM_EV_GRAV_DRAIN_SIMPLE,    /* fl_grav_drain_simple           mo_grav_drain.f90:218 */
+  SAMSIM_EV_NOTZFLUX,             /* sub_notzflux                   mo_functions.f90:270 */
+  SAMSIM_EV_FLUSH3_CLAMP,         /* flush3: negative S_abs clamped mo_flush.f90:218-227 */
+  SAMSIM_EV_SCRUB,                /* layer below N_active scrubbed  mo_grotz.f90:772-783 */
+  SAMSIM_EV_MELT_THICK,           /* sub_melt_thick called          mo_functions.f90:386 */
+  SAMSIM_EV_TURB,                 /* sub_turb_flux                  mo_functions.f90:347 */
+  SAMSIM_EV_TANK,                 /* tank salinity                  mo_grotz.f90:573-578 */
+  SAMSIM_EV_COUNT
+} samsim_event_id;
 
 /* forcing kinds for samsim_b200_set_forcing, in sub_input's order of use */
 typedef enum { SAMSIM_F_FL_SW = 0, SAMSIM_F_FL_LW = 1, SAMSIM_F_T2M = 2, SAMSIM_F_PRECIP = 3, SAMSIM_F_COUNT = 4 } samsim_forcing_kind;
@@ -230,6 +289,7 @@ int samsim_b200_device_layout(samsim_handle_t h, void** arrays, void** scalars, 
                               int64_t* lstride);
 
 /* ---- unit known-answer entry points (device functions evaluated elementwise on the GPU) ---- */
+/* status_out[q]: STOP code (0 or 99) in the low 16 bits, the SAMSIM_EV_GETT_* bits of event word 1 shifted left by 16 */
 int samsim_b200_kat_getT(int32_t salt_flag, int32_t n, const double* H, const double* S_bu, const double* T_in,
                          double* T_out, double* phi_out, int32_t* status_out, int32_t device);
 /* fn: 0 S_br(a) 1 S_br(a,b) 2 ddT_S_br(a) 3 density(a,b) 4 T_freeze(a) 5 k_snow(a,b) 6 albedo(a,b)

@@ -78,6 +78,8 @@ def lib(backend: str = "det") -> C.CDLL:
     L.sam_set_int.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.sam_get_stat.restype = C.c_long
     L.sam_get_stat.argtypes = [C.c_void_p, C.c_char_p]
+    L.sam_event_name.restype = C.c_char_p
+    L.sam_event_name.argtypes = [C.c_int]
     L.sam_set_output_hook.argtypes = [C.c_void_p, _OUTPUT_FN]
     L.sam_math_backend.restype = C.c_char_p
     for f in ("sam_math_exp", "sam_math_sin"):
@@ -220,6 +222,19 @@ class Column:
 
     def stat(self, name: str) -> int:
         return self.L.sam_get_stat(self.h, name.encode())
+
+    def event_counts(self) -> dict:
+        """how often each rarely taken branch of the path ran (names = samsim_b200.api.EVENT_NAMES)"""
+        out, j = {}, 0
+        while True:
+            n = self.L.sam_event_name(j)
+            if n is None:
+                return out
+            out[n.decode()] = self.stat("ev_" + n.decode())
+            j += 1
+
+    def events(self) -> set:
+        return {n for n, v in self.event_counts().items() if v > 0}
 
     def state(self) -> dict:
         """Everything: arrays, double scalars and ints, by mo_data name."""

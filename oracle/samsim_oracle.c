@@ -101,6 +101,8 @@ static inline real r_abs(real a) { return fabs(a); }
 /* Fortran SIGN(a,b): |a| with the sign of b */
 static inline real r_sign(real a, real b) { return (b >= 0.0 && !signbit(b)) ? fabs(a) : -fabs(a); }
 
+#define EV(c, id) ((c)->ev[SAM_EV_##id]++) /* branch counter, see samsim_oracle.h */
+
 #define SAM_STOP(c, code)     \
   do {                        \
     (c)->status = (code);     \
@@ -168,7 +170,7 @@ void sam_getT(sam_col* c, real H, real S_bu, real T_in, real* T_out, real* phi_o
     i = 0;
     while (r_abs(f) > 1.0) { /* :99 ABS(f)>1_wp */
       T_0 = T;
-      if (T_0 > 0.0 || T_0 < -200.0) T_0 = T_fr; /* :101-103 */
+      if (T_0 > 0.0 || T_0 < -200.0) { T_0 = T_fr; EV(c, GETT_TFR_FALLBACK); } /* :101-103 */
       f = -latent_heat - H + latent_heat * S_bu / r_max(sam_func_S_br(c, T_0), 0.0000000001) + c_s * T_0 +
           c_s_beta * T_0 * T_0 / 2.0; /* :104 */
       {
@@ -182,6 +184,7 @@ void sam_getT(sam_col* c, real H, real S_bu, real T_in, real* T_out, real* phi_o
     }
     phi = 1.0 - S_bu / sam_func_S_br2(c, T, S_bu); /* :125 */
   } else if (S_bu < 0.001) { /* :127 */
+    EV(c, GETT_SALTFREE);
     if (H > 0.0) {
       phi = 0.0;
       T = H / c_l;
@@ -193,6 +196,7 @@ void sam_getT(sam_col* c, real H, real S_bu, real T_in, real* T_out, real* phi_o
       phi = -H / latent_heat;
     }
   } else {
+    EV(c, GETT_LIQUID);
     phi = 0.0; /* :139 */
   }
   *T_out = T;
@@ -349,8 +353,10 @@ static void sub_turb_flux(real T_bottom, real S_bu_bottom, real T, real* S_abs, 
 }
 
 /* sub_melt_thick, mo_functions.f90:386-428 */
-static void sub_melt_thick(real psi_l, real psi_s, real psi_g, real T, real T_freeze, real T_top, real fl_Q,
-                           real thick_snow, real dt, real* melt_thick, real* thick, real thick_min) {
+/* returns 1 when the gas-fraction correction (:418-426) ran (branch counter only) */
+static int sub_melt_thick(real psi_l, real psi_s, real psi_g, real T, real T_freeze, real T_top, real fl_Q,
+                          real thick_snow, real dt, real* melt_thick, real* thick, real thick_min) {
+  int gas = 0;
   *melt_thick = 0.0;
   if (thick_snow < thick_min && T_top >= T_freeze) { /* :396 */
     *melt_thick = -fl_Q - 2.0 * (psi_l * k_l + psi_s * k_s) / *thick * (T_freeze - T);
@@ -361,6 +367,7 @@ static void sub_melt_thick(real psi_l, real psi_s, real psi_g, real T, real T_fr
     *melt_thick = *thick * (1.0 - psi_s / psi_s_top_min);
   }
   if (*melt_thick > 0.0 && psi_g > gas_snow_ice2) { /* :418 */
+    gas = 1;
     if (*melt_thick > (psi_g - gas_snow_ice2) * *thick) {
       *melt_thick = *melt_thick - (psi_g - gas_snow_ice2) * *thick;
       *thick = *thick * (1.0 - (psi_g - gas_snow_ice2));
@@ -369,10 +376,11 @@ static void sub_melt_thick(real psi_l, real psi_s, real psi_g, real T, real T_fr
       *melt_thick = 0.0;
     }
   }
+  return gas;
 }
 
-/* sub_melt_snow, mo_functions.f90:443-474 */
-static void sub_melt_snow(real* melt_thick, real* thick, real* thick_snow, real* H_abs, real* H_abs_snow, real* m,
+/* sub_melt_snow, mo_functions.f90:443-474; returns 1 when all the snow went into the ice (:453), 0 for the partial branch */
+static int sub_melt_snow(real* melt_thick, real* thick, real* thick_snow, real* H_abs, real* H_abs_snow, real* m,
                           real* m_snow, real* psi_g_snow) {
   real shift = 1.0 / r_max(*psi_g_snow, 0.01) * *melt_thick;
   if (shift >= *thick_snow) {
@@ -383,6 +391,7 @@ static void sub_melt_snow(real* melt_thick, real* thick, real* thick_snow, real*
     *thick_snow = 0.0;
     *m_snow = 0.0;
     *H_abs_snow = 0.0;
+    return 1;
   } else {
     *H_abs = *H_abs + shift / *thick_snow * *H_abs_snow;
     *H_abs_snow = *H_abs_snow - shift / *thick_snow * *H_abs_snow;
@@ -392,6 +401,7 @@ static void sub_melt_snow(real* melt_thick, real* thick, real* thick_snow, real*
     *thick_snow = *thick_snow - shift;
     *melt_thick = 0.0;
   }
+  return 0;
 }
 
 /* ==========================================================================================
@@ -550,6 +560,7 @@ static void fl_grav_drain(sam_col* c) {
 
   for (k = 1; k <= N_active - 1; k++) { /* :144-171 */
     if (ray[k] > ray_mini && psi_s[k] > 0.001 && S_abs[k] / m[k] > 0.1 && S_br[k] > S_br[k + 1]) {
+      EV(c, GRAV_DRAINED);
       flux = x_grav * (ray[k] - ray_mini) * dt * thick[k];
       flux = r_min(flux, psi_l[k] * rho_l * thick[k]);
       S_abs[k] = S_abs[k] - flux * S_br[k];
@@ -663,11 +674,13 @@ static void snow_coupling(sam_col* c, real* H_abs_snow, real* phi_s, real* T_sno
   getT_aliased(c, *H_abs_snow / m_snow, S_abs_snow / m_snow, T_snow, phi_s, 5701); /* :73 */
   getT_aliased(c, *H, S_bu, T, phi, 5702);                                         /* :74 */
   if (*T > 0 && *H_abs <= -*H_abs_snow) { /* :76 */
+    EV(c, SNOW_COUPLING_WARM1);
     *H_abs_snow = *H_abs_snow + *H_abs;
     *H_abs = 0.0;
     getT_aliased(c, *H_abs_snow / m_snow, S_abs_snow / m_snow, T_snow, phi_s, 5701);
     getT_aliased(c, *H, S_bu, T, phi, 5702);
   } else if (*T > 0. && *H_abs > -*H_abs_snow) { /* :81 */
+    EV(c, SNOW_COUPLING_WARM2);
     *H_abs = (*H_abs + *H_abs_snow) * m / m_snow / (1.0 + m / m_snow);
     *H_abs_snow = *H_abs * m_snow / m;
     getT_aliased(c, *H_abs_snow / m_snow, S_abs_snow / m_snow, T_snow, phi_s, 5701);
@@ -682,6 +695,7 @@ static void snow_coupling(sam_col* c, real* H_abs_snow, real* phi_s, real* T_sno
       jj = jj + 1;
       *H = *H_abs / m;
       c->stat_coupling_iters++;
+      EV(c, SNOW_COUPLING_ITER);
       getT_aliased(c, *H_abs_snow / m_snow, S_abs_snow / m_snow, T_snow, phi_s, 5701);
       getT_aliased(c, *H, S_bu, T, phi, 5702);
     }
@@ -750,6 +764,7 @@ static void snow_thermo_any(sam_col* c, int meltwater, real* m, real* thick, rea
   S_bu_snow = *S_abs_snow / *m_snow;
   psi_s_old = *psi_s_snow;
 
+  if (meltwater) EV(c, SNOW_THERMO_MELTWATER); else EV(c, SNOW_THERMO);
   T_in = *T_snow;
   sam_getT(c, H_snow, S_bu_snow, T_in, T_snow, &phi_snow, 5700);
 
@@ -770,6 +785,7 @@ static void snow_thermo_any(sam_col* c, int meltwater, real* m, real* thick, rea
   }
 
   if (psi_s_old > *psi_s_snow && *psi_s_snow > 0.0) {
+    EV(c, SNOW_COMPACTION);
     if ((1.0 - phi_snow) > max_lwc) {
       *thick_snow = *thick_snow * (1.0 - (psi_s_old - *psi_s_snow) / psi_s_old);
     }
@@ -790,6 +806,7 @@ static void snow_thermo_any(sam_col* c, int meltwater, real* m, real* thick, rea
   if (!meltwater) {
     /* mo_snow.f90:271-309 */
     if ((1.0 - phi_snow) > max_lwc && *psi_g_snow > 0.0) {
+      EV(c, SNOW_WET);
       max_lwc_v = max_lwc * *m_snow / (rho_l * *thick_snow);
       sat_snow = *thick_snow * (*psi_l_snow - max_lwc_v);
       sat_snow = sat_snow / (1.0 - *psi_s_snow - max_lwc_v - r_min(gas_snow_ice2, *psi_g_snow));
@@ -804,6 +821,7 @@ static void snow_thermo_any(sam_col* c, int meltwater, real* m, real* thick, rea
       *H_abs_snow = *H_abs_snow - sat_snow * (1.0 - *psi_s_snow) * rho_l * c_l * *T_snow;
       *H_abs = *H_abs + sat_snow * (1.0 - *psi_s_snow) * rho_l * c_l * *T_snow;
     } else if (*psi_g_snow <= 0.0) {
+      EV(c, SNOW_MERGE);
       sat_snow = *thick_snow;
       *H_abs = *H_abs + *H_abs_snow;
       *m = *m + *m_snow;
@@ -817,6 +835,7 @@ static void snow_thermo_any(sam_col* c, int meltwater, real* m, real* thick, rea
     /* mo_snow.f90:398-449 */
     if ((1.0 - phi_snow) > max_lwc && *psi_l_snow > 0.0 && *psi_g_snow > 0.0) {
       real g;
+      EV(c, SNOW_WET);
       max_lwc_v = max_lwc * *m_snow / (rho_l * *thick_snow);
       psi_l_snow_slush = (*psi_l_snow - max_lwc_v) * (1.0 - c->k_snow_flush);
       psi_l_snow_flush = (*psi_l_snow - max_lwc_v) * c->k_snow_flush;
@@ -836,6 +855,7 @@ static void snow_thermo_any(sam_col* c, int meltwater, real* m, real* thick, rea
                     *melt_thick_snow * rho_l * c_l * *T_snow;
       *H_abs = *H_abs + sat_snow * (1.0 - *psi_s_snow - g) * rho_l * c_l * *T_snow;
     } else if (*psi_g_snow <= 0.0) {
+      EV(c, SNOW_MERGE);
       sat_snow = *thick_snow;
       *H_abs = *H_abs + *H_abs_snow;
       *m = *m + *m_snow;
@@ -907,6 +927,7 @@ static void flood(sam_col* c) {
   real flood_brine, shift_ice, shift_snow, shift, harmonic_perm;
   int k;
   c->stat_flood_calls++;
+  EV(c, FLOOD);
   for (k = 1; k <= N_active; k++) perm[k] = 1e-17 * M_POW(1000.0 * psi_l[k], 3.10); /* :73 */
   harmonic_perm = 0.0;
   for (k = 1; k <= N_active - 1; k++) harmonic_perm = harmonic_perm + thick[k] / perm[k]; /* :77-79 */
@@ -932,6 +953,7 @@ static void flood(sam_col* c) {
   c->thick_snow = c->thick_snow - shift_snow;
 
   if (freeboard + shift_ice < neg_free) { /* :117-138 */
+    EV(c, FLOOD_NEG_FREE);
     shift = neg_free - (freeboard + shift_ice);
     flood_brine = shift * (psi_g_snow)*rho_l;
     S_abs[N_active] = S_abs[N_active] + (c->S_bu_bottom - S_bu[N_active]) * flood_brine;
@@ -959,6 +981,7 @@ static void flood_simple(sam_col* c) {
   real shift = c->freeboard - neg_free;
   real flood_brine = -shift * c->psi_g_snow * rho_l;
   c->stat_flood_calls++;
+  EV(c, FLOOD_SIMPLE);
   thick[1] = thick[1] - shift;
   S_abs[1] = S_abs[1] + c->S_bu_bottom * flood_brine;
   H_abs[1] = H_abs[1] - shift / c->thick_snow * c->H_abs_snow;
@@ -988,6 +1011,7 @@ static void flush3(sam_col* c) {
   real konst, flush_total, loss_S_abs, loss_H_abs, sfh;
   int k;
   c->stat_flush_calls++;
+  EV(c, FLUSH3);
 
   for (k = 1; k <= N_active; k++) { /* :101-102 dummy arrays are DIMENSION(N_active) */
     flush_v[k] = 0.0;
@@ -1074,6 +1098,7 @@ static void flush3(sam_col* c) {
     real mn = S_abs[1]; /* :218 MINVAL(S_abs) all layers */
     for (k = 1; k <= Nlayer; k++) mn = r_min(mn, S_abs[k]);
     if (mn < -0.00000000000000000000000001) {
+      EV(c, FLUSH3_CLAMP);
       for (k = 1; k <= N_active; k++) S_abs[k] = r_max(S_abs[k], 0.0);
     }
   }
@@ -1086,6 +1111,7 @@ static void flush4(sam_col* c) {
   real *psi_l = c->psi_l, *thick = c->thick, *T = c->T, *S_abs = c->S_abs, *H_abs = c->H_abs, *m = c->m;
   real S_bu1 = S_abs[1] / m[1];
   int k;
+  EV(c, FLUSH4);
   H_abs[1] = H_abs[1] - c->melt_thick * rho_l * c_l * T[1];
   S_abs[1] = S_abs[1] - c->melt_thick * rho_l * sam_func_S_br2(c, T[1], S_bu1);
   thick[1] = thick[1] - c->melt_thick;
@@ -1145,10 +1171,12 @@ static void top_melt(sam_col* c, real* rho, real* H, real* S_bu) {
   }
 
   if (c->N_active <= N_top) { /* :247-254 */
+    EV(c, TOP_MELT_A);
     m[c->N_active] = 0.0; S_abs[c->N_active] = 0.0; H_abs[c->N_active] = 0.0; thick[c->N_active] = 0.0;
     BGC_EACH(q) bgc[q][c->N_active] = 0.0;
     c->N_active = c->N_active - 1;
   } else if (c->N_active > N_top && c->N_active <= Nlayer && thick[N_top + 1] / thick_0 < 1.00001) { /* :256-273 */
+    EV(c, TOP_MELT_B);
     for (k = N_top; k <= c->N_active - 1; k++) {
       m[k] = rho[k + 1] * thick_0;
       S_abs[k] = S_bu[k + 1] * rho[k + 1] * thick_0;
@@ -1161,6 +1189,7 @@ static void top_melt(sam_col* c, real* rho, real* H, real* S_bu) {
   }
 
   if (c->N_active == Nlayer && thick[N_top + 1] - thick_0 >= 0.000001) { /* :275-314 */
+    EV(c, TOP_MELT_C);
     loss_m = thick_0 * rho[N_top + 1];
     loss_S_abs = loss_m * S_bu[N_top + 1];
     loss_H_abs = loss_m * H[N_top + 1];
@@ -1331,6 +1360,7 @@ static void top_grow(sam_col* c, real* rho, real* H, real* S_bu) {
   }
 
   if (c->N_active <= N_top) { /* :659-665 */
+    EV(c, TOP_GROW_A);
     c->N_active = c->N_active + 1;
     m[c->N_active] = rho[c->N_active - 1] * thick_0;
     S_abs[c->N_active] = S_bu[c->N_active - 1] * thick_0 * rho[c->N_active - 1];
@@ -1338,6 +1368,7 @@ static void top_grow(sam_col* c, real* rho, real* H, real* S_bu) {
     BGC_EACH(q) bgc[q][c->N_active] = bulk[q][c->N_active - 1] * thick_0 * rho[c->N_active - 1];
     thick[c->N_active] = thick_0;
   } else if (c->N_active > N_top && c->N_active < Nlayer) { /* :668-680 */
+    EV(c, TOP_GROW_B);
     for (k = N_top + 1; k <= c->N_active; k++) {
       m[k] = rho[k - 1] * thick_0;
       S_abs[k] = S_bu[k - 1] * rho[k - 1] * thick_0;
@@ -1351,6 +1382,7 @@ static void top_grow(sam_col* c, real* rho, real* H, real* S_bu) {
     BGC_EACH(q) bgc[q][c->N_active] = bulk[q][c->N_active - 1] * thick_0 * rho[c->N_active - 1];
     thick[c->N_active] = thick_0;
   } else if (c->N_active == Nlayer) { /* :682-711 */
+    EV(c, TOP_GROW_C);
     loss_m = thick_0 * rho[N_top];
     loss_S_abs = loss_m * S_bu[N_top];
     loss_H_abs = loss_m * H[N_top];
@@ -1388,16 +1420,21 @@ static void layer_dynamics(sam_col* c) {
   c->stat_layer_events++;
   if (phi[Nlayer - 1] <= psi_s_min / 2.0 && phi[N_active] < 0.00001 && N_active == Nlayer &&
       thick[N_top + 1] / thick_0 > 1.000001 && bottom_flag == 1) { /* :85-86 */
+    EV(c, BOTTOM_MELT);
     bottom_melt(c, rho, H, S_bu);
   } else if (N_active > 1 && N_active < Nlayer && phi[N_active] < 0.00001 && phi[nm1] <= psi_s_min / 2.0 &&
              bottom_flag == 1) { /* :95-96 */
+    EV(c, BOTTOM_MELT_SIMPLE_A);
     bottom_melt_simple(c);
   } else if (N_active > 1 && phi[N_active] < 0.00001 && phi[nm1] <= psi_s_min / 2.0 &&
              (thick[N_top + 1] / thick_0) < 1.01 && bottom_flag == 1) { /* :106-107 */
+    EV(c, BOTTOM_MELT_SIMPLE_B);
     bottom_melt_simple(c);
   } else if (phi[N_active] > psi_s_min && N_active < Nlayer && bottom_flag == 1) { /* :122 */
+    EV(c, BOTTOM_GROWTH_SIMPLE);
     bottom_growth_simple(c);
   } else if (phi[Nlayer] > psi_s_min && bottom_flag == 1) { /* :132 */
+    EV(c, BOTTOM_GROWTH);
     bottom_growth(c, rho, H, S_bu);
   } else if (thick[1] > 1.5 * thick_0) { /* :145 */
     c->melt_thick_output[3] = c->melt_thick_output[3] - thick[1];
@@ -1487,6 +1524,7 @@ static void sub_heat_fluxes(sam_col* c) {
   if (c->boundflux_flag == 2) { /* :90-195 */
     c->albedo = sam_func_albedo(c->thick_snow, c->T_snow, psi_l[1], thick_min, c->albedo_flag); /* :94 */
     if (c->atmoflux_flag == 1) {
+      EV(c, NOTZFLUX);
       sub_notzflux(c->time + 86400.0 * 180.0, &c->fl_sw, &c->fl_rest);
     } else if (c->atmoflux_flag == 2) { /* :97-111 */
       const int tc = c->time_counter;
@@ -1539,6 +1577,7 @@ static void sub_heat_fluxes(sam_col* c) {
     }
 
     if (c->T_top > c->T_freeze && N_active > 1) { /* :167-180 */
+      EV(c, HEAT_MELT);
       temp1 = emi * sigma * P4(c->T_freeze + zeroK) - (1.0 - c->albedo) * (1.0 - pen) * c->fl_sw - c->fl_rest;
       if (c->thick_snow >= thick_min) {
         c->fl_q_snow = temp1;
@@ -1573,6 +1612,7 @@ static void sub_heat_fluxes(sam_col* c) {
         fl_Q[1] = c->alpha_flux_stable * (c->T_top - c->T2m);
       }
       if (c->thick_snow == 0.0 && c->lab_snow_flag == 1 && c->styropor_flag == 1) {
+        EV(c, STYROPOR);
         fl_Q[1] = fl_Q[1] * c->k_styropor; /* sub_fl_Q_styropor, mo_thermo_functions.f90:276-287 */
       }
     } else if (c->lab_snow_flag == 1) { /* :224-256 */
@@ -1616,6 +1656,7 @@ static void sub_heat_fluxes(sam_col* c) {
   }
 
   if (c->thick_snow >= thick_min / 100.0 && c->thick_snow < thick_min) { /* :291-295 */
+    EV(c, HEAT_THIN_SNOW);
     c->H_abs_snow = c->H_abs_snow - c->fl_q_snow * dt;
     snow_coupling(c, &c->H_abs_snow, &c->phi_s, &c->T_snow, &H_abs[1], &c->H[1], &c->phi[1], &T[1], c->m_snow,
                   c->S_abs_snow, m[1], c->S_bu[1]);
@@ -1681,14 +1722,18 @@ static void one_step(sam_col* c) {
   /* ---- S2 snow fall :251-265 ---- */
   if (c->precip_flag == 1) {
     if (r_max(c->liquid_precip, c->solid_precip) > 0.0 && c->N_active > 1) {
+      EV(c, SNOW_PRECIP);
       snow_precip(&c->m_snow, &c->H_abs_snow, &c->thick_snow, dt, c->liquid_precip, c->T2m, 0, 0.0);
     } else if (r_max(c->liquid_precip, c->solid_precip) > 0.0 && c->N_active == 1) {
+      EV(c, SNOW_PRECIP_0);
       snow_precip_0(&H_abs[1], &S_abs[1], m[1], T[1], dt, c->liquid_precip, c->T2m, 0, 0.0);
     }
   } else if (c->precip_flag == 0) {
     if (r_max(c->liquid_precip, c->solid_precip) > 0.0 && c->N_active > 1) {
+      EV(c, SNOW_PRECIP);
       snow_precip(&c->m_snow, &c->H_abs_snow, &c->thick_snow, dt, c->liquid_precip, c->T2m, 1, c->solid_precip);
     } else if (r_max(c->liquid_precip, c->solid_precip) > 0.0 && c->N_active == 1) {
+      EV(c, SNOW_PRECIP_0);
       snow_precip_0(&H_abs[1], &S_abs[1], m[1], T[1], dt, c->liquid_precip, c->T2m, 1, c->solid_precip);
     }
   }
@@ -1740,6 +1785,7 @@ static void one_step(sam_col* c) {
 
   /* ---- S9 gas in the lowest layer :405-410 ---- */
   if (psi_g[c->N_active] > 0.0) {
+    EV(c, GAS_REFILL);
     temp2 = psi_g[c->N_active] * thick[c->N_active] * rho_l;
     m[c->N_active] = m[c->N_active] + temp2;
     S_abs[c->N_active] = S_abs[c->N_active] + temp2 * c->S_bu_bottom;
@@ -1766,6 +1812,7 @@ static void one_step(sam_col* c) {
 
   /* ---- S12 turbulence :450-457 ---- */
   if (c->turb_flag == 2) {
+    EV(c, TURB);
     if (c->bgc_flag == 2) { /* :451-453, mo_functions.f90:355-360: turb from the S_abs before its update */
       const int Na = c->N_active;
       int q;
@@ -1780,11 +1827,13 @@ static void one_step(sam_col* c) {
   if (c->grav_flag == 2 && c->N_active > 1) {
     fl_grav_drain(c);
   } else if (c->grav_flag == 3 && c->N_active > 1) {
+    EV(c, GRAV_DRAIN_SIMPLE);
     fl_grav_drain_simple(c);
   }
 
   /* ---- S14 prescribed salinity :482-497 (prescribe_flag 2; none of the configs) ---- */
   if (c->prescribe_flag == 2) {
+    EV(c, PRESCRIBE);
     k = c->N_active;
     while (k > 1 && sum_arr(thick, k, c->N_active) < 0.15) {
       S_bu[k] = c->S_bu_bottom - sum_arr(thick, k, c->N_active) / 0.15 * (c->S_bu_bottom - 4.0);
@@ -1827,6 +1876,7 @@ static void one_step(sam_col* c) {
 
   /* ---- S16 tank :573-578 ---- */
   if (c->tank_flag == 2) {
+    EV(c, TANK);
     c->S_bu_bottom = (c->S_total - sum_arr(S_abs, 1, Nlayer)) / (c->m_total - sum_arr(m, 1, Nlayer));
     if (c->bgc_flag == 2) { /* :575-577 (sic: every tracer gets the value computed from tracer 1) */
       int q;
@@ -1862,11 +1912,12 @@ static void one_step(sam_col* c) {
       c->melt_thick = 0.0;
       if (sam_func_freeboard(c) > 0.0000000000001) {
         if (psi_s[1] < psi_s_top_min || c->T_top >= c->T_freeze) {
-          sub_melt_thick(psi_l[1], psi_s[1], psi_g[1], T[1], c->T_freeze, c->T_top, c->fl_Q[1], c->thick_snow, dt,
-                         &c->melt_thick, &thick[1], c->thick_min);
+          EV(c, MELT_THICK);
+          if (sub_melt_thick(psi_l[1], psi_s[1], psi_g[1], T[1], c->T_freeze, c->T_top, c->fl_Q[1], c->thick_snow, dt,
+                             &c->melt_thick, &thick[1], c->thick_min)) EV(c, MELT_THICK_GAS);
           if (c->thick_snow >= c->thick_min / 100.0 && c->melt_thick > 0.00000000001 && c->melt_thick_snow == 0.0) {
-            sub_melt_snow(&c->melt_thick, &thick[1], &c->thick_snow, &H_abs[1], &c->H_abs_snow, &m[1], &c->m_snow,
-                          &c->psi_g_snow);
+            if (sub_melt_snow(&c->melt_thick, &thick[1], &c->thick_snow, &H_abs[1], &c->H_abs_snow, &m[1], &c->m_snow,
+                              &c->psi_g_snow)) EV(c, MELT_SNOW_ALL); else EV(c, MELT_SNOW_PART);
           }
         }
       }
@@ -1876,12 +1927,13 @@ static void one_step(sam_col* c) {
       c->melt_thick = 0.0;
       if (sam_func_freeboard(c) > 0.0000000000001) {
         if (psi_s[1] < psi_s_top_min || c->T2m >= c->T_freeze) {
-          sub_melt_thick(psi_l[1], psi_s[1], psi_g[1], T[1], c->T_freeze, c->T2m, c->fl_Q[1], c->thick_snow, dt,
-                         &c->melt_thick, &thick[1], c->thick_min);
+          EV(c, MELT_THICK);
+          if (sub_melt_thick(psi_l[1], psi_s[1], psi_g[1], T[1], c->T_freeze, c->T2m, c->fl_Q[1], c->thick_snow, dt,
+                             &c->melt_thick, &thick[1], c->thick_min)) EV(c, MELT_THICK_GAS);
           c->melt_thick = r_max(c->melt_thick, 0.0);
           if (c->thick_snow >= c->thick_min / 100.0 && c->melt_thick > 0.00000000001 && c->melt_thick_snow == 0.0) {
-            sub_melt_snow(&c->melt_thick, &thick[1], &c->thick_snow, &H_abs[1], &c->H_abs_snow, &m[1], &c->m_snow,
-                          &c->psi_g_snow);
+            if (sub_melt_snow(&c->melt_thick, &thick[1], &c->thick_snow, &H_abs[1], &c->H_abs_snow, &m[1], &c->m_snow,
+                              &c->psi_g_snow)) EV(c, MELT_SNOW_ALL); else EV(c, MELT_SNOW_PART);
           }
         }
       }
@@ -1894,6 +1946,7 @@ static void one_step(sam_col* c) {
   c->melt_thick_output[2] = c->melt_thick_output[2] + c->melt_thick_snow;
   c->melt_thick = c->melt_thick + c->melt_thick_snow;
   if (c->melt_thick_snow > 0.0) { /* :677-685 */
+    EV(c, SNOW_MELTWATER_TO_ICE);
     H_abs[1] = H_abs[1] + c->melt_thick_snow * rho_l * c_l * c->T_snow;
     S_abs[1] = S_abs[1] + c->melt_thick_snow * rho_l * sam_func_S_br2(c, c->T_snow, c->S_abs_snow / c->m_snow);
     thick[1] = thick[1] + c->melt_thick_snow;
@@ -1910,6 +1963,7 @@ static void one_step(sam_col* c) {
   if (c->N_active > 1 && c->freeboard > 0.001) {
     if (c->flush_flag == 4) { /* :704-713 */
       if (c->melt_thick > 0.000000000001 && c->N_active > 2) {
+        EV(c, FLUSH_INLINE);
         H_abs[1] = H_abs[1] - c->melt_thick * rho_l * c_l * T[1];
         S_abs[1] = S_abs[1] * (1.0 - (c->melt_thick * rho_l) / m[1]);
         thick[1] = thick[1] - c->melt_thick;
@@ -1944,6 +1998,7 @@ static void one_step(sam_col* c) {
     {
       const int kn = (c->N_active + 1 < Nlayer) ? c->N_active + 1 : Nlayer;
       if (c->N_active < Nlayer && thick[kn] == 0) { /* :772-783 */
+        EV(c, SCRUB);
         T[c->N_active + 1] = c->T_bottom;
         S_bu[c->N_active + 1] = c->S_bu_bottom;
         H[c->N_active + 1] = 0.0;
@@ -1970,6 +2025,7 @@ static void one_step(sam_col* c) {
     if (mn < 0.0) {
       SAM_STOP(c, 1337);
     } else if (ms < 0.0) {
+      EV(c, SALT_CLAMP);
       for (k = 1; k <= c->N_active; k++) S_abs[k] = r_max(S_abs[k], 0.0);
     }
   }
@@ -2348,7 +2404,24 @@ int sam_set_int(sam_col* c, const char* name, int v) {
     }
   return -1;
 }
+static const char* const k_event_names[SAM_EV_COUNT] = {
+    "flood", "flood_neg_free", "flood_simple", "flush3", "flush4", "flush_inline", "styropor", "snow_thermo",
+    "snow_thermo_meltwater", "snow_wet", "snow_merge", "snow_compaction", "snow_coupling_iter", "snow_coupling_warm1",
+    "snow_coupling_warm2", "snow_precip", "snow_precip_0", "melt_snow_all", "melt_snow_part", "bottom_melt",
+    "bottom_melt_simple_a", "bottom_melt_simple_b", "bottom_growth_simple", "bottom_growth", "top_grow_a", "top_grow_b",
+    "top_grow_c", "top_melt_a", "top_melt_b", "top_melt_c", "grav_drained", "salt_clamp",
+    "gas_refill", "getT_Tfr_fallback", "getT_saltfree", "getT_liquid", "heat_melt", "heat_thin_snow", "melt_thick_gas",
+    "snow_meltwater_to_ice", "prescribe", "grav_drain_simple", "notzflux", "flush3_clamp", "scrub", "melt_thick", "turb",
+    "tank"};
+const char* sam_event_name(int id) { return (id >= 0 && id < SAM_EV_COUNT) ? k_event_names[id] : NULL; }
+
 long sam_get_stat(const sam_col* c, const char* name) {
+  if (!strncmp(name, "ev_", 3)) {
+    int q;
+    for (q = 0; q < SAM_EV_COUNT; q++)
+      if (!strcmp(name + 3, k_event_names[q])) return c->ev[q];
+    return -1;
+  }
   if (!strcmp(name, "getT_calls")) return c->stat_getT_calls;
   if (!strcmp(name, "newton_fr")) return c->stat_newton_fr;
   if (!strcmp(name, "newton_T")) return c->stat_newton_T;

@@ -90,7 +90,29 @@ struct sam_col {
   /* ---- statistics (not in the reference) ---- */
   long stat_getT_calls, stat_newton_fr, stat_newton_T, stat_layer_events, stat_flush_calls, stat_flood_calls,
       stat_coupling_iters;
+  /* per-branch execution counters (not in the reference): how often each rarely taken branch of the path ran,
+   * so that a parity test can assert that the branch it claims to cover was executed.  Order = SAM_EV_* below =
+   * samsim_event_id of include/samsim_b200.h (checked by tests/test_cabi_cpu.py). */
+  long ev[64];
 };
+
+/* branch ids, each named after the reference lines it marks (see sam_event_name) */
+enum {
+  SAM_EV_FLOOD = 0, SAM_EV_FLOOD_NEG_FREE, SAM_EV_FLOOD_SIMPLE, SAM_EV_FLUSH3, SAM_EV_FLUSH4, SAM_EV_FLUSH_INLINE,
+  SAM_EV_STYROPOR, SAM_EV_SNOW_THERMO, SAM_EV_SNOW_THERMO_MELTWATER, SAM_EV_SNOW_WET, SAM_EV_SNOW_MERGE,
+  SAM_EV_SNOW_COMPACTION, SAM_EV_SNOW_COUPLING_ITER, SAM_EV_SNOW_COUPLING_WARM1, SAM_EV_SNOW_COUPLING_WARM2,
+  SAM_EV_SNOW_PRECIP, SAM_EV_SNOW_PRECIP_0, SAM_EV_MELT_SNOW_ALL, SAM_EV_MELT_SNOW_PART, SAM_EV_BOTTOM_MELT,
+  SAM_EV_BOTTOM_MELT_SIMPLE_A, SAM_EV_BOTTOM_MELT_SIMPLE_B, SAM_EV_BOTTOM_GROWTH_SIMPLE, SAM_EV_BOTTOM_GROWTH,
+  SAM_EV_TOP_GROW_A, SAM_EV_TOP_GROW_B, SAM_EV_TOP_GROW_C, SAM_EV_TOP_MELT_A, SAM_EV_TOP_MELT_B, SAM_EV_TOP_MELT_C,
+  SAM_EV_GRAV_DRAINED, SAM_EV_SALT_CLAMP,
+  SAM_EV_GAS_REFILL, SAM_EV_GETT_TFR_FALLBACK, SAM_EV_GETT_SALTFREE, SAM_EV_GETT_LIQUID, SAM_EV_HEAT_MELT,
+  SAM_EV_HEAT_THIN_SNOW, SAM_EV_MELT_THICK_GAS, SAM_EV_SNOW_MELTWATER_TO_ICE, SAM_EV_PRESCRIBE,
+  SAM_EV_GRAV_DRAIN_SIMPLE, SAM_EV_NOTZFLUX, SAM_EV_FLUSH3_CLAMP, SAM_EV_SCRUB, SAM_EV_MELT_THICK, SAM_EV_TURB,
+  SAM_EV_TANK,
+  SAM_EV_COUNT
+};
+/* "flood", "flood_neg_free", ... in the order above; NULL beyond SAM_EV_COUNT */
+const char* sam_event_name(int id);
 
 /* Allocate a column and run the reference's init(testcase) for testcases 1, 4, 101-105
  * (mo_init.f90:83-132, :865-945, :1127-1207, :222-767, :1982-2009).  Returns NULL for

@@ -39,7 +39,23 @@ SCALAR_IDS = {n: i for i, n in enumerate(
      "grav_drain", "grav_salt", "grav_temp", "melt_thick", "melt_thick_snow", "melt_thick_snow_old",
      "melt_thick_output1", "melt_thick_output2", "melt_thick_output3", "freeboard", "T_freeze", "melt_err", "S_total",
      "ttop_warm", "ttop_cold", "oflux_amp", "bgc_bottom1", "bgc_bottom2", "bgc_total1", "bgc_total2"])}
-INT_IDS = {"N_active": 0, "status": 1, "styropor_flag": 2}
+INT_IDS = {"N_active": 0, "status": 1, "styropor_flag": 2, "events0": 3, "events1": 4}
+# branch events, order of samsim_event_id (include/samsim_b200.h): bit id of events0 (id < 32) / events1 (id - 32)
+EVENT_NAMES = [
+    "flood", "flood_neg_free", "flood_simple", "flush3", "flush4", "flush_inline", "styropor", "snow_thermo",
+    "snow_thermo_meltwater", "snow_wet", "snow_merge", "snow_compaction", "snow_coupling_iter", "snow_coupling_warm1",
+    "snow_coupling_warm2", "snow_precip", "snow_precip_0", "melt_snow_all", "melt_snow_part", "bottom_melt",
+    "bottom_melt_simple_a", "bottom_melt_simple_b", "bottom_growth_simple", "bottom_growth", "top_grow_a", "top_grow_b",
+    "top_grow_c", "top_melt_a", "top_melt_b", "top_melt_c", "grav_drained", "salt_clamp",
+    "gas_refill", "getT_Tfr_fallback", "getT_saltfree", "getT_liquid", "heat_melt", "heat_thin_snow", "melt_thick_gas",
+    "snow_meltwater_to_ice", "prescribe", "grav_drain_simple", "notzflux", "flush3_clamp", "scrub", "melt_thick", "turb",
+    "tank"]
+
+
+def decode_events(ev0: int, ev1: int) -> set:
+    """names of the branch events whose bits are set in the two event words of a column"""
+    w = (int(ev0) & 0xFFFFFFFF) | ((int(ev1) & 0xFFFFFFFF) << 32)
+    return {n for j, n in enumerate(EVENT_NAMES) if (w >> j) & 1}
 SNAP_SCALARS = ["freeboard", "thick_snow", "T_snow", "psi_l_snow", "psi_s_snow", "energy_stored", "freshwater",
                 "total_resist", "thickness", "bulk_salin", "grav_drain", "grav_salt", "grav_temp", "T2m", "T_top",
                 "melt_thick_output1", "melt_thick_output2", "melt_thick_output3", "time", "N_active"]
@@ -272,6 +288,15 @@ class Engine:
         _check(self.L, self.L.samsim_b200_get_int(self.h, INT_IDS[name], _ip(out), col0, n))
         return out
 
+    def events(self, col: int = 0) -> set:
+        """branch events column `col` has executed since the event words were last cleared (names of EVENT_NAMES)"""
+        return decode_events(self.get_int("events0", col, 1)[0], self.get_int("events1", col, 1)[0])
+
+    def clear_events(self):
+        z = np.zeros(self.ncol, dtype=np.int32)
+        self.set_int("events0", z)
+        self.set_int("events1", z)
+
     def broadcast_column(self, src: int = 0, col0: int = 0, n: int | None = None):
         n = self.ncol - col0 if n is None else n
         _check(self.L, self.L.samsim_b200_broadcast_column(self.h, src, col0, n))
@@ -414,7 +439,8 @@ def kat_getT(salt_flag: int, H, S_bu, T_in, device: int = 0):
     n = len(H)
     T, phi, st = np.empty(n), np.empty(n), np.empty(n, dtype=np.int32)
     _check(L, L.samsim_b200_kat_getT(salt_flag, n, _dp(H), _dp(S_bu), _dp(T_in), _dp(T), _dp(phi), _ip(st), device))
-    return T, phi, st
+    # low 16 bits: STOP code; above: the getT branch bits of event word 1 (bit SAMSIM_EV_GETT_* - 32)
+    return T, phi, st & 0xFFFF, (st >> 16) & 0xFFFF
 
 
 def kat_scalar(fn: int, salt_flag: int, a, b=None, device: int = 0):

@@ -63,7 +63,23 @@ enum {
   AR_BGC1 = AR_CORE_COUNT, AR_BGC2, AR_FB_D, AR_FB_U, AR_FB_A, AR_FB_O,
   AR_COUNT
 };
-enum { IN_N_ACTIVE = 0, IN_STATUS, IN_STYROPOR, IN_COUNT };
+enum { IN_N_ACTIVE = 0, IN_STATUS, IN_STYROPOR, IN_EVENTS0, IN_EVENTS1, IN_COUNT };
+
+// Branch events (samsim_event_id of include/samsim_b200.h, same order): bit id of the per-column event words is set
+// when the column executes the branch.  They let a parity test prove that the branch it claims to cover ran; the
+// CPU oracle counts the same branches.  Not part of the model state.
+enum {
+  EV_FLOOD = 0, EV_FLOOD_NEG_FREE, EV_FLOOD_SIMPLE, EV_FLUSH3, EV_FLUSH4, EV_FLUSH_INLINE, EV_STYROPOR, EV_SNOW_THERMO,
+  EV_SNOW_THERMO_MELTWATER, EV_SNOW_WET, EV_SNOW_MERGE, EV_SNOW_COMPACTION, EV_SNOW_COUPLING_ITER,
+  EV_SNOW_COUPLING_WARM1, EV_SNOW_COUPLING_WARM2, EV_SNOW_PRECIP, EV_SNOW_PRECIP_0, EV_MELT_SNOW_ALL, EV_MELT_SNOW_PART,
+  EV_BOTTOM_MELT, EV_BOTTOM_MELT_SIMPLE_A, EV_BOTTOM_MELT_SIMPLE_B, EV_BOTTOM_GROWTH_SIMPLE, EV_BOTTOM_GROWTH,
+  EV_TOP_GROW_A, EV_TOP_GROW_B, EV_TOP_GROW_C, EV_TOP_MELT_A, EV_TOP_MELT_B, EV_TOP_MELT_C, EV_GRAV_DRAINED,
+  EV_SALT_CLAMP,
+  EV_GAS_REFILL, EV_GETT_TFR_FALLBACK, EV_GETT_SALTFREE, EV_GETT_LIQUID, EV_HEAT_MELT, EV_HEAT_THIN_SNOW,
+  EV_MELT_THICK_GAS, EV_SNOW_MELTWATER_TO_ICE, EV_PRESCRIBE, EV_GRAV_DRAIN_SIMPLE, EV_NOTZFLUX, EV_FLUSH3_CLAMP,
+  EV_SCRUB, EV_MELT_THICK, EV_TURB, EV_TANK,
+  EV_COUNT
+};
 
 // strided per-layer view of one column (1-based layer index like the reference)
 struct Lay {
@@ -121,6 +137,7 @@ struct Col {
   __device__ __forceinline__ Lay bgc(int q) const { return A(AR_BGC1 + q); }  // q = 0, 1
   double fb_x;  // fl_brine_bgc(N_active, 1): flooding (N_active >= 3; it is the up-cell of layer 1 when N_active == 2)
   int N_active, status, styropor_flag;
+  unsigned ev0, ev1;  // branch events EV_* (bits 0..31 / 32..63), accumulated over the handle's lifetime
   // T, phi, S_bu of layers 2..N_active still equal what the S18 sweep of the previous step produced and
   // m, S_abs, H_abs of those layers are untouched since: the S4 sweep may reuse them (bit-identical result)
   bool thermo_valid;
@@ -146,6 +163,7 @@ struct Col {
 };
 
 #define SCV(c, id) ((c).sc[id])
+#define EVT(c, id) (((id) < 32) ? ((c).ev0 |= (1u << ((id) & 31))) : ((c).ev1 |= (1u << ((id) & 31))))
 
 __device__ __forceinline__ double f_max(double a, double b) { return (a > b) ? a : b; }  // Fortran MAX
 __device__ __forceinline__ double f_min(double a, double b) { return (a < b) ? a : b; }  // Fortran MIN
@@ -179,17 +197,26 @@ __device__ __forceinline__ double ddT_S_br_of(const DevCfg& g, double T) {
 
 // getT, mo_thermo_functions.f90:62-143: Newton for the freezing point, then Newton for T.
 // `phi` keeps its incoming value when no branch assigns it (cannot happen for finite input).
-__device__ __noinline__ void getT(const DevCfg& g, double H, double S_bu, double T_in, double& T_out, double& phi,
-                                  int& status) {
+//
+// The reference computes the freezing point T_fr (:85-92) before every mushy inversion, but reads it only when an
+// iterate leaves [-200, 0] degC (:101-103).  T_fr depends on S_bu alone and computing it has no side effect, so it
+// is evaluated here on first use: same bits whenever the reference terminates, 11 of the ~25 divisions of a call gone.
+// `ev1` receives the EV_GETT_* branch bits (word 1).
+__device__ __forceinline__ double getT_freezing_point(const DevCfg& g, double S_bu) {
+  double T_fr = -1.0;
+  while (fabs(S_br_of(g, T_fr) / S_bu - 1.0) > SAMSIM_F32(0.0001)) {  // :87
+    const double T_0 = T_fr;
+    const double f = S_br_of(g, T_0) - S_bu;
+    const double ddT_f = ddT_S_br_of(g, T_0);
+    T_fr = T_0 - f / ddT_f;
+  }
+  return T_fr;
+}
+__device__ __forceinline__ void getT_body(const DevCfg& g, double H, double S_bu, double T_in, double& T_out, double& phi,
+                                          int& status, unsigned& ev1) {
   double T = H / c_l;
   if (S_br_of(g, T, S_bu) > S_bu && S_bu > 0.001) {
-    double T_fr = -1.0, T_0, f, ddT_f;
-    while (fabs(S_br_of(g, T_fr) / S_bu - 1.0) > SAMSIM_F32(0.0001)) {  // :87
-      T_0 = T_fr;
-      f = S_br_of(g, T_0) - S_bu;
-      ddT_f = ddT_S_br_of(g, T_0);
-      T_fr = T_0 - f / ddT_f;
-    }
+    double T_0, f, ddT_f;
     T_0 = T_in;
     {
       double sb = S_br_of(g, T_0);
@@ -200,7 +227,10 @@ __device__ __noinline__ void getT(const DevCfg& g, double H, double S_bu, double
     int it = 0;
     while (fabs(f) > 1.0) {  // :99
       T_0 = T;
-      if (T_0 > 0.0 || T_0 < -200.0) T_0 = T_fr;
+      if (T_0 > 0.0 || T_0 < -200.0) {  // :101-103
+        T_0 = getT_freezing_point(g, S_bu);
+        ev1 |= 1u << (EV_GETT_TFR_FALLBACK - 32);
+      }
       double sb = S_br_of(g, T_0);
       f = -latent_heat - H + latent_heat * S_bu / f_max(sb, 0.0000000001) + c_s * T_0 + c_s_beta * T_0 * T_0 / 2.0;  // :104
       ddT_f = c_s + c_s_beta * T_0 - latent_heat * S_bu * ddT_S_br_of(g, T_0) / f_max(sb * sb, 0.0000000001);       // :105
@@ -213,6 +243,7 @@ __device__ __noinline__ void getT(const DevCfg& g, double H, double S_bu, double
     }
     phi = 1.0 - S_bu / S_br_of(g, T, S_bu);  // :125
   } else if (S_bu < 0.001) {  // :127-137 salt-free
+    ev1 |= 1u << (EV_GETT_SALTFREE - 32);
     if (H > 0.0) {
       phi = 0.0;
       T = H / c_l;
@@ -224,9 +255,15 @@ __device__ __noinline__ void getT(const DevCfg& g, double H, double S_bu, double
       phi = -H / latent_heat;
     }
   } else {
+    ev1 |= 1u << (EV_GETT_LIQUID - 32);
     phi = 0.0;
   }
   T_out = T;
+}
+// out-of-line copy for the call sites outside the two Newton sweeps (snow, coupling, layer 1)
+__device__ __noinline__ void getT(const DevCfg& g, double H, double S_bu, double T_in, double& T_out, double& phi,
+                                  int& status, unsigned& ev1) {
+  getT_body(g, H, S_bu, T_in, T_out, phi, status, ev1);
 }
 
 // Expulsion, mo_thermo_functions.f90:157-187
@@ -411,9 +448,11 @@ __device__ __noinline__ double freeboard_of(const DevCfg& g, Col& c) {
 __device__ __forceinline__ void fb_reset(Col& c) { c.fb.tot_valid = false; c.fb.suf_valid = false; c.fb.res_valid = false; }
 
 // sub_melt_thick, mo_functions.f90:386-428
-__device__ __forceinline__ void melt_thick_of(double psi_l, double psi_s, double psi_g, double T, double T_freeze,
+// returns true when the gas-fraction correction (:418-426) ran (event bit only)
+__device__ __forceinline__ bool melt_thick_of(double psi_l, double psi_s, double psi_g, double T, double T_freeze,
                                               double T_top, double fl_Q, double thick_snow, double dt,
                                               double& melt_thick, double& thick, double thick_min) {
+  bool gas = false;
   melt_thick = 0.0;
   if (thick_snow < thick_min && T_top >= T_freeze) {
     melt_thick = -fl_Q - 2.0 * (psi_l * k_l + psi_s * k_s) / thick * (T_freeze - T);
@@ -422,6 +461,7 @@ __device__ __forceinline__ void melt_thick_of(double psi_l, double psi_s, double
   }
   if (psi_s < psi_s_top_min) melt_thick = thick * (1.0 - psi_s / psi_s_top_min);
   if (melt_thick > 0.0 && psi_g > gas_snow_ice2) {
+    gas = true;
     if (melt_thick > (psi_g - gas_snow_ice2) * thick) {
       melt_thick = melt_thick - (psi_g - gas_snow_ice2) * thick;
       thick = thick * (1.0 - (psi_g - gas_snow_ice2));
@@ -430,10 +470,11 @@ __device__ __forceinline__ void melt_thick_of(double psi_l, double psi_s, double
       melt_thick = 0.0;
     }
   }
+  return gas;
 }
 
-// sub_melt_snow, mo_functions.f90:443-474
-__device__ __forceinline__ void melt_snow(double& melt_thick, double& thick, double& thick_snow, double& H_abs,
+// sub_melt_snow, mo_functions.f90:443-474; returns true when all the snow went into the ice (:453)
+__device__ __forceinline__ bool melt_snow(double& melt_thick, double& thick, double& thick_snow, double& H_abs,
                                           double& H_abs_snow, double& m, double& m_snow, double& psi_g_snow) {
   double shift = 1.0 / f_max(psi_g_snow, 0.01) * melt_thick;
   if (shift >= thick_snow) {
@@ -444,6 +485,7 @@ __device__ __forceinline__ void melt_snow(double& melt_thick, double& thick, dou
     thick_snow = 0.0;
     m_snow = 0.0;
     H_abs_snow = 0.0;
+    return true;
   } else {
     H_abs = H_abs + shift / thick_snow * H_abs_snow;
     H_abs_snow = H_abs_snow - shift / thick_snow * H_abs_snow;
@@ -453,6 +495,7 @@ __device__ __forceinline__ void melt_snow(double& melt_thick, double& thick, dou
     thick_snow = thick_snow - shift;
     melt_thick = 0.0;
   }
+  return false;
 }
 
 // ==========================================================================================
@@ -538,20 +581,22 @@ __device__ __noinline__ void snow_coupling(const DevCfg& g, Col& c, double& H_ab
   H_abs_snow = -m_snow * latent_heat;
   double H = H_abs1 / m1;
   double hs = H_abs_snow / m_snow;
-  getT(g, hs, S_abs_snow / m_snow, hs / c_l, T_snow, phi_s, c.status);
-  getT(g, H, S_bu1, H / c_l, T1, phi1, c.status);
+  getT(g, hs, S_abs_snow / m_snow, hs / c_l, T_snow, phi_s, c.status, c.ev1);
+  getT(g, H, S_bu1, H / c_l, T1, phi1, c.status, c.ev1);
   if (T1 > 0 && H_abs1 <= -H_abs_snow) {
+    EVT(c, EV_SNOW_COUPLING_WARM1);
     H_abs_snow = H_abs_snow + H_abs1;
     H_abs1 = 0.0;
     hs = H_abs_snow / m_snow;
-    getT(g, hs, S_abs_snow / m_snow, hs / c_l, T_snow, phi_s, c.status);
-    getT(g, H, S_bu1, H / c_l, T1, phi1, c.status);  // H is NOT refreshed here in the reference (:79-80)
+    getT(g, hs, S_abs_snow / m_snow, hs / c_l, T_snow, phi_s, c.status, c.ev1);
+    getT(g, H, S_bu1, H / c_l, T1, phi1, c.status, c.ev1);  // H is NOT refreshed here in the reference (:79-80)
   } else if (T1 > 0. && H_abs1 > -H_abs_snow) {
+    EVT(c, EV_SNOW_COUPLING_WARM2);
     H_abs1 = (H_abs1 + H_abs_snow) * m1 / m_snow / (1.0 + m1 / m_snow);
     H_abs_snow = H_abs1 * m_snow / m1;
     hs = H_abs_snow / m_snow;
-    getT(g, hs, S_abs_snow / m_snow, hs / c_l, T_snow, phi_s, c.status);
-    getT(g, H, S_bu1, H / c_l, T1, phi1, c.status);
+    getT(g, hs, S_abs_snow / m_snow, hs / c_l, T_snow, phi_s, c.status, c.ev1);
+    getT(g, H, S_bu1, H / c_l, T1, phi1, c.status, c.ev1);
   } else {
     int jj = 0;
     while (fabs(T1 - T_snow) > SAMSIM_F32(0.1) && jj < 201) {
@@ -560,10 +605,11 @@ __device__ __noinline__ void snow_coupling(const DevCfg& g, Col& c, double& H_ab
       H_abs_snow = H_abs_snow - step;
       H_abs1 = H_abs1 + step;
       jj = jj + 1;
+      EVT(c, EV_SNOW_COUPLING_ITER);
       H = H_abs1 / m1;
       hs = H_abs_snow / m_snow;
-      getT(g, hs, S_abs_snow / m_snow, hs / c_l, T_snow, phi_s, c.status);
-      getT(g, H, S_bu1, H / c_l, T1, phi1, c.status);
+      getT(g, hs, S_abs_snow / m_snow, hs / c_l, T_snow, phi_s, c.status, c.ev1);
+      getT(g, H, S_bu1, H / c_l, T1, phi1, c.status, c.ev1);
       if (c.status) return;
     }
     if (jj > 200 && fabs(T1 - T_snow) > 1.0) c.status = 16;
@@ -616,9 +662,10 @@ __device__ __noinline__ void snow_thermo(const DevCfg& g, Col& c, bool meltwater
   const double H_snow = H_abs_snow / m_snow;
   const double S_bu_snow = S_abs_snow / m_snow;
   const double psi_s_old = psi_s_snow;
+  if (meltwater) EVT(c, EV_SNOW_THERMO_MELTWATER); else EVT(c, EV_SNOW_THERMO);
   {
     double T_in = T_snow;
-    getT(g, H_snow, S_bu_snow, T_in, T_snow, phi_snow, c.status);
+    getT(g, H_snow, S_bu_snow, T_in, T_snow, phi_snow, c.status, c.ev1);
   }
   psi_s_snow = m_snow * phi_snow / rho_s / thick_snow;
   psi_l_snow = m_snow * (1.0 - phi_snow) / rho_l / thick_snow;
@@ -633,6 +680,7 @@ __device__ __noinline__ void snow_thermo(const DevCfg& g, Col& c, bool meltwater
   else max_lwc = 0.0;
 
   if (psi_s_old > psi_s_snow && psi_s_snow > 0.0) {
+    EVT(c, EV_SNOW_COMPACTION);
     if ((1.0 - phi_snow) > max_lwc) thick_snow = thick_snow * (1.0 - (psi_s_old - psi_s_snow) / psi_s_old);
     if (thick_snow < (phi_snow * m_snow / rho_s + (1.0 - phi_snow) * m_snow / rho_l))
       thick_snow = (phi_snow * m_snow / rho_s + (1.0 - phi_snow) * m_snow / rho_l);
@@ -650,6 +698,7 @@ __device__ __noinline__ void snow_thermo(const DevCfg& g, Col& c, bool meltwater
   const bool wet = meltwater ? ((1.0 - phi_snow) > max_lwc && psi_l_snow > 0.0 && psi_g_snow > 0.0)
                              : ((1.0 - phi_snow) > max_lwc && psi_g_snow > 0.0);
   if (wet) {
+    EVT(c, EV_SNOW_WET);
     max_lwc_v = max_lwc * m_snow / (rho_l * thick_snow);
     if (!meltwater) {  // mo_snow.f90:272-294
       sat_snow = thick_snow * (psi_l_snow - max_lwc_v);
@@ -684,6 +733,7 @@ __device__ __noinline__ void snow_thermo(const DevCfg& g, Col& c, bool meltwater
       H_abs1 = H_abs1 + sat_snow * (1.0 - psi_s_snow - gg) * rho_l * c_l * T_snow;
     }
   } else if (psi_g_snow <= 0.0) {
+    EVT(c, EV_SNOW_MERGE);
     H_abs1 = H_abs1 + H_abs_snow;
     m1 = m1 + m_snow;
     thick1 = thick1 + thick_snow;
@@ -901,7 +951,7 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
     sum_before = sum_before + Sk;
     // same && chain as :145, evaluated left to right: psi_s and m are only touched where ray exceeds ray_crit
     if (rk > ray_crit && c.psi_s()[k] > 0.001 && Sk / c.m()[k] > 0.1 && sbk > sbk1) {
-      if (kfirst == 0) { kfirst = k; fl_m[k] = 0.0; }  // fl_m(kfirst) = fl_up(kfirst-1) = 0: first face read by mass_transfer
+      if (kfirst == 0) { kfirst = k; fl_m[k] = 0.0; EVT(c, EV_GRAV_DRAINED); }  // fl_m(kfirst) = fl_up(kfirst-1) = 0: first face read by mass_transfer
       const double plk = c.psi_l()[k], thk = c.thick()[k], Tk = c.T()[k];
       double flux = x_grav * (rk - ray_crit) * dt * thk;
       flux = f_min(flux, plk * rho_l * thk);
@@ -1011,6 +1061,7 @@ __device__ __noinline__ void flood(const DevCfg& g, Col& c) {
   double& H_abs_snow = SCV(c, SC_H_ABS_SNOW);
   double& m_snow = SCV(c, SC_M_SNOW);
   double hp = 0.0;
+  EVT(c, EV_FLOOD);
   SAMSIM_LOOP
   for (int k = 1; k <= Na - 1; k++) hp = hp + c.thick()[k] / (1e-17 * det_pow(1000.0 * c.psi_l()[k], 3.10));  // :73-79
   const double bottom_h = c.thick()[Na] * c.psi_s()[Na] / psi_s_min;
@@ -1035,6 +1086,7 @@ __device__ __noinline__ void flood(const DevCfg& g, Col& c) {
   c.S_abs()[1] = S1; c.H_abs()[1] = H1; c.m()[1] = m1; c.thick()[1] = th1;  // Na > 1 here, layer 1 != layer Na
 
   if (freeboard + shift_ice < neg_free) {  // :117-138
+    EVT(c, EV_FLOOD_NEG_FREE);
     const double shift = neg_free - (freeboard + shift_ice);
     flood_brine = shift * (psi_g_snow)*rho_l;
     const double T_Na = c.T()[Na];
@@ -1065,6 +1117,7 @@ __device__ __forceinline__ void flood_simple(Col& c) {
   double& m_snow = SCV(c, SC_M_SNOW);
   const double shift = SCV(c, SC_FREEBOARD) - neg_free;
   const double flood_brine = -shift * SCV(c, SC_PSI_G_SNOW) * rho_l;
+  EVT(c, EV_FLOOD_SIMPLE);
   double S1 = c.S_abs()[1], H1 = c.H_abs()[1], m1 = c.m()[1];
   c.thick()[1] = c.thick()[1] - shift;
   S1 = S1 + SCV(c, SC_S_BU_BOTTOM) * flood_brine;
@@ -1088,6 +1141,7 @@ __device__ __noinline__ void flush3(const DevCfg& g, Col& c) {
   const double dt = g.dt, freeboard = SCV(c, SC_FREEBOARD);
   Lay R_v = c.w0(), R_h = c.w1(), R = c.w2(), S_bu = c.w3(), fl_m = c.fl_m();
   double& melt_thick = SCV(c, SC_MELT_THICK);
+  EVT(c, EV_FLUSH3);
 
   SAMSIM_LOOP
   for (int k = 1; k <= Na; k++) { c.flush_v()[k] = 0.0; c.flush_h()[k] = 0.0; }   // :101-102 (dummies are DIMENSION(N_active))
@@ -1195,9 +1249,11 @@ __device__ __noinline__ void flush3(const DevCfg& g, Col& c) {
   SAMSIM_LOOP
   for (int k = 2; k <= Na; k++) mn = f_min(mn, c.S_abs()[k]);
   mn = f_min(mn, 0.0);  // MINVAL over all Nlayer: inactive layers hold 0 (only matters when Na < N)
-  if (mn < -0.00000000000000000000000001)
+  if (mn < -0.00000000000000000000000001) {
+    EVT(c, EV_FLUSH3_CLAMP);
     SAMSIM_LOOP
     for (int k = 1; k <= Na; k++) c.S_abs()[k] = f_max(c.S_abs()[k], 0.0);
+  }
   if (fabs(c.m()[1]) < 0.000001) c.status = 9876;  // :230-233
 }
 
@@ -1206,6 +1262,7 @@ __device__ __noinline__ void flush4(const DevCfg& g, Col& c) {
   const int N = g.Nlayer, Na = c.N_active;
   double& melt_thick = SCV(c, SC_MELT_THICK);
   const double S_bu1 = c.S_abs()[1] / c.m()[1], T1 = c.T()[1];
+  EVT(c, EV_FLUSH4);
   c.H_abs()[1] = c.H_abs()[1] - melt_thick * rho_l * c_l * T1;
   c.S_abs()[1] = c.S_abs()[1] - melt_thick * rho_l * S_br_of(g, T1, S_bu1);
   c.thick()[1] = c.thick()[1] - melt_thick;
@@ -1254,10 +1311,12 @@ __device__ __noinline__ void top_melt(const DevCfg& g, Col& c) {
     c.H_abs()[k] = H[k + 1] * rho[k + 1] * thick_0;
   }
   if (c.N_active <= N_top) {  // :247-254
+    EVT(c, EV_TOP_MELT_A);
     const int Na = c.N_active;
     c.m()[Na] = 0.0; c.S_abs()[Na] = 0.0; c.H_abs()[Na] = 0.0; c.thick()[Na] = 0.0;
     c.N_active = Na - 1;
   } else if (c.N_active > N_top && c.N_active <= N && c.thick()[N_top + 1] / thick_0 < 1.00001) {  // :256-273
+    EVT(c, EV_TOP_MELT_B);
     const int Na = c.N_active;
     SAMSIM_LOOP
     for (int k = N_top; k <= Na - 1; k++) {
@@ -1269,6 +1328,7 @@ __device__ __noinline__ void top_melt(const DevCfg& g, Col& c) {
     c.N_active = Na - 1;
   }
   if (c.N_active == N && c.thick()[N_top + 1] - thick_0 >= 0.000001) {  // :275-314
+    EVT(c, EV_TOP_MELT_C);
     double loss_m = thick_0 * rho[N_top + 1];
     double loss_S = loss_m * S_bu[N_top + 1];
     double loss_H = loss_m * H[N_top + 1];
@@ -1395,6 +1455,7 @@ __device__ __noinline__ void top_grow(const DevCfg& g, Col& c) {
     c.H_abs()[k] = H[k - 1] * rho[k - 1] * thick_0;
   }
   if (c.N_active <= N_top) {  // :659-665
+    EVT(c, EV_TOP_GROW_A);
     const int Na = c.N_active + 1;
     c.N_active = Na;
     c.m()[Na] = rho[Na - 1] * thick_0;
@@ -1402,6 +1463,7 @@ __device__ __noinline__ void top_grow(const DevCfg& g, Col& c) {
     c.H_abs()[Na] = H[Na - 1] * thick_0 * rho[Na - 1];
     c.thick()[Na] = thick_0;
   } else if (c.N_active > N_top && c.N_active < N) {  // :668-680
+    EVT(c, EV_TOP_GROW_B);
     SAMSIM_LOOP
     for (int k = N_top + 1; k <= c.N_active; k++) {
       c.m()[k] = rho[k - 1] * thick_0;
@@ -1415,6 +1477,7 @@ __device__ __noinline__ void top_grow(const DevCfg& g, Col& c) {
     c.H_abs()[Na] = H[Na - 1] * thick_0 * rho[Na - 1];
     c.thick()[Na] = thick_0;
   } else if (c.N_active == N) {  // :682-711
+    EVT(c, EV_TOP_GROW_C);
     double loss_m = thick_0 * rho[N_top];
     double loss_S = loss_m * S_bu[N_top];
     double loss_H = loss_m * H[N_top];
@@ -1625,18 +1688,23 @@ __device__ __noinline__ void layer_dynamics(const DevCfg& g, Col& c) {
     for (int q = 0; q < g.n_bgc; q++) tracer_layer_dynamics(g, c, op, c.bgc(q), SCV(c, SC_BGC_BOTTOM1 + q));
   };
   if (c.phi()[N - 1] <= psi_s_min / 2.0 && phi_Na < 0.00001 && Na == N && mid_ratio > 1.000001 && bf) {
+    EVT(c, EV_BOTTOM_MELT);
     tracers(1);
     bottom_melt(g, c);
   } else if (Na > 1 && Na < N && phi_Na < 0.00001 && phi_nm1 <= psi_s_min / 2.0 && bf) {
+    EVT(c, EV_BOTTOM_MELT_SIMPLE_A);
     tracers(2);
     bottom_melt_simple(c);
   } else if (Na > 1 && phi_Na < 0.00001 && phi_nm1 <= psi_s_min / 2.0 && mid_ratio < 1.01 && bf) {
+    EVT(c, EV_BOTTOM_MELT_SIMPLE_B);
     tracers(2);
     bottom_melt_simple(c);
   } else if (phi_Na > psi_s_min && Na < N && bf) {
+    EVT(c, EV_BOTTOM_GROWTH_SIMPLE);
     tracers(3);
     bottom_growth_simple(g, c);
   } else if (c.phi()[N] > psi_s_min && bf) {
+    EVT(c, EV_BOTTOM_GROWTH);
     tracers(4);
     bottom_growth(g, c);
   } else if (th1 > 1.5 * thick_0) {

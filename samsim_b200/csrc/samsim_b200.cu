@@ -22,6 +22,8 @@ static_assert((int)SAMSIM_SC_COUNT == (int)SC_COUNT, "scalar ids out of sync wit
 static_assert((int)SAMSIM_ARR_COUNT == (int)AR_STATE_COUNT + 2 && (int)SAMSIM_ARR_BGC_ABS1 == (int)AR_STATE_COUNT,
               "array ids out of sync with include/samsim_b200.h");
 static_assert((int)SAMSIM_INT_COUNT == (int)IN_COUNT, "int ids out of sync with include/samsim_b200.h");
+static_assert((int)SAMSIM_EV_COUNT == (int)EV_COUNT && (int)SAMSIM_EV_TANK == (int)EV_TANK && (int)SAMSIM_EV_GAS_REFILL == 32,
+              "event ids out of sync with include/samsim_b200.h");
 static_assert((int)SAMSIM_SNAPSC_COUNT == 20 && (int)SAMSIM_SNAPARR_COUNT == 14, "snapshot layout");
 
 // Launch shape (measured on B200, profiles/README.md): 512-thread blocks, 2 blocks per SM (64 registers/thread,
@@ -99,6 +101,8 @@ __global__ void __launch_bounds__(SAMSIM_BLOCK, SAMSIM_MINBLOCKS) samsim_step_ke
   c.N_active = p.in[(size_t)IN_N_ACTIVE * ls + col];
   c.status = padding ? -1 : p.in[(size_t)IN_STATUS * ls + col];
   c.styropor_flag = p.in[(size_t)IN_STYROPOR * ls + col];
+  c.ev0 = (unsigned)p.in[(size_t)IN_EVENTS0 * ls + col];
+  c.ev1 = (unsigned)p.in[(size_t)IN_EVENTS1 * ls + col];
   c.time = p.time; c.i = p.i; c.n_time_out = p.n_time_out; c.time_counter = p.time_counter;
   c.fsw0 = c.fsw1 = c.flw0 = c.flw1 = c.ftime0 = c.ftime1 = 0.0;
   c.thermo_valid = false;  // launch-local: the host may have changed the state between launches
@@ -128,6 +132,8 @@ __global__ void __launch_bounds__(SAMSIM_BLOCK, SAMSIM_MINBLOCKS) samsim_step_ke
   p.in[(size_t)IN_N_ACTIVE * ls + col] = c.N_active;
   p.in[(size_t)IN_STATUS * ls + col] = c.status;
   p.in[(size_t)IN_STYROPOR * ls + col] = c.styropor_flag;
+  p.in[(size_t)IN_EVENTS0 * ls + col] = (int)c.ev0;
+  p.in[(size_t)IN_EVENTS1 * ls + col] = (int)c.ev1;
 }
 
 // Column -> slot indirection.  After samsim_b200_rebin the columns of a handle sit in regime order; `map`
@@ -268,8 +274,10 @@ __global__ void samsim_kat_getT_kernel(int salt_flag, int n, const double* H, co
   fill_liquidus(g, salt_flag);
   double T = 0.0, phi = 0.0;
   int status = 0;
-  getT(g, H[q], S_bu[q], T_in[q], T, phi, status);
-  T_out[q] = T; phi_out[q] = phi; st[q] = status;
+  unsigned ev1 = 0;
+  getT(g, H[q], S_bu[q], T_in[q], T, phi, status, ev1);
+  // status_out: the STOP code in the low 16 bits; bits 16.. = the EV_GETT_* branch bits (word 1 of the event words)
+  T_out[q] = T; phi_out[q] = phi; st[q] = status | (int)(ev1 << 16);
 }
 __global__ void samsim_kat_scalar_kernel(int fn, int salt_flag, int n, const double* a, const double* b, double* out) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -875,7 +883,7 @@ int samsim_b200_get_slot_map(samsim_handle_t h, int32_t* slot_of_col) {
 // ---- binary checkpoint / restart (the reference can only start from init) ----------------------
 // File: "SAMB2CK1", sizeof(samsim_config_t), the config, ncol, the clock, then in the caller's column order
 // arrays[id][col][extent], scalars[id][col], ints[id][col].  Forcing tables are inputs, not state: set them again.
-static const char CK_MAGIC[8] = {'S', 'A', 'M', 'B', '2', 'C', 'K', '1'};
+static const char CK_MAGIC[8] = {'S', 'A', 'M', 'B', '2', 'C', 'K', '2'};
 
 int samsim_b200_save_checkpoint(samsim_handle_t h, const char* path) {
   if (!h || !path) return fail(SAMSIM_ERR_ARG, "save_checkpoint: bad argument");

@@ -83,6 +83,7 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
     double& fl_rest = SCV(c, SC_FL_REST);
     albedo = albedo_of(thick_snow, SCV(c, SC_T_SNOW), pl1, thick_min, g.albedo_flag);
     if (g.atmoflux_flag == 1) {
+      EVT(c, EV_NOTZFLUX);
       notzflux(c.time + 86400.0 * 180.0, fl_sw, fl_rest);
     } else if (g.atmoflux_flag == 2) {  // :97-111
       double fl_lw;
@@ -134,6 +135,7 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
     else T_freeze = T_freeze_of(c.S_abs()[1] / c.m()[1], g.salt_flag);
 
     if (T_top > T_freeze && Na > 1) {  // :167-180
+      EVT(c, EV_HEAT_MELT);
       temp1 = emi * sigma * P4(T_freeze + zeroK) - (1.0 - albedo) * (1.0 - pen) * fl_sw - fl_rest;
       if (thick_snow >= thick_min) {
         fl_q_snow = temp1;
@@ -169,7 +171,10 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
         T_top = f_max(T_freeze, T1);
         flQ1 = g.alpha_flux_stable * (T_top - T2m);
       }
-      if (thick_snow == 0.0 && g.lab_snow_flag == 1 && c.styropor_flag == 1) flQ1 = flQ1 * g.k_styropor;
+      if (thick_snow == 0.0 && g.lab_snow_flag == 1 && c.styropor_flag == 1) {  // sub_fl_Q_styropor, mo_thermo_functions.f90:276
+        EVT(c, EV_STYROPOR);
+        flQ1 = flQ1 * g.k_styropor;
+      }
     } else if (g.lab_snow_flag == 1) {
       T_freeze = T_freeze_of(SCV(c, SC_S_ABS_SNOW) / SCV(c, SC_M_SNOW), g.salt_flag);
       T_top = SCV(c, SC_T_SNOW);
@@ -245,6 +250,7 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
 
   bool layer1_changed = false;
   if (thick_snow >= thick_min / 100.0 && thick_snow < thick_min) {  // :291-295
+    EVT(c, EV_HEAT_THIN_SNOW);
     SCV(c, SC_H_ABS_SNOW) = SCV(c, SC_H_ABS_SNOW) - fl_q_snow * dt;
     double H1 = c.H_abs()[1], phi1 = c.phi()[1];
     snow_coupling(g, c, H1, phi1, T1, c.m()[1], c.S_bu()[1]);
@@ -359,7 +365,7 @@ __device__ __noinline__ void fused_thermo_expulsion(const DevCfg& g, Col& c) {
     const double H = c.H_abs()[1] / m_k;
     phi_k = c.phi()[1];
     const double T_test = (Na >= 2) ? c.T()[2] : T_bottom;
-    getT(g, H, sbu_k, T_test, T_k, phi_k, c.status);
+    getT(g, H, sbu_k, T_test, T_k, phi_k, c.status, c.ev1);
     c.T()[1] = T_k; c.phi()[1] = phi_k;
   }
   double T_km1 = 0.0, Sbu_km1 = 0.0, Sabs_km1 = 0.0, f0 = 0.0;
@@ -471,8 +477,10 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     if (f_max(lp, sp) > 0.0 && (g.precip_flag == 1 || g.precip_flag == 0)) {
       const bool have_solid = (g.precip_flag == 0);
       if (c.N_active > 1) {
+        EVT(c, EV_SNOW_PRECIP);
         snow_precip(c, dt, lp, SCV(c, SC_T2M), have_solid, sp);
       } else if (c.N_active == 1) {
+        EVT(c, EV_SNOW_PRECIP_0);
         double H1 = c.H_abs()[1], S1 = c.S_abs()[1];
         snow_precip_0(H1, S1, c.m()[1], c.T()[1], dt, lp, SCV(c, SC_T2M), have_solid, sp);
         c.H_abs()[1] = H1; c.S_abs()[1] = S1;
@@ -524,7 +532,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
         sbu = c.S_abs()[k] / mk;
         const double H = c.H_abs()[k] / mk;
         phi = c.phi()[k];
-        getT(g, H, sbu, T_test, T, phi, c.status);
+        getT(g, H, sbu, T_test, T, phi, c.status, c.ev1);
         c.S_bu()[k] = sbu; c.T()[k] = T; c.phi()[k] = phi;
       }
       T_test = T;
@@ -604,6 +612,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     const int Na = c.N_active;
     const double pg = c.psi_g()[Na];
     if (pg > 0.0) {
+      EVT(c, EV_GAS_REFILL);
       const double temp2 = pg * c.thick()[Na] * rho_l;
       c.fb.res_valid = false;
       c.m()[Na] = c.m()[Na] + temp2;
@@ -630,6 +639,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
 
   // ---- S12 turbulence (sub_turb_flux, mo_functions.f90:347-363) :450-457 ----
   if (g.turb_flag == 2) {
+    EVT(c, EV_TURB);
     const int Na = c.N_active;
     const double S = c.S_abs()[Na], mNa = c.m()[Na];
     const double turb = Turb_A * det_exp(Turb_B * (-density_of(SCV(c, SC_T_BOTTOM), SCV(c, SC_S_BU_BOTTOM)) + density_of(c.T()[Na], S / mNa))) * dt;
@@ -650,10 +660,11 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     const bool next_step_outputs = (c.n_time_out == g.i_time_out);
     grav_drain(g, c, c.want_state || next_step_outputs);
   }
-  else if (g.grav_flag == 3 && c.N_active > 1) grav_drain_simple(g, c);
+  else if (g.grav_flag == 3 && c.N_active > 1) { EVT(c, EV_GRAV_DRAIN_SIMPLE); grav_drain_simple(g, c); }
 
   // ---- S14 prescribed salinity profile :482-497 (prescribe_flag 2) ----
   if (g.prescribe_flag == 2) {
+    EVT(c, EV_PRESCRIBE);
     const int Na = c.N_active;
     const double Sb = SCV(c, SC_S_BU_BOTTOM);
     int k = Na;
@@ -718,6 +729,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
 
   // ---- S16 tank :573-578 ----
   if (g.tank_flag == 2) {
+    EVT(c, EV_TANK);
     SCV(c, SC_S_BU_BOTTOM) = (SCV(c, SC_S_TOTAL) - sum_fwd(c.S_abs(), 1, c.N_active)) / (g.m_total - sum_fwd(c.m(), 1, c.N_active));
     if (g.n_bgc) {  // :575-577 (sic: every tracer gets the value computed from tracer 1)
       const double v = (SCV(c, SC_BGC_TOTAL1) - sum_fwd(c.bgc(0), 1, c.N_active)) / (g.m_total - sum_fwd(c.m(), 1, c.N_active));
@@ -755,7 +767,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
       const double sbu = Sk / mk;
       const double H = c.H_abs()[k] / mk;
       double T, phi = c.phi()[k];
-      getT(g, H, sbu, T_test, T, phi, c.status);
+      getT_body(g, H, sbu, T_test, T, phi, c.status, c.ev1);  // inlined: no call, no spills around it in the hot sweep
       T_test = T;
       c.S_bu()[k] = sbu; c.T()[k] = T; c.phi()[k] = phi;
     }
@@ -780,12 +792,16 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
       const double T_drive = (g.boundflux_flag == 2) ? SCV(c, SC_T_TOP) : SCV(c, SC_T2M);
       if (ps1 < psi_s_top_min || T_drive >= SCV(c, SC_T_FREEZE)) {
         double th1 = c.thick()[1];
-        melt_thick_of(c.psi_l()[1], ps1, c.psi_g()[1], c.T()[1], SCV(c, SC_T_FREEZE), T_drive, c.fl_Q()[1], SCV(c, SC_THICK_SNOW), dt,
-                      SCV(c, SC_MELT_THICK), th1, g.thick_min);
+        EVT(c, EV_MELT_THICK);
+        if (melt_thick_of(c.psi_l()[1], ps1, c.psi_g()[1], c.T()[1], SCV(c, SC_T_FREEZE), T_drive, c.fl_Q()[1], SCV(c, SC_THICK_SNOW), dt,
+                          SCV(c, SC_MELT_THICK), th1, g.thick_min)) EVT(c, EV_MELT_THICK_GAS);
         if (g.boundflux_flag == 3) SCV(c, SC_MELT_THICK) = f_max(SCV(c, SC_MELT_THICK), 0.0);
         if (SCV(c, SC_THICK_SNOW) >= g.thick_min / 100.0 && SCV(c, SC_MELT_THICK) > 0.00000000001 && SCV(c, SC_MELT_THICK_SNOW) == 0.0) {
           double H1 = c.H_abs()[1], m1 = c.m()[1];
-          melt_snow(SCV(c, SC_MELT_THICK), th1, SCV(c, SC_THICK_SNOW), H1, SCV(c, SC_H_ABS_SNOW), m1, SCV(c, SC_M_SNOW), SCV(c, SC_PSI_G_SNOW));
+          if (melt_snow(SCV(c, SC_MELT_THICK), th1, SCV(c, SC_THICK_SNOW), H1, SCV(c, SC_H_ABS_SNOW), m1, SCV(c, SC_M_SNOW), SCV(c, SC_PSI_G_SNOW)))
+            EVT(c, EV_MELT_SNOW_ALL);
+          else
+            EVT(c, EV_MELT_SNOW_PART);
           c.H_abs()[1] = H1; c.m()[1] = m1;
         }
         c.thick()[1] = th1;
@@ -799,6 +815,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   SCV(c, SC_MTO2) = SCV(c, SC_MTO2) + SCV(c, SC_MELT_THICK_SNOW);
   SCV(c, SC_MELT_THICK) = SCV(c, SC_MELT_THICK) + SCV(c, SC_MELT_THICK_SNOW);
   if (SCV(c, SC_MELT_THICK_SNOW) > 0.0) {  // :677-685
+    EVT(c, EV_SNOW_MELTWATER_TO_ICE);
     const double mts = SCV(c, SC_MELT_THICK_SNOW), T_snow = SCV(c, SC_T_SNOW);
     const double H1 = c.H_abs()[1] + mts * rho_l * c_l * T_snow;
     const double S1 = c.S_abs()[1] + mts * rho_l * S_br_of(g, T_snow, SCV(c, SC_S_ABS_SNOW) / SCV(c, SC_M_SNOW));
@@ -814,6 +831,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     if (g.flush_flag == 4) {  // :704-713
       const double mt = SCV(c, SC_MELT_THICK);
       if (mt > 0.000000000001 && c.N_active > 2) {
+        EVT(c, EV_FLUSH_INLINE);
         const double m1 = c.m()[1];
         c.H_abs()[1] = c.H_abs()[1] - mt * rho_l * c_l * c.T()[1];
         c.S_abs()[1] = c.S_abs()[1] * (1.0 - (mt * rho_l) / m1);
@@ -857,6 +875,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
         }
     const int Nb = c.N_active;
     if (Nb < N && c.thick()[(Nb + 1 < N) ? Nb + 1 : N] == 0) {  // :772-783 scrub
+      EVT(c, EV_SCRUB);
       c.T()[Nb + 1] = SCV(c, SC_T_BOTTOM);
       c.S_bu()[Nb + 1] = SCV(c, SC_S_BU_BOTTOM);
       c.psi_l()[Nb + 1] = 1.0;
@@ -885,6 +904,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     if (mn < 0.0) {
       c.status = 1337;
     } else if (ms < 0.0) {
+      EVT(c, EV_SALT_CLAMP);
       SAMSIM_LOOP
       for (int k = 1; k <= Na; k++) c.S_abs()[k] = f_max(c.S_abs()[k], 0.0);
       c.thermo_valid = false;

@@ -54,6 +54,8 @@ def lib():
         L.hostk_snapshot_scalars.restype = dp
         L.hostk_snapshot_scalars.argtypes = [C.c_void_p]
         L.hostk_get_snapshot_array.argtypes = [C.c_void_p, C.c_int, dp, C.c_int]
+        ipp = C.POINTER(C.c_int)
+        L.hostk_kat_getT.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp, ipp, ipp]
         L.hostk_step.restype = C.c_int
         L.hostk_step.argtypes = [C.c_void_p, C.c_longlong]
         _lib = L
@@ -101,9 +103,12 @@ class HostKernel:
         return np.array([self._sc()[api.SCALAR_IDS[name]]])
 
     def get_int(self, name, col=0, n=1):
-        out = (C.c_int * 3)()
+        out = (C.c_int * 5)()
         self.L.hostk_get_ints(self.h, out)
         return np.array([out[api.INT_IDS[name]]], dtype=np.int32)
+
+    def events(self, col: int = 0) -> set:
+        return api.decode_events(self.get_int("events0")[0], self.get_int("events1")[0])
 
     def get_clock(self):
         t, i, n, tc = C.c_double(), C.c_longlong(), C.c_int(), C.c_int()
@@ -143,3 +148,14 @@ class HostKernel:
             self.L.hostk_get_snapshot_array(self.h, j, api._dp(a), len(a))
             out[name] = a[: self.cfg.Nlayer - 1] if name == "ray" else a
         return out
+
+
+def kat_getT(salt_flag: int, H, S_bu, T_in):
+    """getT of the device code on the host, elementwise: T, phi, STOP code, word-1 event bits"""
+    H, S_bu, T_in = (np.ascontiguousarray(x, dtype=np.float64) for x in (H, S_bu, T_in))
+    n = len(H)
+    T, phi = np.empty(n), np.empty(n)
+    st, ev = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    lib().hostk_kat_getT(salt_flag, n, api._dp(H), api._dp(S_bu), api._dp(T_in), api._dp(T), api._dp(phi), ip(st), ip(ev))
+    return T, phi, st, ev

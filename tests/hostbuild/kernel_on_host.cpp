@@ -34,6 +34,7 @@ struct HostKernel {
   std::vector<double> arr;  // [AR_COUNT][LS], ncol_pad = 1
   double sc[SC_COUNT];
   int N_active, status, styropor_flag;
+  unsigned ev0 = 0, ev1 = 0;
   double time;
   long long i;
   int n_time_out, time_counter;
@@ -103,9 +104,9 @@ void hostk_set_ints(void* p, int N_active, int status, int styropor_flag) {
   HostKernel* h = (HostKernel*)p;
   h->N_active = N_active; h->status = status; h->styropor_flag = styropor_flag;
 }
-void hostk_get_ints(void* p, int* out3) {
+void hostk_get_ints(void* p, int* out5) {
   HostKernel* h = (HostKernel*)p;
-  out3[0] = h->N_active; out3[1] = h->status; out3[2] = h->styropor_flag;
+  out5[0] = h->N_active; out5[1] = h->status; out5[2] = h->styropor_flag; out5[3] = (int)h->ev0; out5[4] = (int)h->ev1;
 }
 void hostk_set_clock(void* p, double time, long long i, int n_time_out, int time_counter) {
   HostKernel* h = (HostKernel*)p;
@@ -134,6 +135,23 @@ void hostk_get_snapshot_array(void* p, int id, double* v, int n) {
   for (int k = 0; k < n; k++) v[k] = h->snap_arr[(size_t)id * h->LS + k + 1];
 }
 
+// getT of the device code, elementwise (known-answer test of the lazy freezing point); st = STOP code, ev = word-1 event bits
+void hostk_kat_getT(int salt_flag, int n, const double* H, const double* S_bu, const double* T_in, double* T_out,
+                    double* phi_out, int* st, int* ev) {
+  DevCfg g;
+  memset(&g, 0, sizeof g);
+  g.salt_flag = salt_flag;
+  if (salt_flag == 1) { g.c2 = -18.7; g.c3 = -0.519; g.c4 = -0.00535; g.d2 = -21.4; g.d3x2 = 2.0 * -0.886; g.d4x3 = 3.0 * -0.0170; }
+  else { g.c2 = -17.6; g.c3 = -0.389; g.c4 = -0.00362; g.d2 = -17.6; g.d3x2 = 2.0 * -0.389; g.d4x3 = 3.0 * -0.00362; }
+  for (int q = 0; q < n; q++) {
+    double T = 0.0, phi = 0.0;
+    int status = 0;
+    unsigned ev1 = 0;
+    getT(g, H[q], S_bu[q], T_in[q], T, phi, status, ev1);
+    T_out[q] = T; phi_out[q] = phi; st[q] = status; ev[q] = (int)ev1;
+  }
+}
+
 // one "launch" of nsteps steps: what samsim_step_kernel does for one thread (samsim_b200.cu), whole series as window
 int hostk_step(void* p, long long nsteps) {
   HostKernel* h = (HostKernel*)p;
@@ -143,6 +161,7 @@ int hostk_step(void* p, long long nsteps) {
   c.astr = (unsigned)h->LS;
   for (int q = 0; q < SC_COUNT; q++) c.sc[q] = h->sc[q];
   c.N_active = h->N_active; c.status = h->status; c.styropor_flag = h->styropor_flag;
+  c.ev0 = h->ev0; c.ev1 = h->ev1;
   c.time = h->time; c.i = h->i; c.n_time_out = h->n_time_out; c.time_counter = h->time_counter;
   c.fsw0 = c.fsw1 = c.flw0 = c.flw1 = c.ftime0 = c.ftime1 = 0.0;
   c.thermo_valid = false;
@@ -165,6 +184,7 @@ int hostk_step(void* p, long long nsteps) {
 
   for (int q = 0; q < SC_COUNT; q++) h->sc[q] = c.sc[q];
   h->N_active = c.N_active; h->status = c.status; h->styropor_flag = c.styropor_flag;
+  h->ev0 = c.ev0; h->ev1 = c.ev1;
   h->time = c.time; h->i = c.i; h->n_time_out = c.n_time_out; h->time_counter = c.time_counter;
   return c.status;
 }

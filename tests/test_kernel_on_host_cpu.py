@@ -12,6 +12,7 @@ import pytest
 sys.path.insert(0, str(Path(__file__).resolve().parent))
 from hostbuild import hostkernel as hk  # noqa: E402
 from oracle import parity_util as pu  # noqa: E402
+import scenarios  # noqa: E402
 
 
 def _fmt(bad, n=10):
@@ -181,3 +182,65 @@ def test_device_code_on_host_stop_codes(oracle_mod, what):
     if rc_o == 0:
         bad = pu.compare_column(ref, k, 0)
         assert not bad, _fmt(bad)
+
+
+@pytest.mark.parametrize("name", scenarios.NAMES)
+def test_device_code_on_host_constructed_branch_scenarios(oracle_mod, name):
+    """Branches the SHEBA year never enters (tests/scenarios.py): bitwise state AND proof that the branch ran on both
+    sides (oracle branch counters > 0, device event bits set, and the two event sets equal)."""
+    sc = scenarios.build(oracle_mod, name)
+    k = _from_oracle(sc.col)
+    if sc.forcing is not None:
+        k.set_forcing(sc.forcing)
+    if sc.lab is not None:
+        k.set_lab_forcing(sc.lab)
+    bad = scenarios.run(sc, k, pu.compare_column)
+    assert not bad, _fmt(bad)
+
+
+def test_device_code_on_host_events_of_the_standard_runs(oracle_mod, golden_dir):
+    """The event words agree with the oracle's branch counters on the regimes of the SHEBA year, and the runs execute
+    the branches DESIGN.md section 10 credits them with."""
+    z = np.load(golden_dir / "sheba_oracle_states.npz")
+    F = np.load(golden_dir / "forcing_era.npz")["sheba"]
+    expect = {80: {"bottom_growth_simple", "grav_drained", "snow_compaction"}, 200: {"bottom_growth", "grav_drained"},
+              345: {"flush3", "snow_wet", "flush3_clamp", "snow_meltwater_to_ice", "heat_melt"},
+              380: {"flush3", "getT_Tfr_fallback", "heat_thin_snow", "melt_thick_gas"},
+              400: {"flush3", "bottom_melt_simple_a", "top_melt_b"}, 715: {"top_melt_c", "flush3"},
+              730: {"snow_merge", "melt_snow_part", "heat_thin_snow"}}
+    for rec, need in expect.items():
+        col = oracle_mod.Column(4, "det")
+        col.set_forcing(*F)
+        col.load_state(_state(z, rec))
+        k = _from_oracle(col)
+        k.set_forcing(F)
+        assert col.step(3000) == 0 and k.step(3000) == 0
+        o = col.events()
+        assert need <= o, (rec, sorted(need - o))
+        assert o == k.events(), (rec, sorted(o ^ k.events()))
+
+
+@pytest.mark.parametrize("salt_flag", [1, 2])
+def test_device_getT_on_host_lazy_freezing_point(oracle_mod, salt_flag):
+    """getT evaluates the freezing point only when an iterate leaves [-200, 0] degC (mo_thermo_functions.f90:101-103);
+    the reference computes it every call.  Same bits on inputs that take the fallback and on inputs that do not."""
+    import ctypes as C
+    L = oracle_mod.lib("det")
+    rng = np.random.default_rng(12)
+    n = 20000
+    S = np.concatenate([rng.uniform(0.5, 40, n // 2), rng.uniform(0, 0.002, n // 4), rng.uniform(30, 250, n // 4)])
+    T_true = rng.uniform(-45, 2, n)
+    H = np.where(rng.random(n) < 0.8, -333500.0 * rng.random(n) ** 0.5 + 2020.0 * T_true, 3400.0 * T_true)
+    T_in = T_true + rng.normal(0, 0.3, n)
+    T_in[::7] = rng.uniform(0.5, 30.0, len(T_in[::7]))      # first guesses above 0 degC: iterates leave the interval
+    T_in[3::11] = rng.uniform(-400.0, -210.0, len(T_in[3::11]))
+    Tk, pk, st, ev = hk.kat_getT(salt_flag, H, S, T_in)
+    To, po = np.empty(n), np.empty(n)
+    dp = C.POINTER(C.c_double)
+    L.sam_kat_getT(salt_flag, n, H.ctypes.data_as(dp), S.ctypes.data_as(dp), T_in.ctypes.data_as(dp), To.ctypes.data_as(dp), po.ctypes.data_as(dp))
+    ok = st == 0
+    assert ok.sum() > 0.9 * n
+    assert pu.same_bits(Tk[ok], To[ok]).all() and pu.same_bits(pk[ok], po[ok]).all()
+    assert np.isnan(To[~ok]).all()
+    fallback = (ev >> 1) & 1   # bit (SAMSIM_EV_GETT_TFR_FALLBACK - 32)
+    assert fallback.sum() > 500 and (fallback == 0).sum() > 5000, (fallback.sum(), n)

@@ -7,8 +7,14 @@ both sides use IEEE +,-,*,/ in the reference's operation order (gcc -ffp-contrac
 import numpy as np
 import pytest
 
+import sys
+from pathlib import Path
+
 from samsim_b200 import api
 from oracle import parity_util as pu
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+import scenarios  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -42,7 +48,9 @@ def test_getT_kat(oracle_mod, salt_flag):
     T_true = rng.uniform(-45, 2, n)
     H = np.where(rng.random(n) < 0.8, -333500.0 * rng.random(n) ** 0.5 + 2020.0 * T_true, 3400.0 * T_true)
     T_in = T_true + rng.normal(0, 0.3, n)
-    Tg, pg, st = api.kat_getT(salt_flag, H, S, T_in)
+    T_in[::7] = rng.uniform(0.5, 30.0, len(T_in[::7]))        # first guesses outside [-200, 0]: the iterate restarts at
+    T_in[3::11] = rng.uniform(-400.0, -210.0, len(T_in[3::11]))  # the (lazily evaluated) freezing point, :101-103
+    Tg, pg, st, ev = api.kat_getT(salt_flag, H, S, T_in)
     To, po = np.empty(n), np.empty(n)
     dp = C.POINTER(C.c_double)
     L.sam_kat_getT(salt_flag, n, H.ctypes.data_as(dp), S.ctypes.data_as(dp), T_in.ctypes.data_as(dp), To.ctypes.data_as(dp), po.ctypes.data_as(dp))
@@ -51,6 +59,8 @@ def test_getT_kat(oracle_mod, salt_flag):
     assert pu.same_bits(Tg[ok], To[ok]).all()
     assert pu.same_bits(pg[ok], po[ok]).all()
     assert np.isnan(To[~ok]).all()  # the oracle STOPs (99) exactly where the GPU flags status 99
+    fallback, saltfree, liquid = (ev >> 1) & 1, (ev >> 2) & 1, (ev >> 3) & 1  # bit SAMSIM_EV_GETT_* - 32
+    assert fallback.sum() > 500 and saltfree.sum() > 1000 and liquid.sum() > 100, (fallback.sum(), saltfree.sum(), liquid.sum())
 
 
 @pytest.mark.parametrize("fn,two", [(0, False), (1, True), (2, False), (3, True), (4, False), (5, True), (6, True)])
@@ -272,6 +282,10 @@ def test_lab_tank_batch_of_five(oracle_mod):
             bad = pu.compare_column(col, eng, q, label=f"testcase {101 + q} step {target}: ")
             assert not bad, _fmt(bad)
     assert max(c.int("N_active") for c in cols) >= 3 and max(c.stat("coupling_iters") for c in cols) > 1000  # thin lab snow: iterative snow_coupling
+    for q, col in enumerate(cols):  # the branches this batch is credited with ran, on both sides
+        o, g = col.events(), eng.events(q)
+        assert {"snow_coupling_iter", "tank", "heat_thin_snow"} <= o and o == g, (q, sorted(o ^ g))
+        assert "styropor" not in o  # the plate sits on snow in this series: tests/scenarios.py 'styropor' covers the factor
 
 
 def test_testcase1_perturbed_ensemble(oracle_mod):
@@ -473,8 +487,9 @@ def test_other_testcases_from_init(oracle_mod, testcase):
 
 
 def test_testcase7_simple_parametrisations(oracle_mod, golden_dir):
-    """Testcase 7 = SHEBA forcing with fl_grav_drain_simple, flush4, flood_simple and albedo_flag 1: from the
-    oracle's autumn state so that ice exists within the window."""
+    """Testcase 7 = SHEBA forcing with the simple parametrisations selected: from the oracle's autumn state so that
+    ice exists within the window.  This window executes fl_grav_drain_simple and albedo_flag 1 only (asserted below);
+    flush4 and flood_simple need melt / a negative freeboard and are covered by tests/scenarios.py."""
     F = _forcing(golden_dir)
     col = oracle_mod.Column(7, "det")
     col.set_forcing(*F)
@@ -487,6 +502,8 @@ def test_testcase7_simple_parametrisations(oracle_mod, golden_dir):
         eng.step(n)
         bad = pu.compare_column(col, eng, 1, label=f"testcase 7 +{n}: ")
         assert not bad, _fmt(bad)
+    o = col.events()
+    assert "grav_drain_simple" in o and not ({"flush4", "flood_simple"} & o) and o == eng.events(1)
 
 
 def test_prescribe_flag_2(oracle_mod):
@@ -557,3 +574,47 @@ def test_tracers_tank_and_snapshot(oracle_mod):
             for kind in ("bu", "br"):
                 assert pu.same_bits(rec[f"bgc{t}_{kind}"], snap[f"bgc{t}_{kind}"][1]).all(), (testcase, t, kind)
         assert abs(col.scalar("bgc_bottom1") - 385.0) > 1e-6  # the tank budget really moved the water concentration
+
+
+@pytest.mark.parametrize("name", scenarios.NAMES)
+def test_constructed_branch_scenarios(oracle_mod, name):
+    """Branches that neither the SHEBA year nor the testcases from `init` enter (tests/scenarios.py): flood incl. the
+    instant flooding beyond neg_free, flood_simple, flush4, flush_flag 4, snow_thermo with snow_flush_flag 0, the
+    top_grow / top_melt sub-cases, bottom_melt(_simple) with a full grid, the warm branches of snow_coupling,
+    sub_melt_snow with all the snow flooded, the styropor factor, the S24 salt clamp.  Bitwise state through the C ABI
+    AND proof that each branch ran: oracle counters > 0, device event bits set, the two event sets equal."""
+    sc = scenarios.build(oracle_mod, name)
+    eng = pu.engine_from_oracle(sc.col, ncol=33)
+    if sc.forcing is not None:
+        eng.set_forcing(sc.forcing[None])
+    if sc.lab is not None:
+        eng.set_lab_forcing(sc.lab[None])
+    bad = scenarios.run(sc, eng, lambda o, e, c, label="": pu.compare_column(o, e, 32, label=label))
+    assert not bad, _fmt(bad)
+    assert eng.events(32) == eng.events(0)
+
+
+def test_event_words_of_the_sheba_windows(oracle_mod, golden_dir):
+    """The event words agree with the oracle's branch counters in the regimes of the SHEBA year, and the windows
+    execute the branches DESIGN.md section 10 credits them with."""
+    expect = {80: {"bottom_growth_simple", "grav_drained", "snow_compaction"}, 200: {"bottom_growth", "grav_drained"},
+              345: {"flush3", "snow_wet", "flush3_clamp", "snow_meltwater_to_ice", "heat_melt"},
+              380: {"flush3", "getT_Tfr_fallback", "heat_thin_snow", "melt_thick_gas"},
+              400: {"flush3", "bottom_melt_simple_a", "top_melt_b"}, 715: {"top_melt_c", "flush3"},
+              730: {"snow_merge", "melt_snow_part", "heat_thin_snow"}}
+    F = _forcing(golden_dir)
+    for rec, need in expect.items():
+        col = oracle_mod.Column(4, "det")
+        col.set_forcing(*F)
+        col.load_state(scenarios.sheba_state(rec))
+        eng = pu.engine_from_oracle(col, ncol=2)
+        eng.set_forcing(F[None])
+        assert col.step(3000) == 0
+        eng.step(3000)
+        o = col.events()
+        assert need <= o, (rec, sorted(need - o))
+        assert o == eng.events(1), (rec, sorted(o ^ eng.events(1)))
+        bad = pu.compare_column(col, eng, 1, label=f"state {rec} +3000: ")
+        assert not bad, _fmt(bad)
+        eng.clear_events()
+        assert eng.events(0) == set()
