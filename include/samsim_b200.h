@@ -283,10 +283,13 @@ int samsim_b200_get_slot_map(samsim_handle_t h, int32_t* slot_of_col);
 int samsim_b200_save_checkpoint(samsim_handle_t h, const char* path);
 int samsim_b200_load_checkpoint(samsim_handle_t h, const char* path);
 
-/* raw device pointers for zero-copy interop (torch): arrays[array_id][k][ncol_pad], k = 0..Nlayer+1; the column
- * index is the SLOT (samsim_b200_get_slot_map) once the handle has been re-binned */
+/* raw device pointers for zero-copy interop (torch).  arrays is the warp-tiled state buffer
+ * arrays[ncol_pad/32][lstride][narrays][32]: element (array a, layer k = 0..Nlayer+1) of the column in device slot s is
+ * arrays[(((s/32)*lstride + k)*narrays + a)*32 + s%32]; a = samsim_array_id for the first 15 arrays, the tracer arrays
+ * sit at a = 22, 23 (behind the scratch arrays).  scalars[scalar_id][ncol_pad], ints[int_id][ncol_pad].  The column
+ * index is the SLOT (samsim_b200_get_slot_map) once the handle has been re-binned. */
 int samsim_b200_device_layout(samsim_handle_t h, void** arrays, void** scalars, void** ints, int64_t* ncol_pad,
-                              int64_t* lstride);
+                              int64_t* lstride, int64_t* narrays);
 
 /* ---- unit known-answer entry points (device functions evaluated elementwise on the GPU) ---- */
 /* status_out[q]: STOP code (0 or 99) in the low 16 bits, the SAMSIM_EV_GETT_* bits of event word 1 shifted left by 16 */

@@ -177,7 +177,7 @@ def load_library() -> C.CDLL:
         "samsim_b200_launch_count": (C.c_int64, [H]),
         "samsim_b200_last_step_ms": (C.c_int, [H, C.POINTER(C.c_float)]),
         "samsim_b200_device_layout": (C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
-                                                C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+                                                C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
         "samsim_b200_save_checkpoint": (C.c_int, [H, C.c_char_p]),
         "samsim_b200_load_checkpoint": (C.c_int, [H, C.c_char_p]),
         "samsim_b200_rebin": (C.c_int, [H, ip]),

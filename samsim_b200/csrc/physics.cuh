@@ -1,9 +1,15 @@
 // physics.cuh -- per-column device physics of the SAMSIM timestep for sm_100a.
 //
-// One thread owns one column.  Per-layer arrays live in an SoA, layer-major device buffer
-// (element k of column c of array a is arr[(a*LS + k)*ncol_pad + c]) so that the 32 columns of
-// a warp touch 32 consecutive doubles for every per-layer access.  Per-column scalars are
-// loaded into the Col struct (registers / local memory) for the duration of a launch.
+// One thread owns one column.  Per-layer arrays live in a warp-tiled SoA device buffer: the 32 columns of a warp
+// form a tile, and element (array a, layer k) of column c is
+//     arr[(((c/32)*LS + k)*NA + a)*32 + c%32]            LS = Nlayer+2, NA = number of arrays
+// so that (1) the 32 columns of a warp touch 32 consecutive doubles (one 256-byte request) for every per-layer
+// access, (2) all arrays of one layer sit next to each other: from the thread's layer pointer base + k*(NA*32) every
+// array is a compile-time immediate offset a*256 B (no per-access address arithmetic: the first layout,
+// [a][k][column], spent 30 % of the kernel's instructions on IMAD/LEA/UMOV/R2UR address computation), and (3) a
+// warp's whole state is one contiguous 0.5 MB region (one TLB entry, DRAM pages shared by the arrays of a layer)
+// instead of 2200 rows 8 MB apart.  Per-column scalars are loaded into the Col struct (registers / local memory)
+// for the duration of a launch.
 //
 // Arithmetic contract: this file is compiled with -fmad=false; every expression keeps the
 // reference's left-to-right operation order, the transcendental calls go through detmath.h,
@@ -35,6 +41,18 @@ struct DevCfg {
   // liquidus coefficients for salt_flag
   double c2, c3, c4, d2, d3x2, d4x3;
 };
+
+// The configuration of the running launch.  On the device it lives in constant memory so that flags, dt and the
+// liquidus coefficients are constant-bank operands of the arithmetic instructions (passed by reference through the
+// call tree they were generic loads: three per liquidus evaluation).  samsim_b200_step uploads the handle's DevCfg
+// before a launch whenever another handle used the device last.
+#ifdef SAMSIM_HOST_BUILD
+static const DevCfg* samsim_host_cfg = nullptr;   // tests/hostbuild: set by the harness before column_step
+#define CFG (*samsim::samsim_host_cfg)
+#else
+__constant__ DevCfg samsim_dev_cfg;
+#define CFG samsim::samsim_dev_cfg
+#endif
 
 // scalar slots: MUST stay in the order of samsim_scalar_id (include/samsim_b200.h)
 enum {
@@ -83,9 +101,14 @@ enum {
 
 // strided per-layer view of one column (1-based layer index like the reference)
 struct Lay {
-  double* p;
-  unsigned ls;  // ncol_pad; (Nlayer+2)*ncol_pad < 2^32 is checked at create time, so 32-bit index arithmetic
-  __device__ __forceinline__ double& operator[](int k) const { return p[(unsigned)k * ls]; }
+  double* p;    // &arr[tile][0][a][lane]
+  unsigned ls;  // NA*32: elements between consecutive layers of the tile (32-bit index arithmetic inside a tile)
+  __device__ __forceinline__ double& operator[](int k) const {
+#if !defined(SAMSIM_HOST_BUILD) && defined(__CUDA_ARCH__)
+    __builtin_assume(__isGlobal(p));  // ld.global / st.global instead of generic accesses
+#endif
+    return p[(unsigned)k * ls];
+  }
   // non-blocking L1 prefetch of layer k (sweeps are latency bound: one 256-byte warp request per layer and
   // array, no spatial reuse between layers); k is clamped by the callers to [0, Nlayer+1]
   __device__ __forceinline__ void prefetch(int k) const {
@@ -105,13 +128,16 @@ struct Lay {
 #define SAMSIM_PF 2  // prefetch distance in layers (2 measured best on B200: 70.8 vs 69.5 M col-steps/s at 4, 64.7 at 12)
 #endif
 
-// everything one thread needs.  The per-layer views are built on the fly from three registers (base, ls, astr)
-// instead of being stored: 22 stored views were 350 B of local memory per thread and two local loads per access.
-struct Col {
-  double* base;    // &arr[col]
-  unsigned ls;     // ncol_pad
-  unsigned astr;   // (Nlayer+2)*ncol_pad: elements between consecutive arrays
-  __device__ __forceinline__ Lay A(int id) const { return Lay{base + (size_t)((unsigned)id * astr), ls}; }
+// elements between consecutive arrays of one layer of a tile (the 32 lanes); ARR_TILE*8 = 256 B
+#define SAMSIM_TILE 32
+// The per-layer views are built on the fly from two registers (base, ls) instead of being stored: 22 stored views
+// were 350 B of local memory per thread and two local loads per access.  Functions copy the View out of the Col
+// (`const View v = c`): Col lives in local memory (it is passed by reference through the call tree), and without the
+// copy every layer iteration re-loaded base and ls from it.
+struct View {
+  double* base;    // &arr[tile][0][0][lane]
+  unsigned ls;     // NA*32
+  __device__ __forceinline__ Lay A(int id) const { return Lay{base + id * SAMSIM_TILE, ls}; }
   __device__ __forceinline__ Lay m() const { return A(AR_M); }
   __device__ __forceinline__ Lay S_abs() const { return A(AR_S_ABS); }
   __device__ __forceinline__ Lay H_abs() const { return A(AR_H_ABS); }
@@ -135,6 +161,8 @@ struct Col {
   __device__ __forceinline__ Lay w2() const { return A(AR_W2); }
   __device__ __forceinline__ Lay w3() const { return A(AR_W3); }
   __device__ __forceinline__ Lay bgc(int q) const { return A(AR_BGC1 + q); }  // q = 0, 1
+};
+struct Col : View {
   double fb_x;  // fl_brine_bgc(N_active, 1): flooding (N_active >= 3; it is the up-cell of layer 1 when N_active == 2)
   int N_active, status, styropor_flag;
   unsigned ev0, ev1;  // branch events EV_* (bits 0..31 / 32..63), accumulated over the handle's lifetime
@@ -179,19 +207,19 @@ __device__ __forceinline__ double P4(double x) { double x2 = x * x; return x2 * 
 // ==========================================================================================
 
 // func_S_br(T), mo_thermo_functions.f90:308-351 (c1 = 0 is added first, as in the source)
-__device__ __forceinline__ double S_br_of(const DevCfg& g, double T) {
-  return 0.0 + g.c2 * T + g.c3 * P2(T) + g.c4 * P3(T);
+__device__ __forceinline__ double S_br_of(double T) {
+  return 0.0 + CFG.c2 * T + CFG.c3 * P2(T) + CFG.c4 * P3(T);
 }
 // func_S_br(T,S_bu): clamp to >= S_bu, :353-357
-__device__ __forceinline__ double S_br_of(const DevCfg& g, double T, double S_bu) {
-  double s = S_br_of(g, T);
+__device__ __forceinline__ double S_br_of(double T, double S_bu) {
+  double s = S_br_of(T);
   return (s < S_bu) ? S_bu : s;
 }
 // func_ddT_S_br, :380-414
-__device__ __forceinline__ double ddT_S_br_of(const DevCfg& g, double T) {
+__device__ __forceinline__ double ddT_S_br_of(double T) {
   const double T_crit = -20.0;
-  double d = g.d2 + g.d3x2 * T + g.d4x3 * P2(T);
-  if (T < T_crit) d = g.d2 + g.d3x2 * T_crit + g.d4x3 * P2(T_crit);
+  double d = CFG.d2 + CFG.d3x2 * T + CFG.d4x3 * P2(T);
+  if (T < T_crit) d = CFG.d2 + CFG.d3x2 * T_crit + CFG.d4x3 * P2(T_crit);
   return d;
 }
 
@@ -202,38 +230,38 @@ __device__ __forceinline__ double ddT_S_br_of(const DevCfg& g, double T) {
 // iterate leaves [-200, 0] degC (:101-103).  T_fr depends on S_bu alone and computing it has no side effect, so it
 // is evaluated here on first use: same bits whenever the reference terminates, 11 of the ~25 divisions of a call gone.
 // `ev1` receives the EV_GETT_* branch bits (word 1).
-__device__ __forceinline__ double getT_freezing_point(const DevCfg& g, double S_bu) {
+__device__ __forceinline__ double getT_freezing_point(double S_bu) {
   double T_fr = -1.0;
-  while (fabs(S_br_of(g, T_fr) / S_bu - 1.0) > SAMSIM_F32(0.0001)) {  // :87
+  while (fabs(S_br_of(T_fr) / S_bu - 1.0) > SAMSIM_F32(0.0001)) {  // :87
     const double T_0 = T_fr;
-    const double f = S_br_of(g, T_0) - S_bu;
-    const double ddT_f = ddT_S_br_of(g, T_0);
+    const double f = S_br_of(T_0) - S_bu;
+    const double ddT_f = ddT_S_br_of(T_0);
     T_fr = T_0 - f / ddT_f;
   }
   return T_fr;
 }
-__device__ __forceinline__ void getT_body(const DevCfg& g, double H, double S_bu, double T_in, double& T_out, double& phi,
+__device__ __forceinline__ void getT_body(double H, double S_bu, double T_in, double& T_out, double& phi,
                                           int& status, unsigned& ev1) {
   double T = H / c_l;
-  if (S_br_of(g, T, S_bu) > S_bu && S_bu > 0.001) {
+  if (S_br_of(T, S_bu) > S_bu && S_bu > 0.001) {
     double T_0, f, ddT_f;
     T_0 = T_in;
     {
-      double sb = S_br_of(g, T_0);
+      double sb = S_br_of(T_0);
       f = -latent_heat - H + latent_heat * S_bu / f_max(sb, 0.000000001) + c_s * T_0 + c_s_beta * T_0 * T_0 / 2.0;  // :95
-      ddT_f = c_s + c_s_beta * T_0 - latent_heat * S_bu * ddT_S_br_of(g, T_0) / f_max(P2(sb), 0.0000000001);      // :96
+      ddT_f = c_s + c_s_beta * T_0 - latent_heat * S_bu * ddT_S_br_of(T_0) / f_max(P2(sb), 0.0000000001);      // :96
     }
     T = T_0 - f / ddT_f;
     int it = 0;
     while (fabs(f) > 1.0) {  // :99
       T_0 = T;
       if (T_0 > 0.0 || T_0 < -200.0) {  // :101-103
-        T_0 = getT_freezing_point(g, S_bu);
+        T_0 = getT_freezing_point(S_bu);
         ev1 |= 1u << (EV_GETT_TFR_FALLBACK - 32);
       }
-      double sb = S_br_of(g, T_0);
+      double sb = S_br_of(T_0);
       f = -latent_heat - H + latent_heat * S_bu / f_max(sb, 0.0000000001) + c_s * T_0 + c_s_beta * T_0 * T_0 / 2.0;  // :104
-      ddT_f = c_s + c_s_beta * T_0 - latent_heat * S_bu * ddT_S_br_of(g, T_0) / f_max(sb * sb, 0.0000000001);       // :105
+      ddT_f = c_s + c_s_beta * T_0 - latent_heat * S_bu * ddT_S_br_of(T_0) / f_max(sb * sb, 0.0000000001);       // :105
       T = T_0 - f / ddT_f;
       it++;
       if (it == 260) {  // :114-123 STOP 99
@@ -241,7 +269,7 @@ __device__ __forceinline__ void getT_body(const DevCfg& g, double H, double S_bu
         break;
       }
     }
-    phi = 1.0 - S_bu / S_br_of(g, T, S_bu);  // :125
+    phi = 1.0 - S_bu / S_br_of(T, S_bu);  // :125
   } else if (S_bu < 0.001) {  // :127-137 salt-free
     ev1 |= 1u << (EV_GETT_SALTFREE - 32);
     if (H > 0.0) {
@@ -261,9 +289,9 @@ __device__ __forceinline__ void getT_body(const DevCfg& g, double H, double S_bu
   T_out = T;
 }
 // out-of-line copy for the call sites outside the two Newton sweeps (snow, coupling, layer 1)
-__device__ __noinline__ void getT(const DevCfg& g, double H, double S_bu, double T_in, double& T_out, double& phi,
+__device__ __noinline__ void getT(double H, double S_bu, double T_in, double& T_out, double& phi,
                                   int& status, unsigned& ev1) {
-  getT_body(g, H, S_bu, T_in, T_out, phi, status, ev1);
+  getT_body(H, S_bu, T_in, T_out, phi, status, ev1);
 }
 
 // Expulsion, mo_thermo_functions.f90:157-187
@@ -383,10 +411,11 @@ __device__ __forceinline__ double sum_prod_fwd(const Lay& a, const Lay& b, int i
 // S4/S5 and at flood/flush/layer events (which reset the memo), so between the calls of one step only m(1),
 // thick(1), m_snow can differ and they are compared; (2) the forward totals are reused while thick(1) is unchanged;
 // (3) the exact suffix sums for waterline layer ks are reused.  (2) and (3) are pre-filled by the fused S4 pass.
-__device__ __noinline__ double freeboard_of(const DevCfg& g, Col& c) {
+__device__ __noinline__ double freeboard_of(Col& c) {
+  const View v = c;
   const int Na = c.N_active;
-  const double snowmass = (g.freeboard_snow_flag == 0) ? SCV(c, SC_M_SNOW) : 0.0;
-  const double m1 = c.m()[1], th1 = c.thick()[1];
+  const double snowmass = (CFG.freeboard_snow_flag == 0) ? SCV(c, SC_M_SNOW) : 0.0;
+  const double m1 = v.m()[1], th1 = v.thick()[1];
   Col::FbMemo& fb = c.fb;
   if (fb.res_valid && fb.m1 == m1 && fb.th1 == th1 && fb.msnow == snowmass) return fb.result;
   double A, G;
@@ -396,10 +425,10 @@ __device__ __noinline__ double freeboard_of(const DevCfg& g, Col& c) {
     A = 0.0; G = 0.0;  // forward totals, the reference's order
     SAMSIM_LOOP
     for (int q = 1; q <= Na; q++) {
-      if (q + SAMSIM_PF <= Na) { c.psi_s().prefetch(q + SAMSIM_PF); c.psi_g().prefetch(q + SAMSIM_PF); c.thick().prefetch(q + SAMSIM_PF); }
-      const double t = c.thick()[q];
-      A = A + c.psi_s()[q] * t;
-      G = G + c.psi_g()[q] * t;
+      if (q + SAMSIM_PF <= Na) { v.psi_s().prefetch(q + SAMSIM_PF); v.psi_g().prefetch(q + SAMSIM_PF); v.thick().prefetch(q + SAMSIM_PF); }
+      const double t = v.thick()[q];
+      A = A + v.psi_s()[q] * t;
+      G = G + v.psi_g()[q] * t;
     }
     fb.tot_valid = true; fb.t1 = th1; fb.A = A; fb.G = G;
   }
@@ -414,11 +443,11 @@ __device__ __noinline__ double freeboard_of(const DevCfg& g, Col& c) {
     int k = 0;
     while (test1 < test2) {  // :114-118
       k = k + 1;
-      const double t = c.thick()[k];
-      pA = pA + c.psi_s()[k] * t;   // same partial sums as the forward totals above
-      pG = pG + c.psi_g()[k] * t;
+      const double t = v.thick()[k];
+      pA = pA + v.psi_s()[k] * t;   // same partial sums as the forward totals above
+      pG = pG + v.psi_g()[k] * t;
       msum_prev = msum;
-      msum = msum + c.m()[k];       // SUM(m(1:k)): fixed-start prefix, incremental is the same order
+      msum = msum + v.m()[k];       // SUM(m(1:k)): fixed-start prefix, incremental is the same order
       thsum_prev = thsum;
       thsum = thsum + t;            // SUM(thick(1:k)) likewise
       test1 = msum + snowmass;
@@ -427,8 +456,8 @@ __device__ __noinline__ double freeboard_of(const DevCfg& g, Col& c) {
         test2 = approx + margin;    // certainly test1 < exact test2: keep looping (value unused)
       } else {
         if (!(fb.suf_valid && fb.ks == k)) {
-          fb.As = sum_prod_fwd(c.psi_s(), c.thick(), k + 1, Na);
-          fb.Gs = sum_prod_fwd(c.psi_g(), c.thick(), k + 1, Na);
+          fb.As = sum_prod_fwd(v.psi_s(), v.thick(), k + 1, Na);
+          fb.Gs = sum_prod_fwd(v.psi_g(), v.thick(), k + 1, Na);
           fb.ks = k; fb.suf_valid = true;
         }
         test2 = fb.As * (rho_l - rho_s) + fb.Gs * rho_l;
@@ -436,7 +465,7 @@ __device__ __noinline__ double freeboard_of(const DevCfg& g, Col& c) {
     }
     fb.k_last = k;
     test1 = msum_prev + snowmass;  // :121 SUM(m(1:k-1))
-    const double mk = c.m()[k], tk = c.thick()[k];
+    const double mk = v.m()[k], tk = v.thick()[k];
     freeboard = test2 - test1 + (rho_l - mk / tk) * tk;  // :124
     freeboard = freeboard / rho_l;
     freeboard = freeboard + thsum_prev;                  // :126 SUM(thick(1:k-1))
@@ -504,22 +533,22 @@ __device__ __forceinline__ bool melt_snow(double& melt_thick, double& thick, dou
 
 // One layer of mass_transfer, mo_mass.f90:76-95.  f1 = fl_m(k+1), f0 = fl_m(k); *_km1 / *_kp1 are the neighbours
 // (TT, SS_bu, SS_abs of the reference; Sabs_km1 is the ALREADY UPDATED S_abs(k-1), :91).  H, S = H_abs(k), S_abs(k).
-__device__ __forceinline__ void mass_transfer_layer(const DevCfg& g, double f1, double f0, double T_km1, double Sbu_km1,
+__device__ __forceinline__ void mass_transfer_layer(double f1, double f0, double T_km1, double Sbu_km1,
                                                     double Sabs_km1, double T_k, double Sbu_k, double T_kp1,
                                                     double Sbu_kp1, double Sabs_kp1, double& H, double& S) {
   if (f1 > 0.) {
     H = H + f1 * T_kp1 * c_l;
-    S = S + f_min(f1 * S_br_of(g, T_kp1, Sbu_kp1), Sabs_kp1);
+    S = S + f_min(f1 * S_br_of(T_kp1, Sbu_kp1), Sabs_kp1);
   } else if (f1 < 0.) {
     H = H + f1 * T_k * c_l;
-    S = S + f_max(f1 * S_br_of(g, T_k, Sbu_k), -S);
+    S = S + f_max(f1 * S_br_of(T_k, Sbu_k), -S);
   }
   if (f0 > 0.) {
     H = H - f0 * T_k * c_l;
-    S = S - f_min(f0 * S_br_of(g, T_k, Sbu_k), S);
+    S = S - f_min(f0 * S_br_of(T_k, Sbu_k), S);
   } else if (f0 < 0) {
     H = H - f0 * T_km1 * c_l;
-    S = S - f_max(f0 * S_br_of(g, T_km1, Sbu_km1), -Sabs_km1);
+    S = S - f_max(f0 * S_br_of(T_km1, Sbu_km1), -Sabs_km1);
   }
 }
 
@@ -529,36 +558,37 @@ __device__ __forceinline__ void mass_transfer_layer(const DevCfg& g, double f1, 
 // in the last branch IS the updated value in the reference too (:91).
 // `kstart`: the caller guarantees fl_m(1:kstart) == 0, so layers 1..kstart-1 are left untouched (both of their
 // faces carry no flux) and the pass starts at kstart; with kstart > 1 the carried neighbour values are loaded.
-__device__ __noinline__ void mass_transfer(const DevCfg& g, Col& c, const Lay& fl_m, const Lay& S_bu_view, int kstart = 1) {
+__device__ __noinline__ void mass_transfer(Col& c, const Lay& fl_m, const Lay& S_bu_view, int kstart = 1) {
+  const View v = c;
   const int Na = c.N_active;
   const double T_bottom = SCV(c, SC_T_BOTTOM), S_bu_bottom = SCV(c, SC_S_BU_BOTTOM);
   if (kstart < 1) kstart = 1;
   if (kstart > Na) return;
   double T_km1 = 0.0, Sbu_km1 = 0.0, Sabs_km1 = 0.0;  // k = 1: fl_m(1) == 0 at every call site, never read
-  if (kstart > 1) { T_km1 = c.T()[kstart - 1]; Sbu_km1 = S_bu_view[kstart - 1]; Sabs_km1 = c.S_abs()[kstart - 1]; }
-  double T_k = c.T()[kstart], Sbu_k = S_bu_view[kstart];
+  if (kstart > 1) { T_km1 = v.T()[kstart - 1]; Sbu_km1 = S_bu_view[kstart - 1]; Sabs_km1 = v.S_abs()[kstart - 1]; }
+  double T_k = v.T()[kstart], Sbu_k = S_bu_view[kstart];
   double f0 = fl_m[kstart];
   SAMSIM_LOOP
   for (int k = kstart; k <= Na; k++) {
     if (k + SAMSIM_PF <= Na) {
-      c.T().prefetch(k + SAMSIM_PF); S_bu_view.prefetch(k + SAMSIM_PF); c.S_abs().prefetch(k + SAMSIM_PF);
-      c.H_abs().prefetch(k + SAMSIM_PF); fl_m.prefetch(k + SAMSIM_PF);
+      v.T().prefetch(k + SAMSIM_PF); S_bu_view.prefetch(k + SAMSIM_PF); v.S_abs().prefetch(k + SAMSIM_PF);
+      v.H_abs().prefetch(k + SAMSIM_PF); fl_m.prefetch(k + SAMSIM_PF);
     }
     double T_kp1, Sbu_kp1, Sabs_kp1;
     if (k < Na) {
-      T_kp1 = c.T()[k + 1];
+      T_kp1 = v.T()[k + 1];
       Sbu_kp1 = S_bu_view[k + 1];
-      Sabs_kp1 = c.S_abs()[k + 1];
+      Sabs_kp1 = v.S_abs()[k + 1];
     } else {
       T_kp1 = T_bottom;
       Sbu_kp1 = S_bu_bottom;
       Sabs_kp1 = S_bu_bottom * 2000.0;
     }
     const double f1 = fl_m[k + 1];
-    double H = c.H_abs()[k], S = c.S_abs()[k];
-    mass_transfer_layer(g, f1, f0, T_km1, Sbu_km1, Sabs_km1, T_k, Sbu_k, T_kp1, Sbu_kp1, Sabs_kp1, H, S);
-    c.H_abs()[k] = H;
-    c.S_abs()[k] = S;
+    double H = v.H_abs()[k], S = v.S_abs()[k];
+    mass_transfer_layer(f1, f0, T_km1, Sbu_km1, Sabs_km1, T_k, Sbu_k, T_kp1, Sbu_kp1, Sabs_kp1, H, S);
+    v.H_abs()[k] = H;
+    v.S_abs()[k] = S;
     T_km1 = T_k; Sbu_km1 = Sbu_k; Sabs_km1 = S;
     T_k = T_kp1; Sbu_k = Sbu_kp1;
     f0 = f1;
@@ -571,8 +601,9 @@ __device__ __noinline__ void mass_transfer(const DevCfg& g, Col& c, const Lay& f
 
 // snow_coupling, mo_snow.f90:61-104.  The reference's getT calls alias T_in with T, which makes
 // the first guess H/c_l; passed explicitly here.
-__device__ __noinline__ void snow_coupling(const DevCfg& g, Col& c, double& H_abs1, double& phi1, double& T1, double m1,
+__device__ __noinline__ void snow_coupling(Col& c, double& H_abs1, double& phi1, double& T1, double m1,
                                            double S_bu1) {
+  const View v = c;
   double& H_abs_snow = SCV(c, SC_H_ABS_SNOW);
   double& phi_s = SCV(c, SC_PHI_S);
   double& T_snow = SCV(c, SC_T_SNOW);
@@ -581,22 +612,22 @@ __device__ __noinline__ void snow_coupling(const DevCfg& g, Col& c, double& H_ab
   H_abs_snow = -m_snow * latent_heat;
   double H = H_abs1 / m1;
   double hs = H_abs_snow / m_snow;
-  getT(g, hs, S_abs_snow / m_snow, hs / c_l, T_snow, phi_s, c.status, c.ev1);
-  getT(g, H, S_bu1, H / c_l, T1, phi1, c.status, c.ev1);
+  getT(hs, S_abs_snow / m_snow, hs / c_l, T_snow, phi_s, c.status, c.ev1);
+  getT(H, S_bu1, H / c_l, T1, phi1, c.status, c.ev1);
   if (T1 > 0 && H_abs1 <= -H_abs_snow) {
     EVT(c, EV_SNOW_COUPLING_WARM1);
     H_abs_snow = H_abs_snow + H_abs1;
     H_abs1 = 0.0;
     hs = H_abs_snow / m_snow;
-    getT(g, hs, S_abs_snow / m_snow, hs / c_l, T_snow, phi_s, c.status, c.ev1);
-    getT(g, H, S_bu1, H / c_l, T1, phi1, c.status, c.ev1);  // H is NOT refreshed here in the reference (:79-80)
+    getT(hs, S_abs_snow / m_snow, hs / c_l, T_snow, phi_s, c.status, c.ev1);
+    getT(H, S_bu1, H / c_l, T1, phi1, c.status, c.ev1);  // H is NOT refreshed here in the reference (:79-80)
   } else if (T1 > 0. && H_abs1 > -H_abs_snow) {
     EVT(c, EV_SNOW_COUPLING_WARM2);
     H_abs1 = (H_abs1 + H_abs_snow) * m1 / m_snow / (1.0 + m1 / m_snow);
     H_abs_snow = H_abs1 * m_snow / m1;
     hs = H_abs_snow / m_snow;
-    getT(g, hs, S_abs_snow / m_snow, hs / c_l, T_snow, phi_s, c.status, c.ev1);
-    getT(g, H, S_bu1, H / c_l, T1, phi1, c.status, c.ev1);
+    getT(hs, S_abs_snow / m_snow, hs / c_l, T_snow, phi_s, c.status, c.ev1);
+    getT(H, S_bu1, H / c_l, T1, phi1, c.status, c.ev1);
   } else {
     int jj = 0;
     while (fabs(T1 - T_snow) > SAMSIM_F32(0.1) && jj < 201) {
@@ -608,8 +639,8 @@ __device__ __noinline__ void snow_coupling(const DevCfg& g, Col& c, double& H_ab
       EVT(c, EV_SNOW_COUPLING_ITER);
       H = H_abs1 / m1;
       hs = H_abs_snow / m_snow;
-      getT(g, hs, S_abs_snow / m_snow, hs / c_l, T_snow, phi_s, c.status, c.ev1);
-      getT(g, H, S_bu1, H / c_l, T1, phi1, c.status, c.ev1);
+      getT(hs, S_abs_snow / m_snow, hs / c_l, T_snow, phi_s, c.status, c.ev1);
+      getT(H, S_bu1, H / c_l, T1, phi1, c.status, c.ev1);
       if (c.status) return;
     }
     if (jj > 200 && fabs(T1 - T_snow) > 1.0) c.status = 16;
@@ -619,6 +650,7 @@ __device__ __noinline__ void snow_coupling(const DevCfg& g, Col& c, double& H_ab
 // snow_precip, mo_snow.f90:123-150 (have_solid: precip_flag 0 passes solid_precip)
 __device__ __forceinline__ void snow_precip(Col& c, double dt, double liquid_in, double T2m, bool have_solid,
                                             double solid_in) {
+  const View v = c;
   double solid, liquid;
   if (have_solid) { solid = solid_in; liquid = liquid_in; }
   else if (T2m > 0.0) { solid = 0.0; liquid = liquid_in; }
@@ -647,8 +679,9 @@ __device__ __forceinline__ void snow_precip_0(double& H_abs, double& S_abs, doub
 
 // snow_thermo (mo_snow.f90:212-319) and snow_thermo_meltwater (:331-458) share everything up to
 // the saturated-layer block; `meltwater` selects the variant.
-__device__ __noinline__ void snow_thermo(const DevCfg& g, Col& c, bool meltwater, double& m1, double& thick1,
+__device__ __noinline__ void snow_thermo(Col& c, bool meltwater, double& m1, double& thick1,
                                          double& H_abs1, double& melt_thick_snow) {
+  const View v = c;
   double& psi_l_snow = SCV(c, SC_PSI_L_SNOW);
   double& psi_s_snow = SCV(c, SC_PSI_S_SNOW);
   double& psi_g_snow = SCV(c, SC_PSI_G_SNOW);
@@ -665,7 +698,7 @@ __device__ __noinline__ void snow_thermo(const DevCfg& g, Col& c, bool meltwater
   if (meltwater) EVT(c, EV_SNOW_THERMO_MELTWATER); else EVT(c, EV_SNOW_THERMO);
   {
     double T_in = T_snow;
-    getT(g, H_snow, S_bu_snow, T_in, T_snow, phi_snow, c.status, c.ev1);
+    getT(H_snow, S_bu_snow, T_in, T_snow, phi_snow, c.status, c.ev1);
   }
   psi_s_snow = m_snow * phi_snow / rho_s / thick_snow;
   psi_l_snow = m_snow * (1.0 - phi_snow) / rho_l / thick_snow;
@@ -714,8 +747,8 @@ __device__ __noinline__ void snow_thermo(const DevCfg& g, Col& c, bool meltwater
       H_abs_snow = H_abs_snow - sat_snow * (1.0 - psi_s_snow) * rho_l * c_l * T_snow;
       H_abs1 = H_abs1 + sat_snow * (1.0 - psi_s_snow) * rho_l * c_l * T_snow;
     } else {  // :399-430
-      const double slush = (psi_l_snow - max_lwc_v) * (1.0 - g.k_snow_flush);
-      const double flush = (psi_l_snow - max_lwc_v) * g.k_snow_flush;
+      const double slush = (psi_l_snow - max_lwc_v) * (1.0 - CFG.k_snow_flush);
+      const double flush = (psi_l_snow - max_lwc_v) * CFG.k_snow_flush;
       melt_thick_snow = thick_snow * flush;
       sat_snow = thick_snow * (slush);
       sat_snow = sat_snow / (1.0 - psi_s_snow - max_lwc_v - f_min(gas_snow_ice2, psi_g_snow));
@@ -744,18 +777,19 @@ __device__ __noinline__ void snow_thermo(const DevCfg& g, Col& c, bool meltwater
 }
 
 // the driver's snow block, mo_grotz.f90:273-292 and :601-621
-__device__ __forceinline__ void snow_block(const DevCfg& g, Col& c) {
+__device__ __forceinline__ void snow_block(Col& c) {
+  const View v = c;
   if (SCV(c, SC_THICK_SNOW) > 0.0) {
-    double m1 = c.m()[1], th1 = c.thick()[1], H1 = c.H_abs()[1];
-    if (g.snow_flush_flag == 0) {
+    double m1 = v.m()[1], th1 = v.thick()[1], H1 = v.H_abs()[1];
+    if (CFG.snow_flush_flag == 0) {
       double dummy = 0.0;
-      snow_thermo(g, c, false, m1, th1, H1, dummy);
+      snow_thermo(c, false, m1, th1, H1, dummy);
       SCV(c, SC_MELT_THICK_SNOW) = 0.0;
-    } else if (g.snow_flush_flag == 1) {
+    } else if (CFG.snow_flush_flag == 1) {
       SCV(c, SC_MELT_THICK_SNOW) = 0.0;
-      snow_thermo(g, c, true, m1, th1, H1, SCV(c, SC_MELT_THICK_SNOW));
+      snow_thermo(c, true, m1, th1, H1, SCV(c, SC_MELT_THICK_SNOW));
     }
-    c.m()[1] = m1; c.thick()[1] = th1; c.H_abs()[1] = H1;
+    v.m()[1] = m1; v.thick()[1] = th1; v.H_abs()[1] = H1;
   } else {
     SCV(c, SC_THICK_SNOW) = 0.0; SCV(c, SC_M_SNOW) = 0.0; SCV(c, SC_PSI_S_SNOW) = 0.0; SCV(c, SC_PSI_L_SNOW) = 0.0;
     SCV(c, SC_PSI_G_SNOW) = 0.0; SCV(c, SC_H_ABS_SNOW) = 0.0; SCV(c, SC_S_ABS_SNOW) = 0.0;
@@ -806,26 +840,27 @@ __device__ __forceinline__ double fl_Q_0_snow(double m_snow, double thick_snow, 
 // only for layers whose estimate is above ray_crit*(1 - 1e-10) -- a margin four orders wider than the deviation --
 // so decisions and fluxes are the reference's, bit for bit, and layers that cannot drain cost O(1).
 #define SAMSIM_GB 8
-__device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all) {
-  const int Na = c.N_active, N = g.Nlayer;
-  const double dt = g.dt;
-  Lay q = c.w1(), smin = c.w2(), fl_m = c.fl_m();
+__device__ __noinline__ void grav_drain(Col& c, bool exact_all) {
+  const View v = c;
+  const int Na = c.N_active, N = CFG.Nlayer;
+  const double dt = CFG.dt;
+  Lay q = v.w1(), smin = v.w2(), fl_m = v.fl_m();
   double heat_loss = 0.0;
 
   SAMSIM_LOOP
-  for (int k = Na; k <= N - 1; k++) c.ray()[k] = 0.0;  // :98 ray = 0 (entries below N_active are overwritten next)
-  const double bottom_h = c.thick()[Na] * c.psi_s()[Na] / psi_s_min;  // thick(N_active)*psi_s(N_active)/psi_s_min
-  const double S_br_Na = c.S_br()[Na];
+  for (int k = Na; k <= N - 1; k++) v.ray()[k] = 0.0;  // :98 ray = 0 (entries below N_active are overwritten next)
+  const double bottom_h = v.thick()[Na] * v.psi_s()[Na] / psi_s_min;  // thick(N_active)*psi_s(N_active)/psi_s_min
+  const double S_br_Na = v.S_br()[Na];
   // :104-106 permeability, thick/perm, and the order-independent suffix minimum of perm(k:Na-1), one backward pass
   double perm_Na = 0.0;
   {
     double mn = 0.0, sq = 0.0, st = 0.0, st_below = 0.0, qb_est = 0.0;  // suffix sums for the estimate
     SAMSIM_LOOP
     for (int k = Na; k >= 1; k--) {
-      if (k - SAMSIM_PF >= 1) { c.psi_l().prefetch(k - SAMSIM_PF); c.thick().prefetch(k - SAMSIM_PF); c.S_br().prefetch(k - SAMSIM_PF); }
-      const double pk = 1e-17 * det_pow(1000.0 * fabs(c.psi_l()[k]), 3.10);
+      if (k - SAMSIM_PF >= 1) { v.psi_l().prefetch(k - SAMSIM_PF); v.thick().prefetch(k - SAMSIM_PF); v.S_br().prefetch(k - SAMSIM_PF); }
+      const double pk = 1e-17 * det_pow(1000.0 * fabs(v.psi_l()[k]), 3.10);
       if (k == Na) { perm_Na = pk; qb_est = bottom_h / pk; continue; }  // perm itself is not needed again
-      const double thk = c.thick()[k];
+      const double thk = v.thick()[k];
       const double qk = thk / pk;
       q[k] = qk;
       mn = (k == Na - 1) ? pk : f_min(mn, pk);
@@ -836,17 +871,17 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
         sq = sq + qk;           // ~SUM(thick/perm (k:Na-1))
         st = st + thk;          // ~SUM(thick(k:Na-1))
         double est;
-        if (g.harmonic_flag == 1) {
-          est = grav * rho_l * bbeta * (c.S_br()[k] - S_br_Na) * (st_below + bottom_h) * f_min(mn, perm_Na);
+        if (CFG.harmonic_flag == 1) {
+          est = grav * rho_l * bbeta * (v.S_br()[k] - S_br_Na) * (st_below + bottom_h) * f_min(mn, perm_Na);
           smin[k] = mn;  // needed again by the exact evaluation of candidates
         } else {
           const double hp = (mn < 1e-14) ? 0.0 : (st + bottom_h) / (sq + qb_est);
-          est = grav * rho_l * bbeta * (c.S_br()[k] - S_br_Na) * (st_below + bottom_h) * hp;
+          est = grav * rho_l * bbeta * (v.S_br()[k] - S_br_Na) * (st_below + bottom_h) * hp;
         }
         est = est / (kappa_l * mu);
         // exactly 0 where the reference's value is exactly 0 (hp == 0); negative estimates clip like :135
         // (harmonic_flag 2: a candidate has est > 0, hence mn >= 1e-14: its exact evaluation needs no smin)
-        c.ray()[k] = (g.harmonic_flag == 2 && mn < 1e-14) ? 0.0 : f_max(est, 0.0);
+        v.ray()[k] = (CFG.harmonic_flag == 2 && mn < 1e-14) ? 0.0 : f_max(est, 0.0);
       }
     }
   }
@@ -862,7 +897,7 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
     for (int d = 0; d < SAMSIM_GB; d++) {  // triangular head: layer k0+d feeds accumulators 0..d
       const int kk = k0 + d;
       if (kk <= Na - 1) {
-        const double qv = q[kk], tv = c.thick()[kk];
+        const double qv = q[kk], tv = v.thick()[kk];
 #pragma unroll
         for (int j = 0; j < SAMSIM_GB; j++)
           if (j <= d) { aq[j] = aq[j] + qv; at[j] = at[j] + tv; }
@@ -870,8 +905,8 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
     }
     SAMSIM_LOOP
     for (int kk = k0 + SAMSIM_GB; kk <= Na - 1; kk++) {  // body: every accumulator takes every layer, in order
-      if (kk + SAMSIM_PF <= Na - 1) { q.prefetch(kk + SAMSIM_PF); c.thick().prefetch(kk + SAMSIM_PF); }
-      const double qv = q[kk], tv = c.thick()[kk];
+      if (kk + SAMSIM_PF <= Na - 1) { q.prefetch(kk + SAMSIM_PF); v.thick().prefetch(kk + SAMSIM_PF); }
+      const double qv = q[kk], tv = v.thick()[kk];
 #pragma unroll
       for (int j = 0; j < SAMSIM_GB; j++) { aq[j] = aq[j] + qv; at[j] = at[j] + tv; }
     }
@@ -882,9 +917,9 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
         // height = SUM(thick(k+1:Na-1)) + bottom_h, :128
         const double below = (j == SAMSIM_GB - 1) ? carry_t : ((k + 1 <= Na - 1) ? at[(j + 1) % SAMSIM_GB] : 0.0);
         const double height = below + bottom_h;
-        const double d_S_br = c.S_br()[k] - S_br_Na;
+        const double d_S_br = v.S_br()[k] - S_br_Na;
         double r;
-        if (g.harmonic_flag == 1) {
+        if (CFG.harmonic_flag == 1) {
           r = grav * rho_l * bbeta * d_S_br * height * f_min(smin[k], perm_Na);  // MINVAL(perm(k:N_active))
         } else {
           double hp;
@@ -897,7 +932,7 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
           r = grav * rho_l * bbeta * d_S_br * height * hp;
         }
         r = r / (kappa_l * mu);
-        c.ray()[k] = f_max(r, 0.0);
+        v.ray()[k] = f_max(r, 0.0);
       }
     }
     carry_t = at[0];
@@ -910,23 +945,23 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
   int kfirst = 0;        // first draining layer: fl_m(1:kfirst) == 0
 
   double run = 0.0;  // running sum = fl_up(kk) for every kk not yet clamped
-  double sbk = c.S_br()[1];
+  double sbk = v.S_br()[1];
   SAMSIM_LOOP
   for (int k = 1; k <= Na - 1; k++) {  // :144-171
     if (k + SAMSIM_PF <= Na) {
       // psi_s and m are only read for layers above ray_crit: prefetching them for every layer was 16 B of DRAM
       // traffic per layer and step for nothing
-      c.ray().prefetch(k + SAMSIM_PF); c.S_abs().prefetch(k + SAMSIM_PF); c.S_br().prefetch(k + SAMSIM_PF);
+      v.ray().prefetch(k + SAMSIM_PF); v.S_abs().prefetch(k + SAMSIM_PF); v.S_br().prefetch(k + SAMSIM_PF);
     }
-    double rk = c.ray()[k];
-    const double Sk = c.S_abs()[k];
-    const double sbk1 = c.S_br()[k + 1];
+    double rk = v.ray()[k];
+    const double Sk = v.S_abs()[k];
+    const double sbk1 = v.S_br()[k + 1];
     if (!exact_all && rk > ray_crit * (1.0 - 1e-10)) {
       // candidate: the reference's forward sums (:115-120, :128) for this layer only, then ray(k) as at :126-136
       double hq = 0.0, ht = 0.0, hb = 0.0;
       SAMSIM_LOOP
       for (int kk = k; kk <= Na - 1; kk++) {
-        const double tv = c.thick()[kk];
+        const double tv = v.thick()[kk];
         hq = hq + q[kk];
         ht = ht + tv;
         if (kk > k) hb = hb + tv;
@@ -934,7 +969,7 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
       const double height = hb + bottom_h;
       const double d_S_br = sbk - S_br_Na;
       double r;
-      if (g.harmonic_flag == 1) {
+      if (CFG.harmonic_flag == 1) {
         r = grav * rho_l * bbeta * d_S_br * height * f_min(smin[k], perm_Na);
       } else {
         double hp = hq + qb;  // the estimate was > 0, so minval(perm(k:Na-1)) >= 1e-14 (:112) holds
@@ -943,33 +978,33 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
       }
       r = r / (kappa_l * mu);
       rk = f_max(r, 0.0);
-      c.ray()[k] = rk;
+      v.ray()[k] = rk;
     }
     double up = run;
     double S_after = Sk;
     double fl_down_k = 0.0;
     sum_before = sum_before + Sk;
     // same && chain as :145, evaluated left to right: psi_s and m are only touched where ray exceeds ray_crit
-    if (rk > ray_crit && c.psi_s()[k] > 0.001 && Sk / c.m()[k] > 0.1 && sbk > sbk1) {
+    if (rk > ray_crit && v.psi_s()[k] > 0.001 && Sk / v.m()[k] > 0.1 && sbk > sbk1) {
       if (kfirst == 0) { kfirst = k; fl_m[k] = 0.0; EVT(c, EV_GRAV_DRAINED); }  // fl_m(kfirst) = fl_up(kfirst-1) = 0: first face read by mass_transfer
-      const double plk = c.psi_l()[k], thk = c.thick()[k], Tk = c.T()[k];
+      const double plk = v.psi_l()[k], thk = v.thick()[k], Tk = v.T()[k];
       double flux = x_grav * (rk - ray_crit) * dt * thk;
       flux = f_min(flux, plk * rho_l * thk);
       fl_down_k = flux;
       double Snew = Sk - flux * sbk;
-      c.S_abs()[k] = Snew;
+      v.S_abs()[k] = Snew;
       S_after = Snew;
       if (Snew < 0.0) { c.status = 21234; return; }
       SCV(c, SC_GRAV_TEMP) = SCV(c, SC_GRAV_TEMP) + flux * Tk;
-      c.H_abs()[k] = c.H_abs()[k] - flux * c_l * Tk;
+      v.H_abs()[k] = v.H_abs()[k] - flux * c_l * Tk;
       heat_loss = heat_loss + flux * c_l * Tk;
       run = run + flux;
       up = f_min(run, plk * rho_l * thk);
     }
-    if (g.n_bgc) {  // :178-183 (sic: column N_active+1 is assigned from column N_active), fl_down(k) = this layer's flux
-      const double cellNa = (k == Na - 1) ? c.A(AR_FB_D)[k] : c.A(AR_FB_A)[k];
-      c.A(AR_FB_O)[k] = cellNa + fl_down_k;
-      c.A(AR_FB_U)[k] = c.A(AR_FB_U)[k] + up;
+    if (CFG.n_bgc) {  // :178-183 (sic: column N_active+1 is assigned from column N_active), fl_down(k) = this layer's flux
+      const double cellNa = (k == Na - 1) ? v.A(AR_FB_D)[k] : v.A(AR_FB_A)[k];
+      v.A(AR_FB_O)[k] = cellNa + fl_down_k;
+      v.A(AR_FB_U)[k] = v.A(AR_FB_U)[k] + up;
     }
     if (kfirst) fl_m[k + 1] = up;            // fl_m(2:N_active+1) = fl_up(1:N_active), :177 (zeros above kfirst are not stored)
     else min_S = f_min(min_S, Sk);           // layers above the first draining layer keep this value
@@ -977,10 +1012,10 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
     sbk = sbk1;
   }
   if (kfirst) fl_m[Na + 1] = run;
-  if (g.n_bgc) c.A(AR_FB_U)[Na] = c.A(AR_FB_U)[Na] + run;  // fl_up(N_active)
+  if (CFG.n_bgc) v.A(AR_FB_U)[Na] = v.A(AR_FB_U)[Na] + run;  // fl_up(N_active)
   const double fl_up_Na = run;
   {
-    const double S_Na = c.S_abs()[Na];  // layer N_active never drains; inactive layers hold 0
+    const double S_Na = v.S_abs()[Na];  // layer N_active never drains; inactive layers hold 0
     sum_before = sum_before + S_Na;
     sum_after = sum_after + S_Na;
   }
@@ -988,28 +1023,29 @@ __device__ __noinline__ void grav_drain(const DevCfg& g, Col& c, bool exact_all)
   SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) - sum_after;   // :173
 
   // :188 -- nothing moves above the first draining layer (fl_m(1:kfirst) == 0); without any drainage nothing moves
-  if (kfirst) mass_transfer(g, c, fl_m, c.S_bu(), kfirst);
+  if (kfirst) mass_transfer(c, fl_m, v.S_bu(), kfirst);
 
   SCV(c, SC_GRAV_DRAIN) = SCV(c, SC_GRAV_DRAIN) + run;  // :190 fl_m(N_active+1)
-  if (g.grav_heat_flag == 2) c.H_abs()[Na] = c.H_abs()[Na] + heat_loss - fl_up_Na * c_l * SCV(c, SC_T_BOTTOM);  // :193-195
+  if (CFG.grav_heat_flag == 2) v.H_abs()[Na] = v.H_abs()[Na] + heat_loss - fl_up_Na * c_l * SCV(c, SC_T_BOTTOM);  // :193-195
   // :198 MINVAL(S_abs) < 0: layers above kfirst kept the values scanned by the drain loop (min_S); the others
   // were rewritten by mass_transfer and are scanned here
   double mn = min_S;
-  if (kfirst) for (int k = kfirst; k <= Na; k++) mn = f_min(mn, c.S_abs()[k]);
-  else mn = f_min(mn, c.S_abs()[Na]);
+  if (kfirst) for (int k = kfirst; k <= Na; k++) mn = f_min(mn, v.S_abs()[k]);
+  else mn = f_min(mn, v.S_abs()[Na]);
   if (f_min(mn, 0.0) < 0.0) c.status = 1337;  // (inactive layers are 0)
 }
 
 // fl_grav_drain_simple, mo_grav_drain.f90:218-279 (grav_flag 3)
-__device__ __noinline__ void grav_drain_simple(const DevCfg& g, Col& c) {
-  const int Na = c.N_active, N = g.Nlayer;
-  Lay perm = c.w0(), hperm = c.w2();
+__device__ __noinline__ void grav_drain_simple(Col& c) {
+  const View v = c;
+  const int Na = c.N_active, N = CFG.Nlayer;
+  Lay perm = v.w0(), hperm = v.w2();
   SAMSIM_LOOP
-  for (int k = 1; k <= N - 1; k++) c.ray()[k] = 0.0;
+  for (int k = 1; k <= N - 1; k++) v.ray()[k] = 0.0;
   SAMSIM_LOOP
-  for (int k = 1; k <= Na; k++) perm[k] = 1e-17 * det_pow(1000.0 * fabs(c.psi_l()[k]), 3.10);
-  const double bottom_h = c.thick()[Na] * c.psi_s()[Na] / psi_s_min;
-  if (g.harmonic_flag == 2) {
+  for (int k = 1; k <= Na; k++) perm[k] = 1e-17 * det_pow(1000.0 * fabs(v.psi_l()[k]), 3.10);
+  const double bottom_h = v.thick()[Na] * v.psi_s()[Na] / psi_s_min;
+  if (CFG.harmonic_flag == 2) {
     SAMSIM_LOOP
     for (int k = 1; k <= Na - 1; k++) {
       double mn = perm[k];
@@ -1020,19 +1056,19 @@ __device__ __noinline__ void grav_drain_simple(const DevCfg& g, Col& c) {
       } else {
         double h = 0.0;
         SAMSIM_LOOP
-        for (int kk = k; kk <= Na - 1; kk++) h = h + c.thick()[kk] / perm[kk];
+        for (int kk = k; kk <= Na - 1; kk++) h = h + v.thick()[kk] / perm[kk];
         h = h + bottom_h / perm[Na];
-        hperm[k] = (sum_fwd(c.thick(), k, Na - 1) + bottom_h) / h;
+        hperm[k] = (sum_fwd(v.thick(), k, Na - 1) + bottom_h) / h;
       }
     }
   }
-  const double S_br_Na = c.S_br()[Na];
+  const double S_br_Na = v.S_br()[Na];
   SAMSIM_LOOP
   for (int k = 1; k <= Na - 1; k++) {
-    double d_S_br = c.S_br()[k] - S_br_Na;
-    double height = sum_fwd(c.thick(), k + 1, Na - 1) + bottom_h;
+    double d_S_br = v.S_br()[k] - S_br_Na;
+    double height = sum_fwd(v.thick(), k + 1, Na - 1) + bottom_h;
     double r;
-    if (g.harmonic_flag == 1) {
+    if (CFG.harmonic_flag == 1) {
       double mn = perm[k];
       SAMSIM_LOOP
       for (int kk = k; kk <= Na; kk++) mn = f_min(mn, perm[kk]);
@@ -1041,11 +1077,11 @@ __device__ __noinline__ void grav_drain_simple(const DevCfg& g, Col& c) {
       r = grav * rho_l * bbeta * d_S_br * height * hperm[k];
     }
     r = r / (kappa_l * mu);
-    c.ray()[k] = f_max(r, 0.0);
+    v.ray()[k] = f_max(r, 0.0);
   }
   SAMSIM_LOOP
   for (int k = Na - 1; k >= 1; k--)
-    if (c.ray()[k] > ray_crit) c.S_abs()[k] = c.S_abs()[k] * SAMSIM_F32(0.99);
+    if (v.ray()[k] > ray_crit) v.S_abs()[k] = v.S_abs()[k] * SAMSIM_F32(0.99);
   SCV(c, SC_GRAV_DRAIN) = 0.0;
 }
 
@@ -1054,28 +1090,29 @@ __device__ __noinline__ void grav_drain_simple(const DevCfg& g, Col& c) {
 // ==========================================================================================
 
 // flood, mo_flood.f90:55-153
-__device__ __noinline__ void flood(const DevCfg& g, Col& c) {
+__device__ __noinline__ void flood(Col& c) {
+  const View v = c;
   const int Na = c.N_active;
-  const double dt = g.dt, freeboard = SCV(c, SC_FREEBOARD), psi_g_snow = SCV(c, SC_PSI_G_SNOW);
+  const double dt = CFG.dt, freeboard = SCV(c, SC_FREEBOARD), psi_g_snow = SCV(c, SC_PSI_G_SNOW);
   double& thick_snow = SCV(c, SC_THICK_SNOW);
   double& H_abs_snow = SCV(c, SC_H_ABS_SNOW);
   double& m_snow = SCV(c, SC_M_SNOW);
   double hp = 0.0;
   EVT(c, EV_FLOOD);
   SAMSIM_LOOP
-  for (int k = 1; k <= Na - 1; k++) hp = hp + c.thick()[k] / (1e-17 * det_pow(1000.0 * c.psi_l()[k], 3.10));  // :73-79
-  const double bottom_h = c.thick()[Na] * c.psi_s()[Na] / psi_s_min;
-  hp = hp + bottom_h / (1e-17 * det_pow(1000.0 * c.psi_l()[Na], 3.10));
-  hp = (sum_fwd(c.thick(), 1, Na - 1) + bottom_h) / hp;
+  for (int k = 1; k <= Na - 1; k++) hp = hp + v.thick()[k] / (1e-17 * det_pow(1000.0 * v.psi_l()[k], 3.10));  // :73-79
+  const double bottom_h = v.thick()[Na] * v.psi_s()[Na] / psi_s_min;
+  hp = hp + bottom_h / (1e-17 * det_pow(1000.0 * v.psi_l()[Na], 3.10));
+  hp = (sum_fwd(v.thick(), 1, Na - 1) + bottom_h) / hp;
 
-  double flood_brine = -dt * grav * rho_l * rho_l * hp * (freeboard) / (mu * sum_fwd(c.thick(), 1, Na));  // :85
+  double flood_brine = -dt * grav * rho_l * rho_l * hp * (freeboard) / (mu * sum_fwd(v.thick(), 1, Na));  // :85
   const double shift_ice = flood_brine / (rho_l * psi_g_snow / ratio_flood);
   const double shift_snow = shift_ice * (1 + psi_g_snow / (1.0 - psi_g_snow) * (1.0 - 1.0 / ratio_flood));
 
-  const double S_bu_Na = c.S_abs()[Na] / c.m()[Na];  // S_bu(k) = S_abs(k)/m(k) before any change, :93-95
-  double S1 = c.S_abs()[1], H1 = c.H_abs()[1], m1 = c.m()[1], th1 = c.thick()[1];
+  const double S_bu_Na = v.S_abs()[Na] / v.m()[Na];  // S_bu(k) = S_abs(k)/m(k) before any change, :93-95
+  double S1 = v.S_abs()[1], H1 = v.H_abs()[1], m1 = v.m()[1], th1 = v.thick()[1];
   S1 = S1 + flood_brine * S_bu_Na;                  // :102-104
-  H1 = H1 + flood_brine * c.H_abs()[Na] / c.m()[Na];
+  H1 = H1 + flood_brine * v.H_abs()[Na] / v.m()[Na];
   m1 = m1 + flood_brine;
   th1 = th1 + shift_ice;                            // :107-112
   H1 = H1 + shift_snow / thick_snow * H_abs_snow;
@@ -1083,15 +1120,15 @@ __device__ __noinline__ void flood(const DevCfg& g, Col& c) {
   m1 = m1 + shift_snow / thick_snow * m_snow;
   m_snow = m_snow - shift_snow / thick_snow * m_snow;
   thick_snow = thick_snow - shift_snow;
-  c.S_abs()[1] = S1; c.H_abs()[1] = H1; c.m()[1] = m1; c.thick()[1] = th1;  // Na > 1 here, layer 1 != layer Na
+  v.S_abs()[1] = S1; v.H_abs()[1] = H1; v.m()[1] = m1; v.thick()[1] = th1;  // Na > 1 here, layer 1 != layer Na
 
   if (freeboard + shift_ice < neg_free) {  // :117-138
     EVT(c, EV_FLOOD_NEG_FREE);
     const double shift = neg_free - (freeboard + shift_ice);
     flood_brine = shift * (psi_g_snow)*rho_l;
-    const double T_Na = c.T()[Na];
-    c.S_abs()[Na] = c.S_abs()[Na] + (SCV(c, SC_S_BU_BOTTOM) - S_bu_Na) * flood_brine;
-    c.H_abs()[Na] = c.H_abs()[Na] + (SCV(c, SC_T_BOTTOM) - T_Na) * c_l * flood_brine;
+    const double T_Na = v.T()[Na];
+    v.S_abs()[Na] = v.S_abs()[Na] + (SCV(c, SC_S_BU_BOTTOM) - S_bu_Na) * flood_brine;
+    v.H_abs()[Na] = v.H_abs()[Na] + (SCV(c, SC_T_BOTTOM) - T_Na) * c_l * flood_brine;
     S1 = S1 + S_bu_Na * flood_brine;
     H1 = H1 + T_Na * c_l * flood_brine;
     m1 = m1 + flood_brine;
@@ -1101,10 +1138,10 @@ __device__ __noinline__ void flood(const DevCfg& g, Col& c) {
     m1 = m1 + shift / thick_snow * m_snow;
     m_snow = m_snow - shift / thick_snow * m_snow;
     thick_snow = thick_snow - shift;
-    c.S_abs()[1] = S1; c.H_abs()[1] = H1; c.m()[1] = m1; c.thick()[1] = th1;
+    v.S_abs()[1] = S1; v.H_abs()[1] = H1; v.m()[1] = m1; v.thick()[1] = th1;
   }
-  if (g.n_bgc) {  // :140-144 fl_brine_bgc(N_active,1) and (N_active+1,N_active) += flood_brine
-    Lay U = c.A(AR_FB_U);
+  if (CFG.n_bgc) {  // :140-144 fl_brine_bgc(N_active,1) and (N_active+1,N_active) += flood_brine
+    Lay U = v.A(AR_FB_U);
     if (Na >= 3) c.fb_x = c.fb_x + flood_brine; else U[1] = U[1] + flood_brine;
     U[Na] = U[Na] + flood_brine;
   }
@@ -1112,14 +1149,15 @@ __device__ __noinline__ void flood(const DevCfg& g, Col& c) {
 
 // flood_simple, mo_flood.f90:167-210
 __device__ __forceinline__ void flood_simple(Col& c) {
+  const View v = c;
   double& thick_snow = SCV(c, SC_THICK_SNOW);
   double& H_abs_snow = SCV(c, SC_H_ABS_SNOW);
   double& m_snow = SCV(c, SC_M_SNOW);
   const double shift = SCV(c, SC_FREEBOARD) - neg_free;
   const double flood_brine = -shift * SCV(c, SC_PSI_G_SNOW) * rho_l;
   EVT(c, EV_FLOOD_SIMPLE);
-  double S1 = c.S_abs()[1], H1 = c.H_abs()[1], m1 = c.m()[1];
-  c.thick()[1] = c.thick()[1] - shift;
+  double S1 = v.S_abs()[1], H1 = v.H_abs()[1], m1 = v.m()[1];
+  v.thick()[1] = v.thick()[1] - shift;
   S1 = S1 + SCV(c, SC_S_BU_BOTTOM) * flood_brine;
   H1 = H1 - shift / thick_snow * H_abs_snow;
   H1 = H1 + SCV(c, SC_T_BOTTOM) * c_l * flood_brine;
@@ -1128,7 +1166,7 @@ __device__ __forceinline__ void flood_simple(Col& c) {
   H_abs_snow = H_abs_snow + shift / thick_snow * H_abs_snow;
   m_snow = m_snow + shift / thick_snow * m_snow;
   thick_snow = thick_snow + shift;
-  c.S_abs()[1] = S1; c.H_abs()[1] = H1; c.m()[1] = m1;
+  v.S_abs()[1] = S1; v.H_abs()[1] = H1; v.m()[1] = m1;
 }
 
 // ==========================================================================================
@@ -1136,39 +1174,40 @@ __device__ __forceinline__ void flood_simple(Col& c) {
 // ==========================================================================================
 
 // flush3, mo_flush.f90:70-237.  Scratch: w0 R_v, w1 R_h, w2 R, w3 S_bu(local), fl_m.
-__device__ __noinline__ void flush3(const DevCfg& g, Col& c) {
-  const int Na = c.N_active, N = g.Nlayer;
-  const double dt = g.dt, freeboard = SCV(c, SC_FREEBOARD);
-  Lay R_v = c.w0(), R_h = c.w1(), R = c.w2(), S_bu = c.w3(), fl_m = c.fl_m();
+__device__ __noinline__ void flush3(Col& c) {
+  const View v = c;
+  const int Na = c.N_active, N = CFG.Nlayer;
+  const double dt = CFG.dt, freeboard = SCV(c, SC_FREEBOARD);
+  Lay R_v = v.w0(), R_h = v.w1(), R = v.w2(), S_bu = v.w3(), fl_m = v.fl_m();
   double& melt_thick = SCV(c, SC_MELT_THICK);
   EVT(c, EV_FLUSH3);
 
   SAMSIM_LOOP
-  for (int k = 1; k <= Na; k++) { c.flush_v()[k] = 0.0; c.flush_h()[k] = 0.0; }   // :101-102 (dummies are DIMENSION(N_active))
+  for (int k = 1; k <= Na; k++) { v.flush_v()[k] = 0.0; v.flush_h()[k] = 0.0; }   // :101-102 (dummies are DIMENSION(N_active))
   SAMSIM_LOOP
-  for (int k = 1; k <= Na; k++) S_bu[k] = c.S_abs()[k] / c.m()[k];              // :103
-  const double konst = sum_fwd(c.thick(), 1, Na) * para_flush_horiz;          // :106
-  melt_thick = f_min(melt_thick, c.psi_l()[1] * c.thick()[1]);                  // :110
-  melt_thick = f_min(melt_thick, g.thick_0 / 3.0);                          // :112
+  for (int k = 1; k <= Na; k++) S_bu[k] = v.S_abs()[k] / v.m()[k];              // :103
+  const double konst = sum_fwd(v.thick(), 1, Na) * para_flush_horiz;          // :106
+  melt_thick = f_min(melt_thick, v.psi_l()[1] * v.thick()[1]);                  // :110
+  melt_thick = f_min(melt_thick, CFG.thick_0 / 3.0);                          // :112
 
-  if (g.snow_flush_flag == 1) {  // :114-125
+  if (CFG.snow_flush_flag == 1) {  // :114-125
     SAMSIM_LOOP
-    for (int k = Na + 1; k <= N; k++) c.perm()[k] = 0.0;
+    for (int k = Na + 1; k <= N; k++) v.perm()[k] = 0.0;
     SAMSIM_LOOP
     for (int k = 1; k <= Na; k++) {
-      double p = 1e-17 * det_pow(1000.0 * fabs(c.psi_l()[k] + 2. * c.psi_g()[k]), 3.10);
+      double p = 1e-17 * det_pow(1000.0 * fabs(v.psi_l()[k] + 2. * v.psi_g()[k]), 3.10);
       if (p == 0.0) p = 1.0;
-      c.perm()[k] = p;
+      v.perm()[k] = p;
     }
-  } else if (g.snow_flush_flag == 0) {  // :126-130
+  } else if (CFG.snow_flush_flag == 0) {  // :126-130
     SAMSIM_LOOP
-    for (int k = Na + 1; k <= N; k++) c.perm()[k] = 1.0;
+    for (int k = Na + 1; k <= N; k++) v.perm()[k] = 1.0;
     SAMSIM_LOOP
-    for (int k = 1; k <= Na; k++) c.perm()[k] = 1e-17 * det_pow(1000.0 * fabs(c.psi_l()[k]), 3.10);
+    for (int k = 1; k <= Na; k++) v.perm()[k] = 1e-17 * det_pow(1000.0 * fabs(v.psi_l()[k]), 3.10);
   }
   SAMSIM_LOOP
   for (int k = 1; k <= Na; k++) {  // :133-137
-    const double pk = f_max(c.perm()[k], 0.00000000000000000000001), thk = c.thick()[k];
+    const double pk = f_max(v.perm()[k], 0.00000000000000000000001), thk = v.thick()[k];
     R_v[k] = mu * thk / pk;
     R_h[k] = mu * konst / (thk * pk);
   }
@@ -1179,104 +1218,105 @@ __device__ __noinline__ void flush3(const DevCfg& g, Col& c) {
     double r = R[k + 1] + R_v[k];
     R[k] = ((r)*R_h[k]) / (r + R_h[k]);
   }
-  const double T1 = c.T()[1];
-  double flush_total = (freeboard + melt_thick) / R[1] * grav * dt * density_of(T1, S_br_of(g, T1)) * rho_l;  // :152
+  const double T1 = v.T()[1];
+  double flush_total = (freeboard + melt_thick) / R[1] * grav * dt * density_of(T1, S_br_of(T1)) * rho_l;  // :152
   flush_total = f_min(flush_total, melt_thick * rho_l);
   SCV(c, SC_MELT_ERR) = SCV(c, SC_MELT_ERR) + melt_thick - f_min(flush_total / rho_l, melt_thick);  // :156
 
   {
     const double den = R[2] + R_v[1] + R_h[1];
-    c.flush_h()[1] = flush_total * (R[2] + R_v[1]) / den;  // :159-160
-    c.flush_v()[1] = flush_total * R_h[1] / den;
+    v.flush_h()[1] = flush_total * (R[2] + R_v[1]) / den;  // :159-160
+    v.flush_v()[1] = flush_total * R_h[1] / den;
   }
   SAMSIM_LOOP
   for (int k = 2; k <= Na - 1; k++) {  // :161-164
-    const double fv = c.flush_v()[k - 1], a = R[k + 1] + R_v[k], den = a + R_h[k];
-    c.flush_h()[k] = fv * a / den;
-    c.flush_v()[k] = fv * R_h[k] / den;
+    const double fv = v.flush_v()[k - 1], a = R[k + 1] + R_v[k], den = a + R_h[k];
+    v.flush_h()[k] = fv * a / den;
+    v.flush_v()[k] = fv * R_h[k] / den;
   }
-  c.flush_v()[Na] = c.flush_v()[Na - 1];
-  c.flush_h()[Na] = 0.0;
+  v.flush_v()[Na] = v.flush_v()[Na - 1];
+  v.flush_h()[Na] = 0.0;
 
-  if (g.n_bgc) {  // :168-175
-    Lay D = c.A(AR_FB_D), Ac = c.A(AR_FB_A);
+  if (CFG.n_bgc) {  // :168-175
+    Lay D = v.A(AR_FB_D), Ac = v.A(AR_FB_A);
     double sum_h = 0.0;
     SAMSIM_LOOP
     for (int k = 1; k <= Na - 1; k++) {
-      const double fh = c.flush_h()[k];
+      const double fh = v.flush_h()[k];
       if (k == Na - 1) D[k] = D[k] + fh; else Ac[k] = Ac[k] + fh;  // cell (N_active-1, N_active) is the down-cell
       sum_h = sum_h + fh;
     }
-    sum_h = sum_h + c.flush_h()[Na];
+    sum_h = sum_h + v.flush_h()[Na];
     D[Na] = D[Na] + sum_h;
     SAMSIM_LOOP
-    for (int k = 1; k <= Na; k++) D[k] = D[k] + c.flush_v()[k];
+    for (int k = 1; k <= Na; k++) D[k] = D[k] + v.flush_v()[k];
   }
 
   fl_m[1] = 0.0;  // :179-180
   SAMSIM_LOOP
-  for (int k = 1; k <= Na; k++) fl_m[k + 1] = -c.flush_v()[k];
+  for (int k = 1; k <= Na; k++) fl_m[k + 1] = -v.flush_v()[k];
 
-  mass_transfer(g, c, fl_m, S_bu);  // with the LOCAL S_bu (:182)
-  const double T_Na = c.T()[Na];
-  if (g.flush_heat_flag == 2) c.H_abs()[Na] = c.H_abs()[Na] - fl_m[Na + 1] * T_Na * c_l;  // :185-187
+  mass_transfer(c, fl_m, S_bu);  // with the LOCAL S_bu (:182)
+  const double T_Na = v.T()[Na];
+  if (CFG.flush_heat_flag == 2) v.H_abs()[Na] = v.H_abs()[Na] - fl_m[Na + 1] * T_Na * c_l;  // :185-187
 
-  c.m()[1] = c.m()[1] - flush_total;  // :190-191
-  c.thick()[1] = c.thick()[1] - flush_total / rho_l;
+  v.m()[1] = v.m()[1] - flush_total;  // :190-191
+  v.thick()[1] = v.thick()[1] - flush_total / rho_l;
 
   double sfh = 0.0;
-  double H_Na = c.H_abs()[Na], S_Na = c.S_abs()[Na];
+  double H_Na = v.H_abs()[Na], S_Na = v.S_abs()[Na];
   SAMSIM_LOOP
   for (int k = 1; k <= Na - 1; k++) {  // :196-206
-    const double fh = c.flush_h()[k], Tk = c.T()[k];
-    const double loss_S = fh * S_br_of(g, Tk, c.S_abs()[k] / c.m()[k]);
+    const double fh = v.flush_h()[k], Tk = v.T()[k];
+    const double loss_S = fh * S_br_of(Tk, v.S_abs()[k] / v.m()[k]);
     const double loss_H = fh * Tk * c_l;
-    c.S_abs()[k] = c.S_abs()[k] - loss_S;
-    c.H_abs()[k] = c.H_abs()[k] - loss_H;
+    v.S_abs()[k] = v.S_abs()[k] - loss_S;
+    v.H_abs()[k] = v.H_abs()[k] - loss_H;
     H_Na = H_Na + loss_H;
     S_Na = S_Na + loss_S;
     sfh = sfh + fh;
   }
-  sfh = sfh + c.flush_h()[Na];  // SUM(flush_h) over the N_active-long dummy
+  sfh = sfh + v.flush_h()[Na];  // SUM(flush_h) over the N_active-long dummy
   const double loss_S = sfh * S_bu[Na];  // :207-208
   const double loss_H = sfh * T_Na * c_l;
-  if (g.flush_heat_flag == 2) H_Na = H_Na - loss_H;
+  if (CFG.flush_heat_flag == 2) H_Na = H_Na - loss_H;
   S_Na = S_Na - loss_S;
-  c.H_abs()[Na] = H_Na;
-  c.S_abs()[Na] = S_Na;
+  v.H_abs()[Na] = H_Na;
+  v.S_abs()[Na] = S_Na;
 
-  double mn = c.S_abs()[1];
+  double mn = v.S_abs()[1];
   SAMSIM_LOOP
-  for (int k = 2; k <= Na; k++) mn = f_min(mn, c.S_abs()[k]);
+  for (int k = 2; k <= Na; k++) mn = f_min(mn, v.S_abs()[k]);
   mn = f_min(mn, 0.0);  // MINVAL over all Nlayer: inactive layers hold 0 (only matters when Na < N)
   if (mn < -0.00000000000000000000000001) {
     EVT(c, EV_FLUSH3_CLAMP);
     SAMSIM_LOOP
-    for (int k = 1; k <= Na; k++) c.S_abs()[k] = f_max(c.S_abs()[k], 0.0);
+    for (int k = 1; k <= Na; k++) v.S_abs()[k] = f_max(v.S_abs()[k], 0.0);
   }
-  if (fabs(c.m()[1]) < 0.000001) c.status = 9876;  // :230-233
+  if (fabs(v.m()[1]) < 0.000001) c.status = 9876;  // :230-233
 }
 
 // flush4, mo_flush.f90:253-296 (flush_flag 6)
-__device__ __noinline__ void flush4(const DevCfg& g, Col& c) {
-  const int N = g.Nlayer, Na = c.N_active;
+__device__ __noinline__ void flush4(Col& c) {
+  const View v = c;
+  const int N = CFG.Nlayer, Na = c.N_active;
   double& melt_thick = SCV(c, SC_MELT_THICK);
-  const double S_bu1 = c.S_abs()[1] / c.m()[1], T1 = c.T()[1];
+  const double S_bu1 = v.S_abs()[1] / v.m()[1], T1 = v.T()[1];
   EVT(c, EV_FLUSH4);
-  c.H_abs()[1] = c.H_abs()[1] - melt_thick * rho_l * c_l * T1;
-  c.S_abs()[1] = c.S_abs()[1] - melt_thick * rho_l * S_br_of(g, T1, S_bu1);
-  c.thick()[1] = c.thick()[1] - melt_thick;
-  c.m()[1] = c.m()[1] - melt_thick * rho_l;
+  v.H_abs()[1] = v.H_abs()[1] - melt_thick * rho_l * c_l * T1;
+  v.S_abs()[1] = v.S_abs()[1] - melt_thick * rho_l * S_br_of(T1, S_bu1);
+  v.thick()[1] = v.thick()[1] - melt_thick;
+  v.m()[1] = v.m()[1] - melt_thick * rho_l;
   melt_thick = 0.0;
   int k = 2;
-  while (k <= N && c.psi_l()[k] > c.psi_l()[k - 1]) {
-    c.S_abs()[k] = para_flush_gamma * c.S_abs()[k];
+  while (k <= N && v.psi_l()[k] > v.psi_l()[k - 1]) {
+    v.S_abs()[k] = para_flush_gamma * v.S_abs()[k];
     k = k + 1;
   }
-  c.S_abs()[1] = f_max(c.S_abs()[1], 0.00);
-  double mn = c.S_abs()[1];
+  v.S_abs()[1] = f_max(v.S_abs()[1], 0.00);
+  double mn = v.S_abs()[1];
   SAMSIM_LOOP
-  for (int q = 2; q <= Na; q++) mn = f_min(mn, c.S_abs()[q]);
+  for (int q = 2; q <= Na; q++) mn = f_min(mn, v.S_abs()[q]);
   if (mn < 0.0) c.status = 9876;
 }
 
@@ -1284,198 +1324,205 @@ __device__ __noinline__ void flush4(const DevCfg& g, Col& c) {
 // mo_layer_dynamics.f90.  Snapshots rho/S_bu/H of the reference become w0/w1/w2.
 // ==========================================================================================
 __device__ __forceinline__ void snapshot_layers(Col& c, int k0, int k1) {
+  const View v = c;
   SAMSIM_LOOP
   for (int k = k0; k <= k1; k++) {
-    const double mk = c.m()[k];
-    c.w0()[k] = mk / c.thick()[k];   // rho
-    c.w1()[k] = c.S_abs()[k] / mk;   // S_bu
-    c.w2()[k] = c.H_abs()[k] / mk;   // H
+    const double mk = v.m()[k];
+    v.w0()[k] = mk / v.thick()[k];   // rho
+    v.w1()[k] = v.S_abs()[k] / mk;   // S_bu
+    v.w2()[k] = v.H_abs()[k] / mk;   // H
   }
 }
 
 // top_melt, mo_layer_dynamics.f90:191-326
-__device__ __noinline__ void top_melt(const DevCfg& g, Col& c) {
-  const int N = g.Nlayer, N_middle = g.N_middle, N_top = g.N_top;
-  const double thick_0 = g.thick_0;
-  Lay rho = c.w0(), S_bu = c.w1(), H = c.w2();
+__device__ __noinline__ void top_melt(Col& c) {
+  const View v = c;
+  const int N = CFG.Nlayer, N_middle = CFG.N_middle, N_top = CFG.N_top;
+  const double thick_0 = CFG.thick_0;
+  Lay rho = v.w0(), S_bu = v.w1(), H = v.w2();
   snapshot_layers(c, 1, c.N_active);  // :218-223
-  c.m()[1] = c.m()[1] + c.m()[2];           // :231-235
-  c.S_abs()[1] = c.S_abs()[1] + c.S_abs()[2];
-  c.H_abs()[1] = c.H_abs()[1] + c.H_abs()[2];
-  c.thick()[1] = c.thick()[1] + c.thick()[2];
+  v.m()[1] = v.m()[1] + v.m()[2];           // :231-235
+  v.S_abs()[1] = v.S_abs()[1] + v.S_abs()[2];
+  v.H_abs()[1] = v.H_abs()[1] + v.H_abs()[2];
+  v.thick()[1] = v.thick()[1] + v.thick()[2];
   const int kmax = (N_top - 1 < c.N_active - 1) ? N_top - 1 : c.N_active - 1;
   SAMSIM_LOOP
   for (int k = 2; k <= kmax; k++) {  // :238-243
-    c.m()[k] = rho[k + 1] * thick_0;
-    c.S_abs()[k] = S_bu[k + 1] * rho[k + 1] * thick_0;
-    c.H_abs()[k] = H[k + 1] * rho[k + 1] * thick_0;
+    v.m()[k] = rho[k + 1] * thick_0;
+    v.S_abs()[k] = S_bu[k + 1] * rho[k + 1] * thick_0;
+    v.H_abs()[k] = H[k + 1] * rho[k + 1] * thick_0;
   }
   if (c.N_active <= N_top) {  // :247-254
     EVT(c, EV_TOP_MELT_A);
     const int Na = c.N_active;
-    c.m()[Na] = 0.0; c.S_abs()[Na] = 0.0; c.H_abs()[Na] = 0.0; c.thick()[Na] = 0.0;
+    v.m()[Na] = 0.0; v.S_abs()[Na] = 0.0; v.H_abs()[Na] = 0.0; v.thick()[Na] = 0.0;
     c.N_active = Na - 1;
-  } else if (c.N_active > N_top && c.N_active <= N && c.thick()[N_top + 1] / thick_0 < 1.00001) {  // :256-273
+  } else if (c.N_active > N_top && c.N_active <= N && v.thick()[N_top + 1] / thick_0 < 1.00001) {  // :256-273
     EVT(c, EV_TOP_MELT_B);
     const int Na = c.N_active;
     SAMSIM_LOOP
     for (int k = N_top; k <= Na - 1; k++) {
-      c.m()[k] = rho[k + 1] * thick_0;
-      c.S_abs()[k] = S_bu[k + 1] * rho[k + 1] * thick_0;
-      c.H_abs()[k] = H[k + 1] * rho[k + 1] * thick_0;
+      v.m()[k] = rho[k + 1] * thick_0;
+      v.S_abs()[k] = S_bu[k + 1] * rho[k + 1] * thick_0;
+      v.H_abs()[k] = H[k + 1] * rho[k + 1] * thick_0;
     }
-    c.m()[Na] = 0.0; c.S_abs()[Na] = 0.0; c.H_abs()[Na] = 0.0; c.thick()[Na] = 0.0;
+    v.m()[Na] = 0.0; v.S_abs()[Na] = 0.0; v.H_abs()[Na] = 0.0; v.thick()[Na] = 0.0;
     c.N_active = Na - 1;
   }
-  if (c.N_active == N && c.thick()[N_top + 1] - thick_0 >= 0.000001) {  // :275-314
+  if (c.N_active == N && v.thick()[N_top + 1] - thick_0 >= 0.000001) {  // :275-314
     EVT(c, EV_TOP_MELT_C);
     double loss_m = thick_0 * rho[N_top + 1];
     double loss_S = loss_m * S_bu[N_top + 1];
     double loss_H = loss_m * H[N_top + 1];
-    c.m()[N_top] = loss_m;
-    c.S_abs()[N_top] = loss_S;
-    c.H_abs()[N_top] = loss_H;
+    v.m()[N_top] = loss_m;
+    v.S_abs()[N_top] = loss_S;
+    v.H_abs()[N_top] = loss_H;
     SAMSIM_LOOP
     for (int k = N_top + 1; k <= N_middle + N_top; k++) {
-      double mk = c.m()[k] - loss_m, Hk = c.H_abs()[k] - loss_H, Sk = c.S_abs()[k] - loss_S;
+      double mk = v.m()[k] - loss_m, Hk = v.H_abs()[k] - loss_H, Sk = v.S_abs()[k] - loss_S;
       const double shift = thick_0 * (double)(float)(N_middle - k + N_top) / (double)(float)(N_middle);  // :293
       loss_m = shift * rho[k + 1];
       loss_S = loss_m * S_bu[k + 1];
       loss_H = loss_m * H[k + 1];
-      c.m()[k] = mk + loss_m;
-      c.H_abs()[k] = Hk + loss_H;
-      c.S_abs()[k] = Sk + loss_S;
+      v.m()[k] = mk + loss_m;
+      v.H_abs()[k] = Hk + loss_H;
+      v.S_abs()[k] = Sk + loss_S;
     }
     SAMSIM_LOOP
-    for (int k = N_top + 1; k <= N_top + N_middle; k++) c.thick()[k] = c.thick()[k] - thick_0 / (double)(float)(N_middle);
+    for (int k = N_top + 1; k <= N_top + N_middle; k++) v.thick()[k] = v.thick()[k] - thick_0 / (double)(float)(N_middle);
   }
   // :318-321 grid consistency, STOP 7889 (SUM(thick) over all layers; inactive are 0)
   if (c.N_active < N) {
-    if (thick_0 * (c.N_active + 0.501) <= sum_fwd(c.thick(), 1, N)) c.status = 7889;
+    if (thick_0 * (c.N_active + 0.501) <= sum_fwd(v.thick(), 1, N)) c.status = 7889;
   }
 }
 
 // bottom_melt, mo_layer_dynamics.f90:341-420
-__device__ __noinline__ void bottom_melt(const DevCfg& g, Col& c) {
-  const int N = g.Nlayer, N_middle = g.N_middle, N_top = g.N_top;
-  Lay rho = c.w0(), S_bu = c.w1(), H = c.w2();
+__device__ __noinline__ void bottom_melt(Col& c) {
+  const View v = c;
+  const int N = CFG.Nlayer, N_middle = CFG.N_middle, N_top = CFG.N_top;
+  Lay rho = v.w0(), S_bu = v.w1(), H = v.w2();
   snapshot_layers(c, N_top + 1, N);  // :364-370
-  const double thN = c.thick()[N];
+  const double thN = v.thick()[N];
   double loss_m = 0.0, loss_S = 0.0, loss_H = 0.0;
   SAMSIM_LOOP
   for (int k = N_top + 1; k <= N_top + N_middle; k++) {  // :378-400
-    double mk = c.m()[k] + loss_m, Hk = c.H_abs()[k] + loss_H, Sk = c.S_abs()[k] + loss_S;
+    double mk = v.m()[k] + loss_m, Hk = v.H_abs()[k] + loss_H, Sk = v.S_abs()[k] + loss_S;
     const double shift = thN * (k - N_top) / (double)(float)(N_middle);
     loss_m = shift * rho[k];
     loss_H = loss_m * H[k];
     loss_S = loss_m * S_bu[k];
-    c.m()[k] = mk - loss_m;
-    c.H_abs()[k] = Hk - loss_H;
-    c.S_abs()[k] = Sk - loss_S;
+    v.m()[k] = mk - loss_m;
+    v.H_abs()[k] = Hk - loss_H;
+    v.S_abs()[k] = Sk - loss_S;
   }
   SAMSIM_LOOP
-  for (int k = N_top + 1; k <= N_top + N_middle; k++) c.thick()[k] = c.thick()[k] - thN / (double)(float)(N_middle);
+  for (int k = N_top + 1; k <= N_top + N_middle; k++) v.thick()[k] = v.thick()[k] - thN / (double)(float)(N_middle);
   SAMSIM_LOOP
   for (int k = N_top + N_middle + 1; k <= N; k++) {  // :410-415
-    const double thk = c.thick()[k];
-    c.H_abs()[k] = rho[k - 1] * thk * H[k - 1];
-    c.S_abs()[k] = rho[k - 1] * thk * S_bu[k - 1];
-    c.m()[k] = rho[k - 1] * thk;
+    const double thk = v.thick()[k];
+    v.H_abs()[k] = rho[k - 1] * thk * H[k - 1];
+    v.S_abs()[k] = rho[k - 1] * thk * S_bu[k - 1];
+    v.m()[k] = rho[k - 1] * thk;
   }
 }
 
 // bottom_growth, mo_layer_dynamics.f90:438-520
-__device__ __noinline__ void bottom_growth(const DevCfg& g, Col& c) {
-  const int N = g.Nlayer, N_middle = g.N_middle, N_top = g.N_top, N_bottom = g.N_bottom;
-  Lay rho = c.w0(), S_bu = c.w1(), H = c.w2();
+__device__ __noinline__ void bottom_growth(Col& c) {
+  const View v = c;
+  const int N = CFG.Nlayer, N_middle = CFG.N_middle, N_top = CFG.N_top, N_bottom = CFG.N_bottom;
+  Lay rho = v.w0(), S_bu = v.w1(), H = v.w2();
   snapshot_layers(c, N_top + 1, N_top + N_middle + 1);  // :463-468
-  const double thN = c.thick()[N];
+  const double thN = v.thick()[N];
   double gain_m = 0.0, gain_S = 0.0, gain_H = 0.0;
   SAMSIM_LOOP
   for (int k = N_top + 1; k <= N_top + N_middle; k++) {  // :476-495
-    double mk = c.m()[k] - gain_m, Hk = c.H_abs()[k] - gain_H, Sk = c.S_abs()[k] - gain_S;
+    double mk = v.m()[k] - gain_m, Hk = v.H_abs()[k] - gain_H, Sk = v.S_abs()[k] - gain_S;
     const double shift = thN * (k - N_top) / (double)(float)(N_middle);
     gain_m = shift * rho[k + 1];
     gain_H = gain_m * H[k + 1];
     gain_S = gain_m * S_bu[k + 1];
-    c.m()[k] = mk + gain_m;
-    c.H_abs()[k] = Hk + gain_H;
-    c.S_abs()[k] = Sk + gain_S;
+    v.m()[k] = mk + gain_m;
+    v.H_abs()[k] = Hk + gain_H;
+    v.S_abs()[k] = Sk + gain_S;
   }
   SAMSIM_LOOP
-  for (int k = N_top + 1; k <= N_top + N_middle; k++) c.thick()[k] = c.thick()[k] + thN / (double)(float)(N_middle);
+  for (int k = N_top + 1; k <= N_top + N_middle; k++) v.thick()[k] = v.thick()[k] + thN / (double)(float)(N_middle);
   SAMSIM_LOOP
   for (int k = N - N_bottom + 1; k <= N - 1; k++) {  // :503-508
-    c.H_abs()[k] = c.H_abs()[k + 1];
-    c.S_abs()[k] = c.S_abs()[k + 1];
-    c.m()[k] = c.m()[k + 1];
+    v.H_abs()[k] = v.H_abs()[k + 1];
+    v.S_abs()[k] = v.S_abs()[k + 1];
+    v.m()[k] = v.m()[k + 1];
   }
-  const double mN = c.thick()[N] * rho_l;  // :511-513
-  c.m()[N] = mN;
-  c.H_abs()[N] = mN * SCV(c, SC_T_BOTTOM) * c_l;
-  c.S_abs()[N] = mN * SCV(c, SC_S_BU_BOTTOM);
+  const double mN = v.thick()[N] * rho_l;  // :511-513
+  v.m()[N] = mN;
+  v.H_abs()[N] = mN * SCV(c, SC_T_BOTTOM) * c_l;
+  v.S_abs()[N] = mN * SCV(c, SC_S_BU_BOTTOM);
 }
 
 // bottom_growth_simple :537-561, bottom_melt_simple :573-590
-__device__ __forceinline__ void bottom_growth_simple(const DevCfg& g, Col& c) {
+__device__ __forceinline__ void bottom_growth_simple(Col& c) {
+  const View v = c;
   const int Na = c.N_active + 1;
   c.N_active = Na;
-  c.thick()[Na] = g.thick_0;
-  const double mN = g.thick_0 * rho_l;
-  c.m()[Na] = mN;
-  c.H_abs()[Na] = mN * SCV(c, SC_T_BOTTOM) * c_l;
-  c.S_abs()[Na] = mN * SCV(c, SC_S_BU_BOTTOM);
+  v.thick()[Na] = CFG.thick_0;
+  const double mN = CFG.thick_0 * rho_l;
+  v.m()[Na] = mN;
+  v.H_abs()[Na] = mN * SCV(c, SC_T_BOTTOM) * c_l;
+  v.S_abs()[Na] = mN * SCV(c, SC_S_BU_BOTTOM);
 }
 __device__ __forceinline__ void bottom_melt_simple(Col& c) {
+  const View v = c;
   const int Na = c.N_active;
-  c.thick()[Na] = 0.0; c.m()[Na] = 0.0; c.S_abs()[Na] = 0.0; c.H_abs()[Na] = 0.0;
+  v.thick()[Na] = 0.0; v.m()[Na] = 0.0; v.S_abs()[Na] = 0.0; v.H_abs()[Na] = 0.0;
   c.N_active = Na - 1;
 }
 
 // top_grow, mo_layer_dynamics.f90:607-716
-__device__ __noinline__ void top_grow(const DevCfg& g, Col& c) {
-  const int N = g.Nlayer, N_middle = g.N_middle, N_top = g.N_top;
-  const double thick_0 = g.thick_0;
-  Lay rho = c.w0(), S_bu = c.w1(), H = c.w2();
+__device__ __noinline__ void top_grow(Col& c) {
+  const View v = c;
+  const int N = CFG.Nlayer, N_middle = CFG.N_middle, N_top = CFG.N_top;
+  const double thick_0 = CFG.thick_0;
+  Lay rho = v.w0(), S_bu = v.w1(), H = v.w2();
   snapshot_layers(c, 1, c.N_active);  // :631-636
   {
     const double loss_m = thick_0 * rho[1];  // :639-648
     const double loss_S = loss_m * S_bu[1];
     const double loss_H = loss_m * H[1];
-    c.m()[1] = c.m()[1] - loss_m;
-    c.S_abs()[1] = c.S_abs()[1] - loss_S;
-    c.H_abs()[1] = c.H_abs()[1] - loss_H;
-    c.thick()[1] = c.thick()[1] - thick_0;
+    v.m()[1] = v.m()[1] - loss_m;
+    v.S_abs()[1] = v.S_abs()[1] - loss_S;
+    v.H_abs()[1] = v.H_abs()[1] - loss_H;
+    v.thick()[1] = v.thick()[1] - thick_0;
   }
   const int kmax = (N_top < c.N_active) ? N_top : c.N_active;
   SAMSIM_LOOP
   for (int k = 2; k <= kmax; k++) {  // :651-656
-    c.m()[k] = rho[k - 1] * thick_0;
-    c.S_abs()[k] = S_bu[k - 1] * rho[k - 1] * thick_0;
-    c.H_abs()[k] = H[k - 1] * rho[k - 1] * thick_0;
+    v.m()[k] = rho[k - 1] * thick_0;
+    v.S_abs()[k] = S_bu[k - 1] * rho[k - 1] * thick_0;
+    v.H_abs()[k] = H[k - 1] * rho[k - 1] * thick_0;
   }
   if (c.N_active <= N_top) {  // :659-665
     EVT(c, EV_TOP_GROW_A);
     const int Na = c.N_active + 1;
     c.N_active = Na;
-    c.m()[Na] = rho[Na - 1] * thick_0;
-    c.S_abs()[Na] = S_bu[Na - 1] * thick_0 * rho[Na - 1];
-    c.H_abs()[Na] = H[Na - 1] * thick_0 * rho[Na - 1];
-    c.thick()[Na] = thick_0;
+    v.m()[Na] = rho[Na - 1] * thick_0;
+    v.S_abs()[Na] = S_bu[Na - 1] * thick_0 * rho[Na - 1];
+    v.H_abs()[Na] = H[Na - 1] * thick_0 * rho[Na - 1];
+    v.thick()[Na] = thick_0;
   } else if (c.N_active > N_top && c.N_active < N) {  // :668-680
     EVT(c, EV_TOP_GROW_B);
     SAMSIM_LOOP
     for (int k = N_top + 1; k <= c.N_active; k++) {
-      c.m()[k] = rho[k - 1] * thick_0;
-      c.S_abs()[k] = S_bu[k - 1] * rho[k - 1] * thick_0;
-      c.H_abs()[k] = H[k - 1] * rho[k - 1] * thick_0;
+      v.m()[k] = rho[k - 1] * thick_0;
+      v.S_abs()[k] = S_bu[k - 1] * rho[k - 1] * thick_0;
+      v.H_abs()[k] = H[k - 1] * rho[k - 1] * thick_0;
     }
     const int Na = c.N_active + 1;
     c.N_active = Na;
-    c.m()[Na] = rho[Na - 1] * thick_0;
-    c.S_abs()[Na] = S_bu[Na - 1] * thick_0 * rho[Na - 1];
-    c.H_abs()[Na] = H[Na - 1] * thick_0 * rho[Na - 1];
-    c.thick()[Na] = thick_0;
+    v.m()[Na] = rho[Na - 1] * thick_0;
+    v.S_abs()[Na] = S_bu[Na - 1] * thick_0 * rho[Na - 1];
+    v.H_abs()[Na] = H[Na - 1] * thick_0 * rho[Na - 1];
+    v.thick()[Na] = thick_0;
   } else if (c.N_active == N) {  // :682-711
     EVT(c, EV_TOP_GROW_C);
     double loss_m = thick_0 * rho[N_top];
@@ -1483,17 +1530,17 @@ __device__ __noinline__ void top_grow(const DevCfg& g, Col& c) {
     double loss_H = loss_m * H[N_top];
     SAMSIM_LOOP
     for (int k = N_top + 1; k <= N_middle + N_top; k++) {
-      double mk = c.m()[k] + loss_m, Hk = c.H_abs()[k] + loss_H, Sk = c.S_abs()[k] + loss_S;
+      double mk = v.m()[k] + loss_m, Hk = v.H_abs()[k] + loss_H, Sk = v.S_abs()[k] + loss_S;
       const double shift = thick_0 * (double)(float)(N_middle - k + N_top) / (double)(float)(N_middle);
       loss_m = shift * rho[k];
       loss_S = loss_m * S_bu[k];
       loss_H = loss_m * H[k];
-      c.m()[k] = mk - loss_m;
-      c.H_abs()[k] = Hk - loss_H;
-      c.S_abs()[k] = Sk - loss_S;
+      v.m()[k] = mk - loss_m;
+      v.H_abs()[k] = Hk - loss_H;
+      v.S_abs()[k] = Sk - loss_S;
     }
     SAMSIM_LOOP
-    for (int k = N_top + 1; k <= N_top + N_middle; k++) c.thick()[k] = c.thick()[k] + thick_0 / (double)(float)(N_middle);
+    for (int k = N_top + 1; k <= N_top + N_middle; k++) v.thick()[k] = v.thick()[k] + thick_0 / (double)(float)(N_middle);
   }
 }
 
@@ -1512,10 +1559,11 @@ __device__ __noinline__ void top_grow(const DevCfg& g, Col& c) {
 // The arrays are step-local: the S5 sweep assigns D and clears U, A, O, fb_x (the reference zeroes the matrix
 // after bgc_advection, mo_grotz.f90:745).
 __device__ __forceinline__ double fb_get(const Col& c, int Na, int i, int j) {
-  if (j == i + 1 && i <= Na) return c.A(AR_FB_D)[i];
-  if (i == j + 1 && j <= Na) return c.A(AR_FB_U)[j];
-  if (j == Na && i <= Na - 2) return c.A(AR_FB_A)[i];
-  if (j == Na + 1 && i <= Na - 1) return c.A(AR_FB_O)[i];
+  const View v = c;
+  if (j == i + 1 && i <= Na) return v.A(AR_FB_D)[i];
+  if (i == j + 1 && j <= Na) return v.A(AR_FB_U)[j];
+  if (j == Na && i <= Na - 2) return v.A(AR_FB_A)[i];
+  if (j == Na + 1 && i <= Na - 1) return v.A(AR_FB_O)[i];
   if (i == Na && j == 1 && Na >= 3) return c.fb_x;
   return 0.0;
 }
@@ -1523,19 +1571,20 @@ __device__ __forceinline__ double fb_get(const Col& c, int Na, int i, int j) {
 // bgc_advection.  The reference visits every (i,j) pair; an empty cell moves MIN(0*br, abs/3) = 0 and x -/+ 0 is x,
 // so rows whose content is non-negative (and whose brine concentration is finite) only visit their written cells,
 // in the same ascending-j order; any other row runs the dense loop.  temp/br are the scratch arrays w0/w1.
-__device__ __noinline__ void bgc_advection(const DevCfg& g, Col& c) {
+__device__ __noinline__ void bgc_advection(Col& c) {
+  const View v = c;
   const int Na = c.N_active;
-  Lay temp = c.w0(), br = c.w1();
-  Lay D = c.A(AR_FB_D), U = c.A(AR_FB_U), Ac = c.A(AR_FB_A), O = c.A(AR_FB_O);
-  for (int q = 0; q < g.n_bgc; q++) {
-    Lay x = c.bgc(q);
+  Lay temp = v.w0(), br = v.w1();
+  Lay D = v.A(AR_FB_D), U = v.A(AR_FB_U), Ac = v.A(AR_FB_A), O = v.A(AR_FB_O);
+  for (int q = 0; q < CFG.n_bgc; q++) {
+    Lay x = v.bgc(q);
     const double bottom = SCV(c, SC_BGC_BOTTOM1 + q);
     // bgc_temp = bgc_abs (layers below N_active are not touched: copied back unchanged) and bgc_br, :171
     SAMSIM_LOOP
     for (int k = 1; k <= Na; k++) {
       const double xk = x[k];
       temp[k] = xk;
-      br[k] = xk / (f_max(c.psi_l()[k] * c.thick()[k] * rho_l, 0.000000000000001));
+      br[k] = xk / (f_max(v.psi_l()[k] * v.thick()[k] * rho_l, 0.000000000000001));
     }
     SAMSIM_LOOP
     for (int i = 1; i <= Na; i++) {  // :179-190
@@ -1571,50 +1620,51 @@ __device__ __noinline__ void bgc_advection(const DevCfg& g, Col& c) {
 // routine layer_dynamics() is about to run, for one tracer array, BEFORE m / thick / N_active change; rho and bulk
 // are recomputed from that untouched state, so they equal the reference's snapshots.  `op` = routine chosen by the
 // dispatcher below: 1 bottom_melt, 2 bottom_melt_simple, 3 bottom_growth_simple, 4 bottom_growth, 5 top_grow, 6 top_melt.
-__device__ __noinline__ void tracer_layer_dynamics(const DevCfg& g, Col& c, int op, Lay x, double bottom) {
-  const int N = g.Nlayer, N_top = g.N_top, N_middle = g.N_middle, N_bottom = g.N_bottom, Na = c.N_active;
-  const double thick_0 = g.thick_0;
-  Lay bulk = c.w3();
-  auto rho = [&](int k) { return c.m()[k] / c.thick()[k]; };
+__device__ __noinline__ void tracer_layer_dynamics(Col& c, int op, Lay x, double bottom) {
+  const View v = c;
+  const int N = CFG.Nlayer, N_top = CFG.N_top, N_middle = CFG.N_middle, N_bottom = CFG.N_bottom, Na = c.N_active;
+  const double thick_0 = CFG.thick_0;
+  Lay bulk = v.w3();
+  auto rho = [&](int k) { return v.m()[k] / v.thick()[k]; };
   if (op == 2) { x[Na] = 0.0; return; }                                             // bottom_melt_simple :586
   if (op == 3) { x[Na + 1] = bottom * (thick_0 * rho_l); return; }                  // bottom_growth_simple :557, m = thick_0*rho_l
   if (op == 1) {  // bottom_melt :341-420
     SAMSIM_LOOP
-    for (int k = N_top + 1; k <= N; k++) bulk[k] = x[k] / c.m()[k];
+    for (int k = N_top + 1; k <= N; k++) bulk[k] = x[k] / v.m()[k];
     double loss = 0.0;
     SAMSIM_LOOP
     for (int k = N_top + 1; k <= N_top + N_middle; k++) {
       double xk = x[k] + loss;
-      const double shift = c.thick()[N] * (k - N_top) / (double)(float)(N_middle);
+      const double shift = v.thick()[N] * (k - N_top) / (double)(float)(N_middle);
       const double loss_m = shift * rho(k);
       loss = loss_m * bulk[k];
       x[k] = xk - loss;
     }
     // thick(k) of the bottom layers is not touched by the routine
     SAMSIM_LOOP
-    for (int k = N_top + N_middle + 1; k <= N; k++) x[k] = rho(k - 1) * c.thick()[k] * bulk[k - 1];
+    for (int k = N_top + N_middle + 1; k <= N; k++) x[k] = rho(k - 1) * v.thick()[k] * bulk[k - 1];
     return;
   }
   if (op == 4) {  // bottom_growth :438-520
     SAMSIM_LOOP
-    for (int k = N_top + 1; k <= N_top + N_middle + 1; k++) bulk[k] = x[k] / c.m()[k];
+    for (int k = N_top + 1; k <= N_top + N_middle + 1; k++) bulk[k] = x[k] / v.m()[k];
     double gain = 0.0;
     SAMSIM_LOOP
     for (int k = N_top + 1; k <= N_top + N_middle; k++) {
       double xk = x[k] - gain;
-      const double shift = c.thick()[N] * (k - N_top) / (double)(float)(N_middle);
+      const double shift = v.thick()[N] * (k - N_top) / (double)(float)(N_middle);
       const double gain_m = shift * rho(k + 1);
       gain = gain_m * bulk[k + 1];
       x[k] = xk + gain;
     }
     SAMSIM_LOOP
     for (int k = N - N_bottom + 1; k <= N - 1; k++) x[k] = x[k + 1];
-    x[N] = (c.thick()[N] * rho_l) * bottom;  // m(Nlayer)*bgc_bottom with the new m(Nlayer) = thick(Nlayer)*rho_l
+    x[N] = (v.thick()[N] * rho_l) * bottom;  // m(Nlayer)*bgc_bottom with the new m(Nlayer) = thick(Nlayer)*rho_l
     return;
   }
   // top_grow / top_melt work on layers 1..N_active
   SAMSIM_LOOP
-  for (int k = 1; k <= Na; k++) bulk[k] = x[k] / c.m()[k];
+  for (int k = 1; k <= Na; k++) bulk[k] = x[k] / v.m()[k];
   if (op == 5) {  // top_grow :607-716
     {
       const double loss_m = thick_0 * rho(1);
@@ -1654,13 +1704,13 @@ __device__ __noinline__ void tracer_layer_dynamics(const DevCfg& g, Col& c, int 
   if (Na <= N_top) {
     x[Na] = 0.0;
     Nb = Na - 1;
-  } else if (Na > N_top && Na <= N && c.thick()[N_top + 1] / thick_0 < 1.00001) {
+  } else if (Na > N_top && Na <= N && v.thick()[N_top + 1] / thick_0 < 1.00001) {
     SAMSIM_LOOP
     for (int k = N_top; k <= Na - 1; k++) x[k] = bulk[k + 1] * rho(k + 1) * thick_0;
     x[Na] = 0.0;
     Nb = Na - 1;
   }
-  if (Nb == N && c.thick()[N_top + 1] - thick_0 >= 0.000001) {
+  if (Nb == N && v.thick()[N_top + 1] - thick_0 >= 0.000001) {
     double loss_m = thick_0 * rho(N_top + 1);
     double loss = loss_m * bulk[N_top + 1];
     x[N_top] = loss;
@@ -1676,21 +1726,22 @@ __device__ __noinline__ void tracer_layer_dynamics(const DevCfg& g, Col& c, int 
 }
 
 // layer_dynamics dispatcher, mo_layer_dynamics.f90:64-175
-__device__ __noinline__ void layer_dynamics(const DevCfg& g, Col& c) {
-  const int N = g.Nlayer, N_top = g.N_top, Na = c.N_active;
-  const double thick_0 = g.thick_0;
-  const bool bf = (g.bottom_flag == 1);
+__device__ __noinline__ void layer_dynamics(Col& c) {
+  const View v = c;
+  const int N = CFG.Nlayer, N_top = CFG.N_top, Na = c.N_active;
+  const double thick_0 = CFG.thick_0;
+  const bool bf = (CFG.bottom_flag == 1);
   const int nm1 = (Na - 1 > 1) ? Na - 1 : 1;
-  const double phi_Na = c.phi()[Na], phi_nm1 = c.phi()[nm1], th1 = c.thick()[1];
-  const double mid_ratio = c.thick()[N_top + 1] / thick_0;
+  const double phi_Na = v.phi()[Na], phi_nm1 = v.phi()[nm1], th1 = v.thick()[1];
+  const double mid_ratio = v.thick()[N_top + 1] / thick_0;
   // tracers first (they read the untouched m, thick, N_active), then the routine itself
   auto tracers = [&](int op) {
-    for (int q = 0; q < g.n_bgc; q++) tracer_layer_dynamics(g, c, op, c.bgc(q), SCV(c, SC_BGC_BOTTOM1 + q));
+    for (int q = 0; q < CFG.n_bgc; q++) tracer_layer_dynamics(c, op, v.bgc(q), SCV(c, SC_BGC_BOTTOM1 + q));
   };
-  if (c.phi()[N - 1] <= psi_s_min / 2.0 && phi_Na < 0.00001 && Na == N && mid_ratio > 1.000001 && bf) {
+  if (v.phi()[N - 1] <= psi_s_min / 2.0 && phi_Na < 0.00001 && Na == N && mid_ratio > 1.000001 && bf) {
     EVT(c, EV_BOTTOM_MELT);
     tracers(1);
-    bottom_melt(g, c);
+    bottom_melt(c);
   } else if (Na > 1 && Na < N && phi_Na < 0.00001 && phi_nm1 <= psi_s_min / 2.0 && bf) {
     EVT(c, EV_BOTTOM_MELT_SIMPLE_A);
     tracers(2);
@@ -1702,21 +1753,21 @@ __device__ __noinline__ void layer_dynamics(const DevCfg& g, Col& c) {
   } else if (phi_Na > psi_s_min && Na < N && bf) {
     EVT(c, EV_BOTTOM_GROWTH_SIMPLE);
     tracers(3);
-    bottom_growth_simple(g, c);
-  } else if (c.phi()[N] > psi_s_min && bf) {
+    bottom_growth_simple(c);
+  } else if (v.phi()[N] > psi_s_min && bf) {
     EVT(c, EV_BOTTOM_GROWTH);
     tracers(4);
-    bottom_growth(g, c);
+    bottom_growth(c);
   } else if (th1 > 1.5 * thick_0) {
     SCV(c, SC_MTO3) = SCV(c, SC_MTO3) - th1;
     tracers(5);
-    top_grow(g, c);
-    SCV(c, SC_MTO3) = SCV(c, SC_MTO3) + c.thick()[1];
+    top_grow(c);
+    SCV(c, SC_MTO3) = SCV(c, SC_MTO3) + v.thick()[1];
   } else if (th1 < 0.5 * thick_0) {
     SCV(c, SC_MTO3) = SCV(c, SC_MTO3) - th1;
     tracers(6);
-    top_melt(g, c);
-    SCV(c, SC_MTO3) = SCV(c, SC_MTO3) + c.thick()[1];
+    top_melt(c);
+    SCV(c, SC_MTO3) = SCV(c, SC_MTO3) + v.thick()[1];
   }
 }
 

@@ -41,8 +41,8 @@ static_assert((int)SAMSIM_SNAPSC_COUNT == 20 && (int)SAMSIM_SNAPARR_COUNT == 14,
 // kernel parameters
 // ------------------------------------------------------------------------------------------
 struct KParams {
-  DevCfg cfg;
-  double* arr;   // [AR_COUNT][LS][ncol_pad]
+  double* arr;   // [ncol_pad/32][LS][n_arr][32], see physics.cuh
+  int n_arr;
   double* sc;    // [SC_COUNT][ncol_pad]
   int* in;       // [IN_COUNT][ncol_pad]
   long long ncol, ncol_pad;
@@ -90,13 +90,11 @@ __global__ void __launch_bounds__(SAMSIM_BLOCK, SAMSIM_MINBLOCKS) samsim_step_ke
   const long long col_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool padding = (col_raw >= p.ncol);
   const long long col = padding ? (p.ncol - 1) : col_raw;
-  const size_t ls = (size_t)p.ncol_pad;
-  const size_t astr = (size_t)p.LS * ls;
+  const size_t ls = (size_t)p.ncol_pad;  // row stride of the scalar / int / forcing rows
 
   Col c;
-  c.base = p.arr + col;
-  c.ls = (unsigned)ls;
-  c.astr = (unsigned)astr;
+  c.ls = (unsigned)(p.n_arr * SAMSIM_TILE);
+  c.base = p.arr + (size_t)(col / SAMSIM_TILE) * p.LS * c.ls + (size_t)(col % SAMSIM_TILE);
   for (int q = 0; q < SC_COUNT; q++) c.sc[q] = p.sc[(size_t)q * ls + col];
   c.N_active = p.in[(size_t)IN_N_ACTIVE * ls + col];
   c.status = padding ? -1 : p.in[(size_t)IN_STATUS * ls + col];
@@ -125,7 +123,7 @@ __global__ void __launch_bounds__(SAMSIM_BLOCK, SAMSIM_MINBLOCKS) samsim_step_ke
   snap.scalars = p.snap_sc; snap.arrays = p.snap_arr; snap.ncol_pad = ls; snap.col = (int)col;
 
   // every thread runs every step: a failed column only skips the phase bodies (column_step checks c.status)
-  for (int s = 0; s < p.nsteps; s++) column_step(p.cfg, c, f, s == p.nsteps - 1, snap);
+  for (int s = 0; s < p.nsteps; s++) column_step(c, f, s == p.nsteps - 1, snap);
 
   if (padding) return;
   for (int q = 0; q < SC_COUNT; q++) p.sc[(size_t)q * ls + col] = c.sc[q];
@@ -140,6 +138,11 @@ __global__ void __launch_bounds__(SAMSIM_BLOCK, SAMSIM_MINBLOCKS) samsim_step_ke
 // (slot_of_col, nullptr = identity) translates the caller's column index in every host-facing kernel.
 __device__ __forceinline__ long long slot_of(const int* map, long long col) { return map ? (long long)map[col] : col; }
 
+// element (array slot a, layer k) of the column in device slot s of the tiled state buffer (physics.cuh)
+__host__ __device__ __forceinline__ size_t state_index(long long s, int k, int a, int LS, int n_arr) {
+  return ((((size_t)(s / SAMSIM_TILE)) * LS + k) * n_arr + a) * SAMSIM_TILE + (size_t)(s % SAMSIM_TILE);
+}
+
 // replicate one column (ensemble initialisation)
 __global__ void samsim_broadcast_kernel(double* arr, double* sc, int* in, long long ncol_pad, int LS, int src, int col0,
                                         int n, const int* map, int n_arr) {
@@ -149,11 +152,8 @@ __global__ void samsim_broadcast_kernel(double* arr, double* sc, int* in, long l
   src = (int)slot_of(map, src);
   if (col == src) return;
   const size_t ls = (size_t)ncol_pad;
-  for (int a = 0; a < n_arr; a++)
-    for (int k = 0; k < LS; k++) {
-      const size_t o = ((size_t)a * LS + k) * ls;
-      arr[o + col] = arr[o + src];
-    }
+  for (int k = 0; k < LS; k++)
+    for (int a = 0; a < n_arr; a++) arr[state_index(col, k, a, LS, n_arr)] = arr[state_index(src, k, a, LS, n_arr)];
   for (int q = 0; q < SC_COUNT; q++) sc[(size_t)q * ls + col] = sc[(size_t)q * ls + src];
   for (int q = 0; q < IN_COUNT; q++) in[(size_t)q * ls + col] = in[(size_t)q * ls + src];
 }
@@ -171,14 +171,36 @@ __global__ void samsim_gather_kernel(const double* src, double* dst, long long n
   const int id = (int)(r / ext);
   dst[((size_t)cc * count + id) * ext + k] = src[((size_t)id * LS + (k + k0)) * (size_t)ncol_pad + slot_of(map, col0 + cc)];
 }
-__global__ void samsim_scatter_kernel(double* dstdev, const double* srchost, long long ncol_pad, int LS, int id, int ext,
-                                      int col0, int n, const int* map) {
+// state arrays (tiled layout) <-> host order host[c*ext + (k-1)]
+__global__ void samsim_state_gather_kernel(const double* arr, double* dst, int LS, int n_arr, int a, int ext, int col0, int n,
+                                           const int* map) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * ext) return;
+  const int cc = (int)(t % n), k = (int)(t / n);  // column fastest: coalesced reads within a tile row
+  dst[(size_t)cc * ext + k] = arr[state_index(slot_of(map, col0 + cc), k + 1, a, LS, n_arr)];
+}
+__global__ void samsim_scatter_kernel(double* arr, const double* srchost, int LS, int n_arr, int a, int ext, int col0, int n,
+                                      const int* map) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)n * ext;
   if (t >= total) return;
   const int cc = (int)(t % n);
   const int k = (int)(t / n);
-  dstdev[((size_t)id * LS + (k + 1)) * (size_t)ncol_pad + slot_of(map, col0 + cc)] = srchost[(size_t)cc * ext + k];
+  arr[state_index(slot_of(map, col0 + cc), k + 1, a, LS, n_arr)] = srchost[(size_t)cc * ext + k];
+}
+// re-binning of one state array: rows[k][s] (k = 0..LS-1, row stride ncol_pad) <-> the tiled buffer
+__global__ void samsim_state_to_rows_kernel(const double* arr, double* rows, long long ncol, long long ncol_pad, int LS, int n_arr,
+                                            int a, const int* order) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)LS * ncol) return;
+  const long long k = t / ncol, s = t - k * ncol;
+  rows[k * ncol_pad + s] = arr[state_index(order[s], (int)k, a, LS, n_arr)];
+}
+__global__ void samsim_rows_to_state_kernel(double* arr, const double* rows, long long ncol, long long ncol_pad, int LS, int n_arr, int a) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)LS * ncol) return;
+  const long long k = t / ncol, s = t - k * ncol;
+  arr[state_index(s, (int)k, a, LS, n_arr)] = rows[k * ncol_pad + s];
 }
 // per-column vectors (scalars, ints, forcing perturbations) through the slot map
 template <typename T>
@@ -261,34 +283,31 @@ __global__ void samsim_count_failed_kernel(const int* in, long long ncol, long l
 }
 
 // ---- KAT kernels -----------------------------------------------------------------------------
-__device__ void fill_liquidus(DevCfg& g, int salt_flag) {
+static void fill_liquidus(DevCfg& g, int salt_flag) {
   g.salt_flag = salt_flag;
-  if (salt_flag == 1) { g.c2 = -18.7; g.c3 = -0.519; g.c4 = -0.00535; g.d2 = -21.4; g.d3x2 = 2.0 * -0.886; g.d4x3 = 3.0 * -0.0170; }
-  else { g.c2 = -17.6; g.c3 = -0.389; g.c4 = -0.00362; g.d2 = -17.6; g.d3x2 = 2.0 * -0.389; g.d4x3 = 3.0 * -0.00362; }
+  if (salt_flag == 1) { g.c2 = -18.7; g.c3 = -0.519; g.c4 = -0.00535; g.d2 = -21.4; g.d3x2 = 2.0 * -0.886; g.d4x3 = 3.0 * -0.0170; }  // mo_thermo_functions.f90:321-326 / :393-397
+  else { g.c2 = -17.6; g.c3 = -0.389; g.c4 = -0.00362; g.d2 = -17.6; g.d3x2 = 2.0 * -0.389; g.d4x3 = 3.0 * -0.00362; }                // :331-336 / :398-402
 }
 __global__ void samsim_kat_getT_kernel(int salt_flag, int n, const double* H, const double* S_bu, const double* T_in,
                                        double* T_out, double* phi_out, int* st) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n) return;
-  DevCfg g;
-  fill_liquidus(g, salt_flag);
+  (void)salt_flag;  // the liquidus of salt_flag is in the constant-memory configuration (kat_upload_cfg)
   double T = 0.0, phi = 0.0;
   int status = 0;
   unsigned ev1 = 0;
-  getT(g, H[q], S_bu[q], T_in[q], T, phi, status, ev1);
+  getT(H[q], S_bu[q], T_in[q], T, phi, status, ev1);
   // status_out: the STOP code in the low 16 bits; bits 16.. = the EV_GETT_* branch bits (word 1 of the event words)
   T_out[q] = T; phi_out[q] = phi; st[q] = status | (int)(ev1 << 16);
 }
 __global__ void samsim_kat_scalar_kernel(int fn, int salt_flag, int n, const double* a, const double* b, double* out) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n) return;
-  DevCfg g;
-  fill_liquidus(g, salt_flag);
   double r;
   switch (fn) {
-    case 0: r = S_br_of(g, a[q]); break;
-    case 1: r = S_br_of(g, a[q], b[q]); break;
-    case 2: r = ddT_S_br_of(g, a[q]); break;
+    case 0: r = S_br_of(a[q]); break;
+    case 1: r = S_br_of(a[q], b[q]); break;
+    case 2: r = ddT_S_br_of(a[q]); break;
     case 3: r = density_of(a[q], b[q]); break;
     case 4: r = T_freeze_of(a[q], salt_flag); break;
     case 5: r = k_snow_of(a[q], b[q]); break;
@@ -340,6 +359,7 @@ struct samsim_b200_handle_s {
   int* in = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_launch = nullptr;  // after the last step kernel: the next owner of the constant-memory configuration waits for it
   bool timed = false;
   // clock
   double time = 0.0;
@@ -366,6 +386,29 @@ struct samsim_b200_handle_s {
   int *slot_of_col = nullptr, *col_of_slot = nullptr;
   long long rebin_every = 0, since_rebin = 0, rebins = 0;
 };
+
+// The step kernel reads its configuration from constant memory (samsim_dev_cfg, physics.cuh), one copy per device.
+// `g_cfg_owner[device]` is the handle whose DevCfg is there (nullptr: a KAT call overwrote it).  A handle that is not
+// the owner waits for the owner's last launch and uploads its own on its stream -- nothing in the common case of one
+// handle per device.  One host thread per handle (include/samsim_b200.h); the table itself is guarded by a mutex.
+#include <mutex>
+static std::mutex g_cfg_mutex;
+static samsim_handle_t g_cfg_owner[64] = {nullptr};
+
+static int claim_device_cfg(samsim_handle_t h) {
+  std::lock_guard<std::mutex> lock(g_cfg_mutex);
+  const int d = h->device & 63;
+  if (g_cfg_owner[d] == h) return 0;
+  if (g_cfg_owner[d] && g_cfg_owner[d]->ev_launch) CU(cudaStreamWaitEvent(h->stream, g_cfg_owner[d]->ev_launch, 0));
+  CU(cudaMemcpyToSymbolAsync(samsim_dev_cfg, &h->dcfg, sizeof(DevCfg), 0, cudaMemcpyHostToDevice, h->stream));
+  g_cfg_owner[d] = h;
+  return 0;
+}
+static void release_device_cfg(samsim_handle_t h) {
+  std::lock_guard<std::mutex> lock(g_cfg_mutex);
+  const int d = h->device & 63;
+  if (g_cfg_owner[d] == h) g_cfg_owner[d] = nullptr;
+}
 
 static int ensure_stage(samsim_handle_t h, size_t bytes) {
   if (h->stage_bytes >= bytes) return 0;
@@ -467,9 +510,11 @@ int samsim_b200_create(const samsim_config_t* cfg, int32_t ncol, int32_t device,
   h->ncol_pad = ((long long)ncol + SAMSIM_BLOCK - 1) / SAMSIM_BLOCK * SAMSIM_BLOCK;
   h->LS = cfg->Nlayer + 2;
   h->n_arr = (cfg->N_bgc > 0) ? AR_COUNT : AR_CORE_COUNT;
-  if ((unsigned long long)h->n_arr * h->LS * (unsigned long long)h->ncol_pad >= (1ull << 32)) {
+  // (32-bit index arithmetic is confined to one tile: (Nlayer+2)*n_arr*32 elements; no limit on the column count
+  // other than memory)
+  if ((unsigned long long)h->n_arr * h->LS * SAMSIM_TILE >= (1ull << 31)) {
     delete h;
-    return fail(SAMSIM_ERR_ARG, "create: 22*(Nlayer+2)*ncol (28 with tracers) must stay below 2^32 (32-bit element index); use several handles");
+    return fail(SAMSIM_ERR_ARG, "create: Nlayer too large for the 32-bit in-tile index");
   }
   DevCfg& d = h->dcfg;
   memset(&d, 0, sizeof d);
@@ -486,11 +531,7 @@ int samsim_b200_create(const samsim_config_t* cfg, int32_t ncol, int32_t device,
   d.dt = cfg->dt; d.thick_0 = cfg->thick_0; d.thick_min = cfg->thick_min; d.time_out = cfg->time_out;
   d.alpha_flux_instable = cfg->alpha_flux_instable; d.alpha_flux_stable = cfg->alpha_flux_stable; d.m_total = cfg->m_total;
   d.max_flux_plate = cfg->max_flux_plate; d.k_snow_flush = cfg->k_snow_flush; d.k_styropor = cfg->k_styropor;
-  if (cfg->salt_flag == 1) {  // mo_thermo_functions.f90:321-326 / :393-397
-    d.c2 = -18.7; d.c3 = -0.519; d.c4 = -0.00535; d.d2 = -21.4; d.d3x2 = 2.0 * -0.886; d.d4x3 = 3.0 * -0.0170;
-  } else {                    // :331-336 / :398-402
-    d.c2 = -17.6; d.c3 = -0.389; d.c4 = -0.00362; d.d2 = -17.6; d.d3x2 = 2.0 * -0.389; d.d4x3 = 3.0 * -0.00362;
-  }
+  fill_liquidus(d, cfg->salt_flag);
   const size_t narr = (size_t)h->n_arr * h->LS * h->ncol_pad;
   cudaError_t e;
   if ((e = cudaMalloc(&h->arr, narr * sizeof(double))) != cudaSuccess ||
@@ -505,6 +546,7 @@ int samsim_b200_create(const samsim_config_t* cfg, int32_t ncol, int32_t device,
   cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
+  cudaEventCreateWithFlags(&h->ev_launch, cudaEventDisableTiming);
   *out = h;
   return SAMSIM_OK;
 }
@@ -513,6 +555,8 @@ void samsim_b200_destroy(samsim_handle_t h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  release_device_cfg(h);
+  if (h->ev_launch) cudaEventDestroy(h->ev_launch);
   cudaFree(h->arr); cudaFree(h->sc); cudaFree(h->in); cudaFree(h->series); cudaFree(h->site_of_col);
   cudaFree(h->fscale); cudaFree(h->foffset); cudaFree(h->lab); cudaFree(h->set_of_col); cudaFree(h->snap_sc);
   cudaFree(h->snap_arr); cudaFree(h->stage); cudaFree(h->slot_of_col); cudaFree(h->col_of_slot);
@@ -550,7 +594,7 @@ int samsim_b200_set_array(samsim_handle_t h, int32_t id, const double* host, int
   if ((rc = ensure_stage(h, bytes))) return rc;
   CU(cudaMemcpyAsync(h->stage, host, bytes, cudaMemcpyHostToDevice, h->stream));
   const long long total = (long long)n * ext;
-  samsim_scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->arr, h->stage, h->ncol_pad, h->LS, arr_slot(id), ext, col0, n, h->slot_of_col);
+  samsim_scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->arr, h->stage, h->LS, h->n_arr, arr_slot(id), ext, col0, n, h->slot_of_col);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->stream));
   return 0;
@@ -566,7 +610,7 @@ int samsim_b200_get_array(samsim_handle_t h, int32_t id, double* host, int32_t c
   const size_t bytes = (size_t)n * ext * sizeof(double);
   if ((rc = ensure_stage(h, bytes))) return rc;
   const long long total = (long long)n * ext;
-  samsim_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->arr + (size_t)arr_slot(id) * h->LS * h->ncol_pad, h->stage, h->ncol_pad, h->LS, 1, ext, col0, n, 1, h->slot_of_col);
+  samsim_state_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->arr, h->stage, h->LS, h->n_arr, arr_slot(id), ext, col0, n, h->slot_of_col);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(host, h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -722,8 +766,7 @@ int samsim_b200_step(samsim_handle_t h, int64_t nsteps) {
     // how many steps fit the staged forcing window?
     KParams p;
     memset(&p, 0, sizeof p);
-    p.cfg = h->dcfg;
-    p.arr = h->arr; p.sc = h->sc; p.in = h->in;
+    p.arr = h->arr; p.n_arr = h->n_arr; p.sc = h->sc; p.in = h->in;
     p.ncol = h->ncol; p.ncol_pad = h->ncol_pad; p.LS = h->LS;
     p.time = h->time; p.i = h->i; p.n_time_out = h->n_time_out; p.time_counter = h->time_counter;
     int64_t chunk = left;
@@ -773,8 +816,13 @@ int samsim_b200_step(samsim_handle_t h, int64_t nsteps) {
     int block = SAMSIM_BLOCK;
     while (block > 64 && (h->ncol + block - 1) / block < 2 * h->num_sms) block >>= 1;
     const unsigned grid = (unsigned)((h->ncol + block - 1) / block);
+    {
+      int rc = claim_device_cfg(h);
+      if (rc) return rc;
+    }
     samsim_step_kernel<<<grid, block, 0, h->stream>>>(p);
     CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ev_launch, h->stream));
     h->launches++;
     for (int64_t s = 0; s < chunk; s++) clock_tick(h);
     left -= chunk;
@@ -832,9 +880,18 @@ int samsim_b200_rebin(samsim_handle_t h, int32_t* changed) {
   RB(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys, keys_out, vals, order, (int)n, 0, 32, h->stream));
   RB(cudaMalloc(&tmp, permute_tmp_bytes(h)));
 
-  const size_t astr = (size_t)h->LS * h->ncol_pad;
-  for (int a = 0; a < AR_STATE_COUNT && !rc; a++) rc = permute_rows<double>(h, h->arr + (size_t)a * astr, h->LS, order, tmp);
-  for (int q = 0; q < h->cfg.N_bgc && !rc; q++) rc = permute_rows<double>(h, h->arr + (size_t)(AR_BGC1 + q) * astr, h->LS, order, tmp);
+  const size_t astr = (size_t)h->LS * h->ncol_pad;  // one array of the (row-major) snapshot buffer
+  {
+    // state arrays: gather array a of the columns in their new order into rows, write the rows back into the tiles
+    const long long total = (long long)h->LS * n;
+    const unsigned nbk = (unsigned)((total + 255) / 256);
+    for (int a = 0; a < h->n_arr; a++) {
+      if (a >= AR_STATE_COUNT && !(a >= AR_BGC1 && a < AR_BGC1 + h->cfg.N_bgc)) continue;  // scratch arrays carry no state
+      samsim_state_to_rows_kernel<<<nbk, 256, 0, h->stream>>>(h->arr, (double*)tmp, n, h->ncol_pad, h->LS, h->n_arr, a, order);
+      samsim_rows_to_state_kernel<<<nbk, 256, 0, h->stream>>>(h->arr, (const double*)tmp, n, h->ncol_pad, h->LS, h->n_arr, a);
+    }
+    RB(cudaGetLastError());
+  }
   if (!rc) rc = permute_rows<double>(h, h->sc, SC_COUNT, order, tmp);
   if (!rc) rc = permute_rows<int>(h, h->in, IN_COUNT, order, tmp);
   if (!rc) rc = permute_rows<int>(h, h->site_of_col, 1, order, tmp);
@@ -1072,13 +1129,15 @@ int samsim_b200_last_step_ms(samsim_handle_t h, float* ms) {
   return 0;
 }
 
-int samsim_b200_device_layout(samsim_handle_t h, void** arrays, void** scalars, void** ints, int64_t* ncol_pad, int64_t* lstride) {
+int samsim_b200_device_layout(samsim_handle_t h, void** arrays, void** scalars, void** ints, int64_t* ncol_pad, int64_t* lstride,
+                              int64_t* narrays) {
   if (!h) return fail(SAMSIM_ERR_ARG, "null handle");
   if (arrays) *arrays = h->arr;
   if (scalars) *scalars = h->sc;
   if (ints) *ints = h->in;
   if (ncol_pad) *ncol_pad = h->ncol_pad;
   if (lstride) *lstride = h->LS;
+  if (narrays) *narrays = h->n_arr;
   return 0;
 }
 
@@ -1090,12 +1149,25 @@ static int kat_common(int device) {
   CU(cudaSetDevice(device));
   return 0;
 }
+// the known-answer kernels read the liquidus of `salt_flag` from the constant-memory configuration
+static int kat_upload_cfg(int device, int salt_flag) {
+  if (!(salt_flag == 1 || salt_flag == 2)) return fail(SAMSIM_ERR_ARG, "salt_flag must be 1 or 2");
+  DevCfg g;
+  memset(&g, 0, sizeof g);
+  fill_liquidus(g, salt_flag);
+  std::lock_guard<std::mutex> lock(g_cfg_mutex);
+  CU(cudaDeviceSynchronize());  // no step kernel of another handle may still be reading the old configuration
+  CU(cudaMemcpyToSymbol(samsim_dev_cfg, &g, sizeof(DevCfg), 0, cudaMemcpyHostToDevice));
+  g_cfg_owner[device & 63] = nullptr;
+  return 0;
+}
 
 int samsim_b200_kat_getT(int32_t salt_flag, int32_t n, const double* H, const double* S_bu, const double* T_in, double* T_out,
                          double* phi_out, int32_t* status_out, int32_t device) {
   int rc = kat_common(device);
   if (rc) return rc;
   if (n < 1 || !H || !S_bu || !T_in || !T_out || !phi_out) return fail(SAMSIM_ERR_ARG, "kat_getT: bad argument");
+  if ((rc = kat_upload_cfg(device, salt_flag))) return rc;
   double* d = nullptr;
   int* ds = nullptr;
   const size_t nb = (size_t)n * sizeof(double);
@@ -1118,6 +1190,7 @@ int samsim_b200_kat_scalar(int32_t fn, int32_t salt_flag, int32_t n, const doubl
   int rc = kat_common(device);
   if (rc) return rc;
   if (n < 1 || !a || !out) return fail(SAMSIM_ERR_ARG, "kat_scalar: bad argument");
+  if ((rc = kat_upload_cfg(device, salt_flag))) return rc;
   double* d = nullptr;
   const size_t nb = (size_t)n * sizeof(double);
   CU(cudaMalloc(&d, 3 * nb));

@@ -32,11 +32,12 @@ __device__ __forceinline__ double lab_rec(const Forcing& f, int kind, long long 
 }
 
 // S0 vital signs, mo_grotz.f90:192-223 (diagnostics; psi_* are the previous step's)
-__device__ __noinline__ void vital_signs(const DevCfg& g, Col& c) {
+__device__ __noinline__ void vital_signs(Col& c) {
+  const View v = c;
   const int Na = c.N_active;
   double sumH = 0.0, summ = 0.0, sumS = 0.0;
   SAMSIM_LOOP
-  for (int k = 1; k <= Na; k++) { sumH = sumH + c.H_abs()[k]; summ = summ + c.m()[k]; sumS = sumS + c.S_abs()[k]; }
+  for (int k = 1; k <= Na; k++) { sumH = sumH + v.H_abs()[k]; summ = summ + v.m()[k]; sumS = sumS + v.S_abs()[k]; }
   SCV(c, SC_ENERGY_STORED) = SCV(c, SC_H_ABS_SNOW) + sumH - SCV(c, SC_T_BOTTOM) * summ * c_l;
   double fw = summ / rho_l;
   fw = fw * (1.0 - sumS / summ / ref_salinity);
@@ -44,48 +45,49 @@ __device__ __noinline__ void vital_signs(const DevCfg& g, Col& c) {
   SCV(c, SC_FRESHWATER) = fw;
   double tr = 0.0;
   SAMSIM_LOOP
-  for (int jj = 1; jj <= Na - 1; jj++) tr = tr + c.thick()[jj] / (c.psi_l()[jj] * k_l + c.psi_s()[jj] * k_s);
-  const double thNa = c.thick()[Na], psNa = c.psi_s()[Na];
+  for (int jj = 1; jj <= Na - 1; jj++) tr = tr + v.thick()[jj] / (v.psi_l()[jj] * k_l + v.psi_s()[jj] * k_s);
+  const double thNa = v.thick()[Na], psNa = v.psi_s()[Na];
   tr = tr + thNa * psNa / psi_s_min * (psi_s_min * k_s + 1.0 - psi_s_min * k_l);
-  if (SCV(c, SC_THICK_SNOW) > g.thick_min / 110.0) tr = tr + SCV(c, SC_THICK_SNOW) / k_snow_of(SCV(c, SC_M_SNOW), SCV(c, SC_THICK_SNOW));
+  if (SCV(c, SC_THICK_SNOW) > CFG.thick_min / 110.0) tr = tr + SCV(c, SC_THICK_SNOW) / k_snow_of(SCV(c, SC_M_SNOW), SCV(c, SC_THICK_SNOW));
   SCV(c, SC_TOTAL_RESIST) = tr;
-  double th = (Na > 1) ? sum_fwd(c.thick(), 1, Na - 1) : 0.0;
+  double th = (Na > 1) ? sum_fwd(v.thick(), 1, Na - 1) : 0.0;
   SCV(c, SC_THICKNESS) = th + thNa * psNa / psi_s_min;
   if (Na > 1) {
-    double b = sum_fwd(c.S_abs(), 1, Na - 1) + c.S_abs()[Na] * psNa / psi_s_min;
-    b = b / (sum_fwd(c.m(), 1, Na - 1) + c.m()[Na] * psNa / psi_s_min);
+    double b = sum_fwd(v.S_abs(), 1, Na - 1) + v.S_abs()[Na] * psNa / psi_s_min;
+    b = b / (sum_fwd(v.m(), 1, Na - 1) + v.m()[Na] * psNa / psi_s_min);
     SCV(c, SC_BULK_SALIN) = b;
   } else {
-    SCV(c, SC_BULK_SALIN) = c.S_abs()[1] / c.m()[1];
+    SCV(c, SC_BULK_SALIN) = v.S_abs()[1] / v.m()[1];
   }
 }
 
 // sub_heat_fluxes, mo_heat_fluxes.f90:69-312
-__device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
+__device__ __noinline__ void heat_fluxes(Col& c) {
+  const View v = c;
   const int Na = c.N_active;
-  const double dt = g.dt, thick_min = g.thick_min;
-  const double ps1 = c.psi_s()[1], pl1 = c.psi_l()[1], pg1 = c.psi_g()[1], th1 = c.thick()[1];
-  double T1 = c.T()[1];
+  const double dt = CFG.dt, thick_min = CFG.thick_min;
+  const double ps1 = v.psi_s()[1], pl1 = v.psi_l()[1], pg1 = v.psi_g()[1], th1 = v.thick()[1];
+  double T1 = v.T()[1];
   double& thick_snow = SCV(c, SC_THICK_SNOW);
   double& T_top = SCV(c, SC_T_TOP);
   double& fl_q_snow = SCV(c, SC_FL_Q_SNOW);
-  double flQ1 = c.fl_Q()[1];
+  double flQ1 = v.fl_Q()[1];
   double fl_rad_Na = 0.0;  // fl_rad(N_active): 0 unless boundflux 2 recomputes it (fl_rad = 0 from init, mo_init.f90:1988)
 
-  if (g.boundflux_flag == 1) {  // :77-86
+  if (CFG.boundflux_flag == 1) {  // :77-86
     flQ1 = fl_Q_0_top(ps1, pl1, pg1, th1, T1, T_top);
-    if (fabs(flQ1) > g.max_flux_plate) flQ1 = flQ1 / fabs(flQ1) * g.max_flux_plate;
+    if (fabs(flQ1) > CFG.max_flux_plate) flQ1 = flQ1 / fabs(flQ1) * CFG.max_flux_plate;
   }
 
-  if (g.boundflux_flag == 2) {  // :90-195
+  if (CFG.boundflux_flag == 2) {  // :90-195
     double& albedo = SCV(c, SC_ALBEDO);
     double& fl_sw = SCV(c, SC_FL_SW);
     double& fl_rest = SCV(c, SC_FL_REST);
-    albedo = albedo_of(thick_snow, SCV(c, SC_T_SNOW), pl1, thick_min, g.albedo_flag);
-    if (g.atmoflux_flag == 1) {
+    albedo = albedo_of(thick_snow, SCV(c, SC_T_SNOW), pl1, thick_min, CFG.albedo_flag);
+    if (CFG.atmoflux_flag == 1) {
       EVT(c, EV_NOTZFLUX);
       notzflux(c.time + 86400.0 * 180.0, fl_sw, fl_rest);
-    } else if (g.atmoflux_flag == 2) {  // :97-111
+    } else if (CFG.atmoflux_flag == 2) {  // :97-111
       double fl_lw;
       if (c.time == c.ftime1) {
         fl_sw = c.fsw1;
@@ -122,8 +124,8 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
       const int kend = (temp2 == 0.0) ? 0 : Na;
       SAMSIM_LOOP
       for (int k = 1; k <= kend; k++) {
-        if (k + SAMSIM_PF <= Na) c.thick().prefetch(k + SAMSIM_PF);
-        const double thk = c.thick()[k];
+        if (k + SAMSIM_PF <= Na) v.thick().prefetch(k + SAMSIM_PF);
+        const double thk = v.thick()[k];
         if (thk != last_th) { last_e = det_exp(-extinc * thk); last_th = thk; }
         if (k == Na) fl_rad_Na = temp2 - temp2 * last_e;
         temp2 = temp2 * last_e;
@@ -132,7 +134,7 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
 
     double& T_freeze = SCV(c, SC_T_FREEZE);
     if (thick_snow >= thick_min / 100.0) T_freeze = 0.0;  // :158-162
-    else T_freeze = T_freeze_of(c.S_abs()[1] / c.m()[1], g.salt_flag);
+    else T_freeze = T_freeze_of(v.S_abs()[1] / v.m()[1], CFG.salt_flag);
 
     if (T_top > T_freeze && Na > 1) {  // :167-180
       EVT(c, EV_HEAT_MELT);
@@ -160,25 +162,25 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
     }
   }
 
-  if (g.boundflux_flag == 3) {  // :202-258
+  if (CFG.boundflux_flag == 3) {  // :202-258
     const double T2m = SCV(c, SC_T2M);
     double& T_freeze = SCV(c, SC_T_FREEZE);
-    if (g.lab_snow_flag == 0 || thick_snow <= thick_min / 100.0) {
-      T_freeze = f_min(T_freeze_of(c.S_abs()[Na] / c.m()[Na], g.salt_flag), 0.0);
+    if (CFG.lab_snow_flag == 0 || thick_snow <= thick_min / 100.0) {
+      T_freeze = f_min(T_freeze_of(v.S_abs()[Na] / v.m()[Na], CFG.salt_flag), 0.0);
       T_top = T1;
-      flQ1 = g.alpha_flux_instable * (T_top - T2m);
+      flQ1 = CFG.alpha_flux_instable * (T_top - T2m);
       if (flQ1 < 0.0) {
         T_top = f_max(T_freeze, T1);
-        flQ1 = g.alpha_flux_stable * (T_top - T2m);
+        flQ1 = CFG.alpha_flux_stable * (T_top - T2m);
       }
-      if (thick_snow == 0.0 && g.lab_snow_flag == 1 && c.styropor_flag == 1) {  // sub_fl_Q_styropor, mo_thermo_functions.f90:276
+      if (thick_snow == 0.0 && CFG.lab_snow_flag == 1 && c.styropor_flag == 1) {  // sub_fl_Q_styropor, mo_thermo_functions.f90:276
         EVT(c, EV_STYROPOR);
-        flQ1 = flQ1 * g.k_styropor;
+        flQ1 = flQ1 * CFG.k_styropor;
       }
-    } else if (g.lab_snow_flag == 1) {
-      T_freeze = T_freeze_of(SCV(c, SC_S_ABS_SNOW) / SCV(c, SC_M_SNOW), g.salt_flag);
+    } else if (CFG.lab_snow_flag == 1) {
+      T_freeze = T_freeze_of(SCV(c, SC_S_ABS_SNOW) / SCV(c, SC_M_SNOW), CFG.salt_flag);
       T_top = SCV(c, SC_T_SNOW);
-      double temp1 = g.alpha_flux_instable * (T_top - T2m);
+      double temp1 = CFG.alpha_flux_instable * (T_top - T2m);
       if (temp1 >= 0.0) {
         if (thick_snow >= thick_min) {
           fl_q_snow = temp1;
@@ -188,7 +190,7 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
           flQ1 = 0.0;
         }
       } else {
-        temp1 = g.alpha_flux_stable * (T_top - T2m);
+        temp1 = CFG.alpha_flux_stable * (T_top - T2m);
         if (thick_snow >= thick_min) {
           fl_q_snow = temp1;
           flQ1 = fl_Q_snow_ice(SCV(c, SC_M_SNOW), thick_snow, SCV(c, SC_T_SNOW), ps1, pl1, th1, T1);
@@ -201,8 +203,8 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
   }
 
   const double fl_q_bottom = SCV(c, SC_FL_Q_BOTTOM);
-  c.fl_Q()[1] = flQ1;
-  c.fl_Q()[Na + 1] = fl_q_bottom;  // :262 (every step: it is the entry that stays behind when N_active shrinks)
+  v.fl_Q()[1] = flQ1;
+  v.fl_Q()[Na + 1] = fl_q_bottom;  // :262 (every step: it is the entry that stays behind when N_active shrinks)
 
   // :269-285 in one forward pass: energy sums (forward order), inter-layer fluxes, explicit update.
   double temp1 = 0.0, temp2 = 0.0;
@@ -217,28 +219,28 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
     for (int k = 1; k <= Na; k++) {
       if (k + 1 + SAMSIM_PF <= Na) {
         const int kp = k + 1 + SAMSIM_PF;
-        c.psi_s().prefetch(kp); c.psi_l().prefetch(kp); c.thick().prefetch(kp); c.T().prefetch(kp);
-        c.H_abs().prefetch(kp);
+        v.psi_s().prefetch(kp); v.psi_l().prefetch(kp); v.thick().prefetch(kp); v.T().prefetch(kp);
+        v.H_abs().prefetch(kp);
       }
       double fq_kp1;
       double hr_n = 0.0, T_n = 0.0;
       if (k < Na) {
         // psi_g enters k = psi_s*k_s + psi_l*k_l + psi_g*0._wp only as +-0 (psi_g is a finite volume fraction, k > 0)
-        const double ps_n = c.psi_s()[k + 1], pl_n = c.psi_l()[k + 1], th_n = c.thick()[k + 1];
-        T_n = c.T()[k + 1];
+        const double ps_n = v.psi_s()[k + 1], pl_n = v.psi_l()[k + 1], th_n = v.thick()[k + 1];
+        T_n = v.T()[k + 1];
         hr_n = th_n / (2.0 * (ps_n * k_s + pl_n * k_l + 0.0 * 0.0));
         const double R = hr_k + hr_n;
         fq_kp1 = (T_n - T_k) / R;  // :272-274
-        if (c.want_state) c.fl_Q()[k + 1] = fq_kp1;  // fl_Q(2:N_active) is never read back by the loop body; N_active moves by
+        if (c.want_state) v.fl_Q()[k + 1] = fq_kp1;  // fl_Q(2:N_active) is never read back by the loop body; N_active moves by
                                                      // at most 1 per step, so a stale interior entry is always overwritten by a later :262
       } else {
         fq_kp1 = fl_q_bottom;
       }
-      double H = c.H_abs()[k];
+      double H = v.H_abs()[k];
       temp1 = temp1 + H;                 // :269 sum(H_abs) before the update
       H = H + (fq_kp1 - fq_k) * dt;      // :277-279
       H = H + rad;                       // :282-285 (sic: fl_rad(N_active) for every layer)
-      c.H_abs()[k] = H;
+      v.H_abs()[k] = H;
       temp2 = temp2 + H;                 // :305 sum(H_abs) after the update (layer 1 re-added below if coupling changes it)
       fq_k = fq_kp1;
       hr_k = hr_n; T_k = T_n;
@@ -252,9 +254,9 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
   if (thick_snow >= thick_min / 100.0 && thick_snow < thick_min) {  // :291-295
     EVT(c, EV_HEAT_THIN_SNOW);
     SCV(c, SC_H_ABS_SNOW) = SCV(c, SC_H_ABS_SNOW) - fl_q_snow * dt;
-    double H1 = c.H_abs()[1], phi1 = c.phi()[1];
-    snow_coupling(g, c, H1, phi1, T1, c.m()[1], c.S_bu()[1]);
-    c.H_abs()[1] = H1; c.phi()[1] = phi1; c.T()[1] = T1;
+    double H1 = v.H_abs()[1], phi1 = v.phi()[1];
+    snow_coupling(c, H1, phi1, T1, v.m()[1], v.S_bu()[1]);
+    v.H_abs()[1] = H1; v.phi()[1] = phi1; v.T()[1] = T1;
     layer1_changed = true;
     temp1 = temp1 + fl_q_bottom * dt - fl_q_snow * dt;
   } else if (thick_snow >= thick_min) {  // :296-299
@@ -263,7 +265,7 @@ __device__ __noinline__ void heat_fluxes(const DevCfg& g, Col& c) {
   } else {
     temp1 = temp1 + fl_q_bottom * dt - flQ1 * dt;  // :302
   }
-  if (layer1_changed) temp2 = sum_fwd(c.H_abs(), 1, Na);  // forward order requires a fresh pass when H_abs(1) moved
+  if (layer1_changed) temp2 = sum_fwd(v.H_abs(), 1, Na);  // forward order requires a fresh pass when H_abs(1) moved
   temp2 = temp2 + SCV(c, SC_H_ABS_SNOW);
   if (fabs((temp1 - temp2) / dt) > 0.00001) c.status = 431;  // :307-310
 }
@@ -297,7 +299,8 @@ struct SnapOut {
   int col;
 };
 
-__device__ __noinline__ void write_snapshot(const DevCfg& g, const Col& c, const SnapOut& s) {
+__device__ __noinline__ void write_snapshot(const Col& c, const SnapOut& s) {
+  const View v = c;
   if (s.scalars) {
     const int ids[19] = {SC_FREEBOARD, SC_THICK_SNOW, SC_T_SNOW, SC_PSI_L_SNOW, SC_PSI_S_SNOW, SC_ENERGY_STORED,
                          SC_FRESHWATER, SC_TOTAL_RESIST, SC_THICKNESS, SC_BULK_SALIN, SC_GRAV_DRAIN, SC_GRAV_SALT,
@@ -308,30 +311,30 @@ __device__ __noinline__ void write_snapshot(const DevCfg& g, const Col& c, const
     s.scalars[(size_t)19 * s.ncol_pad + s.col] = (double)c.N_active;
   }
   if (s.arrays) {
-    const int N = g.Nlayer;
+    const int N = CFG.Nlayer;
     const size_t LS = (size_t)(N + 2);
     const int src[10] = {AR_T, AR_PSI_S, AR_THICK, AR_S_BU, AR_RAY, AR_PSI_L, AR_PERM, AR_FLUSH_V, AR_FLUSH_H, AR_PSI_G};
     SAMSIM_LOOP
     for (int a = 0; a < 10; a++) {
       double* dst = s.arrays + ((size_t)a * LS) * s.ncol_pad + s.col;
-      const Lay from = c.A(src[a]);
+      const Lay from = v.A(src[a]);
       const int n = (a == 4) ? N - 1 : N;
       SAMSIM_LOOP
       for (int k = 1; k <= n; k++) dst[(size_t)k * s.ncol_pad] = from[k];
     }
-    for (int q = 0; q < g.n_bgc; q++) {  // output_bgc, mo_output.f90:165-186
+    for (int q = 0; q < CFG.n_bgc; q++) {  // output_bgc, mo_output.f90:165-186
       double* bu = s.arrays + ((size_t)(10 + 2 * q) * LS) * s.ncol_pad + s.col;
       double* br = s.arrays + ((size_t)(11 + 2 * q) * LS) * s.ncol_pad + s.col;
-      const Lay x = c.bgc(q);
+      const Lay x = v.bgc(q);
       const double bottom = c.sc[SC_BGC_BOTTOM1 + q];
       SAMSIM_LOOP
       for (int k = 1; k <= N; k++) {
         double vbu = bottom, vbr = bottom;
         if (k <= c.N_active) {
-          const double mk = c.m()[k];
+          const double mk = v.m()[k];
           if (mk != 0.0) {
             vbu = x[k] / mk;
-            const double pl = c.psi_l()[k], th = c.thick()[k];
+            const double pl = v.psi_l()[k], th = v.thick()[k];
             vbr = (pl != 0.0 && th != 0.0) ? x[k] / pl / th / rho_l : 0.0;
           } else {
             vbu = 0.0; vbr = 0.0;
@@ -353,20 +356,21 @@ __device__ __noinline__ void write_snapshot(const DevCfg& g, const Col& c, const
 //     nor psi_g, and expulsion_flux reads neither H_abs nor S_abs;
 //   * mass_transfer(k) needs S_bu(k-1), S_bu(k+1) from S4 -> the old value is carried / not yet overwritten;
 //   * S7 overwrites S_bu(k) only after mass_transfer(k) and (through the carry) mass_transfer(k+1) used the old one.
-__device__ __noinline__ void fused_thermo_expulsion(const DevCfg& g, Col& c) {
+__device__ __noinline__ void fused_thermo_expulsion(Col& c) {
+  const View v = c;
   const int Na = c.N_active;
   const bool transfer = (c.i != 1);
   const double T_bottom = SCV(c, SC_T_BOTTOM), S_bu_bottom = SCV(c, SC_S_BU_BOTTOM);
   // layer 1 is always recomputed; its first guess is T(2) of the (valid) sweep, T_bottom when it is the only layer
   double T_k, sbu_k, phi_k;
-  double m_k = c.m()[1];
+  double m_k = v.m()[1];
   {
-    sbu_k = c.S_abs()[1] / m_k;
-    const double H = c.H_abs()[1] / m_k;
-    phi_k = c.phi()[1];
-    const double T_test = (Na >= 2) ? c.T()[2] : T_bottom;
-    getT(g, H, sbu_k, T_test, T_k, phi_k, c.status, c.ev1);
-    c.T()[1] = T_k; c.phi()[1] = phi_k;
+    sbu_k = v.S_abs()[1] / m_k;
+    const double H = v.H_abs()[1] / m_k;
+    phi_k = v.phi()[1];
+    const double T_test = (Na >= 2) ? v.T()[2] : T_bottom;
+    getT(H, sbu_k, T_test, T_k, phi_k, c.status, c.ev1);
+    v.T()[1] = T_k; v.phi()[1] = phi_k;
   }
   double T_km1 = 0.0, Sbu_km1 = 0.0, Sabs_km1 = 0.0, f0 = 0.0;
   // func_freeboard memo: forward totals and the exact suffix sums for the waterline layer of the previous step
@@ -376,21 +380,21 @@ __device__ __noinline__ void fused_thermo_expulsion(const DevCfg& g, Col& c) {
   SAMSIM_LOOP
   for (int k = 1; k <= Na; k++) {
     if (k + SAMSIM_PF <= Na) {
-      c.T().prefetch(k + SAMSIM_PF); c.S_bu().prefetch(k + SAMSIM_PF); c.phi().prefetch(k + SAMSIM_PF);
-      c.m().prefetch(k + SAMSIM_PF); c.thick().prefetch(k + SAMSIM_PF); c.S_abs().prefetch(k + SAMSIM_PF);
-      c.H_abs().prefetch(k + SAMSIM_PF);
+      v.T().prefetch(k + SAMSIM_PF); v.S_bu().prefetch(k + SAMSIM_PF); v.phi().prefetch(k + SAMSIM_PF);
+      v.m().prefetch(k + SAMSIM_PF); v.thick().prefetch(k + SAMSIM_PF); v.S_abs().prefetch(k + SAMSIM_PF);
+      v.H_abs().prefetch(k + SAMSIM_PF);
     }
-    const double thk = c.thick()[k];
+    const double thk = v.thick()[k];
     // neighbour below: old T, S_bu (S4 values) and the not yet updated S_abs
     double T_kp1, Sbu_kp1, Sabs_kp1, phi_kp1 = 0.0, m_kp1 = 0.0;
     if (k < Na) {
-      T_kp1 = c.T()[k + 1]; Sbu_kp1 = c.S_bu()[k + 1]; Sabs_kp1 = c.S_abs()[k + 1];
-      phi_kp1 = c.phi()[k + 1]; m_kp1 = c.m()[k + 1];
+      T_kp1 = v.T()[k + 1]; Sbu_kp1 = v.S_bu()[k + 1]; Sabs_kp1 = v.S_abs()[k + 1];
+      phi_kp1 = v.phi()[k + 1]; m_kp1 = v.m()[k + 1];
     } else {
       T_kp1 = T_bottom; Sbu_kp1 = S_bu_bottom; Sabs_kp1 = S_bu_bottom * 2000.0;
     }
     // S4: brine salinity and volume fractions
-    c.S_br()[k] = S_br_of(g, T_k, sbu_k);
+    v.S_br()[k] = S_br_of(T_k, sbu_k);
     double ps, pl, pg, vex;
     expulsion(phi_k, thk, m_k, ps, pl, pg, vex);
     // expulsion_flux, mo_mass.f90:121-134
@@ -403,50 +407,51 @@ __device__ __noinline__ void fused_thermo_expulsion(const DevCfg& g, Col& c) {
       f1 = -f_max((vex - pg * thk) * rho_l, 0.0);
       pg = f_max((pg * thk - vex) / thk, 0.0);
     }
-    c.psi_s()[k] = ps; c.psi_l()[k] = pl; c.psi_g()[k] = pg;
+    v.psi_s()[k] = ps; v.psi_l()[k] = pl; v.psi_g()[k] = pg;
     fbA = fbA + ps * thk;
     fbG = fbG + pg * thk;
     if (ks && k > ks) { fbAs = fbAs + ps * thk; fbGs = fbGs + pg * thk; }
     min_ps = f_min(min_ps, ps);
     const double m_new = m_k + f1 - f0;
-    c.m()[k] = m_new;
+    v.m()[k] = m_new;
     // mass_transfer layer k, then S7
-    double S = c.S_abs()[k];
+    double S = v.S_abs()[k];
     if (transfer) {
-      double H = c.H_abs()[k];
-      mass_transfer_layer(g, f1, f0, T_km1, Sbu_km1, Sabs_km1, T_k, sbu_k, T_kp1, Sbu_kp1, Sabs_kp1, H, S);
-      c.H_abs()[k] = H;
-      c.S_abs()[k] = S;
+      double H = v.H_abs()[k];
+      mass_transfer_layer(f1, f0, T_km1, Sbu_km1, Sabs_km1, T_k, sbu_k, T_kp1, Sbu_kp1, Sabs_kp1, H, S);
+      v.H_abs()[k] = H;
+      v.S_abs()[k] = S;
     }
-    c.S_bu()[k] = S / m_new;
-    if (g.n_bgc) {  // mo_grotz.f90:316-320: fl_brine_bgc(k,k+1) = -fl_m(k+1); the other cells start the step empty
-      c.A(AR_FB_D)[k] = transfer ? -f1 : 0.0;
-      c.A(AR_FB_U)[k] = 0.0; c.A(AR_FB_A)[k] = 0.0; c.A(AR_FB_O)[k] = 0.0;
+    v.S_bu()[k] = S / m_new;
+    if (CFG.n_bgc) {  // mo_grotz.f90:316-320: fl_brine_bgc(k,k+1) = -fl_m(k+1); the other cells start the step empty
+      v.A(AR_FB_D)[k] = transfer ? -f1 : 0.0;
+      v.A(AR_FB_U)[k] = 0.0; v.A(AR_FB_A)[k] = 0.0; v.A(AR_FB_O)[k] = 0.0;
     }
     T_km1 = T_k; Sbu_km1 = sbu_k; Sabs_km1 = S;
     T_k = T_kp1; sbu_k = Sbu_kp1; phi_k = phi_kp1; m_k = m_kp1;
     f0 = f1;
   }
-  c.fb.tot_valid = true; c.fb.t1 = c.thick()[1]; c.fb.A = fbA; c.fb.G = fbG;
+  c.fb.tot_valid = true; c.fb.t1 = v.thick()[1]; c.fb.A = fbA; c.fb.G = fbG;
   c.fb.suf_valid = (ks != 0); c.fb.ks = ks; c.fb.As = fbAs; c.fb.Gs = fbGs;
   c.fb.res_valid = false;
   c.min_psi_s = min_ps;
 }
 
-__device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing& f, bool want_diag, const SnapOut& snap) {
-  const double dt = g.dt;
-  const int N = g.Nlayer;
+__device__ __noinline__ void column_step(Col& c, const Forcing& f, bool want_diag, const SnapOut& snap) {
+  const View v = c;
+  const double dt = CFG.dt;
+  const int N = CFG.Nlayer;
   c.i = c.i + 1;
   c.want_state = want_diag;
-  const bool output_step = (c.n_time_out == g.i_time_out || c.i == 1);
+  const bool output_step = (c.n_time_out == CFG.i_time_out || c.i == 1);
   const bool fused = c.thermo_valid;  // S4+S5+S7 as one forward pass (bit-identical, see fused_thermo_expulsion)
 
   if (c.status == 0) {  // ===== phase 0 =====
   // ---- S0 :192-223 (only observable at S8 or through get_scalar after the launch) ----
-  if (output_step || want_diag) vital_signs(g, c);
+  if (output_step || want_diag) vital_signs(c);
 
   // ---- S1 forcing :229-246 ----
-  if (g.atmoflux_flag == 2) {
+  if (CFG.atmoflux_flag == 2) {
     if (c.time > time_input(c.time_counter)) c.time_counter = c.time_counter + 1;
     const int tc = c.time_counter;
     c.ftime1 = time_input(tc);
@@ -466,7 +471,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     }
   }
   long long lab_idx = 0;
-  if (g.boundflux_flag == 3 && g.lab_snow_flag == 1) {  // :244-246
+  if (CFG.boundflux_flag == 3 && CFG.lab_snow_flag == 1) {  // :244-246
     lab_idx = (long long)floor(1 + c.time / dt);
     SCV(c, SC_SOLID_PRECIP) = lab_rec(f, 1, lab_idx);
   }
@@ -474,22 +479,22 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   // ---- S2 snow fall :251-265 ----
   {
     const double lp = SCV(c, SC_LIQUID_PRECIP), sp = SCV(c, SC_SOLID_PRECIP);
-    if (f_max(lp, sp) > 0.0 && (g.precip_flag == 1 || g.precip_flag == 0)) {
-      const bool have_solid = (g.precip_flag == 0);
+    if (f_max(lp, sp) > 0.0 && (CFG.precip_flag == 1 || CFG.precip_flag == 0)) {
+      const bool have_solid = (CFG.precip_flag == 0);
       if (c.N_active > 1) {
         EVT(c, EV_SNOW_PRECIP);
         snow_precip(c, dt, lp, SCV(c, SC_T2M), have_solid, sp);
       } else if (c.N_active == 1) {
         EVT(c, EV_SNOW_PRECIP_0);
-        double H1 = c.H_abs()[1], S1 = c.S_abs()[1];
-        snow_precip_0(H1, S1, c.m()[1], c.T()[1], dt, lp, SCV(c, SC_T2M), have_solid, sp);
-        c.H_abs()[1] = H1; c.S_abs()[1] = S1;
+        double H1 = v.H_abs()[1], S1 = v.S_abs()[1];
+        snow_precip_0(H1, S1, v.m()[1], v.T()[1], dt, lp, SCV(c, SC_T2M), have_solid, sp);
+        v.H_abs()[1] = H1; v.S_abs()[1] = S1;
       }
     }
   }
 
   // ---- S3 snow thermodynamics :273-292 ----
-  snow_block(g, c);
+  snow_block(c);
 
   }
   SAMSIM_PHASE_SYNC();
@@ -504,7 +509,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   // same T, phi: those layers skip the Newton iterations.  Layer 1 (snow, precipitation, melt water) is always
   // recomputed.  Expulsion depends on phi from S18, so it is evaluated every step.
   if (fused) {
-    fused_thermo_expulsion(g, c);
+    fused_thermo_expulsion(c);
   } else {
     fb_reset(c);
     c.min_psi_s = 1e300;
@@ -512,7 +517,7 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     const bool reuse = false;
 #if SAMSIM_SYNC >= 2
     SAMSIM_LOOP
-    for (int k = g.Nlayer; k >= 1; k--) {
+    for (int k = CFG.Nlayer; k >= 1; k--) {
       SAMSIM_LAYER_SYNC();
       if (k > c.N_active || c.status != 0) continue;
 #else
@@ -520,26 +525,26 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     for (int k = c.N_active; k >= 1; k--) {
 #endif
       if (k - SAMSIM_PF >= 1) {
-        c.m().prefetch(k - SAMSIM_PF); c.thick().prefetch(k - SAMSIM_PF);
-        if (reuse) { c.T().prefetch(k - SAMSIM_PF); c.phi().prefetch(k - SAMSIM_PF); c.S_bu().prefetch(k - SAMSIM_PF); }
-        else { c.S_abs().prefetch(k - SAMSIM_PF); c.H_abs().prefetch(k - SAMSIM_PF); }
+        v.m().prefetch(k - SAMSIM_PF); v.thick().prefetch(k - SAMSIM_PF);
+        if (reuse) { v.T().prefetch(k - SAMSIM_PF); v.phi().prefetch(k - SAMSIM_PF); v.S_bu().prefetch(k - SAMSIM_PF); }
+        else { v.S_abs().prefetch(k - SAMSIM_PF); v.H_abs().prefetch(k - SAMSIM_PF); }
       }
-      const double mk = c.m()[k];
+      const double mk = v.m()[k];
       double sbu, T, phi;
       if (reuse && k >= 2) {
-        sbu = c.S_bu()[k]; T = c.T()[k]; phi = c.phi()[k];
+        sbu = v.S_bu()[k]; T = v.T()[k]; phi = v.phi()[k];
       } else {
-        sbu = c.S_abs()[k] / mk;
-        const double H = c.H_abs()[k] / mk;
-        phi = c.phi()[k];
-        getT(g, H, sbu, T_test, T, phi, c.status, c.ev1);
-        c.S_bu()[k] = sbu; c.T()[k] = T; c.phi()[k] = phi;
+        sbu = v.S_abs()[k] / mk;
+        const double H = v.H_abs()[k] / mk;
+        phi = v.phi()[k];
+        getT(H, sbu, T_test, T, phi, c.status, c.ev1);
+        v.S_bu()[k] = sbu; v.T()[k] = T; v.phi()[k] = phi;
       }
       T_test = T;
-      c.S_br()[k] = S_br_of(g, T, sbu);
+      v.S_br()[k] = S_br_of(T, sbu);
       double ps, pl, pg, vex;
-      expulsion(phi, c.thick()[k], mk, ps, pl, pg, vex);
-      c.psi_s()[k] = ps; c.psi_l()[k] = pl; c.psi_g()[k] = pg; c.V_ex()[k] = vex;
+      expulsion(phi, v.thick()[k], mk, ps, pl, pg, vex);
+      v.psi_s()[k] = ps; v.psi_l()[k] = pl; v.psi_g()[k] = pg; v.V_ex()[k] = vex;
       c.min_psi_s = f_min(c.min_psi_s, ps);
     }
     }
@@ -550,53 +555,53 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   // ---- S5 expulsion_flux (mo_mass.f90:112-136) then mass_transfer (skipped at i == 1) :312-321 ----
   if (!fused) {
     const int Na = c.N_active;
-    Lay fl_m = c.fl_m();
+    Lay fl_m = v.fl_m();
     double f0 = 0.0;
     fl_m[1] = 0.0;
     SAMSIM_LOOP
     for (int k = 1; k <= Na; k++) {
       double f1;
-      const double vex = c.V_ex()[k];
+      const double vex = v.V_ex()[k];
       if (k == 1) {
         f1 = -vex * rho_l;
       } else {
-        const double pg = c.psi_g()[k];
+        const double pg = v.psi_g()[k];
         if (pg < SAMSIM_F32(0.001)) {
           f1 = -vex * rho_l + f0;
         } else {
-          const double thk = c.thick()[k];
+          const double thk = v.thick()[k];
           f1 = -f_max((vex - pg * thk) * rho_l, 0.0);
-          c.psi_g()[k] = f_max((pg * thk - vex) / thk, 0.0);
+          v.psi_g()[k] = f_max((pg * thk - vex) / thk, 0.0);
         }
       }
       fl_m[k + 1] = f1;
-      c.m()[k] = c.m()[k] + f1 - f0;
+      v.m()[k] = v.m()[k] + f1 - f0;
       f0 = f1;
     }
-    if (c.i != 1) mass_transfer(g, c, fl_m, c.S_bu());
-    if (g.n_bgc) {  // :316-320
+    if (c.i != 1) mass_transfer(c, fl_m, v.S_bu());
+    if (CFG.n_bgc) {  // :316-320
       SAMSIM_LOOP
       for (int k = 1; k <= Na; k++) {
-        c.A(AR_FB_D)[k] = (c.i != 1) ? -fl_m[k + 1] : 0.0;
-        c.A(AR_FB_U)[k] = 0.0; c.A(AR_FB_A)[k] = 0.0; c.A(AR_FB_O)[k] = 0.0;
+        v.A(AR_FB_D)[k] = (c.i != 1) ? -fl_m[k + 1] : 0.0;
+        v.A(AR_FB_U)[k] = 0.0; v.A(AR_FB_A)[k] = 0.0; v.A(AR_FB_O)[k] = 0.0;
       }
     }
     // ---- S7 :333-335 ----
     SAMSIM_LOOP
-    for (int k = Na; k >= 1; k--) c.S_bu()[k] = c.S_abs()[k] / c.m()[k];
+    for (int k = Na; k >= 1; k--) v.S_bu()[k] = v.S_abs()[k] / v.m()[k];
   }
 
   c.fb_x = 0.0;
   // ---- S8 output :340-398 ----
   if (output_step) {
-    SCV(c, SC_FREEBOARD) = (c.N_active > 1) ? freeboard_of(g, c) : 0.0;
-    if (g.grav_flag == 2) {
+    SCV(c, SC_FREEBOARD) = (c.N_active > 1) ? freeboard_of(c) : 0.0;
+    if (CFG.grav_flag == 2) {
       if (SCV(c, SC_GRAV_DRAIN) == 0.0) SCV(c, SC_GRAV_TEMP) = 0.0;
       else SCV(c, SC_GRAV_TEMP) = SCV(c, SC_GRAV_TEMP) / SCV(c, SC_GRAV_DRAIN);
-      SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) / g.time_out;
-      SCV(c, SC_GRAV_DRAIN) = SCV(c, SC_GRAV_DRAIN) / g.time_out;
+      SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) / CFG.time_out;
+      SCV(c, SC_GRAV_DRAIN) = SCV(c, SC_GRAV_DRAIN) / CFG.time_out;
     }
-    write_snapshot(g, c, snap);
+    write_snapshot(c, snap);
     SCV(c, SC_GRAV_DRAIN) = 0.0; SCV(c, SC_GRAV_SALT) = 0.0; SCV(c, SC_GRAV_TEMP) = 0.0;
     SCV(c, SC_MTO1) = 0.0; SCV(c, SC_MTO2) = 0.0; SCV(c, SC_MTO3) = 0.0;
     c.n_time_out = 0;
@@ -610,43 +615,43 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   // ---- S9 gas in the lowest layer :405-410 ----
   {
     const int Na = c.N_active;
-    const double pg = c.psi_g()[Na];
+    const double pg = v.psi_g()[Na];
     if (pg > 0.0) {
       EVT(c, EV_GAS_REFILL);
-      const double temp2 = pg * c.thick()[Na] * rho_l;
+      const double temp2 = pg * v.thick()[Na] * rho_l;
       c.fb.res_valid = false;
-      c.m()[Na] = c.m()[Na] + temp2;
-      c.S_abs()[Na] = c.S_abs()[Na] + temp2 * SCV(c, SC_S_BU_BOTTOM);
-      c.H_abs()[Na] = c.H_abs()[Na] + temp2 * c_l * SCV(c, SC_T_BOTTOM);
+      v.m()[Na] = v.m()[Na] + temp2;
+      v.S_abs()[Na] = v.S_abs()[Na] + temp2 * SCV(c, SC_S_BU_BOTTOM);
+      v.H_abs()[Na] = v.H_abs()[Na] + temp2 * c_l * SCV(c, SC_T_BOTTOM);
     }
   }
 
   // ---- S10 thin snow coupling :418-420 ----
-  if (SCV(c, SC_M_SNOW) > 0.0 && SCV(c, SC_THICK_SNOW) < g.thick_min) {
-    double H1 = c.H_abs()[1], phi1 = c.phi()[1], T1 = c.T()[1];
-    snow_coupling(g, c, H1, phi1, T1, c.m()[1], c.S_bu()[1]);
-    c.H_abs()[1] = H1; c.phi()[1] = phi1; c.T()[1] = T1;
+  if (SCV(c, SC_M_SNOW) > 0.0 && SCV(c, SC_THICK_SNOW) < CFG.thick_min) {
+    double H1 = v.H_abs()[1], phi1 = v.phi()[1], T1 = v.T()[1];
+    snow_coupling(c, H1, phi1, T1, v.m()[1], v.S_bu()[1]);
+    v.H_abs()[1] = H1; v.phi()[1] = phi1; v.T()[1] = T1;
     }
 
   // ---- S11 flooding :428-445 ----
-  if (c.N_active > 1 && g.flood_flag > 1) {
-    SCV(c, SC_FREEBOARD) = freeboard_of(g, c);
+  if (c.N_active > 1 && CFG.flood_flag > 1) {
+    SCV(c, SC_FREEBOARD) = freeboard_of(c);
     if (SCV(c, SC_FREEBOARD) < 0.0) {
-      if (g.flood_flag == 2) { flood(g, c); fb_reset(c); }
-      else if (g.flood_flag == 3 && SCV(c, SC_FREEBOARD) < neg_free) { flood_simple(c); fb_reset(c); }
+      if (CFG.flood_flag == 2) { flood(c); fb_reset(c); }
+      else if (CFG.flood_flag == 3 && SCV(c, SC_FREEBOARD) < neg_free) { flood_simple(c); fb_reset(c); }
     }
   }
 
   // ---- S12 turbulence (sub_turb_flux, mo_functions.f90:347-363) :450-457 ----
-  if (g.turb_flag == 2) {
+  if (CFG.turb_flag == 2) {
     EVT(c, EV_TURB);
     const int Na = c.N_active;
-    const double S = c.S_abs()[Na], mNa = c.m()[Na];
-    const double turb = Turb_A * det_exp(Turb_B * (-density_of(SCV(c, SC_T_BOTTOM), SCV(c, SC_S_BU_BOTTOM)) + density_of(c.T()[Na], S / mNa))) * dt;
-    c.S_abs()[Na] = S - turb * (S / mNa - SCV(c, SC_S_BU_BOTTOM));
-    for (int q = 0; q < g.n_bgc; q++) {  // mo_functions.f90:357-359
-      const double b = c.bgc(q)[Na];
-      c.bgc(q)[Na] = b - turb * (b / mNa - SCV(c, SC_BGC_BOTTOM1 + q));
+    const double S = v.S_abs()[Na], mNa = v.m()[Na];
+    const double turb = Turb_A * det_exp(Turb_B * (-density_of(SCV(c, SC_T_BOTTOM), SCV(c, SC_S_BU_BOTTOM)) + density_of(v.T()[Na], S / mNa))) * dt;
+    v.S_abs()[Na] = S - turb * (S / mNa - SCV(c, SC_S_BU_BOTTOM));
+    for (int q = 0; q < CFG.n_bgc; q++) {  // mo_functions.f90:357-359
+      const double b = v.bgc(q)[Na];
+      v.bgc(q)[Na] = b - turb * (b / mNa - SCV(c, SC_BGC_BOTTOM1 + q));
     }
   }
 
@@ -654,65 +659,65 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   SAMSIM_PHASE_SYNC();
   if (c.status == 0) {  // ===== phase 4 =====
   // ---- S13 gravity drainage :463-477 ----
-  if (g.grav_flag == 2 && c.N_active > 1) {
+  if (CFG.grav_flag == 2 && c.N_active > 1) {
     // ray(1:N-1) is observable through the S8 record of the next step (n_time_out was already advanced by S8 above)
     // and through get_array after the launch; otherwise only layers that can drain need their exact value
-    const bool next_step_outputs = (c.n_time_out == g.i_time_out);
-    grav_drain(g, c, c.want_state || next_step_outputs);
+    const bool next_step_outputs = (c.n_time_out == CFG.i_time_out);
+    grav_drain(c, c.want_state || next_step_outputs);
   }
-  else if (g.grav_flag == 3 && c.N_active > 1) { EVT(c, EV_GRAV_DRAIN_SIMPLE); grav_drain_simple(g, c); }
+  else if (CFG.grav_flag == 3 && c.N_active > 1) { EVT(c, EV_GRAV_DRAIN_SIMPLE); grav_drain_simple(c); }
 
   // ---- S14 prescribed salinity profile :482-497 (prescribe_flag 2) ----
-  if (g.prescribe_flag == 2) {
+  if (CFG.prescribe_flag == 2) {
     EVT(c, EV_PRESCRIBE);
     const int Na = c.N_active;
     const double Sb = SCV(c, SC_S_BU_BOTTOM);
     int k = Na;
-    while (k > 1 && sum_fwd(c.thick(), k, Na) < 0.15) {
-      c.S_bu()[k] = Sb - sum_fwd(c.thick(), k, Na) / 0.15 * (Sb - 4.0);
+    while (k > 1 && sum_fwd(v.thick(), k, Na) < 0.15) {
+      v.S_bu()[k] = Sb - sum_fwd(v.thick(), k, Na) / 0.15 * (Sb - 4.0);
       k = k - 1;
     }
-    while (k > 1 && sum_fwd(c.thick(), k, Na) >= 0.15) {
-      c.S_bu()[k] = 4.0 - 4.0 * (sum_fwd(c.thick(), k, Na) - 0.15) / (sum_fwd(c.thick(), 1, Na) - 0.15);
+    while (k > 1 && sum_fwd(v.thick(), k, Na) >= 0.15) {
+      v.S_bu()[k] = 4.0 - 4.0 * (sum_fwd(v.thick(), k, Na) - 0.15) / (sum_fwd(v.thick(), 1, Na) - 0.15);
       k = k - 1;
-      c.S_bu()[1] = 0.0;
+      v.S_bu()[1] = 0.0;
     }
-    c.S_bu()[Na] = Sb;
+    v.S_bu()[Na] = Sb;
     SAMSIM_LOOP
-    for (int kk = 1; kk <= N; kk++) c.S_abs()[kk] = c.S_bu()[kk] * c.m()[kk];  // S_abs = S_bu*m, whole arrays
+    for (int kk = 1; kk <= N; kk++) v.S_abs()[kk] = v.S_bu()[kk] * v.m()[kk];  // S_abs = S_bu*m, whole arrays
   }
 
   }
   SAMSIM_PHASE_SYNC();
   if (c.status == 0) {  // ===== phase 5 =====
   // ---- S15 testcase hooks :503-563 ----
-  if (g.testcase == 1) {  // sub_test1, mo_testcase_specifics.f90:42-89
+  if (CFG.testcase == 1) {  // sub_test1, mo_testcase_specifics.f90:42-89
     const double j = rint(c.time / 43200.0);
     if (j >= 1.0 && j <= 20.0 && fabs(c.time - 12.0 * j * 3600.0) < SAMSIM_F32(0.01))
       SCV(c, SC_T_TOP) = (((int)j) & 1) ? SCV(c, SC_TTOP_COLD) : SCV(c, SC_TTOP_WARM);
-  } else if (g.testcase >= 101 && g.testcase <= 105) {  // :521-530
+  } else if (CFG.testcase >= 101 && CFG.testcase <= 105) {  // :521-530
     const long long idx = (long long)floor(1 + c.time / dt);
-    const double Sb = c.S_bu()[c.N_active + 1];
+    const double Sb = v.S_bu()[c.N_active + 1];
     SCV(c, SC_T2M) = lab_rec(f, 0, idx);
     SCV(c, SC_SOLID_PRECIP) = lab_rec(f, 1, idx);
     SCV(c, SC_FL_Q_BOTTOM) = lab_rec(f, 2, idx);
     SCV(c, SC_T_BOTTOM) = -SAMSIM_F32(0.0575) * Sb + SAMSIM_F32(1.710523e-3) * det_pow(Sb, 3.0 / 2.0) -
-                          SAMSIM_F32(2.154996e-4) * P2(Sb) - SAMSIM_F32(7.53e-4) * sum_fwd(c.thick(), 1, c.N_active - 1);
+                          SAMSIM_F32(2.154996e-4) * P2(Sb) - SAMSIM_F32(7.53e-4) * sum_fwd(v.thick(), 1, c.N_active - 1);
     c.styropor_flag = (int)lab_rec(f, 3, idx);
-  } else if (g.testcase == 4 || g.testcase == 7) {  // sub_test4, mo_testcase_specifics.f90:197-202
+  } else if (CFG.testcase == 4 || CFG.testcase == 7) {  // sub_test4, mo_testcase_specifics.f90:197-202
     const double amp = SCV(c, SC_OFLUX_AMP);
     SCV(c, SC_FL_Q_BOTTOM) = -amp * det_sin(c.time * (2.0 * pi_sp) / (86400.0 * 365.0)) + amp;
-  } else if (g.testcase == 2) {  // sub_test2, mo_testcase_specifics.f90:92-101
+  } else if (CFG.testcase == 2) {  // sub_test2, mo_testcase_specifics.f90:92-101
     if (c.time > 86400.0 * 25.0) SCV(c, SC_T2M) = 15.0;
     else if (c.time > 86400.0 * 15.0) SCV(c, SC_T2M) = 1.0;
-  } else if (g.testcase == 9) {  // sub_test9, :105-116
+  } else if (CFG.testcase == 9) {  // sub_test9, :105-116
     if (c.time < (19.75 * 3600.0)) SCV(c, SC_T2M) = 0.0;
     else if (c.time < (86400.0 * 3.0 + 2.25 * 3600.0)) SCV(c, SC_T2M) = -15.0;
     else SCV(c, SC_T2M) = 1.0;
-  } else if (g.testcase == 3) {  // sub_test3, :170-185
+  } else if (CFG.testcase == 3) {  // sub_test3, :170-185
     SCV(c, SC_LIQUID_PRECIP) = 0.0;
     SCV(c, SC_SOLID_PRECIP) = 0.15 / 86400.0 / 356.0;
-  } else if (g.testcase == 6) {  // sub_test6, :218-243
+  } else if (CFG.testcase == 6) {  // sub_test6, :218-243
     const double t = c.time;
     if (t > 1714.0 * 60.0) SCV(c, SC_T2M) = -19.0;
     else if (t > 1676.0 * 60.0) SCV(c, SC_T2M) = -5.0;
@@ -722,23 +727,23 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     else if (t > 1349.0 * 60.0) SCV(c, SC_T2M) = -5.0;
     else if (t > 1160.0 * 60.0) SCV(c, SC_T2M) = -18.0;
     else if (t > 1100.0 * 60.0) SCV(c, SC_T2M) = -5.0;
-  } else if (g.testcase == 5 && c.i == 2) {  // mo_grotz.f90:541-542
+  } else if (CFG.testcase == 5 && c.i == 2) {  // mo_grotz.f90:541-542
     SAMSIM_LOOP
-    for (int k = 1; k <= N; k++) c.S_abs()[k] = 5.0 * c.m()[k];
+    for (int k = 1; k <= N; k++) v.S_abs()[k] = 5.0 * v.m()[k];
   }
 
   // ---- S16 tank :573-578 ----
-  if (g.tank_flag == 2) {
+  if (CFG.tank_flag == 2) {
     EVT(c, EV_TANK);
-    SCV(c, SC_S_BU_BOTTOM) = (SCV(c, SC_S_TOTAL) - sum_fwd(c.S_abs(), 1, c.N_active)) / (g.m_total - sum_fwd(c.m(), 1, c.N_active));
-    if (g.n_bgc) {  // :575-577 (sic: every tracer gets the value computed from tracer 1)
-      const double v = (SCV(c, SC_BGC_TOTAL1) - sum_fwd(c.bgc(0), 1, c.N_active)) / (g.m_total - sum_fwd(c.m(), 1, c.N_active));
-      for (int q = 0; q < g.n_bgc; q++) SCV(c, SC_BGC_BOTTOM1 + q) = v;
+    SCV(c, SC_S_BU_BOTTOM) = (SCV(c, SC_S_TOTAL) - sum_fwd(v.S_abs(), 1, c.N_active)) / (CFG.m_total - sum_fwd(v.m(), 1, c.N_active));
+    if (CFG.n_bgc) {  // :575-577 (sic: every tracer gets the value computed from tracer 1)
+      const double vb = (SCV(c, SC_BGC_TOTAL1) - sum_fwd(v.bgc(0), 1, c.N_active)) / (CFG.m_total - sum_fwd(v.m(), 1, c.N_active));
+      for (int q = 0; q < CFG.n_bgc; q++) SCV(c, SC_BGC_BOTTOM1 + q) = vb;
     }
   }
 
   // ---- S17 heat fluxes :584 ----
-  heat_fluxes(g, c);
+  heat_fluxes(c);
 
   }
   SAMSIM_PHASE_SYNC();
@@ -753,23 +758,23 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
     double min_S2 = 1e300;
 #if SAMSIM_SYNC >= 2
     SAMSIM_LOOP
-    for (int k = g.Nlayer; k >= 1; k--) {
+    for (int k = CFG.Nlayer; k >= 1; k--) {
       SAMSIM_LAYER_SYNC();
       if (k > c.N_active || c.status != 0) continue;
 #else
     SAMSIM_LOOP
     for (int k = c.N_active; k >= 1; k--) {
 #endif
-      if (k - SAMSIM_PF >= 1) { c.m().prefetch(k - SAMSIM_PF); c.S_abs().prefetch(k - SAMSIM_PF); c.H_abs().prefetch(k - SAMSIM_PF); c.phi().prefetch(k - SAMSIM_PF); }
-      const double mk = c.m()[k];
-      const double Sk = c.S_abs()[k];
+      if (k - SAMSIM_PF >= 1) { v.m().prefetch(k - SAMSIM_PF); v.S_abs().prefetch(k - SAMSIM_PF); v.H_abs().prefetch(k - SAMSIM_PF); v.phi().prefetch(k - SAMSIM_PF); }
+      const double mk = v.m()[k];
+      const double Sk = v.S_abs()[k];
       if (k >= 2) min_S2 = f_min(min_S2, Sk);
       const double sbu = Sk / mk;
-      const double H = c.H_abs()[k] / mk;
-      double T, phi = c.phi()[k];
-      getT_body(g, H, sbu, T_test, T, phi, c.status, c.ev1);  // inlined: no call, no spills around it in the hot sweep
+      const double H = v.H_abs()[k] / mk;
+      double T, phi = v.phi()[k];
+      getT_body(H, sbu, T_test, T, phi, c.status, c.ev1);  // inlined: no call, no spills around it in the hot sweep
       T_test = T;
-      c.S_bu()[k] = sbu; c.T()[k] = T; c.phi()[k] = phi;
+      v.S_bu()[k] = sbu; v.T()[k] = T; v.phi()[k] = phi;
     }
     c.min_S_abs_2 = min_S2;
     c.thermo_valid = true;  // invalidated below by anything that touches layers >= 2
@@ -780,86 +785,86 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   if (c.status == 0) {  // ===== phase 7 =====
   // ---- S19 snow thermodynamics #2 :600-625 ----
   SCV(c, SC_MELT_THICK_SNOW_OLD) = SCV(c, SC_MELT_THICK_SNOW);
-  snow_block(g, c);
+  snow_block(c);
   SCV(c, SC_MELT_THICK_SNOW) = SCV(c, SC_MELT_THICK_SNOW_OLD) + SCV(c, SC_MELT_THICK_SNOW);
 
   // ---- S20 flushing preparations :632-664 ----
-  if (c.N_active > 1 && g.flush_flag > 2 && (g.boundflux_flag == 2 || g.boundflux_flag == 3)) {
-    SCV(c, SC_T_FREEZE) = T_freeze_of(c.S_abs()[1] / c.m()[1], g.salt_flag);
+  if (c.N_active > 1 && CFG.flush_flag > 2 && (CFG.boundflux_flag == 2 || CFG.boundflux_flag == 3)) {
+    SCV(c, SC_T_FREEZE) = T_freeze_of(v.S_abs()[1] / v.m()[1], CFG.salt_flag);
     SCV(c, SC_MELT_THICK) = 0.0;
-    if (freeboard_of(g, c) > 0.0000000000001) {
-      const double ps1 = c.psi_s()[1];
-      const double T_drive = (g.boundflux_flag == 2) ? SCV(c, SC_T_TOP) : SCV(c, SC_T2M);
+    if (freeboard_of(c) > 0.0000000000001) {
+      const double ps1 = v.psi_s()[1];
+      const double T_drive = (CFG.boundflux_flag == 2) ? SCV(c, SC_T_TOP) : SCV(c, SC_T2M);
       if (ps1 < psi_s_top_min || T_drive >= SCV(c, SC_T_FREEZE)) {
-        double th1 = c.thick()[1];
+        double th1 = v.thick()[1];
         EVT(c, EV_MELT_THICK);
-        if (melt_thick_of(c.psi_l()[1], ps1, c.psi_g()[1], c.T()[1], SCV(c, SC_T_FREEZE), T_drive, c.fl_Q()[1], SCV(c, SC_THICK_SNOW), dt,
-                          SCV(c, SC_MELT_THICK), th1, g.thick_min)) EVT(c, EV_MELT_THICK_GAS);
-        if (g.boundflux_flag == 3) SCV(c, SC_MELT_THICK) = f_max(SCV(c, SC_MELT_THICK), 0.0);
-        if (SCV(c, SC_THICK_SNOW) >= g.thick_min / 100.0 && SCV(c, SC_MELT_THICK) > 0.00000000001 && SCV(c, SC_MELT_THICK_SNOW) == 0.0) {
-          double H1 = c.H_abs()[1], m1 = c.m()[1];
+        if (melt_thick_of(v.psi_l()[1], ps1, v.psi_g()[1], v.T()[1], SCV(c, SC_T_FREEZE), T_drive, v.fl_Q()[1], SCV(c, SC_THICK_SNOW), dt,
+                          SCV(c, SC_MELT_THICK), th1, CFG.thick_min)) EVT(c, EV_MELT_THICK_GAS);
+        if (CFG.boundflux_flag == 3) SCV(c, SC_MELT_THICK) = f_max(SCV(c, SC_MELT_THICK), 0.0);
+        if (SCV(c, SC_THICK_SNOW) >= CFG.thick_min / 100.0 && SCV(c, SC_MELT_THICK) > 0.00000000001 && SCV(c, SC_MELT_THICK_SNOW) == 0.0) {
+          double H1 = v.H_abs()[1], m1 = v.m()[1];
           if (melt_snow(SCV(c, SC_MELT_THICK), th1, SCV(c, SC_THICK_SNOW), H1, SCV(c, SC_H_ABS_SNOW), m1, SCV(c, SC_M_SNOW), SCV(c, SC_PSI_G_SNOW)))
             EVT(c, EV_MELT_SNOW_ALL);
           else
             EVT(c, EV_MELT_SNOW_PART);
-          c.H_abs()[1] = H1; c.m()[1] = m1;
+          v.H_abs()[1] = H1; v.m()[1] = m1;
         }
-        c.thick()[1] = th1;
+        v.thick()[1] = th1;
       }
     }
   }
 
   // ---- S21 flushing :670-737 ----
-  SCV(c, SC_FREEBOARD) = freeboard_of(g, c);
+  SCV(c, SC_FREEBOARD) = freeboard_of(c);
   SCV(c, SC_MTO1) = SCV(c, SC_MTO1) + SCV(c, SC_MELT_THICK);
   SCV(c, SC_MTO2) = SCV(c, SC_MTO2) + SCV(c, SC_MELT_THICK_SNOW);
   SCV(c, SC_MELT_THICK) = SCV(c, SC_MELT_THICK) + SCV(c, SC_MELT_THICK_SNOW);
   if (SCV(c, SC_MELT_THICK_SNOW) > 0.0) {  // :677-685
     EVT(c, EV_SNOW_MELTWATER_TO_ICE);
     const double mts = SCV(c, SC_MELT_THICK_SNOW), T_snow = SCV(c, SC_T_SNOW);
-    const double H1 = c.H_abs()[1] + mts * rho_l * c_l * T_snow;
-    const double S1 = c.S_abs()[1] + mts * rho_l * S_br_of(g, T_snow, SCV(c, SC_S_ABS_SNOW) / SCV(c, SC_M_SNOW));
-    const double m1 = c.m()[1] + mts * rho_l;
-    c.H_abs()[1] = H1; c.S_abs()[1] = S1;
-    c.thick()[1] = c.thick()[1] + mts;
-    c.m()[1] = m1;
-    c.S_bu()[1] = S1 / m1;
+    const double H1 = v.H_abs()[1] + mts * rho_l * c_l * T_snow;
+    const double S1 = v.S_abs()[1] + mts * rho_l * S_br_of(T_snow, SCV(c, SC_S_ABS_SNOW) / SCV(c, SC_M_SNOW));
+    const double m1 = v.m()[1] + mts * rho_l;
+    v.H_abs()[1] = H1; v.S_abs()[1] = S1;
+    v.thick()[1] = v.thick()[1] + mts;
+    v.m()[1] = m1;
+    v.S_bu()[1] = S1 / m1;
   }
   // flush_v/h: old = cur; cur = 0; [flush3 fills 1..N_active]; cur = cur + old  (:697-701, :736-737).
   // Without flush3 that is the identity; with it, new + old.  w-arrays hold the old values.
   if (c.N_active > 1 && SCV(c, SC_FREEBOARD) > 0.001) {
-    if (g.flush_flag == 4) {  // :704-713
+    if (CFG.flush_flag == 4) {  // :704-713
       const double mt = SCV(c, SC_MELT_THICK);
       if (mt > 0.000000000001 && c.N_active > 2) {
         EVT(c, EV_FLUSH_INLINE);
-        const double m1 = c.m()[1];
-        c.H_abs()[1] = c.H_abs()[1] - mt * rho_l * c_l * c.T()[1];
-        c.S_abs()[1] = c.S_abs()[1] * (1.0 - (mt * rho_l) / m1);
-        c.thick()[1] = c.thick()[1] - mt;
-        c.m()[1] = m1 - mt * rho_l;
+        const double m1 = v.m()[1];
+        v.H_abs()[1] = v.H_abs()[1] - mt * rho_l * c_l * v.T()[1];
+        v.S_abs()[1] = v.S_abs()[1] * (1.0 - (mt * rho_l) / m1);
+        v.thick()[1] = v.thick()[1] - mt;
+        v.m()[1] = m1 - mt * rho_l;
       }
-    } else if (g.flush_flag == 5) {  // :715-728
+    } else if (CFG.flush_flag == 5) {  // :715-728
       if (SCV(c, SC_MELT_THICK) > 0.000000000001 && c.N_active > 2 && SCV(c, SC_FREEBOARD) > 0.0) {
-        SCV(c, SC_FREEBOARD) = freeboard_of(g, c);
+        SCV(c, SC_FREEBOARD) = freeboard_of(c);
         const int Na = c.N_active;
-        Lay old_v = c.V_ex(), old_h = c.S_br();  // both dead after S13
+        Lay old_v = v.V_ex(), old_h = v.S_br();  // both dead after S13
         SAMSIM_LOOP
-        for (int k = 1; k <= Na; k++) { old_v[k] = c.flush_v()[k]; old_h[k] = c.flush_h()[k]; }
-        flush3(g, c);
+        for (int k = 1; k <= Na; k++) { old_v[k] = v.flush_v()[k]; old_h[k] = v.flush_h()[k]; }
+        flush3(c);
         c.thermo_valid = false;
         SAMSIM_LOOP
-        for (int k = 1; k <= Na; k++) { c.flush_v()[k] = c.flush_v()[k] + old_v[k]; c.flush_h()[k] = c.flush_h()[k] + old_h[k]; }
+        for (int k = 1; k <= Na; k++) { v.flush_v()[k] = v.flush_v()[k] + old_v[k]; v.flush_h()[k] = v.flush_h()[k] + old_h[k]; }
             }
-    } else if (g.flush_flag == 6) {  // :729-733
-      if (SCV(c, SC_MELT_THICK) > 0.000000000001 && c.N_active > 2 && SCV(c, SC_THICK_SNOW) < g.thick_0) {
-        flush4(g, c);
+    } else if (CFG.flush_flag == 6) {  // :729-733
+      if (SCV(c, SC_MELT_THICK) > 0.000000000001 && c.N_active > 2 && SCV(c, SC_THICK_SNOW) < CFG.thick_0) {
+        flush4(c);
         c.thermo_valid = false;
             }
     }
   }
 
   // ---- S22 tracer advection :742-747 ----
-  if (g.n_bgc) bgc_advection(g, c);
+  if (CFG.n_bgc) bgc_advection(c);
 
   }
   SAMSIM_PHASE_SYNC();
@@ -867,23 +872,23 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
   // ---- S23 layer dynamics :755-795 ----
   if (c.N_active > 1) {
     const int Na = c.N_active;
-    const double r1 = c.thick()[1] / g.thick_0;
-    if (c.phi()[Na] > psi_s_min || c.phi()[Na - 1] <= psi_s_min / 2.0 || r1 > 1.5 || r1 < 0.5) {
-      layer_dynamics(g, c);
+    const double r1 = v.thick()[1] / CFG.thick_0;
+    if (v.phi()[Na] > psi_s_min || v.phi()[Na - 1] <= psi_s_min / 2.0 || r1 > 1.5 || r1 < 0.5) {
+      layer_dynamics(c);
       c.thermo_valid = false;
       fb_reset(c);
         }
     const int Nb = c.N_active;
-    if (Nb < N && c.thick()[(Nb + 1 < N) ? Nb + 1 : N] == 0) {  // :772-783 scrub
+    if (Nb < N && v.thick()[(Nb + 1 < N) ? Nb + 1 : N] == 0) {  // :772-783 scrub
       EVT(c, EV_SCRUB);
-      c.T()[Nb + 1] = SCV(c, SC_T_BOTTOM);
-      c.S_bu()[Nb + 1] = SCV(c, SC_S_BU_BOTTOM);
-      c.psi_l()[Nb + 1] = 1.0;
-      c.psi_s()[Nb + 1] = 0.0;
-      for (int q = 0; q < g.n_bgc; q++) c.bgc(q)[Nb + 1] = 0.0;  // :778-780
+      v.T()[Nb + 1] = SCV(c, SC_T_BOTTOM);
+      v.S_bu()[Nb + 1] = SCV(c, SC_S_BU_BOTTOM);
+      v.psi_l()[Nb + 1] = 1.0;
+      v.psi_s()[Nb + 1] = 0.0;
+      for (int q = 0; q < CFG.n_bgc; q++) v.bgc(q)[Nb + 1] = 0.0;  // :778-780
     }
   } else {
-    if (c.phi()[1] > psi_s_min) { layer_dynamics(g, c); c.thermo_valid = false; fb_reset(c); }
+    if (v.phi()[1] > psi_s_min) { layer_dynamics(c); c.thermo_valid = false; fb_reset(c); }
     }
 
   // ---- S24 timestep + health check :802-819 ----
@@ -895,18 +900,18 @@ __device__ __noinline__ void column_step(const DevCfg& g, Col& c, const Forcing&
       // nothing touched psi_s(1:N_active) since S4, nor S_abs(2:N_active) since S18, and N_active is unchanged:
       // the minima gathered by those sweeps are the MINVALs of :808 and :812
       mn = c.min_psi_s;
-      ms = f_min(c.S_abs()[1], c.min_S_abs_2);
+      ms = f_min(v.S_abs()[1], c.min_S_abs_2);
     } else {
-      mn = c.psi_s()[1]; ms = c.S_abs()[1];
+      mn = v.psi_s()[1]; ms = v.S_abs()[1];
       SAMSIM_LOOP
-      for (int k = 2; k <= Na; k++) { mn = f_min(mn, c.psi_s()[k]); ms = f_min(ms, c.S_abs()[k]); }
+      for (int k = 2; k <= Na; k++) { mn = f_min(mn, v.psi_s()[k]); ms = f_min(ms, v.S_abs()[k]); }
     }
     if (mn < 0.0) {
       c.status = 1337;
     } else if (ms < 0.0) {
       EVT(c, EV_SALT_CLAMP);
       SAMSIM_LOOP
-      for (int k = 1; k <= Na; k++) c.S_abs()[k] = f_max(c.S_abs()[k], 0.0);
+      for (int k = 1; k <= Na; k++) v.S_abs()[k] = f_max(v.S_abs()[k], 0.0);
       c.thermo_valid = false;
     }
   }

@@ -31,7 +31,7 @@ struct HostKernel {
   samsim_config_t cfg;
   DevCfg g;
   int LS;
-  std::vector<double> arr;  // [AR_COUNT][LS], ncol_pad = 1
+  std::vector<double> arr;  // one tile, lane 0: element (slot a, layer k) at [(k*AR_COUNT + a)*SAMSIM_TILE]
   double sc[SC_COUNT];
   int N_active, status, styropor_flag;
   unsigned ev0 = 0, ev1 = 0;
@@ -75,7 +75,7 @@ void* hostk_create(const samsim_config_t* cfg) {
     d.c2 = -17.6; d.c3 = -0.389; d.c4 = -0.00362; d.d2 = -17.6; d.d3x2 = 2.0 * -0.389; d.d4x3 = 3.0 * -0.00362;
   }
   h->LS = cfg->Nlayer + 2;
-  h->arr.assign((size_t)AR_COUNT * h->LS, 0.0);
+  h->arr.assign((size_t)AR_COUNT * h->LS * SAMSIM_TILE, 0.0);
   memset(h->sc, 0, sizeof h->sc);
   h->N_active = 1; h->status = 0; h->styropor_flag = 0;
   h->time = 0.0; h->i = 0; h->n_time_out = 0; h->time_counter = 1;
@@ -90,14 +90,14 @@ void hostk_destroy(void* p) { delete (HostKernel*)p; }
 
 static int slot_of_public(int id) { return (id < AR_STATE_COUNT) ? id : AR_BGC1 + (id - AR_STATE_COUNT); }
 
-// layer k (1-based) of public array `id` lives at arr[slot*LS + k]
+// layer k (1-based) of public array `id` lives at arr[(k*AR_COUNT + slot)*SAMSIM_TILE] (lane 0 of the one tile)
 void hostk_set_array(void* p, int id, const double* v, int n) {
   HostKernel* h = (HostKernel*)p;
-  for (int k = 0; k < n; k++) h->arr[(size_t)slot_of_public(id) * h->LS + k + 1] = v[k];
+  for (int k = 0; k < n; k++) h->arr[((size_t)(k + 1) * AR_COUNT + slot_of_public(id)) * SAMSIM_TILE] = v[k];
 }
 void hostk_get_array(void* p, int id, double* v, int n) {
   HostKernel* h = (HostKernel*)p;
-  for (int k = 0; k < n; k++) v[k] = h->arr[(size_t)slot_of_public(id) * h->LS + k + 1];
+  for (int k = 0; k < n; k++) v[k] = h->arr[((size_t)(k + 1) * AR_COUNT + slot_of_public(id)) * SAMSIM_TILE];
 }
 double* hostk_scalars(void* p) { return ((HostKernel*)p)->sc; }
 void hostk_set_ints(void* p, int N_active, int status, int styropor_flag) {
@@ -147,7 +147,8 @@ void hostk_kat_getT(int salt_flag, int n, const double* H, const double* S_bu, c
     double T = 0.0, phi = 0.0;
     int status = 0;
     unsigned ev1 = 0;
-    getT(g, H[q], S_bu[q], T_in[q], T, phi, status, ev1);
+    samsim_host_cfg = &g;
+    getT(H[q], S_bu[q], T_in[q], T, phi, status, ev1);
     T_out[q] = T; phi_out[q] = phi; st[q] = status; ev[q] = (int)ev1;
   }
 }
@@ -157,8 +158,7 @@ int hostk_step(void* p, long long nsteps) {
   HostKernel* h = (HostKernel*)p;
   Col c;
   c.base = h->arr.data();
-  c.ls = 1u;
-  c.astr = (unsigned)h->LS;
+  c.ls = (unsigned)(AR_COUNT * SAMSIM_TILE);
   for (int q = 0; q < SC_COUNT; q++) c.sc[q] = h->sc[q];
   c.N_active = h->N_active; c.status = h->status; c.styropor_flag = h->styropor_flag;
   c.ev0 = h->ev0; c.ev1 = h->ev1;
@@ -177,10 +177,11 @@ int hostk_step(void* p, long long nsteps) {
   f.lab = h->lab.empty() ? nullptr : h->lab.data();
   f.lab_nrec = h->lab_nrec; f.lab_set = 0;
 
+  samsim_host_cfg = &h->g;
   SnapOut snap;
   snap.scalars = h->snap_sc.data(); snap.arrays = h->snap_arr.data(); snap.ncol_pad = 1; snap.col = 0;
 
-  for (long long s = 0; s < nsteps; s++) column_step(h->g, c, f, s == nsteps - 1, snap);
+  for (long long s = 0; s < nsteps; s++) column_step(c, f, s == nsteps - 1, snap);
 
   for (int q = 0; q < SC_COUNT; q++) h->sc[q] = c.sc[q];
   h->N_active = c.N_active; h->status = c.status; h->styropor_flag = c.styropor_flag;

@@ -497,12 +497,13 @@ def test_testcase7_simple_parametrisations(oracle_mod, golden_dir):
     assert col.int("N_active") > 5
     eng = pu.engine_from_oracle(col, ncol=2)
     eng.set_forcing(F[None])
+    before = col.event_counts()  # the spin-up above is the oracle's alone
     for n in (1, 2000, 10000):
         assert col.step(n) == 0
         eng.step(n)
         bad = pu.compare_column(col, eng, 1, label=f"testcase 7 +{n}: ")
         assert not bad, _fmt(bad)
-    o = col.events()
+    o = {k for k, v in col.event_counts().items() if v > before[k]}
     assert "grav_drain_simple" in o and not ({"flush4", "flood_simple"} & o) and o == eng.events(1)
 
 
