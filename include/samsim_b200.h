@@ -169,6 +169,7 @@ typedef enum {
   SAMSIM_EV_MELT_THICK,           /* sub_melt_thick called          mo_functions.f90:386 */
   SAMSIM_EV_TURB,                 /* sub_turb_flux                  mo_functions.f90:347 */
   SAMSIM_EV_TANK,                 /* tank salinity                  mo_grotz.f90:573-578 */
+  SAMSIM_EV_TWO_PASS_STEP,        /* (device only) the column took the merged forward / backward passes of step.cuh in some step */
   SAMSIM_EV_COUNT
 } samsim_event_id;
 

@@ -34,6 +34,10 @@ void samsim_host_case_free(samsim_host_case_t* c);
  * series[kind*nrec + r] in samsim_forcing_kind order. */
 int samsim_host_read_forcing(const char* dir, int32_t nrec, double* series);
 
+/* mo_grotz.f90:138-169: the per-second lab series of testcases 101-105, nrec = length_input_lab values per file;
+ * series[kind*nrec + r], kinds 0 Tice, 1 snowfall, 2 heat, 3 styropor (the order of samsim_b200_set_lab_forcing). */
+int samsim_host_read_lab_series(const char* dir, int32_t testcase, int64_t nrec, double* series);
+
 typedef struct {
   int32_t ncol;              /* >= 1; column 0 writes the output files */
   int32_t device;
@@ -45,6 +49,8 @@ typedef struct {
   const double* forcing_offset;
   const double* ttop_warm; const double* ttop_cold; const double* oflux_amp;   /* [ncol] each or NULL */
   int32_t quiet;
+  const char* lab_input_dir; /* testcases 101-105: directory with {Tice,snowfall,heat,styropor}_exp_<N>.txt
+                                (mo_grotz.f90:138-169); NULL = "2017_input" like the reference */
 } samsim_grotz_options_t;
 
 /* grotz(testcase, description) for ncol columns: init, forcing, time loop on the device, dat_*.dat in the reference's

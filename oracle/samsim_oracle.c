@@ -2412,7 +2412,7 @@ static const char* const k_event_names[SAM_EV_COUNT] = {
     "top_grow_c", "top_melt_a", "top_melt_b", "top_melt_c", "grav_drained", "salt_clamp",
     "gas_refill", "getT_Tfr_fallback", "getT_saltfree", "getT_liquid", "heat_melt", "heat_thin_snow", "melt_thick_gas",
     "snow_meltwater_to_ice", "prescribe", "grav_drain_simple", "notzflux", "flush3_clamp", "scrub", "melt_thick", "turb",
-    "tank"};
+    "tank", "two_pass_step"};
 const char* sam_event_name(int id) { return (id >= 0 && id < SAM_EV_COUNT) ? k_event_names[id] : NULL; }
 
 long sam_get_stat(const sam_col* c, const char* name) {

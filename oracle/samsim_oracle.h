@@ -108,7 +108,7 @@ enum {
   SAM_EV_GAS_REFILL, SAM_EV_GETT_TFR_FALLBACK, SAM_EV_GETT_SALTFREE, SAM_EV_GETT_LIQUID, SAM_EV_HEAT_MELT,
   SAM_EV_HEAT_THIN_SNOW, SAM_EV_MELT_THICK_GAS, SAM_EV_SNOW_MELTWATER_TO_ICE, SAM_EV_PRESCRIBE,
   SAM_EV_GRAV_DRAIN_SIMPLE, SAM_EV_NOTZFLUX, SAM_EV_FLUSH3_CLAMP, SAM_EV_SCRUB, SAM_EV_MELT_THICK, SAM_EV_TURB,
-  SAM_EV_TANK,
+  SAM_EV_TANK, SAM_EV_TWO_PASS_STEP /* device only: never counted here */,
   SAM_EV_COUNT
 };
 /* "flood", "flood_neg_free", ... in the order above; NULL beyond SAM_EV_COUNT */

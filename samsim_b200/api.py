@@ -49,7 +49,7 @@ EVENT_NAMES = [
     "top_grow_c", "top_melt_a", "top_melt_b", "top_melt_c", "grav_drained", "salt_clamp",
     "gas_refill", "getT_Tfr_fallback", "getT_saltfree", "getT_liquid", "heat_melt", "heat_thin_snow", "melt_thick_gas",
     "snow_meltwater_to_ice", "prescribe", "grav_drain_simple", "notzflux", "flush3_clamp", "scrub", "melt_thick", "turb",
-    "tank"]
+    "tank", "two_pass_step"]
 
 
 def decode_events(ev0: int, ev1: int) -> set:

@@ -256,6 +256,28 @@ int samsim_host_read_forcing(const char* dir, int32_t nrec, double* series) {
   return SAMSIM_OK;
 }
 
+// lab series of testcases 101-105 (mo_grotz.f90:138-169): 2017_input/{Tice,snowfall,heat,styropor}_exp_<N>.txt with
+// N = testcase - 100, list-directed reals, nrec = length_input_lab values each; series[kind*nrec + r] in the kind
+// order of samsim_b200_set_lab_forcing.  (Tocean_exp_<N>.txt is read by the reference too but never used by the loop.)
+int samsim_host_read_lab_series(const char* dir, int32_t testcase, int64_t nrec, double* series) {
+  if (!series || nrec < 1 || testcase < 101 || testcase > 105) return SAMSIM_ERR_ARG;
+  static const char* names[4] = {"Tice", "snowfall", "heat", "styropor"};
+  const std::string d = dir ? dir : "2017_input";
+  for (int kind = 0; kind < 4; kind++) {
+    char file[64];
+    snprintf(file, sizeof file, "%s_exp_%d.txt", names[kind], testcase - 100);
+    FILE* f = fopen((d + "/" + file).c_str(), "r");
+    if (!f) return SAMSIM_ERR_STATE;
+    for (int64_t r = 0; r < nrec; r++) {
+      if (fscanf(f, " %lf", &series[(size_t)kind * nrec + r]) != 1) { fclose(f); return SAMSIM_ERR_STATE; }
+      int ch = fgetc(f);  // list-directed input accepts commas between values
+      if (ch != ',' && ch != EOF) ungetc(ch, f);
+    }
+    fclose(f);
+  }
+  return SAMSIM_OK;
+}
+
 int samsim_grotz(int32_t testcase, const char* description, const samsim_grotz_options_t* opt) {
   if (!opt || opt->ncol < 1 || !opt->output_dir) return SAMSIM_ERR_ARG;
   samsim_host_case_t cs;
@@ -273,7 +295,22 @@ int samsim_grotz(int32_t testcase, const char* description, const samsim_grotz_o
   F.vital = open_out(out, "dat_vital_signs.dat"); F.grav = open_out(out, "dat_grav_drain.dat");
   F.T2m = open_out(out, "dat_T2m_T_top.dat"); F.perm = open_out(out, "dat_perm.dat"); F.flush_v = open_out(out, "dat_flush_v.dat");
   F.flush_h = open_out(out, "dat_flush_h.dat"); F.psi_g = open_out(out, "dat_psi_g.dat"); F.melt = open_out(out, "dat_melt.dat");
-  if (!F.T || !F.melt) { samsim_host_case_free(&cs); return SAMSIM_ERR_STATE; }
+  FILE* Fbgc[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  samsim_handle_t h = nullptr;
+  auto all_files = [&]() {
+    return std::vector<FILE**>{&F.T, &F.psi_s, &F.thick, &F.S_bu, &F.ray, &F.psi_l, &F.freeboard, &F.snow, &F.vital, &F.grav, &F.T2m,
+                               &F.perm, &F.flush_v, &F.flush_h, &F.psi_g, &F.melt, &Fbgc[0][0], &Fbgc[0][1], &Fbgc[1][0], &Fbgc[1][1]};
+  };
+  auto finish = [&](int code) {  // every exit path: close the files, release the device and the host case
+    for (FILE** f : all_files())
+      if (*f) { fclose(*f); *f = nullptr; }
+    if (h) samsim_b200_destroy(h);
+    samsim_host_case_free(&cs);
+    return code;
+  };
+  for (FILE** f : all_files())
+    if (f < &Fbgc[0][0] || f > &Fbgc[1][1])  // the 16 standard files must all be open (the reference aborts in OPEN)
+      if (!*f) return finish(SAMSIM_ERR_STATE);
   {
     FILE* s = open_out(out, "dat_settings.dat");
     if (s) {
@@ -289,17 +326,16 @@ int samsim_grotz(int32_t testcase, const char* description, const samsim_grotz_o
   }
 
   // output_begin_bgc (mo_output.f90:354-384): dat_bgc0<k>.bu.dat / .br.dat per tracer
-  FILE* Fbgc[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   for (int q = 0; q < g.N_bgc; q++) {
     char name[32];
     snprintf(name, sizeof name, "dat_bgc0%d.bu.dat", q + 1); Fbgc[q][0] = open_out(out, name);
     snprintf(name, sizeof name, "dat_bgc0%d.br.dat", q + 1); Fbgc[q][1] = open_out(out, name);
+    if (!Fbgc[q][0] || !Fbgc[q][1]) return finish(SAMSIM_ERR_STATE);
   }
 
   // ---- device ----
-  samsim_handle_t h = nullptr;
   rc = samsim_b200_create(&g, opt->ncol, opt->device, &h);
-  if (rc) { samsim_host_case_free(&cs); return rc; }
+  if (rc) return finish(rc);
   for (int a = 0; a < SAMSIM_ARR_COUNT && !rc; a++)
     if (samsim_b200_array_extent(h, a) > 0) rc = samsim_b200_set_array(h, a, cs.arrays[a], 0, 1);
   for (int q = 0; q < SAMSIM_SC_COUNT && !rc; q++) rc = samsim_b200_set_scalar(h, q, &cs.scalars[q], 0, 1);
@@ -316,6 +352,12 @@ int samsim_grotz(int32_t testcase, const char* description, const samsim_grotz_o
     rc = samsim_host_read_forcing(opt->forcing_dir, nrec, series.data());
     if (!rc) rc = samsim_b200_set_forcing(h, 1, nrec, series.data(), nullptr, opt->forcing_scale, opt->forcing_offset);
   }
+  if (!rc && testcase >= 101 && testcase <= 105) {  // mo_grotz.f90:138-169: the four per-second lab series
+    const int64_t nrec = cs.length_input_lab;
+    std::vector<double> lab((size_t)4 * (size_t)nrec);
+    rc = samsim_host_read_lab_series(opt->lab_input_dir, testcase, nrec, lab.data());
+    if (!rc) rc = samsim_b200_set_lab_forcing(h, 1, nrec, lab.data(), nullptr);
+  }
   if (!rc) rc = samsim_b200_set_snapshot_mode(h, SAMSIM_SNAP_FULL);
 
   // ---- the time loop in chunks that end on output steps (mo_grotz.f90:182, :340) ----
@@ -325,6 +367,7 @@ int samsim_grotz(int32_t testcase, const char* description, const samsim_grotz_o
   int32_t status = 0;
   while (!rc && done < total) {
     int64_t n = samsim_b200_steps_to_next_output(h);
+    if (n <= 0) { rc = SAMSIM_ERR_STATE; break; }  // cannot happen with a consistent clock; never spin on step(h, 0)
     const bool wrote = (done + n <= total);
     if (n > total - done) n = total - done;
     rc = samsim_b200_step(h, n);
@@ -366,15 +409,7 @@ int samsim_grotz(int32_t testcase, const char* description, const samsim_grotz_o
                ssc[SAMSIM_SNAPSC_THICKNESS], ssc[SAMSIM_SNAPSC_T_TOP], ssc[SAMSIM_SNAPSC_T2M]);
     }
   }
-  for (FILE* f : {F.T, F.psi_s, F.thick, F.S_bu, F.ray, F.psi_l, F.freeboard, F.snow, F.vital, F.grav, F.T2m, F.perm, F.flush_v, F.flush_h, F.psi_g, F.melt})
-    if (f) fclose(f);
-  for (int q = 0; q < 2; q++)
-    for (int w = 0; w < 2; w++)
-      if (Fbgc[q][w]) fclose(Fbgc[q][w]);
-  if (h) samsim_b200_destroy(h);
-  samsim_host_case_free(&cs);
-  if (rc) return rc;
-  return status;  // 0 or the reference STOP code of column 0
+  return finish(rc ? rc : status);  // 0, a negative samsim_b200_err, or the reference STOP code of column 0
 }
 
 }  // extern "C"

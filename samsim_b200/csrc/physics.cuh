@@ -95,7 +95,7 @@ enum {
   EV_SALT_CLAMP,
   EV_GAS_REFILL, EV_GETT_TFR_FALLBACK, EV_GETT_SALTFREE, EV_GETT_LIQUID, EV_HEAT_MELT, EV_HEAT_THIN_SNOW,
   EV_MELT_THICK_GAS, EV_SNOW_MELTWATER_TO_ICE, EV_PRESCRIBE, EV_GRAV_DRAIN_SIMPLE, EV_NOTZFLUX, EV_FLUSH3_CLAMP,
-  EV_SCRUB, EV_MELT_THICK, EV_TURB, EV_TANK,
+  EV_SCRUB, EV_MELT_THICK, EV_TURB, EV_TANK, EV_TWO_PASS_STEP,
   EV_COUNT
 };
 
@@ -180,6 +180,15 @@ struct Col : View {
   } fb;
   // order-independent minima gathered by sweeps that read the data anyway (S24 health check, mo_grotz.f90:808-819)
   double min_psi_s, min_S_abs_2;
+  // What the S18 sweep of the previous step prepared for the merged forward pass of this step (step.cuh,
+  // backward_pass / forward_pass): gravity-drainage quantities of layers 2..N_active that depend only on T, phi, m,
+  // thick, S_abs of those layers.  Valid while c.thermo_valid holds (nothing touched layers >= 2 since).
+  struct Pre {
+    bool valid;
+    double mn2, sq2, st2;                 // layers 2..N_active-1: min(perm), ~SUM(thick/perm), ~SUM(thick) (suffix, backward order)
+    double bottom_h, S_br_Na, perm_Na;    // thick(Na)*psi_s(Na)/psi_s_min, S_br(Na), perm(Na) as S4 / fl_grav_drain will see them
+    double A2;                            // ~SUM(psi_s(2:Na)*thick(2:Na)): lower-bound certificate that the ice floats (S11)
+  } pre;
   double sc[SC_COUNT];
   // clock (shared by the batch, advanced in lock step)
   double time;
@@ -240,8 +249,11 @@ __device__ __forceinline__ double getT_freezing_point(double S_bu) {
   }
   return T_fr;
 }
-__device__ __forceinline__ void getT_body(double H, double S_bu, double T_in, double& T_out, double& phi,
+// Returns false in the one case where the reference leaves phi untouched (salt-free branch with a NaN enthalpy):
+// the caller then keeps the value the array holds.
+__device__ __forceinline__ bool getT_body(double H, double S_bu, double T_in, double& T_out, double& phi,
                                           int& status, unsigned& ev1) {
+  bool assigned = true;
   double T = H / c_l;
   if (S_br_of(T, S_bu) > S_bu && S_bu > 0.001) {
     double T_0, f, ddT_f;
@@ -281,12 +293,15 @@ __device__ __forceinline__ void getT_body(double H, double S_bu, double T_in, do
     } else if (H <= 0.0 && -latent_heat < H) {
       T = 0.0;
       phi = -H / latent_heat;
+    } else {
+      assigned = false;
     }
   } else {
     ev1 |= 1u << (EV_GETT_LIQUID - 32);
     phi = 0.0;
   }
   T_out = T;
+  return assigned;
 }
 // out-of-line copy for the call sites outside the two Newton sweeps (snow, coupling, layer 1)
 __device__ __noinline__ void getT(double H, double S_bu, double T_in, double& T_out, double& phi,

@@ -22,7 +22,7 @@ static_assert((int)SAMSIM_SC_COUNT == (int)SC_COUNT, "scalar ids out of sync wit
 static_assert((int)SAMSIM_ARR_COUNT == (int)AR_STATE_COUNT + 2 && (int)SAMSIM_ARR_BGC_ABS1 == (int)AR_STATE_COUNT,
               "array ids out of sync with include/samsim_b200.h");
 static_assert((int)SAMSIM_INT_COUNT == (int)IN_COUNT, "int ids out of sync with include/samsim_b200.h");
-static_assert((int)SAMSIM_EV_COUNT == (int)EV_COUNT && (int)SAMSIM_EV_TANK == (int)EV_TANK && (int)SAMSIM_EV_GAS_REFILL == 32,
+static_assert((int)SAMSIM_EV_COUNT == (int)EV_COUNT && (int)SAMSIM_EV_TWO_PASS_STEP == (int)EV_TWO_PASS_STEP && (int)SAMSIM_EV_GAS_REFILL == 32,
               "event ids out of sync with include/samsim_b200.h");
 static_assert((int)SAMSIM_SNAPSC_COUNT == 20 && (int)SAMSIM_SNAPARR_COUNT == 14, "snapshot layout");
 
@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(SAMSIM_BLOCK, SAMSIM_MINBLOCKS) samsim_step_ke
   c.time = p.time; c.i = p.i; c.n_time_out = p.n_time_out; c.time_counter = p.time_counter;
   c.fsw0 = c.fsw1 = c.flw0 = c.flw1 = c.ftime0 = c.ftime1 = 0.0;
   c.thermo_valid = false;  // launch-local: the host may have changed the state between launches
+  c.pre.valid = false;
   c.want_state = false;
   c.fb.tot_valid = c.fb.suf_valid = c.fb.res_valid = false; c.fb.k_last = 0; c.fb.ks = 0;
   c.min_psi_s = 0.0; c.min_S_abs_2 = 0.0;
@@ -661,6 +662,8 @@ int samsim_b200_broadcast_column(samsim_handle_t h, int32_t src, int32_t col0, i
 int samsim_b200_set_clock(samsim_handle_t h, double time, int64_t i, int32_t n_time_out, int32_t time_counter) {
   if (!h) return fail(SAMSIM_ERR_ARG, "null handle");
   if (time_counter < 1) return fail(SAMSIM_ERR_ARG, "time_counter is 1-based");
+  if (i < 0 || n_time_out < 0 || n_time_out > h->cfg.i_time_out)
+    return fail(SAMSIM_ERR_ARG, "set_clock: need i >= 0 and 0 <= n_time_out <= i_time_out (mo_grotz.f90:340: a record is written when n_time_out == i_time_out)");
   h->time = time; h->i = i; h->n_time_out = n_time_out; h->time_counter = time_counter;
   return 0;
 }
@@ -676,7 +679,11 @@ int samsim_b200_get_clock(samsim_handle_t h, double* time, int64_t* i, int32_t* 
 int samsim_b200_set_forcing(samsim_handle_t h, int32_t nsite, int32_t nrec, const double* series, const int32_t* site_of_col,
                             const double* scale, const double* offset) {
   if (!h || !series || nsite < 1 || nsite > SAMSIM_MAXSITE || nrec < 2) return fail(SAMSIM_ERR_ARG, "set_forcing: bad argument (nsite <= 16)");
+  if (site_of_col)  // validate everything before the tables of the previous call are replaced
+    for (long long c = 0; c < h->ncol; c++)
+      if (site_of_col[c] < 0 || site_of_col[c] >= nsite) return fail(SAMSIM_ERR_ARG, "set_forcing: site index out of range");
   CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));  // a launch in flight may still read the old tables
   cudaFree(h->series); cudaFree(h->site_of_col); cudaFree(h->fscale); cudaFree(h->foffset);
   h->series = nullptr; h->site_of_col = nullptr; h->fscale = nullptr; h->foffset = nullptr;
   const size_t nb = (size_t)nsite * 4 * nrec * sizeof(double);
@@ -684,8 +691,6 @@ int samsim_b200_set_forcing(samsim_handle_t h, int32_t nsite, int32_t nrec, cons
   CU(cudaMemcpy(h->series, series, nb, cudaMemcpyHostToDevice));
   h->nsite = nsite; h->nrec = nrec;
   if (site_of_col) {
-    for (long long c = 0; c < h->ncol; c++)
-      if (site_of_col[c] < 0 || site_of_col[c] >= nsite) return fail(SAMSIM_ERR_ARG, "set_forcing: site index out of range");
     CU(cudaMalloc(&h->site_of_col, (size_t)h->ncol_pad * sizeof(int)));
     CU(cudaMemset(h->site_of_col, 0, (size_t)h->ncol_pad * sizeof(int)));
     CU(cudaMemcpy(h->site_of_col, site_of_col, (size_t)h->ncol * sizeof(int), cudaMemcpyHostToDevice));
@@ -715,7 +720,11 @@ int samsim_b200_update_forcing(samsim_handle_t h, const double* series) {
 
 int samsim_b200_set_lab_forcing(samsim_handle_t h, int32_t nset, int64_t nrec, const double* series, const int32_t* set_of_col) {
   if (!h || !series || nset < 1 || nrec < 1) return fail(SAMSIM_ERR_ARG, "set_lab_forcing: bad argument");
+  if (set_of_col)
+    for (long long c = 0; c < h->ncol; c++)
+      if (set_of_col[c] < 0 || set_of_col[c] >= nset) return fail(SAMSIM_ERR_ARG, "set_lab_forcing: set index out of range");
   CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
   cudaFree(h->lab); cudaFree(h->set_of_col);
   h->lab = nullptr; h->set_of_col = nullptr;
   const size_t nb = (size_t)nset * 4 * nrec * sizeof(double);
@@ -726,8 +735,6 @@ int samsim_b200_set_lab_forcing(samsim_handle_t h, int32_t nset, int64_t nrec, c
   }
   h->lab_nrec = nrec;
   if (set_of_col) {
-    for (long long c = 0; c < h->ncol; c++)
-      if (set_of_col[c] < 0 || set_of_col[c] >= nset) return fail(SAMSIM_ERR_ARG, "set_lab_forcing: set index out of range");
     CU(cudaMalloc(&h->set_of_col, (size_t)h->ncol_pad * sizeof(int)));
     CU(cudaMemset(h->set_of_col, 0, (size_t)h->ncol_pad * sizeof(int)));
     CU(cudaMemcpy(h->set_of_col, set_of_col, (size_t)h->ncol * sizeof(int), cudaMemcpyHostToDevice));
@@ -799,13 +806,21 @@ int samsim_b200_step(samsim_handle_t h, int64_t nsteps) {
       p.site_of_col = h->site_of_col; p.fscale = h->fscale; p.foffset = h->foffset;
     }
     if (need_lab) {
-      // records FLOOR(1 + time/dt) for every step of the chunk must exist
-      const double tend = h->time + (double)(chunk - 1) * h->cfg.dt;
-      const long long last = (long long)floor(1 + tend / h->cfg.dt);
-      if (last > h->lab_nrec) {
-        const long long ok = h->lab_nrec - (long long)floor(1 + h->time / h->cfg.dt) + 1;
+      // Records FLOOR(1 + time/dt) of every step of the chunk must exist.  The device accumulates time by repeated
+      // `+ dt`, which for a dt that is not exactly representable can sit an ulp above k*dt: the bound is found by
+      // replaying the same additions, never by a multiplication.  Only the tail of the series needs the replay.
+      const long long first_rec = (long long)floor(1 + h->time / h->cfg.dt);
+      if (first_rec < 1 || first_rec > h->lab_nrec) return fail(SAMSIM_ERR_STATE, "step: lab series exhausted");
+      if (first_rec + chunk + 2 > h->lab_nrec) {
+        double t = h->time;
+        int64_t ok = 0;
+        for (; ok < chunk; ok++) {
+          const long long rec = (long long)floor(1 + t / h->cfg.dt);
+          if (rec < 1 || rec > h->lab_nrec) break;
+          t = t + h->cfg.dt;
+        }
         if (ok < 1) return fail(SAMSIM_ERR_STATE, "step: lab series exhausted");
-        if (ok < chunk) chunk = ok;
+        chunk = ok;
       }
       p.lab = h->lab; p.lab_nrec = h->lab_nrec; p.set_of_col = h->set_of_col;
     }

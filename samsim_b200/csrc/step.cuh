@@ -61,18 +61,24 @@ __device__ __noinline__ void vital_signs(Col& c) {
   }
 }
 
-// sub_heat_fluxes, mo_heat_fluxes.f90:69-312
-__device__ __noinline__ void heat_fluxes(Col& c) {
+// Surface part of sub_heat_fluxes, mo_heat_fluxes.f90:77-258: the flux into layer 1 (returned), T_top, albedo, the snow
+// flux and fl_rad(N_active).  Shared by the sub-step-by-sub-step path (heat_fluxes) and the merged forward pass
+// (forward_pass), so both evaluate the same expressions.  Layer-1 / bottom-layer inputs are passed by value.
+struct SurfIn {
+  double ps1, pl1, pg1, th1, T1;   // psi_s(1), psi_l(1), psi_g(1), thick(1), T(1)
+  double S1, m1, SNa, mNa;         // S_abs / m of layer 1 and layer N_active as they are when sub_heat_fluxes runs
+  double flQ1_prev;                // fl_Q(1) of the previous step (kept when no boundflux branch assigns it)
+};
+__device__ __noinline__ double heat_surface(Col& c, const SurfIn& in, double& fl_rad_Na) {
   const View v = c;
   const int Na = c.N_active;
-  const double dt = CFG.dt, thick_min = CFG.thick_min;
-  const double ps1 = v.psi_s()[1], pl1 = v.psi_l()[1], pg1 = v.psi_g()[1], th1 = v.thick()[1];
-  double T1 = v.T()[1];
+  const double thick_min = CFG.thick_min;
+  const double ps1 = in.ps1, pl1 = in.pl1, pg1 = in.pg1, th1 = in.th1, T1 = in.T1;
   double& thick_snow = SCV(c, SC_THICK_SNOW);
   double& T_top = SCV(c, SC_T_TOP);
   double& fl_q_snow = SCV(c, SC_FL_Q_SNOW);
-  double flQ1 = v.fl_Q()[1];
-  double fl_rad_Na = 0.0;  // fl_rad(N_active): 0 unless boundflux 2 recomputes it (fl_rad = 0 from init, mo_init.f90:1988)
+  double flQ1 = in.flQ1_prev;
+  fl_rad_Na = 0.0;  // fl_rad(N_active): 0 unless boundflux 2 recomputes it (fl_rad = 0 from init, mo_init.f90:1988)
 
   if (CFG.boundflux_flag == 1) {  // :77-86
     flQ1 = fl_Q_0_top(ps1, pl1, pg1, th1, T1, T_top);
@@ -134,7 +140,7 @@ __device__ __noinline__ void heat_fluxes(Col& c) {
 
     double& T_freeze = SCV(c, SC_T_FREEZE);
     if (thick_snow >= thick_min / 100.0) T_freeze = 0.0;  // :158-162
-    else T_freeze = T_freeze_of(v.S_abs()[1] / v.m()[1], CFG.salt_flag);
+    else T_freeze = T_freeze_of(in.S1 / in.m1, CFG.salt_flag);
 
     if (T_top > T_freeze && Na > 1) {  // :167-180
       EVT(c, EV_HEAT_MELT);
@@ -166,7 +172,7 @@ __device__ __noinline__ void heat_fluxes(Col& c) {
     const double T2m = SCV(c, SC_T2M);
     double& T_freeze = SCV(c, SC_T_FREEZE);
     if (CFG.lab_snow_flag == 0 || thick_snow <= thick_min / 100.0) {
-      T_freeze = f_min(T_freeze_of(v.S_abs()[Na] / v.m()[Na], CFG.salt_flag), 0.0);
+      T_freeze = f_min(T_freeze_of(in.SNa / in.mNa, CFG.salt_flag), 0.0);
       T_top = T1;
       flQ1 = CFG.alpha_flux_instable * (T_top - T2m);
       if (flQ1 < 0.0) {
@@ -201,6 +207,22 @@ __device__ __noinline__ void heat_fluxes(Col& c) {
       }
     }
   }
+
+  return flQ1;
+}
+
+// sub_heat_fluxes, mo_heat_fluxes.f90:69-312
+__device__ __noinline__ void heat_fluxes(Col& c) {
+  const View v = c;
+  const int Na = c.N_active;
+  const double dt = CFG.dt, thick_min = CFG.thick_min;
+  const double ps1 = v.psi_s()[1], pl1 = v.psi_l()[1], pg1 = v.psi_g()[1], th1 = v.thick()[1];
+  double T1 = v.T()[1];
+  const double thick_snow = SCV(c, SC_THICK_SNOW);
+  double fl_rad_Na;
+  const SurfIn in = {ps1, pl1, pg1, th1, T1, v.S_abs()[1], v.m()[1], v.S_abs()[Na], v.m()[Na], v.fl_Q()[1]};
+  const double flQ1 = heat_surface(c, in, fl_rad_Na);
+  const double fl_q_snow = SCV(c, SC_FL_Q_SNOW);
 
   const double fl_q_bottom = SCV(c, SC_FL_Q_BOTTOM);
   v.fl_Q()[1] = flQ1;
@@ -279,17 +301,18 @@ __device__ __noinline__ void heat_fluxes(Col& c) {
 #ifndef SAMSIM_SYNC
 #define SAMSIM_SYNC 1
 #endif
+// S_bu is rewritten by S4 / S7 before anything reads it; only its value after the last step of a launch is observable
+#ifndef SAMSIM_ALWAYS_STORE_S_BU
+#define SAMSIM_ALWAYS_STORE_S_BU false
+#endif
 #if SAMSIM_SYNC
 #define SAMSIM_PHASE_SYNC() __syncthreads()
 #else
 #define SAMSIM_PHASE_SYNC() ((void)0)
 #endif
-// SAMSIM_SYNC=2 additionally re-aligns the warps after every layer of the two Newton sweeps (their trip counts
-// are data dependent); the sweeps then run a block-uniform Nlayer iterations with the body predicated on k <= N_active.
 #if SAMSIM_SYNC >= 2
-#define SAMSIM_LAYER_SYNC() __syncthreads()
-#else
-#define SAMSIM_LAYER_SYNC() ((void)0)
+#error "SAMSIM_SYNC=2 (a barrier per layer of the Newton sweeps) was removed: it measured slower and its fused / unfused \
+choice per thread made the barrier divergent (ADVICE round 1)"
 #endif
 
 struct SnapOut {
@@ -380,7 +403,7 @@ __device__ __noinline__ void fused_thermo_expulsion(Col& c) {
   SAMSIM_LOOP
   for (int k = 1; k <= Na; k++) {
     if (k + SAMSIM_PF <= Na) {
-      v.T().prefetch(k + SAMSIM_PF); v.S_bu().prefetch(k + SAMSIM_PF); v.phi().prefetch(k + SAMSIM_PF);
+      v.T().prefetch(k + SAMSIM_PF); v.phi().prefetch(k + SAMSIM_PF);
       v.m().prefetch(k + SAMSIM_PF); v.thick().prefetch(k + SAMSIM_PF); v.S_abs().prefetch(k + SAMSIM_PF);
       v.H_abs().prefetch(k + SAMSIM_PF);
     }
@@ -388,8 +411,9 @@ __device__ __noinline__ void fused_thermo_expulsion(Col& c) {
     // neighbour below: old T, S_bu (S4 values) and the not yet updated S_abs
     double T_kp1, Sbu_kp1, Sabs_kp1, phi_kp1 = 0.0, m_kp1 = 0.0;
     if (k < Na) {
-      T_kp1 = v.T()[k + 1]; Sbu_kp1 = v.S_bu()[k + 1]; Sabs_kp1 = v.S_abs()[k + 1];
+      T_kp1 = v.T()[k + 1]; Sabs_kp1 = v.S_abs()[k + 1];
       phi_kp1 = v.phi()[k + 1]; m_kp1 = v.m()[k + 1];
+      Sbu_kp1 = Sabs_kp1 / m_kp1;  // S_bu(k+1) of S4 (:299); the S_bu array is not kept current by the two-pass steps
     } else {
       T_kp1 = T_bottom; Sbu_kp1 = S_bu_bottom; Sabs_kp1 = S_bu_bottom * 2000.0;
     }
@@ -431,6 +455,369 @@ __device__ __noinline__ void fused_thermo_expulsion(Col& c) {
     T_k = T_kp1; sbu_k = Sbu_kp1; phi_k = phi_kp1; m_k = m_kp1;
     f0 = f1;
   }
+  c.fb.tot_valid = true; c.fb.t1 = v.thick()[1]; c.fb.A = fbA; c.fb.G = fbG;
+  c.fb.suf_valid = (ks != 0); c.fb.ks = ks; c.fb.As = fbAs; c.fb.Gs = fbGs;
+  c.fb.res_valid = false;
+  c.min_psi_s = min_ps;
+}
+
+// S15 testcase hooks, mo_grotz.f90:503-563
+__device__ __forceinline__ void testcase_hooks(Col& c, const Forcing& f) {
+  const View v = c;
+  const double dt = CFG.dt;
+  const int N = CFG.Nlayer;
+  if (CFG.testcase == 1) {  // sub_test1, mo_testcase_specifics.f90:42-89
+    const double j = rint(c.time / 43200.0);
+    if (j >= 1.0 && j <= 20.0 && fabs(c.time - 12.0 * j * 3600.0) < SAMSIM_F32(0.01))
+      SCV(c, SC_T_TOP) = (((int)j) & 1) ? SCV(c, SC_TTOP_COLD) : SCV(c, SC_TTOP_WARM);
+  } else if (CFG.testcase >= 101 && CFG.testcase <= 105) {  // :521-530
+    const long long idx = (long long)floor(1 + c.time / dt);
+    const double Sb = v.S_bu()[c.N_active + 1];
+    SCV(c, SC_T2M) = lab_rec(f, 0, idx);
+    SCV(c, SC_SOLID_PRECIP) = lab_rec(f, 1, idx);
+    SCV(c, SC_FL_Q_BOTTOM) = lab_rec(f, 2, idx);
+    SCV(c, SC_T_BOTTOM) = -SAMSIM_F32(0.0575) * Sb + SAMSIM_F32(1.710523e-3) * det_pow(Sb, 3.0 / 2.0) -
+                          SAMSIM_F32(2.154996e-4) * P2(Sb) - SAMSIM_F32(7.53e-4) * sum_fwd(v.thick(), 1, c.N_active - 1);
+    c.styropor_flag = (int)lab_rec(f, 3, idx);
+  } else if (CFG.testcase == 4 || CFG.testcase == 7) {  // sub_test4, mo_testcase_specifics.f90:197-202
+    const double amp = SCV(c, SC_OFLUX_AMP);
+    SCV(c, SC_FL_Q_BOTTOM) = -amp * det_sin(c.time * (2.0 * pi_sp) / (86400.0 * 365.0)) + amp;
+  } else if (CFG.testcase == 2) {  // sub_test2, mo_testcase_specifics.f90:92-101
+    if (c.time > 86400.0 * 25.0) SCV(c, SC_T2M) = 15.0;
+    else if (c.time > 86400.0 * 15.0) SCV(c, SC_T2M) = 1.0;
+  } else if (CFG.testcase == 9) {  // sub_test9, :105-116
+    if (c.time < (19.75 * 3600.0)) SCV(c, SC_T2M) = 0.0;
+    else if (c.time < (86400.0 * 3.0 + 2.25 * 3600.0)) SCV(c, SC_T2M) = -15.0;
+    else SCV(c, SC_T2M) = 1.0;
+  } else if (CFG.testcase == 3) {  // sub_test3, :170-185
+    SCV(c, SC_LIQUID_PRECIP) = 0.0;
+    SCV(c, SC_SOLID_PRECIP) = 0.15 / 86400.0 / 356.0;
+  } else if (CFG.testcase == 6) {  // sub_test6, :218-243
+    const double t = c.time;
+    if (t > 1714.0 * 60.0) SCV(c, SC_T2M) = -19.0;
+    else if (t > 1676.0 * 60.0) SCV(c, SC_T2M) = -5.0;
+    else if (t > 1525.0 * 60.0) SCV(c, SC_T2M) = -18.0;
+    else if (t > 1483.0 * 60.0) SCV(c, SC_T2M) = -5.0;
+    else if (t > 1385.0 * 60.0) SCV(c, SC_T2M) = -18.0;
+    else if (t > 1349.0 * 60.0) SCV(c, SC_T2M) = -5.0;
+    else if (t > 1160.0 * 60.0) SCV(c, SC_T2M) = -18.0;
+    else if (t > 1100.0 * 60.0) SCV(c, SC_T2M) = -5.0;
+  } else if (CFG.testcase == 5 && c.i == 2) {  // mo_grotz.f90:541-542
+    SAMSIM_LOOP
+    for (int k = 1; k <= N; k++) v.S_abs()[k] = 5.0 * v.m()[k];
+  }
+
+}
+
+// ==========================================================================================================
+// The two-pass step.  In the steady regime (no flooding, no flushing, no layer event, a proper snow layer or none)
+// a model step touches the per-layer arrays in exactly two sweeps instead of five:
+//
+//   forward_pass   k = 1..N_active   S4 (layer 1 getT; layers >= 2 reuse the S18 result), S5 expulsion_flux +
+//                                    mass_transfer, S7, S9, S12, S13 fl_grav_drain incl. its mass_transfer, S17
+//                                    sub_heat_fluxes -- merged with a lag of one layer (layer k-1 is finished while
+//                                    layer k is expelled and drained)
+//   backward_pass  k = N_active..1   S18 getT sweep, plus the layer-local half of the NEXT step's fl_grav_drain
+//                                    (permeability, thick/perm, suffix estimates of the Rayleigh numbers)
+//
+// Per layer and step the forward pass reads m, S_abs, H_abs, thick, T, phi, ray (7) and writes m, S_abs, H_abs, psi_s,
+// psi_l, psi_g (6); the backward pass reads m, S_abs, H_abs, thick (4) and writes T, phi, ray, thick/perm (4): 21
+// array passes instead of 37.  S_br, V_ex, fl_m, S_bu, fl_Q(2:) never leave the registers.  Every value is computed by
+// the same expression, in the same order, as in the sub-step-by-sub-step path below (and in the reference); the
+// bitwise parity tests run both.  column_step takes this path only when fast_path_ok() holds; everything else --
+// output steps, the last step of a launch (whose ray / S_bu / fl_Q arrays are observable), thin snow, possible
+// flooding, tracers, tank / lab cases -- goes through the general path.
+// ==========================================================================================================
+
+// S18, mo_grotz.f90:592-598 (psi_* are NOT refreshed).  `prepare`: also evaluate, for layers 2..N_active, what the
+// next step's S4 and fl_grav_drain (mo_grav_drain.f90:104-136) will compute from T, phi, m, thick, S_abs of the layer
+// alone: Expulsion -> psi_l -> perm, thick/perm (stored in w1), and the suffix estimates of ray (stored in ray, see
+// grav_drain for the estimate / candidate scheme).  Only done when ray is not observable before it is recomputed.
+__device__ __noinline__ void backward_pass(Col& c, bool prepare, bool store_S_bu) {
+  const View v = c;
+  const int Na = c.N_active;
+  Lay q = v.w1();
+  double T_test = SCV(c, SC_T_BOTTOM);
+  double min_S2 = 1e300;
+  double mn = 0.0, sq = 0.0, st = 0.0, bottom_h = 0.0, S_br_Na = 0.0, perm_Na = 0.0, qb_est = 0.0, A2 = 0.0;
+  SAMSIM_LOOP
+  for (int k = Na; k >= 1; k--) {
+    if (k - SAMSIM_PF >= 1) {
+      v.m().prefetch(k - SAMSIM_PF); v.S_abs().prefetch(k - SAMSIM_PF); v.H_abs().prefetch(k - SAMSIM_PF);
+      if (prepare) v.thick().prefetch(k - SAMSIM_PF);
+    }
+    const double mk = v.m()[k];
+    const double Sk = v.S_abs()[k];
+    if (k >= 2) min_S2 = f_min(min_S2, Sk);
+    const double sbu = Sk / mk;
+    const double H = v.H_abs()[k] / mk;
+    double T, phi;
+    if (!getT_body(H, sbu, T_test, T, phi, c.status, c.ev1)) phi = v.phi()[k];  // inlined: no call, no spills in the hot sweep
+    T_test = T;
+    v.T()[k] = T; v.phi()[k] = phi;
+    if (store_S_bu) v.S_bu()[k] = sbu;
+    if (prepare && k >= 2) {
+      const double thk = v.thick()[k];
+      double ps, pl, pg, vex;
+      expulsion(phi, thk, mk, ps, pl, pg, vex);                       // S4 of the next step, :298-307
+      A2 = A2 + ps * thk;
+      const double pk = 1e-17 * det_pow(1000.0 * fabs(pl), 3.10);     // mo_grav_drain.f90:104-106
+      const double sbr = S_br_of(T, sbu);
+      if (k == Na) {
+        perm_Na = pk; bottom_h = thk * ps / psi_s_min; qb_est = bottom_h / pk; S_br_Na = sbr;
+      } else {
+        const double qk = thk / pk;
+        q[k] = qk;
+        mn = (k == Na - 1) ? pk : f_min(mn, pk);
+        const double st_below = st;
+        sq = sq + qk;
+        st = st + thk;
+        const double hp = (mn < 1e-14) ? 0.0 : (st + bottom_h) / (sq + qb_est);
+        double est = grav * rho_l * bbeta * (sbr - S_br_Na) * (st_below + bottom_h) * hp;
+        est = est / (kappa_l * mu);
+        v.ray()[k] = (mn < 1e-14) ? 0.0 : f_max(est, 0.0);
+      }
+    }
+  }
+  c.min_S_abs_2 = min_S2;
+  c.thermo_valid = true;  // invalidated by anything that touches layers >= 2
+  c.pre.valid = prepare;
+  c.pre.mn2 = mn; c.pre.sq2 = sq; c.pre.st2 = st; c.pre.bottom_h = bottom_h; c.pre.S_br_Na = S_br_Na; c.pre.perm_Na = perm_Na;
+  c.pre.A2 = A2;
+}
+
+// May this column take the merged forward pass in this step?  Everything here is a per-column, per-step decision.
+__device__ __forceinline__ bool fast_path_ok(const Col& c, bool output_step, bool observable_after) {
+  if (!(c.thermo_valid && c.pre.valid) || output_step || observable_after) return false;
+  if (c.N_active < 3 || c.i == 1) return false;
+  if (CFG.grav_flag != 2 || CFG.harmonic_flag != 2 || CFG.n_bgc != 0 || CFG.prescribe_flag == 2 || CFG.tank_flag == 2) return false;
+  if (!(CFG.boundflux_flag == 1 || CFG.boundflux_flag == 2)) return false;
+  if (CFG.testcase == 5 || (CFG.testcase >= 101 && CFG.testcase <= 105)) return false;  // hooks that edit the column / read S_bu
+  // snow: a layer of its own (>= thick_min) or none at all; thin snow couples to layer 1 (S10, S17) -> general path
+  const double ts = SCV(c, SC_THICK_SNOW), ms = SCV(c, SC_M_SNOW);
+  if (!(ts >= CFG.thick_min || (ms <= 0.0 && ts < CFG.thick_min / 100.0))) return false;
+  if (CFG.flood_flag > 1) {
+    // S11: func_freeboard < 0 needs either m_snow > total buoyancy (mo_functions.f90:99) or a waterline in layer 1.
+    // With m(1) + m_snow below the buoyancy of layers 2..Na (psi_s part only, backward-order sum, 1e-9 safety) the
+    // waterline is in layer 2 or deeper and the freeboard is >= thick(1) > 0: no flooding, rigorously.
+    const double snowmass = (CFG.freeboard_snow_flag == 0) ? ms : 0.0;
+    if (!(c.m()[1] + snowmass < c.pre.A2 * (rho_l - rho_s) * (1.0 - 1e-9))) return false;
+  }
+  return true;
+}
+
+// S4 .. S17 of one step in one forward pass (see the block comment above).  Preconditions: fast_path_ok().
+__device__ __noinline__ void forward_pass(Col& c) {
+  const View v = c;
+  const int Na = c.N_active;
+  const double dt = CFG.dt;
+  const double T_bottom = SCV(c, SC_T_BOTTOM), S_bu_bottom = SCV(c, SC_S_BU_BOTTOM);
+  const double bottom_h = c.pre.bottom_h, S_br_Na = c.pre.S_br_Na;
+  const double qb = bottom_h / c.pre.perm_Na;
+  Lay q = v.w1();
+
+  // ---- layer 1: the S4 getT (layers >= 2 keep T, phi of the S18 sweep: same inputs, same first-guess chain) ----
+  double m_k = v.m()[1], Sabs_k = v.S_abs()[1], H_k = v.H_abs()[1], thk = v.thick()[1];
+  double sbu_k = Sabs_k / m_k;                 // S_bu(k) of S4 (:299)
+  double T_k, phi_k = v.phi()[1];
+  getT(H_k / m_k, sbu_k, v.T()[2], T_k, phi_k, c.status, c.ev1);
+  v.T()[1] = T_k; v.phi()[1] = phi_k;
+
+  // carried between iterations: layer k-1 after expulsion (E), drainage (D); layer k-2 after the drainage transfer (G)
+  double T_km1 = 0.0, SbuE_km1 = 0.0, SabsE_km1 = 0.0;       // S4 values / S_abs after E, for E(k)'s mass_transfer
+  double Sbu7_km1 = 0.0, S_km1 = 0.0, H_km1 = 0.0, hr_km1 = 0.0, up_km1 = 0.0;
+  double T_km2 = 0.0, Sbu7_km2 = 0.0, S_km2 = 0.0, up_km2 = 0.0;
+  double f0 = 0.0;                                           // fl_m(k) of expulsion_flux
+  double fq_km1 = 0.0, rad = 0.0, flQ1 = 0.0;                // heat: flux into layer k-1 from above, fl_rad(Na)*dt
+  double run = 0.0, heat_loss = 0.0, sum_before = 0.0, sum_after = 0.0, min_S = 1e300;
+  int kfirst = 0;
+  double temp1 = 0.0, temp2 = 0.0;                           // energy check sums, mo_heat_fluxes.f90:269, :305
+  // func_freeboard memo and S24 minimum, as in fused_thermo_expulsion
+  double fbA = 0.0, fbG = 0.0, fbAs = 0.0, fbGs = 0.0, min_ps = 1e300;
+  const int ks = (c.fb.k_last >= 1 && c.fb.k_last < Na) ? c.fb.k_last : 0;
+  // suffix quantities of the Rayleigh estimate, extended to layer 1 inside the loop
+  double sbr_k = S_br_of(T_k, sbu_k);                        // S_br(k) of S4 (:304)
+
+  SAMSIM_LOOP
+  for (int k = 1; k <= Na; k++) {
+    if (k + 1 + SAMSIM_PF <= Na) {
+      const int kp = k + 1 + SAMSIM_PF;
+      v.T().prefetch(kp); v.phi().prefetch(kp); v.m().prefetch(kp); v.thick().prefetch(kp); v.S_abs().prefetch(kp);
+      v.H_abs().prefetch(kp); v.ray().prefetch(kp);
+    }
+    // ---- neighbour below, S4 values: T, S_bu = S_abs/m (:299), S_br (:304) ----
+    double T_kp1, Sbu_kp1, Sabs_kp1, phi_kp1 = 0.0, m_kp1 = 0.0, sbr_kp1 = 0.0;
+    if (k < Na) {
+      T_kp1 = v.T()[k + 1]; Sabs_kp1 = v.S_abs()[k + 1]; phi_kp1 = v.phi()[k + 1]; m_kp1 = v.m()[k + 1];
+      Sbu_kp1 = Sabs_kp1 / m_kp1;
+      sbr_kp1 = S_br_of(T_kp1, Sbu_kp1);
+    } else {
+      T_kp1 = T_bottom; Sbu_kp1 = S_bu_bottom; Sabs_kp1 = S_bu_bottom * 2000.0;
+    }
+
+    // ================= E(k): S4 volume fractions, S5 expulsion_flux + mass_transfer, S7 =================
+    double ps, pl, pg, vex;
+    expulsion(phi_k, thk, m_k, ps, pl, pg, vex);
+    double f1;  // fl_m(k+1), mo_mass.f90:121-134
+    if (k == 1) {
+      f1 = -vex * rho_l;
+    } else if (pg < SAMSIM_F32(0.001)) {
+      f1 = -vex * rho_l + f0;
+    } else {
+      f1 = -f_max((vex - pg * thk) * rho_l, 0.0);
+      pg = f_max((pg * thk - vex) / thk, 0.0);
+    }
+    v.psi_s()[k] = ps; v.psi_l()[k] = pl; v.psi_g()[k] = pg;
+    fbA = fbA + ps * thk;
+    fbG = fbG + pg * thk;
+    if (ks && k > ks) { fbAs = fbAs + ps * thk; fbGs = fbGs + pg * thk; }
+    min_ps = f_min(min_ps, ps);
+    double m_new = m_k + f1 - f0;
+    double S = Sabs_k, H = H_k;
+    mass_transfer_layer(f1, f0, T_km1, SbuE_km1, SabsE_km1, T_k, sbu_k, T_kp1, Sbu_kp1, Sabs_kp1, H, S);  // (i != 1 here)
+    const double SabsE_k = S;
+    const double Sbu7_k = S / m_new;           // S7 (:333-335)
+    if (k == Na) {
+      // ---- S9 gas in the lowest layer :405-410, S12 sub_turb_flux (mo_functions.f90:347-363) ----
+      if (pg > 0.0) {
+        EVT(c, EV_GAS_REFILL);
+        const double g2 = pg * thk * rho_l;
+        m_new = m_new + g2;
+        S = S + g2 * S_bu_bottom;
+        H = H + g2 * c_l * T_bottom;
+      }
+      if (CFG.turb_flag == 2) {
+        EVT(c, EV_TURB);
+        const double turb = Turb_A * det_exp(Turb_B * (-density_of(T_bottom, S_bu_bottom) + density_of(T_k, S / m_new))) * dt;
+        S = S - turb * (S / m_new - S_bu_bottom);
+      }
+    }
+    v.m()[k] = m_new;
+
+    // ================= D(k): the drain decision of layer k, mo_grav_drain.f90:126-171 =================
+    double up_k = run;
+    if (k < Na) {
+      double rk;
+      if (k == 1) {
+        // layer 1 of the Rayleigh estimate (layers >= 2 were prepared by backward_pass)
+        const double pk = 1e-17 * det_pow(1000.0 * fabs(pl), 3.10);
+        const double qk = thk / pk;
+        q[1] = qk;
+        const double mn = (Na == 2) ? pk : f_min(c.pre.mn2, pk);
+        const double hp = (mn < 1e-14) ? 0.0 : ((c.pre.st2 + thk) + bottom_h) / ((c.pre.sq2 + qk) + qb);
+        double est = grav * rho_l * bbeta * (sbr_k - S_br_Na) * (c.pre.st2 + bottom_h) * hp;
+        est = est / (kappa_l * mu);
+        rk = (mn < 1e-14) ? 0.0 : f_max(est, 0.0);
+      } else {
+        rk = v.ray()[k];
+      }
+      if (rk > ray_crit * (1.0 - 1e-10)) {
+        // candidate: the reference's forward sums (:115-120, :128) for this layer only, then ray(k) as at :126-136
+        double hq = 0.0, ht = 0.0, hb = 0.0;
+        SAMSIM_LOOP
+        for (int kk = k; kk <= Na - 1; kk++) {
+          const double tv = v.thick()[kk];
+          hq = hq + q[kk];
+          ht = ht + tv;
+          if (kk > k) hb = hb + tv;
+        }
+        double hp = hq + qb;  // the estimate was > 0, so minval(perm(k:Na-1)) >= 1e-14 (:112) holds
+        hp = (ht + bottom_h) / hp;
+        double r = grav * rho_l * bbeta * (sbr_k - S_br_Na) * (hb + bottom_h) * hp;
+        r = r / (kappa_l * mu);
+        rk = f_max(r, 0.0);
+      }
+      sum_before = sum_before + S;
+      if (rk > ray_crit && ps > 0.001 && S / m_new > 0.1 && sbr_k > sbr_kp1) {  // :145
+        if (kfirst == 0) { kfirst = k; EVT(c, EV_GRAV_DRAINED); }
+        double flux = x_grav * (rk - ray_crit) * dt * thk;
+        flux = f_min(flux, pl * rho_l * thk);
+        S = S - flux * sbr_k;
+        if (S < 0.0) { c.status = 21234; return; }
+        SCV(c, SC_GRAV_TEMP) = SCV(c, SC_GRAV_TEMP) + flux * T_k;
+        H = H - flux * c_l * T_k;
+        heat_loss = heat_loss + flux * c_l * T_k;
+        run = run + flux;
+        up_k = f_min(run, pl * rho_l * thk);
+      } else {
+        up_k = run;
+      }
+      sum_after = sum_after + S;
+    }
+    if (!kfirst) up_k = 0.0;  // fl_m(2:kfirst) = 0: nothing moves above the first draining layer (run is still 0 there)
+
+    // ================= G(k-1), Q(k-1): drainage transfer and heat update of the layer above =================
+    const double hr_k = thk / (2.0 * (ps * k_s + pl * k_l + ((k == 1) ? pg * 0.0 : 0.0 * 0.0)));  // half resistance, sub_fl_Q
+    if (k >= 2) {
+      if (kfirst && k - 1 >= kfirst)
+        mass_transfer_layer(up_km1, up_km2, T_km2, Sbu7_km2, S_km2, T_km1, Sbu7_km1, T_k, Sbu7_k, S, H_km1, S_km1);
+      if (k == 2) {
+        // ---- surface energy balance (needs S_abs(1) after the drainage transfer), mo_heat_fluxes.f90:77-195 ----
+        double fl_rad_Na;
+        const SurfIn in = {v.psi_s()[1], v.psi_l()[1], v.psi_g()[1], v.thick()[1], v.T()[1], S_km1, v.m()[1], 0.0, 0.0, v.fl_Q()[1]};
+        flQ1 = heat_surface(c, in, fl_rad_Na);
+        fq_km1 = flQ1;
+        rad = fl_rad_Na * dt;
+      }
+      const double fq_k = (T_k - T_km1) / (hr_km1 + hr_k);  // fl_Q(k), :272-274
+      double Hh = H_km1;
+      temp1 = temp1 + Hh;                  // :269
+      Hh = Hh + (fq_k - fq_km1) * dt;      // :277-279
+      Hh = Hh + rad;                       // :282-285 (sic)
+      v.H_abs()[k - 1] = Hh;
+      v.S_abs()[k - 1] = S_km1;
+      temp2 = temp2 + Hh;
+      min_S = f_min(min_S, S_km1);
+      fq_km1 = fq_k;
+    }
+
+    // ---- shift the window ----
+    T_km2 = T_km1; Sbu7_km2 = Sbu7_km1; S_km2 = S_km1; up_km2 = up_km1;
+    T_km1 = T_k; SbuE_km1 = sbu_k; SabsE_km1 = SabsE_k; Sbu7_km1 = Sbu7_k; S_km1 = S; H_km1 = H; hr_km1 = hr_k; up_km1 = up_k;
+    f0 = f1;
+    if (k < Na) {
+      T_k = T_kp1; sbu_k = Sbu_kp1; phi_k = phi_kp1; m_k = m_kp1; Sabs_k = Sabs_kp1; sbr_k = sbr_kp1;
+      thk = v.thick()[k + 1]; H_k = v.H_abs()[k + 1];
+    }
+  }
+
+  // ================= layer N_active: G(Na), grav_heat, Q(Na) =================
+  // S_abs(Na) enters both SUM(S_abs) of :141 / :173 with its value before the drainage transfer
+  sum_before = sum_before + S_km1;
+  sum_after = sum_after + S_km1;
+  SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) + sum_before;
+  SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) - sum_after;
+  if (kfirst)
+    mass_transfer_layer(run, up_km2, T_km2, Sbu7_km2, S_km2, T_km1, Sbu7_km1, T_bottom, S_bu_bottom, S_bu_bottom * 2000.0, H_km1, S_km1);
+  SCV(c, SC_GRAV_DRAIN) = SCV(c, SC_GRAV_DRAIN) + run;                                   // :190
+  if (CFG.grav_heat_flag == 2) H_km1 = H_km1 + heat_loss - run * c_l * T_bottom;        // :193-195
+  min_S = f_min(min_S, S_km1);
+  if (f_min(min_S, 0.0) < 0.0) { c.status = 1337; }                                      // :198
+  const double fl_q_bottom = SCV(c, SC_FL_Q_BOTTOM);
+  {
+    double Hh = H_km1;
+    temp1 = temp1 + Hh;
+    Hh = Hh + (fl_q_bottom - fq_km1) * dt;
+    Hh = Hh + rad;
+    v.H_abs()[Na] = Hh;
+    v.S_abs()[Na] = S_km1;
+    temp2 = temp2 + Hh;
+  }
+  v.fl_Q()[1] = flQ1;
+  v.fl_Q()[Na + 1] = fl_q_bottom;  // :262
+  temp1 = temp1 + SCV(c, SC_H_ABS_SNOW);
+  SAMSIM_LOOP
+  for (int k = 1; k <= Na; k++) temp1 = temp1 + rad;  // :284
+  if (SCV(c, SC_THICK_SNOW) >= CFG.thick_min) {  // :296-299 (thin snow never takes this path)
+    const double fl_q_snow = SCV(c, SC_FL_Q_SNOW);
+    SCV(c, SC_H_ABS_SNOW) = SCV(c, SC_H_ABS_SNOW) + (flQ1 - fl_q_snow) * dt;
+    temp1 = temp1 + fl_q_bottom * dt - fl_q_snow * dt;
+  } else {
+    temp1 = temp1 + fl_q_bottom * dt - flQ1 * dt;  // :302
+  }
+  temp2 = temp2 + SCV(c, SC_H_ABS_SNOW);
+  if (c.status == 0 && fabs((temp1 - temp2) / dt) > 0.00001) c.status = 431;  // :307-310
+
   c.fb.tot_valid = true; c.fb.t1 = v.thick()[1]; c.fb.A = fbA; c.fb.G = fbG;
   c.fb.suf_valid = (ks != 0); c.fb.ks = ks; c.fb.As = fbAs; c.fb.Gs = fbGs;
   c.fb.res_valid = false;
@@ -498,11 +885,11 @@ __device__ __noinline__ void column_step(Col& c, const Forcing& f, bool want_dia
 
   }
   SAMSIM_PHASE_SYNC();
-#if SAMSIM_SYNC >= 2
-  {  // ===== phase 1: the sweep is block-uniform (barrier per layer), its body checks c.status =====
-#else
-  if (c.status == 0) {  // ===== phase 1 =====
-#endif
+  // Two-pass step (forward_pass / backward_pass above) or the general sub-step-by-sub-step path?  Decided per column
+  // after S3: the snow state and m(1) are final for this step's S10 / S11 decisions.
+  const bool next_step_outputs_pre = ((output_step ? 0 : c.n_time_out + 1) == CFG.i_time_out);
+  const bool fast = (c.status == 0) && fast_path_ok(c, output_step, want_diag || next_step_outputs_pre);
+  if (c.status == 0 && !fast) {  // ===== phase 1 =====
   // ---- S4 backward sweep: S_bu, H -> T, phi -> S_br -> volume fractions :298-307 ----
   // When nothing touched m, S_abs, H_abs of layers 2..N_active since the S18 sweep of the previous step
   // (c.thermo_valid), getT would be called with the same H, S_bu and the same chained first guess and return the
@@ -515,15 +902,8 @@ __device__ __noinline__ void column_step(Col& c, const Forcing& f, bool want_dia
     c.min_psi_s = 1e300;
     double T_test = SCV(c, SC_T_BOTTOM);
     const bool reuse = false;
-#if SAMSIM_SYNC >= 2
-    SAMSIM_LOOP
-    for (int k = CFG.Nlayer; k >= 1; k--) {
-      SAMSIM_LAYER_SYNC();
-      if (k > c.N_active || c.status != 0) continue;
-#else
     SAMSIM_LOOP
     for (int k = c.N_active; k >= 1; k--) {
-#endif
       if (k - SAMSIM_PF >= 1) {
         v.m().prefetch(k - SAMSIM_PF); v.thick().prefetch(k - SAMSIM_PF);
         if (reuse) { v.T().prefetch(k - SAMSIM_PF); v.phi().prefetch(k - SAMSIM_PF); v.S_bu().prefetch(k - SAMSIM_PF); }
@@ -611,7 +991,7 @@ __device__ __noinline__ void column_step(Col& c, const Forcing& f, bool want_dia
 
   }
   SAMSIM_PHASE_SYNC();
-  if (c.status == 0) {  // ===== phase 3 =====
+  if (c.status == 0 && !fast) {  // ===== phase 3 =====
   // ---- S9 gas in the lowest layer :405-410 ----
   {
     const int Na = c.N_active;
@@ -657,7 +1037,12 @@ __device__ __noinline__ void column_step(Col& c, const Forcing& f, bool want_dia
 
   }
   SAMSIM_PHASE_SYNC();
-  if (c.status == 0) {  // ===== phase 4 =====
+  if (c.status == 0 && fast) {  // ===== phase 4, two-pass step: S4 .. S17 in one forward pass =====
+    EVT(c, EV_TWO_PASS_STEP);
+    testcase_hooks(c, f);  // S15: these testcases' hooks depend on the clock only (fast_path_ok), so they commute with S4-S13
+    forward_pass(c);
+  }
+  if (c.status == 0 && !fast) {  // ===== phase 4 =====
   // ---- S13 gravity drainage :463-477 ----
   if (CFG.grav_flag == 2 && c.N_active > 1) {
     // ray(1:N-1) is observable through the S8 record of the next step (n_time_out was already advanced by S8 above)
@@ -689,48 +1074,9 @@ __device__ __noinline__ void column_step(Col& c, const Forcing& f, bool want_dia
 
   }
   SAMSIM_PHASE_SYNC();
-  if (c.status == 0) {  // ===== phase 5 =====
+  if (c.status == 0 && !fast) {  // ===== phase 5 =====
   // ---- S15 testcase hooks :503-563 ----
-  if (CFG.testcase == 1) {  // sub_test1, mo_testcase_specifics.f90:42-89
-    const double j = rint(c.time / 43200.0);
-    if (j >= 1.0 && j <= 20.0 && fabs(c.time - 12.0 * j * 3600.0) < SAMSIM_F32(0.01))
-      SCV(c, SC_T_TOP) = (((int)j) & 1) ? SCV(c, SC_TTOP_COLD) : SCV(c, SC_TTOP_WARM);
-  } else if (CFG.testcase >= 101 && CFG.testcase <= 105) {  // :521-530
-    const long long idx = (long long)floor(1 + c.time / dt);
-    const double Sb = v.S_bu()[c.N_active + 1];
-    SCV(c, SC_T2M) = lab_rec(f, 0, idx);
-    SCV(c, SC_SOLID_PRECIP) = lab_rec(f, 1, idx);
-    SCV(c, SC_FL_Q_BOTTOM) = lab_rec(f, 2, idx);
-    SCV(c, SC_T_BOTTOM) = -SAMSIM_F32(0.0575) * Sb + SAMSIM_F32(1.710523e-3) * det_pow(Sb, 3.0 / 2.0) -
-                          SAMSIM_F32(2.154996e-4) * P2(Sb) - SAMSIM_F32(7.53e-4) * sum_fwd(v.thick(), 1, c.N_active - 1);
-    c.styropor_flag = (int)lab_rec(f, 3, idx);
-  } else if (CFG.testcase == 4 || CFG.testcase == 7) {  // sub_test4, mo_testcase_specifics.f90:197-202
-    const double amp = SCV(c, SC_OFLUX_AMP);
-    SCV(c, SC_FL_Q_BOTTOM) = -amp * det_sin(c.time * (2.0 * pi_sp) / (86400.0 * 365.0)) + amp;
-  } else if (CFG.testcase == 2) {  // sub_test2, mo_testcase_specifics.f90:92-101
-    if (c.time > 86400.0 * 25.0) SCV(c, SC_T2M) = 15.0;
-    else if (c.time > 86400.0 * 15.0) SCV(c, SC_T2M) = 1.0;
-  } else if (CFG.testcase == 9) {  // sub_test9, :105-116
-    if (c.time < (19.75 * 3600.0)) SCV(c, SC_T2M) = 0.0;
-    else if (c.time < (86400.0 * 3.0 + 2.25 * 3600.0)) SCV(c, SC_T2M) = -15.0;
-    else SCV(c, SC_T2M) = 1.0;
-  } else if (CFG.testcase == 3) {  // sub_test3, :170-185
-    SCV(c, SC_LIQUID_PRECIP) = 0.0;
-    SCV(c, SC_SOLID_PRECIP) = 0.15 / 86400.0 / 356.0;
-  } else if (CFG.testcase == 6) {  // sub_test6, :218-243
-    const double t = c.time;
-    if (t > 1714.0 * 60.0) SCV(c, SC_T2M) = -19.0;
-    else if (t > 1676.0 * 60.0) SCV(c, SC_T2M) = -5.0;
-    else if (t > 1525.0 * 60.0) SCV(c, SC_T2M) = -18.0;
-    else if (t > 1483.0 * 60.0) SCV(c, SC_T2M) = -5.0;
-    else if (t > 1385.0 * 60.0) SCV(c, SC_T2M) = -18.0;
-    else if (t > 1349.0 * 60.0) SCV(c, SC_T2M) = -5.0;
-    else if (t > 1160.0 * 60.0) SCV(c, SC_T2M) = -18.0;
-    else if (t > 1100.0 * 60.0) SCV(c, SC_T2M) = -5.0;
-  } else if (CFG.testcase == 5 && c.i == 2) {  // mo_grotz.f90:541-542
-    SAMSIM_LOOP
-    for (int k = 1; k <= N; k++) v.S_abs()[k] = 5.0 * v.m()[k];
-  }
+  testcase_hooks(c, f);
 
   // ---- S16 tank :573-578 ----
   if (CFG.tank_flag == 2) {
@@ -747,37 +1093,15 @@ __device__ __noinline__ void column_step(Col& c, const Forcing& f, bool want_dia
 
   }
   SAMSIM_PHASE_SYNC();
-#if SAMSIM_SYNC >= 2
-  {  // ===== phase 6: the sweep is block-uniform (barrier per layer), its body checks c.status =====
-#else
   if (c.status == 0) {  // ===== phase 6 =====
-#endif
   // ---- S18 second backward sweep :592-598 (psi_* are NOT refreshed) ----
   {
-    double T_test = SCV(c, SC_T_BOTTOM);
-    double min_S2 = 1e300;
-#if SAMSIM_SYNC >= 2
-    SAMSIM_LOOP
-    for (int k = CFG.Nlayer; k >= 1; k--) {
-      SAMSIM_LAYER_SYNC();
-      if (k > c.N_active || c.status != 0) continue;
-#else
-    SAMSIM_LOOP
-    for (int k = c.N_active; k >= 1; k--) {
-#endif
-      if (k - SAMSIM_PF >= 1) { v.m().prefetch(k - SAMSIM_PF); v.S_abs().prefetch(k - SAMSIM_PF); v.H_abs().prefetch(k - SAMSIM_PF); v.phi().prefetch(k - SAMSIM_PF); }
-      const double mk = v.m()[k];
-      const double Sk = v.S_abs()[k];
-      if (k >= 2) min_S2 = f_min(min_S2, Sk);
-      const double sbu = Sk / mk;
-      const double H = v.H_abs()[k] / mk;
-      double T, phi = v.phi()[k];
-      getT_body(H, sbu, T_test, T, phi, c.status, c.ev1);  // inlined: no call, no spills around it in the hot sweep
-      T_test = T;
-      v.S_bu()[k] = sbu; v.T()[k] = T; v.phi()[k] = phi;
-    }
-    c.min_S_abs_2 = min_S2;
-    c.thermo_valid = true;  // invalidated below by anything that touches layers >= 2
+    // Prepare the next step's merged forward pass unless ray must stay as fl_grav_drain left it (observable after
+    // the launch or in the next step's S8 record).  S_bu is only observable after the launch.
+    const bool next_step_outputs = (c.n_time_out == CFG.i_time_out);
+    const bool prepare = !(c.want_state || next_step_outputs) && c.N_active >= 3 && CFG.grav_flag == 2 &&
+                         CFG.harmonic_flag == 2 && CFG.n_bgc == 0;
+    backward_pass(c, prepare, c.want_state || SAMSIM_ALWAYS_STORE_S_BU);
   }
 
   }
@@ -851,14 +1175,14 @@ __device__ __noinline__ void column_step(Col& c, const Forcing& f, bool want_dia
         SAMSIM_LOOP
         for (int k = 1; k <= Na; k++) { old_v[k] = v.flush_v()[k]; old_h[k] = v.flush_h()[k]; }
         flush3(c);
-        c.thermo_valid = false;
+        c.thermo_valid = false; c.pre.valid = false;
         SAMSIM_LOOP
         for (int k = 1; k <= Na; k++) { v.flush_v()[k] = v.flush_v()[k] + old_v[k]; v.flush_h()[k] = v.flush_h()[k] + old_h[k]; }
             }
     } else if (CFG.flush_flag == 6) {  // :729-733
       if (SCV(c, SC_MELT_THICK) > 0.000000000001 && c.N_active > 2 && SCV(c, SC_THICK_SNOW) < CFG.thick_0) {
         flush4(c);
-        c.thermo_valid = false;
+        c.thermo_valid = false; c.pre.valid = false;
             }
     }
   }
@@ -875,7 +1199,7 @@ __device__ __noinline__ void column_step(Col& c, const Forcing& f, bool want_dia
     const double r1 = v.thick()[1] / CFG.thick_0;
     if (v.phi()[Na] > psi_s_min || v.phi()[Na - 1] <= psi_s_min / 2.0 || r1 > 1.5 || r1 < 0.5) {
       layer_dynamics(c);
-      c.thermo_valid = false;
+      c.thermo_valid = false; c.pre.valid = false;
       fb_reset(c);
         }
     const int Nb = c.N_active;
@@ -888,7 +1212,7 @@ __device__ __noinline__ void column_step(Col& c, const Forcing& f, bool want_dia
       for (int q = 0; q < CFG.n_bgc; q++) v.bgc(q)[Nb + 1] = 0.0;  // :778-780
     }
   } else {
-    if (v.phi()[1] > psi_s_min) { layer_dynamics(c); c.thermo_valid = false; fb_reset(c); }
+    if (v.phi()[1] > psi_s_min) { layer_dynamics(c); c.thermo_valid = false; c.pre.valid = false; fb_reset(c); }
     }
 
   // ---- S24 timestep + health check :802-819 ----
@@ -912,7 +1236,7 @@ __device__ __noinline__ void column_step(Col& c, const Forcing& f, bool want_dia
       EVT(c, EV_SALT_CLAMP);
       SAMSIM_LOOP
       for (int k = 1; k <= Na; k++) v.S_abs()[k] = f_max(v.S_abs()[k], 0.0);
-      c.thermo_valid = false;
+      c.thermo_valid = false; c.pre.valid = false;
     }
   }
   }

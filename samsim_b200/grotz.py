@@ -23,7 +23,7 @@ class _GrotzOptions(C.Structure):
     _fields_ = [("ncol", C.c_int32), ("device", C.c_int32), ("forcing_dir", C.c_char_p), ("output_dir", C.c_char_p),
                 ("max_steps", C.c_int64), ("forcing_scale", C.POINTER(C.c_double)), ("forcing_offset", C.POINTER(C.c_double)),
                 ("ttop_warm", C.POINTER(C.c_double)), ("ttop_cold", C.POINTER(C.c_double)), ("oflux_amp", C.POINTER(C.c_double)),
-                ("quiet", C.c_int32)]
+                ("quiet", C.c_int32), ("lab_input_dir", C.c_char_p)]
 
 
 def _lib():
@@ -33,6 +33,8 @@ def _lib():
     L.samsim_host_case_free.argtypes = [C.POINTER(_HostCase)]
     L.samsim_host_read_forcing.restype = C.c_int
     L.samsim_host_read_forcing.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_double)]
+    L.samsim_host_read_lab_series.restype = C.c_int
+    L.samsim_host_read_lab_series.argtypes = [C.c_char_p, C.c_int32, C.c_int64, C.POINTER(C.c_double)]
     L.samsim_grotz.restype = C.c_int
     L.samsim_grotz.argtypes = [C.c_int32, C.c_char_p, C.POINTER(_GrotzOptions)]
     return L
@@ -69,9 +71,19 @@ def read_forcing(directory, nrec: int = 13148) -> np.ndarray:
     return out
 
 
+def read_lab_series(directory, testcase: int, nrec: int) -> np.ndarray:
+    """mo_grotz.f90:138-169: {Tice,snowfall,heat,styropor}_exp_<testcase-100>.txt -> [4, nrec]"""
+    L = _lib()
+    out = np.empty((4, nrec))
+    rc = L.samsim_host_read_lab_series(str(directory).encode(), testcase, nrec, api._dp(out))
+    if rc != 0:
+        raise api.SamsimError(rc, f"cannot read {nrec} records of the four lab series of testcase {testcase} in {directory}")
+    return out
+
+
 def grotz(testcase: int, description: str = "", *, output_dir, forcing_dir=".", ncol: int = 1, device: int = 0,
           max_steps: int = 0, forcing_scale=None, forcing_offset=None, ttop_warm=None, ttop_cold=None, oflux_amp=None,
-          quiet: bool = True) -> int:
+          quiet: bool = True, lab_input_dir="2017_input") -> int:
     """Run grotz(testcase, description) on the GPU; returns 0 or the reference STOP code of column 0."""
     L = _lib()
     Path(output_dir).mkdir(parents=True, exist_ok=True)
@@ -86,7 +98,7 @@ def grotz(testcase: int, description: str = "", *, output_dir, forcing_dir=".", 
     o = _GrotzOptions(ncol=ncol, device=device, forcing_dir=str(forcing_dir).encode(), output_dir=str(output_dir).encode(),
                       max_steps=max_steps, forcing_scale=vec(forcing_scale, (4, ncol)), forcing_offset=vec(forcing_offset, (4, ncol)),
                       ttop_warm=vec(ttop_warm, (ncol,)), ttop_cold=vec(ttop_cold, (ncol,)), oflux_amp=vec(oflux_amp, (ncol,)),
-                      quiet=int(quiet))
+                      quiet=int(quiet), lab_input_dir=str(lab_input_dir).encode())
     rc = L.samsim_grotz(testcase, description.encode(), C.byref(o))
     if rc < 0:
         raise api.SamsimError(rc, L.samsim_b200_last_error().decode())

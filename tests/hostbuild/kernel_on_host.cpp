@@ -165,6 +165,7 @@ int hostk_step(void* p, long long nsteps) {
   c.time = h->time; c.i = h->i; c.n_time_out = h->n_time_out; c.time_counter = h->time_counter;
   c.fsw0 = c.fsw1 = c.flw0 = c.flw1 = c.ftime0 = c.ftime1 = 0.0;
   c.thermo_valid = false;
+  c.pre.valid = false;
   c.want_state = false;
   c.fb.tot_valid = c.fb.suf_valid = c.fb.res_valid = false; c.fb.k_last = 0; c.fb.ks = 0;
   c.min_psi_s = 0.0; c.min_S_abs_2 = 0.0;

@@ -53,6 +53,17 @@ def test_ids_match_header():
     assert snapa == [k.lower() for k in api.SNAP_ARRAYS]
 
 
+def test_event_ids_match_header_and_oracle(oracle_mod):
+    """samsim_event_id (header) = api.EVENT_NAMES = the oracle's branch counters, same order: the parity tests compare
+    the device's event bits with the oracle's counters by name."""
+    ev = [n[len("SAMSIM_EV_"):].lower() for n in _enum_names("SAMSIM_EV_")]
+    assert ev == [k.lower() for k in api.EVENT_NAMES] and len(ev) <= 64
+    assert list(oracle_mod.Column(1, "det").event_counts()) == api.EVENT_NAMES
+    ints = [n[len("SAMSIM_INT_"):].lower() for n in _enum_names("SAMSIM_INT_")]
+    assert ints == ["n_active", "status", "styropor_flag", "events0", "events1"] and list(api.INT_IDS.values()) == [0, 1, 2, 3, 4]
+    assert api.decode_events(1 | (1 << 31), 1 | (1 << 15)) == {"flood", "salt_clamp", "gas_refill", "tank"}
+
+
 def test_config_struct_layout():
     # 26 int32 + 10 doubles, no padding surprises: the Fortran BIND(C) type in fortran/mo_samsim_b200.f90 mirrors it
     assert C.sizeof(api._CConfig) == 26 * 4 + 10 * 8

@@ -52,6 +52,22 @@ def test_read_forcing_is_sub_input(tmp_path, golden_dir):
         grotz.read_forcing(tmp_path / "missing", 10)
 
 
+def test_read_lab_series_is_the_reference_read(tmp_path):
+    """mo_grotz.f90:138-169: READ(1234,*) of 2017_input/{Tice,snowfall,heat,styropor}_exp_<N>.txt, list-directed."""
+    rng = np.random.default_rng(5)
+    want = rng.normal(size=(4, 500))
+    for name, row in zip(["Tice", "snowfall", "heat", "styropor"], want):
+        with open(tmp_path / f"{name}_exp_3.txt", "w") as f:
+            # list-directed input: blanks, commas and line breaks all separate values
+            f.write("\n".join(", ".join(repr(float(v)) for v in row[j:j + 7]) for j in range(0, 500, 7)))
+    got = grotz.read_lab_series(tmp_path, 103, 500)
+    assert np.array_equal(got, want)
+    with pytest.raises(api.SamsimError):
+        grotz.read_lab_series(tmp_path, 103, 501)   # shorter than length_input_lab
+    with pytest.raises(api.SamsimError):
+        grotz.read_lab_series(tmp_path, 104, 10)    # files of another experiment are missing
+
+
 def test_host_header_symbols_exported():
     L = api.load_library()
     hdr = (ROOT / "include" / "samsim_b200_host.h").read_text()

@@ -217,7 +217,9 @@ def test_device_code_on_host_events_of_the_standard_runs(oracle_mod, golden_dir)
         assert col.step(3000) == 0 and k.step(3000) == 0
         o = col.events()
         assert need <= o, (rec, sorted(need - o))
-        assert o == k.events(), (rec, sorted(o ^ k.events()))
+        dev = k.events() - scenarios.DEVICE_ONLY
+        assert o == dev, (rec, sorted(o ^ dev))
+        assert rec not in (80, 200) or "two_pass_step" in k.events(), rec  # the steady winter regimes take the two-pass step
 
 
 @pytest.mark.parametrize("salt_flag", [1, 2])

@@ -284,7 +284,7 @@ def test_lab_tank_batch_of_five(oracle_mod):
     assert max(c.int("N_active") for c in cols) >= 3 and max(c.stat("coupling_iters") for c in cols) > 1000  # thin lab snow: iterative snow_coupling
     for q, col in enumerate(cols):  # the branches this batch is credited with ran, on both sides
         o, g = col.events(), eng.events(q)
-        assert {"snow_coupling_iter", "tank", "heat_thin_snow"} <= o and o == g, (q, sorted(o ^ g))
+        assert {"snow_coupling_iter", "tank", "heat_thin_snow"} <= o and o == g - scenarios.DEVICE_ONLY, (q, sorted(o ^ g))
         assert "styropor" not in o  # the plate sits on snow in this series: tests/scenarios.py 'styropor' covers the factor
 
 
@@ -504,7 +504,7 @@ def test_testcase7_simple_parametrisations(oracle_mod, golden_dir):
         bad = pu.compare_column(col, eng, 1, label=f"testcase 7 +{n}: ")
         assert not bad, _fmt(bad)
     o = {k for k, v in col.event_counts().items() if v > before[k]}
-    assert "grav_drain_simple" in o and not ({"flush4", "flood_simple"} & o) and o == eng.events(1)
+    assert "grav_drain_simple" in o and not ({"flush4", "flood_simple"} & o) and o == eng.events(1) - scenarios.DEVICE_ONLY
 
 
 def test_prescribe_flag_2(oracle_mod):
@@ -614,7 +614,9 @@ def test_event_words_of_the_sheba_windows(oracle_mod, golden_dir):
         eng.step(3000)
         o = col.events()
         assert need <= o, (rec, sorted(need - o))
-        assert o == eng.events(1), (rec, sorted(o ^ eng.events(1)))
+        dev = eng.events(1) - scenarios.DEVICE_ONLY
+        assert o == dev, (rec, sorted(o ^ dev))
+        assert rec not in (80, 200) or "two_pass_step" in eng.events(1), rec  # the steady winter regimes take the two-pass step
         bad = pu.compare_column(col, eng, 1, label=f"state {rec} +3000: ")
         assert not bad, _fmt(bad)
         eng.clear_events()
