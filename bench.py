@@ -16,8 +16,19 @@ One bench "step" = MODEL_STEPS consecutive model timesteps of every column of th
            per-column diagnostics (pinned host memory) plus the 18-number ensemble reduction.
   roofline: FP64 vector pipe.  achieved = F_ALG x column-steps/s; peak = DFMA micro-benchmark run live on the same
            GPU (MEASURED_PEAKS.json has no FP64 entry); HBM view alongside (peak from MEASURED_PEAKS.json).
+  roofline.issue_ceiling: the FP64 pipe issues one instruction per lane and clock whether it is a DADD, a DMUL or a
+           DFMA, and the bit-exact contract (-fmad=false) forbids contracting a*b+c: the DFMA peak (2 flop per slot)
+           is not reachable by construction.  issue_ceiling = 148 SMs x 64 lanes x SM clock / (FP64 instructions per
+           column-step from the committed ncu capture) is the throughput at which the FP64 pipe would be saturated;
+           roofline.hw_tflops is what the hardware executed (dadd + dmul + 2 dfma), next to the algorithmic rate.
+  strong : (N > 1) the same 1,048,576-column ensemble sharded over the N ranks (fixed total), timed the same way.
+  year_weighted: (N = 1) throughput over the regimes of a SHEBA year instead of the mid-winter state alone: six
+           ensembles start from the oracle states of records 60 / 100 / 200 / 330 / 345 / 400, drift 8,640 steps (one
+           model day) under per-column forcing with re-binning on, are timed for 640 more steps, and are combined
+           with the share of the golden run's 1,643 records that each regime represents (harmonic mean = time-weighted).
   cpu_baseline / --impl reference: the CPU oracle (C port of the Fortran; no Fortran compiler exists in this image),
-           one column per OS thread on all host cores, on a bounded sample of the same columns.
+           one column per OS thread on all host cores, on a bounded sample of the same columns; the libm build (what
+           the reference binary links) is the one that is timed, the deterministic-math build is reported beside it.
 """
 from __future__ import annotations
 
@@ -45,8 +56,17 @@ SITES = ["sheba", "70N00W", "75N00W", "75N180E", "80N00E", "80N90E", "85N180E", 
 # per column-timestep from the mid-January SHEBA state (N_active = 100).
 F_ALG_FLOP_PER_COLUMN_STEP = 112930.0
 B_ALG_BYTES_PER_COLUMN_STEP = 2 * 4 * 100 * 8  # read+write of m, S_abs, H_abs, thick once per model step
-NCU_DIGEST = "r1h_ncu_step_kernel.json"          # committed ncu --set full digest of samsim_step_kernel
+NCU_DIGEST = "r2_ncu_step_kernel.json"           # committed ncu --set full digest of samsim_step_kernel
 NCU_DIGEST_COLUMN_STEPS = 262144 * 16            # columns x model steps of the launch captured there
+# Regimes of the SHEBA year: oracle restart record -> share of the golden run's 1,643 records it represents
+# (reference_output/Reference_SHEBA_with_Version_2: N_active from dat_thick, melt from dat_melt; classification in
+# open water N_active = 1; ice melt with / without a full grid; snow melt; growth; full-grid winter)
+YEAR_REGIMES = [(200, "winter, grid full", 0.6190), (345, "bare-ice melt, flushing", 0.1382), (100, "growth, grid filling", 0.1181),
+                (400, "late-summer melt, grid shrinking", 0.0493), (60, "open water / freeze-up", 0.0402),
+                (330, "melt onset, wet snow", 0.0353)]
+YEAR_COLUMNS = 151552            # one full wave of the step kernel (148 SMs x 2 blocks x 512 threads)
+YEAR_DRIFT_STEPS = 8640          # one model day
+YEAR_TIMED_STEPS = 640
 
 
 def load_state(rec: int) -> dict:
@@ -140,11 +160,11 @@ def make_oracle_columns(st: dict, sites: np.ndarray, cols: np.ndarray, backend: 
     return out
 
 
-def cpu_oracle_rate(st: dict, sites: np.ndarray, ncols: int, nsteps: int, nthreads: int, reps: int = 1):
+def cpu_oracle_rate(st: dict, sites: np.ndarray, ncols: int, nsteps: int, nthreads: int, reps: int = 1, backend: str = "libm"):
     """column-steps/s of the CPU oracle, one column per OS thread."""
     from oracle import oracle
     oracle.build()
-    cols = make_oracle_columns(st, sites, np.linspace(0, TOTAL_COLUMNS - 1, ncols).astype(np.int64))
+    cols = make_oracle_columns(st, sites, np.linspace(0, TOTAL_COLUMNS - 1, ncols).astype(np.int64), backend)
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
@@ -156,6 +176,8 @@ def cpu_oracle_rate(st: dict, sites: np.ndarray, ncols: int, nsteps: int, nthrea
 
 
 def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path on all host cores.  The Fortran cannot
+    be compiled here, so this is the oracle port in its libm build (the math library the reference binary links)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -165,7 +187,8 @@ def run_reference_arm(args):
     sample_cols = 4 * ncores
     from oracle import oracle
     oracle.build()
-    cols = make_oracle_columns(st, sites, np.linspace(0, TOTAL_COLUMNS - 1, sample_cols).astype(np.int64))
+    idx = np.linspace(0, TOTAL_COLUMNS - 1, sample_cols).astype(np.int64)
+    cols = make_oracle_columns(st, sites, idx, "libm")
     steps_per = MODEL_STEPS * 64  # 1024 model steps per bench step so that a step is ~a second of CPU work
     for _ in range(args.warmup):
         oracle.run_batch(cols, steps_per, ncores)
@@ -176,21 +199,29 @@ def run_reference_arm(args):
             raise RuntimeError(f"oracle STOP {rc}")
     dt = time.perf_counter() - t0
     value = sample_cols * steps_per * args.steps / dt
+    # the deterministic-math build (what the GPU is compared with bit for bit), one bench step, for the record
+    cols_det = make_oracle_columns(st, sites, idx, "det")
+    t0 = time.perf_counter()
+    oracle.run_batch(cols_det, steps_per, ncores)
+    value_det = sample_cols * steps_per / (time.perf_counter() - t0)
+    per = args.columns if args.scaling == "weak" else args.columns // max(args.gpus, 1)
     line = {
         "impl": "reference", "metric": "column-timesteps/sec (FP64, 100 layers)", "value": value,
         "unit": "column-timesteps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus, scaling=args.scaling, per_gpu=(args.columns if args.scaling == "weak" else args.columns // max(args.gpus, 1)), sample=f"{sample_cols} of the {TOTAL_COLUMNS} columns x {steps_per} model steps per step"),
+        "config": workload_config(args.gpus, scaling=args.scaling, per_gpu=per),
         "cpu_baseline": {"value": value, "unit": "column-timesteps/s", "cores": ncores, "kind": "port",
-                         "sample": f"{sample_cols} columns x {steps_per * args.steps} model steps, one column per thread; "
-                                   "C oracle (gcc -O2 -ffp-contract=off), the Fortran reference cannot be compiled in this image"},
+                         "sample": f"{sample_cols} of the {per * max(args.gpus, 1)} columns x {steps_per} model steps per bench step "
+                                   f"({steps_per * args.steps} timed), one column per thread; C oracle, libm build "
+                                   "(gcc -O2 -ffp-contract=off), the Fortran reference cannot be compiled in this image",
+                         "det_build_value": value_det},
         "e2e": {"value": value, "unit": "column-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def workload_config(n_gpus: int, sample: str | None = None, scaling: str = "weak", per_gpu: int | None = None) -> dict:
+def workload_config(n_gpus: int, scaling: str = "weak", per_gpu: int | None = None) -> dict:
     per = per_gpu if per_gpu is not None else (TOTAL_COLUMNS if scaling == "weak" else TOTAL_COLUMNS // n_gpus)
     cfg = {
         "workload": "config 5: 1,048,576 ERA-interim-style columns per GPU (testcase 4 flags, Nlayer 100, dt 10 s), "
@@ -200,9 +231,41 @@ def workload_config(n_gpus: int, sample: str | None = None, scaling: str = "weak
         "parallelism": f"columns sharded over {n_gpus} GPU(s), no data-path collective",
         "cache": "working set (>= 12 KB/column x columns) is far larger than the 126 MB L2; no flush needed",
     }
-    if sample:
-        cfg["sample"] = sample
     return cfg
+
+
+def make_engine(api, st: dict, sites: np.ndarray, per: int, col0: int, device: int):
+    """`per` columns of the ensemble starting at global column col0, all in state `st`, with their own forcing."""
+    cfg = api.Config.from_state({**st, "thick_min": st["thick_min"]})
+    eng = api.Engine(cfg, per, device)
+    eng.load_column_state(st, 0)
+    eng.broadcast_column(0, 0, per)
+    site, scale, offset, amp = perturbations(col0, per)
+    eng.set_forcing(sites, site, scale, offset)
+    eng.set_scalar("oflux_amp", amp)
+    return eng
+
+
+def year_weighted(api, sites: np.ndarray, device: int) -> dict:
+    """Throughput over the regimes of a SHEBA year (see the module docstring)."""
+    rows, t_per_step = [], 0.0
+    for rec, what, share in YEAR_REGIMES:
+        eng = make_engine(api, load_state(rec), sites, YEAR_COLUMNS, 0, device)
+        eng.set_rebin_interval(1080)           # re-bin every 3 model hours while the ensemble drifts apart
+        eng.step(YEAR_DRIFT_STEPS)
+        eng.step(YEAR_TIMED_STEPS // 2)        # warm
+        eng.step(YEAR_TIMED_STEPS, sync=False)
+        eng.synchronize()
+        ms = eng.last_step_ms()
+        rate = YEAR_COLUMNS * YEAR_TIMED_STEPS / (ms * 1e-3)
+        na = eng.get_int("N_active")
+        rows.append({"record": rec, "regime": what, "share": share, "value": rate, "N_active_mean": float(na.mean()),
+                     "N_active_min": int(na.min()), "N_active_max": int(na.max()), "failed_columns": int(eng.count_failed())})
+        t_per_step += share / rate
+        eng.close()
+    return {"value": 1.0 / t_per_step, "unit": "column-timesteps/s", "columns": YEAR_COLUMNS, "drift_steps": YEAR_DRIFT_STEPS,
+            "timed_steps": YEAR_TIMED_STEPS, "rebin_interval": 1080, "regimes": rows,
+            "how": "harmonic mean of the regime rates weighted by the regime's share of the golden SHEBA records"}
 
 
 def main():
@@ -215,6 +278,7 @@ def main():
                     help="columns per GPU (weak scaling, default: the config-5 ensemble) or in total (--scaling strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-year-weighted", action="store_true", help="skip the six-regime year-weighted block (N = 1 only)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -258,13 +322,7 @@ def main():
         col0, per = D.shard(total, rank, world)
     st = load_state(START_RECORD)
     sites = load_sites(64)
-    cfg = api.Config.from_state({**st, "thick_min": st["thick_min"]})
-    eng = api.Engine(cfg, per, local_rank)
-    eng.load_column_state(st, 0)
-    eng.broadcast_column(0, 0, per)
-    site, scale, offset, amp = perturbations(col0, per)
-    eng.set_forcing(sites, site, scale, offset)
-    eng.set_scalar("oflux_amp", amp)
+    eng = make_engine(api, st, sites, per, col0, local_rank)
     eng.set_snapshot_mode(api.SNAP_SCALARS_ONLY)
 
     def barrier():
@@ -273,7 +331,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- FP64 peak of this GPU (live) ----
-    fp64_peak = api.fp64_peak(local_rank, 0.5)
+    fp64_peak = api.fp64_peak(local_rank, 1.2)
 
     # ---- warm-up ----
     for _ in range(max(args.warmup, 3)):
@@ -320,10 +378,35 @@ def main():
 
     # ---- ensemble diagnostics: the only cross-GPU exchange of the model (NCCL all-reduce of 18 numbers) ----
     ensemble = D.reduce_ensemble(eng.reduce_diag(), per, device=torch.device("cuda", local_rank))
+    nf = torch.tensor([eng.count_failed()], dtype=torch.int64, device="cuda")
+
+    # ---- strong scaling: the SAME 1,048,576-column ensemble sharded over the ranks (fixed total) ----
+    strong = None
+    if world > 1 and args.scaling == "weak":
+        eng.close()
+        s_col0, s_per = D.shard(TOTAL_COLUMNS, rank, world)
+        eng_s = make_engine(api, st, sites, s_per, s_col0, local_rank)
+        for _ in range(max(args.warmup, 3)):
+            eng_s.step(MODEL_STEPS)
+        barrier()
+        t0 = time.perf_counter()
+        ms_s = 0.0
+        for _ in range(args.steps):
+            eng_s.step(MODEL_STEPS, sync=False)
+            eng_s.synchronize()
+            ms_s += eng_s.last_step_ms()
+        barrier()
+        wall_s = time.perf_counter() - t0
+        ts = torch.tensor([ms_s * 1e-3, wall_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        strong = {"columns_total": TOTAL_COLUMNS, "columns_per_gpu": int(s_per), "value": TOTAL_COLUMNS * MODEL_STEPS * args.steps / float(ts[1]),
+                  "kernel_value": TOTAL_COLUMNS * MODEL_STEPS * args.steps / float(ts[0]), "unit": "column-timesteps/s",
+                  "ms_per_step": float(ts[1]) / args.steps * 1e3,
+                  "note": "fixed total: the config-5 ensemble split over the ranks; no data-path collective"}
+        eng = eng_s
 
     # ---- max over ranks ----
     t = torch.tensor([kernel_ms * 1e-3, wall_a, wall_b], dtype=torch.float64, device="cuda")
-    nf = torch.tensor([eng.count_failed()], dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(nf, op=dist.ReduceOp.SUM)
@@ -353,8 +436,22 @@ def main():
             traffic = per_colstep * per * MODEL_STEPS
             traffic_src = (f"profiles/{NCU_DIGEST}: {per_colstep / 1e3:.1f} KB of DRAM traffic per column-step (ncu --set full, "
                            f"{NCU_DIGEST_COLUMN_STEPS} column-steps in the captured launch) x the column-steps of one launch here")
+            # FP64 pipe instructions per column-step (thread level) from the same capture -> the pipe's issue ceiling
+            cyc = float(m["sm__cycles_elapsed.max"][0])
+            pc = {op: float(m[f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed"][0]) for op in ("dadd", "dmul", "dfma")}
+            fp64_inst = sum(pc.values()) * cyc / NCU_DIGEST_COLUMN_STEPS
+            hw_flop = (pc["dadd"] + pc["dmul"] + 2.0 * pc["dfma"]) * cyc / NCU_DIGEST_COLUMN_STEPS
         except Exception:
-            pass
+            fp64_inst = hw_flop = None
+        clocks = sampler.summary()
+        issue = None
+        if fp64_inst:
+            sm_hz = (clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)) * 1e6
+            ceiling = 148 * 64 * sm_hz / fp64_inst
+            issue = {"fp64_inst_per_column_step": fp64_inst, "ceiling": ceiling, "unit": "column-timesteps/s",
+                     "frac": per_gpu_rate / ceiling, "hw_flop_per_column_step": hw_flop,
+                     "how": "148 SMs x 64 FP64 lanes x sampled SM clock / FP64 instructions per column-step (dadd + dmul + dfma, "
+                            f"profiles/{NCU_DIGEST}); with -fmad=false a multiply-add is two pipe slots, so the DFMA peak is not reachable"}
         line = {
             "metric": "column-timesteps/sec (FP64, 100 layers)", "value": value, "unit": "column-timesteps/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -368,22 +465,32 @@ def main():
                          "traffic_source": traffic_src,
                          "peak_source": "DFMA micro-benchmark on this GPU in this run (samsim_b200_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                          "flop_per_column_step": F_ALG_FLOP_PER_COLUMN_STEP,
+                         "flop_note": "operation count of the reference algorithm AS WRITTEN (oracle counting build); the kernel "
+                                      "skips work bit-identically (lazy freezing point, S4 sweep reuse, O(N) sums), so `achieved` is an "
+                                      "algorithmic rate; hw_tflops is what the hardware executed",
+                         "hw_tflops": (per_gpu_rate * hw_flop / 1e12) if hw_flop else None,
+                         "issue_ceiling": issue,
                          "kernel": "samsim_step_kernel", "kernel_ms_per_launch": kern_s / max(launches, 1) * 1e3,
                          "hbm": {"achieved": per_gpu_rate * B_ALG_BYTES_PER_COLUMN_STEP / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": per_gpu_rate * B_ALG_BYTES_PER_COLUMN_STEP / 1e9 / hbm_peak,
                                  "bytes_per_column_step": B_ALG_BYTES_PER_COLUMN_STEP,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}},
-            "clocks": sampler.summary(),
+            "clocks": clocks,
             "failed_columns": int(nf.item()),
             "ensemble": {k: ensemble[k] for k in ("thickness", "thick_snow", "N_active", "columns")},
         }
+        if strong is not None:
+            line["strong"] = strong
+        if world == 1 and not args.no_year_weighted:
+            eng.close()
+            line["year_weighted"] = year_weighted(api, sites, local_rank)
         if world == 1 and not args.no_cpu_baseline:
             ncores = os.cpu_count() or 1
             ncols_cpu, nsteps_cpu = 4 * ncores, 50000   # ~10 s of CPU work on all host cores
-            rate, times = cpu_oracle_rate(st, sites, ncols_cpu, nsteps_cpu, ncores)
+            rate, times = cpu_oracle_rate(st, sites, ncols_cpu, nsteps_cpu, ncores, backend="libm")
             line["cpu_baseline"] = {"value": rate, "unit": "column-timesteps/s", "cores": ncores, "kind": "port",
                                     "sample": f"{ncols_cpu} of the {total} columns x {nsteps_cpu} model steps, one column per thread "
-                                              f"({times[0]:.1f} s); C oracle, Fortran reference not compilable here"}
+                                              f"({times[0]:.1f} s); C oracle in its libm build, Fortran reference not compilable here"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

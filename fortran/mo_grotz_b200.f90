@@ -40,6 +40,7 @@ CONTAINS
     TYPE(C_PTR)            :: h
     TYPE(samsim_config_t)  :: cfg
     INTEGER(C_INT64_T)     :: n, done, total
+    INTEGER(C_INT32_T)     :: col_status(1)
     LOGICAL                :: wrote                 ! (the layer index k is mo_data's)
     REAL(C_DOUBLE), ALLOCATABLE :: series(:), snap_sc(:), snap_ar(:,:)
     REAL(wp), ALLOCATABLE  :: o_T(:), o_psi_s(:), o_thick(:), o_S_bu(:), o_ray(:), o_psi_l(:), o_perm(:), o_fv(:), &
@@ -74,14 +75,14 @@ CONTAINS
     cfg = b200_config_from_mo_data(testcase)
     CALL b200_check(samsim_b200_create(cfg, INT(ncol, C_INT32_T), 0_C_INT32_T, h), 'create')
     CALL b200_push_mo_data(h)
-    IF (ncol > 1) CALL b200_check(samsim_b200_broadcast_column(h, 0, 0, INT(ncol, C_INT32_T)), 'broadcast')
+    IF (ncol > 1) CALL b200_check(samsim_b200_broadcast_column(h, 0_C_INT32_T, 0_C_INT32_T, INT(ncol, C_INT32_T)), 'broadcast')
     IF (atmoflux_flag == 2) THEN            ! series[(site*4+kind)*nrec + r], kinds fl_sw, fl_lw, T2m, precip
        ALLOCATE(series(4*Length_Input))
        series(1:Length_Input)                  = fl_sw_input
        series(Length_Input+1:2*Length_Input)   = fl_lw_input
        series(2*Length_Input+1:3*Length_Input) = T2m_input
        series(3*Length_Input+1:4*Length_Input) = precip_input
-       CALL b200_check(samsim_b200_set_forcing(h, 1, INT(Length_Input, C_INT32_T), series, C_NULL_PTR, C_NULL_PTR, &
+       CALL b200_check(samsim_b200_set_forcing(h, 1_C_INT32_T, INT(Length_Input, C_INT32_T), series, C_NULL_PTR, C_NULL_PTR, &
             &                                  C_NULL_PTR), 'set_forcing')
        DEALLOCATE(series)
     END IF
@@ -91,7 +92,7 @@ CONTAINS
        series(length_input_lab+1:2*length_input_lab)   = precipinput
        series(2*length_input_lab+1:3*length_input_lab) = ocean_flux_input
        series(3*length_input_lab+1:4*length_input_lab) = styropor_input
-       CALL b200_check(samsim_b200_set_lab_forcing(h, 1, INT(length_input_lab, C_INT64_T), series, C_NULL_PTR), 'lab')
+       CALL b200_check(samsim_b200_set_lab_forcing(h, 1_C_INT32_T, INT(length_input_lab, C_INT64_T), series, C_NULL_PTR), 'lab')
        DEALLOCATE(series)
     END IF
     CALL b200_check(samsim_b200_set_snapshot_mode(h, SAMSIM_SNAP_FULL), 'snapshot mode')
@@ -104,13 +105,24 @@ CONTAINS
     done  = 0
     DO WHILE (done < total)
        n     = samsim_b200_steps_to_next_output(h)
+       IF (n <= 0) THEN                      ! cannot happen with a consistent clock; never spin on step(h, 0)
+          WRITE(*,*) 'samsim_b200: steps_to_next_output returned ', n
+          STOP 1
+       END IF
        wrote = (done + n <= total)
        n     = MIN(n, total - done)
        CALL b200_check(samsim_b200_step(h, n), 'step')
        done = done + n
+       ! the reference STOPs the moment a check fails (codes 99, 16, 345, 9876, 21234, 1337, 431, 7889); column 1 is
+       ! the drop-in column, so its status ends the run here instead of after the loop
+       CALL b200_check(samsim_b200_get_status(h, col_status, 0_C_INT32_T, 1_C_INT32_T), 'status')
+       IF (col_status(1) /= 0) THEN
+          WRITE(*,*) 'samsim_b200: column 1 stopped with the reference code ', col_status(1), ' after step ', done
+          CALL b200_stop_with(INT(col_status(1)))
+       END IF
        IF (wrote) THEN
           ! S8 (mo_grotz.f90:340-398): the device captured the record where the reference calls output()
-          CALL b200_check(samsim_b200_get_snapshot(h, snap_sc, snap_ar, 0, 1), 'snapshot')
+          CALL b200_check(samsim_b200_get_snapshot(h, snap_sc, snap_ar, 0_C_INT32_T, 1_C_INT32_T), 'snapshot')
           o_T = snap_ar(:,1);  o_psi_s = snap_ar(:,2);  o_thick = snap_ar(:,3);  o_S_bu = snap_ar(:,4)
           o_ray = snap_ar(1:Nlayer-1,5);  o_psi_l = snap_ar(:,6);  o_perm = snap_ar(:,7)
           o_fv = snap_ar(:,8);  o_fh = snap_ar(:,9);  o_psi_g = snap_ar(:,10)

@@ -223,6 +223,24 @@ CONTAINS
     END IF
   END SUBROUTINE b200_check
 
+  !> Re-raises a reference STOP code reported by the device for the drop-in column (STOP needs a constant in
+  !> Fortran 2003, hence the SELECT over the codes the path can raise; SURVEY section 4).
+  SUBROUTINE b200_stop_with(code)
+    INTEGER, INTENT(in) :: code
+    SELECT CASE (code)
+    CASE (99);    STOP 99
+    CASE (98);    STOP 98
+    CASE (16);    STOP 16
+    CASE (345);   STOP 345
+    CASE (9876);  STOP 9876
+    CASE (21234); STOP 21234
+    CASE (1337);  STOP 1337
+    CASE (431);   STOP 431
+    CASE (7889);  STOP 7889
+    CASE DEFAULT; STOP 1
+    END SELECT
+  END SUBROUTINE b200_stop_with
+
   !> Builds samsim_config_t from the flags and scalars init() left in mo_data (mo_init.f90:83-132, :1982-2009).
   FUNCTION b200_config_from_mo_data(testcase) RESULT(cfg)
     USE mo_data
@@ -268,21 +286,21 @@ CONTAINS
     USE mo_data
     TYPE(C_PTR), INTENT(in) :: h
     INTEGER(C_INT32_T) :: ibuf(1)
-    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_M,       m,       0, 1), 'm')
-    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_S_ABS,   S_abs,   0, 1), 'S_abs')
-    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_H_ABS,   H_abs,   0, 1), 'H_abs')
-    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_THICK,   thick,   0, 1), 'thick')
-    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_T,       T,       0, 1), 'T')
-    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_PHI,     phi,     0, 1), 'phi')
-    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_S_BU,    S_bu,    0, 1), 'S_bu')
-    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_PSI_S,   psi_s,   0, 1), 'psi_s')
-    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_PSI_L,   psi_l,   0, 1), 'psi_l')
-    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_PSI_G,   psi_g,   0, 1), 'psi_g')
-    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_RAY,     ray,     0, 1), 'ray')
-    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_PERM,    perm,    0, 1), 'perm')
-    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_FLUSH_V, flush_v, 0, 1), 'flush_v')
-    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_FLUSH_H, flush_h, 0, 1), 'flush_h')
-    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_FL_Q,    fl_Q,    0, 1), 'fl_Q')
+    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_M,       m,       0_C_INT32_T, 1_C_INT32_T), 'm')
+    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_S_ABS,   S_abs,   0_C_INT32_T, 1_C_INT32_T), 'S_abs')
+    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_H_ABS,   H_abs,   0_C_INT32_T, 1_C_INT32_T), 'H_abs')
+    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_THICK,   thick,   0_C_INT32_T, 1_C_INT32_T), 'thick')
+    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_T,       T,       0_C_INT32_T, 1_C_INT32_T), 'T')
+    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_PHI,     phi,     0_C_INT32_T, 1_C_INT32_T), 'phi')
+    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_S_BU,    S_bu,    0_C_INT32_T, 1_C_INT32_T), 'S_bu')
+    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_PSI_S,   psi_s,   0_C_INT32_T, 1_C_INT32_T), 'psi_s')
+    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_PSI_L,   psi_l,   0_C_INT32_T, 1_C_INT32_T), 'psi_l')
+    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_PSI_G,   psi_g,   0_C_INT32_T, 1_C_INT32_T), 'psi_g')
+    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_RAY,     ray,     0_C_INT32_T, 1_C_INT32_T), 'ray')
+    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_PERM,    perm,    0_C_INT32_T, 1_C_INT32_T), 'perm')
+    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_FLUSH_V, flush_v, 0_C_INT32_T, 1_C_INT32_T), 'flush_v')
+    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_FLUSH_H, flush_h, 0_C_INT32_T, 1_C_INT32_T), 'flush_h')
+    CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_FL_Q,    fl_Q,    0_C_INT32_T, 1_C_INT32_T), 'fl_Q')
     CALL put_sc(h, SC_T_BOTTOM, T_bottom);        CALL put_sc(h, SC_T_TOP, T_top)
     CALL put_sc(h, SC_S_BU_BOTTOM, S_bu_bottom);  CALL put_sc(h, SC_T2M, T2m)
     CALL put_sc(h, SC_FL_Q_BOTTOM, fl_q_bottom)
@@ -305,17 +323,17 @@ CONTAINS
     CALL put_sc(h, SC_TTOP_COLD, -10._C_DOUBLE)
     CALL put_sc(h, SC_OFLUX_AMP, 7._C_DOUBLE)
     IF (bgc_flag == 2) THEN                       ! passive tracers: bgc_abs(:,k) is a contiguous column
-       CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_BGC_ABS1, bgc_abs(:,1), 0, 1), 'bgc_abs(:,1)')
+       CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_BGC_ABS1, bgc_abs(:,1), 0_C_INT32_T, 1_C_INT32_T), 'bgc_abs(:,1)')
        CALL put_sc(h, SC_BGC_BOTTOM1, bgc_bottom(1));  CALL put_sc(h, SC_BGC_TOTAL1, bgc_total(1))
        IF (N_bgc >= 2) THEN
-          CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_BGC_ABS2, bgc_abs(:,2), 0, 1), 'bgc_abs(:,2)')
+          CALL b200_check(samsim_b200_set_array(h, SAMSIM_ARR_BGC_ABS2, bgc_abs(:,2), 0_C_INT32_T, 1_C_INT32_T), 'bgc_abs(:,2)')
           CALL put_sc(h, SC_BGC_BOTTOM2, bgc_bottom(2));  CALL put_sc(h, SC_BGC_TOTAL2, bgc_total(2))
        END IF
     END IF
     ibuf(1) = N_active
-    CALL b200_check(samsim_b200_set_int(h, SAMSIM_INT_N_ACTIVE, ibuf, 0, 1), 'N_active')
+    CALL b200_check(samsim_b200_set_int(h, SAMSIM_INT_N_ACTIVE, ibuf, 0_C_INT32_T, 1_C_INT32_T), 'N_active')
     ibuf(1) = styropor_flag
-    CALL b200_check(samsim_b200_set_int(h, SAMSIM_INT_STYROPOR_FLAG, ibuf, 0, 1), 'styropor_flag')
+    CALL b200_check(samsim_b200_set_int(h, SAMSIM_INT_STYROPOR_FLAG, ibuf, 0_C_INT32_T, 1_C_INT32_T), 'styropor_flag')
     CALL b200_check(samsim_b200_set_clock(h, time, INT(i - 1, C_INT64_T), n_time_out, MAX(time_counter, 1)), 'clock')
   END SUBROUTINE b200_push_mo_data
 
@@ -327,26 +345,26 @@ CONTAINS
     INTEGER(C_INT32_T) :: ibuf(1)
     INTEGER(C_INT64_T) :: i64
     CALL b200_check(samsim_b200_synchronize(h), 'sync')
-    CALL b200_check(samsim_b200_get_status(h, ibuf, 0, 1), 'status')
+    CALL b200_check(samsim_b200_get_status(h, ibuf, 0_C_INT32_T, 1_C_INT32_T), 'status')
     IF (ibuf(1) /= 0) THEN
        PRINT*, 'column 1 stopped with the reference STOP code', ibuf(1)
        STOP 1
     END IF
-    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_M,       m,       0, 1), 'm')
-    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_S_ABS,   S_abs,   0, 1), 'S_abs')
-    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_H_ABS,   H_abs,   0, 1), 'H_abs')
-    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_THICK,   thick,   0, 1), 'thick')
-    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_T,       T,       0, 1), 'T')
-    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_PHI,     phi,     0, 1), 'phi')
-    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_S_BU,    S_bu,    0, 1), 'S_bu')
-    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_PSI_S,   psi_s,   0, 1), 'psi_s')
-    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_PSI_L,   psi_l,   0, 1), 'psi_l')
-    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_PSI_G,   psi_g,   0, 1), 'psi_g')
-    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_RAY,     ray,     0, 1), 'ray')
-    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_PERM,    perm,    0, 1), 'perm')
-    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_FLUSH_V, flush_v, 0, 1), 'flush_v')
-    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_FLUSH_H, flush_h, 0, 1), 'flush_h')
-    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_FL_Q,    fl_Q,    0, 1), 'fl_Q')
+    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_M,       m,       0_C_INT32_T, 1_C_INT32_T), 'm')
+    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_S_ABS,   S_abs,   0_C_INT32_T, 1_C_INT32_T), 'S_abs')
+    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_H_ABS,   H_abs,   0_C_INT32_T, 1_C_INT32_T), 'H_abs')
+    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_THICK,   thick,   0_C_INT32_T, 1_C_INT32_T), 'thick')
+    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_T,       T,       0_C_INT32_T, 1_C_INT32_T), 'T')
+    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_PHI,     phi,     0_C_INT32_T, 1_C_INT32_T), 'phi')
+    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_S_BU,    S_bu,    0_C_INT32_T, 1_C_INT32_T), 'S_bu')
+    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_PSI_S,   psi_s,   0_C_INT32_T, 1_C_INT32_T), 'psi_s')
+    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_PSI_L,   psi_l,   0_C_INT32_T, 1_C_INT32_T), 'psi_l')
+    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_PSI_G,   psi_g,   0_C_INT32_T, 1_C_INT32_T), 'psi_g')
+    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_RAY,     ray,     0_C_INT32_T, 1_C_INT32_T), 'ray')
+    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_PERM,    perm,    0_C_INT32_T, 1_C_INT32_T), 'perm')
+    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_FLUSH_V, flush_v, 0_C_INT32_T, 1_C_INT32_T), 'flush_v')
+    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_FLUSH_H, flush_h, 0_C_INT32_T, 1_C_INT32_T), 'flush_h')
+    CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_FL_Q,    fl_Q,    0_C_INT32_T, 1_C_INT32_T), 'fl_Q')
     CALL get_sc(h, SC_T_BOTTOM, T_bottom);        CALL get_sc(h, SC_T_TOP, T_top)
     CALL get_sc(h, SC_S_BU_BOTTOM, S_bu_bottom);  CALL get_sc(h, SC_T2M, T2m)
     CALL get_sc(h, SC_FL_Q_BOTTOM, fl_q_bottom)
@@ -368,16 +386,16 @@ CONTAINS
     CALL get_sc(h, SC_MTO3, melt_thick_output(3)); CALL get_sc(h, SC_FREEBOARD, freeboard)
     CALL get_sc(h, SC_T_FREEZE, T_freeze);        CALL get_sc(h, SC_MELT_ERR, melt_err)
     IF (bgc_flag == 2) THEN
-       CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_BGC_ABS1, bgc_abs(:,1), 0, 1), 'bgc_abs(:,1)')
+       CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_BGC_ABS1, bgc_abs(:,1), 0_C_INT32_T, 1_C_INT32_T), 'bgc_abs(:,1)')
        CALL get_sc(h, SC_BGC_BOTTOM1, bgc_bottom(1))
        IF (N_bgc >= 2) THEN
-          CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_BGC_ABS2, bgc_abs(:,2), 0, 1), 'bgc_abs(:,2)')
+          CALL b200_check(samsim_b200_get_array(h, SAMSIM_ARR_BGC_ABS2, bgc_abs(:,2), 0_C_INT32_T, 1_C_INT32_T), 'bgc_abs(:,2)')
           CALL get_sc(h, SC_BGC_BOTTOM2, bgc_bottom(2))
        END IF
     END IF
-    CALL b200_check(samsim_b200_get_int(h, SAMSIM_INT_N_ACTIVE, ibuf, 0, 1), 'N_active')
+    CALL b200_check(samsim_b200_get_int(h, SAMSIM_INT_N_ACTIVE, ibuf, 0_C_INT32_T, 1_C_INT32_T), 'N_active')
     N_active = ibuf(1)
-    CALL b200_check(samsim_b200_get_int(h, SAMSIM_INT_STYROPOR_FLAG, ibuf, 0, 1), 'styropor_flag')
+    CALL b200_check(samsim_b200_get_int(h, SAMSIM_INT_STYROPOR_FLAG, ibuf, 0_C_INT32_T, 1_C_INT32_T), 'styropor_flag')
     styropor_flag = ibuf(1)
     CALL b200_check(samsim_b200_get_clock(h, time, i64, n_time_out, time_counter), 'clock')
   END SUBROUTINE b200_pull_mo_data

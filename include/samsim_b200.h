@@ -271,6 +271,13 @@ int samsim_b200_last_step_ms(samsim_handle_t h, float* ms);
  * differ do not share a warp.  Results do not depend on it (columns are independent); every entry point keeps
  * taking the caller's column numbers.  *changed = 1 if the device order changed. */
 int samsim_b200_rebin(samsim_handle_t h, int32_t* changed);
+/* Kernel tuning; results do not depend on it (bitwise, tests/test_parity_gpu.py runs both settings).
+ * two_pass = 1: columns in a steady regime (no flooding, flushing or layer event, a snow layer of its own or no snow)
+ * advance a step in two sweeps over their layers -- S4..S17 merged into one forward pass, S18 plus the next step's
+ * Rayleigh-number estimates in one backward pass -- 21 array passes per step instead of 34 and
+ * 30 % less DRAM traffic; the general sub-step-by-sub-step path (two_pass = 0, the default) is currently the faster
+ * one on B200 because the merged pass is register-starved at 64 registers per thread. */
+int samsim_b200_set_tuning(samsim_handle_t h, int32_t two_pass);
 /* re-bin automatically every nsteps steps inside samsim_b200_step (0 = never, the default) */
 int samsim_b200_set_rebin_interval(samsim_handle_t h, int64_t nsteps);
 /* slot_of_col[c] = position of column c in the device arrays (identity until the first re-binning) */

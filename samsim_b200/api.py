@@ -181,6 +181,7 @@ def load_library() -> C.CDLL:
         "samsim_b200_save_checkpoint": (C.c_int, [H, C.c_char_p]),
         "samsim_b200_load_checkpoint": (C.c_int, [H, C.c_char_p]),
         "samsim_b200_rebin": (C.c_int, [H, ip]),
+        "samsim_b200_set_tuning": (C.c_int, [H, C.c_int32]),
         "samsim_b200_set_rebin_interval": (C.c_int, [H, C.c_int64]),
         "samsim_b200_get_slot_map": (C.c_int, [H, ip]),
         "samsim_b200_kat_getT": (C.c_int, [C.c_int32, C.c_int32, dp, dp, dp, dp, dp, ip, C.c_int32]),
@@ -204,7 +205,7 @@ EXPORTED_SYMBOLS = [
     "samsim_b200_step", "samsim_b200_synchronize", "samsim_b200_steps_to_next_output",
     "samsim_b200_set_snapshot_mode", "samsim_b200_get_snapshot", "samsim_b200_get_status",
     "samsim_b200_count_failed", "samsim_b200_reduce_diag", "samsim_b200_launch_count", "samsim_b200_last_step_ms",
-    "samsim_b200_device_layout", "samsim_b200_save_checkpoint", "samsim_b200_load_checkpoint", "samsim_b200_rebin", "samsim_b200_set_rebin_interval", "samsim_b200_get_slot_map",
+    "samsim_b200_device_layout", "samsim_b200_save_checkpoint", "samsim_b200_load_checkpoint", "samsim_b200_rebin", "samsim_b200_set_tuning", "samsim_b200_set_rebin_interval", "samsim_b200_get_slot_map",
     "samsim_b200_kat_getT", "samsim_b200_kat_scalar", "samsim_b200_fp64_peak",
 ]
 
@@ -408,6 +409,10 @@ class Engine:
         v = C.c_int32()
         _check(self.L, self.L.samsim_b200_rebin(self.h, C.byref(v)))
         return bool(v.value)
+
+    def set_tuning(self, two_pass: bool) -> None:
+        """kernel tuning (results do not depend on it): merged forward / backward passes for steady columns"""
+        _check(self.L, self.L.samsim_b200_set_tuning(self.h, int(bool(two_pass))))
 
     def set_rebin_interval(self, nsteps: int) -> None:
         _check(self.L, self.L.samsim_b200_set_rebin_interval(self.h, int(nsteps)))

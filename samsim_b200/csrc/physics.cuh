@@ -40,6 +40,8 @@ struct DevCfg {
   double max_flux_plate, k_snow_flush, k_styropor;
   // liquidus coefficients for salt_flag
   double c2, c3, c4, d2, d3x2, d4x3;
+  // tuning (samsim_b200_set_tuning; results do not depend on it)
+  int two_pass;   // 1: steady columns take the merged forward / backward passes of step.cuh
 };
 
 // The configuration of the running launch.  On the device it lives in constant memory so that flags, dt and the

@@ -933,6 +933,15 @@ int samsim_b200_rebin(samsim_handle_t h, int32_t* changed) {
   return 0;
 }
 
+int samsim_b200_set_tuning(samsim_handle_t h, int32_t two_pass) {
+  if (!h || two_pass < 0 || two_pass > 1) return fail(SAMSIM_ERR_ARG, "set_tuning: bad argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  h->dcfg.two_pass = two_pass;
+  release_device_cfg(h);  // the next launch uploads the configuration again
+  return 0;
+}
+
 int samsim_b200_set_rebin_interval(samsim_handle_t h, int64_t nsteps) {
   if (!h || nsteps < 0) return fail(SAMSIM_ERR_ARG, "set_rebin_interval: bad argument");
   h->rebin_every = nsteps;

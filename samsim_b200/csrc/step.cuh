@@ -586,8 +586,14 @@ __device__ __noinline__ void backward_pass(Col& c, bool prepare, bool store_S_bu
   c.pre.A2 = A2;
 }
 
+// The two-pass step is selected per handle at run time (samsim_b200_set_tuning); -DSAMSIM_TWO_PASS=0 compiles it out.
+#ifndef SAMSIM_TWO_PASS
+#define SAMSIM_TWO_PASS 1
+#endif
+
 // May this column take the merged forward pass in this step?  Everything here is a per-column, per-step decision.
 __device__ __forceinline__ bool fast_path_ok(const Col& c, bool output_step, bool observable_after) {
+  if (!SAMSIM_TWO_PASS || !CFG.two_pass) return false;
   if (!(c.thermo_valid && c.pre.valid) || output_step || observable_after) return false;
   if (c.N_active < 3 || c.i == 1) return false;
   if (CFG.grav_flag != 2 || CFG.harmonic_flag != 2 || CFG.n_bgc != 0 || CFG.prescribe_flag == 2 || CFG.tank_flag == 2) return false;
@@ -606,208 +612,381 @@ __device__ __forceinline__ bool fast_path_ok(const Col& c, bool output_step, boo
   return true;
 }
 
+// One layer of S4 (volume fractions) + S5 (expulsion_flux, mass_transfer) + S7 for the forward pass.
+// In: the layer's S4 values (m, S_abs, H_abs, thick, T, phi, S_bu = S_abs/m), its neighbours' S4 values, fl_m(k) = f0.
+// Out: psi_* (psi_g after expulsion_flux), fl_m(k+1) = f1, m, S_abs, H_abs after the transfer.
+//
+// expulsion_flux only ever produces fl_m <= 0 (V_ex >= 0, mo_mass.f90:121-134: -V_ex*rho_l + fl_m(k) with fl_m(1) = 0, or
+// -MAX(.., 0)), so of mass_transfer's four branches (mo_mass.f90:76-95) only `fl_m(k+1) < 0` (the layer loses its own
+// brine) and `fl_m(k) < 0` (it receives the brine of the layer above) can be taken here: the layer BELOW is never read,
+// and the forward pass needs no look-ahead.  (NaN fluxes take neither branch, exactly like the general routine.)
+struct Expelled { double ps, pl, pg, f1, m_new, S, H; };
+__device__ __forceinline__ Expelled expel_layer(int k, double phi_k, double thk, double m_k, double Sabs_k, double H_k, double T_k,
+                                                double sbu_k, double f0, double T_km1, double SbuE_km1, double SabsE_km1) {
+  Expelled e;
+  double vex;
+  expulsion(phi_k, thk, m_k, e.ps, e.pl, e.pg, vex);
+  if (k == 1) {  // fl_m(k+1), mo_mass.f90:121-134
+    e.f1 = -vex * rho_l;
+  } else if (e.pg < SAMSIM_F32(0.001)) {
+    e.f1 = -vex * rho_l + f0;
+  } else {
+    e.f1 = -f_max((vex - e.pg * thk) * rho_l, 0.0);
+    e.pg = f_max((e.pg * thk - vex) / thk, 0.0);
+  }
+  e.m_new = m_k + e.f1 - f0;
+  e.S = Sabs_k; e.H = H_k;
+  if (e.f1 < 0.) {  // mo_mass.f90:82-84
+    e.H = e.H + e.f1 * T_k * c_l;
+    e.S = e.S + f_max(e.f1 * S_br_of(T_k, sbu_k), -e.S);
+  }
+  if (f0 < 0) {     // :89-92 (S_abs(k-1) is the value the transfer of layer k-1 left)
+    e.H = e.H - f0 * T_km1 * c_l;
+    e.S = e.S - f_max(f0 * S_br_of(T_km1, SbuE_km1), -SabsE_km1);
+  }
+  return e;
+}
+
+// S9 gas in the lowest layer (mo_grotz.f90:405-410) and S12 sub_turb_flux (mo_functions.f90:347-363) on layer N_active
+__device__ __forceinline__ void bottom_layer_updates(Col& c, double pg, double thk, double T_Na, double& m_new, double& S, double& H) {
+  const double T_bottom = SCV(c, SC_T_BOTTOM), S_bu_bottom = SCV(c, SC_S_BU_BOTTOM);
+  if (pg > 0.0) {
+    EVT(c, EV_GAS_REFILL);
+    const double g2 = pg * thk * rho_l;
+    m_new = m_new + g2;
+    S = S + g2 * S_bu_bottom;
+    H = H + g2 * c_l * T_bottom;
+  }
+  if (CFG.turb_flag == 2) {
+    EVT(c, EV_TURB);
+    const double turb = Turb_A * det_exp(Turb_B * (-density_of(T_bottom, S_bu_bottom) + density_of(T_Na, S / m_new))) * CFG.dt;
+    S = S - turb * (S / m_new - S_bu_bottom);
+  }
+}
+
+// ray(k) by the reference's forward sums (mo_grav_drain.f90:115-120, :128, :126-136) for one layer whose estimate can
+// exceed ray_crit.  Out of line: the forward pass calls it for the few candidate layers only.
+__device__ __noinline__ double exact_ray(const Col& c, int k, double sbr_k) {
+  const View v = c;
+  const int Na = c.N_active;
+  const double bottom_h = c.pre.bottom_h;
+  const double qb = bottom_h / c.pre.perm_Na;
+  Lay q = v.w1();
+  double hq = 0.0, ht = 0.0, hb = 0.0;
+  SAMSIM_LOOP
+  for (int kk = k; kk <= Na - 1; kk++) {
+    const double tv = v.thick()[kk];
+    hq = hq + q[kk];
+    ht = ht + tv;
+    if (kk > k) hb = hb + tv;
+  }
+  double hp = hq + qb;  // the estimate was > 0, so minval(perm(k:Na-1)) >= 1e-14 (:112) holds
+  hp = (ht + bottom_h) / hp;
+  double r = grav * rho_l * bbeta * (sbr_k - c.pre.S_br_Na) * (hb + bottom_h) * hp;
+  r = r / (kappa_l * mu);
+  return f_max(r, 0.0);
+}
+// Layer 1 of the Rayleigh estimate (layers >= 2 were prepared by backward_pass); stores thick(1)/perm(1) for exact_ray.
+__device__ __noinline__ double ray_estimate_layer1(const Col& c, double pl, double thk, double sbr_1) {
+  const View v = c;
+  const double bottom_h = c.pre.bottom_h;
+  const double qb = bottom_h / c.pre.perm_Na;
+  const double pk = 1e-17 * det_pow(1000.0 * fabs(pl), 3.10);
+  const double qk = thk / pk;
+  v.w1()[1] = qk;
+  const double mn = (c.N_active == 2) ? pk : f_min(c.pre.mn2, pk);
+  const double hp = (mn < 1e-14) ? 0.0 : ((c.pre.st2 + thk) + bottom_h) / ((c.pre.sq2 + qk) + qb);
+  double est = grav * rho_l * bbeta * (sbr_1 - c.pre.S_br_Na) * (c.pre.st2 + bottom_h) * hp;
+  est = est / (kappa_l * mu);
+  return (mn < 1e-14) ? 0.0 : f_max(est, 0.0);
+}
+// One draining layer (mo_grav_drain.f90:146-166): S_abs, H_abs of the layer, the accumulators, fl_up(k) (returned).
+// Returns a negative value on STOP 21234.
+__device__ __noinline__ double drain_layer(Col& c, double rk, double thk, double pl, double T_k, double sbr_k, double& S, double& H,
+                                           double& run, double& heat_loss) {
+  double flux = x_grav * (rk - ray_crit) * CFG.dt * thk;
+  flux = f_min(flux, pl * rho_l * thk);
+  S = S - flux * sbr_k;
+  if (S < 0.0) { c.status = 21234; return -1.0; }
+  SCV(c, SC_GRAV_TEMP) = SCV(c, SC_GRAV_TEMP) + flux * T_k;
+  H = H - flux * c_l * T_k;
+  heat_loss = heat_loss + flux * c_l * T_k;
+  run = run + flux;
+  return f_min(run, pl * rho_l * thk);
+}
+
+#ifndef SAMSIM_MERGE_HEAT
+#define SAMSIM_MERGE_HEAT 1   // 1: sub_heat_fluxes' layer update rides along phase A of the forward pass; 0: it stays a sweep of its own
+#endif
+
 // S4 .. S17 of one step in one forward pass (see the block comment above).  Preconditions: fast_path_ok().
+//
+// Phase A (layers above the first draining layer kfirst): per iteration k the layer is expelled (E), its drain
+// decision is taken (D), and layer k-1 gets its heat-flux update (Q) -- gravity drainage moves nothing above kfirst,
+// so those layers are final.  Phase B (k >= kfirst, typically the warm bottom fifth of the column): E and D only;
+// the drainage mass_transfer (which needs S_abs(k+1) after ITS drain) and the heat update of these layers follow in
+// the reference's own order on the layers kfirst..N_active.  The loops touch nothing of `c`: every per-column scalar
+// they need is a local, rare events are out-of-line calls, the minima of the health checks are sign flags.
 __device__ __noinline__ void forward_pass(Col& c) {
   const View v = c;
   const int Na = c.N_active;
   const double dt = CFG.dt;
   const double T_bottom = SCV(c, SC_T_BOTTOM), S_bu_bottom = SCV(c, SC_S_BU_BOTTOM);
-  const double bottom_h = c.pre.bottom_h, S_br_Na = c.pre.S_br_Na;
-  const double qb = bottom_h / c.pre.perm_Na;
-  Lay q = v.w1();
+  const double cand = ray_crit * (1.0 - 1e-10);
+  const bool merge_heat = SAMSIM_MERGE_HEAT;
+
+  double temp1 = 0.0, temp2 = 0.0;             // energy check sums, mo_heat_fluxes.f90:269, :305
+  double sum_before = 0.0, sum_after = 0.0;    // SUM(S_abs) of mo_grav_drain.f90:141 / :173
+  double fbA = 0.0, fbG = 0.0, fbAs = 0.0, fbGs = 0.0;  // func_freeboard memo
+  bool neg_ps = false, neg_S = false;          // MINVAL(psi_s) < 0 (S24), MINVAL(S_abs) < 0 (:198): only the sign is used
+  const int ks = (c.fb.k_last >= 1 && c.fb.k_last < Na) ? c.fb.k_last : 0;
+  int kfirst = 0;
+  double run = 0.0, heat_loss = 0.0;
+  double H_km1 = 0.0, hr_km1 = 0.0, fq_km1 = 0.0, rad = 0.0, flQ1 = 0.0;  // Q: layer k-1 waiting for its lower flux
 
   // ---- layer 1: the S4 getT (layers >= 2 keep T, phi of the S18 sweep: same inputs, same first-guess chain) ----
-  double m_k = v.m()[1], Sabs_k = v.S_abs()[1], H_k = v.H_abs()[1], thk = v.thick()[1];
-  double sbu_k = Sabs_k / m_k;                 // S_bu(k) of S4 (:299)
-  double T_k, phi_k = v.phi()[1];
-  getT(H_k / m_k, sbu_k, v.T()[2], T_k, phi_k, c.status, c.ev1);
-  v.T()[1] = T_k; v.phi()[1] = phi_k;
-
-  // carried between iterations: layer k-1 after expulsion (E), drainage (D); layer k-2 after the drainage transfer (G)
-  double T_km1 = 0.0, SbuE_km1 = 0.0, SabsE_km1 = 0.0;       // S4 values / S_abs after E, for E(k)'s mass_transfer
-  double Sbu7_km1 = 0.0, S_km1 = 0.0, H_km1 = 0.0, hr_km1 = 0.0, up_km1 = 0.0;
-  double T_km2 = 0.0, Sbu7_km2 = 0.0, S_km2 = 0.0, up_km2 = 0.0;
-  double f0 = 0.0;                                           // fl_m(k) of expulsion_flux
-  double fq_km1 = 0.0, rad = 0.0, flQ1 = 0.0;                // heat: flux into layer k-1 from above, fl_rad(Na)*dt
-  double run = 0.0, heat_loss = 0.0, sum_before = 0.0, sum_after = 0.0, min_S = 1e300;
-  int kfirst = 0;
-  double temp1 = 0.0, temp2 = 0.0;                           // energy check sums, mo_heat_fluxes.f90:269, :305
-  // func_freeboard memo and S24 minimum, as in fused_thermo_expulsion
-  double fbA = 0.0, fbG = 0.0, fbAs = 0.0, fbGs = 0.0, min_ps = 1e300;
-  const int ks = (c.fb.k_last >= 1 && c.fb.k_last < Na) ? c.fb.k_last : 0;
-  // suffix quantities of the Rayleigh estimate, extended to layer 1 inside the loop
-  double sbr_k = S_br_of(T_k, sbu_k);                        // S_br(k) of S4 (:304)
-
-  SAMSIM_LOOP
-  for (int k = 1; k <= Na; k++) {
-    if (k + 1 + SAMSIM_PF <= Na) {
-      const int kp = k + 1 + SAMSIM_PF;
-      v.T().prefetch(kp); v.phi().prefetch(kp); v.m().prefetch(kp); v.thick().prefetch(kp); v.S_abs().prefetch(kp);
-      v.H_abs().prefetch(kp); v.ray().prefetch(kp);
-    }
-    // ---- neighbour below, S4 values: T, S_bu = S_abs/m (:299), S_br (:304) ----
-    double T_kp1, Sbu_kp1, Sabs_kp1, phi_kp1 = 0.0, m_kp1 = 0.0, sbr_kp1 = 0.0;
-    if (k < Na) {
-      T_kp1 = v.T()[k + 1]; Sabs_kp1 = v.S_abs()[k + 1]; phi_kp1 = v.phi()[k + 1]; m_kp1 = v.m()[k + 1];
-      Sbu_kp1 = Sabs_kp1 / m_kp1;
-      sbr_kp1 = S_br_of(T_kp1, Sbu_kp1);
+  double T_km1, SbuE_km1, SabsE_km1, f0;       // E: layer k-1's S4 values, its S_abs after the transfer, fl_m(k)
+  {
+    const double m_k = v.m()[1], Sabs_k = v.S_abs()[1], H_k = v.H_abs()[1], thk = v.thick()[1];
+    const double sbu_k = Sabs_k / m_k;                 // S_bu(k) of S4 (:299)
+    double T_k, phi_k = v.phi()[1];
+    getT(H_k / m_k, sbu_k, v.T()[2], T_k, phi_k, c.status, c.ev1);
+    v.T()[1] = T_k; v.phi()[1] = phi_k;
+    // ---- E(1), D(1) peeled: layer 1 has no upper neighbour, makes its own Rayleigh estimate, and (when it does not
+    //      drain) is final right away, so the surface energy balance can be evaluated before the loop ----
+    Expelled e = expel_layer(1, phi_k, thk, m_k, Sabs_k, H_k, T_k, sbu_k, 0.0, 0.0, 0.0, 0.0);
+    v.psi_s()[1] = e.ps; v.psi_l()[1] = e.pl; v.psi_g()[1] = e.pg; v.m()[1] = e.m_new;
+    fbA = fbA + e.ps * thk;
+    fbG = fbG + e.pg * thk;
+    neg_ps = neg_ps || (e.ps < 0.0);
+    const double SabsE_1 = e.S;
+    const double sbr_1 = S_br_of(T_k, sbu_k);
+    double rk = ray_estimate_layer1(c, e.pl, thk, sbr_1);
+    if (rk > cand) rk = exact_ray(c, 1, sbr_1);
+    sum_before = sum_before + e.S;
+    if (rk > ray_crit && e.ps > 0.001 && e.S / e.m_new > 0.1 && sbr_1 > S_br_of(v.T()[2], v.S_abs()[2] / v.m()[2])) {
+      kfirst = 1;
+      EVT(c, EV_GRAV_DRAINED);
+      const double up = drain_layer(c, rk, thk, e.pl, T_k, sbr_1, e.S, e.H, run, heat_loss);
+      if (up < 0.0) return;
+      sum_after = 0.0 + e.S;
+      v.S_abs()[1] = e.S; v.H_abs()[1] = e.H;
+      v.S_bu()[1] = SabsE_1 / e.m_new;  // S7
+      v.fl_m()[1] = 0.0; v.fl_m()[2] = up;
     } else {
-      T_kp1 = T_bottom; Sbu_kp1 = S_bu_bottom; Sabs_kp1 = S_bu_bottom * 2000.0;
-    }
-
-    // ================= E(k): S4 volume fractions, S5 expulsion_flux + mass_transfer, S7 =================
-    double ps, pl, pg, vex;
-    expulsion(phi_k, thk, m_k, ps, pl, pg, vex);
-    double f1;  // fl_m(k+1), mo_mass.f90:121-134
-    if (k == 1) {
-      f1 = -vex * rho_l;
-    } else if (pg < SAMSIM_F32(0.001)) {
-      f1 = -vex * rho_l + f0;
-    } else {
-      f1 = -f_max((vex - pg * thk) * rho_l, 0.0);
-      pg = f_max((pg * thk - vex) / thk, 0.0);
-    }
-    v.psi_s()[k] = ps; v.psi_l()[k] = pl; v.psi_g()[k] = pg;
-    fbA = fbA + ps * thk;
-    fbG = fbG + pg * thk;
-    if (ks && k > ks) { fbAs = fbAs + ps * thk; fbGs = fbGs + pg * thk; }
-    min_ps = f_min(min_ps, ps);
-    double m_new = m_k + f1 - f0;
-    double S = Sabs_k, H = H_k;
-    mass_transfer_layer(f1, f0, T_km1, SbuE_km1, SabsE_km1, T_k, sbu_k, T_kp1, Sbu_kp1, Sabs_kp1, H, S);  // (i != 1 here)
-    const double SabsE_k = S;
-    const double Sbu7_k = S / m_new;           // S7 (:333-335)
-    if (k == Na) {
-      // ---- S9 gas in the lowest layer :405-410, S12 sub_turb_flux (mo_functions.f90:347-363) ----
-      if (pg > 0.0) {
-        EVT(c, EV_GAS_REFILL);
-        const double g2 = pg * thk * rho_l;
-        m_new = m_new + g2;
-        S = S + g2 * S_bu_bottom;
-        H = H + g2 * c_l * T_bottom;
-      }
-      if (CFG.turb_flag == 2) {
-        EVT(c, EV_TURB);
-        const double turb = Turb_A * det_exp(Turb_B * (-density_of(T_bottom, S_bu_bottom) + density_of(T_k, S / m_new))) * dt;
-        S = S - turb * (S / m_new - S_bu_bottom);
-      }
-    }
-    v.m()[k] = m_new;
-
-    // ================= D(k): the drain decision of layer k, mo_grav_drain.f90:126-171 =================
-    double up_k = run;
-    if (k < Na) {
-      double rk;
-      if (k == 1) {
-        // layer 1 of the Rayleigh estimate (layers >= 2 were prepared by backward_pass)
-        const double pk = 1e-17 * det_pow(1000.0 * fabs(pl), 3.10);
-        const double qk = thk / pk;
-        q[1] = qk;
-        const double mn = (Na == 2) ? pk : f_min(c.pre.mn2, pk);
-        const double hp = (mn < 1e-14) ? 0.0 : ((c.pre.st2 + thk) + bottom_h) / ((c.pre.sq2 + qk) + qb);
-        double est = grav * rho_l * bbeta * (sbr_k - S_br_Na) * (c.pre.st2 + bottom_h) * hp;
-        est = est / (kappa_l * mu);
-        rk = (mn < 1e-14) ? 0.0 : f_max(est, 0.0);
-      } else {
-        rk = v.ray()[k];
-      }
-      if (rk > ray_crit * (1.0 - 1e-10)) {
-        // candidate: the reference's forward sums (:115-120, :128) for this layer only, then ray(k) as at :126-136
-        double hq = 0.0, ht = 0.0, hb = 0.0;
-        SAMSIM_LOOP
-        for (int kk = k; kk <= Na - 1; kk++) {
-          const double tv = v.thick()[kk];
-          hq = hq + q[kk];
-          ht = ht + tv;
-          if (kk > k) hb = hb + tv;
-        }
-        double hp = hq + qb;  // the estimate was > 0, so minval(perm(k:Na-1)) >= 1e-14 (:112) holds
-        hp = (ht + bottom_h) / hp;
-        double r = grav * rho_l * bbeta * (sbr_k - S_br_Na) * (hb + bottom_h) * hp;
-        r = r / (kappa_l * mu);
-        rk = f_max(r, 0.0);
-      }
-      sum_before = sum_before + S;
-      if (rk > ray_crit && ps > 0.001 && S / m_new > 0.1 && sbr_k > sbr_kp1) {  // :145
-        if (kfirst == 0) { kfirst = k; EVT(c, EV_GRAV_DRAINED); }
-        double flux = x_grav * (rk - ray_crit) * dt * thk;
-        flux = f_min(flux, pl * rho_l * thk);
-        S = S - flux * sbr_k;
-        if (S < 0.0) { c.status = 21234; return; }
-        SCV(c, SC_GRAV_TEMP) = SCV(c, SC_GRAV_TEMP) + flux * T_k;
-        H = H - flux * c_l * T_k;
-        heat_loss = heat_loss + flux * c_l * T_k;
-        run = run + flux;
-        up_k = f_min(run, pl * rho_l * thk);
-      } else {
-        up_k = run;
-      }
-      sum_after = sum_after + S;
-    }
-    if (!kfirst) up_k = 0.0;  // fl_m(2:kfirst) = 0: nothing moves above the first draining layer (run is still 0 there)
-
-    // ================= G(k-1), Q(k-1): drainage transfer and heat update of the layer above =================
-    const double hr_k = thk / (2.0 * (ps * k_s + pl * k_l + ((k == 1) ? pg * 0.0 : 0.0 * 0.0)));  // half resistance, sub_fl_Q
-    if (k >= 2) {
-      if (kfirst && k - 1 >= kfirst)
-        mass_transfer_layer(up_km1, up_km2, T_km2, Sbu7_km2, S_km2, T_km1, Sbu7_km1, T_k, Sbu7_k, S, H_km1, S_km1);
-      if (k == 2) {
-        // ---- surface energy balance (needs S_abs(1) after the drainage transfer), mo_heat_fluxes.f90:77-195 ----
+      v.S_abs()[1] = e.S;
+      neg_S = neg_S || (e.S < 0.0);
+      if (merge_heat) {  // surface energy balance, mo_heat_fluxes.f90:77-195 (layer 1 is final)
         double fl_rad_Na;
-        const SurfIn in = {v.psi_s()[1], v.psi_l()[1], v.psi_g()[1], v.thick()[1], v.T()[1], S_km1, v.m()[1], 0.0, 0.0, v.fl_Q()[1]};
+        const SurfIn in = {e.ps, e.pl, e.pg, thk, T_k, e.S, e.m_new, 0.0, 0.0, v.fl_Q()[1]};
         flQ1 = heat_surface(c, in, fl_rad_Na);
         fq_km1 = flQ1;
         rad = fl_rad_Na * dt;
+        H_km1 = e.H;
+        hr_km1 = thk / (2.0 * (e.ps * k_s + e.pl * k_l + e.pg * 0.0));  // half resistance of layer 1, sub_fl_Q
+      } else {
+        v.H_abs()[1] = e.H;
       }
-      const double fq_k = (T_k - T_km1) / (hr_km1 + hr_k);  // fl_Q(k), :272-274
-      double Hh = H_km1;
-      temp1 = temp1 + Hh;                  // :269
-      Hh = Hh + (fq_k - fq_km1) * dt;      // :277-279
-      Hh = Hh + rad;                       // :282-285 (sic)
-      v.H_abs()[k - 1] = Hh;
-      v.S_abs()[k - 1] = S_km1;
-      temp2 = temp2 + Hh;
-      min_S = f_min(min_S, S_km1);
-      fq_km1 = fq_k;
     }
+    T_km1 = T_k; SbuE_km1 = sbu_k; SabsE_km1 = SabsE_1; f0 = e.f1;
+  }
 
-    // ---- shift the window ----
-    T_km2 = T_km1; Sbu7_km2 = Sbu7_km1; S_km2 = S_km1; up_km2 = up_km1;
-    T_km1 = T_k; SbuE_km1 = sbu_k; SabsE_km1 = SabsE_k; Sbu7_km1 = Sbu7_k; S_km1 = S; H_km1 = H; hr_km1 = hr_k; up_km1 = up_k;
-    f0 = f1;
-    if (k < Na) {
-      T_k = T_kp1; sbu_k = Sbu_kp1; phi_k = phi_kp1; m_k = m_kp1; Sabs_k = Sabs_kp1; sbr_k = sbr_kp1;
-      thk = v.thick()[k + 1]; H_k = v.H_abs()[k + 1];
+  // =============================== phase A: k = 2 .. kfirst (or N_active) ===============================
+  int k = 2;
+  if (!kfirst) {
+    SAMSIM_LOOP
+    for (; k <= Na; k++) {
+      if (k + SAMSIM_PF <= Na) {
+        const int kp = k + SAMSIM_PF;
+        v.T().prefetch(kp); v.phi().prefetch(kp); v.m().prefetch(kp); v.thick().prefetch(kp); v.S_abs().prefetch(kp);
+        v.H_abs().prefetch(kp); v.ray().prefetch(kp);
+      }
+      // ---- the layer's S4 values: T, phi of the S18 sweep, S_bu = S_abs/m (:299) ----
+      const double m_k = v.m()[k], Sabs_k = v.S_abs()[k], H_k = v.H_abs()[k], thk = v.thick()[k], T_k = v.T()[k], phi_k = v.phi()[k];
+      const double sbu_k = Sabs_k / m_k;
+      // ---- E(k) ----
+      Expelled e = expel_layer(k, phi_k, thk, m_k, Sabs_k, H_k, T_k, sbu_k, f0, T_km1, SbuE_km1, SabsE_km1);
+      v.psi_s()[k] = e.ps; v.psi_l()[k] = e.pl; v.psi_g()[k] = e.pg;
+      fbA = fbA + e.ps * thk;
+      fbG = fbG + e.pg * thk;
+      if (ks && k > ks) { fbAs = fbAs + e.ps * thk; fbGs = fbGs + e.pg * thk; }
+      neg_ps = neg_ps || (e.ps < 0.0);
+      const double SabsE_k = e.S;
+      if (k == Na) bottom_layer_updates(c, e.pg, thk, T_k, e.m_new, e.S, e.H);
+      v.m()[k] = e.m_new;
+      // ---- Q(k-1): heat update of the layer above (final: nothing drains above kfirst) ----
+      double hr_k = 0.0;
+      if (merge_heat) {
+        hr_k = thk / (2.0 * (e.ps * k_s + e.pl * k_l + 0.0 * 0.0));  // half resistance, sub_fl_Q
+        const double fq_k = (T_k - T_km1) / (hr_km1 + hr_k);          // fl_Q(k), :272-274
+        double Hh = H_km1;
+        temp1 = temp1 + Hh;                  // :269
+        Hh = Hh + (fq_k - fq_km1) * dt;      // :277-279
+        Hh = Hh + rad;                       // :282-285 (sic)
+        v.H_abs()[k - 1] = Hh;
+        temp2 = temp2 + Hh;
+        fq_km1 = fq_k;
+      }
+      // ---- D(k): does this layer drain?  (mo_grav_drain.f90:145) ----
+      bool drains = false;
+      if (k < Na) {
+        double rk = v.ray()[k];
+        if (rk > cand) {
+          const double sbr_k = S_br_of(T_k, sbu_k);
+          rk = exact_ray(c, k, sbr_k);
+          if (rk > ray_crit && e.ps > 0.001 && e.S / e.m_new > 0.1 && sbr_k > S_br_of(v.T()[k + 1], v.S_abs()[k + 1] / v.m()[k + 1])) {
+            // first draining layer: the layers from here on are settled in phase B
+            drains = true;
+            kfirst = k;
+            EVT(c, EV_GRAV_DRAINED);
+            const double prefix = sum_before;   // SUM(S_abs) before (:141) and after (:173) share the terms 1..kfirst-1
+            sum_before = prefix + e.S;
+            const double up = drain_layer(c, rk, thk, e.pl, T_k, sbr_k, e.S, e.H, run, heat_loss);
+            if (up < 0.0) return;
+            sum_after = prefix + e.S;
+            v.S_abs()[k] = e.S; v.H_abs()[k] = e.H;
+            v.S_bu()[k] = SabsE_k / e.m_new;                          // S7 of layer k
+            v.S_bu()[k - 1] = v.S_abs()[k - 1] / v.m()[k - 1];        // S7 of layer k-1 (it did not drain: S_abs is its S5 value)
+            v.fl_m()[k] = 0.0;
+            v.fl_m()[k + 1] = up;
+          }
+        }
+      }
+      if (!drains) {
+        if (k < Na) sum_before = sum_before + e.S;
+        v.S_abs()[k] = e.S;
+        neg_S = neg_S || (e.S < 0.0);
+        if (!merge_heat) v.H_abs()[k] = e.H;
+      }
+      // ---- shift the window ----
+      T_km1 = T_k; SbuE_km1 = sbu_k; SabsE_km1 = SabsE_k; H_km1 = e.H; hr_km1 = hr_k;
+      f0 = e.f1;
+      if (drains) { k++; break; }
     }
   }
 
-  // ================= layer N_active: G(Na), grav_heat, Q(Na) =================
-  // S_abs(Na) enters both SUM(S_abs) of :141 / :173 with its value before the drainage transfer
-  sum_before = sum_before + S_km1;
-  sum_after = sum_after + S_km1;
-  SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) + sum_before;
-  SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) - sum_after;
-  if (kfirst)
-    mass_transfer_layer(run, up_km2, T_km2, Sbu7_km2, S_km2, T_km1, Sbu7_km1, T_bottom, S_bu_bottom, S_bu_bottom * 2000.0, H_km1, S_km1);
-  SCV(c, SC_GRAV_DRAIN) = SCV(c, SC_GRAV_DRAIN) + run;                                   // :190
-  if (CFG.grav_heat_flag == 2) H_km1 = H_km1 + heat_loss - run * c_l * T_bottom;        // :193-195
-  min_S = f_min(min_S, S_km1);
-  if (f_min(min_S, 0.0) < 0.0) { c.status = 1337; }                                      // :198
   const double fl_q_bottom = SCV(c, SC_FL_Q_BOTTOM);
-  {
-    double Hh = H_km1;
-    temp1 = temp1 + Hh;
-    Hh = Hh + (fl_q_bottom - fq_km1) * dt;
-    Hh = Hh + rad;
-    v.H_abs()[Na] = Hh;
-    v.S_abs()[Na] = S_km1;
-    temp2 = temp2 + Hh;
+  if (!kfirst) {
+    // nothing drained: SUM(S_abs) before = after (:141, :173), no transfer; layer N_active awaits its heat update
+    const double S_Na = v.S_abs()[Na];  // after S9 / S12
+    sum_before = sum_before + S_Na;
+    SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) + sum_before;
+    SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) - sum_before;
+    SCV(c, SC_GRAV_DRAIN) = SCV(c, SC_GRAV_DRAIN) + run;                                // :190 (run = 0)
+    double H_Na = H_km1;
+    if (CFG.grav_heat_flag == 2) H_Na = H_Na + heat_loss - run * c_l * T_bottom;       // :193-195 (adds 0 - 0)
+    if (neg_S) c.status = 1337;                                                          // :198
+    if (merge_heat) {
+      temp1 = temp1 + H_Na;
+      H_Na = H_Na + (fl_q_bottom - fq_km1) * dt;
+      H_Na = H_Na + rad;
+      v.H_abs()[Na] = H_Na;
+      temp2 = temp2 + H_Na;
+    } else {
+      v.H_abs()[Na] = H_Na;
+    }
+  } else {
+    // =============================== phase B: k = kfirst+1 .. N_active, E and D only ===============================
+    SAMSIM_LOOP
+    for (; k <= Na; k++) {
+      if (k + SAMSIM_PF <= Na) {
+        const int kp = k + SAMSIM_PF;
+        v.T().prefetch(kp); v.phi().prefetch(kp); v.m().prefetch(kp); v.thick().prefetch(kp); v.S_abs().prefetch(kp);
+        v.H_abs().prefetch(kp); v.ray().prefetch(kp);
+      }
+      const double m_k = v.m()[k], Sabs_k = v.S_abs()[k], H_k = v.H_abs()[k], thk = v.thick()[k], T_k = v.T()[k], phi_k = v.phi()[k];
+      const double sbu_k = Sabs_k / m_k;
+      Expelled e = expel_layer(k, phi_k, thk, m_k, Sabs_k, H_k, T_k, sbu_k, f0, T_km1, SbuE_km1, SabsE_km1);
+      v.psi_s()[k] = e.ps; v.psi_l()[k] = e.pl; v.psi_g()[k] = e.pg;
+      fbA = fbA + e.ps * thk;
+      fbG = fbG + e.pg * thk;
+      if (ks && k > ks) { fbAs = fbAs + e.ps * thk; fbGs = fbGs + e.pg * thk; }
+      neg_ps = neg_ps || (e.ps < 0.0);
+      const double SabsE_k = e.S;
+      v.S_bu()[k] = e.S / e.m_new;  // S7
+      if (k == Na) bottom_layer_updates(c, e.pg, thk, T_k, e.m_new, e.S, e.H);
+      v.m()[k] = e.m_new;
+      double up_k = run;
+      if (k < Na) {
+        sum_before = sum_before + e.S;
+        double rk = v.ray()[k];
+        if (rk > cand) {
+          const double sbr_k = S_br_of(T_k, sbu_k);
+          rk = exact_ray(c, k, sbr_k);
+          if (rk > ray_crit && e.ps > 0.001 && e.S / e.m_new > 0.1 && sbr_k > S_br_of(v.T()[k + 1], v.S_abs()[k + 1] / v.m()[k + 1])) {
+            up_k = drain_layer(c, rk, thk, e.pl, T_k, sbr_k, e.S, e.H, run, heat_loss);
+            if (up_k < 0.0) return;
+          }
+        }
+        sum_after = sum_after + e.S;
+      }
+      v.S_abs()[k] = e.S; v.H_abs()[k] = e.H;
+      v.fl_m()[k + 1] = up_k;  // fl_m(k+1) = fl_up(k); for k = N_active that is the running sum (:162-164, :177)
+      T_km1 = T_k; SbuE_km1 = sbu_k; SabsE_km1 = SabsE_k;
+      f0 = e.f1;
+    }
+    const double S_Na = v.S_abs()[Na];
+    sum_before = sum_before + S_Na;
+    sum_after = sum_after + S_Na;
+    SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) + sum_before;  // :141
+    SCV(c, SC_GRAV_SALT) = SCV(c, SC_GRAV_SALT) - sum_after;   // :173
+    mass_transfer(c, v.fl_m(), v.S_bu(), kfirst);               // :188
+    SCV(c, SC_GRAV_DRAIN) = SCV(c, SC_GRAV_DRAIN) + run;        // :190
+    if (CFG.grav_heat_flag == 2) v.H_abs()[Na] = v.H_abs()[Na] + heat_loss - run * c_l * T_bottom;  // :193-195
+    SAMSIM_LOOP
+    for (int kk = kfirst; kk <= Na; kk++) neg_S = neg_S || (v.S_abs()[kk] < 0.0);
+    if (neg_S) c.status = 1337;                                  // :198
+    if (merge_heat) {
+      // ---- heat update of layers kfirst .. N_active (mo_heat_fluxes.f90:272-285) ----
+      int j = kfirst;
+      double T_j = v.T()[j];
+      double hr_j;
+      if (j == 1) {
+        double fl_rad_Na;
+        const SurfIn in = {v.psi_s()[1], v.psi_l()[1], v.psi_g()[1], v.thick()[1], v.T()[1], v.S_abs()[1], v.m()[1], 0.0, 0.0, v.fl_Q()[1]};
+        flQ1 = heat_surface(c, in, fl_rad_Na);
+        fq_km1 = flQ1;
+        rad = fl_rad_Na * dt;
+        hr_j = v.thick()[1] / (2.0 * (v.psi_s()[1] * k_s + v.psi_l()[1] * k_l + v.psi_g()[1] * 0.0));
+      } else {
+        hr_j = hr_km1;  // layer kfirst's half resistance and the flux into it were evaluated with Q(kfirst-1)
+      }
+      SAMSIM_LOOP
+      for (; j <= Na; j++) {
+        double fq_jp1, hr_n = 0.0, T_n = 0.0;
+        if (j < Na) {
+          const double ps_n = v.psi_s()[j + 1], pl_n = v.psi_l()[j + 1], th_n = v.thick()[j + 1];
+          T_n = v.T()[j + 1];
+          hr_n = th_n / (2.0 * (ps_n * k_s + pl_n * k_l + 0.0 * 0.0));
+          fq_jp1 = (T_n - T_j) / (hr_j + hr_n);
+        } else {
+          fq_jp1 = fl_q_bottom;
+        }
+        double Hh = v.H_abs()[j];
+        temp1 = temp1 + Hh;
+        Hh = Hh + (fq_jp1 - fq_km1) * dt;
+        Hh = Hh + rad;
+        v.H_abs()[j] = Hh;
+        temp2 = temp2 + Hh;
+        fq_km1 = fq_jp1; hr_j = hr_n; T_j = T_n;
+      }
+    }
+  }
+
+  c.fb.tot_valid = true; c.fb.t1 = v.thick()[1]; c.fb.A = fbA; c.fb.G = fbG;
+  c.fb.suf_valid = (ks != 0); c.fb.ks = ks; c.fb.As = fbAs; c.fb.Gs = fbGs;
+  c.fb.res_valid = false;
+  c.min_psi_s = neg_ps ? -1.0 : 1.0;  // S24 reads the sign only
+
+  if (!merge_heat) {
+    if (c.status == 0) heat_fluxes(c);  // S17 as a sweep of its own
+    return;
   }
   v.fl_Q()[1] = flQ1;
   v.fl_Q()[Na + 1] = fl_q_bottom;  // :262
   temp1 = temp1 + SCV(c, SC_H_ABS_SNOW);
   SAMSIM_LOOP
-  for (int k = 1; k <= Na; k++) temp1 = temp1 + rad;  // :284
+  for (int kk = 1; kk <= Na; kk++) temp1 = temp1 + rad;  // :284
   if (SCV(c, SC_THICK_SNOW) >= CFG.thick_min) {  // :296-299 (thin snow never takes this path)
     const double fl_q_snow = SCV(c, SC_FL_Q_SNOW);
     SCV(c, SC_H_ABS_SNOW) = SCV(c, SC_H_ABS_SNOW) + (flQ1 - fl_q_snow) * dt;
@@ -817,11 +996,6 @@ __device__ __noinline__ void forward_pass(Col& c) {
   }
   temp2 = temp2 + SCV(c, SC_H_ABS_SNOW);
   if (c.status == 0 && fabs((temp1 - temp2) / dt) > 0.00001) c.status = 431;  // :307-310
-
-  c.fb.tot_valid = true; c.fb.t1 = v.thick()[1]; c.fb.A = fbA; c.fb.G = fbG;
-  c.fb.suf_valid = (ks != 0); c.fb.ks = ks; c.fb.As = fbAs; c.fb.Gs = fbGs;
-  c.fb.res_valid = false;
-  c.min_psi_s = min_ps;
 }
 
 __device__ __noinline__ void column_step(Col& c, const Forcing& f, bool want_diag, const SnapOut& snap) {
@@ -1099,7 +1273,7 @@ __device__ __noinline__ void column_step(Col& c, const Forcing& f, bool want_dia
     // Prepare the next step's merged forward pass unless ray must stay as fl_grav_drain left it (observable after
     // the launch or in the next step's S8 record).  S_bu is only observable after the launch.
     const bool next_step_outputs = (c.n_time_out == CFG.i_time_out);
-    const bool prepare = !(c.want_state || next_step_outputs) && c.N_active >= 3 && CFG.grav_flag == 2 &&
+    const bool prepare = SAMSIM_TWO_PASS && CFG.two_pass && !(c.want_state || next_step_outputs) && c.N_active >= 3 && CFG.grav_flag == 2 &&
                          CFG.harmonic_flag == 2 && CFG.n_bgc == 0;
     backward_pass(c, prepare, c.want_state || SAMSIM_ALWAYS_STORE_S_BU);
   }

@@ -50,7 +50,8 @@ def gather_columns(values, group=None, dst: int = 0):
 
 def _uneven(out, values, group):
     import torch.distributed as dist
-    for r, buf in enumerate(out):
+    for r, buf in enumerate(out):  # r = rank inside `group`; broadcast wants the GLOBAL rank of the source
         if r == dist.get_rank(group):
             buf.copy_(values)
-        dist.broadcast(buf, src=r, group=group)
+        src = dist.get_global_rank(group, r) if group is not None else r
+        dist.broadcast(buf, src=src, group=group)

@@ -41,6 +41,7 @@ def lib():
         L.hostk_create.restype = C.c_void_p
         L.hostk_create.argtypes = [C.POINTER(api._CConfig)]
         L.hostk_destroy.argtypes = [C.c_void_p]
+        L.hostk_set_tuning.argtypes = [C.c_void_p, C.c_int]
         L.hostk_set_array.argtypes = [C.c_void_p, C.c_int, dp, C.c_int]
         L.hostk_get_array.argtypes = [C.c_void_p, C.c_int, dp, C.c_int]
         L.hostk_scalars.restype = dp
@@ -77,6 +78,9 @@ class HostKernel:
         if getattr(self, "h", None):
             self.L.hostk_destroy(self.h)
             self.h = None
+
+    def set_tuning(self, two_pass: bool):
+        self.L.hostk_set_tuning(self.h, int(bool(two_pass)))
 
     def extent(self, name: str) -> int:
         N = self.cfg.Nlayer

@@ -87,6 +87,7 @@ void* hostk_create(const samsim_config_t* cfg) {
 }
 
 void hostk_destroy(void* p) { delete (HostKernel*)p; }
+void hostk_set_tuning(void* p, int two_pass) { ((HostKernel*)p)->g.two_pass = two_pass; }
 
 static int slot_of_public(int id) { return (id < AR_STATE_COUNT) ? id : AR_BGC1 + (id - AR_STATE_COUNT); }
 

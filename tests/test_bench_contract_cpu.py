@@ -22,6 +22,11 @@ def test_reference_arm_prints_one_json_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert "workload" in d["config"] and "model" not in d["config"]
+    # same `config` as the repo arm prints for this launch (the sample lives in cpu_baseline): the driver compares them
+    sys.path.insert(0, str(ROOT))
+    import bench
+    assert d["config"] == bench.workload_config(1, scaling="weak", per_gpu=bench.TOTAL_COLUMNS)
+    assert "sample" not in d["config"] and "libm" in cb["sample"] and cb["det_build_value"] > 1e3
 
 
 def test_main_arm_needs_a_gpu():

@@ -19,9 +19,10 @@ def _fmt(bad, n=10):
     return "\n".join(bad[:n]) + (f"\n... {len(bad)} mismatches" if len(bad) > n else "")
 
 
-def _from_oracle(col):
+def _from_oracle(col, two_pass=False):
     k = hk.HostKernel(pu.config_from_oracle(col))
     k.load_state(col.state())
+    k.set_tuning(two_pass)
     return k
 
 
@@ -38,6 +39,7 @@ def _advance(col, k, chunks):
         assert not bad, _fmt(bad)
 
 
+@pytest.mark.parametrize("two_pass", [False, True])
 @pytest.mark.parametrize("testcase,chunks", [
     (1, (1, 1, 7, 100, 3493, 3601, 12000)),          # plate cooling, NaCl, two tracers, first output records
     (2, (1, 2, 5000, 15000)),                         # tank + tracers, boundflux 3
@@ -46,16 +48,19 @@ def _advance(col, k, chunks):
     (6, (1, 2, 70000)),                               # small tank, one tracer, dt 0.5 s
     (9, (1, 2, 12000)),
 ])
-def test_device_code_on_host_equals_oracle_from_init(oracle_mod, testcase, chunks):
+def test_device_code_on_host_equals_oracle_from_init(oracle_mod, testcase, chunks, two_pass):
     col = oracle_mod.Column(testcase, "det")
-    _advance(col, _from_oracle(col), chunks)
+    if two_pass and testcase == 1:
+        col.set_int("bgc_flag", 1)  # without its tracers testcase 1 is eligible for the two-pass step
+    _advance(col, _from_oracle(col, two_pass), chunks)
 
 
+@pytest.mark.parametrize("two_pass", [False, True])
 @pytest.mark.parametrize("rec,chunks", [
     (60, (1, 500, 2500)), (100, (1, 700, 1500)), (200, (3, 400, 1200)), (330, (1, 900, 1500)),
     (345, (2, 600, 1500)), (400, (1, 800, 1200)),
 ])
-def test_device_code_on_host_equals_oracle_in_the_sheba_year(oracle_mod, golden_dir, rec, chunks):
+def test_device_code_on_host_equals_oracle_in_the_sheba_year(oracle_mod, golden_dir, rec, chunks, two_pass):
     """Restart states of the SHEBA run: freeze-up, winter growth, full grid, melt onset with flushing, bare-ice melt
     with layer merges, late-summer bottom melt."""
     z = np.load(golden_dir / "sheba_oracle_states.npz")
@@ -63,9 +68,11 @@ def test_device_code_on_host_equals_oracle_in_the_sheba_year(oracle_mod, golden_
     col = oracle_mod.Column(4, "det")
     col.set_forcing(*F)
     col.load_state(_state(z, rec))
-    k = _from_oracle(col)
+    k = _from_oracle(col, two_pass)
     k.set_forcing(F)
     _advance(col, k, chunks)
+    took = "two_pass_step" in k.events()
+    assert not (took and not two_pass) and (took or not two_pass or rec not in (100, 200)), (rec, two_pass, took)
 
 
 def test_device_code_on_host_output_record_and_simple_parametrisations(oracle_mod, golden_dir):
@@ -184,12 +191,13 @@ def test_device_code_on_host_stop_codes(oracle_mod, what):
         assert not bad, _fmt(bad)
 
 
+@pytest.mark.parametrize("two_pass", [False, True])
 @pytest.mark.parametrize("name", scenarios.NAMES)
-def test_device_code_on_host_constructed_branch_scenarios(oracle_mod, name):
+def test_device_code_on_host_constructed_branch_scenarios(oracle_mod, name, two_pass):
     """Branches the SHEBA year never enters (tests/scenarios.py): bitwise state AND proof that the branch ran on both
     sides (oracle branch counters > 0, device event bits set, and the two event sets equal)."""
     sc = scenarios.build(oracle_mod, name)
-    k = _from_oracle(sc.col)
+    k = _from_oracle(sc.col, two_pass)
     if sc.forcing is not None:
         k.set_forcing(sc.forcing)
     if sc.lab is not None:
@@ -212,7 +220,7 @@ def test_device_code_on_host_events_of_the_standard_runs(oracle_mod, golden_dir)
         col = oracle_mod.Column(4, "det")
         col.set_forcing(*F)
         col.load_state(_state(z, rec))
-        k = _from_oracle(col)
+        k = _from_oracle(col, two_pass=True)
         k.set_forcing(F)
         assert col.step(3000) == 0 and k.step(3000) == 0
         o = col.events()

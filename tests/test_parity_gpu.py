@@ -139,9 +139,10 @@ SHEBA_WINDOWS = {
 }
 
 
-@pytest.mark.parametrize("rec", sorted(SHEBA_WINDOWS))
-def test_sheba_windows(oracle_mod, golden_dir, rec):
-    """Restart both implementations from an oracle state of the SHEBA run and advance 2 days."""
+@pytest.mark.parametrize("rec,two_pass", [(r, False) for r in sorted(SHEBA_WINDOWS)] + [(r, True) for r in (100, 200, 345, 1000)])
+def test_sheba_windows(oracle_mod, golden_dir, rec, two_pass):
+    """Restart both implementations from an oracle state of the SHEBA run and advance 2 days (general path; and with
+    the two-pass step switched on for the winter, growth and melt windows)."""
     z = np.load(golden_dir / "sheba_oracle_states.npz")
     st = _state(z, rec)
     F = _forcing(golden_dir)
@@ -149,6 +150,7 @@ def test_sheba_windows(oracle_mod, golden_dir, rec):
     col.set_forcing(*F)
     col.load_state(st)
     eng = pu.engine_from_oracle(col, ncol=2)
+    eng.set_tuning(two_pass)
     eng.set_forcing(F[None])
     ev0 = {k: col.stat(k) for k in ("layer_events", "flush_calls", "coupling_iters")}
     for n in (1, 999, 8641, 7641):
@@ -157,6 +159,7 @@ def test_sheba_windows(oracle_mod, golden_dir, rec):
         bad = pu.compare_column(col, eng, 1, label=f"rec {rec} (+{n}): ")
         assert not bad, SHEBA_WINDOWS[rec] + "\n" + _fmt(bad)
     print(rec, SHEBA_WINDOWS[rec], {k: col.stat(k) - ev0[k] for k in ev0})
+    assert ("two_pass_step" in eng.events(1)) == two_pass
 
 
 def test_snapshot_matches_oracle_output(oracle_mod, golden_dir):
@@ -577,8 +580,9 @@ def test_tracers_tank_and_snapshot(oracle_mod):
         assert abs(col.scalar("bgc_bottom1") - 385.0) > 1e-6  # the tank budget really moved the water concentration
 
 
+@pytest.mark.parametrize("two_pass", [False, True])
 @pytest.mark.parametrize("name", scenarios.NAMES)
-def test_constructed_branch_scenarios(oracle_mod, name):
+def test_constructed_branch_scenarios(oracle_mod, name, two_pass):
     """Branches that neither the SHEBA year nor the testcases from `init` enter (tests/scenarios.py): flood incl. the
     instant flooding beyond neg_free, flood_simple, flush4, flush_flag 4, snow_thermo with snow_flush_flag 0, the
     top_grow / top_melt sub-cases, bottom_melt(_simple) with a full grid, the warm branches of snow_coupling,
@@ -586,6 +590,7 @@ def test_constructed_branch_scenarios(oracle_mod, name):
     AND proof that each branch ran: oracle counters > 0, device event bits set, the two event sets equal."""
     sc = scenarios.build(oracle_mod, name)
     eng = pu.engine_from_oracle(sc.col, ncol=33)
+    eng.set_tuning(two_pass)
     if sc.forcing is not None:
         eng.set_forcing(sc.forcing[None])
     if sc.lab is not None:
@@ -609,6 +614,7 @@ def test_event_words_of_the_sheba_windows(oracle_mod, golden_dir):
         col.set_forcing(*F)
         col.load_state(scenarios.sheba_state(rec))
         eng = pu.engine_from_oracle(col, ncol=2)
+        eng.set_tuning(True)  # the two-pass step where the column is steady, the general path elsewhere
         eng.set_forcing(F[None])
         assert col.step(3000) == 0
         eng.step(3000)
