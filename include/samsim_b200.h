@@ -277,7 +277,8 @@ int samsim_b200_rebin(samsim_handle_t h, int32_t* changed);
  * Rayleigh-number estimates in one backward pass -- 21 array passes per step instead of 34 and
  * 30 % less DRAM traffic; the general sub-step-by-sub-step path (two_pass = 0, the default) is currently the faster
  * one on B200 because the merged pass is register-starved at 64 registers per thread. */
-int samsim_b200_set_tuning(samsim_handle_t h, int32_t two_pass);
+/* prefetch_layers: L1 prefetch distance of the layer sweeps (0 = keep the default of 2). */
+int samsim_b200_set_tuning(samsim_handle_t h, int32_t two_pass, int32_t prefetch_layers);
 /* re-bin automatically every nsteps steps inside samsim_b200_step (0 = never, the default) */
 int samsim_b200_set_rebin_interval(samsim_handle_t h, int64_t nsteps);
 /* slot_of_col[c] = position of column c in the device arrays (identity until the first re-binning) */

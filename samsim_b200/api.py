@@ -181,7 +181,7 @@ def load_library() -> C.CDLL:
         "samsim_b200_save_checkpoint": (C.c_int, [H, C.c_char_p]),
         "samsim_b200_load_checkpoint": (C.c_int, [H, C.c_char_p]),
         "samsim_b200_rebin": (C.c_int, [H, ip]),
-        "samsim_b200_set_tuning": (C.c_int, [H, C.c_int32]),
+        "samsim_b200_set_tuning": (C.c_int, [H, C.c_int32, C.c_int32]),
         "samsim_b200_set_rebin_interval": (C.c_int, [H, C.c_int64]),
         "samsim_b200_get_slot_map": (C.c_int, [H, ip]),
         "samsim_b200_kat_getT": (C.c_int, [C.c_int32, C.c_int32, dp, dp, dp, dp, dp, ip, C.c_int32]),
@@ -410,9 +410,10 @@ class Engine:
         _check(self.L, self.L.samsim_b200_rebin(self.h, C.byref(v)))
         return bool(v.value)
 
-    def set_tuning(self, two_pass: bool) -> None:
-        """kernel tuning (results do not depend on it): merged forward / backward passes for steady columns"""
-        _check(self.L, self.L.samsim_b200_set_tuning(self.h, int(bool(two_pass))))
+    def set_tuning(self, two_pass: bool, prefetch_layers: int = 0) -> None:
+        """kernel tuning (results do not depend on it): merged forward / backward passes for steady columns; L1
+        prefetch distance of the layer sweeps (0 = keep the default)"""
+        _check(self.L, self.L.samsim_b200_set_tuning(self.h, int(bool(two_pass)), int(prefetch_layers)))
 
     def set_rebin_interval(self, nsteps: int) -> None:
         _check(self.L, self.L.samsim_b200_set_rebin_interval(self.h, int(nsteps)))

@@ -42,6 +42,7 @@ struct DevCfg {
   double c2, c3, c4, d2, d3x2, d4x3;
   // tuning (samsim_b200_set_tuning; results do not depend on it)
   int two_pass;   // 1: steady columns take the merged forward / backward passes of step.cuh
+  int pf;         // L1 prefetch distance of the layer sweeps, in layers
 };
 
 // The configuration of the running launch.  On the device it lives in constant memory so that flags, dt and the
@@ -126,8 +127,9 @@ struct Lay {
 #ifndef SAMSIM_LOOP
 #define SAMSIM_LOOP _Pragma("unroll 1")
 #endif
+// Prefetch distance in layers, a per-handle run-time value (constant memory, samsim_b200_set_tuning); default 2.
 #ifndef SAMSIM_PF
-#define SAMSIM_PF 2  // prefetch distance in layers (2 measured best on B200: 70.8 vs 69.5 M col-steps/s at 4, 64.7 at 12)
+#define SAMSIM_PF (CFG.pf)
 #endif
 
 // elements between consecutive arrays of one layer of a tile (the 32 lanes); ARR_TILE*8 = 256 B

@@ -533,6 +533,10 @@ int samsim_b200_create(const samsim_config_t* cfg, int32_t ncol, int32_t device,
   d.alpha_flux_instable = cfg->alpha_flux_instable; d.alpha_flux_stable = cfg->alpha_flux_stable; d.m_total = cfg->m_total;
   d.max_flux_plate = cfg->max_flux_plate; d.k_snow_flush = cfg->k_snow_flush; d.k_styropor = cfg->k_styropor;
   fill_liquidus(d, cfg->salt_flag);
+  // prefetch distance: 2 layers (large batches: 70.8 M column-steps/s against 69.5 at 4 and 64.7 at 12 in round 1; small
+  // batches are bound by the dependent FP64 chains of their few warps, not by load latency: 2 / 6 / 12 / 24 layers all
+  // give 31.2 M column-steps/s on 10,000 testcase-1 columns, profiles/README.md)
+  d.pf = 2;
   const size_t narr = (size_t)h->n_arr * h->LS * h->ncol_pad;
   cudaError_t e;
   if ((e = cudaMalloc(&h->arr, narr * sizeof(double))) != cudaSuccess ||
@@ -829,7 +833,7 @@ int samsim_b200_step(samsim_handle_t h, int64_t nsteps) {
     p.snap_arr = (h->snap_mode >= SAMSIM_SNAP_FULL) ? h->snap_arr : nullptr;
     // small batches: shrink the block (the kernel is compiled for <= SAMSIM_BLOCK threads) until every SM has work
     int block = SAMSIM_BLOCK;
-    while (block > 64 && (h->ncol + block - 1) / block < 2 * h->num_sms) block >>= 1;
+    while (block > 32 && (h->ncol + block - 1) / block < 4 * h->num_sms) block >>= 1;  // down to one warp per block: one warp per SM sub-partition
     const unsigned grid = (unsigned)((h->ncol + block - 1) / block);
     {
       int rc = claim_device_cfg(h);
@@ -933,11 +937,12 @@ int samsim_b200_rebin(samsim_handle_t h, int32_t* changed) {
   return 0;
 }
 
-int samsim_b200_set_tuning(samsim_handle_t h, int32_t two_pass) {
-  if (!h || two_pass < 0 || two_pass > 1) return fail(SAMSIM_ERR_ARG, "set_tuning: bad argument");
+int samsim_b200_set_tuning(samsim_handle_t h, int32_t two_pass, int32_t prefetch_layers) {
+  if (!h || two_pass < 0 || two_pass > 1 || prefetch_layers < 0 || prefetch_layers > 64) return fail(SAMSIM_ERR_ARG, "set_tuning: bad argument");
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
   h->dcfg.two_pass = two_pass;
+  if (prefetch_layers > 0) h->dcfg.pf = prefetch_layers;
   release_device_cfg(h);  // the next launch uploads the configuration again
   return 0;
 }

@@ -69,6 +69,7 @@ void* hostk_create(const samsim_config_t* cfg) {
   d.dt = cfg->dt; d.thick_0 = cfg->thick_0; d.thick_min = cfg->thick_min; d.time_out = cfg->time_out;
   d.alpha_flux_instable = cfg->alpha_flux_instable; d.alpha_flux_stable = cfg->alpha_flux_stable; d.m_total = cfg->m_total;
   d.max_flux_plate = cfg->max_flux_plate; d.k_snow_flush = cfg->k_snow_flush; d.k_styropor = cfg->k_styropor;
+  d.pf = 2;
   if (cfg->salt_flag == 1) {
     d.c2 = -18.7; d.c3 = -0.519; d.c4 = -0.00535; d.d2 = -21.4; d.d3x2 = 2.0 * -0.886; d.d4x3 = 3.0 * -0.0170;
   } else {
