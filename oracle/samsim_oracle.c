@@ -1870,6 +1870,14 @@ static void one_step(sam_col* c) {
     sub_test4(c);
   } else if (c->testcase == 6) {
     sub_test6(c);
+  } else if (c->testcase == 8) { /* :539-544 */
+    if (c->time < (double)(3600.f * 12.f * 11.f)) {
+      const long idx = (long)floor(1 + c->time / 60);
+      if (idx < 1 || idx > c->length_input_lab) SAM_STOP(c, 8001); /* the reference would read Tinput out of bounds */
+      c->T_top = c->Tinput[idx];
+    } else {
+      c->T_top = -15.0;
+    }
   } else if (c->testcase == 5 && c->i == 2) { /* :541-542 */
     for (k = 1; k <= Nlayer; k++) S_abs[k] = 5.0 * m[k];
   }
@@ -2069,8 +2077,8 @@ sam_col* sam_create(int testcase) {
   int k;
   int is_lab = (testcase >= 101 && testcase <= 105);
   if (!(testcase == 1 || testcase == 2 || testcase == 3 || testcase == 4 || testcase == 5 || testcase == 6 || testcase == 7 ||
-        testcase == 9 || is_lab))
-    return NULL; /* 8 needs Tinput.txt (not shipped, "settings are likely outdated", mo_init.f90:1453) */
+        testcase == 8 || testcase == 9 || is_lab))
+    return NULL;
   c = (sam_col*)calloc(1, sizeof(sam_col));
   c->testcase = testcase;
   /* defaults, mo_init.f90:83-132 */
@@ -2099,6 +2107,23 @@ sam_col* sam_create(int testcase) {
     c->N_bgc = 2;
     c->bgc_bottom[1] = 400.0; c->bgc_bottom[2] = 500.0;
     c->bgc_abs[1][1] = c->bgc_bottom[1] * c->m[1]; c->bgc_abs[2][1] = c->bgc_bottom[2] * c->m[1];
+  } else if (testcase == 8) { /* mo_init.f90:1451-1494: field temperatures (input/DNotz_fieldT/Tinput.txt, one value per
+                               * minute) prescribe T_top.  The reference marks the settings "likely outdated": its init
+                               * does not allocate Tinput and mo_grotz.f90:138-143 builds a file name from testcase-100; the
+                               * time loop itself (:539-544) is well defined once Tinput holds the series, and that is what
+                               * is restated: the caller supplies the series through sam_set_lab_forcing (kind Tice). */
+    c->Nlayer = 50; c->N_active = 1; c->N_bottom = 5; c->N_top = 4;
+    c->N_middle = c->Nlayer - c->N_top - c->N_bottom;
+    sub_allocate(c, c->Nlayer);
+    c->T_top = -5.0; c->T_bottom = F32(-1.8); c->S_bu_bottom = 34.0; /* :1461 T_bottom = -1.8 is a default-REAL literal */
+    c->boundflux_flag = 1; c->fl_q_bottom = 15.0;
+    c->grav_flag = 2; c->flush_flag = 5; c->flood_flag = 2;
+    c->thick_0 = 0.005;
+    c->thick[1] = c->thick_0;
+    c->m[1] = c->thick[1] * rho_l;
+    c->S_abs[1] = c->S_bu_bottom * c->m[1];
+    c->H_abs[1] = c->m[1] * (c->T_bottom) * c_l;
+    c->time = 0.0; c->time_out = 3600.0; c->time_total = c->time_out * 12.0 * 12.0; c->dt = 1.0;
   } else if (testcase == 4) { /* mo_init.f90:1127-1207 */
     c->Nlayer = 100; c->N_bottom = 20; c->N_top = 20; c->N_active = 1;
     c->N_middle = c->Nlayer - c->N_top - c->N_bottom;

@@ -93,6 +93,16 @@ int samsim_host_init_testcase(int32_t testcase, samsim_host_case_t* c) {
     c->arrays[SAMSIM_ARR_M][0] = c->arrays[SAMSIM_ARR_THICK][0] * rho_l;
     c->arrays[SAMSIM_ARR_S_ABS][0] = S_bu_bottom * c->arrays[SAMSIM_ARR_M][0];
     c->arrays[SAMSIM_ARR_H_ABS][0] = c->arrays[SAMSIM_ARR_M][0] * (T_bottom)*c_l;
+  } else if (testcase == 8) {  // mo_init.f90:1451-1494 (field temperatures prescribe T_top; the series comes from Tinput.txt)
+    g->Nlayer = 50; g->N_bottom = 5; g->N_top = 4; g->N_middle = g->Nlayer - g->N_top - g->N_bottom;
+    g->boundflux_flag = 1; g->grav_flag = 2; g->flush_flag = 5; g->flood_flag = 2;
+    T_top = -5.0; T_bottom = (double)(-1.8f); S_bu_bottom = 34.0; fl_q_bottom = 15.0;
+    g->thick_0 = 0.005; g->dt = 1.0; time_out = 3600.0; c->time_total = time_out * 12.0 * 12.0;
+    alloc_case(c);
+    c->arrays[SAMSIM_ARR_THICK][0] = g->thick_0;
+    c->arrays[SAMSIM_ARR_M][0] = c->arrays[SAMSIM_ARR_THICK][0] * rho_l;
+    c->arrays[SAMSIM_ARR_S_ABS][0] = S_bu_bottom * c->arrays[SAMSIM_ARR_M][0];
+    c->arrays[SAMSIM_ARR_H_ABS][0] = c->arrays[SAMSIM_ARR_M][0] * (T_bottom)*c_l;
   } else if (testcase == 4) {  // mo_init.f90:1127-1207
     g->Nlayer = 100; g->N_bottom = 20; g->N_top = 20; g->N_middle = g->Nlayer - g->N_top - g->N_bottom;
     g->atmoflux_flag = 2; g->precip_flag = 1; g->boundflux_flag = 2; g->snow_flush_flag = 1; g->flush_heat_flag = 2;
@@ -351,6 +361,23 @@ int samsim_grotz(int32_t testcase, const char* description, const samsim_grotz_o
     std::vector<double> series((size_t)4 * nrec);
     rc = samsim_host_read_forcing(opt->forcing_dir, nrec, series.data());
     if (!rc) rc = samsim_b200_set_forcing(h, 1, nrec, series.data(), nullptr, opt->forcing_scale, opt->forcing_offset);
+  }
+  if (!rc && testcase == 8) {  // mo_grotz.f90:138-143 reads Tinput; the field series is Tinput.txt, one value per minute
+    std::vector<double> T;
+    const std::string path = std::string(opt->lab_input_dir ? opt->lab_input_dir : "2017_input") + "/Tinput.txt";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) rc = SAMSIM_ERR_STATE;
+    else {
+      double x;
+      while (fscanf(f, " %lf", &x) == 1) T.push_back(x);
+      fclose(f);
+      if (T.empty()) rc = SAMSIM_ERR_STATE;
+    }
+    if (!rc) {
+      std::vector<double> lab(4 * T.size(), 0.0);
+      for (size_t r = 0; r < T.size(); r++) lab[r] = T[r];
+      rc = samsim_b200_set_lab_forcing(h, 1, (int64_t)T.size(), lab.data(), nullptr);
+    }
   }
   if (!rc && testcase >= 101 && testcase <= 105) {  // mo_grotz.f90:138-169: the four per-second lab series
     const int64_t nrec = cs.length_input_lab;

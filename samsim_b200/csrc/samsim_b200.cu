@@ -767,7 +767,8 @@ int samsim_b200_step(samsim_handle_t h, int64_t nsteps) {
   if (!h || nsteps < 0) return fail(SAMSIM_ERR_ARG, "step: bad argument");
   if (nsteps == 0) return 0;
   const bool need_forcing = (h->cfg.atmoflux_flag == 2);
-  const bool need_lab = (h->cfg.testcase >= 101 && h->cfg.testcase <= 105) || (h->cfg.boundflux_flag == 3 && h->cfg.lab_snow_flag == 1);
+  const bool tc8 = (h->cfg.testcase == 8);  // T_top = Tinput(FLOOR(1 + time/60)) while time < 475200 s (mo_grotz.f90:539-544)
+  const bool need_lab = tc8 || (h->cfg.testcase >= 101 && h->cfg.testcase <= 105) || (h->cfg.boundflux_flag == 3 && h->cfg.lab_snow_flag == 1);
   if (need_forcing && !h->series) return fail(SAMSIM_ERR_STATE, "step: atmoflux_flag 2 needs samsim_b200_set_forcing first");
   if (need_lab && !h->lab) return fail(SAMSIM_ERR_STATE, "step: lab testcases need samsim_b200_set_lab_forcing first");
   CU(cudaSetDevice(h->device));
@@ -813,13 +814,16 @@ int samsim_b200_step(samsim_handle_t h, int64_t nsteps) {
       // Records FLOOR(1 + time/dt) of every step of the chunk must exist.  The device accumulates time by repeated
       // `+ dt`, which for a dt that is not exactly representable can sit an ulp above k*dt: the bound is found by
       // replaying the same additions, never by a multiplication.  Only the tail of the series needs the replay.
-      const long long first_rec = (long long)floor(1 + h->time / h->cfg.dt);
+      const double per_rec = tc8 ? 60.0 : h->cfg.dt;       // seconds per record
+      const double t_last = tc8 ? 475200.0 : 1e300;          // the series is not read from this time on
+      auto rec_at = [&](double t) { return (t < t_last) ? (long long)floor(1 + t / per_rec) : 1LL; };
+      const long long first_rec = rec_at(h->time);
       if (first_rec < 1 || first_rec > h->lab_nrec) return fail(SAMSIM_ERR_STATE, "step: lab series exhausted");
-      if (first_rec + chunk + 2 > h->lab_nrec) {
+      if (first_rec + (long long)((double)chunk * h->cfg.dt / per_rec) + 2 > h->lab_nrec) {
         double t = h->time;
         int64_t ok = 0;
         for (; ok < chunk; ok++) {
-          const long long rec = (long long)floor(1 + t / h->cfg.dt);
+          const long long rec = rec_at(t);
           if (rec < 1 || rec > h->lab_nrec) break;
           t = t + h->cfg.dt;
         }

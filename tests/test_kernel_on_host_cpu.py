@@ -101,6 +101,22 @@ def test_device_code_on_host_output_record_and_simple_parametrisations(oracle_mo
     _advance(col7, k7, (1, 3000, 6000))
 
 
+@pytest.mark.parametrize("two_pass", [False, True])
+def test_device_code_on_host_testcase8_field_temperatures(oracle_mod, golden_dir, two_pass):
+    """Testcase 8 (mo_init.f90:1451-1494, mo_grotz.f90:539-544): T_top follows the field series of
+    input/DNotz_fieldT/Tinput.txt (fixture tests/golden/tinput_dnotz.npz), one record per minute."""
+    Tin = np.load(golden_dir / "tinput_dnotz.npz")["Tinput"]
+    lab = np.zeros((4, len(Tin)))
+    lab[0] = Tin
+    col = oracle_mod.Column(8, "det")
+    col.set_lab_forcing(*lab)
+    k = _from_oracle(col, two_pass)
+    k.set_lab_forcing(lab)
+    _advance(col, k, (1, 2, 3598, 40000, 50000))
+    assert col.int("N_active") > 10 and col.scalar("T_top") == Tin[int(1 + (col.scalar("time") - 1.0) / 60) - 1]
+    assert ("two_pass_step" in k.events()) == two_pass
+
+
 def test_device_code_on_host_with_impermeable_layers(oracle_mod, golden_dir):
     """fl_grav_drain's `minval(perm(k:N_active-1)) < 1e-14 -> harmonic_perm = 0` branch (mo_grav_drain.f90:112-113):
     a band of nearly fresh layers in the mid-winter column makes the layers above it non-draining while the layers

@@ -390,6 +390,54 @@ def test_grotz_sheba_first_records(tmp_path, golden_dir):
     assert np.array_equal((thick != 0).sum(1), gold["N_active"][:13])
 
 
+def test_grotz_lab_and_field_testcases_read_their_series(oracle_mod, tmp_path, golden_dir):
+    """samsim_grotz for the testcases that READ series in the reference's prologue (mo_grotz.f90:138-169): lab
+    testcase 101 (2017_input/{Tice,snowfall,heat,styropor}_exp_1.txt; synthetic files, the real ones are not shipped)
+    and testcase 8 (the field temperatures input/DNotz_fieldT/Tinput.txt).  The written dat_thick / dat_T records
+    equal the oracle's records at print precision, N_active exactly."""
+    from samsim_b200 import grotz
+    nsteps = 3 * 3601 + 1
+    # ---- testcase 101: four per-second series, length_input_lab values each ----
+    nrec = grotz.init_testcase(101)["length_input_lab"]
+    series = scenarios.lab_series(20000, styropor_hours=(1, 2))
+    labdir = tmp_path / "2017_input"
+    labdir.mkdir()
+    for name, row in zip(["Tice", "snowfall", "heat", "styropor"], series):
+        full = np.concatenate([row, np.full(nrec - len(row), row[-1])])
+        np.savetxt(labdir / f"{name}_exp_1.txt", full, fmt="%.9e")
+    out = tmp_path / "out101"
+    assert grotz.grotz(101, "lab", output_dir=out, lab_input_dir=labdir, max_steps=nsteps) == 0
+    col = oracle_mod.Column(101, "det")
+    col.set_lab_forcing(*[np.loadtxt(labdir / f"{n}_exp_1.txt")[:20000] for n in ("Tice", "snowfall", "heat", "styropor")])
+    col.record_outputs()
+    assert col.step(nsteps) == 0
+    thick, T = _read_dat(out / "dat_thick.dat"), _read_dat(out / "dat_T.dat")
+    assert thick.shape[0] == len(col.records) == 4
+    for j, rec in enumerate(col.records):
+        assert np.abs(thick[j] - rec["thick"]).max() <= 0.5e-5 and np.abs(T[j] - rec["T"]).max() <= 0.5e-3
+        assert (thick[j] != 0).sum() == rec["N_active"]
+    # ---- testcase 8: Tinput.txt, one value per minute ----
+    Tin = np.load(golden_dir / "tinput_dnotz.npz")["Tinput"]
+    fdir = tmp_path / "field"
+    fdir.mkdir()
+    np.savetxt(fdir / "Tinput.txt", Tin, fmt="%.4f")
+    out8 = tmp_path / "out8"
+    assert grotz.grotz(8, "field T", output_dir=out8, lab_input_dir=fdir, max_steps=nsteps) == 0
+    lab = np.zeros((4, len(Tin)))
+    lab[0] = np.loadtxt(fdir / "Tinput.txt")
+    col8 = oracle_mod.Column(8, "det")
+    col8.set_lab_forcing(*lab)
+    col8.record_outputs()
+    assert col8.step(nsteps) == 0
+    thick8 = _read_dat(out8 / "dat_thick.dat")
+    tt8 = _read_dat(out8 / "dat_T2m_T_top.dat")
+    assert thick8.shape[0] == len(col8.records) == 4
+    for j, rec in enumerate(col8.records):
+        assert np.abs(thick8[j] - rec["thick"]).max() <= 0.5e-5 and (thick8[j] != 0).sum() == rec["N_active"]
+        assert tt8[j, 1] == rec["T_top"]
+    assert col8.int("N_active") > 2
+
+
 def test_rebin_is_invisible_to_results(oracle_mod, golden_dir):
     """SURVEY 8e re-binning: sorting the columns by regime on the device changes neither any column's result (bit
     for bit, against a handle that never re-bins and against the oracle) nor the caller's column numbering --
@@ -468,15 +516,25 @@ OTHER_TESTCASES = {
     3: (200000, "climatological forcing (notzflux) + solid precipitation, 139 days: open water to a full grid (sub_test3)"),
     5: (15000, "top melt of a 1 m block of cold fresh ice, atmoflux 3, N_active = Nlayer from the start, S_abs reset at i = 2"),
     6: (140000, "small tank, dt 0.5 s, T2m schedule of sub_test6"),
+    8: (90000, "field surface temperatures (input/DNotz_fieldT/Tinput.txt, one per minute) prescribe T_top, 25 h"),
     9: (30000, "cooling chamber with the T2m schedule of sub_test9 (growth, then melt)"),
 }
 
 
 @pytest.mark.parametrize("testcase", sorted(OTHER_TESTCASES))
-def test_other_testcases_from_init(oracle_mod, testcase):
+def test_other_testcases_from_init(oracle_mod, golden_dir, testcase):
     nsteps, _what = OTHER_TESTCASES[testcase]
     col = oracle_mod.Column(testcase, "det")
+    lab = None
+    if testcase == 8:
+        Tin = np.load(golden_dir / "tinput_dnotz.npz")["Tinput"]
+        lab = np.zeros((4, len(Tin)))
+        lab[0] = Tin
+        col.set_lab_forcing(*lab)
     eng = pu.engine_from_oracle(col, ncol=2)
+    if lab is not None:
+        eng.set_lab_forcing(lab[None])
+    eng.set_tuning(testcase == 8)  # testcase 8 (boundflux 1, no tracers) may take the two-pass step
     done = 0
     for target in (1, 2, 3, nsteps // 3, nsteps):
         n = target - done

@@ -68,8 +68,16 @@ def bgc_golden():
     print('tc1_bgc_reference.npz', (OUT / 'tc1_bgc_reference.npz').stat().st_size)
 
 
+def field_temperatures():
+    """input/DNotz_fieldT/Tinput.txt: the per-minute surface temperatures testcase 8 prescribes (mo_grotz.f90:539-544)."""
+    a = np.loadtxt(REF / 'input' / 'DNotz_fieldT' / 'Tinput.txt', dtype=np.float64)
+    np.savez_compressed(OUT / 'tinput_dnotz.npz', Tinput=a)
+    print('tinput_dnotz.npz', a.shape, (OUT / 'tinput_dnotz.npz').stat().st_size)
+
+
 def main_reference():
     forcing()
+    field_temperatures()
     bgc_golden()
     golden('Reference_testcase1_with_Version_2', 'tc1_reference.npz', np.arange(72))
     sel = sorted(set(range(0, 1643, 6)) | set(range(320, 361)) | {1642})
