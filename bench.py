@@ -24,7 +24,7 @@ One bench "step" = MODEL_STEPS consecutive model timesteps of every column of th
   strong : (N > 1) the same 1,048,576-column ensemble sharded over the N ranks (fixed total), timed the same way.
   year_weighted: (N = 1) throughput over the regimes of a SHEBA year instead of the mid-winter state alone: six
            ensembles start from the oracle states of records 60 / 100 / 200 / 330 / 345 / 400, drift 8,640 steps (one
-           model day) under per-column forcing with re-binning on, are timed for 640 more steps, and are combined
+           model day) under per-column forcing with divergence-driven re-binning, are timed for 640 more steps, and are combined
            with the share of the golden run's 1,643 records that each regime represents (harmonic mean = time-weighted).
   cpu_baseline / --impl reference: the CPU oracle (C port of the Fortran; no Fortran compiler exists in this image),
            one column per OS thread on all host cores, on a bounded sample of the same columns; the libm build (what
@@ -67,6 +67,7 @@ YEAR_REGIMES = [(200, "winter, grid full", 0.6190), (345, "bare-ice melt, flushi
 YEAR_COLUMNS = 151552            # one full wave of the step kernel (148 SMs x 2 blocks x 512 threads)
 YEAR_DRIFT_STEPS = 8640          # one model day
 YEAR_TIMED_STEPS = 640
+YEAR_REBIN_THRESHOLD = 0.03      # re-bin when more than 3 % of the lane-layers of a launch were idle
 
 
 def load_state(rec: int) -> dict:
@@ -251,20 +252,26 @@ def year_weighted(api, sites: np.ndarray, device: int) -> dict:
     rows, t_per_step = [], 0.0
     for rec, what, share in YEAR_REGIMES:
         eng = make_engine(api, load_state(rec), sites, YEAR_COLUMNS, 0, device)
-        eng.set_rebin_interval(1080)           # re-bin every 3 model hours while the ensemble drifts apart
-        eng.step(YEAR_DRIFT_STEPS)
+        # re-binning is driven by the divergence the kernel measures itself (idle lane-layers per warp), checked
+        # between calls: the drift runs in eight calls of three model hours
+        eng.set_rebin_auto(YEAR_REBIN_THRESHOLD)
+        for _ in range(YEAR_DRIFT_STEPS // 1080):
+            eng.step(1080)
         eng.step(YEAR_TIMED_STEPS // 2)        # warm
         eng.step(YEAR_TIMED_STEPS, sync=False)
         eng.synchronize()
         ms = eng.last_step_ms()
         rate = YEAR_COLUMNS * YEAR_TIMED_STEPS / (ms * 1e-3)
         na = eng.get_int("N_active")
+        div = eng.divergence()
         rows.append({"record": rec, "regime": what, "share": share, "value": rate, "N_active_mean": float(na.mean()),
-                     "N_active_min": int(na.min()), "N_active_max": int(na.max()), "failed_columns": int(eng.count_failed())})
+                     "N_active_min": int(na.min()), "N_active_max": int(na.max()), "failed_columns": int(eng.count_failed()),
+                     "idle_lane_layer_share": div["idle_lane_layer_share"], "snow_class_split_warp_share": div["snow_class_split_warp_share"],
+                     "rebins": div["rebins"]})
         t_per_step += share / rate
         eng.close()
     return {"value": 1.0 / t_per_step, "unit": "column-timesteps/s", "columns": YEAR_COLUMNS, "drift_steps": YEAR_DRIFT_STEPS,
-            "timed_steps": YEAR_TIMED_STEPS, "rebin_interval": 1080, "regimes": rows,
+            "timed_steps": YEAR_TIMED_STEPS, "rebin": f"automatic, kernel-measured idle lane-layer share > {YEAR_REBIN_THRESHOLD}", "regimes": rows,
             "how": "harmonic mean of the regime rates weighted by the regime's share of the golden SHEBA records"}
 
 

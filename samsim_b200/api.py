@@ -183,6 +183,8 @@ def load_library() -> C.CDLL:
         "samsim_b200_rebin": (C.c_int, [H, ip]),
         "samsim_b200_set_tuning": (C.c_int, [H, C.c_int32, C.c_int32]),
         "samsim_b200_set_rebin_interval": (C.c_int, [H, C.c_int64]),
+        "samsim_b200_set_rebin_auto": (C.c_int, [H, C.c_double]),
+        "samsim_b200_get_divergence": (C.c_int, [H, dp, dp, C.POINTER(C.c_int64)]),
         "samsim_b200_get_slot_map": (C.c_int, [H, ip]),
         "samsim_b200_kat_getT": (C.c_int, [C.c_int32, C.c_int32, dp, dp, dp, dp, dp, ip, C.c_int32]),
         "samsim_b200_kat_scalar": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, dp, dp, dp, C.c_int32]),
@@ -205,7 +207,7 @@ EXPORTED_SYMBOLS = [
     "samsim_b200_step", "samsim_b200_synchronize", "samsim_b200_steps_to_next_output",
     "samsim_b200_set_snapshot_mode", "samsim_b200_get_snapshot", "samsim_b200_get_status",
     "samsim_b200_count_failed", "samsim_b200_reduce_diag", "samsim_b200_launch_count", "samsim_b200_last_step_ms",
-    "samsim_b200_device_layout", "samsim_b200_save_checkpoint", "samsim_b200_load_checkpoint", "samsim_b200_rebin", "samsim_b200_set_tuning", "samsim_b200_set_rebin_interval", "samsim_b200_get_slot_map",
+    "samsim_b200_device_layout", "samsim_b200_save_checkpoint", "samsim_b200_load_checkpoint", "samsim_b200_rebin", "samsim_b200_set_tuning", "samsim_b200_set_rebin_interval", "samsim_b200_set_rebin_auto", "samsim_b200_get_divergence", "samsim_b200_get_slot_map",
     "samsim_b200_kat_getT", "samsim_b200_kat_scalar", "samsim_b200_fp64_peak",
 ]
 
@@ -417,6 +419,16 @@ class Engine:
 
     def set_rebin_interval(self, nsteps: int) -> None:
         _check(self.L, self.L.samsim_b200_set_rebin_interval(self.h, int(nsteps)))
+
+    def set_rebin_auto(self, idle_share_threshold: float) -> None:
+        """re-bin whenever the kernel-measured share of idle lane-layers of the last launch exceeds the threshold"""
+        _check(self.L, self.L.samsim_b200_set_rebin_auto(self.h, float(idle_share_threshold)))
+
+    def divergence(self) -> dict:
+        """warp divergence of the last launch, measured in the kernel (reductions / ballots per warp)"""
+        a, b, n = C.c_double(), C.c_double(), C.c_int64()
+        _check(self.L, self.L.samsim_b200_get_divergence(self.h, C.byref(a), C.byref(b), C.byref(n)))
+        return {"idle_lane_layer_share": a.value, "snow_class_split_warp_share": b.value, "rebins": n.value}
 
     def slot_map(self) -> np.ndarray:
         out = np.empty(self.ncol, dtype=np.int32)

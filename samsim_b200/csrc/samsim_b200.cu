@@ -64,6 +64,9 @@ struct KParams {
   // snapshot
   double* snap_sc;
   double* snap_arr;
+  // divergence counters (see the end of samsim_step_kernel): [0] idle lane-layers, [1] all lane-layers, [2] warps whose
+  // lanes disagree on the snow class or the status, [3] warps
+  unsigned long long* divergence;
 };
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
@@ -125,6 +128,31 @@ __global__ void __launch_bounds__(SAMSIM_BLOCK, SAMSIM_MINBLOCKS) samsim_step_ke
 
   // every thread runs every step: a failed column only skips the phase bodies (column_step checks c.status)
   for (int s = 0; s < p.nsteps; s++) column_step(c, f, s == p.nsteps - 1, snap);
+
+  // ---- lane divergence of this launch's end state, measured where it arises: in the warp --------------------------
+  // A warp runs every layer sweep to the deepest of its 32 columns and every branch that one of its lanes takes.
+  // idle lane-layers = SUM over lanes (max N_active in the warp - N_active of the lane); lanes that disagree on the
+  // snow class (the S2 / S3 / S10 / S17 branches) or on being failed are counted per warp with a ballot.  The host
+  // re-bins the columns when the idle share crosses its threshold (samsim_b200_set_rebin_auto) instead of on a
+  // fixed interval.
+  if (p.divergence) {
+    const unsigned full = 0xffffffffu;
+    const bool live = !padding && c.status == 0;
+    const int na = live ? c.N_active : 0;
+    const int mx = __reduce_max_sync(full, na);
+    const int idle = __reduce_add_sync(full, live ? (mx - na) : 0);
+    const int nlive = __popc(__ballot_sync(full, live));
+    const double ts = c.sc[SC_THICK_SNOW];
+    const int cls = !live ? -1 : (ts <= 0.0) ? 0 : (ts < CFG.thick_min / 100.0) ? 1 : (ts < CFG.thick_min) ? 2 : 3;
+    const int cls0 = __shfl_sync(full, cls, __ffs(__ballot_sync(full, live)) - 1);
+    const unsigned differ = __ballot_sync(full, live && cls != cls0);
+    if ((threadIdx.x & 31) == 0 && nlive > 0) {
+      atomicAdd(&p.divergence[0], (unsigned long long)idle);
+      atomicAdd(&p.divergence[1], (unsigned long long)mx * (unsigned long long)nlive);
+      atomicAdd(&p.divergence[2], (unsigned long long)(differ != 0u));
+      atomicAdd(&p.divergence[3], 1ull);
+    }
+  }
 
   if (padding) return;
   for (int q = 0; q < SC_COUNT; q++) p.sc[(size_t)q * ls + col] = c.sc[q];
@@ -386,6 +414,13 @@ struct samsim_b200_handle_s {
   // re-binning: slot_of_col[c] = where column c lives, col_of_slot[s] = which column lives in slot s (nullptr = identity)
   int *slot_of_col = nullptr, *col_of_slot = nullptr;
   long long rebin_every = 0, since_rebin = 0, rebins = 0;
+  // in-kernel divergence measurement: 4 counters on the device, read back after each step() call into pinned host memory
+  unsigned long long* divergence = nullptr;       // device
+  unsigned long long* divergence_host = nullptr;  // pinned
+  cudaEvent_t ev_div = nullptr;
+  bool div_pending = false;
+  double rebin_auto_threshold = 0.0;              // 0 = off
+  double last_idle_share = 0.0, last_class_split_share = 0.0;
 };
 
 // The step kernel reads its configuration from constant memory (samsim_dev_cfg, physics.cuh), one copy per device.
@@ -552,6 +587,13 @@ int samsim_b200_create(const samsim_config_t* cfg, int32_t ncol, int32_t device,
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
   cudaEventCreateWithFlags(&h->ev_launch, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_div, cudaEventDisableTiming);
+  if (cudaMalloc(&h->divergence, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMallocHost(&h->divergence_host, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+    samsim_b200_destroy(h);
+    return fail(SAMSIM_ERR_CUDA, "cudaMalloc: divergence counters");
+  }
+  memset(h->divergence_host, 0, 4 * sizeof(unsigned long long));
   *out = h;
   return SAMSIM_OK;
 }
@@ -562,6 +604,9 @@ void samsim_b200_destroy(samsim_handle_t h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   release_device_cfg(h);
   if (h->ev_launch) cudaEventDestroy(h->ev_launch);
+  if (h->ev_div) cudaEventDestroy(h->ev_div);
+  cudaFree(h->divergence);
+  if (h->divergence_host) cudaFreeHost(h->divergence_host);
   cudaFree(h->arr); cudaFree(h->sc); cudaFree(h->in); cudaFree(h->series); cudaFree(h->site_of_col);
   cudaFree(h->fscale); cudaFree(h->foffset); cudaFree(h->lab); cudaFree(h->set_of_col); cudaFree(h->snap_sc);
   cudaFree(h->snap_arr); cudaFree(h->stage); cudaFree(h->slot_of_col); cudaFree(h->col_of_slot);
@@ -757,6 +802,38 @@ static inline void clock_tick(samsim_handle_t h) {
   h->time = h->time + h->cfg.dt;
 }
 
+// Divergence of the last launch (measured in the kernel with warp reductions / ballots): fold the counters into the
+// handle and, when automatic re-binning is on and idle lane-layers exceed the threshold, re-bin the columns.
+static int collect_divergence(samsim_handle_t h, bool may_rebin) {
+  if (!h->div_pending) return 0;
+  CU(cudaEventSynchronize(h->ev_div));
+  h->div_pending = false;
+  const unsigned long long* d = h->divergence_host;
+  h->last_idle_share = d[1] ? (double)d[0] / (double)d[1] : 0.0;
+  h->last_class_split_share = d[3] ? (double)d[2] / (double)d[3] : 0.0;
+  if (may_rebin && h->rebin_auto_threshold > 0.0 &&
+      (h->last_idle_share > h->rebin_auto_threshold || h->last_class_split_share > 4.0 * h->rebin_auto_threshold))
+    return samsim_b200_rebin(h, nullptr);
+  return 0;
+}
+
+int samsim_b200_set_rebin_auto(samsim_handle_t h, double idle_share_threshold) {
+  if (!h || !(idle_share_threshold >= 0.0) || idle_share_threshold >= 1.0) return fail(SAMSIM_ERR_ARG, "set_rebin_auto: threshold in [0, 1)");
+  h->rebin_auto_threshold = idle_share_threshold;
+  return 0;
+}
+
+int samsim_b200_get_divergence(samsim_handle_t h, double* idle_lane_layer_share, double* snow_class_split_warp_share, int64_t* rebins) {
+  if (!h) return fail(SAMSIM_ERR_ARG, "null handle");
+  CU(cudaSetDevice(h->device));
+  int rc = collect_divergence(h, /*may_rebin=*/false);
+  if (rc) return rc;
+  if (idle_lane_layer_share) *idle_lane_layer_share = h->last_idle_share;
+  if (snow_class_split_warp_share) *snow_class_split_warp_share = h->last_class_split_share;
+  if (rebins) *rebins = h->rebins;
+  return 0;
+}
+
 int64_t samsim_b200_steps_to_next_output(samsim_handle_t h) {
   if (!h) return -1;
   if (h->i == 0) return 1;
@@ -772,6 +849,11 @@ int samsim_b200_step(samsim_handle_t h, int64_t nsteps) {
   if (need_forcing && !h->series) return fail(SAMSIM_ERR_STATE, "step: atmoflux_flag 2 needs samsim_b200_set_forcing first");
   if (need_lab && !h->lab) return fail(SAMSIM_ERR_STATE, "step: lab testcases need samsim_b200_set_lab_forcing first");
   CU(cudaSetDevice(h->device));
+  {
+    int rc = collect_divergence(h, /*may_rebin=*/true);  // the previous call's measurement decides about re-binning now
+    if (rc) return rc;
+  }
+  CU(cudaMemsetAsync(h->divergence, 0, 4 * sizeof(unsigned long long), h->stream));
   CU(cudaEventRecord(h->ev0, h->stream));
   int64_t left = nsteps;
   while (left > 0) {
@@ -833,6 +915,7 @@ int samsim_b200_step(samsim_handle_t h, int64_t nsteps) {
       p.lab = h->lab; p.lab_nrec = h->lab_nrec; p.set_of_col = h->set_of_col;
     }
     p.nsteps = (int)chunk;
+    p.divergence = h->divergence;
     p.snap_sc = (h->snap_mode >= SAMSIM_SNAP_SCALARS) ? h->snap_sc : nullptr;
     p.snap_arr = (h->snap_mode >= SAMSIM_SNAP_FULL) ? h->snap_arr : nullptr;
     // small batches: shrink the block (the kernel is compiled for <= SAMSIM_BLOCK threads) until every SM has work
@@ -857,6 +940,10 @@ int samsim_b200_step(samsim_handle_t h, int64_t nsteps) {
   }
   CU(cudaEventRecord(h->ev1, h->stream));
   h->timed = true;
+  // the last launch's divergence counters travel to pinned host memory behind the kernel; nobody waits for them here
+  CU(cudaMemcpyAsync(h->divergence_host, h->divergence, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaEventRecord(h->ev_div, h->stream));
+  h->div_pending = true;
   return 0;
 }
 

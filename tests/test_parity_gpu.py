@@ -510,6 +510,44 @@ def test_rebin_is_invisible_to_results(oracle_mod, golden_dir):
     assert binned.count_failed() == plain.count_failed()
 
 
+def test_divergence_is_measured_in_the_kernel_and_triggers_rebinning(oracle_mod, golden_dir):
+    """The step kernel measures its own warp divergence (warp max / add reductions over N_active, a ballot over the snow
+    class) and samsim_b200_set_rebin_auto re-bins when the idle share of lane-layers crosses the threshold: a drifting
+    ensemble gets re-binned without a host-set interval, the measured idle share drops, results stay bit-identical."""
+    z = np.load(golden_dir / "sheba_oracle_states.npz")
+    F = _forcing(golden_dir)
+    ncol = 4096
+    rng = np.random.default_rng(12)
+    scale, offset = np.ones((4, ncol)), np.zeros((4, ncol))
+    scale[1] = rng.uniform(0.55, 1.1, ncol)
+    offset[2] = rng.uniform(-2, 2, ncol)
+    base = oracle_mod.Column(4, "det")
+    base.set_forcing(*F)
+    base.load_state(_state(z, 80))
+
+    def make(auto):
+        e = pu.engine_from_oracle(base, ncol=ncol)
+        e.set_forcing(F[None], None, scale, offset)
+        e.set_rebin_auto(auto)
+        return e
+
+    plain, auto = make(0.0), make(0.02)
+    for e in (plain, auto):
+        for _ in range(6):
+            e.step(2000)
+    dp, da = plain.divergence(), auto.divergence()
+    na = plain.get_int("N_active")
+    assert na.max() - na.min() >= 3
+    # idle share by definition, from the final N_active in the caller's (= plain's device) order
+    w = na.reshape(-1, 32)
+    expect = (w.max(1, keepdims=True) - w).sum() / (w.max(1) * 32).sum()
+    assert abs(dp["idle_lane_layer_share"] - expect) < 1e-12 and dp["rebins"] == 0
+    assert da["rebins"] >= 1 and da["idle_lane_layer_share"] < 0.5 * dp["idle_lane_layer_share"], (dp, da)
+    for name in ("m", "S_abs", "H_abs", "thick", "T", "phi"):
+        assert pu.same_bits(plain.get_array(name), auto.get_array(name)).all(), name
+    assert (plain.get_int("N_active") == auto.get_int("N_active")).all()
+
+
 # SURVEY 8f-4: the remaining testcases of mo_init.f90 (no golden output exists for them: GPU vs oracle only)
 OTHER_TESTCASES = {
     2: (40000, "cooling chamber: tank, boundflux 3, T2m steps to +1 after 15 days (sub_test2)"),
