@@ -250,6 +250,9 @@ def make_engine(api, st: dict, sites: np.ndarray, per: int, col0: int, device: i
 def year_weighted(api, sites: np.ndarray, device: int) -> dict:
     """Throughput over the regimes of a SHEBA year (see the module docstring)."""
     rows, t_per_step = [], 0.0
+    # the ERA-interim site files hold one year (2,920 three-hourly records); the late-summer state lies in the second
+    # year of the run, so the annual cycle of every site is repeated once
+    sites = np.concatenate([sites[:, :, :2920], sites[:, :, :2920]], axis=2)
     for rec, what, share in YEAR_REGIMES:
         eng = make_engine(api, load_state(rec), sites, YEAR_COLUMNS, 0, device)
         # re-binning is driven by the divergence the kernel measures itself (idle lane-layers per warp), checked

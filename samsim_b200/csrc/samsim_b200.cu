@@ -74,6 +74,7 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem_src));
 }
 
+template <bool TWO_PASS>
 __global__ void __launch_bounds__(SAMSIM_BLOCK, SAMSIM_MINBLOCKS) samsim_step_kernel(const __grid_constant__ KParams p) {
   __shared__ double s_win[SAMSIM_MAXSITE * 4 * SAMSIM_MAXWIN];
   // stage the forcing window: records win_first .. win_first+win_len-1 of every site/kind (cp.async)
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(SAMSIM_BLOCK, SAMSIM_MINBLOCKS) samsim_step_ke
   snap.scalars = p.snap_sc; snap.arrays = p.snap_arr; snap.ncol_pad = ls; snap.col = (int)col;
 
   // every thread runs every step: a failed column only skips the phase bodies (column_step checks c.status)
-  for (int s = 0; s < p.nsteps; s++) column_step(c, f, s == p.nsteps - 1, snap);
+  for (int s = 0; s < p.nsteps; s++) column_step<TWO_PASS>(c, f, s == p.nsteps - 1, snap);
 
   // ---- lane divergence of this launch's end state, measured where it arises: in the warp --------------------------
   // A warp runs every layer sweep to the deepest of its 32 columns and every branch that one of its lanes takes.
@@ -926,7 +927,8 @@ int samsim_b200_step(samsim_handle_t h, int64_t nsteps) {
       int rc = claim_device_cfg(h);
       if (rc) return rc;
     }
-    samsim_step_kernel<<<grid, block, 0, h->stream>>>(p);
+    if (h->dcfg.two_pass) samsim_step_kernel<true><<<grid, block, 0, h->stream>>>(p);
+    else samsim_step_kernel<false><<<grid, block, 0, h->stream>>>(p);
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev_launch, h->stream));
     h->launches++;

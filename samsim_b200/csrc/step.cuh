@@ -536,7 +536,11 @@ __device__ __forceinline__ void testcase_hooks(Col& c, const Forcing& f) {
 // next step's S4 and fl_grav_drain (mo_grav_drain.f90:104-136) will compute from T, phi, m, thick, S_abs of the layer
 // alone: Expulsion -> psi_l -> perm, thick/perm (stored in w1), and the suffix estimates of ray (stored in ray, see
 // grav_drain for the estimate / candidate scheme).  Only done when ray is not observable before it is recomputed.
-__device__ __noinline__ void backward_pass(Col& c, bool prepare, bool store_S_bu) {
+// PREP is a template parameter: the general-path kernel is instantiated without the preparation code (and without
+// forward_pass): compiled into one kernel, the unused two-pass code cost the general path 10 % (instruction cache).
+template <bool PREP>
+__device__ __noinline__ void backward_pass(Col& c, bool prepare_now, bool store_S_bu) {
+  const bool prepare = PREP && prepare_now;
   const View v = c;
   const int Na = c.N_active;
   Lay q = v.w1();
@@ -589,14 +593,11 @@ __device__ __noinline__ void backward_pass(Col& c, bool prepare, bool store_S_bu
   c.pre.A2 = A2;
 }
 
-// The two-pass step is selected per handle at run time (samsim_b200_set_tuning); -DSAMSIM_TWO_PASS=0 compiles it out.
-#ifndef SAMSIM_TWO_PASS
-#define SAMSIM_TWO_PASS 1
-#endif
+// The two-pass step is selected per handle at run time (samsim_b200_set_tuning): the library carries two instantiations
+// of the step kernel, samsim_step_kernel<false> (general path only) and samsim_step_kernel<true>.
 
 // May this column take the merged forward pass in this step?  Everything here is a per-column, per-step decision.
 __device__ __forceinline__ bool fast_path_ok(const Col& c, bool output_step, bool observable_after) {
-  if (!SAMSIM_TWO_PASS || !CFG.two_pass) return false;
   if (!(c.thermo_valid && c.pre.valid) || output_step || observable_after) return false;
   if (c.N_active < 3 || c.i == 1) return false;
   if (CFG.grav_flag != 2 || CFG.harmonic_flag != 2 || CFG.n_bgc != 0 || CFG.prescribe_flag == 2 || CFG.tank_flag == 2) return false;
@@ -1001,6 +1002,7 @@ __device__ __noinline__ void forward_pass(Col& c) {
   if (c.status == 0 && fabs((temp1 - temp2) / dt) > 0.00001) c.status = 431;  // :307-310
 }
 
+template <bool TWO_PASS>
 __device__ __noinline__ void column_step(Col& c, const Forcing& f, bool want_diag, const SnapOut& snap) {
   const View v = c;
   const double dt = CFG.dt;
@@ -1065,7 +1067,7 @@ __device__ __noinline__ void column_step(Col& c, const Forcing& f, bool want_dia
   // Two-pass step (forward_pass / backward_pass above) or the general sub-step-by-sub-step path?  Decided per column
   // after S3: the snow state and m(1) are final for this step's S10 / S11 decisions.
   const bool next_step_outputs_pre = ((output_step ? 0 : c.n_time_out + 1) == CFG.i_time_out);
-  const bool fast = (c.status == 0) && fast_path_ok(c, output_step, want_diag || next_step_outputs_pre);
+  const bool fast = TWO_PASS && (c.status == 0) && fast_path_ok(c, output_step, want_diag || next_step_outputs_pre);
   if (c.status == 0 && !fast) {  // ===== phase 1 =====
   // ---- S4 backward sweep: S_bu, H -> T, phi -> S_br -> volume fractions :298-307 ----
   // When nothing touched m, S_abs, H_abs of layers 2..N_active since the S18 sweep of the previous step
@@ -1214,10 +1216,12 @@ __device__ __noinline__ void column_step(Col& c, const Forcing& f, bool want_dia
 
   }
   SAMSIM_PHASE_SYNC();
-  if (c.status == 0 && fast) {  // ===== phase 4, two-pass step: S4 .. S17 in one forward pass =====
-    EVT(c, EV_TWO_PASS_STEP);
-    testcase_hooks(c, f);  // S15: these testcases' hooks depend on the clock only (fast_path_ok), so they commute with S4-S13
-    forward_pass(c);
+  if (TWO_PASS) {
+    if (c.status == 0 && fast) {  // ===== phase 4, two-pass step: S4 .. S17 in one forward pass =====
+      EVT(c, EV_TWO_PASS_STEP);
+      testcase_hooks(c, f);  // S15: these testcases' hooks depend on the clock only (fast_path_ok), so they commute with S4-S13
+      forward_pass(c);
+    }
   }
   if (c.status == 0 && !fast) {  // ===== phase 4 =====
   // ---- S13 gravity drainage :463-477 ----
@@ -1276,9 +1280,9 @@ __device__ __noinline__ void column_step(Col& c, const Forcing& f, bool want_dia
     // Prepare the next step's merged forward pass unless ray must stay as fl_grav_drain left it (observable after
     // the launch or in the next step's S8 record).  S_bu is only observable after the launch.
     const bool next_step_outputs = (c.n_time_out == CFG.i_time_out);
-    const bool prepare = SAMSIM_TWO_PASS && CFG.two_pass && !(c.want_state || next_step_outputs) && c.N_active >= 3 && CFG.grav_flag == 2 &&
+    const bool prepare = TWO_PASS && !(c.want_state || next_step_outputs) && c.N_active >= 3 && CFG.grav_flag == 2 &&
                          CFG.harmonic_flag == 2 && CFG.n_bgc == 0;
-    backward_pass(c, prepare, c.want_state || SAMSIM_ALWAYS_STORE_S_BU);
+    backward_pass<TWO_PASS>(c, prepare, c.want_state || SAMSIM_ALWAYS_STORE_S_BU);
   }
 
   }

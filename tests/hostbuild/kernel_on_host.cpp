@@ -184,7 +184,10 @@ int hostk_step(void* p, long long nsteps) {
   SnapOut snap;
   snap.scalars = h->snap_sc.data(); snap.arrays = h->snap_arr.data(); snap.ncol_pad = 1; snap.col = 0;
 
-  for (long long s = 0; s < nsteps; s++) column_step(c, f, s == nsteps - 1, snap);
+  for (long long s = 0; s < nsteps; s++) {
+    if (h->g.two_pass) column_step<true>(c, f, s == nsteps - 1, snap);
+    else column_step<false>(c, f, s == nsteps - 1, snap);
+  }
 
   for (int q = 0; q < SC_COUNT; q++) h->sc[q] = c.sc[q];
   h->N_active = c.N_active; h->status = c.status; h->styropor_flag = c.styropor_flag;

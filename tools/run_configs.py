@@ -90,5 +90,41 @@ out["config5_one_day"] = {"columns": ncol, "steps": nsteps, "column_steps": ncol
                           "thickness_m_min_mean_max": [float(th.min()), float(th.mean()), float(th.max())],
                           "oracle_spot_check_columns": check, "oracle_bitwise_mismatches": bad_total}
 print(json.dumps(out["config5_one_day"]), flush=True)
+eng.close()
+
+# ---------------- config 5, one model month of one wave of columns (31 S8 records), divergence-driven re-binning ----------------
+ncol = bench.YEAR_COLUMNS
+eng = bench.make_engine(api, st, sites, ncol, 0, 0)
+eng.set_snapshot_mode(api.SNAP_SCALARS_ONLY)
+eng.set_rebin_auto(bench.YEAR_REBIN_THRESHOLD)
+ndays = 31
+t0 = time.time()
+kernel_ms = 0.0
+for d in range(ndays):
+    for _ in range(8):
+        eng.step(1080, sync=False)
+        eng.synchronize()
+        kernel_ms += eng.last_step_ms()
+    eng.step(1, sync=False)   # 8 x 1080 + 1 = 8641 = one output period
+    eng.synchronize()
+    kernel_ms += eng.last_step_ms()
+wall = time.time() - t0
+nsteps = ndays * 8641
+na = eng.get_int("N_active"); th = eng.get_scalar("thickness")
+check = [0, 1, ncol // 2, ncol - 1]
+cols = bench.make_oracle_columns(st, sites, np.array(check))
+bad_total = 0
+for j, col in zip(check, cols):
+    assert col.step(nsteps) == 0
+    bad = pu.compare_column(col, eng, j)
+    bad_total += len(bad)
+    if bad: print("config 5 month column", j, bad[:3])
+out["config5_one_month"] = {"columns": ncol, "steps": nsteps, "column_steps": ncol * nsteps, "wall_s": wall, "kernel_ms": kernel_ms,
+                            "Mcolsteps_per_s": ncol * nsteps / (kernel_ms * 1e-3) / 1e6, "failed": eng.count_failed(),
+                            "divergence": eng.divergence(),
+                            "N_active_min_mean_max": [int(na.min()), float(na.mean()), int(na.max())],
+                            "thickness_m_min_mean_max": [float(th.min()), float(th.mean()), float(th.max())],
+                            "oracle_spot_check_columns": check, "oracle_bitwise_mismatches": bad_total}
+print(json.dumps(out["config5_one_month"]), flush=True)
 (ROOT / "gpurun_out").mkdir(exist_ok=True)
 json.dump(out, open(ROOT / "gpurun_out" / "configs.json", "w"), indent=1)
