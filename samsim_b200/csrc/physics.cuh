@@ -872,6 +872,7 @@ __device__ __noinline__ void grav_drain(Col& c, bool exact_all) {
   const double S_br_Na = v.S_br()[Na];
   // :104-106 permeability, thick/perm, and the order-independent suffix minimum of perm(k:Na-1), one backward pass
   double perm_Na = 0.0;
+  int kmin_cand = 0, ncand = 0;  // candidates: layers whose estimate can exceed ray_crit
   {
     double mn = 0.0, sq = 0.0, st = 0.0, st_below = 0.0, qb_est = 0.0;  // suffix sums for the estimate
     SAMSIM_LOOP
@@ -900,15 +901,24 @@ __device__ __noinline__ void grav_drain(Col& c, bool exact_all) {
         est = est / (kappa_l * mu);
         // exactly 0 where the reference's value is exactly 0 (hp == 0); negative estimates clip like :135
         // (harmonic_flag 2: a candidate has est > 0, hence mn >= 1e-14: its exact evaluation needs no smin)
-        v.ray()[k] = (CFG.harmonic_flag == 2 && mn < 1e-14) ? 0.0 : f_max(est, 0.0);
+        const double rest = (CFG.harmonic_flag == 2 && mn < 1e-14) ? 0.0 : f_max(est, 0.0);
+        v.ray()[k] = rest;
+        if (rest > ray_crit * (1.0 - 1e-10)) { kmin_cand = k; ncand++; }
       }
     }
   }
   const double qb = bottom_h / perm_Na;
 
-  // blocks of GB layers, from the bottom block upwards; `carry_t` = SUM(thick(k0+GB : Na-1)) of the block below
+  // blocks of GB layers, from the bottom block upwards; `carry_t` = SUM(thick(k0+GB : Na-1)) of the block below.
+  // All layers when ray is observable (exact_all); otherwise, when several layers are candidates, the blocks from the
+  // topmost candidate down: the candidates of a column sit together (the warm lower part of the ice), and their
+  // forward sums share every load -- evaluating them one by one in the drain loop is O(candidates x depth).
+  const bool blocked = exact_all || ncand >= 3;
+  const int kstop = exact_all ? 1 : kmin_cand;   // evaluate the blocks that reach up to this layer
+  int kexact_from = exact_all ? 1 : Na;          // ray(k) is exact for k >= kexact_from
   double carry_t = 0.0;
-  for (int k0 = ((Na - 2) / SAMSIM_GB) * SAMSIM_GB + 1; exact_all && k0 >= 1 && Na >= 2; k0 -= SAMSIM_GB) {
+  for (int k0 = ((Na - 2) / SAMSIM_GB) * SAMSIM_GB + 1; blocked && k0 >= 1 && k0 + SAMSIM_GB - 1 >= kstop && Na >= 2; k0 -= SAMSIM_GB) {
+    kexact_from = k0;
     double aq[SAMSIM_GB], at[SAMSIM_GB];
 #pragma unroll
     for (int j = 0; j < SAMSIM_GB; j++) { aq[j] = 0.0; at[j] = 0.0; }
@@ -941,8 +951,12 @@ __device__ __noinline__ void grav_drain(Col& c, bool exact_all) {
         if (CFG.harmonic_flag == 1) {
           r = grav * rho_l * bbeta * d_S_br * height * f_min(smin[k], perm_Na);  // MINVAL(perm(k:N_active))
         } else {
+          // :112-113 minval(perm(k:Na-1)) < 1e-14 -> harmonic_perm = 0.  Without exact_all the suffix minimum was not
+          // stored; there the estimate is exactly 0 iff the minimum is below 1e-14 or S_br(k) <= S_br(Na), and in both
+          // cases ray(k) = MAX(.., 0) is exactly 0 as well (height, harmonic_perm > 0 otherwise): such layers keep their 0
+          const bool zero = exact_all ? (smin[k] < 1e-14) : (v.ray()[k] == 0.0);
           double hp;
-          if (smin[k] < 1e-14) {  // :112-113
+          if (zero) {
             hp = 0.0;
           } else {                // :115-120
             hp = aq[j] + qb;
@@ -975,7 +989,7 @@ __device__ __noinline__ void grav_drain(Col& c, bool exact_all) {
     double rk = v.ray()[k];
     const double Sk = v.S_abs()[k];
     const double sbk1 = v.S_br()[k + 1];
-    if (!exact_all && rk > ray_crit * (1.0 - 1e-10)) {
+    if (k < kexact_from && rk > ray_crit * (1.0 - 1e-10)) {
       // candidate: the reference's forward sums (:115-120, :128) for this layer only, then ray(k) as at :126-136
       double hq = 0.0, ht = 0.0, hb = 0.0;
       SAMSIM_LOOP
