@@ -289,6 +289,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-year-weighted", action="store_true", help="skip the six-regime year-weighted block (N = 1 only)")
+    ap.add_argument("--two-pass", action="store_true", help="kernel tuning: the two-pass step (samsim_step_kernel<true>) instead of the general path")
+    ap.add_argument("--model-steps", type=int, default=MODEL_STEPS, help="model timesteps per bench step (one launch)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -332,7 +334,10 @@ def main():
         col0, per = D.shard(total, rank, world)
     st = load_state(START_RECORD)
     sites = load_sites(64)
+    global MODEL_STEPS
+    MODEL_STEPS = args.model_steps
     eng = make_engine(api, st, sites, per, col0, local_rank)
+    eng.set_tuning(args.two_pass)
     eng.set_snapshot_mode(api.SNAP_SCALARS_ONLY)
 
     def barrier():
@@ -468,6 +473,7 @@ def main():
             "ms_per_step": wall_a_s / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world, scaling=args.scaling, per_gpu=per),
+            "kernel_path": "two-pass step (samsim_step_kernel<true>)" if args.two_pass else "general path (samsim_step_kernel<false>)",
             "e2e": {"value": col_steps / wall_b_s, "unit": "column-timesteps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
