@@ -279,6 +279,7 @@ def year_weighted(api, sites: np.ndarray, device: int) -> dict:
 
 
 def main():
+    global MODEL_STEPS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -334,7 +335,6 @@ def main():
         col0, per = D.shard(total, rank, world)
     st = load_state(START_RECORD)
     sites = load_sites(64)
-    global MODEL_STEPS
     MODEL_STEPS = args.model_steps
     eng = make_engine(api, st, sites, per, col0, local_rank)
     eng.set_tuning(args.two_pass)
