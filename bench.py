@@ -47,7 +47,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 TOTAL_COLUMNS = 1 << 20
-MODEL_STEPS = 16            # model timesteps per bench step (one launch)
+MODEL_STEPS = 64            # model timesteps per bench step (one launch)
 START_RECORD = 200          # oracle SHEBA state (tests/golden/sheba_oracle_states.npz)
 SITES = ["sheba", "70N00W", "75N00W", "75N180E", "80N00E", "80N90E", "85N180E", "NorthPole", "barrow"]
 # Algorithmic FP64 work of ONE column timestep of this workload, counted on the CPU oracle with the
