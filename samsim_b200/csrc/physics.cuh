@@ -1329,6 +1329,170 @@ __device__ __noinline__ void flush3(Col& c) {
   if (fabs(v.m()[1]) < 0.000001) c.status = 9876;  // :230-233
 }
 
+// flush3 without tracers, with its sweeps merged (the melt season is bound by DRAM traffic: 109 KB per column-step at
+// SHEBA state 345, profiles/r2_ncu_step_kernel_state345.json).  Same expressions, same order as flush3 above; the
+// differences are where values live:
+//   * R_v, R_h (:133-137) are recomputed from perm and thick where they are used instead of being stored;
+//   * the new flush_v / flush_h are ADDED to the accumulated arrays as they are produced -- the driver's
+//     old = cur; cur = 0; flush3; cur = cur + old (mo_grotz.f90:697-701, :736-737) is cur + new, and IEEE addition
+//     commutes -- so the two copy sweeps and the zeroing disappear (flush_h of this step is kept in w3 for :196-206);
+//   * the local S_bu = S_abs/m (:103) is evaluated inside mass_transfer from the values it reads anyway
+//     (S_abs(k+1) before layer k+1 is updated, the carried pre-update value of layer k, m is not modified);
+//   * fl_m (:179-180) is written by the flush_v sweep; the MINVAL of :218 rides along the horizontal-loss sweep.
+// Scratch: w2 R, w3 flush_h of this step, fl_m.
+__device__ __noinline__ void flush3_fused(Col& c) {
+  const View v = c;
+  const int Na = c.N_active, N = CFG.Nlayer;
+  const double dt = CFG.dt, freeboard = SCV(c, SC_FREEBOARD);
+  Lay R = v.w2(), fh_new = v.w3(), fl_m = v.fl_m();
+  double& melt_thick = SCV(c, SC_MELT_THICK);
+  EVT(c, EV_FLUSH3);
+
+  const double konst = sum_fwd(v.thick(), 1, Na) * para_flush_horiz;          // :106
+  melt_thick = f_min(melt_thick, v.psi_l()[1] * v.thick()[1]);                  // :110
+  melt_thick = f_min(melt_thick, CFG.thick_0 / 3.0);                          // :112
+
+  // :114-130 permeability (a state array: dat_perm), then :137-146 the resistance recurrence, one backward sweep
+  if (CFG.snow_flush_flag == 1) {
+    SAMSIM_LOOP
+    for (int k = Na + 1; k <= N; k++) v.perm()[k] = 0.0;
+  } else if (CFG.snow_flush_flag == 0) {
+    SAMSIM_LOOP
+    for (int k = Na + 1; k <= N; k++) v.perm()[k] = 1.0;
+  }
+  auto perm_of = [&](int k) {
+    double p;
+    if (CFG.snow_flush_flag == 1) {
+      p = 1e-17 * det_pow(1000.0 * fabs(v.psi_l()[k] + 2. * v.psi_g()[k]), 3.10);
+      if (p == 0.0) p = 1.0;
+    } else {
+      p = 1e-17 * det_pow(1000.0 * fabs(v.psi_l()[k]), 3.10);
+    }
+    return p;
+  };
+  double Rv1 = 0.0, Rh1 = 0.0, R2 = 0.0, R1 = 0.0;
+  {
+    double Rk1 = 0.0;  // R(k+1)
+    SAMSIM_LOOP
+    for (int k = Na; k >= 1; k--) {
+      const double p = perm_of(k);
+      v.perm()[k] = p;
+      const double pk = f_max(p, 0.00000000000000000000001), thk = v.thick()[k];
+      const double Rv = mu * thk / pk;
+      const double Rh = mu * konst / (thk * pk);
+      double Rk;
+      if (k == Na) Rk = 0.0;                 // :138
+      else if (k == Na - 1) Rk = Rv;         // :139
+      else {                                 // :141-146
+        const double r = Rk1 + Rv;
+        Rk = ((r)*Rh) / (r + Rh);
+      }
+      R[k] = Rk;
+      if (k == 2) R2 = Rk;
+      if (k == 1) { R1 = Rk; Rv1 = Rv; Rh1 = Rh; }
+      Rk1 = Rk;
+    }
+  }
+  const double T1 = v.T()[1];
+  double flush_total = (freeboard + melt_thick) / R1 * grav * dt * density_of(T1, S_br_of(T1)) * rho_l;  // :152
+  flush_total = f_min(flush_total, melt_thick * rho_l);
+  SCV(c, SC_MELT_ERR) = SCV(c, SC_MELT_ERR) + melt_thick - f_min(flush_total / rho_l, melt_thick);  // :156
+
+  // :158-165 flush_h / flush_v top -> bottom, accumulated into the output arrays; fl_m(k+1) = -flush_v(k) (:179-180)
+  fl_m[1] = 0.0;
+  double sfh = 0.0;  // SUM(flush_h), forward
+  {
+    const double den = R2 + Rv1 + Rh1;
+    double fh = flush_total * (R2 + Rv1) / den;   // :159-160
+    double fv = flush_total * Rh1 / den;
+    SAMSIM_LOOP
+    for (int k = 1; k <= Na; k++) {
+      if (k >= 2 && k <= Na - 1) {                // :161-164
+        const double pk = f_max(v.perm()[k], 0.00000000000000000000001), thk = v.thick()[k];
+        const double Rv = mu * thk / pk;
+        const double Rh = mu * konst / (thk * pk);
+        const double a = R[k + 1] + Rv, den2 = a + Rh;
+        fh = fv * a / den2;
+        fv = fv * Rh / den2;
+      } else if (k == Na) {
+        fh = 0.0;                                  // flush_h(Na) = 0, flush_v(Na) = flush_v(Na-1)
+      }
+      v.flush_h()[k] = fh + v.flush_h()[k];
+      v.flush_v()[k] = fv + v.flush_v()[k];
+      fh_new[k] = fh;
+      fl_m[k + 1] = -fv;
+      if (k <= Na - 1) sfh = sfh + fh;
+    }
+  }
+  const double fv_Na = -fl_m[Na + 1];
+
+  // :182 mass_transfer with the LOCAL S_bu = S_abs/m of the state before the transfer (mo_mass.f90:53-96)
+  const double T_bottom = SCV(c, SC_T_BOTTOM), S_bu_bottom = SCV(c, SC_S_BU_BOTTOM);
+  double sbu_Na;
+  {
+    double T_km1 = 0.0, Sbu_km1 = 0.0, Sabs_km1 = 0.0;
+    double T_k = v.T()[1], Sbu_k = v.S_abs()[1] / v.m()[1];
+    double f0 = 0.0;
+    SAMSIM_LOOP
+    for (int k = 1; k <= Na; k++) {
+      double T_kp1, Sbu_kp1, Sabs_kp1;
+      if (k < Na) {
+        T_kp1 = v.T()[k + 1];
+        Sabs_kp1 = v.S_abs()[k + 1];
+        Sbu_kp1 = Sabs_kp1 / v.m()[k + 1];
+      } else {
+        T_kp1 = T_bottom; Sbu_kp1 = S_bu_bottom; Sabs_kp1 = S_bu_bottom * 2000.0;
+      }
+      const double f1 = fl_m[k + 1];
+      double H = v.H_abs()[k], S = v.S_abs()[k];
+      mass_transfer_layer(f1, f0, T_km1, Sbu_km1, Sabs_km1, T_k, Sbu_k, T_kp1, Sbu_kp1, Sabs_kp1, H, S);
+      v.H_abs()[k] = H;
+      v.S_abs()[k] = S;
+      T_km1 = T_k; Sbu_km1 = Sbu_k; Sabs_km1 = S;
+      if (k < Na) { T_k = T_kp1; Sbu_k = Sbu_kp1; }
+      f0 = f1;
+    }
+    sbu_Na = Sbu_k;  // S_bu(N_active) of :103
+  }
+  const double T_Na = v.T()[Na];
+  if (CFG.flush_heat_flag == 2) v.H_abs()[Na] = v.H_abs()[Na] - (-fv_Na) * T_Na * c_l;  // :185-187 (fl_m(Na+1) = -flush_v(Na))
+
+  v.m()[1] = v.m()[1] - flush_total;  // :190-191
+  v.thick()[1] = v.thick()[1] - flush_total / rho_l;
+
+  double H_Na = v.H_abs()[Na], S_Na = v.S_abs()[Na];
+  double mn = 1e300;
+  SAMSIM_LOOP
+  for (int k = 1; k <= Na - 1; k++) {  // :196-206
+    const double fh = fh_new[k], Tk = v.T()[k];
+    const double Sk = v.S_abs()[k];
+    const double loss_S = fh * S_br_of(Tk, Sk / v.m()[k]);
+    const double loss_H = fh * Tk * c_l;
+    const double Snew = Sk - loss_S;
+    v.S_abs()[k] = Snew;
+    v.H_abs()[k] = v.H_abs()[k] - loss_H;
+    H_Na = H_Na + loss_H;
+    S_Na = S_Na + loss_S;
+    mn = f_min(mn, Snew);
+  }
+  // SUM(flush_h) over the N_active-long dummy: sfh + flush_h(Na) = sfh + 0
+  sfh = sfh + 0.0;
+  const double loss_S = sfh * sbu_Na;  // :207-208
+  const double loss_H = sfh * T_Na * c_l;
+  if (CFG.flush_heat_flag == 2) H_Na = H_Na - loss_H;
+  S_Na = S_Na - loss_S;
+  v.H_abs()[Na] = H_Na;
+  v.S_abs()[Na] = S_Na;
+  mn = f_min(mn, S_Na);
+  mn = f_min(mn, 0.0);  // MINVAL over all Nlayer: inactive layers hold 0
+  if (mn < -0.00000000000000000000000001) {  // :218-227
+    EVT(c, EV_FLUSH3_CLAMP);
+    SAMSIM_LOOP
+    for (int k = 1; k <= Na; k++) v.S_abs()[k] = f_max(v.S_abs()[k], 0.0);
+  }
+  if (fabs(v.m()[1]) < 0.000001) c.status = 9876;  // :230-233
+}
+
 // flush4, mo_flush.f90:253-296 (flush_flag 6)
 __device__ __noinline__ void flush4(Col& c) {
   const View v = c;

@@ -1010,7 +1010,6 @@ __device__ __noinline__ void column_step(Col& c, const Forcing& f, bool want_dia
   c.i = c.i + 1;
   c.want_state = want_diag;
   const bool output_step = (c.n_time_out == CFG.i_time_out || c.i == 1);
-  const bool fused = c.thermo_valid;  // S4+S5+S7 as one forward pass (bit-identical, see fused_thermo_expulsion)
 
   if (c.status == 0) {  // ===== phase 0 =====
   // ---- S0 :192-223 (only observable at S8 or through get_scalar after the launch) ----
@@ -1069,87 +1068,19 @@ __device__ __noinline__ void column_step(Col& c, const Forcing& f, bool want_dia
   const bool next_step_outputs_pre = ((output_step ? 0 : c.n_time_out + 1) == CFG.i_time_out);
   const bool fast = TWO_PASS && (c.status == 0) && fast_path_ok(c, output_step, want_diag || next_step_outputs_pre);
   if (c.status == 0 && !fast) {  // ===== phase 1 =====
-  // ---- S4 backward sweep: S_bu, H -> T, phi -> S_br -> volume fractions :298-307 ----
-  // When nothing touched m, S_abs, H_abs of layers 2..N_active since the S18 sweep of the previous step
-  // (c.thermo_valid), getT would be called with the same H, S_bu and the same chained first guess and return the
-  // same T, phi: those layers skip the Newton iterations.  Layer 1 (snow, precipitation, melt water) is always
-  // recomputed.  Expulsion depends on phi from S18, so it is evaluated every step.
-  if (fused) {
-    fused_thermo_expulsion(c);
-  } else {
-    fb_reset(c);
-    c.min_psi_s = 1e300;
-    double T_test = SCV(c, SC_T_BOTTOM);
-    const bool reuse = false;
-    SAMSIM_LOOP
-    for (int k = c.N_active; k >= 1; k--) {
-      if (k - SAMSIM_PF >= 1) {
-        v.m().prefetch(k - SAMSIM_PF); v.thick().prefetch(k - SAMSIM_PF);
-        if (reuse) { v.T().prefetch(k - SAMSIM_PF); v.phi().prefetch(k - SAMSIM_PF); v.S_bu().prefetch(k - SAMSIM_PF); }
-        else { v.S_abs().prefetch(k - SAMSIM_PF); v.H_abs().prefetch(k - SAMSIM_PF); }
-      }
-      const double mk = v.m()[k];
-      double sbu, T, phi;
-      if (reuse && k >= 2) {
-        sbu = v.S_bu()[k]; T = v.T()[k]; phi = v.phi()[k];
-      } else {
-        sbu = v.S_abs()[k] / mk;
-        const double H = v.H_abs()[k] / mk;
-        phi = v.phi()[k];
-        getT(H, sbu, T_test, T, phi, c.status, c.ev1);
-        v.S_bu()[k] = sbu; v.T()[k] = T; v.phi()[k] = phi;
-      }
-      T_test = T;
-      v.S_br()[k] = S_br_of(T, sbu);
-      double ps, pl, pg, vex;
-      expulsion(phi, v.thick()[k], mk, ps, pl, pg, vex);
-      v.psi_s()[k] = ps; v.psi_l()[k] = pl; v.psi_g()[k] = pg; v.V_ex()[k] = vex;
-      c.min_psi_s = f_min(c.min_psi_s, ps);
-    }
-    }
+  // ---- S4 :298-307, S5 :312-321, S7 :333-335 ----
+  // S4's getT sweep is the same computation as S18's (S_bu = S_abs/m, H = H_abs/m, first guess chained from the layer
+  // below, T_bottom at N_active).  When nothing touched m, S_abs, H_abs of layers 2..N_active since the S18 sweep of
+  // the previous step (c.thermo_valid), it would return the same T, phi and is skipped; otherwise (first step of a
+  // launch, after flushing or a layer event) it is run as that sweep.  Either way the volume fractions (Expulsion),
+  // expulsion_flux, mass_transfer and S7 then run as ONE forward pass with fl_m, V_ex, S_br in registers; layer 1
+  // (snow, precipitation, melt water) is always recomputed there.
+  if (!c.thermo_valid) backward_pass<false>(c, false, false);
+  fused_thermo_expulsion(c);
 
   }
   SAMSIM_PHASE_SYNC();
   if (c.status == 0) {  // ===== phase 2 =====
-  // ---- S5 expulsion_flux (mo_mass.f90:112-136) then mass_transfer (skipped at i == 1) :312-321 ----
-  if (!fused) {
-    const int Na = c.N_active;
-    Lay fl_m = v.fl_m();
-    double f0 = 0.0;
-    fl_m[1] = 0.0;
-    SAMSIM_LOOP
-    for (int k = 1; k <= Na; k++) {
-      double f1;
-      const double vex = v.V_ex()[k];
-      if (k == 1) {
-        f1 = -vex * rho_l;
-      } else {
-        const double pg = v.psi_g()[k];
-        if (pg < SAMSIM_F32(0.001)) {
-          f1 = -vex * rho_l + f0;
-        } else {
-          const double thk = v.thick()[k];
-          f1 = -f_max((vex - pg * thk) * rho_l, 0.0);
-          v.psi_g()[k] = f_max((pg * thk - vex) / thk, 0.0);
-        }
-      }
-      fl_m[k + 1] = f1;
-      v.m()[k] = v.m()[k] + f1 - f0;
-      f0 = f1;
-    }
-    if (c.i != 1) mass_transfer(c, fl_m, v.S_bu());
-    if (CFG.n_bgc) {  // :316-320
-      SAMSIM_LOOP
-      for (int k = 1; k <= Na; k++) {
-        v.A(AR_FB_D)[k] = (c.i != 1) ? -fl_m[k + 1] : 0.0;
-        v.A(AR_FB_U)[k] = 0.0; v.A(AR_FB_A)[k] = 0.0; v.A(AR_FB_O)[k] = 0.0;
-      }
-    }
-    // ---- S7 :333-335 ----
-    SAMSIM_LOOP
-    for (int k = Na; k >= 1; k--) v.S_bu()[k] = v.S_abs()[k] / v.m()[k];
-  }
-
   c.fb_x = 0.0;
   // ---- S8 output :340-398 ----
   if (output_step) {
@@ -1351,14 +1282,18 @@ __device__ __noinline__ void column_step(Col& c, const Forcing& f, bool want_dia
     } else if (CFG.flush_flag == 5) {  // :715-728
       if (SCV(c, SC_MELT_THICK) > 0.000000000001 && c.N_active > 2 && SCV(c, SC_FREEBOARD) > 0.0) {
         SCV(c, SC_FREEBOARD) = freeboard_of(c);
-        const int Na = c.N_active;
-        Lay old_v = v.V_ex(), old_h = v.S_br();  // both dead after S13
-        SAMSIM_LOOP
-        for (int k = 1; k <= Na; k++) { old_v[k] = v.flush_v()[k]; old_h[k] = v.flush_h()[k]; }
-        flush3(c);
+        if (CFG.n_bgc == 0) {
+          flush3_fused(c);  // adds this step's flush_v / flush_h to the accumulated arrays itself
+        } else {
+          const int Na = c.N_active;
+          Lay old_v = v.V_ex(), old_h = v.S_br();  // both dead after S13
+          SAMSIM_LOOP
+          for (int k = 1; k <= Na; k++) { old_v[k] = v.flush_v()[k]; old_h[k] = v.flush_h()[k]; }
+          flush3(c);
+          SAMSIM_LOOP
+          for (int k = 1; k <= Na; k++) { v.flush_v()[k] = v.flush_v()[k] + old_v[k]; v.flush_h()[k] = v.flush_h()[k] + old_h[k]; }
+        }
         c.thermo_valid = false; c.pre.valid = false;
-        SAMSIM_LOOP
-        for (int k = 1; k <= Na; k++) { v.flush_v()[k] = v.flush_v()[k] + old_v[k]; v.flush_h()[k] = v.flush_h()[k] + old_h[k]; }
             }
     } else if (CFG.flush_flag == 6) {  // :729-733
       if (SCV(c, SC_MELT_THICK) > 0.000000000001 && c.N_active > 2 && SCV(c, SC_THICK_SNOW) < CFG.thick_0) {
