@@ -383,19 +383,19 @@ __device__ __noinline__ void fused_thermo_expulsion(Col& c) {
   const View v = c;
   const int Na = c.N_active;
   const bool transfer = (c.i != 1);
-  const double T_bottom = SCV(c, SC_T_BOTTOM), S_bu_bottom = SCV(c, SC_S_BU_BOTTOM);
-  // layer 1 is always recomputed; its first guess is T(2) of the (valid) sweep, T_bottom when it is the only layer
-  double T_k, sbu_k, phi_k;
-  double m_k = v.m()[1];
-  {
-    sbu_k = v.S_abs()[1] / m_k;
-    const double H = v.H_abs()[1] / m_k;
-    phi_k = v.phi()[1];
-    const double T_test = (Na >= 2) ? v.T()[2] : T_bottom;
-    getT(H, sbu_k, T_test, T_k, phi_k, c.status, c.ev1);
-    v.T()[1] = T_k; v.phi()[1] = phi_k;
+  {  // layer 1 is always recomputed; its first guess is T(2) of the (valid) sweep, T_bottom when it is the only layer
+    const double m1 = v.m()[1];
+    const double sbu1 = v.S_abs()[1] / m1, H = v.H_abs()[1] / m1;
+    double phi1 = v.phi()[1], T1;
+    const double T_test = (Na >= 2) ? v.T()[2] : SCV(c, SC_T_BOTTOM);
+    getT(H, sbu1, T_test, T1, phi1, c.status, c.ev1);
+    v.T()[1] = T1; v.phi()[1] = phi1;
   }
-  double T_km1 = 0.0, Sbu_km1 = 0.0, Sabs_km1 = 0.0, f0 = 0.0;
+  // expulsion_flux only produces fl_m <= 0 (see expel_layer below): of mass_transfer's four branches only
+  // `fl_m(k+1) < 0` and `fl_m(k) < 0` can be taken, the layer below is never read, and the pass needs no look-ahead.
+  // Carried from layer k-1: T, S_br (the S4 value mass_transfer evaluates again from the same T and S_bu,
+  // mo_mass.f90:91), the S_abs the transfer left there, fl_m(k).
+  double T_km1 = 0.0, sbr_km1 = 0.0, Sabs_km1 = 0.0, f0 = 0.0;
   // func_freeboard memo: forward totals and the exact suffix sums for the waterline layer of the previous step
   double fbA = 0.0, fbG = 0.0, fbAs = 0.0, fbGs = 0.0;
   const int ks = (c.fb.k_last >= 1 && c.fb.k_last < Na) ? c.fb.k_last : 0;
@@ -407,20 +407,13 @@ __device__ __noinline__ void fused_thermo_expulsion(Col& c) {
       v.m().prefetch(k + SAMSIM_PF); v.thick().prefetch(k + SAMSIM_PF); v.S_abs().prefetch(k + SAMSIM_PF);
       v.H_abs().prefetch(k + SAMSIM_PF);
     }
-    const double thk = v.thick()[k];
-    // neighbour below: old T, S_bu (S4 values) and the not yet updated S_abs
-    double T_kp1, Sbu_kp1, Sabs_kp1, phi_kp1 = 0.0, m_kp1 = 0.0;
-    if (k < Na) {
-      T_kp1 = v.T()[k + 1]; Sabs_kp1 = v.S_abs()[k + 1];
-      phi_kp1 = v.phi()[k + 1]; m_kp1 = v.m()[k + 1];
-      Sbu_kp1 = Sabs_kp1 / m_kp1;  // S_bu(k+1) of S4 (:299); the S_bu array is not kept current by the two-pass steps
-    } else {
-      T_kp1 = T_bottom; Sbu_kp1 = S_bu_bottom; Sabs_kp1 = S_bu_bottom * 2000.0;
-    }
-    // S4: brine salinity and volume fractions
-    v.S_br()[k] = S_br_of(T_k, sbu_k);
+    const double thk = v.thick()[k], m_k = v.m()[k], T_k = v.T()[k];
+    double S = v.S_abs()[k];
+    // S4: S_bu = S_abs/m (:299; the S_bu array is not kept current by the S18 sweep), brine salinity, volume fractions
+    const double sbr_k = S_br_of(T_k, S / m_k);
+    v.S_br()[k] = sbr_k;
     double ps, pl, pg, vex;
-    expulsion(phi_k, thk, m_k, ps, pl, pg, vex);
+    expulsion(v.phi()[k], thk, m_k, ps, pl, pg, vex);
     // expulsion_flux, mo_mass.f90:121-134
     double f1;
     if (k == 1) {
@@ -438,11 +431,17 @@ __device__ __noinline__ void fused_thermo_expulsion(Col& c) {
     min_ps = f_min(min_ps, ps);
     const double m_new = m_k + f1 - f0;
     v.m()[k] = m_new;
-    // mass_transfer layer k, then S7
-    double S = v.S_abs()[k];
+    // mass_transfer layer k (mo_mass.f90:82-84, :89-92), then S7
     if (transfer) {
       double H = v.H_abs()[k];
-      mass_transfer_layer(f1, f0, T_km1, Sbu_km1, Sabs_km1, T_k, sbu_k, T_kp1, Sbu_kp1, Sabs_kp1, H, S);
+      if (f1 < 0.) {
+        H = H + f1 * T_k * c_l;
+        S = S + f_max(f1 * sbr_k, -S);
+      }
+      if (f0 < 0) {
+        H = H - f0 * T_km1 * c_l;
+        S = S - f_max(f0 * sbr_km1, -Sabs_km1);
+      }
       v.H_abs()[k] = H;
       v.S_abs()[k] = S;
     }
@@ -451,8 +450,7 @@ __device__ __noinline__ void fused_thermo_expulsion(Col& c) {
       v.A(AR_FB_D)[k] = transfer ? -f1 : 0.0;
       v.A(AR_FB_U)[k] = 0.0; v.A(AR_FB_A)[k] = 0.0; v.A(AR_FB_O)[k] = 0.0;
     }
-    T_km1 = T_k; Sbu_km1 = sbu_k; Sabs_km1 = S;
-    T_k = T_kp1; sbu_k = Sbu_kp1; phi_k = phi_kp1; m_k = m_kp1;
+    T_km1 = T_k; sbr_km1 = sbr_k; Sabs_km1 = S;
     f0 = f1;
   }
   c.fb.tot_valid = true; c.fb.t1 = v.thick()[1]; c.fb.A = fbA; c.fb.G = fbG;
