@@ -406,16 +406,31 @@ __device__ __forceinline__ void notzflux(double time, double& fl_sw, double& fl_
 }
 
 // forward sums in the reference's order: SUM(a(i:j)) and SUM(a(i:j)*b(i:j))
+// Four layers are loaded before they are added (one after the other, in order): four loads in flight per thread
+// instead of one; the sums are latency-bound otherwise.
 __device__ __forceinline__ double sum_fwd(const Lay& a, int i, int j) {
   double s = 0.0;
+  int q = i;
   SAMSIM_LOOP
-  for (int q = i; q <= j; q++) s = s + a[q];
+  for (; q + 3 <= j; q += 4) {
+    const double a0 = a[q], a1 = a[q + 1], a2 = a[q + 2], a3 = a[q + 3];
+    s = s + a0; s = s + a1; s = s + a2; s = s + a3;
+  }
+  SAMSIM_LOOP
+  for (; q <= j; q++) s = s + a[q];
   return s;
 }
 __device__ __forceinline__ double sum_prod_fwd(const Lay& a, const Lay& b, int i, int j) {
   double s = 0.0;
+  int q = i;
   SAMSIM_LOOP
-  for (int q = i; q <= j; q++) s = s + a[q] * b[q];
+  for (; q + 3 <= j; q += 4) {
+    const double a0 = a[q], a1 = a[q + 1], a2 = a[q + 2], a3 = a[q + 3];
+    const double b0 = b[q], b1 = b[q + 1], b2 = b[q + 2], b3 = b[q + 3];
+    s = s + a0 * b0; s = s + a1 * b1; s = s + a2 * b2; s = s + a3 * b3;
+  }
+  SAMSIM_LOOP
+  for (; q <= j; q++) s = s + a[q] * b[q];
   return s;
 }
 
@@ -437,10 +452,21 @@ __device__ __noinline__ double freeboard_of(Col& c) {
   const double m1 = v.m()[1], th1 = v.thick()[1];
   Col::FbMemo& fb = c.fb;
   if (fb.res_valid && fb.m1 == m1 && fb.th1 == th1 && fb.msnow == snowmass) return fb.result;
-  double A, G;
+  double A = 0.0, G = 0.0;
+  bool have_totals = false;
   if (fb.tot_valid && fb.t1 == th1) {
     A = fb.A; G = fb.G;
-  } else {
+    have_totals = true;
+  } else if (fb.tot_valid) {
+    // Only thick(1) moved since the totals were taken (S20 melts the surface every step of the melt season).  Swap
+    // the first term: equal to the fresh forward sum up to a few ulps, far inside `margin`.  The totals are used
+    // exactly only when the snow outweighs the buoyancy (:99-102), so this needs snowmass < buoy beyond the margin.
+    const double ps1 = v.psi_s()[1], pg1 = v.psi_g()[1];
+    const double A1 = fb.A - ps1 * fb.t1 + ps1 * th1, G1 = fb.G - pg1 * fb.t1 + pg1 * th1;
+    const double b1 = A1 * (rho_l - rho_s) + G1 * rho_l;
+    if (snowmass < b1 - (1e-9 * (fabs(b1) + fabs(snowmass)) + 1e-300)) { A = A1; G = G1; have_totals = true; }
+  }
+  if (!have_totals) {
     A = 0.0; G = 0.0;  // forward totals, the reference's order
     SAMSIM_LOOP
     for (int q = 1; q <= Na; q++) {
@@ -934,7 +960,8 @@ __device__ __noinline__ void grav_drain(Col& c, bool exact_all) {
     }
     SAMSIM_LOOP
     for (int kk = k0 + SAMSIM_GB; kk <= Na - 1; kk++) {  // body: every accumulator takes every layer, in order
-      if (kk + SAMSIM_PF <= Na - 1) { q.prefetch(kk + SAMSIM_PF); v.thick().prefetch(kk + SAMSIM_PF); }
+      // an iteration is 16 independent additions: the data must be requested several iterations ahead to arrive in time
+      if (kk + 8 <= Na - 1) { q.prefetch(kk + 8); v.thick().prefetch(kk + 8); }
       const double qv = q[kk], tv = v.thick()[kk];
 #pragma unroll
       for (int j = 0; j < SAMSIM_GB; j++) { aq[j] = aq[j] + qv; at[j] = at[j] + tv; }

@@ -10,6 +10,8 @@ from oracle import oracle, parity_util as pu
 ncol = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 rec = int(sys.argv[3]) if len(sys.argv) > 3 else 200
+pf = int(sys.argv[4]) if len(sys.argv) > 4 else 0          # L1 prefetch distance of the layer sweeps (0 = default)
+two_pass = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 z = np.load(ROOT / 'tests/golden/sheba_oracle_states.npz')
 p = f'state{rec}_'
 st = {k[len(p):]: (z[k] if z[k].ndim else z[k].item()) for k in z.files if k.startswith(p)}
@@ -18,6 +20,7 @@ col = oracle.Column(4, 'det'); col.set_forcing(*F); col.load_state(st)
 print('fp64 peak TF/s', api.fp64_peak(0, 1.0))
 eng = pu.engine_from_oracle(col, ncol=ncol)
 eng.set_forcing(F[None])
+if pf or two_pass: eng.set_tuning(bool(two_pass), pf)
 eng.step(20)
 for rep in range(3):
     t0 = time.time(); eng.step(nsteps); dt = time.time() - t0
