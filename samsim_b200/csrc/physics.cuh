@@ -408,7 +408,12 @@ __device__ __forceinline__ void notzflux(double time, double& fl_sw, double& fl_
 // forward sums in the reference's order: SUM(a(i:j)) and SUM(a(i:j)*b(i:j))
 // Four layers are loaded before they are added (one after the other, in order): four loads in flight per thread
 // instead of one; the sums are latency-bound otherwise.
-__device__ __forceinline__ double sum_fwd(const Lay& a, int i, int j) {
+#ifdef SAMSIM_SUM_NOINLINE
+#define SAMSIM_SUM_ATTR __noinline__
+#else
+#define SAMSIM_SUM_ATTR __forceinline__
+#endif
+__device__ SAMSIM_SUM_ATTR double sum_fwd(const Lay& a, int i, int j) {
   double s = 0.0;
   int q = i;
   SAMSIM_LOOP
@@ -420,7 +425,7 @@ __device__ __forceinline__ double sum_fwd(const Lay& a, int i, int j) {
   for (; q <= j; q++) s = s + a[q];
   return s;
 }
-__device__ __forceinline__ double sum_prod_fwd(const Lay& a, const Lay& b, int i, int j) {
+__device__ SAMSIM_SUM_ATTR double sum_prod_fwd(const Lay& a, const Lay& b, int i, int j) {
   double s = 0.0;
   int q = i;
   SAMSIM_LOOP
@@ -948,14 +953,20 @@ __device__ __noinline__ void grav_drain(Col& c, bool exact_all) {
     double aq[SAMSIM_GB], at[SAMSIM_GB];
 #pragma unroll
     for (int j = 0; j < SAMSIM_GB; j++) { aq[j] = 0.0; at[j] = 0.0; }
-#pragma unroll
+    // The head and the per-layer evaluation below are rolled loops over register arrays (selects / a shift register):
+    // unrolled they were 16 KB of straight-line code run three times per step, and the step kernel is bound by
+    // instruction fetch as much as by anything else (profiles/README.md, round 2).
+    SAMSIM_LOOP
     for (int d = 0; d < SAMSIM_GB; d++) {  // triangular head: layer k0+d feeds accumulators 0..d
       const int kk = k0 + d;
       if (kk <= Na - 1) {
         const double qv = q[kk], tv = v.thick()[kk];
 #pragma unroll
-        for (int j = 0; j < SAMSIM_GB; j++)
-          if (j <= d) { aq[j] = aq[j] + qv; at[j] = at[j] + tv; }
+        for (int j = 0; j < SAMSIM_GB; j++) {
+          const double nq = aq[j] + qv, nt = at[j] + tv;
+          aq[j] = (j <= d) ? nq : aq[j];
+          at[j] = (j <= d) ? nt : at[j];
+        }
       }
     }
     SAMSIM_LOOP
@@ -966,13 +977,16 @@ __device__ __noinline__ void grav_drain(Col& c, bool exact_all) {
 #pragma unroll
       for (int j = 0; j < SAMSIM_GB; j++) { aq[j] = aq[j] + qv; at[j] = at[j] + tv; }
     }
-#pragma unroll
+    const double carry_next = at[0];
+    double below = carry_t;  // SUM(thick(k+1:Na-1)): the accumulator of the layer below (0 when there is none)
+    SAMSIM_LOOP
     for (int j = SAMSIM_GB - 1; j >= 0; j--) {
       const int k = k0 + j;
+      const double aqj = aq[SAMSIM_GB - 1], atj = at[SAMSIM_GB - 1];  // accumulators of layer k: top of the shift register
+#pragma unroll
+      for (int i = SAMSIM_GB - 1; i >= 1; i--) { aq[i] = aq[i - 1]; at[i] = at[i - 1]; }
       if (k <= Na - 1) {
-        // height = SUM(thick(k+1:Na-1)) + bottom_h, :128
-        const double below = (j == SAMSIM_GB - 1) ? carry_t : ((k + 1 <= Na - 1) ? at[(j + 1) % SAMSIM_GB] : 0.0);
-        const double height = below + bottom_h;
+        const double height = below + bottom_h;  // :128
         const double d_S_br = v.S_br()[k] - S_br_Na;
         double r;
         if (CFG.harmonic_flag == 1) {
@@ -986,16 +1000,17 @@ __device__ __noinline__ void grav_drain(Col& c, bool exact_all) {
           if (zero) {
             hp = 0.0;
           } else {                // :115-120
-            hp = aq[j] + qb;
-            hp = (at[j] + bottom_h) / hp;
+            hp = aqj + qb;
+            hp = (atj + bottom_h) / hp;
           }
           r = grav * rho_l * bbeta * d_S_br * height * hp;
         }
         r = r / (kappa_l * mu);
         v.ray()[k] = f_max(r, 0.0);
       }
+      below = atj;
     }
-    carry_t = at[0];
+    carry_t = carry_next;
   }
 
   // :141 / :173 grav_salt = grav_salt + SUM(S_abs) before the drain loop and - SUM(S_abs) after it: both are
