@@ -57,7 +57,7 @@ SITES = ["sheba", "70N00W", "75N00W", "75N180E", "80N00E", "80N90E", "85N180E", 
 F_ALG_FLOP_PER_COLUMN_STEP = 112930.0
 B_ALG_BYTES_PER_COLUMN_STEP = 2 * 4 * 100 * 8  # read+write of m, S_abs, H_abs, thick once per model step
 NCU_DIGEST = "r2_ncu_step_kernel.json"           # committed ncu --set full digest of samsim_step_kernel
-NCU_DIGEST_COLUMN_STEPS = 262144 * 16            # columns x model steps of the launch captured there
+NCU_DIGEST_COLUMN_STEPS = 262144 * 64            # columns x model steps of the launch captured there
 # Regimes of the SHEBA year: oracle restart record -> share of the golden run's 1,643 records it represents
 # (reference_output/Reference_SHEBA_with_Version_2: N_active from dat_thick, melt from dat_melt; classification in
 # open water N_active = 1; ice melt with / without a full grid; snow melt; growth; full-grid winter)
@@ -490,6 +490,9 @@ def main():
                          "hbm": {"achieved": per_gpu_rate * B_ALG_BYTES_PER_COLUMN_STEP / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": per_gpu_rate * B_ALG_BYTES_PER_COLUMN_STEP / 1e9 / hbm_peak,
                                  "bytes_per_column_step": B_ALG_BYTES_PER_COLUMN_STEP,
+                                 # what the kernel really moves (ncu traffic per launch / measured launch time): the second limit
+                                 "dram_gbs": (traffic / (kern_s / max(launches, 1)) / 1e9) if traffic else None,
+                                 "dram_frac": (traffic / (kern_s / max(launches, 1)) / 1e9 / hbm_peak) if traffic else None,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}},
             "clocks": clocks,
             "failed_columns": int(nf.item()),

@@ -283,9 +283,12 @@ int samsim_b200_set_tuning(samsim_handle_t h, int32_t two_pass, int32_t prefetch
 int samsim_b200_set_rebin_interval(samsim_handle_t h, int64_t nsteps);
 /* Divergence-driven re-binning.  At the end of every launch each warp of the step kernel measures its own divergence
  * with warp reductions and ballots: idle lane-layers = SUM over lanes of (deepest N_active in the warp - the lane's
- * N_active) against all lane-layers, and whether its lanes disagree on the snow class.  With a threshold > 0 the next
- * samsim_b200_step re-bins the columns first when the idle share of the previous launch exceeded it (or more than four
- * times that share of warps were split by snow class); 0 switches the automatic mode off (the default). */
+ * N_active) against all lane-layers, and whether its lanes disagree on the regime class: the snow class (no snow /
+ * traces / thin, coupled to layer 1 / a layer of its own) and whether the surface melted in the last step (such a
+ * column flushes and re-solves every layer in the next step; one such lane makes its warp pay for both).  With a
+ * threshold > 0 the next samsim_b200_step re-bins the columns first when the idle share of the previous launch
+ * exceeded it (or more than four times that share of warps were split by class); 0 switches the automatic mode off
+ * (the default).  Re-binning sorts by (failed, N_active descending, class, forcing site). */
 int samsim_b200_set_rebin_auto(samsim_handle_t h, double idle_share_threshold);
 /* the last launch's measurement (waits for it), and the number of re-binnings so far; any pointer may be NULL */
 int samsim_b200_get_divergence(samsim_handle_t h, double* idle_lane_layer_share, double* snow_class_split_warp_share,

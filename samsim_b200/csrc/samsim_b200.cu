@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(SAMSIM_BLOCK, SAMSIM_MINBLOCKS) samsim_step_ke
   // ---- lane divergence of this launch's end state, measured where it arises: in the warp --------------------------
   // A warp runs every layer sweep to the deepest of its 32 columns and every branch that one of its lanes takes.
   // idle lane-layers = SUM over lanes (max N_active in the warp - N_active of the lane); lanes that disagree on the
-  // snow class (the S2 / S3 / S10 / S17 branches) or on being failed are counted per warp with a ballot.  The host
+  // snow class (the S2 / S3 / S10 / S17 branches), on a melting surface (S20-S21 flushing and the full S4 sweep that
+  // follows it) or on being failed are counted per warp with a ballot.  The host
   // re-bins the columns when the idle share crosses its threshold (samsim_b200_set_rebin_auto) instead of on a
   // fixed interval.
   if (p.divergence) {
@@ -144,7 +145,10 @@ __global__ void __launch_bounds__(SAMSIM_BLOCK, SAMSIM_MINBLOCKS) samsim_step_ke
     const int idle = __reduce_add_sync(full, live ? (mx - na) : 0);
     const int nlive = __popc(__ballot_sync(full, live));
     const double ts = c.sc[SC_THICK_SNOW];
-    const int cls = !live ? -1 : (ts <= 0.0) ? 0 : (ts < CFG.thick_min / 100.0) ? 1 : (ts < CFG.thick_min) ? 2 : 3;
+    // + 4 for columns whose surface melted in the last step: they flush (S21) and re-solve every layer in the next S4,
+    // and one such lane makes its warp pay for both
+    const int cls = !live ? -1 : (((ts <= 0.0) ? 0 : (ts < CFG.thick_min / 100.0) ? 1 : (ts < CFG.thick_min) ? 2 : 3) |
+                                  ((c.sc[SC_MELT_THICK] > 0.0) ? 4 : 0));
     const int cls0 = __shfl_sync(full, cls, __ffs(__ballot_sync(full, live)) - 1);
     const unsigned differ = __ballot_sync(full, live && cls != cls0);
     if ((threadIdx.x & 31) == 0 && nlive > 0) {
@@ -245,7 +249,8 @@ __global__ void samsim_vec_set_kernel(T* row, const T* src, int col0, int n, con
 }
 
 // ---- re-binning (columns are re-binned by regime for warp coherence; local permutation only) ----
-// key: failed columns last; then N_active descending (loop trip counts), snow class (the snow branches), forcing site
+// key: failed columns last; then N_active descending (loop trip counts), snow class (the snow branches) and melting
+// surface (flushing, full S4 sweep), forcing site
 __global__ void samsim_rebin_key_kernel(const double* sc, const int* in, const int* site_of_col, long long ncol,
                                         long long ncol_pad, double thick_min, unsigned* keys, int* vals) {
   const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -253,7 +258,8 @@ __global__ void samsim_rebin_key_kernel(const double* sc, const int* in, const i
   const int na = in[(size_t)IN_N_ACTIVE * ncol_pad + s];
   const int st = in[(size_t)IN_STATUS * ncol_pad + s];
   const double snow = sc[(size_t)SC_THICK_SNOW * ncol_pad + s];
-  const unsigned cls = (snow <= 0.0) ? 0u : (snow < thick_min / 100.0) ? 1u : (snow < thick_min) ? 2u : 3u;
+  const unsigned cls = ((snow <= 0.0) ? 0u : (snow < thick_min / 100.0) ? 1u : (snow < thick_min) ? 2u : 3u) |
+                       ((sc[(size_t)SC_MELT_THICK * ncol_pad + s] > 0.0) ? 4u : 0u);  // melting surface: the flushing / full-S4 path
   const unsigned site = site_of_col ? (unsigned)site_of_col[s] : 0u;
   // deepest columns first: blocks are dispatched in index order, so the cheap ones fill the tail of the launch
   keys[s] = ((st != 0) ? 0x80000000u : 0u) | ((0x7FFFFu - ((unsigned)na & 0x7FFFFu)) << 12) | (cls << 8) | (site & 0xFFu);
