@@ -90,6 +90,7 @@ NAMES = [
     "flood_with_instant_flooding", "flood_simple", "flush4", "flush_flag4_inline", "snow_thermo_flag0",
     "top_grow_middle", "top_melt_middle", "top_grow_few_layers", "top_melt_few_layers", "bottom_melt_full_grid",
     "snow_coupling_warm1_melt_snow_all", "snow_coupling_warm2", "styropor", "salt_clamp",
+    "flush3_heat_flag1", "flush3_snow_flush_flag0",
 ]
 
 
@@ -112,6 +113,16 @@ def build(oracle_mod, name: str) -> Scenario:
         col, F = _sheba(oracle_mod, sheba_state(345), ints=dict(flush_flag=4))
         return Scenario(name, col, (1, 2, 597), {"flush_inline", "snow_meltwater_to_ice", "snow_wet"}, forcing=F,
                         cite="mo_grotz.f90:704-713")
+    if name == "flush3_heat_flag1":
+        # bare-ice melt with the heat of the flushed brine staying in the lowest layer (flush_heat_flag 1: mo_flush.f90
+        # :185-187 and :211-213 are skipped); SHEBA runs with flag 2
+        col, F = _sheba(oracle_mod, sheba_state(345), ints=dict(flush_heat_flag=1))
+        return Scenario(name, col, (1, 2, 597), {"flush3", "melt_thick"}, forcing=F, cite="mo_flush.f90:185-187, :211-213")
+    if name == "flush3_snow_flush_flag0":
+        # flush3 with the permeability of snow_flush_flag 0 (mo_flush.f90:114-130: inactive layers fully permeable)
+        # (state 360: bare melting ice; with this flag a snow-covered column does not flush)
+        col, F = _sheba(oracle_mod, sheba_state(360), ints=dict(snow_flush_flag=0))
+        return Scenario(name, col, (1, 2, 597), {"flush3"}, forcing=F, cite="mo_flush.f90:114-130")
     if name == "snow_thermo_flag0":
         col, F = _sheba(oracle_mod, sheba_state(330), ints=dict(snow_flush_flag=0))
         return Scenario(name, col, (1, 2, 1497, 1500), {"snow_thermo", "snow_wet", "snow_compaction"}, forcing=F,
