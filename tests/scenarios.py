@@ -90,7 +90,7 @@ NAMES = [
     "flood_with_instant_flooding", "flood_simple", "flush4", "flush_flag4_inline", "snow_thermo_flag0",
     "top_grow_middle", "top_melt_middle", "top_grow_few_layers", "top_melt_few_layers", "bottom_melt_full_grid",
     "snow_coupling_warm1_melt_snow_all", "snow_coupling_warm2", "styropor", "salt_clamp",
-    "flush3_heat_flag1", "flush3_snow_flush_flag0",
+    "flush3_heat_flag1", "flush3_snow_flush_flag0", "flush3_with_tracers",
 ]
 
 
@@ -118,6 +118,16 @@ def build(oracle_mod, name: str) -> Scenario:
         # :185-187 and :211-213 are skipped); SHEBA runs with flag 2
         col, F = _sheba(oracle_mod, sheba_state(345), ints=dict(flush_heat_flag=1))
         return Scenario(name, col, (1, 2, 597), {"flush3", "melt_thick"}, forcing=F, cite="mo_flush.f90:185-187, :211-213")
+    if name == "flush3_with_tracers":
+        # the melt season with two passive tracers: the general flush3 (tracer replay through the brine-flux matrix,
+        # mo_flush.f90:166-178) and bgc_advection under flushing; the reference ships no such case (tracers: testcases 1, 2, 6)
+        col, F = _sheba(oracle_mod, sheba_state(345), ints=dict(bgc_flag=2, N_bgc=2))
+        m = col.array("m")
+        for q, conc in ((1, 400.0), (2, 500.0)):
+            col.set_array(f"bgc_abs{q}", m * conc)
+            col.set_scalar(f"bgc_bottom{q}", conc)
+            col.set_scalar(f"bgc_total{q}", float((m * conc).sum()))
+        return Scenario(name, col, (1, 2, 597), {"flush3", "flush3_clamp", "grav_drained"}, forcing=F, cite="mo_flush.f90:166-178, mo_grotz.f90:742-747")
     if name == "flush3_snow_flush_flag0":
         # flush3 with the permeability of snow_flush_flag 0 (mo_flush.f90:114-130: inactive layers fully permeable)
         # (state 360: bare melting ice; with this flag a snow-covered column does not flush)
