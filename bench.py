@@ -190,7 +190,7 @@ def run_reference_arm(args):
     oracle.build()
     idx = np.linspace(0, TOTAL_COLUMNS - 1, sample_cols).astype(np.int64)
     cols = make_oracle_columns(st, sites, idx, "libm")
-    steps_per = MODEL_STEPS * 64  # 1024 model steps per bench step so that a step is ~a second of CPU work
+    steps_per = MODEL_STEPS * 64  # 4,096 model steps per bench step: a few seconds of CPU work on all host cores
     for _ in range(args.warmup):
         oracle.run_batch(cols, steps_per, ncores)
     t0 = time.perf_counter()
