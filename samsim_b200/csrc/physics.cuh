@@ -889,7 +889,9 @@ __device__ __forceinline__ double fl_Q_0_snow(double m_snow, double thick_snow, 
 // relative deviation <= ~1e-14) and classifies every layer with them; the reference's forward sums are evaluated
 // only for layers whose estimate is above ray_crit*(1 - 1e-10) -- a margin four orders wider than the deviation --
 // so decisions and fluxes are the reference's, bit for bit, and layers that cannot drain cost O(1).
-#define SAMSIM_GB 8
+#ifndef SAMSIM_GB
+#define SAMSIM_GB 8   // layers per block of the blocked forward sums: 16 accumulators in registers
+#endif
 __device__ __noinline__ void grav_drain(Col& c, bool exact_all) {
   const View v = c;
   const int Na = c.N_active, N = CFG.Nlayer;
