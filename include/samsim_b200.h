@@ -288,7 +288,7 @@ int samsim_b200_set_rebin_interval(samsim_handle_t h, int64_t nsteps);
  * column flushes and re-solves every layer in the next step; one such lane makes its warp pay for both).  With a
  * threshold > 0 the next samsim_b200_step re-bins the columns first when the idle share of the previous launch
  * exceeded it (or more than four times that share of warps were split by class); 0 switches the automatic mode off
- * (the default).  Re-binning sorts by (failed, N_active descending, class, forcing site). */
+ * (the default).  Re-binning sorts by (failed, N_active descending, class, forcing site, surface temperature in 0.1 K buckets). */
 int samsim_b200_set_rebin_auto(samsim_handle_t h, double idle_share_threshold);
 /* the last launch's measurement (waits for it), and the number of re-binnings so far; any pointer may be NULL */
 int samsim_b200_get_divergence(samsim_handle_t h, double* idle_lane_layer_share, double* snow_class_split_warp_share,

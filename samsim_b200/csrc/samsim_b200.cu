@@ -250,7 +250,7 @@ __global__ void samsim_vec_set_kernel(T* row, const T* src, int col0, int n, con
 
 // ---- re-binning (columns are re-binned by regime for warp coherence; local permutation only) ----
 // key: failed columns last; then N_active descending (loop trip counts), snow class (the snow branches) and melting
-// surface (flushing, full S4 sweep), forcing site
+// surface (flushing, full S4 sweep), forcing site, surface temperature
 __global__ void samsim_rebin_key_kernel(const double* sc, const int* in, const int* site_of_col, long long ncol,
                                         long long ncol_pad, double thick_min, unsigned* keys, int* vals) {
   const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -262,7 +262,11 @@ __global__ void samsim_rebin_key_kernel(const double* sc, const int* in, const i
                        ((sc[(size_t)SC_MELT_THICK * ncol_pad + s] > 0.0) ? 4u : 0u);  // melting surface: the flushing / full-S4 path
   const unsigned site = site_of_col ? (unsigned)site_of_col[s] : 0u;
   // deepest columns first: blocks are dispatched in index order, so the cheap ones fill the tail of the launch
-  keys[s] = ((st != 0) ? 0x80000000u : 0u) | ((0x7FFFFu - ((unsigned)na & 0x7FFFFu)) << 12) | (cls << 8) | (site & 0xFFu);
+  // within a site, columns with a similar surface temperature (0.1 K buckets over -80..+22 degC) sit next to each other:
+  // their Newton sweeps take the same number of iterations and their drainage candidates span the same layers
+  const double tt = sc[(size_t)SC_T_TOP * ncol_pad + s];
+  const unsigned tb = (tt > -80.0) ? ((tt < 22.3) ? (unsigned)((tt + 80.0) * 10.0) : 1023u) : 0u;  // NaN -> 0
+  keys[s] = ((st != 0) ? 0x80000000u : 0u) | ((0xFFFu - ((unsigned)na & 0xFFFu)) << 19) | (cls << 15) | ((site & 0x1Fu) << 10) | tb;
   vals[s] = (int)s;
 }
 __global__ void samsim_rebin_unsorted_kernel(const unsigned* keys, long long ncol, int* out) {
