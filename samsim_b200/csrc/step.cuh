@@ -370,15 +370,16 @@ __device__ __noinline__ void write_snapshot(const Col& c, const SnapOut& s) {
   }
 }
 
-// S4 + S5 + S7 in ONE forward pass, valid when c.thermo_valid (layers 2..N_active carry T, phi, S_bu from the S18
-// sweep, so S4 has no backward dependency left): volume fractions and S_br (S4, :298-307), expulsion_flux
-// (mo_mass.f90:112-136), mass_transfer (mo_mass.f90:53-96, skipped at i == 1) and S_bu = S_abs/m (S7, :333-335)
-// per layer, with fl_m and V_ex carried in registers instead of being written and re-read.  Same operations in
-// the same order as the three separate sweeps:
+// S4 + S5 + S7 in ONE forward pass.  Precondition: layers 2..N_active carry the T and phi of a getT sweep over their
+// current m, S_abs, H_abs -- the S18 sweep of the previous step when nothing touched them since (c.thermo_valid),
+// otherwise the same sweep run just before (column_step, phase 1) -- so S4 has no backward dependency left.
+// Per layer: S_br and the volume fractions (S4, :298-307), expulsion_flux (mo_mass.f90:112-136), mass_transfer
+// (mo_mass.f90:53-96, skipped at i == 1) and S_bu = S_abs/m (S7, :333-335), with fl_m and V_ex carried in registers
+// instead of being written and re-read.  Same operations in the same order as the three separate sweeps:
 //   * expulsion_flux finishes before mass_transfer starts in the reference, but mass_transfer reads neither m
 //     nor psi_g, and expulsion_flux reads neither H_abs nor S_abs;
-//   * mass_transfer(k) needs S_bu(k-1), S_bu(k+1) from S4 -> the old value is carried / not yet overwritten;
-//   * S7 overwrites S_bu(k) only after mass_transfer(k) and (through the carry) mass_transfer(k+1) used the old one.
+//   * mass_transfer(k) evaluates S_br from the S4 values T, S_bu of layers k-1 and k: S_br(k) is computed once and
+//     carried; S7 overwrites S_bu(k) after mass_transfer(k) used the S4 value.
 __device__ __noinline__ void fused_thermo_expulsion(Col& c) {
   const View v = c;
   const int Na = c.N_active;
