@@ -1482,6 +1482,27 @@ static void sub_test9(sam_col* c) {
   else c->T2m = 1.0;
 }
 
+/* sub_test34, mo_testcase_specifics.f90:146-161 */
+static void sub_test34(sam_col* c) {
+  if (c->time < 2.0 * 3600.0) c->T2m = 0.0;
+  else if (c->time < (86400.0 * 5.0)) c->T2m = -15.0;
+  else if (c->time < (86400.0 * 7.0)) c->T2m = -5.0;
+  else c->T2m = 1.0;
+}
+
+/* testcase 99, mo_grotz.f90:547-563: air temperature schedule; from day 3 on the snow cover is reset every step */
+static void hook_test99(sam_col* c) {
+  if (c->time < (double)(86400.f * 3.f)) {
+    c->T2m = -40.0;
+  } else {
+    c->T2m = (c->time > (double)(86400.f * 5.f)) ? 5.0 : -5.0;
+    c->thick_snow = 0.2;
+    c->T_snow = -5.0;
+    c->m_snow = 30.0;
+    c->H_abs_snow = -c->m_snow * latent_heat;
+  }
+}
+
 /* sub_test3, mo_testcase_specifics.f90:170-185 (the day counter it computes is unused) */
 static void sub_test3(sam_col* c) {
   c->liquid_precip = 0.0;
@@ -1864,6 +1885,10 @@ static void one_step(sam_col* c) {
     sub_test2(c);
   } else if (c->testcase == 9) {
     sub_test9(c);
+  } else if (c->testcase == 34) {
+    sub_test34(c);
+  } else if (c->testcase == 99) {
+    hook_test99(c);
   } else if (c->testcase == 3) {
     sub_test3(c);
   } else if (c->testcase == 4 || c->testcase == 7) {
@@ -2077,7 +2102,7 @@ sam_col* sam_create(int testcase) {
   int k;
   int is_lab = (testcase >= 101 && testcase <= 105);
   if (!(testcase == 1 || testcase == 2 || testcase == 3 || testcase == 4 || testcase == 5 || testcase == 6 || testcase == 7 ||
-        testcase == 8 || testcase == 9 || is_lab))
+        testcase == 8 || testcase == 9 || testcase == 33 || testcase == 34 || testcase == 50 || testcase == 99 || is_lab))
     return NULL;
   c = (sam_col*)calloc(1, sizeof(sam_col));
   c->testcase = testcase;
@@ -2137,6 +2162,47 @@ sam_col* sam_create(int testcase) {
     for (k = 1; k <= c->Nlayer; k++) c->S_abs[k] = c->S_bu_bottom * c->m[k];
     for (k = 1; k <= c->Nlayer; k++) c->H_abs[k] = 0.0;
     c->bgc_flag = 1;
+  } else if (testcase == 33 || testcase == 34 || testcase == 99) { /* more cooling-chamber tanks, mo_init.f90:1779-1873, 1876-1970, 768-862 */
+    c->fl_q_bottom = (testcase == 99) ? 5.0 : 10.0;
+    c->alpha_flux_instable = 22.0; c->alpha_flux_stable = 15.0; c->tank_depth = 0.94;
+    if (testcase == 99) { c->Nlayer = 20; c->N_bottom = 5; c->N_top = 5; }
+    else { c->Nlayer = 100; c->N_bottom = 10; c->N_top = 3; }
+    c->N_active = 1;
+    c->N_middle = c->Nlayer - c->N_top - c->N_bottom;
+    sub_allocate(c, c->Nlayer);
+    c->tank_flag = 2; c->boundflux_flag = 3; c->grav_heat_flag = 1;
+    if (testcase == 99) { c->precip_flag = 0; c->flush_flag = 1; c->flood_flag = 1; c->grav_flag = 2; }
+    if (testcase == 33) {        /* fresh water */
+      c->T2m = -15.0; c->T_top = -10.0; c->T_bottom = 0.5; c->S_bu_bottom = 0.13;
+      c->thick_0 = 0.005; c->time_out = 60.0 * 5.0; c->time_total = c->time_out * 12.0 * 6.0; c->dt = 10.0;
+    } else if (testcase == 34) {
+      c->T2m = -15.0; c->T_top = -10.0; c->T_bottom = 0.5; c->S_bu_bottom = 34.9;
+      c->thick_0 = 0.005; c->time_out = 60.0 * 10.0; c->time_total = 86400.0 * 10.0; c->dt = 10.0;
+    } else {                     /* snow on ice in the chamber */
+      c->T2m = -5.0; c->T_top = -2.0; c->T_bottom = -1.8; c->S_bu_bottom = 34.0;
+      c->thick_0 = 0.05; c->time_out = 60.0 * 10.0; c->time_total = 3600.0 * 24.0 * 7.0; c->dt = 10.0;
+    }
+    c->m_total = rho_l * c->tank_depth;
+    c->S_total = rho_l * c->S_bu_bottom * c->tank_depth;
+    c->thick[1] = c->thick_0;
+    for (k = 1; k <= c->Nlayer; k++) c->m[k] = c->thick[k] * rho_l;
+    for (k = 1; k <= c->Nlayer; k++) c->S_abs[k] = c->S_bu_bottom * c->m[k];
+    for (k = 1; k <= c->Nlayer; k++) c->H_abs[k] = c->m[k] * c->T_bottom; /* sic: no c_l */
+    c->bgc_flag = 1;
+  } else if (testcase == 50) { /* mo_init.f90:1497-1532: spin-up of a stable profile (Griewank & Notz 2012) */
+    c->fl_sw = 0.0; c->boundflux_flag = 2;
+    c->fl_rest = sigma * 4106877291.8310046; /* sigma*(zeroK-20._wp)**4._wp, the power folded at compile time (correctly rounded) */
+    c->fl_q_bottom = 20.0;
+    c->Nlayer = 70; c->N_bottom = 5; c->N_top = 5;
+    c->N_middle = c->Nlayer - c->N_top - c->N_bottom;
+    c->T_top = -20.0; c->T_bottom = -1.72; c->S_bu_bottom = 34.0; c->N_active = 1;
+    sub_allocate(c, c->Nlayer);
+    c->thick_0 = 0.005;
+    c->thick[1] = c->thick_0;
+    c->m[1] = c->thick[1] * rho_l;
+    c->S_abs[1] = c->S_bu_bottom * c->m[1];
+    c->H_abs[1] = c->m[1] * (c->T_bottom) * c_l;
+    c->time = 0.0; c->time_out = 3600.0 * 24.0 * 30.0; c->dt = 10.0; c->time_total = c->time_out * 12.0 * 3.0;
   } else if (testcase == 2 || testcase == 6 || testcase == 9) { /* cooling-chamber tanks, mo_init.f90:948-1042, 1278-1357, 1684-1776 */
     if (testcase == 2) {
       c->fl_q_bottom = 10.0; c->alpha_flux_instable = 22.0; c->alpha_flux_stable = 15.0; c->tank_depth = 1.0;

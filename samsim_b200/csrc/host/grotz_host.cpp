@@ -146,6 +146,48 @@ int samsim_host_init_testcase(int32_t testcase, samsim_host_case_t* c) {
       c->arrays[SAMSIM_ARR_S_ABS][k] = S_bu_bottom * c->arrays[SAMSIM_ARR_M][k];
       c->arrays[SAMSIM_ARR_H_ABS][k] = c->arrays[SAMSIM_ARR_M][k] * T_bottom;
     }
+  } else if (testcase == 33 || testcase == 34 || testcase == 99) {
+    // three more chamber set-ups: mo_init.f90:1779-1873 (33, fresh water), :1876-1970 (34), :768-862 (99, snow on ice)
+    const double tank_depth = 0.94;
+    g->alpha_flux_instable = 22.0; g->alpha_flux_stable = 15.0;
+    g->tank_flag = 2; g->boundflux_flag = 3; g->grav_heat_flag = 1;
+    g->dt = 10.0;
+    if (testcase == 99) {
+      fl_q_bottom = 5.0;
+      g->Nlayer = 20; g->N_bottom = 5; g->N_top = 5;
+      g->precip_flag = 0; g->flush_flag = 1; g->flood_flag = 1; g->grav_flag = 2;
+      T2m = -5.0; T_top = -2.0; T_bottom = -1.8; S_bu_bottom = 34.0;
+      g->thick_0 = 0.05; time_out = 60.0 * 10.0; c->time_total = 3600.0 * 24.0 * 7.0;
+    } else {
+      fl_q_bottom = 10.0;
+      g->Nlayer = 100; g->N_bottom = 10; g->N_top = 3;
+      T2m = -15.0; T_top = -10.0; T_bottom = 0.5; S_bu_bottom = (testcase == 33) ? 0.13 : 34.9;
+      g->thick_0 = 0.005;
+      if (testcase == 33) { time_out = 60.0 * 5.0; c->time_total = time_out * 12.0 * 6.0; }
+      else { time_out = 60.0 * 10.0; c->time_total = 86400.0 * 10.0; }
+    }
+    g->N_middle = g->Nlayer - g->N_top - g->N_bottom;
+    g->m_total = rho_l * tank_depth;
+    sc[SAMSIM_SC_S_TOTAL] = rho_l * S_bu_bottom * tank_depth;
+    alloc_case(c);
+    c->arrays[SAMSIM_ARR_THICK][0] = g->thick_0;
+    for (int k = 0; k < g->Nlayer; k++) {
+      c->arrays[SAMSIM_ARR_M][k] = c->arrays[SAMSIM_ARR_THICK][k] * rho_l;
+      c->arrays[SAMSIM_ARR_S_ABS][k] = S_bu_bottom * c->arrays[SAMSIM_ARR_M][k];
+      c->arrays[SAMSIM_ARR_H_ABS][k] = c->arrays[SAMSIM_ARR_M][k] * T_bottom;  // sic: no c_l
+    }
+  } else if (testcase == 50) {  // mo_init.f90:1497-1532: stable initial conditions for the convection studies
+    g->Nlayer = 70; g->N_bottom = 5; g->N_top = 5; g->N_middle = g->Nlayer - g->N_top - g->N_bottom;
+    g->boundflux_flag = 2;
+    sc[SAMSIM_SC_FL_SW] = 0.0;
+    sc[SAMSIM_SC_FL_REST] = sigma_sb * 4106877291.8310046;  // sigma*(zeroK-20._wp)**4._wp: a constant expression, folded with a correctly rounded power
+    fl_q_bottom = 20.0; T_top = -20.0; T_bottom = -1.72; S_bu_bottom = 34.0;
+    g->thick_0 = 0.005; time_out = 3600.0 * 24.0 * 30.0; g->dt = 10.0; c->time_total = time_out * 12.0 * 3.0;
+    alloc_case(c);
+    c->arrays[SAMSIM_ARR_THICK][0] = g->thick_0;
+    c->arrays[SAMSIM_ARR_M][0] = c->arrays[SAMSIM_ARR_THICK][0] * rho_l;
+    c->arrays[SAMSIM_ARR_S_ABS][0] = S_bu_bottom * c->arrays[SAMSIM_ARR_M][0];
+    c->arrays[SAMSIM_ARR_H_ABS][0] = c->arrays[SAMSIM_ARR_M][0] * (T_bottom)*c_l;
   } else if (testcase == 3) {  // mo_init.f90:1045-1124
     g->Nlayer = 20; g->N_bottom = 5; g->N_top = 5; g->N_middle = g->Nlayer - g->N_top - g->N_bottom;
     g->atmoflux_flag = 1; g->precip_flag = 0; g->boundflux_flag = 2;

@@ -488,6 +488,21 @@ __device__ __forceinline__ void testcase_hooks(Col& c, const Forcing& f) {
     if (c.time < (19.75 * 3600.0)) SCV(c, SC_T2M) = 0.0;
     else if (c.time < (86400.0 * 3.0 + 2.25 * 3600.0)) SCV(c, SC_T2M) = -15.0;
     else SCV(c, SC_T2M) = 1.0;
+  } else if (CFG.testcase == 34) {  // sub_test34, :146-161
+    if (c.time < 2.0 * 3600.0) SCV(c, SC_T2M) = 0.0;
+    else if (c.time < (86400.0 * 5.0)) SCV(c, SC_T2M) = -15.0;
+    else if (c.time < (86400.0 * 7.0)) SCV(c, SC_T2M) = -5.0;
+    else SCV(c, SC_T2M) = 1.0;
+  } else if (CFG.testcase == 99) {  // mo_grotz.f90:547-563: from day 3 on the snow cover is reset every step
+    if (c.time < 86400.0 * 3.0) {
+      SCV(c, SC_T2M) = -40.0;
+    } else {
+      SCV(c, SC_T2M) = (c.time > 86400.0 * 5.0) ? 5.0 : -5.0;
+      SCV(c, SC_THICK_SNOW) = 0.2;
+      SCV(c, SC_T_SNOW) = -5.0;
+      SCV(c, SC_M_SNOW) = 30.0;
+      SCV(c, SC_H_ABS_SNOW) = -SCV(c, SC_M_SNOW) * latent_heat;
+    }
   } else if (CFG.testcase == 3) {  // sub_test3, :170-185
     SCV(c, SC_LIQUID_PRECIP) = 0.0;
     SCV(c, SC_SOLID_PRECIP) = 0.15 / 86400.0 / 356.0;
