@@ -49,7 +49,7 @@ def _advance(col, k, chunks):
     (9, (1, 2, 12000)),
     (33, (1, 2, 9000)),                               # fresh-water chamber (S_bu 0.13: the salt-free branch of getT)
     (34, (1, 2, 50000)),                              # chamber with the T2m schedule of sub_test34 (0 -> -15 degC after 2 h)
-    (50, (1, 2, 40000)),                              # notzflux spin-up column of the convection studies
+    (50, (1, 2, 600000, 80000)),                      # spin-up column of the convection studies: 70 days of open water under the climatological fluxes, then freeze-up
     (99, (1, 2, 27000, 20000)),                       # snow on ice in the chamber: the hook resets the snow cover from day 3 on
 ])
 def test_device_code_on_host_equals_oracle_from_init(oracle_mod, testcase, chunks, two_pass):

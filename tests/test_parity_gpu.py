@@ -558,7 +558,7 @@ OTHER_TESTCASES = {
     9: (30000, "cooling chamber with the T2m schedule of sub_test9 (growth, then melt)"),
     33: (9000, "fresh-water chamber (S_bu_bottom 0.13)"),
     34: (60000, "chamber with the T2m schedule of sub_test34"),
-    50: (40000, "spin-up column of the convection studies (boundflux 2, climatological fluxes)"),
+    50: (680000, "spin-up column of the convection studies (boundflux 2, climatological fluxes): 70 days of open water, then freeze-up to ~35 layers"),
     99: (50000, "snow on ice in the chamber: T2m -40 for three days, then the hook resets the snow cover every step (mo_grotz.f90:547-563)"),
 }
 
