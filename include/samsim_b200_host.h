@@ -25,10 +25,10 @@ typedef struct {
 
 /* mo_init.f90: defaults :83-132, testcase 1 :865-945, 2 :948-1042, 3 :1045-1124, 4 :1127-1207, 5 :1210-1275,
  * 6 :1278-1357, 7 :1360-1448, 9 :1684-1776, 33 :1779-1873, 34 :1876-1970, 50 :1497-1532, 99 :768-862, 101-105 :222-767,
- * tail :1982-2009.
+ * 111 :141-221 (its series <lab_input_dir>/Ts_<int(dt)>s.txt is read by samsim_grotz, mo_grotz.f90:171-176), tail :1982-2009.
  * 8 :1451-1494 (its field temperature series input/DNotz_fieldT/Tinput.txt is read by samsim_grotz).
  * Returns SAMSIM_ERR_CONFIG for other testcases (the reference STOPs with 4321 for unknown ones; 51 is a table of 280
- * restart values and 111 reads a series the reference does not ship: not covered). */
+ * restart values: not covered). */
 int samsim_host_init_testcase(int32_t testcase, samsim_host_case_t* out);
 void samsim_host_case_free(samsim_host_case_t* c);
 

@@ -1895,6 +1895,10 @@ static void one_step(sam_col* c) {
     sub_test4(c);
   } else if (c->testcase == 6) {
     sub_test6(c);
+  } else if (c->testcase == 111) { /* :505-506 */
+    const long idx = (long)floor(1 + c->time / c->dt);
+    if (idx < 1 || idx > c->length_input_lab || !c->Tinput) SAM_STOP(c, 8001); /* the reference would read Ttop_input out of bounds */
+    c->T_top = c->Tinput[idx];
   } else if (c->testcase == 8) { /* :539-544 */
     if (c->time < (double)(3600.f * 12.f * 11.f)) {
       const long idx = (long)floor(1 + c->time / 60);
@@ -2102,7 +2106,8 @@ sam_col* sam_create(int testcase) {
   int k;
   int is_lab = (testcase >= 101 && testcase <= 105);
   if (!(testcase == 1 || testcase == 2 || testcase == 3 || testcase == 4 || testcase == 5 || testcase == 6 || testcase == 7 ||
-        testcase == 8 || testcase == 9 || testcase == 33 || testcase == 34 || testcase == 50 || testcase == 99 || is_lab))
+        testcase == 8 || testcase == 9 || testcase == 33 || testcase == 34 || testcase == 50 || testcase == 99 || testcase == 111 ||
+        is_lab))
     return NULL;
   c = (sam_col*)calloc(1, sizeof(sam_col));
   c->testcase = testcase;
@@ -2149,6 +2154,21 @@ sam_col* sam_create(int testcase) {
     c->S_abs[1] = c->S_bu_bottom * c->m[1];
     c->H_abs[1] = c->m[1] * (c->T_bottom) * c_l;
     c->time = 0.0; c->time_out = 3600.0; c->time_total = c->time_out * 12.0 * 12.0; c->dt = 1.0;
+  } else if (testcase == 111) { /* mo_init.f90:141-221: salinity-harp comparison; the uppermost harp sensor prescribes T_top, one
+                                 * value per time step (2017_input/Ts_<dt>s.txt, mo_grotz.f90:171-176, not shipped): the caller
+                                 * supplies the series through sam_set_lab_forcing (kind Tice) */
+    c->Nlayer = 100; c->N_active = 1; c->N_top = 10; c->N_bottom = 10;
+    c->N_middle = c->Nlayer - c->N_top - c->N_bottom;
+    c->length_input_lab = 860333;
+    sub_allocate(c, c->Nlayer);
+    c->turb_flag = 1; c->boundflux_flag = 1; c->grav_heat_flag = 1; c->flush_flag = 1; c->salt_flag = 2;
+    c->T_top = -2.0; c->T_bottom = -1.67; c->S_bu_bottom = 33.4079; c->fl_q_bottom = 0.;
+    c->thick_0 = 0.01; c->dt = 3.0; c->time = 0.0; c->time_out = 3600.0 * 2.0; c->time_total = 2580996.0;
+    c->thick[1] = c->thick_0;
+    c->m[1] = c->thick[1] * rho_l;
+    c->S_abs[1] = c->S_bu_bottom * c->m[1];
+    c->H_abs[1] = c->m[1] * (c->T_bottom) * c_l;
+    c->bgc_flag = 1;
   } else if (testcase == 4) { /* mo_init.f90:1127-1207 */
     c->Nlayer = 100; c->N_bottom = 20; c->N_top = 20; c->N_active = 1;
     c->N_middle = c->Nlayer - c->N_top - c->N_bottom;

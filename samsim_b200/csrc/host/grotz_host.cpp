@@ -103,6 +103,17 @@ int samsim_host_init_testcase(int32_t testcase, samsim_host_case_t* c) {
     c->arrays[SAMSIM_ARR_M][0] = c->arrays[SAMSIM_ARR_THICK][0] * rho_l;
     c->arrays[SAMSIM_ARR_S_ABS][0] = S_bu_bottom * c->arrays[SAMSIM_ARR_M][0];
     c->arrays[SAMSIM_ARR_H_ABS][0] = c->arrays[SAMSIM_ARR_M][0] * (T_bottom)*c_l;
+  } else if (testcase == 111) {  // mo_init.f90:141-221 (the harp temperature series Ts_<dt>s.txt is read by samsim_grotz)
+    g->Nlayer = 100; g->N_top = 10; g->N_bottom = 10; g->N_middle = g->Nlayer - g->N_top - g->N_bottom;
+    c->length_input_lab = 860333;
+    g->turb_flag = 1; g->boundflux_flag = 1; g->grav_heat_flag = 1; g->flush_flag = 1; g->salt_flag = 2;
+    T_top = -2.0; T_bottom = -1.67; S_bu_bottom = 33.4079; fl_q_bottom = 0.;
+    g->thick_0 = 0.01; g->dt = 3.0; time_out = 3600.0 * 2.0; c->time_total = 2580996.0;
+    alloc_case(c);
+    c->arrays[SAMSIM_ARR_THICK][0] = g->thick_0;
+    c->arrays[SAMSIM_ARR_M][0] = c->arrays[SAMSIM_ARR_THICK][0] * rho_l;
+    c->arrays[SAMSIM_ARR_S_ABS][0] = S_bu_bottom * c->arrays[SAMSIM_ARR_M][0];
+    c->arrays[SAMSIM_ARR_H_ABS][0] = c->arrays[SAMSIM_ARR_M][0] * (T_bottom)*c_l;
   } else if (testcase == 4) {  // mo_init.f90:1127-1207
     g->Nlayer = 100; g->N_bottom = 20; g->N_top = 20; g->N_middle = g->Nlayer - g->N_top - g->N_bottom;
     g->atmoflux_flag = 2; g->precip_flag = 1; g->boundflux_flag = 2; g->snow_flush_flag = 1; g->flush_heat_flag = 2;
@@ -404,9 +415,13 @@ int samsim_grotz(int32_t testcase, const char* description, const samsim_grotz_o
     rc = samsim_host_read_forcing(opt->forcing_dir, nrec, series.data());
     if (!rc) rc = samsim_b200_set_forcing(h, 1, nrec, series.data(), nullptr, opt->forcing_scale, opt->forcing_offset);
   }
-  if (!rc && testcase == 8) {  // mo_grotz.f90:138-143 reads Tinput; the field series is Tinput.txt, one value per minute
+  if (!rc && (testcase == 8 || testcase == 111)) {
+    // 8: mo_grotz.f90:138-143 reads Tinput; the field series is Tinput.txt, one value per minute.
+    // 111: mo_grotz.f90:171-176 reads Ts_<int(dt)>s.txt, one value per time step.
     std::vector<double> T;
-    const std::string path = std::string(opt->lab_input_dir ? opt->lab_input_dir : "2017_input") + "/Tinput.txt";
+    char ts_name[64];
+    snprintf(ts_name, sizeof ts_name, "/Ts_%ds.txt", (int)g.dt);
+    const std::string path = std::string(opt->lab_input_dir ? opt->lab_input_dir : "2017_input") + (testcase == 8 ? "/Tinput.txt" : ts_name);
     FILE* f = fopen(path.c_str(), "r");
     if (!f) rc = SAMSIM_ERR_STATE;
     else {

@@ -856,7 +856,8 @@ int samsim_b200_step(samsim_handle_t h, int64_t nsteps) {
   if (nsteps == 0) return 0;
   const bool need_forcing = (h->cfg.atmoflux_flag == 2);
   const bool tc8 = (h->cfg.testcase == 8);  // T_top = Tinput(FLOOR(1 + time/60)) while time < 475200 s (mo_grotz.f90:539-544)
-  const bool need_lab = tc8 || (h->cfg.testcase >= 101 && h->cfg.testcase <= 105) || (h->cfg.boundflux_flag == 3 && h->cfg.lab_snow_flag == 1);
+  const bool need_lab = tc8 || h->cfg.testcase == 111 || (h->cfg.testcase >= 101 && h->cfg.testcase <= 105) ||
+                        (h->cfg.boundflux_flag == 3 && h->cfg.lab_snow_flag == 1);  // 111: T_top = Ttop_input(FLOOR(1 + time/dt))
   if (need_forcing && !h->series) return fail(SAMSIM_ERR_STATE, "step: atmoflux_flag 2 needs samsim_b200_set_forcing first");
   if (need_lab && !h->lab) return fail(SAMSIM_ERR_STATE, "step: lab testcases need samsim_b200_set_lab_forcing first");
   CU(cudaSetDevice(h->device));

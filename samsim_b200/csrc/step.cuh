@@ -516,6 +516,8 @@ __device__ __forceinline__ void testcase_hooks(Col& c, const Forcing& f) {
     else if (t > 1349.0 * 60.0) SCV(c, SC_T2M) = -5.0;
     else if (t > 1160.0 * 60.0) SCV(c, SC_T2M) = -18.0;
     else if (t > 1100.0 * 60.0) SCV(c, SC_T2M) = -5.0;
+  } else if (CFG.testcase == 111) {  // mo_grotz.f90:505-506: harp temperatures, one record per time step
+    SCV(c, SC_T_TOP) = lab_rec(f, 0, (long long)floor(1 + c.time / dt));
   } else if (CFG.testcase == 8) {  // mo_grotz.f90:539-544: field temperatures, one record per minute, until day 5.5
     if (c.time < (double)(3600.f * 12.f * 11.f)) SCV(c, SC_T_TOP) = lab_rec(f, 0, (long long)floor(1 + c.time / 60));
     else SCV(c, SC_T_TOP) = -15.0;

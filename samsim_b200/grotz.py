@@ -46,7 +46,7 @@ def init_testcase(testcase: int) -> dict:
     hc = _HostCase()
     rc = L.samsim_host_init_testcase(testcase, C.byref(hc))
     if rc != 0:
-        raise api.SamsimError(rc, f"testcase {testcase} is not covered (1-9, 33, 34, 50, 99, 101-105)")
+        raise api.SamsimError(rc, f"testcase {testcase} is not covered (1-9, 33, 34, 50, 99, 101-105, 111)")
     try:
         N = hc.cfg.Nlayer
         st = {n: getattr(hc.cfg, n) for n in api._CFG_INT_FIELDS + api._CFG_DBL_FIELDS}

@@ -15,7 +15,7 @@ def _built():
     build.build()
 
 
-@pytest.mark.parametrize("testcase", [1, 2, 3, 4, 5, 6, 7, 8, 9, 33, 34, 50, 99, 101, 102, 103, 104, 105])
+@pytest.mark.parametrize("testcase", [1, 2, 3, 4, 5, 6, 7, 8, 9, 33, 34, 50, 99, 101, 102, 103, 104, 105, 111])
 def test_init_testcase_equals_reference_init(oracle_mod, testcase):
     """samsim_host_init_testcase against the oracle's restatement of mo_init.f90 (flags, grid, initial column)."""
     st = grotz.init_testcase(testcase)
@@ -34,7 +34,7 @@ def test_init_testcase_equals_reference_init(oracle_mod, testcase):
 
 
 def test_unknown_testcase_is_an_error():
-    for tc in (51, 0, 44, 111):  # 51 / 111 need data the reference does not ship in usable form; 44 has no init block
+    for tc in (51, 0, 44):  # 51 is a table of 280 restart values; 44 has no init block
         with pytest.raises(api.SamsimError):
             grotz.init_testcase(tc)
 

@@ -121,6 +121,26 @@ def test_device_code_on_host_testcase8_field_temperatures(oracle_mod, golden_dir
     assert ("two_pass_step" in k.events()) == two_pass
 
 
+def harp_series(n: int) -> np.ndarray:
+    """Synthetic uppermost-harp temperatures for testcase 111 (the reference's 2017_input/Ts_3s.txt is not shipped):
+    a cold spell with a diurnal cycle, one value per 3 s step."""
+    t = 3.0 * np.arange(n, dtype=np.float64)
+    return -12.0 - 8.0 * np.sin(2.0 * np.pi * t / 86400.0) - 4.0 * np.minimum(t / 86400.0, 2.0)
+
+
+@pytest.mark.parametrize("two_pass", [False, True])
+def test_device_code_on_host_testcase111_harp_temperatures(oracle_mod, two_pass):
+    """Testcase 111 (mo_init.f90:141-221, mo_grotz.f90:171-176, :505-506): T_top = Ttop_input(FLOOR(1 + time/dt))."""
+    lab = np.zeros((4, 30000))
+    lab[0] = harp_series(30000)
+    col = oracle_mod.Column(111, "det")
+    col.set_lab_forcing(*lab)
+    k = _from_oracle(col, two_pass)
+    k.set_lab_forcing(lab)
+    _advance(col, k, (1, 2, 2397, 20000))
+    assert col.int("N_active") > 5 and col.scalar("T_top") == lab[0][int(col.int("i")) - 1]
+
+
 def test_device_code_on_host_with_impermeable_layers(oracle_mod, golden_dir):
     """fl_grav_drain's `minval(perm(k:N_active-1)) < 1e-14 -> harmonic_perm = 0` branch (mo_grav_drain.f90:112-113):
     a band of nearly fresh layers in the mid-winter column makes the layers above it non-draining while the layers

@@ -393,7 +393,7 @@ def test_grotz_sheba_first_records(tmp_path, golden_dir):
 def test_grotz_lab_and_field_testcases_read_their_series(oracle_mod, tmp_path, golden_dir):
     """samsim_grotz for the testcases that READ series in the reference's prologue (mo_grotz.f90:138-169): lab
     testcase 101 (2017_input/{Tice,snowfall,heat,styropor}_exp_1.txt; synthetic files, the real ones are not shipped)
-    and testcase 8 (the field temperatures input/DNotz_fieldT/Tinput.txt).  The written dat_thick / dat_T records
+    testcase 8 (the field temperatures input/DNotz_fieldT/Tinput.txt) and testcase 111 (harp temperatures Ts_3s.txt, synthetic).  The written dat_thick / dat_T records
     equal the oracle's records at print precision, N_active exactly."""
     from samsim_b200 import grotz
     nsteps = 3 * 3601 + 1
@@ -436,6 +436,26 @@ def test_grotz_lab_and_field_testcases_read_their_series(oracle_mod, tmp_path, g
         assert np.abs(thick8[j] - rec["thick"]).max() <= 0.5e-5 and (thick8[j] != 0).sum() == rec["N_active"]
         assert tt8[j, 1] == rec["T_top"]
     assert col8.int("N_active") > 2
+    # ---- testcase 111: Ts_<int(dt)>s.txt, one value per time step (mo_grotz.f90:171-176) ----
+    n111 = 8000
+    t = 3.0 * np.arange(n111, dtype=np.float64)
+    np.savetxt(fdir / "Ts_3s.txt", -12.0 - 8.0 * np.sin(2.0 * np.pi * t / 86400.0), fmt="%.6f")
+    out111 = tmp_path / "out111"
+    steps111 = 2 * 2401 + 1   # time_out 7200 s / dt 3 s: an output record every 2401 steps
+    assert grotz.grotz(111, "harp", output_dir=out111, lab_input_dir=fdir, max_steps=steps111) == 0
+    lab = np.zeros((4, n111))
+    lab[0] = np.loadtxt(fdir / "Ts_3s.txt")
+    col111 = oracle_mod.Column(111, "det")
+    col111.set_lab_forcing(*lab)
+    col111.record_outputs()
+    assert col111.step(steps111) == 0
+    thick111 = _read_dat(out111 / "dat_thick.dat")
+    tt111 = _read_dat(out111 / "dat_T2m_T_top.dat")
+    assert thick111.shape[0] == len(col111.records) == 3
+    for j, rec in enumerate(col111.records):
+        assert np.abs(thick111[j] - rec["thick"]).max() <= 0.5e-5 and (thick111[j] != 0).sum() == rec["N_active"]
+        assert tt111[j, 1] == rec["T_top"]
+    assert col111.int("N_active") > 2
 
 
 def test_rebin_is_invisible_to_results(oracle_mod, golden_dir):
@@ -560,6 +580,7 @@ OTHER_TESTCASES = {
     34: (60000, "chamber with the T2m schedule of sub_test34"),
     50: (680000, "spin-up column of the convection studies (boundflux 2, climatological fluxes): 70 days of open water, then freeze-up to ~35 layers"),
     99: (50000, "snow on ice in the chamber: T2m -40 for three days, then the hook resets the snow cover every step (mo_grotz.f90:547-563)"),
+    111: (25000, "salinity-harp comparison: T_top = Ttop_input(FLOOR(1 + time/dt)) (mo_grotz.f90:505-506), synthetic series"),
 }
 
 
@@ -572,6 +593,11 @@ def test_other_testcases_from_init(oracle_mod, golden_dir, testcase):
         Tin = np.load(golden_dir / "tinput_dnotz.npz")["Tinput"]
         lab = np.zeros((4, len(Tin)))
         lab[0] = Tin
+        col.set_lab_forcing(*lab)
+    if testcase == 111:  # the reference's 2017_input/Ts_3s.txt is not shipped: a cold spell with a diurnal cycle
+        t = 3.0 * np.arange(30000, dtype=np.float64)
+        lab = np.zeros((4, 30000))
+        lab[0] = -12.0 - 8.0 * np.sin(2.0 * np.pi * t / 86400.0) - 4.0 * np.minimum(t / 86400.0, 2.0)
         col.set_lab_forcing(*lab)
     eng = pu.engine_from_oracle(col, ncol=2)
     if lab is not None:
