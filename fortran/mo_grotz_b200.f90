@@ -70,6 +70,11 @@ CONTAINS
        OPEN(1234,file='2017_input/styropor_exp_'//num//'.txt',status='old'); READ(1234,*) styropor_input;   CLOSE(1234)
     END IF
 
+    IF (testcase == 111) THEN                     ! mo_grotz.f90:171-176
+       WRITE(num,fmt) INT(dt)
+       OPEN(1234,file='2017_input/Ts_'//num//'s.txt',status='old'); READ(1234,*) Ttop_input; CLOSE(1234)
+    END IF
+
     !---- device set-up -----------------------------------------------------------------------------------------
     i = 1                                   ! mo_data loop index: the next step to execute
     cfg = b200_config_from_mo_data(testcase)
@@ -92,6 +97,13 @@ CONTAINS
        series(length_input_lab+1:2*length_input_lab)   = precipinput
        series(2*length_input_lab+1:3*length_input_lab) = ocean_flux_input
        series(3*length_input_lab+1:4*length_input_lab) = styropor_input
+       CALL b200_check(samsim_b200_set_lab_forcing(h, 1_C_INT32_T, INT(length_input_lab, C_INT64_T), series, C_NULL_PTR), 'lab')
+       DEALLOCATE(series)
+    END IF
+    IF (testcase == 111) THEN                         ! T_top = Ttop_input(FLOOR(1+time/dt)): the series travels as kind Tice
+       ALLOCATE(series(4*length_input_lab))
+       series = 0.0_C_DOUBLE
+       series(1:length_input_lab) = Ttop_input
        CALL b200_check(samsim_b200_set_lab_forcing(h, 1_C_INT32_T, INT(length_input_lab, C_INT64_T), series, C_NULL_PTR), 'lab')
        DEALLOCATE(series)
     END IF
