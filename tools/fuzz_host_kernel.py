@@ -20,12 +20,20 @@ nbad = 0
 
 
 def other_testcase(t):
-    """testcases 1, 2, 3, 5, 6, 9 from init with random boundary values (and testcase 1's tracers)"""
-    tc = int(rng.choice([1, 1, 2, 3, 5, 6, 9, 101, 103, 105]))
+    """testcases 1, 2, 3, 5, 6, 9, 33, 34, 50, 99, 111 and lab cases from init with random boundary values (and testcase 1's tracers)"""
+    tc = int(rng.choice([1, 1, 2, 3, 5, 6, 9, 33, 34, 50, 99, 111, 101, 103, 105]))
     col = oracle.Column(tc, "det")
     edits = []
     lab = None
-    if tc > 100:   # synthetic per-second lab inputs (the reference's 2017_input files are not shipped)
+    if tc == 111:  # synthetic harp temperatures, one per 3 s step
+        n = 30000
+        tt = 3.0 * np.arange(n, dtype=np.float64)
+        amp, mean = float(rng.uniform(1, 10)), float(rng.uniform(-20, -3))
+        lab = np.zeros((4, n))
+        lab[0] = mean - amp * np.sin(2.0 * np.pi * tt / 86400.0)
+        col.set_lab_forcing(*lab)
+        edits = [f"harp mean {mean:.1f} amp {amp:.1f}"]
+    elif tc > 100:   # synthetic per-second lab inputs (the reference's 2017_input files are not shipped)
         n = 40000
         tt = np.arange(n, dtype=np.float64)
         amp, mean = float(rng.uniform(2, 14)), float(rng.uniform(-12, -2))
@@ -42,14 +50,14 @@ def other_testcase(t):
         col.set_scalar("fl_q_bottom", float(rng.uniform(0, 12)))
         if rng.random() < 0.3: col.set_int("prescribe_flag", 2)
         edits = [f"ttop {w:.2f}/{c_:.2f}"]
-    elif tc in (2, 6, 9):
+    elif tc in (2, 6, 9, 33, 34, 99):
         col.set_scalar("fl_q_bottom", float(rng.uniform(0, 40)))
         col.set_scalar("alpha_flux_instable", float(rng.uniform(10, 40)))
     k = hk.HostKernel(pu.config_from_oracle(col))
     k.load_state(col.state())
     if lab is not None:
         k.set_lab_forcing(lab)
-    total = int(rng.integers(500, {1: 60000, 2: 30000, 3: 250000, 5: 20000, 6: 150000, 9: 30000}.get(tc, 38000)))
+    total = int(rng.integers(500, {1: 60000, 2: 30000, 3: 250000, 5: 20000, 6: 150000, 9: 30000, 33: 9000, 34: 80000, 50: 750000, 99: 60000, 111: 29000}.get(tc, 38000)))
     done, ok = 0, True
     while done < total and ok:
         n = int(min(total - done, rng.choice([1, 2, 5, 100, 3601, 20000])))
